@@ -1,0 +1,273 @@
+#!/usr/bin/env python
+"""Mint golden vectors from the UNMODIFIED reference, run in the build container.
+
+    python tests/golden/make_golden.py            # writes tests/golden/*.npz
+
+The reference (``/root/reference/NerualNetwork/bert4rec&sas4rec``) has no tests or fixtures of its
+own, so these vectors -- outputs of the reference's own ``BERTModel`` /
+``SASModel`` / ``recalls_ndcgs_and_mrr_for_ks`` / ``optim.Adam`` on seeded inputs -- are what pins the
+CPU oracle (tests/test_oracle_golden.py) and, through it, the CUDA path.  Nothing here is read at
+test time except the .npz files; ``/root/reference`` does not exist on the GPU box.
+"""
+import argparse
+import os
+import sys
+from types import SimpleNamespace
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+REF = "/root/reference/NerualNetwork/bert4rec&sas4rec"
+
+
+def ref_imports():
+    sys.argv = sys.argv[:1]
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, REF)
+    import models  # noqa
+    from models import model_factory
+    from trainers.utils import recalls_ndcgs_and_mrr_for_ks
+    return model_factory, recalls_ndcgs_and_mrr_for_ks
+
+
+def bert_args(V, L, d, nb, h, p=0.0, seed=0):
+    return SimpleNamespace(model_code="bert", num_items=V, max_len=L, device="cpu", model_init_seed=seed,
+                           bert_num_blocks=nb, bert_num_heads=h, bert_hidden_units=d, bert_dropout=p,
+                           bert_hidden_dropout=p)
+
+
+def sas_args(V, L, d, nb, h, p=0.0):
+    return SimpleNamespace(model_code="sas", num_items=V, max_len=L, device="cpu", sas_hidden_units=d,
+                           sas_num_blocks=nb, sas_heads=h, sas_dropout=p)
+
+
+def make_bert_batch(rng, B, L, V, mask_prob=0.3):
+    """Wire format of BertTrainDataset.__getitem__ (NN/dataloaders/bert.py:77-110)."""
+    toks = np.zeros((B, L), np.int64)
+    labs = np.zeros((B, L), np.int64)
+    for b in range(B):
+        n = rng.randint(max(2, L // 3), L + 1) if b else L  # first row unpadded
+        seq = rng.randint(1, V + 1, size=n)
+        t, l = [], []
+        for s in seq:
+            pr = rng.rand()
+            if pr < mask_prob:
+                pr /= mask_prob
+                t.append(V + 1 if pr < 0.8 else (rng.randint(1, V + 1) if pr < 0.9 else s))
+                l.append(s)
+            else:
+                t.append(s)
+                l.append(0)
+        toks[b, L - n:] = t
+        labs[b, L - n:] = l
+    if labs.sum() == 0:
+        labs[0, -1] = toks[0, -1]
+    return toks, labs
+
+
+def make_sas_batch(rng, B, L, V):
+    """Wire format of sample_function (NN/dataloaders/sas.py:70-86), negatives may be item 0."""
+    seq = np.zeros((B, L), np.int64)
+    pos = np.zeros((B, L), np.int64)
+    neg = np.zeros((B, L), np.int64)
+    for b in range(B):
+        n = rng.randint(3, L + 2) if b else L + 1
+        train = rng.randint(1, V + 1, size=n)
+        pad = L - n + 1
+        seq[b, pad:] = train[:-1]
+        pos[b, pad:] = train[1:]
+        allowed = np.array(sorted(set(range(0, V + 1)) - set(train.tolist())))
+        neg[b, pad:] = allowed[rng.randint(0, len(allowed), size=n - 1)]
+    return seq, pos, neg
+
+
+def sd_numpy(model, prefix="sd."):
+    return {prefix + k: v.detach().numpy().copy() for k, v in model.state_dict().items()}
+
+
+def grads_numpy(model, prefix="grad."):
+    return {prefix + k: p.grad.detach().numpy().copy() for k, p in model.named_parameters()}
+
+
+def gen_bert(model_factory, name, V, L, d, nb, h, B, seed, store_sd=True, adam_steps=5):
+    rng = np.random.RandomState(seed)
+    args = bert_args(V, L, d, nb, h, seed=seed)
+    model = model_factory(args)
+    if not store_sd:  # cfg-shaped case: weights regenerated from the seed at test time, not stored
+        from oracle import bert4rec as ob
+        model.load_state_dict(ob.random_state_dict(V, L, d, nb, seed=seed))
+    model.train()
+    toks, labs = make_bert_batch(rng, B, L, V)
+    t, l = torch.from_numpy(toks), torch.from_numpy(labs)
+    out = {"tokens": toks, "labels": labs, "cfg": np.array([V, L, d, nb, h, B, seed], np.int64)}
+    if store_sd:
+        out.update(sd_numpy(model))
+    logits = model(t)
+    ce = torch.nn.CrossEntropyLoss(ignore_index=0)
+    loss = ce(logits.view(-1, logits.size(-1)), l.view(-1))
+    model.zero_grad()
+    loss.backward()
+    out["loss"] = np.float32(loss.item())
+    if store_sd:
+        out["logits"] = logits.detach().numpy()
+        out.update(grads_numpy(model))
+    else:
+        out["logits_last"] = logits[:, -1, :].detach().numpy()
+        out["grad_norms"] = np.array([p.grad.norm().item() for _, p in model.named_parameters()], np.float32)
+    # eval-style candidate scores (NN/trainers/bert.py:43-49): seq ends in [MASK]
+    ev = toks.copy()
+    ev[:, :-1] = toks[:, 1:]
+    ev[:, -1] = V + 1
+    cands = np.stack([rng.permutation(np.arange(1, V + 1))[:min(V, 21)] for _ in range(B)]).astype(np.int64)
+    model.eval()
+    with torch.no_grad():
+        sc = model(torch.from_numpy(ev))[:, -1, :]
+        out["eval_tokens"], out["candidates"] = ev, cands
+        out["cand_scores"] = sc.gather(1, torch.from_numpy(cands)).numpy()
+        out["scores_last"] = sc.numpy()
+    # a few Adam steps on the same batch (NN/trainers/base.py:110-123, :228)
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)
+    losses = []
+    for _ in range(adam_steps):
+        opt.zero_grad()
+        lg = model(t)
+        ls = ce(lg.view(-1, lg.size(-1)), l.view(-1))
+        losses.append(ls.item())
+        ls.backward()
+        opt.step()
+    out["adam_losses"] = np.array(losses, np.float32)
+    if store_sd:
+        out.update(sd_numpy(model, "sd_after."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "adam", losses)
+
+
+def gen_sas(model_factory, name, V, L, d, nb, h, B, seed, store_sd=True, adam_steps=5):
+    rng = np.random.RandomState(seed)
+    torch.manual_seed(seed)  # SAS never seeds itself
+    model = model_factory(sas_args(V, L, d, nb, h))
+    if not store_sd:
+        from oracle import sasrec as osr
+        model.load_state_dict(osr.random_state_dict(V, L, d, nb, seed=seed))
+    model.train()
+    seq, pos, neg = make_sas_batch(rng, B, L, V)
+    out = {"seq": seq, "pos": pos, "neg": neg, "cfg": np.array([V, L, d, nb, h, B, seed], np.int64)}
+    if store_sd:
+        out.update(sd_numpy(model))
+    bce = torch.nn.BCEWithLogitsLoss()
+
+    def step_loss():
+        pl, nl = model(seq, pos, neg)
+        idx = np.where(pos != 0)
+        return pl, nl, bce(pl[idx], torch.ones_like(pl)[idx]) + bce(nl[idx], torch.zeros_like(nl)[idx])
+
+    pl, nl, loss = step_loss()
+    model.zero_grad()
+    loss.backward()
+    out["pos_logits"], out["neg_logits"] = pl.detach().numpy(), nl.detach().numpy()
+    out["loss"] = np.float32(loss.item())
+    if store_sd:
+        out.update(grads_numpy(model))
+    else:
+        out["grad_norms"] = np.array([p.grad.norm().item() for _, p in model.named_parameters()], np.float32)
+    cands = np.stack([rng.permutation(np.arange(1, V + 1))[:min(V, 21)] for _ in range(B)]).astype(np.int64)
+    model.eval()
+    with torch.no_grad():
+        out["candidates"] = cands
+        out["cand_scores"] = model.predict(seq, cands).numpy()
+        allc = np.tile(np.arange(1, V + 1, dtype=np.int64), (B, 1))
+        out["scores_full"] = model.predict(seq, allc).numpy()
+    model.train()
+    opt = torch.optim.Adam(model.parameters(), lr=1e-3, weight_decay=0)
+    losses = []
+    for _ in range(adam_steps):
+        opt.zero_grad()
+        _, _, ls = step_loss()
+        losses.append(ls.item())
+        ls.backward()
+        opt.step()
+    out["adam_losses"] = np.array(losses, np.float32)
+    if store_sd:
+        out.update(sd_numpy(model, "sd_after."))
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "loss", out["loss"], "adam", losses)
+
+
+def gen_metrics(fn, name="metrics"):
+    rng = np.random.RandomState(7)
+    out = {}
+    for tag, (B, C) in {"c101": (64, 101), "c3416": (16, 3416)}.items():
+        scores = rng.randn(B, C).astype(np.float32)
+        labels = np.zeros((B, C), np.int64)
+        labels[:, 0] = 1
+        # make a decent share of positives land in the top-20
+        boost = rng.rand(B) < 0.6
+        scores[boost, 0] += 2.5
+        ks = [1, 5, 10, 20]
+        m = fn(torch.from_numpy(scores), torch.from_numpy(labels), ks)
+        out[tag + ".scores"], out[tag + ".labels"] = scores, labels
+        out[tag + ".keys"] = np.array(sorted(m.keys()))
+        out[tag + ".vals"] = np.array([m[k] for k in sorted(m.keys())], np.float64)
+        rank = (-torch.from_numpy(scores)).argsort(dim=1)[:, :20].numpy()
+        out[tag + ".rank20"] = rank
+    # multi-positive case (labels with 1..3 positives)
+    B, C = 32, 50
+    scores = rng.randn(B, C).astype(np.float32)
+    labels = (rng.rand(B, C) < 0.05).astype(np.int64)
+    labels[:, 0] = 1
+    m = fn(torch.from_numpy(scores), torch.from_numpy(labels), [1, 5, 10])
+    out["multi.scores"], out["multi.labels"] = scores, labels
+    out["multi.keys"] = np.array(sorted(m.keys()))
+    out["multi.vals"] = np.array([m[k] for k in sorted(m.keys())], np.float64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written")
+
+
+def gen_scatter_adam(name="scatter_adam"):
+    """embedding_dense_backward and optim.Adam of the installed torch (the reference's L0 substrate)."""
+    rng = np.random.RandomState(11)
+    out = {}
+    V, d, n = 53, 16, 400
+    idx = rng.zipf(1.3, size=n) % V
+    rows = rng.randn(n, d).astype(np.float32)
+    emb = torch.nn.Embedding(V, d, padding_idx=0)
+    y = emb(torch.from_numpy(idx.astype(np.int64)))
+    y.backward(torch.from_numpy(rows))
+    out["scatter.idx"], out["scatter.rows"], out["scatter.grad"] = idx.astype(np.int64), rows, emb.weight.grad.numpy().copy()
+    p = torch.nn.Parameter(torch.from_numpy(rng.randn(300).astype(np.float32)))
+    out["adam.p0"] = p.detach().numpy().copy()
+    opt = torch.optim.Adam([p], lr=1e-3)
+    gs = rng.randn(4, 300).astype(np.float32)
+    gs[2, :100] = 0  # rows with zero grad still move (dense Adam semantics)
+    ps = []
+    for i in range(4):
+        p.grad = torch.from_numpy(gs[i].copy())
+        opt.step()
+        ps.append(p.detach().numpy().copy())
+    out["adam.grads"], out["adam.ps"] = gs, np.stack(ps)
+    st = opt.state[p]
+    out["adam.m"], out["adam.v"] = st["exp_avg"].numpy().copy(), st["exp_avg_sq"].numpy().copy()
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print(name, "written")
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.parse_args()
+    torch.set_num_threads(1)  # fixed reduction order in the generated vectors
+    model_factory, metric_fn = ref_imports()
+    gen_bert(model_factory, "bert_tiny", V=37, L=8, d=16, nb=2, h=2, B=4, seed=0)
+    gen_bert(model_factory, "bert_odd", V=101, L=13, d=32, nb=1, h=4, B=3, seed=3)
+    gen_bert(model_factory, "bert_cfg2", V=3416, L=200, d=64, nb=2, h=2, B=4, seed=1, store_sd=False, adam_steps=2)
+    gen_sas(model_factory, "sas_tiny", V=37, L=8, d=16, nb=2, h=2, B=4, seed=0)
+    gen_sas(model_factory, "sas_odd", V=101, L=13, d=32, nb=1, h=1, B=3, seed=3)
+    gen_sas(model_factory, "sas_cfg1", V=3416, L=50, d=64, nb=2, h=1, B=8, seed=1, store_sd=False, adam_steps=2)
+    gen_metrics(metric_fn)
+    gen_scatter_adam()
+
+
+if __name__ == "__main__":
+    main()
