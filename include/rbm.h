@@ -1,0 +1,219 @@
+/* rbm.h -- C ABI of librbm_b200.so: the B200 (sm_100a) kernels behind the BERT4Rec / SASRec
+ * train step and full-catalogue evaluation.
+ *
+ * The reference (Furyton/Recommender-Baseline-Model) has no FFI: its "operator interface" for this
+ * path is the set of torch ops its modules call.  Each entry point below replaces one group of those
+ * ops; the reference call site is cited as NN/<file>:<line> with
+ *   NN/ = NerualNetwork/bert4rec&sas4rec/.
+ * The Python host side (recommender-baseline-model_b200/) binds these with ctypes and mirrors the
+ * reference's model / trainer / metric API on top.
+ *
+ * Conventions
+ *  - all pointers are DEVICE pointers unless the name ends in _host; fp32 data, int64 indices;
+ *    row-major; every fp32 pointer must be 16-byte aligned and every hidden size d % 4 == 0.
+ *  - `stream` is a cudaStream_t passed as void*; every call only enqueues work on it (no sync,
+ *    no allocation, no global state besides the thread-local last-error string).
+ *  - return 0 on success, <0 for an invalid argument / unsupported shape (no CPU fallback),
+ *    >0 = cudaError_t of the launch.  rbm_last_error() describes the last failure on this thread.
+ *  - dropout: keep-mask = Philox4x32-10(key=seed, counter=(element/4, site)) >= p*2^32, scaled by
+ *    1/(1-p); `site` identifies the dropout call site within a step (DESIGN.md "dropout").  The
+ *    backward entry points regenerate the mask from (seed, site); nothing is stored.
+ */
+#ifndef RBM_H
+#define RBM_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RBM_ABI_VERSION 1
+
+typedef void* rbm_stream_t; /* cudaStream_t */
+
+/* activation codes for rbm_linear_* */
+#define RBM_ACT_NONE 0
+#define RBM_ACT_RELU 1      /* NN/models/sas_model/sas.py:12 */
+#define RBM_ACT_GELU_TANH 2 /* NN/models/bert_modules/utils/gelu.py:12 */
+
+/* LayerNorm flavours */
+#define RBM_LN_TORCH 0 /* nn.LayerNorm: biased var, eps inside sqrt  (NN/models/sas_model/sas.py:39,42,50) */
+#define RBM_LN_BERT 1  /* a*(x-mean)/(std_unbiased+eps)+b           (NN/models/bert_modules/utils/layer_norm.py:14-17) */
+
+/* attention mask modes */
+#define RBM_MASK_NONE 0
+#define RBM_MASK_CAUSAL 1 /* future keys -> -inf                      (NN/models/sas_model/sas.py:70,75-76) */
+#define RBM_MASK_KEYPAD 2 /* keys whose token == 0 -> -1e9            (NN/models/bert_modules/bert.py:38, attention/single.py:27-28) */
+
+int rbm_abi_version(void);
+const char* rbm_last_error(void);
+
+/* ---- embedding stage ---------------------------------------------------------------------------
+ * out[r,:] = keep(r) * dropout( table[tok[r],:]*scale + pos[r % L,:] ),  keep(r) = zero_pad ? tok[r]!=0 : 1
+ * replaces  SAS.log2feats NN/models/sas_model/sas.py:60-67  (scale=sqrt(d), zero_pad=1)
+ *           BERTEmbedding.forward NN/models/bert_modules/embedding/bert.py:29-31 (scale=1, zero_pad=0) */
+int rbm_embed_fwd(const int64_t* tok, const float* table, const float* pos, float* out, int64_t rows, int L,
+                  int d, int64_t vocab, float scale, int zero_pad, float p, uint64_t seed, uint64_t site,
+                  rbm_stream_t stream);
+/* g[r,:] = keep(r)*mask*dout[r,:]  (gradient w.r.t. the pre-dropout sum);  dpos[l,:] = sum_b g[b*L+l,:]
+ * (batch-ascending order).  The table gradient is rbm_scatter_add_sorted(tok, g, alpha=scale). */
+int rbm_embed_bwd(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
+                  int zero_pad, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
+
+/* ---- embedding-gradient scatter-add (autograd of nn.Embedding = embedding_dense_backward; triggered by
+ * loss.backward() NN/trainers/base.py:121).  grad[idx[i],:] += alpha * coef[i] * src[i,:], summed over i in
+ * ASCENDING i per destination row (stable LSD radix sort of idx, then one sequential fp32 segment sum per
+ * row: bit-identical to the CPU reference's index-ordered loop).  idx == padding_idx contributes nothing
+ * (padding_idx < 0: none).  coef may be NULL (=1).  ws: rbm_scatter_ws_bytes(n, vocab) bytes. */
+size_t rbm_scatter_ws_bytes(int64_t n, int64_t vocab);
+int rbm_scatter_add_sorted(const int64_t* idx, const float* src, const float* coef, float alpha, float* grad,
+                           int64_t n, int d, int64_t vocab, int64_t padding_idx, void* ws, size_t ws_bytes,
+                           rbm_stream_t stream);
+
+/* ---- LayerNorm (both flavours), stats[r] = {mean, 1/(sqrt(var+eps)) | 1/(std+eps)} saved for backward --- */
+int rbm_layernorm_fwd(const float* x, const float* gamma, const float* beta, float* y, float* stats,
+                      int64_t rows, int d, float eps, int flavour, rbm_stream_t stream);
+/* dx = LN'(x)*dy; dgamma/dbeta [d] (deterministic two-stage column reduction; ws >= rbm_layernorm_ws_bytes) */
+size_t rbm_layernorm_ws_bytes(int64_t rows, int d);
+int rbm_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* stats, float* dx,
+                      float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour, void* ws,
+                      size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- Linear with fused epilogue --------------------------------------------------------------------
+ * pre = x[M,K] . w[N,K]^T + bias        (optionally stored to `pre` when act needs it in backward)
+ * y   = rowkeep * dropB( residual + dropA( act(pre) ) )      rowkeep(r) = row_tok ? row_tok[r]!=0 : 1
+ * replaces nn.Linear / Conv1d(k=1) + Dropout + activation + residual chains:
+ *   NN/models/bert_modules/attention/multi_head.py:29-30,40; utils/feed_forward.py:16; utils/sublayer.py:18;
+ *   transformer.py:32; NN/models/sas_model/sas.py:16-19,75,79,84 (in/out-proj of nn.MultiheadAttention). */
+int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
+                   float* pre, int64_t M, int N, int K, int act, const float* residual, int64_t ldres,
+                   const int64_t* row_tok, float pA, uint64_t siteA, float pB, uint64_t siteB, uint64_t seed,
+                   rbm_stream_t stream);
+/* elementwise backward of the epilogue: dres = rowkeep*maskB*dout (may be NULL), dpre = dres*maskA*act'(pre) */
+int rbm_linear_epilogue_bwd(const float* dout, const float* pre, float* dpre, float* dres, int64_t M, int N,
+                            int act, const int64_t* row_tok, float pA, uint64_t siteA, float pB,
+                            uint64_t siteB, uint64_t seed, rbm_stream_t stream);
+/* dx[M,K] = dpre[M,N] . w[N,K] */
+int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const float* w, float* dx, int64_t lddx, int64_t M,
+                        int N, int K, rbm_stream_t stream);
+/* dw[N,K] = dpre^T . x ; db[N] = colsum(dpre)  (split over M, fixed-order reduction; ws from _ws_bytes) */
+size_t rbm_linear_bwd_weight_ws_bytes(int64_t M, int N, int K);
+int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const float* x, int64_t ldx, float* dw, float* db,
+                          int64_t M, int N, int K, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- short-sequence multi-head attention (L <= 256), one CTA per (sequence, head) -------------------
+ * q/k/v/out are [B*L, ld*] row-major with head hh occupying columns [hh*dk, (hh+1)*dk).
+ * P = dropout(softmax(mask(scale * q.k^T)));  out = P.v;  stats[(b*h+hh)*L+i] = {rowmax, 1/rowsum}.
+ * replaces Attention.forward NN/models/bert_modules/attention/single.py:13-35 and the core of
+ * nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76. */
+int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                 const int64_t* tok, float* out, int64_t ldo, float* stats, int B, int L, int h, int dk,
+                 int mask_mode, float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
+size_t rbm_attn_bwd_ws_bytes(int B, int L, int h);
+int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                 const int64_t* tok, const float* out, int64_t ldo, const float* dout, int64_t lddo,
+                 const float* stats, float* dq, int64_t lddq, float* dk_, int64_t lddk, float* dv,
+                 int64_t lddv, int B, int L, int h, int dk, int mask_mode, float scale, float p, uint64_t seed,
+                 uint64_t site, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- BERT4Rec output scoring fused with masked cross-entropy (logits never materialised) ------------
+ * rows with labels != 0 are compacted (ascending); for those rows logits = h.w^T + bias over V1 = V+1
+ * columns; loss = mean(logsumexp - target logit).
+ * replaces self.out(...) NN/models/bert.py:16 + CrossEntropyLoss(ignore_index=0) NN/trainers/bert.py:11,36-40. */
+/* compaction: rows_out[0..count) = ascending row ids with labels != 0, tgt_out = their labels, *count_out. */
+size_t rbm_compact_ws_bytes(int64_t n);
+int rbm_compact_labels(const int64_t* labels, int64_t n, int32_t* rows_out, int64_t* tgt_out, int32_t* count_out,
+                       void* ws, size_t ws_bytes, rbm_stream_t stream);
+size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d);
+/* forward: lse[cap], loss (1 float).  cap = capacity (>= count); count read from device. */
+int rbm_ce_fwd(const float* h, const int32_t* rows, const int64_t* tgt, const int32_t* count, const float* w,
+               const float* bias, float* lse, float* loss, int64_t cap, int V1, int d, void* ws, size_t ws_bytes,
+               rbm_stream_t stream);
+/* backward: dh_full[n_rows_total,d] must be pre-zeroed; rows listed in `rows` receive their gradient;
+ * dw[V1,d], db[V1] overwritten.  dloss: device scalar (upstream gradient). */
+int rbm_ce_bwd(const float* h, const int32_t* rows, const int64_t* tgt, const int32_t* count, const float* w,
+               const float* bias, const float* lse, const float* dloss, float* dh_full, float* dw, float* db,
+               int64_t cap, int V1, int d, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- SASRec train scoring + BCE ---------------------------------------------------------------------
+ * pos_logit[r] = <f[r,:], table[pos[r],:]>, same for neg     (SAS.forward NN/models/sas_model/sas.py:93-100) */
+int rbm_sas_score_fwd(const float* f, const float* table, const int64_t* pos, const int64_t* neg,
+                      float* pos_logit, float* neg_logit, int64_t rows, int d, rbm_stream_t stream);
+/* df[r,:] = dpl[r]*table[pos[r]] + dnl[r]*table[neg[r]]; table grads: scatter with coef=dpl / dnl, src=f */
+int rbm_sas_score_bwd(const float* table, const int64_t* pos, const int64_t* neg, const float* dpl,
+                      const float* dnl, float* df, int64_t rows, int d, rbm_stream_t stream);
+/* loss = mean_{pos!=0} softplus(-pl) + mean_{pos!=0} softplus(nl)   (NN/trainers/sas.py:38-49);
+ * also writes count (int32) of pos != 0.  ws >= rbm_bce_ws_bytes(rows). */
+size_t rbm_bce_ws_bytes(int64_t rows);
+int rbm_bce_pair_fwd(const float* pl, const float* nl, const int64_t* pos, float* loss, int32_t* count,
+                     int64_t rows, void* ws, size_t ws_bytes, rbm_stream_t stream);
+int rbm_bce_pair_bwd(const float* pl, const float* nl, const int64_t* pos, const int32_t* count,
+                     const float* dloss, float* dpl, float* dnl, int64_t rows, rbm_stream_t stream);
+
+/* ---- candidate scoring for sampled evaluation -------------------------------------------------------
+ * out[u,c] = <table[cand[u,c],:], f[u,:]> (+ bias[cand[u,c]])
+ * replaces SAS.predict NN/models/sas_model/sas.py:110-114 and scores.gather NN/trainers/bert.py:47-49 */
+int rbm_candidate_scores(const float* f, int64_t ldf, const float* table, const float* bias, const int64_t* cand,
+                         float* out, int64_t U, int C, int d, rbm_stream_t stream);
+
+/* ---- full-catalogue scoring fused with top-k (scores never materialised) ----------------------------
+ * For each user u: rank items v in [v_begin, v_end) (rows of `table`) by s = <f[u],table[v]> (+bias[v]),
+ * order (score desc, id asc), id = v + id_offset; emit top_scores/top_ids [U,k] (k <= 32; unfilled slots
+ * = (-inf, -1)).  ws >= rbm_score_topk_ws_bytes. */
+size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k);
+int rbm_score_topk(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin,
+                   int64_t v_end, int64_t id_offset, float* top_scores, int64_t* top_ids, int64_t U, int d,
+                   int k, void* ws, size_t ws_bytes, rbm_stream_t stream);
+/* top-k of materialised scores [U,C] (ld = row stride), same order rule; id = column + id_offset.
+ * replaces (-scores).argsort(dim=1)[:, :k]  NN/trainers/utils.py:36-38 */
+int rbm_topk_rows(const float* scores, int64_t ld, float* top_scores, int64_t* top_ids, int64_t U, int64_t C,
+                  int k, int64_t id_offset, rbm_stream_t stream);
+/* merge S per-shard lists [S,U,k] (global ids, (-inf,-1) padding) into [U,k]; shard-count invariant */
+int rbm_topk_merge(const float* scores, const int64_t* ids, float* out_scores, int64_t* out_ids, int S,
+                   int64_t U, int k, rbm_stream_t stream);
+/* ranking metrics, NN/trainers/utils.py:41-55.  hits[u,t] = labels[u, top_ids[u,t]-id_offset] (labels
+ * [U,C] i64) or, when labels==NULL, (top_ids[u,t] == positives[u]).  For each k in ks (nk values, host
+ * array, each <= K): per_user[u, j, 0..2] = Recall@k, NDCG@k, MRR@k; w_ndcg/w_mrr: [K] weight tables. */
+int rbm_rank_metrics(const int64_t* top_ids, const int64_t* labels, const int64_t* positives,
+                     const float* w_ndcg, const float* w_mrr, const int32_t* ks_host, int nk, float* per_user,
+                     int64_t U, int K, int64_t C, int64_t id_offset, rbm_stream_t stream);
+/* mean over rows of x[U,cols] accumulated in double in fixed order -> out[cols] (fp32); cols <= 256 */
+size_t rbm_column_mean_ws_bytes(int64_t U, int cols);
+int rbm_column_mean(const float* x, float* out, int64_t U, int cols, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- dense Adam over many tensors in one launch (optim.Adam NN/trainers/base.py:225-233, .step() :123) */
+typedef struct {
+  float* p;
+  const float* g;
+  float* m;
+  float* v;
+  int64_t n;
+} rbm_adam_tensor;
+/* tensors: DEVICE array of n_tensors descriptors; total_chunks = sum ceil(n/RBM_ADAM_CHUNK);
+ * chunk_map: DEVICE int32 [total_chunks*2] = (tensor id, chunk id within tensor). */
+#define RBM_ADAM_CHUNK 4096
+int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chunk_map, int total_chunks, float lr,
+                   float beta1, float beta2, float eps, float weight_decay, int step, rbm_stream_t stream);
+/* flat-bucket helpers for the data-parallel gradient all-reduce: copy n_tensors tensors to/from one
+ * contiguous bucket (offsets in elements), optionally scaling. */
+typedef struct {
+  float* ptr;
+  int64_t n;
+  int64_t offset;
+} rbm_bucket_tensor;
+int rbm_bucket_pack(const rbm_bucket_tensor* tensors, const int32_t* chunk_map, int total_chunks, float* bucket,
+                    float scale, int unpack, rbm_stream_t stream);
+
+/* ---- test / debug ---------------------------------------------------------------------------------- */
+/* materialise the keep-mask (1 = keep) the kernels use for an elementwise site over n elements */
+int rbm_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
+/* ... and for an attention site: out [B*h*L, L] */
+int rbm_dropout_mask_attn(uint8_t* out, int64_t rows, int L, float p, uint64_t seed, uint64_t site,
+                          rbm_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RBM_H */

@@ -1,0 +1,117 @@
+// common.cuh -- shared device helpers for librbm_b200 (sm_100a).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <math.h>
+#include "../../include/rbm.h"
+
+#define RBM_NUM_SMS 148  // B200: 2 dies x 74 SMs; persistent / capped grids are sized in multiples of this
+
+void rbm_set_error(const char* fmt, ...);
+
+#define RBM_REQUIRE(cond, ...)        \
+  do {                                \
+    if (!(cond)) {                    \
+      rbm_set_error(__VA_ARGS__);     \
+      return -1;                      \
+    }                                 \
+  } while (0)
+
+#define RBM_LAUNCH_CHECK(name)                                              \
+  do {                                                                      \
+    cudaError_t _e = cudaGetLastError();                                    \
+    if (_e != cudaSuccess) {                                                \
+      rbm_set_error("%s: launch failed: %s", name, cudaGetErrorString(_e)); \
+      return (int)_e;                                                       \
+    }                                                                       \
+  } while (0)
+
+static inline bool rbm_aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
+static inline int64_t rbm_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
+
+// ---------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based RNG.  One call yields 4 x u32 for 4 consecutive logical elements.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ uint32_t rbm_mulhi(uint32_t a, uint32_t b) {
+#ifdef __CUDA_ARCH__
+  return __umulhi(a, b);
+#else
+  return (uint32_t)(((uint64_t)a * (uint64_t)b) >> 32);
+#endif
+}
+
+__host__ __device__ __forceinline__ uint4 rbm_philox(uint64_t seed, uint64_t site, uint64_t idx4) {
+  uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = (uint32_t)site, c3 = (uint32_t)(site >> 32);
+  uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
+#pragma unroll
+  for (int r = 0; r < 10; ++r) {
+    uint32_t hi0 = rbm_mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+    uint32_t hi1 = rbm_mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+    c0 = hi1 ^ c1 ^ k0;
+    c1 = lo1;
+    c2 = hi0 ^ c3 ^ k1;
+    c3 = lo0;
+    k0 += 0x9E3779B9u;
+    k1 += 0xBB67AE85u;
+  }
+  return make_uint4(c0, c1, c2, c3);
+}
+
+// dropout threshold: an element is KEPT iff its u32 >= thr, i.e. dropped with probability thr / 2^32.
+__host__ __device__ __forceinline__ uint32_t rbm_drop_threshold(float p) {
+  double t = (double)p * 4294967296.0;
+  if (t <= 0.0) return 0u;
+  if (t >= 4294967295.0) return 4294967295u;
+  return (uint32_t)t;
+}
+
+// keep-scale of the 4 elements [4*idx4, 4*idx4+4) of an elementwise site: 0 or 1/(1-p)
+__device__ __forceinline__ float4 rbm_drop4(uint64_t seed, uint64_t site, uint64_t idx4, uint32_t thr, float inv_keep) {
+  uint4 r = rbm_philox(seed, site, idx4);
+  return make_float4(r.x >= thr ? inv_keep : 0.f, r.y >= thr ? inv_keep : 0.f, r.z >= thr ? inv_keep : 0.f,
+                     r.w >= thr ? inv_keep : 0.f);
+}
+
+// Attention-probability sites: element (row R = (b*h+hh)*L + i, key j).  Lane (j & 31) of the warp that owns
+// row i holds keys j = lane + 32*jj, so one Philox call serves jj = 4g .. 4g+3 of one lane:
+//   call index = R * RBM_ATTN_GROUPS + (j & 31) + 32 * ((j >> 5) >> 2),   component = (j >> 5) & 3.
+#define RBM_ATTN_GROUPS 64  // supports L <= 256
+__host__ __device__ __forceinline__ uint64_t rbm_attn_call(uint64_t R, int j) {
+  return R * RBM_ATTN_GROUPS + (uint64_t)((j & 31) + 32 * ((j >> 5) >> 2));
+}
+__host__ __device__ __forceinline__ uint32_t rbm_u4_get(const uint4& r, int c) {
+  return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
+}
+
+// ---------------------------------------------------------------------------------------------
+// warp helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+
+__device__ __forceinline__ float gelu_tanh_f(float x) {
+  // 0.5*x*(1+tanh(sqrt(2/pi)*(x+0.044715*x^3)))   NN/models/bert_modules/utils/gelu.py:12
+  const float c = 0.7978845608028654f;
+  float u = c * (x + 0.044715f * x * x * x);
+  return 0.5f * x * (1.f + tanhf(u));
+}
+__device__ __forceinline__ float gelu_tanh_grad_f(float x) {
+  const float c = 0.7978845608028654f;
+  float x2 = x * x;
+  float u = c * (x + 0.044715f * x * x2);
+  float t = tanhf(u);
+  float du = c * (1.f + 3.f * 0.044715f * x2);
+  return 0.5f * (1.f + t) + 0.5f * x * (1.f - t * t) * du;
+}

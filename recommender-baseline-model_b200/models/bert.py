@@ -1,0 +1,178 @@
+"""BERT4Rec with the reference's constructor, ``forward`` and ``state_dict`` (NN/models/bert.py:6-16,
+NN/models/bert_modules/**), computed by the sm_100a kernels of librbm_b200.
+
+The nn.Module tree below only *holds parameters* under the reference's names -- so checkpoints interchange and, being
+built from the same torch layers in the same order after ``fix_random_seed_as(model_init_seed)``
+(NN/models/bert_modules/bert.py:12), the initial weights are bit-identical to the reference's.  None of these holder
+modules' own ``forward`` is ever used.
+"""
+import math
+import random
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import lib as L
+from .. import ops
+from .base import BaseModel
+
+
+def fix_random_seed_as(random_seed):
+    """NN/utils.py:65-71."""
+    random.seed(random_seed)
+    torch.manual_seed(random_seed)
+    torch.cuda.manual_seed_all(random_seed)
+    np.random.seed(random_seed)
+    torch.backends.cudnn.deterministic = True
+    torch.backends.cudnn.benchmark = False
+
+
+class _Norm(nn.Module):  # NN/models/bert_modules/utils/layer_norm.py:8-12 (a_2, b_2, eps=1e-6)
+    def __init__(self, size):
+        super().__init__()
+        self.a_2 = nn.Parameter(torch.ones(size))
+        self.b_2 = nn.Parameter(torch.zeros(size))
+        self.eps = 1e-6
+
+
+class _Sublayer(nn.Module):  # NN/models/bert_modules/utils/sublayer.py:11-14
+    def __init__(self, size):
+        super().__init__()
+        self.norm = _Norm(size)
+
+
+class _Attention(nn.Module):  # NN/models/bert_modules/attention/multi_head.py:10-22
+    def __init__(self, h, d_model):
+        super().__init__()
+        assert d_model % h == 0
+        self.d_k = d_model // h
+        self.h = h
+        self.linear_layers = nn.ModuleList([nn.Linear(d_model, d_model) for _ in range(3)])
+        self.output_linear = nn.Linear(d_model, d_model)
+
+
+class _FeedForward(nn.Module):  # NN/models/bert_modules/utils/feed_forward.py:8-13
+    def __init__(self, d_model, d_ff):
+        super().__init__()
+        self.w_1 = nn.Linear(d_model, d_ff)
+        self.w_2 = nn.Linear(d_ff, d_model)
+
+
+class _Block(nn.Module):  # NN/models/bert_modules/transformer.py:13-26
+    def __init__(self, hidden, heads, ff_hidden):
+        super().__init__()
+        self.attention = _Attention(heads, hidden)
+        self.feed_forward = _FeedForward(hidden, ff_hidden)
+        self.input_sublayer = _Sublayer(hidden)
+        self.output_sublayer = _Sublayer(hidden)
+
+
+class _Token(nn.Embedding):  # NN/models/bert_modules/embedding/token.py:4-6
+    def __init__(self, vocab_size, embed_size):
+        super().__init__(vocab_size, embed_size, padding_idx=0)
+
+
+class _Position(nn.Module):  # NN/models/bert_modules/embedding/position.py:8-12
+    def __init__(self, max_len, d_model):
+        super().__init__()
+        self.pe = nn.Embedding(max_len, d_model)
+
+
+class _Embedding(nn.Module):  # NN/models/bert_modules/embedding/bert.py:17-27
+    def __init__(self, vocab_size, embed_size, max_len):
+        super().__init__()
+        self.token = _Token(vocab_size, embed_size)
+        self.position = _Position(max_len, embed_size)
+
+
+class BERT(nn.Module):
+    """Parameter tree of NN/models/bert_modules/bert.py:8-34."""
+
+    def __init__(self, args):
+        super().__init__()
+        fix_random_seed_as(args.model_init_seed)
+        self.max_len = args.max_len
+        self.hidden = args.bert_hidden_units
+        self.heads = args.bert_num_heads
+        self.n_layers = args.bert_num_blocks
+        self.p_attn = float(args.bert_dropout)
+        self.p_hidden = float(args.bert_hidden_dropout)
+        vocab_size = args.num_items + 2  # [MASK] = num_items + 1, padding = 0
+        self.embedding = _Embedding(vocab_size, self.hidden, self.max_len)
+        self.transformer_blocks = nn.ModuleList([_Block(self.hidden, self.heads, self.hidden * 4) for _ in range(self.n_layers)])
+
+
+class BERTModel(BaseModel):
+    def __init__(self, args):
+        super().__init__(args)
+        self.bert = BERT(args)
+        self.out = nn.Linear(self.bert.hidden, args.num_items + 1)
+        self.num_items = args.num_items
+
+    @classmethod
+    def code(cls):
+        return 'bert'
+
+    # ------------------------------------------------------------------ transformer body (a7-a11)
+    def hidden_states(self, x):
+        """BERT.forward NN/models/bert_modules/bert.py:36-43 -> [B, L, d]."""
+        bert = self.bert
+        tok = self._device_long(x)
+        Bsz, Ln = tok.shape
+        if Ln != bert.max_len:
+            raise RuntimeError("BERT4Rec adds the whole positional table: sequence length %d must equal max_len %d "
+                               "(NN/models/bert_modules/embedding/position.py:16)" % (Ln, bert.max_len))
+        d, h = bert.hidden, bert.heads
+        train = self.training
+        p_h = bert.p_hidden if train else 0.0
+        p_a = bert.p_attn if train else 0.0
+        seed = self.dropout_seed
+        base = self._next_site_base() if train else 0
+        x = ops.EmbedFn.apply(tok, bert.embedding.token.weight, bert.embedding.position.pe.weight, 1.0, 0, p_h, seed, base)
+        scale = 1.0 / math.sqrt(d // h)
+        for b, blk in enumerate(bert.transformer_blocks):
+            s = base + 1 + 5 * b
+            att, ff = blk.attention, blk.feed_forward
+            n1 = ops.layernorm(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            w_qkv = torch.cat([l.weight for l in att.linear_layers], 0)
+            b_qkv = torch.cat([l.bias for l in att.linear_layers], 0)
+            qkv = ops.linear(n1, w_qkv, b_qkv)
+            ctx = ops.attention(qkv, None, tok, Bsz, Ln, h, 0, d, 2 * d, L.MASK_KEYPAD, scale, p_a, seed, s)
+            x = ops.linear(ctx.view(Bsz, Ln, d), att.output_linear.weight, att.output_linear.bias, residual=x, pA=p_h,
+                           siteA=s + 1, seed=seed)
+            n2 = ops.layernorm(x, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH, pA=p_h, siteA=s + 2, seed=seed)
+            x = ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=x, pA=p_h, siteA=s + 3, pB=p_h, siteB=s + 4, seed=seed)
+        return x
+
+    # ------------------------------------------------------------------ reference API
+    def forward(self, x):
+        """NN/models/bert.py:15-16: logits [B, L, V+1].  Compatibility path that materialises the logits (small shapes,
+        parity tests); training uses :meth:`loss`, evaluation :meth:`candidate_scores` / :meth:`full_catalogue_topk`."""
+        h = self.hidden_states(x)
+        V1 = self.out.weight.shape[0]
+        pad = (-V1) % 4
+        w, b = self.out.weight, self.out.bias
+        if pad:
+            w = torch.cat([w, w.new_zeros(pad, w.shape[1])], 0)
+            b = torch.cat([b, b.new_zeros(pad)], 0)
+        logits = ops.linear(h, w, b)
+        return logits[..., :V1].contiguous() if pad else logits
+
+    # ------------------------------------------------------------------ fused paths used by the drop-in trainer
+    def loss(self, x, labels):
+        """CE(ignore_index=0) of NN/trainers/bert.py:30-41 without materialising [B*L, V+1] logits (K15-K16)."""
+        h = self.hidden_states(x)
+        return ops.score_cross_entropy(h, self._device_long(labels), self.out.weight, self.out.bias)
+
+    def last_hidden(self, x):
+        return self.hidden_states(x)[:, -1, :]
+
+    def candidate_scores(self, x, candidates):
+        """scores[:, -1, :].gather(1, candidates) of NN/trainers/bert.py:47-49, scoring only the candidates."""
+        return ops.candidate_scores(self.last_hidden(x), self.out.weight, self.out.bias, self._device_long(candidates))
+
+    def full_catalogue_topk(self, x, k=10):
+        """Top-k items (ids 1..V) of the last position, (score desc, id asc); scores never materialised (K19-K21)."""
+        return ops.score_topk(self.last_hidden(x), self.out.weight, self.out.bias, 1, self.num_items + 1, k)

@@ -1,0 +1,103 @@
+"""SASRec with the reference's constructor, ``forward`` / ``predict`` and ``state_dict`` (NN/models/sas.py:6-19,
+NN/models/sas_model/sas.py:24-118), computed by the sm_100a kernels of librbm_b200.
+
+``self.sas`` holds parameters under the reference's names, built from the same torch layers in the same order (so a
+given torch seed yields the reference's initial weights); their own ``forward`` is never used.
+"""
+import math
+
+import torch
+import torch.nn as nn
+
+from .. import lib as L
+from .. import ops
+from .base import BaseModel
+
+
+class _PointWiseFeedForward(nn.Module):  # NN/models/sas_model/sas.py:7-14
+    def __init__(self, hidden_units):
+        super().__init__()
+        self.conv1 = nn.Conv1d(hidden_units, hidden_units, kernel_size=1)
+        self.conv2 = nn.Conv1d(hidden_units, hidden_units, kernel_size=1)
+
+
+class SAS(nn.Module):
+    """Parameter tree of NN/models/sas_model/sas.py:24-57."""
+
+    def __init__(self, args):
+        super().__init__()
+        self.item_num = args.num_items
+        d = args.sas_hidden_units
+        self.hidden = d
+        self.heads = args.sas_heads
+        self.p = float(args.sas_dropout)
+        self.item_emb = nn.Embedding(self.item_num + 1, d, padding_idx=0)
+        self.pos_emb = nn.Embedding(args.max_len, d)
+        self.attention_layernorms = nn.ModuleList()
+        self.attention_layers = nn.ModuleList()
+        self.forward_layernorms = nn.ModuleList()
+        self.forward_layers = nn.ModuleList()
+        self.last_layernorm = nn.LayerNorm(d, eps=1e-8)
+        for _ in range(args.sas_num_blocks):
+            self.attention_layernorms.append(nn.LayerNorm(d, eps=1e-8))
+            self.attention_layers.append(nn.MultiheadAttention(d, self.heads, self.p))
+            self.forward_layernorms.append(nn.LayerNorm(d, eps=1e-8))
+            self.forward_layers.append(_PointWiseFeedForward(d))
+
+
+class SASModel(BaseModel):
+    def __init__(self, args):
+        super().__init__(args)
+        self.sas = SAS(args)
+
+    @classmethod
+    def code(cls):
+        return 'sas'
+
+    def log2feats(self, log_seqs):
+        """SAS.log2feats NN/models/sas_model/sas.py:59-88 -> [B, L, d]."""
+        sas = self.sas
+        seq = self._device_long(log_seqs)
+        Bsz, Ln = seq.shape
+        d, h = sas.hidden, sas.heads
+        train = self.training
+        p = sas.p if train else 0.0
+        seed = self.dropout_seed
+        base = self._next_site_base() if train else 0
+        x = ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base)
+        scale = math.sqrt(1.0 / (d // h))
+        for b in range(len(sas.attention_layers)):
+            s = base + 1 + 3 * b
+            ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
+            Q = ops.layernorm(x, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
+            w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
+            q = ops.linear(Q, w_in[:d], b_in[:d])          # q from the normalised stream
+            kv = ops.linear(x, w_in[d:], b_in[d:])         # k, v from the un-normalised stream (sas.py:75)
+            ctx = ops.attention(q, kv, None, Bsz, Ln, h, 0, 0, d, L.MASK_CAUSAL, scale, p, seed, s)
+            x = ops.linear(ctx.view(Bsz, Ln, d), mha.out_proj.weight, mha.out_proj.bias, residual=Q)  # Q + mha (sas.py:79)
+            x = ops.layernorm(x, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
+            u = ops.linear(x, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU, pA=p, siteA=s + 1, seed=seed)
+            x = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=x, row_tok=seq, pA=p, siteA=s + 2, seed=seed)
+        return ops.layernorm(x, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
+
+    def forward(self, log_seqs, pos_seqs, neg_seqs):  # for training
+        """NN/models/sas_model/sas.py:90-105 -> (pos_logits, neg_logits) [B, L]."""
+        f = self.log2feats(log_seqs)
+        return ops.sas_scores(f, self.sas.item_emb.weight, self._device_long(pos_seqs), self._device_long(neg_seqs))
+
+    def loss(self, log_seqs, pos_seqs, neg_seqs):
+        """BCE part of SASTrainer.calculate_loss NN/trainers/sas.py:34-49."""
+        pos = self._device_long(pos_seqs)
+        pl, nl = self.forward(log_seqs, pos, neg_seqs)
+        return ops.bce_pair_loss(pl, nl, pos)
+
+    def last_hidden(self, log_seqs):
+        return self.log2feats(log_seqs)[:, -1, :]
+
+    def predict(self, log_seqs, item_indices):  # for inference
+        """NN/models/sas_model/sas.py:107-118 -> [B, C]."""
+        return ops.candidate_scores(self.last_hidden(log_seqs), self.sas.item_emb.weight, None, self._device_long(item_indices))
+
+    def full_catalogue_topk(self, log_seqs, k=10):
+        """Top-k items (ids 1..V), (score desc, id asc); the [B, V, d] gather of ``predict`` is never built (K19-K21)."""
+        return ops.score_topk(self.last_hidden(log_seqs), self.sas.item_emb.weight, None, 1, self.sas.item_num + 1, k)

@@ -1,0 +1,485 @@
+"""autograd.Functions over the C ABI (include/rbm.h).  Each op = one group of reference torch ops replaced by a
+hand-written sm_100a kernel; `loss.backward()` (NN/trainers/base.py:121) walks these backward methods.
+No torch math on the hot path: torch only allocates the output tensors and orders the calls."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import lib as L
+from .lib import check, ptr, stream, workspaces, count_launches
+
+
+def _ws(tag: str, nbytes: int, device) -> torch.Tensor:
+    return workspaces.get(tag, nbytes, device)
+
+
+def _rows2d(x: torch.Tensor) -> torch.Tensor:
+    """View as [rows, cols] with unit inner stride (no copy when already so)."""
+    x2 = x.reshape(-1, x.shape[-1])
+    if x2.stride(-1) != 1:
+        x2 = x2.contiguous()
+    return x2
+
+
+# ------------------------------------------------------------------------------------------ scatter-add
+def scatter_add_sorted_(grad: torch.Tensor, idx: torch.Tensor, src: torch.Tensor, coef: Optional[torch.Tensor] = None,
+                        alpha: float = 1.0, padding_idx: int = 0) -> torch.Tensor:
+    """grad[idx[i]] += alpha*coef[i]*src[i] in ascending i per row (deterministic; K17)."""
+    lib = L.load()
+    L.require_cuda(grad, idx, src)
+    n, d = idx.numel(), grad.shape[1]
+    idx = idx.reshape(-1).contiguous()
+    src = src.reshape(n, d).contiguous()
+    nb = lib.rbm_scatter_ws_bytes(n, grad.shape[0])
+    ws = _ws("scatter", nb, grad.device)
+    check(lib.rbm_scatter_add_sorted(ptr(idx), ptr(src), ptr(coef), float(alpha), ptr(grad), n, d, grad.shape[0],
+                                     int(padding_idx), ptr(ws), nb, stream()), "scatter_add_sorted")
+    bits = max(1, (grad.shape[0] - 1).bit_length())
+    count_launches(3 * ((bits + 7) // 8) + 1)
+    return grad
+
+
+# --------------------------------------------------------------------------------------------- embedding
+class EmbedFn(torch.autograd.Function):
+    """out = keep * dropout(table[tok]*scale + pos)   (K1-K3, K12)."""
+
+    @staticmethod
+    def forward(ctx, tok, table, pos, scale, zero_pad, p, seed, site):
+        lib = L.load()
+        L.require_cuda(tok, table, pos)
+        Bsz, Ln = tok.shape
+        d = table.shape[1]
+        if pos.shape[0] < Ln:
+            raise RuntimeError("positional table has %d rows < sequence length %d" % (pos.shape[0], Ln))
+        tok = tok.contiguous()
+        out = torch.empty(Bsz, Ln, d, device=table.device, dtype=torch.float32)
+        check(lib.rbm_embed_fwd(ptr(tok), ptr(table), ptr(pos), ptr(out), Bsz * Ln, Ln, d, table.shape[0], float(scale),
+                                int(zero_pad), float(p), seed, site, stream()), "embed_fwd")
+        count_launches()
+        ctx.save_for_backward(tok)
+        ctx.meta = (table.shape, pos.shape, float(scale), int(zero_pad), float(p), seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        (tok,) = ctx.saved_tensors
+        tshape, pshape, scale, zero_pad, p, seed, site = ctx.meta
+        Bsz, Ln = tok.shape
+        d = tshape[1]
+        dout = dout.contiguous()
+        g = torch.empty_like(dout)
+        dpos = torch.zeros(pshape, device=dout.device, dtype=torch.float32)
+        check(lib.rbm_embed_bwd(ptr(tok), ptr(dout), ptr(g), ptr(dpos), Bsz * Ln, Ln, d, zero_pad, p, seed, site, stream()),
+              "embed_bwd")
+        count_launches()
+        dtable = torch.zeros(tshape, device=dout.device, dtype=torch.float32)
+        scatter_add_sorted_(dtable, tok, g, None, scale, padding_idx=0)
+        return None, dtable, dpos, None, None, None, None, None
+
+
+# --------------------------------------------------------------------------------------------- layernorm
+class LayerNormFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, flavour):
+        lib = L.load()
+        L.require_cuda(x, gamma, beta)
+        x2 = _rows2d(x).contiguous()
+        rows, d = x2.shape
+        y = torch.empty_like(x2)
+        stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+        check(lib.rbm_layernorm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(y), ptr(stats), rows, d, float(eps), int(flavour),
+                                    stream()), "layernorm_fwd")
+        count_launches()
+        ctx.save_for_backward(x2, gamma, stats)
+        ctx.meta = (float(eps), int(flavour), x.shape)
+        return y.view(x.shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x2, gamma, stats = ctx.saved_tensors
+        eps, flavour, shape = ctx.meta
+        rows, d = x2.shape
+        dy2 = dy.reshape(rows, d).contiguous()
+        dx = torch.empty_like(x2)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        nb = lib.rbm_layernorm_ws_bytes(rows, d)
+        ws = _ws("ln", nb, x2.device)
+        check(lib.rbm_layernorm_bwd(ptr(x2), ptr(gamma), ptr(dy2), ptr(stats), ptr(dx), ptr(dgamma), ptr(dbeta), rows, d, eps,
+                                    flavour, ptr(ws), nb, stream()), "layernorm_bwd")
+        count_launches(2)
+        return dx.view(shape), dgamma, dbeta, None, None
+
+
+def layernorm(x, gamma, beta, eps, flavour):
+    return LayerNormFn.apply(x, gamma, beta, eps, flavour)
+
+
+# ------------------------------------------------------------------------------------------------ linear
+class LinearFn(torch.autograd.Function):
+    """y = rowkeep * dropB(residual + dropA(act(x.w^T + b)))   (K6, K9-K12)."""
+
+    @staticmethod
+    def forward(ctx, x, w, bias, residual, row_tok, act, pA, siteA, pB, siteB, seed):
+        lib = L.load()
+        L.require_cuda(x, w)
+        x2 = _rows2d(x)
+        M, K = x2.shape
+        N = w.shape[0]
+        w = w.contiguous()
+        y = torch.empty(M, N, device=x.device, dtype=torch.float32)
+        need_pre = act != L.ACT_NONE and (x.requires_grad or w.requires_grad)
+        pre = torch.empty(M, N, device=x.device, dtype=torch.float32) if need_pre else None
+        res2 = _rows2d(residual) if residual is not None else None
+        if row_tok is not None:
+            row_tok = row_tok.reshape(-1).contiguous()
+        check(lib.rbm_linear_fwd(ptr(x2), x2.stride(0), ptr(w), ptr(bias), ptr(y), N, ptr(pre), M, N, K, int(act), ptr(res2),
+                                 res2.stride(0) if res2 is not None else 0, ptr(row_tok), float(pA), siteA, float(pB), siteB,
+                                 seed, stream()), "linear_fwd")
+        count_launches()
+        ctx.save_for_backward(x2, w, pre, row_tok)
+        ctx.meta = (int(act), float(pA), siteA, float(pB), siteB, seed, bias is not None, residual is not None, x.shape,
+                    residual.shape if residual is not None else None)
+        return y.view(*x.shape[:-1], N)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        x2, w, pre, row_tok = ctx.saved_tensors
+        act, pA, siteA, pB, siteB, seed, has_bias, has_res, xshape, rshape = ctx.meta
+        M, K = x2.shape
+        N = w.shape[0]
+        dy2 = dy.reshape(M, N).contiguous()
+        trivial = act == L.ACT_NONE and pA == 0.0 and pB == 0.0 and row_tok is None
+        if trivial:
+            dpre, dres = dy2, (dy2 if has_res else None)
+        else:
+            dpre = torch.empty_like(dy2)
+            # dres is needed as a separate tensor only when something sits between the residual add and the output
+            need_dres = has_res
+            dres = torch.empty_like(dy2) if need_dres else None
+            check(lib.rbm_linear_epilogue_bwd(ptr(dy2), ptr(pre), ptr(dpre), ptr(dres), M, N, act, ptr(row_tok), pA, siteA, pB,
+                                              siteB, seed, stream()), "linear_epilogue_bwd")
+            count_launches()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
+            check(lib.rbm_linear_bwd_data(ptr(dpre), N, ptr(w), ptr(dx), K, M, N, K, stream()), "linear_bwd_data")
+            count_launches()
+            dx = dx.view(xshape)
+        if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
+            dw = torch.empty_like(w)
+            db = torch.empty(N, device=dy.device, dtype=torch.float32) if has_bias else None
+            nb = lib.rbm_linear_bwd_weight_ws_bytes(M, N, K)
+            ws = _ws("lin_dw", nb, dy.device)
+            check(lib.rbm_linear_bwd_weight(ptr(dpre), N, ptr(x2), x2.stride(0), ptr(dw), ptr(db), M, N, K, ptr(ws), nb, stream()),
+                  "linear_bwd_weight")
+            count_launches(3 if has_bias else 2)
+        return dx, dw, db, (dres.view(rshape) if has_res else None), None, None, None, None, None, None, None
+
+
+def linear(x, w, bias=None, residual=None, row_tok=None, act=L.ACT_NONE, pA=0.0, siteA=0, pB=0.0, siteB=0, seed=0):
+    return LinearFn.apply(x, w, bias, residual, row_tok, act, pA, siteA, pB, siteB, seed)
+
+
+# --------------------------------------------------------------------------------------------- attention
+class AttnFn(torch.autograd.Function):
+    """ctx = dropout(softmax(mask(scale q.k^T))).v, heads laid out as column blocks (K7-K9).
+
+    ``a`` holds q (columns [qc, qc+d)); ``b`` (or ``a`` when b is None) holds k and v at columns kc / vc."""
+
+    @staticmethod
+    def forward(ctx, a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p, seed, site):
+        lib = L.load()
+        L.require_cuda(a, b)
+        a2 = _rows2d(a)
+        b2 = _rows2d(b) if b is not None else a2
+        M = a2.shape[0]
+        d = (a2.shape[1] // 3) if b is None else a2.shape[1]
+        dk = d // h
+        if tok is not None:
+            tok = tok.reshape(-1).contiguous()
+        out = torch.empty(M, d, device=a.device, dtype=torch.float32)
+        stats = torch.empty(Bsz * h * Ln, 2, device=a.device, dtype=torch.float32)
+        check(lib.rbm_attn_fwd(a2.data_ptr() + 4 * qc, a2.stride(0), b2.data_ptr() + 4 * kc, b2.stride(0), b2.data_ptr() + 4 * vc,
+                               b2.stride(0), ptr(tok), ptr(out), d, ptr(stats), Bsz, Ln, h, dk, int(mask_mode), float(scale),
+                               float(p), seed, site, stream()), "attn_fwd")
+        count_launches()
+        ctx.save_for_backward(a2, b2 if b is not None else None, tok, out, stats)
+        ctx.meta = (Bsz, Ln, h, dk, d, qc, kc, vc, int(mask_mode), float(scale), float(p), seed, site, a.shape,
+                    b.shape if b is not None else None)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        a2, b2s, tok, out, stats = ctx.saved_tensors
+        Bsz, Ln, h, dk, d, qc, kc, vc, mask_mode, scale, p, seed, site, ashape, bshape = ctx.meta
+        b2 = b2s if b2s is not None else a2
+        dout = dout.reshape(-1, d).contiguous()
+        da = torch.empty_like(a2) if a2.is_contiguous() else torch.empty(a2.shape, device=a2.device, dtype=torch.float32)
+        db = da if b2s is None else torch.empty(b2.shape, device=a2.device, dtype=torch.float32)
+        nb = lib.rbm_attn_bwd_ws_bytes(Bsz, Ln, h)
+        ws = _ws("attn", nb, a2.device)
+        check(lib.rbm_attn_bwd(a2.data_ptr() + 4 * qc, a2.stride(0), b2.data_ptr() + 4 * kc, b2.stride(0),
+                               b2.data_ptr() + 4 * vc, b2.stride(0), ptr(tok), ptr(out), d, ptr(dout), d, ptr(stats),
+                               da.data_ptr() + 4 * qc, da.stride(0), db.data_ptr() + 4 * kc, db.stride(0),
+                               db.data_ptr() + 4 * vc, db.stride(0), Bsz, Ln, h, dk, mask_mode, scale, p, seed, site, ptr(ws),
+                               nb, stream()), "attn_bwd")
+        count_launches(2)
+        return (da.view(ashape), (db.view(bshape) if b2s is not None else None)) + (None,) * 12
+
+
+def attention(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p=0.0, seed=0, site=0):
+    return AttnFn.apply(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p, seed, site)
+
+
+# ---------------------------------------------------------------------- BERT scoring + masked cross-entropy
+class ScoreCEFn(torch.autograd.Function):
+    """loss = mean over labels != 0 of (logsumexp(h.w^T + b) - target logit); logits never materialised (K15-K16)."""
+
+    @staticmethod
+    def forward(ctx, hidden, labels, w, bias):
+        lib = L.load()
+        L.require_cuda(hidden, labels, w, bias)
+        h2 = _rows2d(hidden).contiguous()
+        n, d = h2.shape
+        V1 = w.shape[0]
+        labels = labels.reshape(-1).contiguous()
+        dev = hidden.device
+        rows = torch.empty(n, device=dev, dtype=torch.int32)
+        tgt = torch.empty(n, device=dev, dtype=torch.int64)
+        count = torch.empty(1, device=dev, dtype=torch.int32)
+        nb = lib.rbm_compact_ws_bytes(n)
+        ws = _ws("compact", nb, dev)
+        check(lib.rbm_compact_labels(ptr(labels), n, ptr(rows), ptr(tgt), ptr(count), ptr(ws), nb, stream()), "compact_labels")
+        lse = torch.empty(n, device=dev, dtype=torch.float32)
+        loss = torch.empty((), device=dev, dtype=torch.float32)
+        nb = lib.rbm_ce_ws_bytes(n, V1, d)
+        ws = _ws("ce", nb, dev)
+        w = w.contiguous()
+        check(lib.rbm_ce_fwd(ptr(h2), ptr(rows), ptr(tgt), ptr(count), ptr(w), ptr(bias), ptr(lse), ptr(loss), n, V1, d, ptr(ws),
+                             nb, stream()), "ce_fwd")
+        count_launches(5)
+        ctx.save_for_backward(h2, rows, tgt, count, w, bias, lse)
+        ctx.shape = hidden.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = L.load()
+        h2, rows, tgt, count, w, bias, lse = ctx.saved_tensors
+        n, d = h2.shape
+        V1 = w.shape[0]
+        dloss = dloss.reshape(1).contiguous().float()
+        dh = torch.zeros_like(h2)
+        dw = torch.empty_like(w)
+        db = torch.empty(V1, device=h2.device, dtype=torch.float32)
+        nb = lib.rbm_ce_ws_bytes(n, V1, d)
+        ws = _ws("ce", nb, h2.device)
+        check(lib.rbm_ce_bwd(ptr(h2), ptr(rows), ptr(tgt), ptr(count), ptr(w), ptr(bias), ptr(lse), ptr(dloss), ptr(dh), ptr(dw),
+                             ptr(db), n, V1, d, ptr(ws), nb, stream()), "ce_bwd")
+        count_launches(4)
+        return dh.view(ctx.shape), None, dw, db
+
+
+def score_cross_entropy(hidden, labels, w, bias):
+    return ScoreCEFn.apply(hidden, labels, w, bias)
+
+
+# ------------------------------------------------------------------------------------ SASRec scoring + BCE
+class SasScoreFn(torch.autograd.Function):
+    """pos/neg logits = <f, table[pos]> / <f, table[neg]>   (K13)."""
+
+    @staticmethod
+    def forward(ctx, f, table, pos, neg):
+        lib = L.load()
+        L.require_cuda(f, table, pos, neg)
+        f2 = _rows2d(f).contiguous()
+        rows, d = f2.shape
+        pos = pos.reshape(-1).contiguous()
+        neg = neg.reshape(-1).contiguous()
+        pl = torch.empty(rows, device=f.device, dtype=torch.float32)
+        nl = torch.empty(rows, device=f.device, dtype=torch.float32)
+        check(lib.rbm_sas_score_fwd(ptr(f2), ptr(table), ptr(pos), ptr(neg), ptr(pl), ptr(nl), rows, d, stream()), "sas_score_fwd")
+        count_launches()
+        ctx.save_for_backward(f2, table, pos, neg)
+        ctx.shape = f.shape
+        return pl.view(f.shape[:-1]), nl.view(f.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, dpl, dnl):
+        lib = L.load()
+        f2, table, pos, neg = ctx.saved_tensors
+        rows, d = f2.shape
+        dpl = dpl.reshape(-1).contiguous()
+        dnl = dnl.reshape(-1).contiguous()
+        df = torch.empty_like(f2)
+        check(lib.rbm_sas_score_bwd(ptr(table), ptr(pos), ptr(neg), ptr(dpl), ptr(dnl), ptr(df), rows, d, stream()), "sas_score_bwd")
+        count_launches()
+        dtable = torch.zeros_like(table)
+        scatter_add_sorted_(dtable, pos, f2, dpl, 1.0, padding_idx=0)
+        scatter_add_sorted_(dtable, neg, f2, dnl, 1.0, padding_idx=0)
+        return df.view(ctx.shape), dtable, None, None
+
+
+def sas_scores(f, table, pos, neg):
+    return SasScoreFn.apply(f, table, pos, neg)
+
+
+class BcePairFn(torch.autograd.Function):
+    """mean_{pos!=0} BCEWithLogits(pl, 1) + mean_{pos!=0} BCEWithLogits(nl, 0)   (K14)."""
+
+    @staticmethod
+    def forward(ctx, pl, nl, pos):
+        lib = L.load()
+        L.require_cuda(pl, nl, pos)
+        plc, nlc, posc = pl.reshape(-1).contiguous(), nl.reshape(-1).contiguous(), pos.reshape(-1).contiguous()
+        rows = plc.numel()
+        loss = torch.empty((), device=pl.device, dtype=torch.float32)
+        count = torch.empty(1, device=pl.device, dtype=torch.int32)
+        nb = lib.rbm_bce_ws_bytes(rows)
+        ws = _ws("bce", nb, pl.device)
+        check(lib.rbm_bce_pair_fwd(ptr(plc), ptr(nlc), ptr(posc), ptr(loss), ptr(count), rows, ptr(ws), nb, stream()), "bce_pair_fwd")
+        count_launches(2)
+        ctx.save_for_backward(plc, nlc, posc, count)
+        ctx.shape = pl.shape
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        lib = L.load()
+        plc, nlc, posc, count = ctx.saved_tensors
+        dloss = dloss.reshape(1).contiguous().float()
+        dpl = torch.empty_like(plc)
+        dnl = torch.empty_like(nlc)
+        check(lib.rbm_bce_pair_bwd(ptr(plc), ptr(nlc), ptr(posc), ptr(count), ptr(dloss), ptr(dpl), ptr(dnl), plc.numel(), stream()),
+              "bce_pair_bwd")
+        count_launches()
+        return dpl.view(ctx.shape), dnl.view(ctx.shape), None
+
+
+def bce_pair_loss(pl, nl, pos):
+    return BcePairFn.apply(pl, nl, pos)
+
+
+# ------------------------------------------------------------------------------------- evaluation kernels
+def candidate_scores(f, table, bias, cand):
+    """out[u,c] = <table[cand[u,c]], f[u]> (+bias)  -- sampled-candidate evaluation (K19 with C=101)."""
+    lib = L.load()
+    L.require_cuda(f, table, cand)
+    f2 = _rows2d(f)
+    cand = cand.contiguous()
+    U, Cn = cand.shape
+    out = torch.empty(U, Cn, device=f.device, dtype=torch.float32)
+    check(lib.rbm_candidate_scores(ptr(f2), f2.stride(0), ptr(table), ptr(bias), ptr(cand), ptr(out), U, Cn, table.shape[1], stream()),
+          "candidate_scores")
+    count_launches()
+    return out
+
+
+def score_topk(f, table, bias, v_begin, v_end, k, id_offset=0):
+    """Fused full-catalogue scoring + top-k over table rows [v_begin, v_end)  (K19-K21)."""
+    lib = L.load()
+    L.require_cuda(f, table)
+    f2 = _rows2d(f)
+    U, d = f2.shape
+    vals = torch.empty(U, k, device=f.device, dtype=torch.float32)
+    ids = torch.empty(U, k, device=f.device, dtype=torch.int64)
+    nb = lib.rbm_score_topk_ws_bytes(U, v_end - v_begin, k)
+    ws = _ws("topk", nb, f.device)
+    check(lib.rbm_score_topk(ptr(f2), f2.stride(0), ptr(table), ptr(bias), v_begin, v_end, id_offset, ptr(vals), ptr(ids), U, d, k,
+                             ptr(ws), nb, stream()), "score_topk")
+    count_launches(2)
+    return vals, ids
+
+
+def topk_rows(scores, k, id_offset=0):
+    lib = L.load()
+    L.require_cuda(scores)
+    s2 = _rows2d(scores)
+    U, Cn = s2.shape
+    vals = torch.empty(U, k, device=scores.device, dtype=torch.float32)
+    ids = torch.empty(U, k, device=scores.device, dtype=torch.int64)
+    check(lib.rbm_topk_rows(ptr(s2), s2.stride(0), ptr(vals), ptr(ids), U, Cn, k, id_offset, stream()), "topk_rows")
+    count_launches()
+    return vals, ids
+
+
+def topk_merge(vals, ids):
+    """[S,U,k] per-shard lists -> [U,k]."""
+    lib = L.load()
+    L.require_cuda(vals, ids)
+    S, U, k = vals.shape
+    vals, ids = vals.contiguous(), ids.contiguous()
+    ov = torch.empty(U, k, device=vals.device, dtype=torch.float32)
+    oi = torch.empty(U, k, device=vals.device, dtype=torch.int64)
+    check(lib.rbm_topk_merge(ptr(vals), ptr(ids), ptr(ov), ptr(oi), S, U, k, stream()), "topk_merge")
+    count_launches()
+    return ov, oi
+
+
+_weight_cache = {}
+
+
+def _rank_weights(K, device):
+    """1/log2(t+2) and 1/(t+1) tables, computed by torch on the CPU exactly as NN/trainers/utils.py:43-44,51-52."""
+    key = (K, str(device))
+    if key not in _weight_cache:
+        w_ndcg = 1 / torch.log2(torch.arange(2, 2 + K).float())
+        w_mrr = 1 / torch.arange(1, K + 1).float()
+        _weight_cache[key] = (w_ndcg.to(device), w_mrr.to(device))
+    return _weight_cache[key]
+
+
+def rank_metrics(top_ids, ks, labels=None, positives=None, id_offset=0):
+    """per-user [U, len(ks), 3] = (Recall@k, NDCG@k, MRR@k)   (K22)."""
+    lib = L.load()
+    L.require_cuda(top_ids)
+    U, K = top_ids.shape
+    ks = [int(k) for k in ks]
+    w_ndcg, w_mrr = _rank_weights(K, top_ids.device)
+    per_user = torch.empty(U, len(ks), 3, device=top_ids.device, dtype=torch.float32)
+    ks_arr = (C.c_int32 * len(ks))(*ks)
+    Cn = labels.shape[1] if labels is not None else 0
+    if labels is not None:
+        labels = labels.contiguous()
+    if positives is not None:
+        positives = positives.contiguous()
+    check(lib.rbm_rank_metrics(ptr(top_ids.contiguous()), ptr(labels), ptr(positives), ptr(w_ndcg), ptr(w_mrr),
+                               C.cast(ks_arr, C.c_void_p), len(ks), ptr(per_user), U, K, Cn, id_offset, stream()), "rank_metrics")
+    count_launches()
+    return per_user
+
+
+def column_mean(x):
+    lib = L.load()
+    L.require_cuda(x)
+    x2 = x.reshape(x.shape[0], -1).contiguous()
+    U, cols = x2.shape
+    out = torch.empty(cols, device=x.device, dtype=torch.float32)
+    nb = lib.rbm_column_mean_ws_bytes(U, cols)
+    ws = _ws("colmean", nb, x.device)
+    check(lib.rbm_column_mean(ptr(x2), ptr(out), U, cols, ptr(ws), nb, stream()), "column_mean")
+    count_launches(2)
+    return out
+
+
+def dropout_mask(n, p, seed, site, device):
+    """Debug/test: the keep mask an elementwise dropout site uses."""
+    lib = L.load()
+    out = torch.empty(n, device=device, dtype=torch.uint8)
+    check(lib.rbm_dropout_mask(ptr(out), n, float(p), seed, site, stream()), "dropout_mask")
+    return out
+
+
+def dropout_mask_attn(rows, Ln, p, seed, site, device):
+    lib = L.load()
+    out = torch.empty(rows, Ln, device=device, dtype=torch.uint8)
+    check(lib.rbm_dropout_mask_attn(ptr(out), rows, Ln, float(p), seed, site, stream()), "dropout_mask_attn")
+    return out

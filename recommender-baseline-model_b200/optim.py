@@ -1,0 +1,73 @@
+"""FusedAdam -- ``torch.optim.Adam`` semantics (NN/trainers/base.py:225-233: default betas, eps 1e-8, dense update of
+EVERY parameter incl. whole item tables) as ONE multi-tensor kernel launch per step (rbm_adam_multi).
+
+State layout (``state[p] = {step, exp_avg, exp_avg_sq}``) and ``param_groups`` match torch's Adam, so ``StepLR``
+(NN/trainers/base.py:40), ``get_lr`` (:95-97) and checkpoint dicts (:255-259) work unchanged."""
+from __future__ import annotations
+
+import torch
+
+from . import lib as L
+from .lib import check, ptr, stream, count_launches
+
+
+class FusedAdam(torch.optim.Optimizer):
+    def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8, weight_decay=0.0):
+        if lr < 0 or eps < 0 or not 0 <= betas[0] < 1 or not 0 <= betas[1] < 1 or weight_decay < 0:
+            raise ValueError("invalid Adam hyper-parameter")
+        super().__init__(params, dict(lr=lr, betas=betas, eps=eps, weight_decay=weight_decay))
+        self._table_cache = {}
+
+    def zero_grad(self, set_to_none: bool = True):
+        super().zero_grad(set_to_none=set_to_none)
+
+    @staticmethod
+    def _chunk_map(sizes, device):
+        rows = []
+        for ti, n in enumerate(sizes):
+            for ci in range((n + L.ADAM_CHUNK - 1) // L.ADAM_CHUNK):
+                rows.append((ti, ci))
+        return torch.tensor(rows, dtype=torch.int32).reshape(-1, 2).to(device)
+
+    @torch.no_grad()
+    def step(self, closure=None):
+        loss = closure() if closure is not None else None
+        lib = L.load()
+        for gi, group in enumerate(self.param_groups):
+            plist = [p for p in group["params"] if p.grad is not None]
+            if not plist:
+                continue
+            L.require_cuda(*plist)
+            dev = plist[0].device
+            steps = set()
+            table = []
+            for p in plist:
+                if p.dtype != torch.float32 or p.grad.dtype != torch.float32 or p.grad.is_sparse:
+                    raise RuntimeError("FusedAdam handles dense fp32 parameters only")
+                if not p.is_contiguous():
+                    raise RuntimeError("FusedAdam needs contiguous parameters")
+                st = self.state[p]
+                if len(st) == 0:
+                    st["step"] = torch.tensor(0.0)
+                    st["exp_avg"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                    st["exp_avg_sq"] = torch.zeros_like(p, memory_format=torch.preserve_format)
+                st["step"] += 1
+                steps.add(int(st["step"]))
+                g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
+                if g is not p.grad:
+                    p.grad = g
+                table.append((p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), p.numel()))
+            if len(steps) != 1:
+                raise RuntimeError("FusedAdam: parameters of one group must share their step count")
+            sizes = tuple(t[4] for t in table)
+            key = (gi, sizes, str(dev))
+            cmap = self._table_cache.get(key)
+            if cmap is None:
+                cmap = self._chunk_map(sizes, dev)
+                self._table_cache = {key: cmap}
+            desc = torch.tensor(table, dtype=torch.int64).to(dev)  # rbm_adam_tensor[] : 5 x 8-byte fields
+            b1, b2 = group["betas"]
+            check(lib.rbm_adam_multi(ptr(desc), ptr(cmap), cmap.shape[0], float(group["lr"]), float(b1), float(b2),
+                                     float(group["eps"]), float(group["weight_decay"]), steps.pop(), stream()), "adam_multi")
+            count_launches()
+        return loss

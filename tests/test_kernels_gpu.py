@@ -1,0 +1,371 @@
+"""Kernel-level parity: every C-ABI entry point vs the CPU oracle on seeded inputs (run with -m gpu on a B200)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+import rbm_b200
+from rbm_b200 import ops, lib as L
+from oracle import common as oc, metrics as om, optim as oo
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def g(x):
+    return x.to(DEV)
+
+
+def close(a, b, rtol=1e-4, atol=1e-5, msg=""):
+    np.testing.assert_allclose(a.detach().cpu().numpy(), b.detach().cpu().numpy(), rtol=rtol, atol=atol, err_msg=msg)
+
+
+# ------------------------------------------------------------------------------------------- embedding
+@pytest.mark.parametrize("zero_pad,scale", [(1, 8.0), (0, 1.0)])
+@pytest.mark.parametrize("p", [0.0, 0.25])
+def test_embed_fwd_bwd(zero_pad, scale, p):
+    torch.manual_seed(0)
+    B, Ln, d, V = 5, 12, 32, 41
+    tok = torch.randint(0, V, (B, Ln))
+    tok[0, :4] = 0
+    table = torch.randn(V, d)
+    pos = torch.randn(Ln, d)
+    dout = torch.randn(B, Ln, d)
+    seed, site = 1234, 7
+    tg, pg = g(table).requires_grad_(True), g(pos).requires_grad_(True)
+    out = ops.EmbedFn.apply(g(tok), tg, pg, scale, zero_pad, p, seed, site)
+    out.backward(g(dout))
+    mask = ops.dropout_mask(B * Ln * d, p, seed, site, DEV).cpu().view(B, Ln, d) if p > 0 else None
+    tr, pr = table.clone().requires_grad_(True), pos.clone().requires_grad_(True)
+    ref = F.embedding(tok, tr, padding_idx=0) * scale + pr.unsqueeze(0)
+    if p > 0:
+        assert abs(mask.float().mean().item() - (1 - p)) < 0.03
+        ref = ref * mask * (1.0 / (1.0 - p))
+    if zero_pad:
+        ref = ref * (tok != 0).unsqueeze(-1)
+    ref.backward(dout)
+    close(out, ref, 1e-6, 1e-6)
+    close(pg.grad, pr.grad, 1e-5, 1e-5)
+    close(tg.grad, tr.grad, 1e-5, 1e-5)
+
+
+def test_embed_bad_shapes_raise():
+    with pytest.raises(RuntimeError):
+        ops.EmbedFn.apply(g(torch.zeros(2, 4, dtype=torch.long)), g(torch.randn(5, 6)), g(torch.randn(4, 6)), 1.0, 0, 0.0, 0, 0)
+    with pytest.raises(RuntimeError):  # CPU tensors are refused: there is no fallback
+        ops.EmbedFn.apply(torch.zeros(2, 4, dtype=torch.long), torch.randn(5, 8), torch.randn(4, 8), 1.0, 0, 0.0, 0, 0)
+
+
+# ------------------------------------------------------------------------------------------ scatter-add
+@pytest.mark.parametrize("n,V,d", [(400, 53, 16), (5000, 3418, 64), (70000, 12102, 128), (3, 300000, 8)])
+def test_scatter_add_bit_exact(n, V, d):
+    rng = np.random.RandomState(n)
+    idx = (rng.zipf(1.2, size=n) % V).astype(np.int64)
+    rows = rng.randn(n, d).astype(np.float32)
+    coef = rng.randn(n).astype(np.float32)
+    ref = oc.embedding_grad_scatter_fast(idx, rows, V, padding_idx=0)
+    grad = torch.zeros(V, d, device=DEV)
+    ops.scatter_add_sorted_(grad, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), None, 1.0, 0)
+    np.testing.assert_array_equal(grad.cpu().numpy(), ref)  # bit-exact, run-to-run and vs the CPU order
+    grad2 = torch.zeros(V, d, device=DEV)
+    ops.scatter_add_sorted_(grad2, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), None, 1.0, 0)
+    assert torch.equal(grad, grad2)
+    ref_c = oc.embedding_grad_scatter_fast(idx, rows * coef[:, None], V, padding_idx=0)
+    grad3 = torch.zeros(V, d, device=DEV)
+    ops.scatter_add_sorted_(grad3, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), g(torch.from_numpy(coef)), 1.0, 0)
+    np.testing.assert_array_equal(grad3.cpu().numpy(), ref_c)
+    assert grad.cpu()[0].abs().sum() == 0  # padding row untouched
+
+
+def test_scatter_golden():
+    z = np.load("tests/golden/scatter_adam.npz")
+    grad = torch.zeros(53, 16, device=DEV)
+    ops.scatter_add_sorted_(grad, g(torch.from_numpy(z["scatter.idx"])), g(torch.from_numpy(z["scatter.rows"])), None, 1.0, 0)
+    np.testing.assert_array_equal(grad.cpu().numpy(), z["scatter.grad"])
+
+
+# -------------------------------------------------------------------------------------------- layernorm
+@pytest.mark.parametrize("flavour", [L.LN_TORCH, L.LN_BERT])
+@pytest.mark.parametrize("rows,d", [(7, 16), (33, 32), (1000, 64), (129, 128), (65, 256), (9, 512)])
+def test_layernorm(flavour, rows, d):
+    torch.manual_seed(rows + d)
+    x = torch.randn(rows, d) * 2 + 0.5
+    w, b = torch.randn(d), torch.randn(d)
+    dy = torch.randn(rows, d)
+    eps = 1e-8 if flavour == L.LN_TORCH else 1e-6
+    xg, wg, bg = (g(t).requires_grad_(True) for t in (x, w, b))
+    y = ops.layernorm(xg, wg, bg, eps, flavour)
+    y.backward(g(dy))
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    ref = oc.torch_layernorm(xr, wr, br, eps) if flavour == L.LN_TORCH else oc.bert_layernorm(xr, wr, br, eps)
+    ref.backward(dy)
+    close(y, ref, 1e-5, 1e-5)
+    close(xg.grad, xr.grad, 1e-4, 1e-5)
+    close(wg.grad, wr.grad, 1e-4, 1e-4)
+    close(bg.grad, br.grad, 1e-4, 1e-4)
+
+
+# ----------------------------------------------------------------------------------------------- linear
+def _ref_act(x, act):
+    return {L.ACT_NONE: lambda t: t, L.ACT_RELU: torch.relu, L.ACT_GELU_TANH: oc.gelu_tanh}[act](x)
+
+
+@pytest.mark.parametrize("M,N,K", [(10, 16, 16), (300, 192, 64), (257, 64, 256), (1000, 256, 64), (131, 48, 32)])
+@pytest.mark.parametrize("act,res,rowtok,pA,pB", [(L.ACT_NONE, False, False, 0.0, 0.0), (L.ACT_GELU_TANH, False, False, 0.2, 0.0),
+                                                  (L.ACT_NONE, True, False, 0.1, 0.3), (L.ACT_RELU, False, False, 0.2, 0.0),
+                                                  (L.ACT_NONE, True, True, 0.2, 0.0)])
+def test_linear(M, N, K, act, res, rowtok, pA, pB):
+    torch.manual_seed(M + N)
+    x, w, b = torch.randn(M, K), torch.randn(N, K) * 0.2, torch.randn(N)
+    r = torch.randn(M, N) if res else None
+    tok = (torch.rand(M) > 0.3).long() if rowtok else None
+    dy = torch.randn(M, N)
+    seed, sA, sB = 99, 3, 4
+    xg, wg, bg = (g(t).requires_grad_(True) for t in (x, w, b))
+    rg = g(r).requires_grad_(True) if res else None
+    y = ops.linear(xg, wg, bg, residual=rg, row_tok=g(tok) if rowtok else None, act=act, pA=pA, siteA=sA, pB=pB, siteB=sB, seed=seed)
+    y.backward(g(dy))
+    xr, wr, br = (t.clone().requires_grad_(True) for t in (x, w, b))
+    rr = r.clone().requires_grad_(True) if res else None
+    ref = _ref_act(F.linear(xr, wr, br), act)
+    if pA > 0:
+        ref = ref * ops.dropout_mask(M * N, pA, seed, sA, DEV).cpu().view(M, N) / (1 - pA)
+    if res:
+        ref = ref + rr
+    if pB > 0:
+        ref = ref * ops.dropout_mask(M * N, pB, seed, sB, DEV).cpu().view(M, N) / (1 - pB)
+    if rowtok:
+        ref = ref * (tok != 0).unsqueeze(-1)
+    ref.backward(dy)
+    close(y, ref, 1e-4, 1e-4)
+    close(xg.grad, xr.grad, 1e-4, 1e-4)
+    close(wg.grad, wr.grad, 1e-4, 1e-3)
+    close(bg.grad, br.grad, 1e-4, 1e-3)
+    if res:
+        close(rg.grad, rr.grad, 1e-5, 1e-5)
+
+
+def test_linear_strided_input():
+    """q/k/v column blocks of a packed tensor are consumed through their row stride."""
+    torch.manual_seed(1)
+    big = torch.randn(50, 96)
+    w = torch.randn(16, 32)
+    y = ops.linear(g(big)[:, 32:64], g(w))
+    close(y, F.linear(big[:, 32:64], w), 1e-4, 1e-4)
+
+
+# -------------------------------------------------------------------------------------------- attention
+def _ref_attention(q, k, v, tok, mode, scale, p, mask):
+    s = torch.matmul(q, k.transpose(-2, -1)) * scale
+    Ln = q.shape[-2]
+    if mode == L.MASK_CAUSAL:
+        s = s.masked_fill(~torch.tril(torch.ones(Ln, Ln, dtype=torch.bool)), float("-inf"))
+    elif mode == L.MASK_KEYPAD:
+        s = s.masked_fill((tok == 0)[:, None, None, :], -1e9)
+    pr = F.softmax(s, dim=-1)
+    if p > 0:
+        pr = pr * mask / (1 - p)
+    return torch.matmul(pr, v)
+
+
+@pytest.mark.parametrize("B,Ln,h,dk", [(3, 8, 2, 8), (2, 13, 4, 8), (4, 50, 1, 64), (3, 50, 2, 64), (2, 200, 2, 32), (2, 200, 4, 64), (1, 256, 1, 16), (2, 100, 2, 128)])
+@pytest.mark.parametrize("mode", [L.MASK_CAUSAL, L.MASK_KEYPAD])
+@pytest.mark.parametrize("p", [0.0, 0.2])
+def test_attention_packed(B, Ln, h, dk, mode, p):
+    torch.manual_seed(B * Ln + dk)
+    d = h * dk
+    qkv = torch.randn(B * Ln, 3 * d)
+    tok = torch.randint(1, 50, (B, Ln))
+    tok[0, : Ln // 3] = 0
+    if B > 1:
+        tok[1, :] = 0  # a fully padded sequence: softmax over -1e9 everywhere must stay finite/uniform
+        tok[1, -1] = 5 if mode == L.MASK_CAUSAL else 0
+    dout = torch.randn(B * Ln, d)
+    scale = 1 / math.sqrt(dk)
+    seed, site = 5, 11
+    qg = g(qkv).requires_grad_(True)
+    out = ops.attention(qg, None, g(tok), B, Ln, h, 0, d, 2 * d, mode, scale, p, seed, site)
+    out.backward(g(dout))
+    mask = ops.dropout_mask_attn(B * h * Ln, Ln, p, seed, site, DEV).cpu().view(B, h, Ln, Ln) if p > 0 else None
+    if p > 0:
+        assert abs(mask.float().mean().item() - (1 - p)) < 0.02
+    qr = qkv.clone().requires_grad_(True)
+    q, k, v = (qr[:, i * d:(i + 1) * d].view(B, Ln, h, dk).transpose(1, 2) for i in range(3))
+    ref = _ref_attention(q, k, v, tok, mode, scale, p, mask).transpose(1, 2).reshape(B * Ln, d)
+    ref.backward(dout)
+    close(out, ref, 1e-4, 1e-5)
+    close(qg.grad, qr.grad, 1e-3, 2e-5)
+
+
+def test_attention_split_sources_and_bad_shapes():
+    torch.manual_seed(0)
+    B, Ln, h, dk = 2, 20, 2, 16
+    d = h * dk
+    q, kv = torch.randn(B * Ln, d), torch.randn(B * Ln, 2 * d)
+    dout = torch.randn(B * Ln, d)
+    qg, kvg = g(q).requires_grad_(True), g(kv).requires_grad_(True)
+    out = ops.attention(qg, kvg, None, B, Ln, h, 0, 0, d, L.MASK_CAUSAL, 0.25)
+    out.backward(g(dout))
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    sp = lambda t: t.view(B, Ln, h, dk).transpose(1, 2)
+    ref = _ref_attention(sp(qr), sp(kvr[:, :d]), sp(kvr[:, d:]), None, L.MASK_CAUSAL, 0.25, 0.0, None).transpose(1, 2).reshape(B * Ln, d)
+    ref.backward(dout)
+    close(out, ref, 1e-4, 1e-5)
+    close(qg.grad, qr.grad, 1e-3, 2e-5)
+    close(kvg.grad, kvr.grad, 1e-3, 2e-5)
+    with pytest.raises(RuntimeError):  # L > 256 is unsupported and must say so
+        ops.attention(g(torch.randn(300, 48)), None, None, 1, 300, 1, 0, 16, 32, L.MASK_CAUSAL, 1.0)
+
+
+# ----------------------------------------------------------------------------------- scoring + cross-entropy
+@pytest.mark.parametrize("n,V1,d,frac", [(40, 38, 16, 0.5), (500, 3417, 64, 0.15), (300, 1001, 128, 0.3), (130, 777, 256, 0.9), (64, 65, 32, 0.0)])
+def test_score_ce(n, V1, d, frac):
+    torch.manual_seed(n)
+    h = torch.randn(n, d)
+    w, b = torch.randn(V1, d) * 0.3, torch.randn(V1)
+    labels = torch.where(torch.rand(n) < frac, torch.randint(1, V1, (n,)), torch.zeros(n, dtype=torch.long))
+    if frac == 0.0:
+        labels[5] = V1 - 1  # exactly one scored row, last vocabulary id
+    hg, wg, bg = (g(t).requires_grad_(True) for t in (h, w, b))
+    loss = ops.score_cross_entropy(hg, g(labels), wg, bg)
+    (loss * 1.7).backward()
+    hr, wr, br = (t.clone().requires_grad_(True) for t in (h, w, b))
+    ref = F.cross_entropy(F.linear(hr, wr, br), labels, ignore_index=0)
+    (ref * 1.7).backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    close(hg.grad, hr.grad, 1e-3, 1e-6)
+    close(wg.grad, wr.grad, 1e-3, 1e-6)
+    close(bg.grad, br.grad, 1e-3, 1e-6)
+
+
+# -------------------------------------------------------------------------------------- SAS scoring + BCE
+@pytest.mark.parametrize("rows,d,V", [(30, 16, 20), (1000, 64, 3417), (640, 128, 12102)])
+def test_sas_score_bce(rows, d, V):
+    torch.manual_seed(rows)
+    f, table = torch.randn(rows, d), torch.randn(V, d) * 0.3
+    table[0] = 0
+    pos = torch.randint(0, V, (rows,))
+    pos[::3] = 0
+    neg = torch.randint(0, V, (rows,))
+    fg, tg = g(f).requires_grad_(True), g(table).requires_grad_(True)
+    pl, nl = ops.sas_scores(fg, tg, g(pos), g(neg))
+    loss = ops.bce_pair_loss(pl, nl, g(pos))
+    loss.backward()
+    fr, tr = f.clone().requires_grad_(True), table.clone().requires_grad_(True)
+    plr = (fr * F.embedding(pos, tr, padding_idx=0)).sum(-1)
+    nlr = (fr * F.embedding(neg, tr, padding_idx=0)).sum(-1)
+    idx = pos != 0
+    ref = F.binary_cross_entropy_with_logits(plr[idx], torch.ones(int(idx.sum()))) + \
+        F.binary_cross_entropy_with_logits(nlr[idx], torch.zeros(int(idx.sum())))
+    ref.backward()
+    close(pl, plr, 1e-4, 1e-5)
+    close(nl, nlr, 1e-4, 1e-5)
+    assert abs(loss.item() - ref.item()) < 1e-5 * max(1.0, abs(ref.item()))
+    close(fg.grad, fr.grad, 1e-4, 1e-7)
+    close(tg.grad, tr.grad, 1e-4, 1e-7)
+
+
+def test_candidate_scores():
+    torch.manual_seed(0)
+    U, Cn, d, V = 9, 101, 64, 500
+    f3 = torch.randn(U, 7, d)
+    table, bias = torch.randn(V, d), torch.randn(V)
+    cand = torch.randint(0, V, (U, Cn))
+    out = ops.candidate_scores(g(f3)[:, -1, :], g(table), g(bias), g(cand))
+    ref = torch.einsum("ucd,ud->uc", table[cand], f3[:, -1, :]) + bias[cand]
+    close(out, ref, 1e-4, 1e-5)
+
+
+# ------------------------------------------------------------------------------------------------ top-k
+@pytest.mark.parametrize("U,Cn,k", [(5, 101, 10), (17, 3416, 10), (3, 40, 20), (4, 7, 10), (2, 100000, 32)])
+def test_topk_rows_bit_exact_with_ties(U, Cn, k):
+    rng = np.random.RandomState(U * Cn)
+    scores = rng.randn(U, Cn).astype(np.float32)
+    scores[:, Cn // 2:] = np.round(scores[:, Cn // 2:], 1)  # plenty of exact ties
+    scores[0, :] = 1.0  # all tied: ids must come out ascending
+    ref_v, ref_i = om.topk_canonical(scores, k, id_offset=3)
+    v, i = ops.topk_rows(g(torch.from_numpy(scores)), k, id_offset=3)
+    np.testing.assert_array_equal(i.cpu().numpy(), ref_i)
+    np.testing.assert_array_equal(v.cpu().numpy(), ref_v)
+
+
+@pytest.mark.parametrize("U,V,d,k,bias", [(10, 300, 16, 10, False), (70, 3416, 64, 10, True), (130, 12101, 128, 10, False), (64, 5000, 256, 20, True)])
+def test_score_topk_fused(U, V, d, k, bias):
+    torch.manual_seed(U + V)
+    f, table = torch.randn(U, d), torch.randn(V + 1, d)
+    b = torch.randn(V + 1) if bias else None
+    vals, ids = ops.score_topk(g(f), g(table), g(b) if bias else None, 1, V + 1, k)
+    # score parity, then selection parity on the kernel's own scores (fp32 sum order differs from torch's matmul)
+    sc = f @ table[1:].t() + (b[1:] if bias else 0)
+    gathered = torch.gather(sc, 1, ids.cpu() - 1)
+    close(vals, gathered, 1e-4, 1e-4)
+    ref_v, ref_i = om.topk_canonical(sc.numpy(), k, id_offset=1)
+    kth_gap = ref_v[:, -1] - np.sort(sc.numpy(), 1)[:, -(k + 1)]
+    safe = kth_gap > 1e-3
+    assert safe.mean() > 0.8
+    # same SET where the k-th/(k+1)-th gap exceeds the fp tolerance; same ORDER where neighbouring gaps do too
+    for u in np.flatnonzero(safe):
+        assert set(ids[u].tolist()) == set(ref_i[u].tolist())
+    well_sep = safe & (np.min(-np.diff(ref_v, axis=1), axis=1) > 1e-3)
+    np.testing.assert_array_equal(ids.cpu().numpy()[well_sep], ref_i[well_sep])
+
+
+def test_topk_merge_shard_invariance():
+    rng = np.random.RandomState(3)
+    U, V, k = 33, 4000, 10
+    scores = np.round(rng.randn(U, V).astype(np.float32), 2)  # ties across shards
+    ref_v, ref_i = om.topk_canonical(scores, k, id_offset=1)
+    sg = g(torch.from_numpy(scores))
+    for S in (1, 2, 3, 8):
+        bounds = np.linspace(0, V, S + 1).astype(int)
+        parts = [ops.topk_rows(sg[:, a:b2], k, id_offset=1 + int(a)) for a, b2 in zip(bounds[:-1], bounds[1:])]
+        v, i = ops.topk_merge(torch.stack([p[0] for p in parts]), torch.stack([p[1] for p in parts]))
+        np.testing.assert_array_equal(i.cpu().numpy(), ref_i)
+        np.testing.assert_array_equal(v.cpu().numpy(), ref_v)
+
+
+def test_metrics_match_reference_golden():
+    z = np.load("tests/golden/metrics.npz")
+    for tag, ks in (("c101", [1, 5, 10, 20]), ("c3416", [1, 5, 10, 20]), ("multi", [1, 5, 10])):
+        scores, labels = torch.from_numpy(z[tag + ".scores"]), torch.from_numpy(z[tag + ".labels"])
+        m = rbm_b200.recalls_ndcgs_and_mrr_for_ks(g(scores), g(labels), ks)
+        keys = [str(k) for k in z[tag + ".keys"]]
+        assert sorted(m.keys()) == keys
+        got = np.array([m[k] for k in keys])
+        np.testing.assert_allclose(got, z[tag + ".vals"], rtol=2e-6, atol=1e-7)
+        if tag != "multi":  # per-user values and HR are bit-exact
+            _, ids = ops.topk_rows(g(scores), 20)
+            np.testing.assert_array_equal(ids.cpu().numpy(), z[tag + ".rank20"])
+            pu = ops.rank_metrics(ids, [20, 10, 5, 1], labels=g(labels)).cpu().numpy()
+            ref = om.recalls_ndcgs_and_mrr_for_ks(scores, labels, ks, per_user=True)
+            for j, k in enumerate([20, 10, 5, 1]):
+                np.testing.assert_array_equal(pu[:, j, 0], ref["Recall@%d" % k].numpy())
+                np.testing.assert_array_equal(pu[:, j, 1], ref["NDCG@%d" % k].numpy())
+                np.testing.assert_array_equal(pu[:, j, 2], ref["MRR@%d" % k].numpy())
+            pu2 = ops.rank_metrics(ids, [10], positives=g(torch.zeros(scores.shape[0], dtype=torch.long))).cpu().numpy()
+            np.testing.assert_array_equal(pu2[:, 0, 1], ref["NDCG@10"].numpy())
+
+
+# ------------------------------------------------------------------------------------------------- Adam
+def test_fused_adam_matches_torch_golden():
+    z = np.load("tests/golden/scatter_adam.npz")
+    p = torch.nn.Parameter(g(torch.from_numpy(z["adam.p0"])))
+    odd = torch.nn.Parameter(g(torch.randn(4097 * 3 + 1)))  # multi-chunk, ragged tail
+    odd_ref = odd.detach().cpu().numpy().copy()
+    m_ref, v_ref = np.zeros_like(odd_ref), np.zeros_like(odd_ref)
+    opt = rbm_b200.FusedAdam([p, odd], lr=1e-3)
+    rng = np.random.RandomState(0)
+    for s in range(4):
+        p.grad = g(torch.from_numpy(z["adam.grads"][s].copy()))
+        go = rng.randn(odd_ref.size).astype(np.float32)
+        odd.grad = g(torch.from_numpy(go))
+        opt.step()
+        np.testing.assert_allclose(p.detach().cpu().numpy(), z["adam.ps"][s], rtol=1e-6, atol=1e-7)
+        oo.adam_step(odd_ref, go, m_ref, v_ref, s + 1, 1e-3)
+        np.testing.assert_allclose(odd.detach().cpu().numpy(), odd_ref, rtol=1e-5, atol=1e-7)
+    st = opt.state[p]
+    np.testing.assert_allclose(st["exp_avg"].cpu().numpy(), z["adam.m"], rtol=1e-5, atol=1e-8)
+    np.testing.assert_allclose(st["exp_avg_sq"].cpu().numpy(), z["adam.v"], rtol=1e-5, atol=1e-12)
+    assert set(opt.state_dict()["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}

@@ -1,0 +1,201 @@
+"""Model-level parity against golden vectors minted from the reference (tests/golden/make_golden.py) and the oracle."""
+import os
+from types import SimpleNamespace
+
+import numpy as np
+import pytest
+import torch
+
+import rbm_b200
+from rbm_b200 import ops
+from oracle import bert4rec as ob, sasrec as osr, metrics as om
+
+pytestmark = pytest.mark.gpu
+G = os.path.join(os.path.dirname(__file__), "golden")
+DEV = "cuda"
+
+
+def load(name):
+    z = np.load(os.path.join(G, name + ".npz"))
+    return {k: z[k] for k in z.files}
+
+
+def bert_args(V, Ln, d, nb, h, p=0.0, seed=0):
+    return SimpleNamespace(model_code="bert", num_items=V, max_len=Ln, device=DEV, model_init_seed=seed, bert_num_blocks=nb,
+                           bert_num_heads=h, bert_hidden_units=d, bert_dropout=p, bert_hidden_dropout=p)
+
+
+def sas_args(V, Ln, d, nb, h, p=0.0):
+    return SimpleNamespace(model_code="sas", num_items=V, max_len=Ln, device=DEV, sas_hidden_units=d, sas_num_blocks=nb,
+                           sas_heads=h, sas_dropout=p)
+
+
+def sd_of(z, prefix="sd."):
+    return {k[len(prefix):]: torch.from_numpy(v) for k, v in z.items() if k.startswith(prefix)}
+
+
+def relclose(a, b, rel=1e-3, floor=1e-6, msg=""):
+    a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
+    scale = max(np.abs(b).max(), floor)
+    assert np.abs(a - b).max() <= rel * scale, "%s: max err %g vs scale %g" % (msg, np.abs(a - b).max(), scale)
+
+
+@pytest.mark.parametrize("name", ["bert_tiny", "bert_odd"])
+def test_bert_vs_reference_golden(name):
+    z = load(name)
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, seed=seed))
+    model.load_state_dict(sd_of(z))
+    model.to(DEV).train()
+    t, l = torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"])
+    logits = model(t.to(DEV))
+    assert logits.shape == (B, Ln, V + 1) and logits.is_contiguous()
+    relclose(logits.detach().cpu().numpy(), z["logits"], 1e-4, msg="logits")
+    loss = model.loss(t, l)
+    assert abs(loss.item() - float(z["loss"])) < 1e-5 * abs(float(z["loss"])) + 1e-6
+    loss.backward()
+    for k, p in model.named_parameters():
+        relclose(p.grad.cpu().numpy(), z["grad." + k], 1e-3, msg=k)
+    # the compatibility forward + torch CE gives the same loss and gradients through the same kernels
+    model.zero_grad()
+    lg = model(t.to(DEV))
+    l2 = torch.nn.functional.cross_entropy(lg.view(-1, V + 1), l.to(DEV).view(-1), ignore_index=0)
+    l2.backward()
+    assert abs(l2.item() - float(z["loss"])) < 1e-5 * abs(float(z["loss"])) + 1e-6
+    relclose(model.out.weight.grad.cpu().numpy(), z["grad.out.weight"], 1e-3, msg="out.weight via forward()")
+    # evaluation scoring
+    model.eval()
+    with torch.no_grad():
+        cs = model.candidate_scores(torch.from_numpy(z["eval_tokens"]), torch.from_numpy(z["candidates"]))
+        relclose(cs.cpu().numpy(), z["cand_scores"], 1e-4, msg="cand_scores")
+        vals, ids = model.full_catalogue_topk(torch.from_numpy(z["eval_tokens"]), 10)
+        ref_v, ref_i = om.topk_canonical(z["scores_last"][:, 1:], 10, id_offset=1)
+        relclose(vals.cpu().numpy(), ref_v, 1e-4, msg="topk scores")
+        np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+
+
+def test_bert_adam_trajectory():
+    z = load("bert_tiny")
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    args = bert_args(V, Ln, d, nb, h, seed=seed)
+    args.update = None
+    model = rbm_b200.model_factory(args)
+    model.load_state_dict(sd_of(z))
+    targs = SimpleNamespace(**vars(args), optimizer="Adam", lr=1e-3, weight_decay=0, momentum=None, decay_step=50, gamma=0.95,
+                            num_epochs=1, metric_ks=[1, 5, 10], best_metric="NDCG@10", train_batch_size=B, resume_path=None)
+    trainer = rbm_b200.trainer_factory(targs, model, None, None, None, None)
+    model.train()
+    batch = (torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"]))
+    losses = [trainer.train_step(batch).item() for _ in range(len(z["adam_losses"]))]
+    np.testing.assert_allclose(losses, z["adam_losses"], rtol=1e-4)
+    after = sd_of(z, "sd_after.")
+    for k, v in model.state_dict().items():
+        if k.endswith("linear_layers.1.bias"):
+            continue  # analytically-zero gradient amplified by Adam (see tests/test_oracle_golden.py)
+        relclose(v.cpu().numpy(), after[k].numpy(), 2e-3, msg=k)
+
+
+@pytest.mark.parametrize("name", ["sas_tiny", "sas_odd"])
+def test_sas_vs_reference_golden(name):
+    z = load(name)
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h))
+    model.load_state_dict(sd_of(z))
+    model.to(DEV).train()
+    pl, nl = model(z["seq"], z["pos"], z["neg"])  # numpy in, like the reference
+    relclose(pl.detach().cpu().numpy(), z["pos_logits"], 1e-4, msg="pos_logits")
+    relclose(nl.detach().cpu().numpy(), z["neg_logits"], 1e-4, msg="neg_logits")
+    loss = model.loss(z["seq"], z["pos"], z["neg"])
+    assert abs(loss.item() - float(z["loss"])) < 1e-5 * abs(float(z["loss"])) + 1e-6
+    loss.backward()
+    for k, p in model.named_parameters():
+        relclose(p.grad.cpu().numpy(), z["grad." + k], 1e-3, msg=k)
+    model.eval()
+    with torch.no_grad():
+        relclose(model.predict(z["seq"], z["candidates"]).cpu().numpy(), z["cand_scores"], 1e-4, msg="predict")
+        vals, ids = model.full_catalogue_topk(z["seq"], 10)
+        ref_v, ref_i = om.topk_canonical(z["scores_full"], 10, id_offset=1)
+        relclose(vals.cpu().numpy(), ref_v, 1e-4, msg="topk scores")
+        np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+
+
+def test_sas_adam_trajectory():
+    z = load("sas_tiny")
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    args = sas_args(V, Ln, d, nb, h)
+    model = rbm_b200.model_factory(args)
+    model.load_state_dict(sd_of(z))
+    targs = SimpleNamespace(**vars(args), optimizer="Adam", lr=1e-3, weight_decay=0, momentum=None, decay_step=50, gamma=0.95,
+                            num_epochs=1, metric_ks=[1, 5, 10], best_metric="NDCG@10", train_batch_size=B, resume_path=None, l2_emb=0.0)
+    trainer = rbm_b200.trainer_factory(targs, model, None, None, None, None)
+    model.train()
+    losses = [trainer.train_step((z["seq"], z["pos"], z["neg"])).item() for _ in range(len(z["adam_losses"]))]
+    np.testing.assert_allclose(losses, z["adam_losses"], rtol=1e-4)
+
+
+def test_cfg_shaped_losses():
+    """cfg2-shaped BERT4Rec and cfg1-shaped SASRec batches: loss / grad norms / scores vs the reference goldens."""
+    z = load("bert_cfg2")
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, seed=seed))
+    model.load_state_dict(ob.random_state_dict(V, Ln, d, nb, seed=seed))
+    model.to(DEV).train()
+    loss = model.loss(torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"]))
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    gn = np.array([p.grad.norm().item() for _, p in model.named_parameters()])
+    np.testing.assert_allclose(gn, z["grad_norms"], rtol=2e-3, atol=1e-7)
+    model.eval()
+    with torch.no_grad():
+        vals, ids = model.full_catalogue_topk(torch.from_numpy(z["eval_tokens"]), 10)
+    ref_v, ref_i = om.topk_canonical(z["scores_last"][:, 1:], 10, id_offset=1)
+    relclose(vals.cpu().numpy(), ref_v, 1e-4)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+
+    z = load("sas_cfg1")
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h))
+    model.load_state_dict(osr.random_state_dict(V, Ln, d, nb, seed=seed))
+    model.to(DEV).train()
+    loss = model.loss(z["seq"], z["pos"], z["neg"])
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 1e-4 * abs(float(z["loss"]))
+    gn = np.array([p.grad.norm().item() for _, p in model.named_parameters()])
+    np.testing.assert_allclose(gn, z["grad_norms"], rtol=2e-3, atol=1e-7)
+    model.eval()
+    with torch.no_grad():
+        vals, ids = model.full_catalogue_topk(z["seq"], 10)
+    ref_v, ref_i = om.topk_canonical(z["scores_full"], 10, id_offset=1)
+    relclose(vals.cpu().numpy(), ref_v, 1e-4)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+
+
+def test_training_mode_dropout_against_injected_masks():
+    """Training-mode BERT4Rec: the oracle consumes the Philox masks the kernels used (exported per site)."""
+    from oracle.common import DropoutPlan
+    V, Ln, d, nb, h, B, p = 37, 8, 16, 2, 2, 4, 0.25
+    model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, p=p, seed=1)).to(DEV).train()
+    model.dropout_seed = 4242
+    rng = np.random.RandomState(0)
+    tok = torch.from_numpy(rng.randint(1, V + 2, size=(B, Ln)).astype(np.int64))
+    tok[0, :3] = 0
+    lab = torch.from_numpy(np.where(rng.rand(B, Ln) < 0.4, rng.randint(1, V + 1, size=(B, Ln)), 0).astype(np.int64))
+    step0 = model._step
+    loss = model.loss(tok, lab)
+    loss.backward()
+    base = step0 * 64
+    masks = {0: ops.dropout_mask(B * Ln * d, p, 4242, base, DEV).cpu()}
+    for b in range(nb):
+        s = ob.block_sites(b)
+        masks[s["attn"]] = ops.dropout_mask_attn(B * h * Ln, Ln, p, 4242, base + s["attn"], DEV).cpu()
+        for key, n in (("sub_in", B * Ln * d), ("ffn", B * Ln * 4 * d), ("sub_out", B * Ln * d), ("block", B * Ln * d)):
+            masks[s[key]] = ops.dropout_mask(n, p, 4242, base + s[key], DEV).cpu()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    ref = ob.loss(sd, tok, lab, nb, h, p_attn=p, p_hidden=p, drop=DropoutPlan(True, masks))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item())
+    for k, prm in model.named_parameters():
+        gr = sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])
+        relclose(prm.grad.cpu().numpy(), gr.numpy(), 1e-3, msg=k)
+    # a second forward draws a different mask stream
+    assert model.loss(tok, lab).item() != loss.item()
