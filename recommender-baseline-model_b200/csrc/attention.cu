@@ -261,7 +261,8 @@ __global__ void __launch_bounds__(32 * WARPS, 1) attn_bwd_dq_kernel(AttnArgs a) 
             float p = (i >= L || key_masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mx) * inv;
             float mk = 1.f;
             if (a.thr) mk = rbm_u4_get(rnd, t) >= a.thr ? a.inv_keep : 0.f;
-            Ps[j * R + r] = p * (mk * dp[r][jj] - delta[r]);
+            // masked_fill(-1e9) replaces the score by a constant: no gradient reaches q.k through a padded key
+            Ps[j * R + r] = padk[j] != 0.f ? 0.f : p * (mk * dp[r][jj] - delta[r]);
           }
         }
       }
@@ -341,7 +342,7 @@ __global__ void __launch_bounds__(32 * WARPS, 1) attn_bwd_dkv_kernel(AttnArgs a)
           uint4 rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x * L + i, j));
           mk = rbm_u4_get(rnd, (j >> 5) & 3) >= a.thr ? a.inv_keep : 0.f;
         }
-        P1[i * R + r] = p * (mk * dp[r][ii] - st_d[i]);
+        P1[i * R + r] = jpad ? 0.f : p * (mk * dp[r][ii] - st_d[i]);  // no score gradient through a padded key
         P2[i * R + r] = p * mk;
       }
     }

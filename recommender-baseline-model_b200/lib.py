@@ -86,15 +86,45 @@ def load() -> C.CDLL:
         raise RuntimeError(
             "librbm_b200.so is missing (%s). Build it with `python __graft_entry__.py build` "
             "(nvcc, sm_100a). This package has no CPU or PyTorch fallback." % LIB_PATH)
-    lib = C.CDLL(LIB_PATH)
+    cdll = C.CDLL(LIB_PATH)
+    lib = _Lib()
     for name, (res, args) in SIGNATURES.items():
-        fn = getattr(lib, name)  # AttributeError if the symbol is missing
+        fn = getattr(cdll, name)  # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
+        setattr(lib, name, _timed(name, fn) if res is _I and name != "rbm_abi_version" else fn)
     if lib.rbm_abi_version() != 1:
         raise RuntimeError("librbm_b200.so ABI version mismatch")
     _lib = lib
     return lib
+
+
+class _Lib:
+    """Namespace of the bound C functions."""
+
+
+# Optional per-entry-point device timing (bench.py's roofline leg): when `profile` is a dict, every kernel-launching
+# call is bracketed by CUDA events on the launching stream; `profile_collect()` turns them into milliseconds.
+profile = None
+
+
+def _timed(name, fn):
+    def call(*a):
+        if profile is None:
+            return fn(*a)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*a)
+        e1.record()
+        profile.setdefault(name, []).append((e0, e1))
+        return rc
+    return call
+
+
+def profile_collect():
+    """{entry point: [ms per call]} for the calls recorded since `profile` was set to a dict."""
+    torch.cuda.synchronize()
+    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (profile or {}).items()}
 
 
 def check(rc: int, what: str = ""):
