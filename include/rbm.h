@@ -194,8 +194,8 @@ typedef struct {
 /* tensors: DEVICE array of n_tensors descriptors; total_chunks = sum ceil(n/RBM_ADAM_CHUNK);
  * chunk_map: DEVICE int32 [total_chunks*2] = (tensor id, chunk id within tensor). */
 #define RBM_ADAM_CHUNK 4096
-int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chunk_map, int total_chunks, float lr,
-                   float beta1, float beta2, float eps, float weight_decay, int step, rbm_stream_t stream);
+int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chunk_map, int total_chunks, double lr,
+                   double beta1, double beta2, double eps, double weight_decay, int step, rbm_stream_t stream);
 /* flat-bucket helpers for the data-parallel gradient all-reduce: copy n_tensors tensors to/from one
  * contiguous bucket (offsets in elements), optionally scaling. */
 typedef struct {

@@ -67,20 +67,21 @@ __global__ void __launch_bounds__(256) bucket_pack_kernel(const rbm_bucket_tenso
 
 }  // namespace
 
-extern "C" int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chunk_map, int total_chunks, float lr, float beta1,
-                              float beta2, float eps, float weight_decay, int step, rbm_stream_t stream) {
+extern "C" int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chunk_map, int total_chunks, double lr, double beta1,
+                              double beta2, double eps, double weight_decay, int step, rbm_stream_t stream) {
   RBM_REQUIRE(tensors && chunk_map, "rbm_adam_multi: null pointer");
   RBM_REQUIRE(total_chunks >= 0 && step >= 1, "rbm_adam_multi: need step >= 1");
   if (total_chunks == 0) return 0;
-  double bc1 = 1.0 - pow((double)beta1, (double)step);
-  double bc2 = 1.0 - pow((double)beta2, (double)step);
+  // hyper-parameters arrive as doubles (python floats) and are rounded to fp32 once, like torch's scalar arguments
+  double bc1 = 1.0 - pow(beta1, (double)step);
+  double bc2 = 1.0 - pow(beta2, (double)step);
   AdamHyper h;
-  h.one_minus_b1 = 1.f - beta1;
-  h.b2 = beta2;
-  h.one_minus_b2 = 1.f - beta2;
-  h.eps = eps;
-  h.wd = weight_decay;
-  h.neg_step_size = (float)(-((double)lr / bc1));
+  h.one_minus_b1 = (float)(1.0 - beta1);
+  h.b2 = (float)beta2;
+  h.one_minus_b2 = (float)(1.0 - beta2);
+  h.eps = (float)eps;
+  h.wd = (float)weight_decay;
+  h.neg_step_size = (float)(-(lr / bc1));
   h.bc2_sqrt = (float)sqrt(bc2);
   adam_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(tensors, chunk_map, h);
   RBM_LAUNCH_CHECK("rbm_adam_multi");

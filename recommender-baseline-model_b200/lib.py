@@ -21,7 +21,7 @@ LN_TORCH, LN_BERT = 0, 1
 MASK_NONE, MASK_CAUSAL, MASK_KEYPAD = 0, 1, 2
 ADAM_CHUNK = 4096
 
-_P, _I, _L, _F, _U64, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64, C.c_size_t
+_P, _I, _L, _F, _D, _U64, _SZ = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_double, C.c_uint64, C.c_size_t
 
 # name -> (restype, argtypes); must list every function include/rbm.h declares (tests/test_abi.py checks this)
 SIGNATURES = {
@@ -61,7 +61,7 @@ SIGNATURES = {
     "rbm_rank_metrics": (_I, [_P, _P, _P, _P, _P, _P, _I, _P, _L, _I, _L, _L, _P]),
     "rbm_column_mean_ws_bytes": (_SZ, [_L, _I]),
     "rbm_column_mean": (_I, [_P, _P, _L, _I, _P, _SZ, _P]),
-    "rbm_adam_multi": (_I, [_P, _P, _I, _F, _F, _F, _F, _F, _I, _P]),
+    "rbm_adam_multi": (_I, [_P, _P, _I, _D, _D, _D, _D, _D, _I, _P]),
     "rbm_bucket_pack": (_I, [_P, _P, _I, _P, _F, _I, _P]),
     "rbm_dropout_mask": (_I, [_P, _L, _F, _U64, _U64, _P]),
     "rbm_dropout_mask_attn": (_I, [_P, _L, _I, _F, _U64, _U64, _P]),
@@ -116,15 +116,15 @@ def _timed(name, fn):
         e0.record()
         rc = fn(*a)
         e1.record()
-        profile.setdefault(name, []).append((e0, e1))
+        profile.setdefault(name, []).append((e0, e1, a))
         return rc
     return call
 
 
 def profile_collect():
-    """{entry point: [ms per call]} for the calls recorded since `profile` was set to a dict."""
+    """{entry point: [(ms, call args)]} for the calls recorded since `profile` was set to a dict."""
     torch.cuda.synchronize()
-    return {k: [a.elapsed_time(b) for a, b in v] for k, v in (profile or {}).items()}
+    return {k: [(a.elapsed_time(b), args) for a, b, args in v] for k, v in (profile or {}).items()}
 
 
 def check(rc: int, what: str = ""):

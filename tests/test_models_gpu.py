@@ -34,7 +34,7 @@ def sd_of(z, prefix="sd."):
     return {k[len(prefix):]: torch.from_numpy(v) for k, v in z.items() if k.startswith(prefix)}
 
 
-def relclose(a, b, rel=1e-3, floor=1e-6, msg=""):
+def relclose(a, b, rel=1e-3, floor=1e-4, msg=""):
     a, b = np.asarray(a, np.float64), np.asarray(b, np.float64)
     scale = max(np.abs(b).max(), floor)
     assert np.abs(a - b).max() <= rel * scale, "%s: max err %g vs scale %g" % (msg, np.abs(a - b).max(), scale)
