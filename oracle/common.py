@@ -87,6 +87,33 @@ def embedding_grad_scatter_fast(idx: np.ndarray, rows: np.ndarray, vocab: int, p
     return grad
 
 
+def embedding_grad_scatter_chunked(idx: np.ndarray, rows: np.ndarray, vocab: int, padding_idx: int = 0,
+                                   chunk: int = 64) -> np.ndarray:
+    """The CUDA kernel's exact summation contract (rbm_scatter_add_sorted): per destination row the contributions,
+    in ascending position, are cut into pieces of ``chunk``; each piece is summed sequentially, the piece sums are
+    added in order.  Rows with <= chunk contributions coincide bit-for-bit with :func:`embedding_grad_scatter`
+    (the reference's order); longer rows differ from it only in fp32 rounding."""
+    idx = np.asarray(idx).reshape(-1)
+    rows = np.asarray(rows, dtype=np.float32).reshape(idx.shape[0], -1)
+    grad = np.zeros((vocab, rows.shape[1]), dtype=np.float32)
+    order = np.argsort(idx, kind="stable")
+    sidx = idx[order]
+    bounds = np.flatnonzero(np.r_[True, sidx[1:] != sidx[:-1], True])
+    for a, b in zip(bounds[:-1], bounds[1:]):
+        key = int(sidx[a])
+        if key == padding_idx:
+            continue
+        total = None
+        for p0 in range(a, b, chunk):
+            pos = order[p0:min(p0 + chunk, b)]
+            acc = rows[pos[0]].copy()
+            for r in pos[1:]:
+                acc += rows[r]
+            total = acc if total is None else total + acc
+        grad[key] += total
+    return grad
+
+
 def synth_state_dict(shapes: Dict[str, tuple], seed: int, scale: float = 0.1) -> Dict[str, torch.Tensor]:
     g = torch.Generator().manual_seed(seed)
     return {k: torch.randn(*s, generator=g) * scale for k, s in shapes.items()}

@@ -1,15 +1,24 @@
-// attention.cu -- short-sequence (L <= 256) multi-head attention, forward and backward, fp32.
-// One CTA per (sequence, head): the whole K/V (or Q/dO) panel of the head lives in shared memory, every warp owns
-// groups of R query (or key) rows, scores stay in registers, softmax via warp shuffles, dropout regenerated from
-// Philox -- the [B,h,L,L] probability tensor the reference materialises (NN/models/bert_modules/attention/single.py:14-33,
-// torch MHA inside NN/models/sas_model/sas.py:75-76) never touches HBM.  Backward is recompute-based and
-// atomics-free (pass A: dQ by query rows; pass B: dK,dV by key rows) so results are bit-deterministic.
+// attention.cu -- short-sequence (L <= 256) multi-head attention, forward and backward, on tensor cores.
+//
+// One CTA per (sequence, head).  The K/V (or Q/dO) panel of the head sits in shared memory, XOR-swizzled so that both
+// mma B-fragment access patterns (contraction along the panel's columns, as in q.k^T, and along its rows, as in P.v)
+// are bank-conflict free.  Each warp owns 16-row query (or key) tiles and walks the other dimension in 64-wide
+// chunks, flash-attention style: scores live in mma accumulator registers, the masked softmax runs on them with
+// quad shuffles, dropout is regenerated from Philox, probabilities go through a small per-warp shared tile back into
+// the tensor cores.  The [B,h,L,L] probability tensor the reference materialises (NN/models/bert_modules/attention/
+// single.py:14-33; torch MHA inside NN/models/sas_model/sas.py:75-76) never exists in HBM.
+//
+// Math: mma.sync m16n8k8 TF32 with fp32 accumulation and 3xTF32 error compensation (a = a_hi + a_lo, three MMAs per
+// product), i.e. fp32-level accuracy on the legacy tensor path; -DRBM_ATTN_TF32X1 selects single-pass TF32.  The
+// backward is recompute-based and atomics-free (pass A: dQ by query tiles; pass B: dK, dV by key tiles), so results
+// are bit-deterministic.  A tcgen05/TMEM formulation of these L<=256 tiles is tracked in DESIGN.md ("next").
 #include "common.cuh"
 
 namespace {
 
-constexpr int WARPS = 8;
-constexpr int DCMAX = 4;  // dk <= 128
+constexpr int CH = 64;         // keys (queries in pass B) per chunk = 8 mma n-tiles
+constexpr int PB_LD = CH + 4;  // per-warp probability tile row stride (== 4*odd mod 32: conflict-free A fragments)
+constexpr int MAX_WARPS = 8;
 
 struct AttnArgs {
   const float *q, *k, *v, *o, *dout, *stats_in;
@@ -18,297 +27,379 @@ struct AttnArgs {
   const int64_t* tok;
   int L, h, dk, mask_mode;
   float scale;
-  uint32_t thr;
+  uint32_t thr16;
   float inv_keep;
   uint64_t seed, site;
 };
 
-// dst[LP][KS] <- src rows (b*L + j), columns [hh*dk, hh*dk+dk); rows >= L zero-filled.  All threads of the CTA.
-__device__ __forceinline__ void load_panel(float* dst, const float* __restrict__ src, int64_t ld, int64_t row0, int col0,
-                                           int L, int LP, int dk, int KS, float mul) {
+__device__ __forceinline__ int swz(int r) { return (((r & 3) << 1) | ((r >> 2) & 1)) << 2; }
+
+__device__ __forceinline__ uint32_t f2tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = f2tf32(x);
+  lo = f2tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+struct FragA {
+  uint32_t hi[4], lo[4];
+};
+struct FragB {
+  uint32_t hi[2], lo[2];
+};
+__device__ __forceinline__ void mma3(float (&d)[4], const FragA& a, const FragB& b) {
+#ifndef RBM_ATTN_TF32X1
+  mma_tf32(d, a.lo, b.hi);
+  mma_tf32(d, a.hi, b.lo);
+#endif
+  mma_tf32(d, a.hi, b.hi);
+}
+
+// A fragment (16 x 8) of a row-major per-warp tile [16][ld] at column k0
+__device__ __forceinline__ FragA load_a(const float* tile, int ld, int k0, int g, int t) {
+  FragA f;
+  split_tf32(tile[g * ld + k0 + t], f.hi[0], f.lo[0]);
+  split_tf32(tile[(g + 8) * ld + k0 + t], f.hi[1], f.lo[1]);
+  split_tf32(tile[g * ld + k0 + t + 4], f.hi[2], f.lo[2]);
+  split_tf32(tile[(g + 8) * ld + k0 + t + 4], f.hi[3], f.lo[3]);
+  return f;
+}
+// B fragment, contraction along the panel's COLUMNS: B[k][n] = panel[n0 + n][k0 + k]
+__device__ __forceinline__ FragB load_b_nk(const float* panel, int LD, int n0, int k0, int g, int t) {
+  const float* row = panel + (n0 + g) * LD;
+  int s = swz(g);
+  FragB f;
+  split_tf32(row[(k0 + t) ^ s], f.hi[0], f.lo[0]);
+  split_tf32(row[(k0 + t + 4) ^ s], f.hi[1], f.lo[1]);
+  return f;
+}
+// B fragment, contraction along the panel's ROWS: B[k][n] = panel[k0 + k][n0 + n]
+__device__ __forceinline__ FragB load_b_kn(const float* panel, int LD, int k0, int n0, int g, int t) {
+  FragB f;
+  split_tf32(panel[(k0 + t) * LD + ((n0 + g) ^ swz(t))], f.hi[0], f.lo[0]);
+  split_tf32(panel[(k0 + t + 4) * LD + ((n0 + g) ^ swz(t + 4))], f.hi[1], f.lo[1]);
+  return f;
+}
+
+// panel[LP8][LD] (swizzled) <- rows (row0 + r) of src, columns [col0, col0 + dk), times mul; rows >= L are zero
+__device__ __forceinline__ void load_panel(float* dst, const float* __restrict__ src, int64_t ld, int64_t row0, int col0, int L,
+                                           int LP8, int dk, int LD, float mul) {
   int dk4 = dk >> 2;
-  for (int idx = threadIdx.x; idx < LP * dk4; idx += blockDim.x) {
-    int j = idx / dk4, c4 = idx - j * dk4;
+  for (int idx = threadIdx.x; idx < LP8 * dk4; idx += blockDim.x) {
+    int r = idx / dk4, c4 = idx - r * dk4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (j < L) v = ld4(src + (row0 + j) * ld + col0 + c4 * 4);
-    float* d = dst + j * KS + c4 * 4;
-    d[0] = v.x * mul; d[1] = v.y * mul; d[2] = v.z * mul; d[3] = v.w * mul;
+    if (r < L) v = ld4(src + (row0 + r) * ld + col0 + c4 * 4);
+    st4(dst + r * LD + ((c4 * 4) ^ swz(r)), make_float4(v.x * mul, v.y * mul, v.z * mul, v.w * mul));
+  }
+}
+// per-warp tile[16][ldt] <- rows (row0 + i0 + r), r < 16
+__device__ __forceinline__ void stage_tile(float* dst, int ldt, const float* __restrict__ src, int64_t ld, int64_t row0, int col0,
+                                           int i0, int L, int dk, float mul, int lane) {
+  int dk4 = dk >> 2;
+  for (int idx = lane; idx < 16 * dk4; idx += 32) {
+    int r = idx / dk4, c4 = idx - r * dk4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (i0 + r < L) v = ld4(src + (row0 + i0 + r) * ld + col0 + c4 * 4);
+    st4(dst + r * ldt + c4 * 4, make_float4(v.x * mul, v.y * mul, v.z * mul, v.w * mul));
   }
 }
 
-// per-warp: dst[c*R + r] <- src row (row0 + i0 + r), r < R (zero beyond L)
-template <int R>
-__device__ __forceinline__ void load_rows_cr(float* dst, const float* __restrict__ src, int64_t ld, int64_t row0, int col0,
-                                             int i0, int L, int dk, float mul, int lane) {
-  for (int idx = lane; idx < R * dk; idx += 32) {
-    int r = idx / dk, c = idx - r * dk;
-    int i = i0 + r;
-    dst[c * R + r] = i < L ? src[(row0 + i) * ld + col0 + c] * mul : 0.f;
-  }
+__device__ __forceinline__ float quad_max(float v) {
+  v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));
+  return fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 2));
 }
+__device__ __forceinline__ float quad_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1);
+  return v + __shfl_xor_sync(0xffffffffu, v, 2);
+}
+__device__ __forceinline__ bool masked_inf(int mode, int i, int j, int L) { return j >= L || (mode == RBM_MASK_CAUSAL && j > i); }
 
-// acc[r][jj] += sum_c rows_cr[c][r] * panel[(lane + 32*jj)][c]
-template <int NJ, int R>
-__device__ __forceinline__ void rows_dot_panel(const float* rows_cr, const float* panel, int KS, int dk, int lane,
-                                               float (&acc)[R][NJ]) {
-  for (int c = 0; c < dk; ++c) {
-    float rv[R];
+// acc[nt] (+)= Atile(16 x dk) . panel[jb + nt*8 .. +8][0..dk)^T  for nt < 8
+__device__ __forceinline__ void tile_dot_panel(float (&acc)[8][4], const float* atile, int lda, const float* panel, int LD, int jb,
+                                               int LP8, int dk, int g, int t) {
+  for (int k0 = 0; k0 < dk; k0 += 8) {
+    FragA a = load_a(atile, lda, k0, g, t);
 #pragma unroll
-    for (int r4 = 0; r4 < R / 4; ++r4) {
-      float4 t = ld4(rows_cr + c * R + r4 * 4);
-      rv[r4 * 4] = t.x; rv[r4 * 4 + 1] = t.y; rv[r4 * 4 + 2] = t.z; rv[r4 * 4 + 3] = t.w;
-    }
-#pragma unroll
-    for (int jj = 0; jj < NJ; ++jj) {
-      float pv = panel[(lane + 32 * jj) * KS + c];
-#pragma unroll
-      for (int r = 0; r < R; ++r) acc[r][jj] = fmaf(rv[r], pv, acc[r][jj]);
+    for (int nt = 0; nt < 8; ++nt) {
+      if (jb + nt * 8 < LP8) {
+        FragB b = load_b_nk(panel, LD, jb + nt * 8, k0, g, t);
+        mma3(acc[nt], a, b);
+      }
     }
   }
 }
-
-// o[r][cc] = sum_{j in [jb, je)} w_jr[j*R + r] * panel[j][cc*32 + lane]
-template <int R>
-__device__ __forceinline__ void weights_times_panel(const float* w_jr, const float* panel, int KS, int dk, int jb, int je,
-                                                    int lane, float (&o)[R][DCMAX]) {
+// acc[dt] += Ptile(16 x 64 chunk) . panel[jb .. jb+64][dt*8 .. +8]   for dt*8 < dk
+template <int DT>
+__device__ __forceinline__ void ptile_times_panel(float (&acc)[DT][4], const float* ptile, const float* panel, int LD, int jb, int LP8,
+                                                  int dk, int g, int t) {
 #pragma unroll
-  for (int r = 0; r < R; ++r)
+  for (int ks = 0; ks < 8; ++ks) {
+    if (jb + ks * 8 < LP8) {
+      FragA a = load_a(ptile, PB_LD, ks * 8, g, t);
 #pragma unroll
-    for (int cc = 0; cc < DCMAX; ++cc) o[r][cc] = 0.f;
-  for (int j = jb; j < je; ++j) {
-    float wv[R];
-#pragma unroll
-    for (int r4 = 0; r4 < R / 4; ++r4) {
-      float4 t = ld4(w_jr + j * R + r4 * 4);
-      wv[r4 * 4] = t.x; wv[r4 * 4 + 1] = t.y; wv[r4 * 4 + 2] = t.z; wv[r4 * 4 + 3] = t.w;
-    }
-#pragma unroll
-    for (int cc = 0; cc < DCMAX; ++cc) {
-      if (cc * 32 < dk) {
-        int c = cc * 32 + lane;
-        float pv = c < dk ? panel[j * KS + c] : 0.f;
-#pragma unroll
-        for (int r = 0; r < R; ++r) o[r][cc] = fmaf(wv[r], pv, o[r][cc]);
+      for (int dt = 0; dt < DT; ++dt) {
+        if (dt * 8 < dk) {
+          FragB b = load_b_kn(panel, LD, jb + ks * 8, dt * 8, g, t);
+          mma3(acc[dt], a, b);
+        }
       }
     }
   }
 }
 
-__device__ __forceinline__ bool key_masked_inf(int mask_mode, int i, int j, int L) {
-  return j >= L || (mask_mode == RBM_MASK_CAUSAL && j > i);
-}
-
-// ------------------------------------------------------------------------------------------------ forward
-template <int NJ, int R>
-__global__ void __launch_bounds__(32 * WARPS, 1) attn_fwd_kernel(AttnArgs a) {
+// ---------------------------------------------------------------------------------------------------- forward
+template <int DT>
+__global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int L = a.L, dk = a.dk, KS = dk + 1, LP = NJ * 32;
+  const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)b * L;
   const int col0 = hh * dk;
-  float* Ks = sm;
-  float* Vs = Ks + LP * KS;
-  float* padk = Vs + LP * KS;  // [LP] 1.0 where the key token is padding
-  float* wbase = padk + LP + (size_t)warp * (R * dk + LP * R);
-  float* Qs = wbase;           // [dk][R]
-  float* Ps = wbase + R * dk;  // [LP][R]
+  float* Kp = sm;
+  float* Vp = Kp + LP8 * LD;
+  float* padk = Vp + LP8 * LD;  // [LPC]
+  float* wbase = padk + LPC + (size_t)warp * (16 * QLD + 16 * PB_LD);
+  float* Qs = wbase;             // [16][QLD] scaled q tile
+  float* Pb = wbase + 16 * QLD;  // [16][PB_LD]
 
-  load_panel(Ks, a.k, a.ldk, row0, col0, L, LP, dk, KS, 1.f);
-  load_panel(Vs, a.v, a.ldv, row0, col0, L, LP, dk, KS, 1.f);
-  for (int j = threadIdx.x; j < LP; j += blockDim.x)
+  load_panel(Kp, a.k, a.ldk, row0, col0, L, LP8, dk, LD, 1.f);
+  load_panel(Vp, a.v, a.ldv, row0, col0, L, LP8, dk, LD, 1.f);
+  for (int j = threadIdx.x; j < LPC; j += blockDim.x)
     padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
   __syncthreads();
 
-  for (int i0 = warp * R; i0 < L; i0 += WARPS * R) {
-    load_rows_cr<R>(Qs, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
+  for (int i0 = warp * 16; i0 < L; i0 += nwarps * 16) {
+    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
     __syncwarp();
-    float s[R][NJ];
+    float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
+    float o[DT][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
+    for (int dt = 0; dt < DT; ++dt) o[dt][0] = o[dt][1] = o[dt][2] = o[dt][3] = 0.f;
+    const int kend = a.mask_mode == RBM_MASK_CAUSAL ? (i0 + 16 < L ? i0 + 16 : L) : L;
+    for (int jb = 0; jb < kend; jb += CH) {
+      float s[8][4];
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) s[r][jj] = 0.f;
-    rows_dot_panel<NJ, R>(Qs, Ks, KS, dk, lane, s);
+      for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+      tile_dot_panel(s, Qs, QLD, Kp, LD, jb, LP8, dk, g, t);
+      float cm[2] = {-INFINITY, -INFINITY};
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = i0 + r;
-      float mx = -INFINITY;
+      for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) {
-        int j = lane + 32 * jj;
-        float v = s[r][jj];
-        if (padk[j] != 0.f) v = -1e9f;
-        if (key_masked_inf(a.mask_mode, i, j, L)) v = -INFINITY;
-        s[r][jj] = v;
-        mx = fmaxf(mx, v);
+        for (int c = 0; c < 4; ++c) {
+          int hrow = c >> 1, j = jb + nt * 8 + 2 * t + (c & 1), i = i0 + g + 8 * hrow;
+          float v = s[nt][c];
+          if (padk[j] != 0.f) v = -1e9f;
+          if (masked_inf(a.mask_mode, i, j, L)) v = -INFINITY;
+          s[nt][c] = v;
+          cm[hrow] = fmaxf(cm[hrow], v);
+        }
+      float base[2], alpha[2], ps[2] = {0.f, 0.f};
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) {
+        float mn = fmaxf(m[hrow], quad_max(cm[hrow]));
+        alpha[hrow] = m[hrow] == -INFINITY ? 0.f : expf(m[hrow] - mn);
+        base[hrow] = mn == -INFINITY ? 0.f : mn;
+        m[hrow] = mn;
       }
-      mx = warp_max(mx);
-      float sum = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) {
-        float e = expf(s[r][jj] - mx);
-        s[r][jj] = e;
-        sum += e;
+      for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          float p = expf(s[nt][c] - base[c >> 1]);
+          s[nt][c] = p;
+          ps[c >> 1] += p;
+        }
+#pragma unroll
+      for (int hrow = 0; hrow < 2; ++hrow) l[hrow] = l[hrow] * alpha[hrow] + quad_sum(ps[hrow]);
+#pragma unroll
+      for (int dt = 0; dt < DT; ++dt) {
+        o[dt][0] *= alpha[0]; o[dt][1] *= alpha[0]; o[dt][2] *= alpha[1]; o[dt][3] *= alpha[1];
       }
-      sum = warp_sum(sum);
-      float inv = 1.f / sum;
-      if (lane == 0 && i < L && a.stats) {
-        int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
-        a.stats[sr] = mx;
-        a.stats[sr + 1] = inv;
-      }
-      const uint64_t Rrow = (uint64_t)blockIdx.x * L + i;
+      if (a.thr16) {
 #pragma unroll
-      for (int g = 0; g < (NJ + 3) / 4; ++g) {
-        uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (a.thr) rnd = rbm_philox(a.seed, a.site, rbm_attn_call(Rrow, lane + 128 * g));
+        for (int qd = 0; qd < 4; ++qd) {
+          if (jb + qd * 16 < LP8) {
+            uint4 rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          int jj = g * 4 + t;
-          if (jj < NJ) {
-            float p = s[r][jj] * inv;
-            if (a.thr) p = rbm_u4_get(rnd, t) >= a.thr ? p * a.inv_keep : 0.f;
-            Ps[(lane + 32 * jj) * R + r] = p;
+            for (int bb = 0; bb < 2; ++bb)
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                int f = (c >> 1) * 4 + (c & 1) * 2 + bb;
+                s[qd * 2 + bb][c] = rbm_attn_field(rnd, f) >= a.thr16 ? s[qd * 2 + bb][c] * a.inv_keep : 0.f;
+              }
           }
         }
       }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
+        *reinterpret_cast<float2*>(Pb + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][2], s[nt][3]);
+      }
+      __syncwarp();
+      ptile_times_panel<DT>(o, Pb, Vp, LD, jb, LP8, dk, g, t);
+      __syncwarp();
     }
-    __syncwarp();
-    float o[R][DCMAX];
-    int je = a.mask_mode == RBM_MASK_CAUSAL ? (i0 + R < L ? i0 + R : L) : L;
-    weights_times_panel<R>(Ps, Vs, KS, dk, 0, je, lane, o);
+    float inv[2] = {1.f / l[0], 1.f / l[1]};
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int i = i0 + r;
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      int i = i0 + g + 8 * hrow;
       if (i < L) {
-#pragma unroll
-        for (int cc = 0; cc < DCMAX; ++cc) {
-          int c = cc * 32 + lane;
-          if (c < dk) a.out[(row0 + i) * a.ldo + col0 + c] = o[r][cc];
+        if (t == 0 && a.stats) {
+          int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
+          a.stats[sr] = m[hrow];
+          a.stats[sr + 1] = inv[hrow];
         }
+#pragma unroll
+        for (int dt = 0; dt < DT; ++dt)
+          if (dt * 8 < dk)
+            *reinterpret_cast<float2*>(a.out + (row0 + i) * a.ldo + col0 + dt * 8 + 2 * t) =
+                make_float2(o[dt][2 * hrow] * inv[hrow], o[dt][2 * hrow + 1] * inv[hrow]);
       }
     }
     __syncwarp();
   }
 }
 
-// --------------------------------------------------------------------------- backward pass A: dQ and delta
-template <int NJ, int R>
-__global__ void __launch_bounds__(32 * WARPS, 1) attn_bwd_dq_kernel(AttnArgs a) {
+// ------------------------------------------------------------------------------- backward pass A: dQ and delta
+template <int DT>
+__global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int L = a.L, dk = a.dk, KS = dk + 1, LP = NJ * 32;
+  const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)b * L;
   const int col0 = hh * dk;
-  float* Ks = sm;
-  float* Vs = Ks + LP * KS;
-  float* padk = Vs + LP * KS;
-  float* wbase = padk + LP + (size_t)warp * (2 * R * dk + LP * R);
-  float* Qs = wbase;            // [dk][R]  (scaled q)
-  float* dOs = wbase + R * dk;  // [dk][R]
-  float* Ps = dOs + R * dk;     // [LP][R]  dS
+  float* Kp = sm;
+  float* Vp = Kp + LP8 * LD;
+  float* padk = Vp + LP8 * LD;
+  float* wbase = padk + LPC + (size_t)warp * (32 * QLD + 16 * PB_LD);
+  float* Qs = wbase;              // [16][QLD] scaled q
+  float* dOs = wbase + 16 * QLD;  // [16][QLD]
+  float* Pb = dOs + 16 * QLD;     // [16][PB_LD] dS chunk
 
-  load_panel(Ks, a.k, a.ldk, row0, col0, L, LP, dk, KS, 1.f);
-  load_panel(Vs, a.v, a.ldv, row0, col0, L, LP, dk, KS, 1.f);
-  for (int j = threadIdx.x; j < LP; j += blockDim.x)
+  load_panel(Kp, a.k, a.ldk, row0, col0, L, LP8, dk, LD, 1.f);
+  load_panel(Vp, a.v, a.ldv, row0, col0, L, LP8, dk, LD, 1.f);
+  for (int j = threadIdx.x; j < LPC; j += blockDim.x)
     padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
   __syncthreads();
 
-  for (int i0 = warp * R; i0 < L; i0 += WARPS * R) {
-    load_rows_cr<R>(Qs, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
-    load_rows_cr<R>(dOs, a.dout, a.lddo, row0, col0, i0, L, dk, 1.f, lane);
-    float delta[R];
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
+  for (int i0 = warp * 16; i0 < L; i0 += nwarps * 16) {
+    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
+    stage_tile(dOs, QLD, a.dout, a.lddo, row0, col0, i0, L, dk, 1.f, lane);
+    float delta[2] = {0.f, 0.f}, mx[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
+    for (int r = 0; r < 16; ++r) {
       int i = i0 + r;
       float part = 0.f;
       if (i < L)
         for (int c = lane; c < dk; c += 32)
           part = fmaf(a.dout[(row0 + i) * a.lddo + col0 + c], a.o[(row0 + i) * a.ldo + col0 + c], part);
-      delta[r] = warp_sum(part);
-      if (lane == 0 && i < L) a.delta[(int64_t)blockIdx.x * L + i] = delta[r];
+      part = warp_sum(part);
+      if (lane == 0 && i < L) a.delta[(int64_t)blockIdx.x * L + i] = part;
+      if (r == g) delta[0] = part;
+      if (r == g + 8) delta[1] = part;
     }
-    __syncwarp();
-    float s[R][NJ], dp[R][NJ];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int jj = 0; jj < NJ; ++jj) s[r][jj] = dp[r][jj] = 0.f;
-    rows_dot_panel<NJ, R>(Qs, Ks, KS, dk, lane, s);
-    rows_dot_panel<NJ, R>(dOs, Vs, KS, dk, lane, dp);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int i = i0 + r;
-      float mx = 0.f, inv = 0.f;
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      int i = i0 + g + 8 * hrow;
       if (i < L) {
         int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
-        mx = a.stats_in[sr];
-        inv = a.stats_in[sr + 1];
+        mx[hrow] = a.stats_in[sr];
+        inv[hrow] = a.stats_in[sr + 1];
       }
-      const uint64_t Rrow = (uint64_t)blockIdx.x * L + i;
+    }
+    __syncwarp();
+    float dq[DT][4];
 #pragma unroll
-      for (int g = 0; g < (NJ + 3) / 4; ++g) {
+    for (int dt = 0; dt < DT; ++dt) dq[dt][0] = dq[dt][1] = dq[dt][2] = dq[dt][3] = 0.f;
+    const int kend = a.mask_mode == RBM_MASK_CAUSAL ? (i0 + 16 < L ? i0 + 16 : L) : L;
+    for (int jb = 0; jb < kend; jb += CH) {
+      float s[8][4], dp[8][4];
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+      }
+      tile_dot_panel(s, Qs, QLD, Kp, LD, jb, LP8, dk, g, t);
+      tile_dot_panel(dp, dOs, QLD, Vp, LD, jb, LP8, dk, g, t);
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
         uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
-        if (a.thr) rnd = rbm_philox(a.seed, a.site, rbm_attn_call(Rrow, lane + 128 * g));
+        if (a.thr16 && jb + qd * 16 < LP8)
+          rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          int jj = g * 4 + t;
-          if (jj < NJ) {
-            int j = lane + 32 * jj;
-            float v = s[r][jj];
-            if (padk[j] != 0.f) v = -1e9f;
-            float p = (i >= L || key_masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mx) * inv;
+        for (int bb = 0; bb < 2; ++bb) {
+          const int nt = qd * 2 + bb;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            int hrow = c >> 1, j = jb + nt * 8 + 2 * t + (c & 1), i = i0 + g + 8 * hrow;
+            bool pad = padk[j] != 0.f;
+            float v = pad ? -1e9f : s[nt][c];
+            float p = (i >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mx[hrow]) * inv[hrow];
             float mk = 1.f;
-            if (a.thr) mk = rbm_u4_get(rnd, t) >= a.thr ? a.inv_keep : 0.f;
+            if (a.thr16) mk = rbm_attn_field(rnd, hrow * 4 + (c & 1) * 2 + bb) >= a.thr16 ? a.inv_keep : 0.f;
             // masked_fill(-1e9) replaces the score by a constant: no gradient reaches q.k through a padded key
-            Ps[j * R + r] = padk[j] != 0.f ? 0.f : p * (mk * dp[r][jj] - delta[r]);
+            s[nt][c] = pad ? 0.f : p * (mk * dp[nt][c] - delta[hrow]);
           }
         }
       }
-    }
-    __syncwarp();
-    float o[R][DCMAX];
-    int je = a.mask_mode == RBM_MASK_CAUSAL ? (i0 + R < L ? i0 + R : L) : L;
-    weights_times_panel<R>(Ps, Ks, KS, dk, 0, je, lane, o);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int i = i0 + r;
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
+        *reinterpret_cast<float2*>(Pb + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][2], s[nt][3]);
+      }
+      __syncwarp();
+      ptile_times_panel<DT>(dq, Pb, Kp, LD, jb, LP8, dk, g, t);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      int i = i0 + g + 8 * hrow;
       if (i < L) {
 #pragma unroll
-        for (int cc = 0; cc < DCMAX; ++cc) {
-          int c = cc * 32 + lane;
-          if (c < dk) a.dq[(row0 + i) * a.lddq + col0 + c] = o[r][cc] * a.scale;
-        }
+        for (int dt = 0; dt < DT; ++dt)
+          if (dt * 8 < dk)
+            *reinterpret_cast<float2*>(a.dq + (row0 + i) * a.lddq + col0 + dt * 8 + 2 * t) =
+                make_float2(dq[dt][2 * hrow] * a.scale, dq[dt][2 * hrow + 1] * a.scale);
       }
     }
     __syncwarp();
   }
 }
 
-// --------------------------------------------------------------------------- backward pass B: dK and dV
-template <int NJ, int R>
-__global__ void __launch_bounds__(32 * WARPS, 1) attn_bwd_dkv_kernel(AttnArgs a) {
+// ------------------------------------------------------------------------------- backward pass B: dK and dV
+template <int DT>
+__global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int L = a.L, dk = a.dk, KS = dk + 1, LP = NJ * 32;
+  const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
   const int64_t row0 = (int64_t)b * L;
   const int col0 = hh * dk;
-  float* Qa = sm;               // [LP][KS] scaled q
-  float* dOa = Qa + LP * KS;    // [LP][KS]
-  float* st_m = dOa + LP * KS;  // [LP]
-  float* st_i = st_m + LP;      // [LP]
-  float* st_d = st_i + LP;      // [LP]
-  float* wbase = st_d + LP + (size_t)warp * (2 * R * dk + 2 * LP * R);
-  float* Kg = wbase;            // [dk][R]
-  float* Vg = Kg + R * dk;      // [dk][R]
-  float* P1 = Vg + R * dk;      // [LP][R] dS^T
-  float* P2 = P1 + LP * R;      // [LP][R] P~^T
+  float* Qp = sm;               // [LP8][LD] scaled q panel
+  float* dOp = Qp + LP8 * LD;   // [LP8][LD]
+  float* st_m = dOp + LP8 * LD; // [LPC]
+  float* st_i = st_m + LPC;
+  float* st_d = st_i + LPC;
+  float* wbase = st_d + LPC + (size_t)warp * (32 * QLD + 32 * PB_LD);
+  float* Ks = wbase;             // [16][QLD] key tile
+  float* Vs = Ks + 16 * QLD;     // [16][QLD] value tile
+  float* P1 = Vs + 16 * QLD;     // [16][PB_LD] dS^T chunk
+  float* P2 = P1 + 16 * PB_LD;   // [16][PB_LD] P~^T chunk
 
-  load_panel(Qa, a.q, a.ldq, row0, col0, L, LP, dk, KS, a.scale);
-  load_panel(dOa, a.dout, a.lddo, row0, col0, L, LP, dk, KS, 1.f);
-  for (int i = threadIdx.x; i < LP; i += blockDim.x) {
+  load_panel(Qp, a.q, a.ldq, row0, col0, L, LP8, dk, LD, a.scale);
+  load_panel(dOp, a.dout, a.lddo, row0, col0, L, LP8, dk, LD, 1.f);
+  for (int i = threadIdx.x; i < LPC; i += blockDim.x) {
     bool in = i < L;
     int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
     st_m[i] = in ? a.stats_in[sr] : 0.f;
@@ -317,74 +408,96 @@ __global__ void __launch_bounds__(32 * WARPS, 1) attn_bwd_dkv_kernel(AttnArgs a)
   }
   __syncthreads();
 
-  for (int j0 = warp * R; j0 < L; j0 += WARPS * R) {
-    load_rows_cr<R>(Kg, a.k, a.ldk, row0, col0, j0, L, dk, 1.f, lane);
-    load_rows_cr<R>(Vg, a.v, a.ldv, row0, col0, j0, L, dk, 1.f, lane);
-    __syncwarp();
-    float s[R][NJ], dp[R][NJ];
+  for (int j0 = warp * 16; j0 < L; j0 += nwarps * 16) {
+    stage_tile(Ks, QLD, a.k, a.ldk, row0, col0, j0, L, dk, 1.f, lane);
+    stage_tile(Vs, QLD, a.v, a.ldv, row0, col0, j0, L, dk, 1.f, lane);
+    bool jpad[2];
 #pragma unroll
-    for (int r = 0; r < R; ++r)
-#pragma unroll
-      for (int ii = 0; ii < NJ; ++ii) s[r][ii] = dp[r][ii] = 0.f;
-    rows_dot_panel<NJ, R>(Kg, Qa, KS, dk, lane, s);
-    rows_dot_panel<NJ, R>(Vg, dOa, KS, dk, lane, dp);
-#pragma unroll
-    for (int r = 0; r < R; ++r) {
-      const int j = j0 + r;
-      const bool jpad = a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0;
-#pragma unroll
-      for (int ii = 0; ii < NJ; ++ii) {
-        int i = lane + 32 * ii;
-        float v = jpad ? -1e9f : s[r][ii];
-        float p = (i >= L || key_masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - st_m[i]) * st_i[i];
-        float mk = 1.f;
-        if (a.thr) {
-          uint4 rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x * L + i, j));
-          mk = rbm_u4_get(rnd, (j >> 5) & 3) >= a.thr ? a.inv_keep : 0.f;
-        }
-        P1[i * R + r] = jpad ? 0.f : p * (mk * dp[r][ii] - st_d[i]);  // no score gradient through a padded key
-        P2[i * R + r] = p * mk;
-      }
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      int j = j0 + g + 8 * hrow;
+      jpad[hrow] = a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0;
     }
     __syncwarp();
-    float o[R][DCMAX];
-    int ib = a.mask_mode == RBM_MASK_CAUSAL ? j0 : 0;
-    weights_times_panel<R>(P1, Qa, KS, dk, ib, L, lane, o);  // Qa already carries `scale`
+    float dkacc[DT][4], dvacc[DT][4];
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int j = j0 + r;
-      if (j < L) {
+    for (int dt = 0; dt < DT; ++dt) {
+      dkacc[dt][0] = dkacc[dt][1] = dkacc[dt][2] = dkacc[dt][3] = 0.f;
+      dvacc[dt][0] = dvacc[dt][1] = dvacc[dt][2] = dvacc[dt][3] = 0.f;
+    }
+    const int ib0 = a.mask_mode == RBM_MASK_CAUSAL ? (j0 / CH) * CH : 0;  // queries before j0 never see these keys
+    for (int ib = ib0; ib < L; ib += CH) {
+      float s[8][4], dp[8][4];
 #pragma unroll
-        for (int cc = 0; cc < DCMAX; ++cc) {
-          int c = cc * 32 + lane;
-          if (c < dk) a.dk_[(row0 + j) * a.lddk + col0 + c] = o[r][cc];
+      for (int nt = 0; nt < 8; ++nt) {
+        s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+        dp[nt][0] = dp[nt][1] = dp[nt][2] = dp[nt][3] = 0.f;
+      }
+      tile_dot_panel(s, Ks, QLD, Qp, LD, ib, LP8, dk, g, t);    // S^T chunk: rows = keys, cols = queries
+      tile_dot_panel(dp, Vs, QLD, dOp, LD, ib, LP8, dk, g, t);  // dP~^T chunk
+#pragma unroll
+      for (int qd = 0; qd < 4; ++qd) {
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {
+          uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
+          if (a.thr16 && ib + qd * 16 < LP8)
+            rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, (ib >> 4) + qd, 2 * t + e, g >> 1, j0 >> 4));
+#pragma unroll
+          for (int bb = 0; bb < 2; ++bb) {
+            const int nt = qd * 2 + bb;
+            const int i = ib + nt * 8 + 2 * t + e;
+            const float mi = st_m[i], ii = st_i[i], di = st_d[i];
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+              const int c = hrow * 2 + e, j = j0 + g + 8 * hrow;
+              float v = jpad[hrow] ? -1e9f : s[nt][c];
+              float p = (i >= L || j >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mi) * ii;
+              float mk = 1.f;
+              if (a.thr16) mk = rbm_attn_field(rnd, bb * 4 + (g & 1) * 2 + hrow) >= a.thr16 ? a.inv_keep : 0.f;
+              s[nt][c] = jpad[hrow] ? 0.f : p * (mk * dp[nt][c] - di);  // dS^T (no score gradient through a padded key)
+              dp[nt][c] = p * mk;                                      // P~^T
+            }
+          }
         }
       }
-    }
-    weights_times_panel<R>(P2, dOa, KS, dk, ib, L, lane, o);
 #pragma unroll
-    for (int r = 0; r < R; ++r) {
-      int j = j0 + r;
+      for (int nt = 0; nt < 8; ++nt) {
+        *reinterpret_cast<float2*>(P1 + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
+        *reinterpret_cast<float2*>(P1 + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][2], s[nt][3]);
+        *reinterpret_cast<float2*>(P2 + g * PB_LD + nt * 8 + 2 * t) = make_float2(dp[nt][0], dp[nt][1]);
+        *reinterpret_cast<float2*>(P2 + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(dp[nt][2], dp[nt][3]);
+      }
+      __syncwarp();
+      ptile_times_panel<DT>(dkacc, P1, Qp, LD, ib, LP8, dk, g, t);   // Qp carries `scale`
+      ptile_times_panel<DT>(dvacc, P2, dOp, LD, ib, LP8, dk, g, t);
+      __syncwarp();
+    }
+#pragma unroll
+    for (int hrow = 0; hrow < 2; ++hrow) {
+      int j = j0 + g + 8 * hrow;
       if (j < L) {
 #pragma unroll
-        for (int cc = 0; cc < DCMAX; ++cc) {
-          int c = cc * 32 + lane;
-          if (c < dk) a.dv[(row0 + j) * a.lddv + col0 + c] = o[r][cc];
-        }
+        for (int dt = 0; dt < DT; ++dt)
+          if (dt * 8 < dk) {
+            *reinterpret_cast<float2*>(a.dk_ + (row0 + j) * a.lddk + col0 + dt * 8 + 2 * t) = make_float2(dkacc[dt][2 * hrow], dkacc[dt][2 * hrow + 1]);
+            *reinterpret_cast<float2*>(a.dv + (row0 + j) * a.lddv + col0 + dt * 8 + 2 * t) = make_float2(dvacc[dt][2 * hrow], dvacc[dt][2 * hrow + 1]);
+          }
       }
     }
     __syncwarp();
   }
 }
 
-int pick_nj(int L) { return L <= 32 ? 1 : L <= 64 ? 2 : L <= 128 ? 4 : L <= 224 ? 7 : 8; }
-
-size_t smem_fwd(int NJ, int R, int dk) { return sizeof(float) * ((size_t)2 * NJ * 32 * (dk + 1) + NJ * 32 + (size_t)WARPS * (R * dk + NJ * 32 * R)); }
-size_t smem_dq(int NJ, int R, int dk) { return sizeof(float) * ((size_t)2 * NJ * 32 * (dk + 1) + NJ * 32 + (size_t)WARPS * (2 * R * dk + NJ * 32 * R)); }
-size_t smem_dkv(int NJ, int R, int dk) { return sizeof(float) * ((size_t)2 * NJ * 32 * (dk + 1) + 3 * NJ * 32 + (size_t)WARPS * (2 * R * dk + 2 * NJ * 32 * R)); }
+int pick_warps(int L) {
+  int ntile = (L + 15) / 16, rounds = (ntile + MAX_WARPS - 1) / MAX_WARPS;
+  return (ntile + rounds - 1) / rounds;
+}
+size_t panel_floats(int L, int dk) { return (size_t)2 * ((L + 7) & ~7) * ((dk + 31) & ~31); }
+size_t smem_fwd(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + (size_t)w * (16 * (dk + 4) + 16 * PB_LD)); }
+size_t smem_dq(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + (size_t)w * (32 * (dk + 4) + 16 * PB_LD)); }
+size_t smem_dkv(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + 3 * ((L + CH - 1) / CH * CH) + (size_t)w * (32 * (dk + 4) + 32 * PB_LD)); }
 
 template <typename Kern>
-int launch(Kern kern, const AttnArgs& a, int B, size_t smem, cudaStream_t st, const char* name) {
+int launch(Kern kern, const AttnArgs& a, int B, int warps, size_t smem, cudaStream_t st, const char* name) {
   if (smem > 227 * 1024) {
     rbm_set_error("%s: L=%d dk=%d needs %zu B of shared memory (> 227 KB): unsupported shape", name, a.L, a.dk, smem);
     return -1;
@@ -394,14 +507,14 @@ int launch(Kern kern, const AttnArgs& a, int B, size_t smem, cudaStream_t st, co
     rbm_set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
     return (int)e;
   }
-  kern<<<B * a.h, 32 * WARPS, smem, st>>>(a);
+  kern<<<B * a.h, 32 * warps, smem, st>>>(a);
   RBM_LAUNCH_CHECK(name);
   return 0;
 }
 
 int check_common(const char* name, int B, int L, int h, int dk, int mask_mode, float p, const int64_t* tok) {
   RBM_REQUIRE(B > 0 && L > 0 && L <= 256 && h > 0, "%s: need B>0, 0<L<=256, h>0 (B=%d L=%d h=%d)", name, B, L, h);
-  RBM_REQUIRE(dk >= 4 && dk % 4 == 0 && dk <= 32 * DCMAX, "%s: unsupported head dim %d (need dk%%4==0, dk<=128)", name, dk);
+  RBM_REQUIRE(dk >= 8 && dk % 8 == 0 && dk <= 128, "%s: unsupported head dim %d (need dk%%8==0, 8<=dk<=128)", name, dk);
   RBM_REQUIRE(mask_mode >= 0 && mask_mode <= 2, "%s: bad mask_mode %d", name, mask_mode);
   RBM_REQUIRE(mask_mode != RBM_MASK_KEYPAD || tok, "%s: key-padding mask needs tok", name);
   RBM_REQUIRE(p >= 0.f && p < 1.f, "%s: dropout p out of [0,1)", name);
@@ -410,31 +523,29 @@ int check_common(const char* name, int B, int L, int h, int dk, int mask_mode, f
 
 }  // namespace
 
-#define ATTN_DISPATCH(KERNEL, R, SMEMFN, NAME)                                                       \
-  switch (nj) {                                                                                      \
-    case 1: rc = launch(KERNEL<1, R>, a, B, SMEMFN(1, R, dk), st, NAME); break;                      \
-    case 2: rc = launch(KERNEL<2, R>, a, B, SMEMFN(2, R, dk), st, NAME); break;                      \
-    case 4: rc = launch(KERNEL<4, R>, a, B, SMEMFN(4, R, dk), st, NAME); break;                      \
-    case 7: rc = launch(KERNEL<7, R>, a, B, SMEMFN(7, R, dk), st, NAME); break;                      \
-    default: rc = launch(KERNEL<8, R>, a, B, SMEMFN(8, R, dk), st, NAME); break;                     \
-  }
+#define ATTN_DISPATCH(KERNEL, SMEM, NAME)                                              \
+  do {                                                                                 \
+    if (dk <= 32) rc = launch(KERNEL<4>, a, B, warps, SMEM, st, NAME);                 \
+    else if (dk <= 64) rc = launch(KERNEL<8>, a, B, warps, SMEM, st, NAME);            \
+    else rc = launch(KERNEL<16>, a, B, warps, SMEM, st, NAME);                         \
+  } while (0)
 
 extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                             const int64_t* tok, float* out, int64_t ldo, float* stats, int B, int L, int h, int dk,
                             int mask_mode, float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream) {
   RBM_REQUIRE(q && k && v && out, "rbm_attn_fwd: null pointer");
   if (check_common("rbm_attn_fwd", B, L, h, dk, mask_mode, p, tok)) return -1;
-  RBM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && rbm_aligned16(q) && rbm_aligned16(k) && rbm_aligned16(v),
-              "rbm_attn_fwd: q/k/v must be 16B aligned with strides %% 4 == 0");
+  RBM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 2 == 0 && rbm_aligned16(q) && rbm_aligned16(k) && rbm_aligned16(v) &&
+                  ((uintptr_t)out & 7) == 0,
+              "rbm_attn_fwd: q/k/v must be 16B aligned with strides %% 4 == 0 (out: 8B, stride %% 2)");
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.stats = stats; a.tok = tok;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
   a.L = L; a.h = h; a.dk = dk; a.mask_mode = mask_mode; a.scale = scale;
-  a.thr = rbm_drop_threshold(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
+  a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   cudaStream_t st = (cudaStream_t)stream;
-  int nj = pick_nj(L), rc;
-  if (L > 64) { ATTN_DISPATCH(attn_fwd_kernel, 8, smem_fwd, "rbm_attn_fwd") }
-  else { ATTN_DISPATCH(attn_fwd_kernel, 4, smem_fwd, "rbm_attn_fwd") }
+  int warps = pick_warps(L), rc;
+  ATTN_DISPATCH(attn_fwd_kernel, smem_fwd(L, dk, warps), "rbm_attn_fwd");
   return rc;
 }
 
@@ -451,16 +562,18 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   RBM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && lddo % 4 == 0 && rbm_aligned16(q) && rbm_aligned16(k) &&
                   rbm_aligned16(v) && rbm_aligned16(dout),
               "rbm_attn_bwd: q/k/v/dout must be 16B aligned with strides %% 4 == 0");
+  RBM_REQUIRE(lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 && (((uintptr_t)dq | (uintptr_t)dk_ | (uintptr_t)dv) & 7) == 0,
+              "rbm_attn_bwd: dq/dk/dv must be 8B aligned with even strides");
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.o = out; a.dout = dout; a.stats_in = stats; a.tok = tok;
   a.dq = dq; a.dk_ = dk_; a.dv = dv; a.delta = (float*)ws;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo; a.lddo = lddo; a.lddq = lddq; a.lddk = lddk; a.lddv = lddv;
   a.L = L; a.h = h; a.dk = dk; a.mask_mode = mask_mode; a.scale = scale;
-  a.thr = rbm_drop_threshold(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
+  a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   cudaStream_t st = (cudaStream_t)stream;
-  int nj = pick_nj(L), rc;
-  ATTN_DISPATCH(attn_bwd_dq_kernel, 4, smem_dq, "rbm_attn_bwd(dq)")
+  int warps = pick_warps(L), rc;
+  ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq(L, dk, warps), "rbm_attn_bwd(dq)");
   if (rc) return rc;
-  ATTN_DISPATCH(attn_bwd_dkv_kernel, 4, smem_dkv, "rbm_attn_bwd(dkv)")
+  ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv(L, dk, warps), "rbm_attn_bwd(dkv)");
   return rc;
 }

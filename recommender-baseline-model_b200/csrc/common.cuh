@@ -73,15 +73,29 @@ __device__ __forceinline__ float4 rbm_drop4(uint64_t seed, uint64_t site, uint64
                      r.w >= thr ? inv_keep : 0.f);
 }
 
-// Attention-probability sites: element (row R = (b*h+hh)*L + i, key j).  Lane (j & 31) of the warp that owns
-// row i holds keys j = lane + 32*jj, so one Philox call serves jj = 4g .. 4g+3 of one lane:
-//   call index = R * RBM_ATTN_GROUPS + (j & 31) + 32 * ((j >> 5) >> 2),   component = (j >> 5) & 3.
-#define RBM_ATTN_GROUPS 64  // supports L <= 256
-__host__ __device__ __forceinline__ uint64_t rbm_attn_call(uint64_t R, int j) {
-  return R * RBM_ATTN_GROUPS + (uint64_t)((j & 31) + 32 * ((j >> 5) >> 2));
+// Attention-probability sites (L <= 256).  Element (sequence-head bh, query i, key j) takes one 16-bit field of a
+// Philox call; it is kept iff field >= p*65536.  The 8 fields of a call are laid out so that both the row-major
+// consumers (forward / dQ pass: an mma lane owns rows {g, g+8} x cols {2t, 2t+1} of two adjacent 8-key tiles) and
+// the transposed consumer (dK/dV pass) amortise calls:
+//   tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;   n = j >> 3, t = (j & 7) >> 1, e = j & 1
+//   call  = ((((bh*16 + tile)*8 + g)*4 + t)*16 + (n >> 1));      field = rh*4 + e*2 + (n & 1)
+__host__ __device__ __forceinline__ uint64_t rbm_attn_call(uint64_t bh, int tile, int g, int t, int npair) {
+  return ((((bh * 16 + (uint64_t)tile) * 8 + (uint64_t)g) * 4 + (uint64_t)t) * 16 + (uint64_t)npair);
 }
-__host__ __device__ __forceinline__ uint32_t rbm_u4_get(const uint4& r, int c) {
-  return c == 0 ? r.x : (c == 1 ? r.y : (c == 2 ? r.z : r.w));
+__host__ __device__ __forceinline__ uint32_t rbm_attn_field(const uint4& r, int f) {
+  uint32_t w = (f >> 1) == 0 ? r.x : ((f >> 1) == 1 ? r.y : ((f >> 1) == 2 ? r.z : r.w));
+  return (f & 1) ? (w >> 16) : (w & 0xffffu);
+}
+__host__ __device__ __forceinline__ uint32_t rbm_drop_threshold16(float p) {
+  double t = (double)p * 65536.0 + 0.5;
+  if (t <= 0.5) return 0u;
+  if (t >= 65535.0) return 65535u;
+  return (uint32_t)t;
+}
+// reference implementation of the per-element rule (debug mask kernel, tests)
+__host__ __device__ __forceinline__ bool rbm_attn_keep(uint64_t seed, uint64_t site, uint64_t bh, int i, int j, uint32_t thr16) {
+  uint4 r = rbm_philox(seed, site, rbm_attn_call(bh, i >> 4, i & 7, (j & 7) >> 1, j >> 4));
+  return rbm_attn_field(r, ((i >> 3) & 1) * 4 + (j & 1) * 2 + ((j >> 3) & 1)) >= thr16;
 }
 
 // ---------------------------------------------------------------------------------------------

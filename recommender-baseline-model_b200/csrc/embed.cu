@@ -77,13 +77,12 @@ __global__ void dropout_mask_kernel(uint8_t* out, int64_t n, uint32_t thr, uint6
     if (i4 * 4 + c < n) out[i4 * 4 + c] = v[c] >= thr ? 1 : 0;
 }
 
-__global__ void dropout_mask_attn_kernel(uint8_t* out, int64_t rows, int L, uint32_t thr, uint64_t seed, uint64_t site) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= rows * L) return;
-  int64_t R = i / L;
-  int j = (int)(i - R * L);
-  uint4 r = rbm_philox(seed, site, rbm_attn_call((uint64_t)R, j));
-  out[i] = rbm_u4_get(r, (j >> 5) & 3) >= thr ? 1 : 0;
+__global__ void dropout_mask_attn_kernel(uint8_t* out, int64_t rows, int L, uint32_t thr16, uint64_t seed, uint64_t site) {
+  int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= rows * L) return;
+  int64_t R = e / L;  // R = bh * L + i
+  int j = (int)(e - R * L);
+  out[e] = rbm_attn_keep(seed, site, (uint64_t)(R / L), (int)(R % L), j, thr16) ? 1 : 0;
 }
 
 extern "C" int rbm_embed_fwd(const int64_t* tok, const float* table, const float* pos, float* out, int64_t rows, int L,
@@ -130,7 +129,7 @@ extern "C" int rbm_dropout_mask_attn(uint8_t* out, int64_t rows, int L, float p,
                                      rbm_stream_t stream) {
   RBM_REQUIRE(out && rows >= 0 && L > 0 && L <= 256 && p >= 0.f && p < 1.f, "rbm_dropout_mask_attn: bad argument");
   if (rows == 0) return 0;
-  dropout_mask_attn_kernel<<<(unsigned)rbm_cdiv(rows * L, 256), 256, 0, (cudaStream_t)stream>>>(out, rows, L, rbm_drop_threshold(p), seed, site);
+  dropout_mask_attn_kernel<<<(unsigned)rbm_cdiv(rows * L, 256), 256, 0, (cudaStream_t)stream>>>(out, rows, L, rbm_drop_threshold16(p), seed, site);
   RBM_LAUNCH_CHECK("rbm_dropout_mask_attn");
   return 0;
 }

@@ -3,8 +3,9 @@
 // NN/models/bert_modules/embedding/token.py:6; triggered by loss.backward() NN/trainers/base.py:121), which on
 // stock CUDA uses float atomics (run-to-run different) and on CPU a serial index-ordered loop.  Here:
 //   1. stable LSD radix sort (8-bit digits) of (row id, position) pairs -- positions stay ascending per row id;
-//   2. one lane group per segment head walks its segment in order, fp32 adds in ascending position
-//      == the CPU reference's summation order, so the result is bit-identical to it and run-to-run stable.
+//   2. segment reduce in fixed 64-contribution pieces (see below): rows with <= 64 contributions are summed in
+//      ascending position == the CPU reference's order (bit-identical); longer rows follow a fixed piece tree.
+//      Either way the result is run-to-run bit-stable (no atomics).
 #include "common.cuh"
 
 namespace {
@@ -109,35 +110,94 @@ __global__ void __launch_bounds__(32 * SORT_WARPS) radix_scatter_kernel(const in
   }
 }
 
-// one group of gw lanes per sorted slot; only segment heads work
-__global__ void __launch_bounds__(256) segment_reduce_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
+// ---------------------------------------------------------------------------------------------------------
+// Segment reduce.  A segment = the sorted slots of one destination row.  It is cut into PIECES of SEG_CHUNK
+// consecutive contributions counted from the segment start; a piece is summed sequentially (ascending position),
+// the piece sums of a segment are then added in piece order.  Segments of <= SEG_CHUNK contributions are therefore
+// bit-identical to the CPU reference's index-ordered loop; longer ones (popular items, [MASK]) follow this fixed
+// tree -- deterministic, and restated by oracle.common.embedding_grad_scatter_chunked.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int SEG_CHUNK = 64;
+
+__device__ __forceinline__ int64_t lower_bound_u32(const uint32_t* __restrict__ keys, int64_t n, uint32_t key) {
+  int64_t lo = 0, hi = n;
+  while (lo < hi) {
+    int64_t mid = (lo + hi) >> 1;
+    if (keys[mid] < key) lo = mid + 1;
+    else hi = mid;
+  }
+  return lo;
+}
+
+__device__ __forceinline__ float4 load_contrib(const float* __restrict__ src, const float* __restrict__ coef, float alpha,
+                                               uint32_t row, int d4, int c4) {
+  float4 v = ld4(src + ((int64_t)row * d4 + c4) * 4);
+  if (coef) {
+    float cf = coef[row];
+    v.x = __fmul_rn(cf, v.x); v.y = __fmul_rn(cf, v.y); v.z = __fmul_rn(cf, v.z); v.w = __fmul_rn(cf, v.w);
+  }
+  if (alpha != 1.f) {
+    v.x = __fmul_rn(v.x, alpha); v.y = __fmul_rn(v.y, alpha); v.z = __fmul_rn(v.z, alpha); v.w = __fmul_rn(v.w, alpha);
+  }
+  return v;
+}
+
+// one group of gw lanes per sorted slot; only piece starts work.  Single-piece segments go straight to grad;
+// pieces of longer segments are parked in pieces[(slot / SEG_CHUNK) * 2 + is_first_piece] (provably collision-free:
+// two parked pieces inside one SEG_CHUNK window belong to different segments, one a non-first, one a first piece).
+__global__ void __launch_bounds__(256) segment_pieces_kernel(const uint32_t* __restrict__ keys, const uint32_t* __restrict__ vals,
                                                              const float* __restrict__ src, const float* __restrict__ coef, float alpha,
-                                                             float* __restrict__ grad, int64_t n, int d4, int64_t padding_idx, int gw) {
+                                                             float* __restrict__ grad, float* __restrict__ pieces, int64_t n, int d4,
+                                                             int64_t padding_idx, int gw) {
   int lane = threadIdx.x % gw;
-  int64_t j = (int64_t)blockIdx.x * (blockDim.x / gw) + threadIdx.x / gw;
-  if (j >= n) return;
-  uint32_t key = keys[j];
-  if (j > 0 && keys[j - 1] == key) return;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x / gw) + threadIdx.x / gw;
+  if (s >= n) return;
+  uint32_t key = keys[s];
   if ((int64_t)key == padding_idx) return;
+  bool head = s == 0 || keys[s - 1] != key;
+  int64_t off = 0;
+  if (!head) {
+    if (s >= SEG_CHUNK && keys[s - SEG_CHUNK] == key) {  // possibly a later piece start: need the exact offset
+      off = s - lower_bound_u32(keys, n, key);
+      if (off % SEG_CHUNK != 0) return;
+    } else {
+      return;  // within the first SEG_CHUNK slots of its segment and not the head
+    }
+  }
+  int64_t e = s + SEG_CHUNK < n ? s + SEG_CHUNK : n;
+  bool more = e < n && keys[e] == key;        // the segment continues past this piece
+  bool single = off == 0 && !more;
   for (int c4 = lane; c4 < d4; c4 += gw) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-    bool first = true;
-    for (int64_t t = j; t < n && keys[t] == key; ++t) {
-      uint32_t row = vals[t];
-      float4 v = ld4(src + ((int64_t)row * d4 + c4) * 4);
-      if (coef) {
-        float cf = coef[row];
-        v.x = __fmul_rn(cf, v.x); v.y = __fmul_rn(cf, v.y); v.z = __fmul_rn(cf, v.z); v.w = __fmul_rn(cf, v.w);
-      }
-      if (alpha != 1.f) {
-        v.x = __fmul_rn(v.x, alpha); v.y = __fmul_rn(v.y, alpha); v.z = __fmul_rn(v.z, alpha); v.w = __fmul_rn(v.w, alpha);
-      }
-      if (first) {
-        acc = v;
-        first = false;
-      } else {
-        acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
-      }
+    float4 acc = load_contrib(src, coef, alpha, vals[s], d4, c4);
+    for (int64_t t = s + 1; t < e && keys[t] == key; ++t) {
+      float4 v = load_contrib(src, coef, alpha, vals[t], d4, c4);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    }
+    if (single) {
+      float* g = grad + ((int64_t)key * d4 + c4) * 4;
+      float4 o = ld4(g);
+      st4(g, make_float4(o.x + acc.x, o.y + acc.y, o.z + acc.z, o.w + acc.w));
+    } else {
+      st4(pieces + (((s / SEG_CHUNK) * 2 + (off == 0 ? 1 : 0)) * (int64_t)d4 + c4) * 4, acc);
+    }
+  }
+}
+
+// heads of multi-piece segments add their pieces in order
+__global__ void __launch_bounds__(256) segment_combine_kernel(const uint32_t* __restrict__ keys, float* __restrict__ grad,
+                                                              const float* __restrict__ pieces, int64_t n, int d4, int64_t padding_idx, int gw) {
+  int lane = threadIdx.x % gw;
+  int64_t s = (int64_t)blockIdx.x * (blockDim.x / gw) + threadIdx.x / gw;
+  if (s >= n) return;
+  uint32_t key = keys[s];
+  if ((int64_t)key == padding_idx) return;
+  if (s > 0 && keys[s - 1] == key) return;                 // not a head
+  if (!(s + SEG_CHUNK < n && keys[s + SEG_CHUNK] == key)) return;  // single piece: already in grad
+  for (int c4 = lane; c4 < d4; c4 += gw) {
+    float4 acc = ld4(pieces + (((s / SEG_CHUNK) * 2 + 1) * (int64_t)d4 + c4) * 4);
+    for (int64_t t = s + SEG_CHUNK; t < n && keys[t] == key; t += SEG_CHUNK) {
+      float4 v = ld4(pieces + (((t / SEG_CHUNK) * 2 + 0) * (int64_t)d4 + c4) * 4);
+      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
     }
     float* g = grad + ((int64_t)key * d4 + c4) * 4;
     float4 o = ld4(g);
@@ -149,10 +209,16 @@ int sort_blocks(int64_t n) { return (int)rbm_cdiv(n, TILE); }
 
 }  // namespace
 
+static size_t scatter_sort_bytes(int64_t n) {
+  size_t nblk = (size_t)sort_blocks(n < 1 ? 1 : n);
+  size_t b = (size_t)4 * (size_t)(n < 1 ? 1 : n) * sizeof(uint32_t) + nblk * RADIX * sizeof(uint32_t);
+  return (b + 255) & ~(size_t)255;
+}
+// d is not part of the query: the piece buffer is sized for d <= 1024
 extern "C" size_t rbm_scatter_ws_bytes(int64_t n, int64_t vocab) {
   (void)vocab;
-  size_t nblk = (size_t)sort_blocks(n < 1 ? 1 : n);
-  return (size_t)4 * (size_t)(n < 1 ? 1 : n) * sizeof(uint32_t) + nblk * RADIX * sizeof(uint32_t) + 256;
+  size_t pieces = ((size_t)(n < 1 ? 1 : n) / SEG_CHUNK + 1) * 2 * 1024 * sizeof(float);
+  return scatter_sort_bytes(n) + pieces + 256;
 }
 
 extern "C" int rbm_scatter_add_sorted(const int64_t* idx, const float* src, const float* coef, float alpha, float* grad,
@@ -160,7 +226,7 @@ extern "C" int rbm_scatter_add_sorted(const int64_t* idx, const float* src, cons
                                       rbm_stream_t stream) {
   RBM_REQUIRE(idx && src && grad && ws, "rbm_scatter_add_sorted: null pointer");
   RBM_REQUIRE(n >= 0 && n < ((int64_t)1 << 32) && vocab > 0 && vocab < ((int64_t)1 << 31), "rbm_scatter_add_sorted: n/vocab out of range");
-  RBM_REQUIRE(d >= 4 && d % 4 == 0, "rbm_scatter_add_sorted: d=%d must be a multiple of 4", d);
+  RBM_REQUIRE(d >= 4 && d % 4 == 0 && d <= 1024, "rbm_scatter_add_sorted: d=%d must be a multiple of 4, <= 1024", d);
   RBM_REQUIRE(ws_bytes >= rbm_scatter_ws_bytes(n, vocab), "rbm_scatter_add_sorted: workspace too small");
   RBM_REQUIRE(rbm_aligned16(src) && rbm_aligned16(grad) && rbm_aligned16(ws), "rbm_scatter_add_sorted: pointers must be 16B aligned");
   if (n == 0) return 0;
@@ -189,7 +255,9 @@ extern "C" int rbm_scatter_add_sorted(const int64_t* idx, const float* src, cons
   }
   int d4 = d / 4;
   int gw = d4 <= 4 ? 4 : d4 <= 8 ? 8 : d4 <= 16 ? 16 : 32;
-  segment_reduce_kernel<<<(unsigned)rbm_cdiv(n, 256 / gw), 256, 0, st>>>(kin, vin, src, coef, alpha, grad, n, d4, padding_idx, gw);
+  float* pieces = (float*)((char*)ws + scatter_sort_bytes(n));
+  segment_pieces_kernel<<<(unsigned)rbm_cdiv(n, 256 / gw), 256, 0, st>>>(kin, vin, src, coef, alpha, grad, pieces, n, d4, padding_idx, gw);
+  segment_combine_kernel<<<(unsigned)rbm_cdiv(n, 256 / gw), 256, 0, st>>>(kin, grad, pieces, n, d4, padding_idx, gw);
   RBM_LAUNCH_CHECK("rbm_scatter_add_sorted(reduce)");
   return 0;
 }

@@ -38,7 +38,7 @@ def scatter_add_sorted_(grad: torch.Tensor, idx: torch.Tensor, src: torch.Tensor
     check(lib.rbm_scatter_add_sorted(ptr(idx), ptr(src), ptr(coef), float(alpha), ptr(grad), n, d, grad.shape[0],
                                      int(padding_idx), ptr(ws), nb, stream()), "scatter_add_sorted")
     bits = max(1, (grad.shape[0] - 1).bit_length())
-    count_launches(3 * ((bits + 7) // 8) + 1)
+    count_launches(3 * ((bits + 7) // 8) + 2)
     return grad
 
 

@@ -65,14 +65,16 @@ def test_scatter_add_bit_exact(n, V, d):
     idx = (rng.zipf(1.2, size=n) % V).astype(np.int64)
     rows = rng.randn(n, d).astype(np.float32)
     coef = rng.randn(n).astype(np.float32)
-    ref = oc.embedding_grad_scatter_fast(idx, rows, V, padding_idx=0)
+    ref = oc.embedding_grad_scatter_chunked(idx, rows, V, padding_idx=0)
+    short = np.bincount(idx, minlength=V) <= 64  # rows with <= 64 contributions: the reference's own order, bit for bit
+    np.testing.assert_array_equal(ref[short], oc.embedding_grad_scatter_fast(idx, rows, V, padding_idx=0)[short])
     grad = torch.zeros(V, d, device=DEV)
     ops.scatter_add_sorted_(grad, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), None, 1.0, 0)
     np.testing.assert_array_equal(grad.cpu().numpy(), ref)  # bit-exact, run-to-run and vs the CPU order
     grad2 = torch.zeros(V, d, device=DEV)
     ops.scatter_add_sorted_(grad2, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), None, 1.0, 0)
     assert torch.equal(grad, grad2)
-    ref_c = oc.embedding_grad_scatter_fast(idx, rows * coef[:, None], V, padding_idx=0)
+    ref_c = oc.embedding_grad_scatter_chunked(idx, rows * coef[:, None], V, padding_idx=0)
     grad3 = torch.zeros(V, d, device=DEV)
     ops.scatter_add_sorted_(grad3, g(torch.from_numpy(idx)), g(torch.from_numpy(rows)), g(torch.from_numpy(coef)), 1.0, 0)
     np.testing.assert_array_equal(grad3.cpu().numpy(), ref_c)
@@ -83,7 +85,11 @@ def test_scatter_golden():
     z = np.load("tests/golden/scatter_adam.npz")
     grad = torch.zeros(53, 16, device=DEV)
     ops.scatter_add_sorted_(grad, g(torch.from_numpy(z["scatter.idx"])), g(torch.from_numpy(z["scatter.rows"])), None, 1.0, 0)
-    np.testing.assert_array_equal(grad.cpu().numpy(), z["scatter.grad"])
+    got = grad.cpu().numpy()
+    short = np.bincount(z["scatter.idx"], minlength=53) <= 64
+    np.testing.assert_array_equal(got[short], z["scatter.grad"][short])  # torch's own embedding_dense_backward, bit for bit
+    np.testing.assert_allclose(got[~short], z["scatter.grad"][~short], rtol=1e-5, atol=1e-5)  # >64 contributions: fixed piece tree
+    np.testing.assert_array_equal(got, oc.embedding_grad_scatter_chunked(z["scatter.idx"], z["scatter.rows"], 53))
 
 
 # -------------------------------------------------------------------------------------------- layernorm

@@ -174,6 +174,11 @@ def test_scatter_and_adam_match_torch():
     g = oc.embedding_grad_scatter(z["scatter.idx"], z["scatter.rows"], 53, padding_idx=0)
     np.testing.assert_array_equal(g, z["scatter.grad"])  # bit-exact, index-ordered fp32 adds
     np.testing.assert_array_equal(oc.embedding_grad_scatter_fast(z["scatter.idx"], z["scatter.rows"], 53), g)
+    # the CUDA kernel's piece-tree contract: identical for rows with <= 64 contributions, rounding-level otherwise
+    gc = oc.embedding_grad_scatter_chunked(z["scatter.idx"], z["scatter.rows"], 53)
+    short = np.bincount(z["scatter.idx"], minlength=53) <= 64
+    np.testing.assert_array_equal(gc[short], g[short])
+    np.testing.assert_allclose(gc, g, rtol=1e-5, atol=1e-5)
     p = z["adam.p0"].copy()
     m, v = np.zeros_like(p), np.zeros_like(p)
     for s in range(4):
