@@ -120,6 +120,15 @@ __device__ __forceinline__ float quad_sum(float v) {
   return v + __shfl_xor_sync(0xffffffffu, v, 2);
 }
 __device__ __forceinline__ bool masked_inf(int mode, int i, int j, int L) { return j >= L || (mode == RBM_MASK_CAUSAL && j > i); }
+// Scores are kept in the log2 domain (q is pre-multiplied by scale*log2(e)): softmax needs one ex2.approx per element.
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+#define RBM_LOG2E 1.4426950408889634f
+#define RBM_LN2 0.6931471805599453f
+#define RBM_PADFILL (-1.0e9f * RBM_LOG2E)  // masked_fill(mask == 0, -1e9) expressed in the log2 domain
 
 // acc[nt] (+)= Atile(16 x dk) . panel[jb + nt*8 .. +8][0..dk)^T  for nt < 8
 __device__ __forceinline__ void tile_dot_panel(float (&acc)[8][4], const float* atile, int lda, const float* panel, int LD, int jb,
@@ -167,7 +176,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
   float* Kp = sm;
   float* Vp = Kp + LP8 * LD;
   float* padk = Vp + LP8 * LD;  // [LPC]
-  float* wbase = padk + LPC + (size_t)warp * (16 * QLD + 16 * PB_LD);
+  float* chunk_pad = padk + LPC;  // [4]: chunk contains a padded key
+  float* wbase = chunk_pad + 4 + (size_t)warp * (16 * QLD + 16 * PB_LD);
   float* Qs = wbase;             // [16][QLD] scaled q tile
   float* Pb = wbase + 16 * QLD;  // [16][PB_LD]
 
@@ -176,9 +186,15 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
   for (int j = threadIdx.x; j < LPC; j += blockDim.x)
     padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
   __syncthreads();
+  if (threadIdx.x < 4) {
+    float any = 0.f;
+    for (int j = threadIdx.x * CH; j < (threadIdx.x + 1) * CH && j < LPC; ++j) any += padk[j];
+    chunk_pad[threadIdx.x] = any;
+  }
+  __syncthreads();
 
   for (int i0 = warp * 16; i0 < L; i0 += nwarps * 16) {
-    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
+    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale * RBM_LOG2E, lane);
     __syncwarp();
     float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f};
     float o[DT][4];
@@ -191,22 +207,32 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
       for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
       tile_dot_panel(s, Qs, QLD, Kp, LD, jb, LP8, dk, g, t);
       float cm[2] = {-INFINITY, -INFINITY};
+      // masking only where it can bite: padded keys (chunk flag), the causal diagonal chunk, the ragged last chunk
+      const bool need_mask = chunk_pad[jb / CH] != 0.f || jb + CH > L || (a.mask_mode == RBM_MASK_CAUSAL && jb + CH > i0);
+      if (need_mask) {
 #pragma unroll
-      for (int nt = 0; nt < 8; ++nt)
+        for (int nt = 0; nt < 8; ++nt) {
+          float2 pk = *reinterpret_cast<const float2*>(padk + jb + nt * 8 + 2 * t);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          int hrow = c >> 1, j = jb + nt * 8 + 2 * t + (c & 1), i = i0 + g + 8 * hrow;
-          float v = s[nt][c];
-          if (padk[j] != 0.f) v = -1e9f;
-          if (masked_inf(a.mask_mode, i, j, L)) v = -INFINITY;
-          s[nt][c] = v;
-          cm[hrow] = fmaxf(cm[hrow], v);
+          for (int c = 0; c < 4; ++c) {
+            int hrow = c >> 1, j = jb + nt * 8 + 2 * t + (c & 1), i = i0 + g + 8 * hrow;
+            float v = s[nt][c];
+            if (((c & 1) ? pk.y : pk.x) != 0.f) v = RBM_PADFILL;
+            if (masked_inf(a.mask_mode, i, j, L)) v = -INFINITY;
+            s[nt][c] = v;
+          }
         }
+      }
+#pragma unroll
+      for (int nt = 0; nt < 8; ++nt) {
+        cm[0] = fmaxf(cm[0], fmaxf(s[nt][0], s[nt][1]));
+        cm[1] = fmaxf(cm[1], fmaxf(s[nt][2], s[nt][3]));
+      }
       float base[2], alpha[2], ps[2] = {0.f, 0.f};
 #pragma unroll
       for (int hrow = 0; hrow < 2; ++hrow) {
         float mn = fmaxf(m[hrow], quad_max(cm[hrow]));
-        alpha[hrow] = m[hrow] == -INFINITY ? 0.f : expf(m[hrow] - mn);
+        alpha[hrow] = m[hrow] == -INFINITY ? 0.f : ex2(m[hrow] - mn);
         base[hrow] = mn == -INFINITY ? 0.f : mn;
         m[hrow] = mn;
       }
@@ -214,7 +240,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
       for (int nt = 0; nt < 8; ++nt)
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          float p = expf(s[nt][c] - base[c >> 1]);
+          float p = ex2(s[nt][c] - base[c >> 1]);
           s[nt][c] = p;
           ps[c >> 1] += p;
         }
@@ -282,7 +308,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
   float* Kp = sm;
   float* Vp = Kp + LP8 * LD;
   float* padk = Vp + LP8 * LD;
-  float* wbase = padk + LPC + (size_t)warp * (32 * QLD + 16 * PB_LD);
+  float* chunk_pad = padk + LPC;
+  float* wbase = chunk_pad + 4 + (size_t)warp * (32 * QLD + 16 * PB_LD);
   float* Qs = wbase;              // [16][QLD] scaled q
   float* dOs = wbase + 16 * QLD;  // [16][QLD]
   float* Pb = dOs + 16 * QLD;     // [16][PB_LD] dS chunk
@@ -292,9 +319,15 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
   for (int j = threadIdx.x; j < LPC; j += blockDim.x)
     padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
   __syncthreads();
+  if (threadIdx.x < 4) {
+    float any = 0.f;
+    for (int j = threadIdx.x * CH; j < (threadIdx.x + 1) * CH && j < LPC; ++j) any += padk[j];
+    chunk_pad[threadIdx.x] = any;
+  }
+  __syncthreads();
 
   for (int i0 = warp * 16; i0 < L; i0 += nwarps * 16) {
-    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale, lane);
+    stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale * RBM_LOG2E, lane);
     stage_tile(dOs, QLD, a.dout, a.lddo, row0, col0, i0, L, dk, 1.f, lane);
     float delta[2] = {0.f, 0.f}, mx[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
     for (int r = 0; r < 16; ++r) {
@@ -343,8 +376,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
           for (int c = 0; c < 4; ++c) {
             int hrow = c >> 1, j = jb + nt * 8 + 2 * t + (c & 1), i = i0 + g + 8 * hrow;
             bool pad = padk[j] != 0.f;
-            float v = pad ? -1e9f : s[nt][c];
-            float p = (i >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mx[hrow]) * inv[hrow];
+            float v = pad ? RBM_PADFILL : s[nt][c];
+            float p = (i >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : ex2(v - mx[hrow]) * inv[hrow];
             float mk = 1.f;
             if (a.thr16) mk = rbm_attn_field(rnd, hrow * 4 + (c & 1) * 2 + bb) >= a.thr16 ? a.inv_keep : 0.f;
             // masked_fill(-1e9) replaces the score by a constant: no gradient reaches q.k through a padded key
@@ -397,7 +430,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
   float* P1 = Vs + 16 * QLD;     // [16][PB_LD] dS^T chunk
   float* P2 = P1 + 16 * PB_LD;   // [16][PB_LD] P~^T chunk
 
-  load_panel(Qp, a.q, a.ldq, row0, col0, L, LP8, dk, LD, a.scale);
+  load_panel(Qp, a.q, a.ldq, row0, col0, L, LP8, dk, LD, a.scale * RBM_LOG2E);
   load_panel(dOp, a.dout, a.lddo, row0, col0, L, LP8, dk, LD, 1.f);
   for (int i = threadIdx.x; i < LPC; i += blockDim.x) {
     bool in = i < L;
@@ -449,8 +482,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
 #pragma unroll
             for (int hrow = 0; hrow < 2; ++hrow) {
               const int c = hrow * 2 + e, j = j0 + g + 8 * hrow;
-              float v = jpad[hrow] ? -1e9f : s[nt][c];
-              float p = (i >= L || j >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : expf(v - mi) * ii;
+              float v = jpad[hrow] ? RBM_PADFILL : s[nt][c];
+              float p = (i >= L || j >= L || masked_inf(a.mask_mode, i, j, L)) ? 0.f : ex2(v - mi) * ii;
               float mk = 1.f;
               if (a.thr16) mk = rbm_attn_field(rnd, bb * 4 + (g & 1) * 2 + hrow) >= a.thr16 ? a.inv_keep : 0.f;
               s[nt][c] = jpad[hrow] ? 0.f : p * (mk * dp[nt][c] - di);  // dS^T (no score gradient through a padded key)
@@ -467,7 +500,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
         *reinterpret_cast<float2*>(P2 + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(dp[nt][2], dp[nt][3]);
       }
       __syncwarp();
-      ptile_times_panel<DT>(dkacc, P1, Qp, LD, ib, LP8, dk, g, t);   // Qp carries `scale`
+      ptile_times_panel<DT>(dkacc, P1, Qp, LD, ib, LP8, dk, g, t);   // Qp carries scale*log2(e); ln2 applied at the store
       ptile_times_panel<DT>(dvacc, P2, dOp, LD, ib, LP8, dk, g, t);
       __syncwarp();
     }
@@ -478,7 +511,8 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
 #pragma unroll
         for (int dt = 0; dt < DT; ++dt)
           if (dt * 8 < dk) {
-            *reinterpret_cast<float2*>(a.dk_ + (row0 + j) * a.lddk + col0 + dt * 8 + 2 * t) = make_float2(dkacc[dt][2 * hrow], dkacc[dt][2 * hrow + 1]);
+            *reinterpret_cast<float2*>(a.dk_ + (row0 + j) * a.lddk + col0 + dt * 8 + 2 * t) =
+                make_float2(dkacc[dt][2 * hrow] * RBM_LN2, dkacc[dt][2 * hrow + 1] * RBM_LN2);
             *reinterpret_cast<float2*>(a.dv + (row0 + j) * a.lddv + col0 + dt * 8 + 2 * t) = make_float2(dvacc[dt][2 * hrow], dvacc[dt][2 * hrow + 1]);
           }
       }
@@ -492,12 +526,14 @@ int pick_warps(int L) {
   return (ntile + rounds - 1) / rounds;
 }
 size_t panel_floats(int L, int dk) { return (size_t)2 * ((L + 7) & ~7) * ((dk + 31) & ~31); }
-size_t smem_fwd(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + (size_t)w * (16 * (dk + 4) + 16 * PB_LD)); }
-size_t smem_dq(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + (size_t)w * (32 * (dk + 4) + 16 * PB_LD)); }
+size_t smem_fwd(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * (16 * (dk + 4) + 16 * PB_LD)); }
+size_t smem_dq(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * (32 * (dk + 4) + 16 * PB_LD)); }
 size_t smem_dkv(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + 3 * ((L + CH - 1) / CH * CH) + (size_t)w * (32 * (dk + 4) + 32 * PB_LD)); }
 
 template <typename Kern>
-int launch(Kern kern, const AttnArgs& a, int B, int warps, size_t smem, cudaStream_t st, const char* name) {
+int launch(Kern kern, const AttnArgs& a, int B, int warps, size_t (*smem_fn)(int, int, int), cudaStream_t st, const char* name) {
+  while (warps > 1 && smem_fn(a.L, a.dk, warps) > 227 * 1024) --warps;  // fewer warps per CTA when the tiles are wide
+  size_t smem = smem_fn(a.L, a.dk, warps);
   if (smem > 227 * 1024) {
     rbm_set_error("%s: L=%d dk=%d needs %zu B of shared memory (> 227 KB): unsupported shape", name, a.L, a.dk, smem);
     return -1;
@@ -545,7 +581,7 @@ extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   cudaStream_t st = (cudaStream_t)stream;
   int warps = pick_warps(L), rc;
-  ATTN_DISPATCH(attn_fwd_kernel, smem_fwd(L, dk, warps), "rbm_attn_fwd");
+  ATTN_DISPATCH(attn_fwd_kernel, smem_fwd, "rbm_attn_fwd");
   return rc;
 }
 
@@ -572,8 +608,8 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   cudaStream_t st = (cudaStream_t)stream;
   int warps = pick_warps(L), rc;
-  ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq(L, dk, warps), "rbm_attn_bwd(dq)");
+  ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq, "rbm_attn_bwd(dq)");
   if (rc) return rc;
-  ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv(L, dk, warps), "rbm_attn_bwd(dkv)");
+  ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
   return rc;
 }

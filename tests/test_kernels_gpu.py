@@ -196,7 +196,7 @@ def test_attention_packed(B, Ln, h, dk, mode, p):
     out.backward(g(dout))
     mask = ops.dropout_mask_attn(B * h * Ln, Ln, p, seed, site, DEV).cpu().view(B, h, Ln, Ln) if p > 0 else None
     if p > 0:
-        assert abs(mask.float().mean().item() - (1 - p)) < 0.02
+        assert abs(mask.float().mean().item() - (1 - p)) < 0.01 + 4 * math.sqrt(p * (1 - p) / mask.numel())
     qr = qkv.clone().requires_grad_(True)
     q, k, v = (qr[:, i * d:(i + 1) * d].view(B, Ln, h, dk).transpose(1, 2) for i in range(3))
     ref = _ref_attention(q, k, v, tok, mode, scale, p, mask).transpose(1, 2).reshape(B * Ln, d)
