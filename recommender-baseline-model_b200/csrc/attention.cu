@@ -34,17 +34,16 @@ struct AttnArgs {
 
 __device__ __forceinline__ int swz(int r) { return (((r & 3) << 1) | ((r >> 2) & 1)) << 2; }
 
-__device__ __forceinline__ uint32_t f2tf32(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return r;
-}
+// 3xTF32 operand split.  The tensor core reads only the upper 19 bits of a tf32 operand, so hi = x with the low 13
+// mantissa bits cleared (one LOP3; cvt.rna.tf32 is emulated with ~10 integer instructions on sm_100) and lo = x - hi,
+// which is exact in fp32 and is itself truncated by the hardware to its top 11 significant bits: the dropped part is
+// O(2^-22 |x|), the same order as the lo*lo term 3xTF32 neglects anyway.
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  hi = f2tf32(x);
-  lo = f2tf32(x - __uint_as_float(hi));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
 }
@@ -74,10 +73,10 @@ __device__ __forceinline__ FragA load_a(const float* tile, int ld, int k0, int g
 // B fragment, contraction along the panel's COLUMNS: B[k][n] = panel[n0 + n][k0 + k]
 __device__ __forceinline__ FragB load_b_nk(const float* panel, int LD, int n0, int k0, int g, int t) {
   const float* row = panel + (n0 + g) * LD;
-  int s = swz(g);
+  int c0 = (k0 ^ swz(g)) + t;  // == (k0 + t) ^ swz(g): k0 is a multiple of 8, the swizzle touches bits 2..4 only
   FragB f;
-  split_tf32(row[(k0 + t) ^ s], f.hi[0], f.lo[0]);
-  split_tf32(row[(k0 + t + 4) ^ s], f.hi[1], f.lo[1]);
+  split_tf32(row[c0], f.hi[0], f.lo[0]);
+  split_tf32(row[c0 ^ 4], f.hi[1], f.lo[1]);
   return f;
 }
 // B fragment, contraction along the panel's ROWS: B[k][n] = panel[k0 + k][n0 + n]

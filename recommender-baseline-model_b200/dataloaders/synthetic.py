@@ -41,8 +41,11 @@ def synthetic_interactions(num_users: int, num_items: int, mean_len: float, min_
         mu = np.log(max(mean_len, 1.0)) - 0.5 * sigma * sigma
         lens = np.clip(np.round(rng.lognormal(mu, sigma, size=num_users)), min_len, max_user_len).astype(np.int64)
     flat = draw(rng, int(lens.sum()))
-    rep = np.flatnonzero(flat[1:] == flat[:-1]) + 1  # break immediate repeats
-    flat[rep] = flat[rep] % num_items + 1
+    while True:  # break immediate repeats (a replacement can collide with its right neighbour: iterate)
+        rep = np.flatnonzero(flat[1:] == flat[:-1]) + 1
+        if rep.size == 0:
+            break
+        flat[rep] = (flat[rep] + rng.randint(0, num_items - 1, size=rep.size)) % num_items + 1
     out, o = [], 0
     for n in lens:
         out.append(flat[o:o + n])
