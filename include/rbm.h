@@ -84,6 +84,8 @@ int rbm_layernorm_bwd(const float* x, const float* gamma, const float* dy, const
 /* ---- Linear with fused epilogue --------------------------------------------------------------------
  * pre = x[M,K] . w[N,K]^T + bias        (optionally stored to `pre` when act needs it in backward)
  * y   = rowkeep * dropB( residual + dropA( act(pre) ) )      rowkeep(r) = row_tok ? row_tok[r]!=0 : 1
+ * Blackwell path: tcgen05.mma kind::tf32 (fp32 operands read as TF32, fp32 accumulation in TMEM), TMA-fed, whenever
+ * K % 32 == 0 and N % 16 == 0; other shapes use the fp32 SIMT kernel.  RBM_LINEAR_IMPL=simt forces the latter.
  * replaces nn.Linear / Conv1d(k=1) + Dropout + activation + residual chains:
  *   NN/models/bert_modules/attention/multi_head.py:29-30,40; utils/feed_forward.py:16; utils/sublayer.py:18;
  *   transformer.py:32; NN/models/sas_model/sas.py:16-19,75,79,84 (in/out-proj of nn.MultiheadAttention). */
@@ -95,9 +97,10 @@ int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bia
 int rbm_linear_epilogue_bwd(const float* dout, const float* pre, float* dpre, float* dres, int64_t M, int N,
                             int act, const int64_t* row_tok, float pA, uint64_t siteA, float pB,
                             uint64_t siteB, uint64_t seed, rbm_stream_t stream);
-/* dx[M,K] = dpre[M,N] . w[N,K] */
+/* dx[M,K] = dpre[M,N] . w[N,K]   (ws: rbm_linear_bwd_data_ws_bytes(N,K) bytes, holds w^T for the tcgen05 path) */
+size_t rbm_linear_bwd_data_ws_bytes(int N, int K);
 int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const float* w, float* dx, int64_t lddx, int64_t M,
-                        int N, int K, rbm_stream_t stream);
+                        int N, int K, void* ws, size_t ws_bytes, rbm_stream_t stream);
 /* dw[N,K] = dpre^T . x ; db[N] = colsum(dpre)  (split over M, fixed-order reduction; ws from _ws_bytes) */
 size_t rbm_linear_bwd_weight_ws_bytes(int64_t M, int N, int K);
 int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const float* x, int64_t ldx, float* dw, float* db,

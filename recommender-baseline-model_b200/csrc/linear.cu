@@ -5,7 +5,10 @@
 //
 // Round-1 implementation: register-tiled SIMT fp32 GEMM (exact fp32 parity with the reference).  The tcgen05 /
 // TMEM path for these shapes is tracked in DESIGN.md ("next").
+#include <stdlib.h>
+#include <string.h>
 #include "common.cuh"
+#include "tc_gemm.cuh"
 
 namespace {
 
@@ -258,6 +261,27 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const float* __restri
   st4(dpre + i * 4, g);
 }
 
+// RBM_LINEAR_IMPL=simt forces the fp32 SIMT kernels (A/B testing); default: tcgen05 wherever the shape allows
+bool use_tc() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RBM_LINEAR_IMPL");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, int rows, int cols) {
+  __shared__ float tile[32][33];
+  int c = blockIdx.x * 32 + threadIdx.x, r0 = blockIdx.y * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (r0 + i < rows && c < cols) tile[i][threadIdx.x] = src[(int64_t)(r0 + i) * cols + c];
+  __syncthreads();
+  int r = r0 + threadIdx.x, c0 = blockIdx.x * 32;
+  for (int i = threadIdx.y; i < 32; i += 8)
+    if (c0 + i < cols && r < rows) dst[(int64_t)(c0 + i) * rows + r] = tile[threadIdx.x][i];
+}
+
 int tn_splits(int64_t M, int N, int K) {
   int64_t tiles = rbm_cdiv(N, 64) * rbm_cdiv(K, 64);
   int64_t want = rbm_cdiv((int64_t)RBM_NUM_SMS * 4, tiles);
@@ -281,6 +305,11 @@ extern "C" int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const
   RBM_REQUIRE(rbm_aligned16(x) && rbm_aligned16(w) && rbm_aligned16(y) && rbm_aligned16(bias) && rbm_aligned16(pre) && rbm_aligned16(residual),
               "rbm_linear_fwd: pointers must be 16B aligned");
   if (M == 0) return 0;
+  if (use_tc() && ldy % 4 == 0 && rbm_tc_linear_supported(M, N, K, ldx, x, w)) {
+    RbmTcEpilogue te{y, ldy, pre, bias, residual, ldres, row_tok, act, rbm_drop_threshold(pA), rbm_drop_threshold(pB),
+                     1.f / (1.f - pA), 1.f / (1.f - pB), siteA, siteB, seed};
+    return rbm_tc_linear_launch(x, ldx, w, M, N, K, te, (cudaStream_t)stream);
+  }
   Epilogue ep{bias, pre, residual, ldres, row_tok, act, rbm_drop_threshold(pA), rbm_drop_threshold(pB),
               1.f / (1.f - pA), 1.f / (1.f - pB), siteA, siteB, seed};
   dim3 grid((unsigned)rbm_cdiv(M, 128), (unsigned)rbm_cdiv(N, 64));
@@ -306,13 +335,29 @@ extern "C" int rbm_linear_epilogue_bwd(const float* dout, const float* pre, floa
   return 0;
 }
 
+extern "C" size_t rbm_linear_bwd_data_ws_bytes(int N, int K) { return (size_t)N * K * sizeof(float) + 256; }
+
 extern "C" int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const float* w, float* dx, int64_t lddx, int64_t M,
-                                   int N, int K, rbm_stream_t stream) {
+                                   int N, int K, void* ws, size_t ws_bytes, rbm_stream_t stream) {
   RBM_REQUIRE(dpre && w && dx, "rbm_linear_bwd_data: null pointer");
   RBM_REQUIRE(N > 0 && K > 0 && N % 4 == 0 && K % 4 == 0, "rbm_linear_bwd_data: need N%%4==0 and K%%4==0");
   RBM_REQUIRE(lddpre % 4 == 0 && lddx % 4 == 0 && lddpre >= N && lddx >= K, "rbm_linear_bwd_data: bad leading dimensions");
   RBM_REQUIRE(rbm_aligned16(dpre) && rbm_aligned16(w) && rbm_aligned16(dx), "rbm_linear_bwd_data: pointers must be 16B aligned");
   if (M == 0) return 0;
+  // dx = dpre . w  ==  dpre[M,N] . (w^T)[K,N]^T : the tcgen05 kernel wants both operands contraction-major, so the
+  // (small) weight is transposed into the workspace first
+  if (use_tc() && ws && ws_bytes >= rbm_linear_bwd_data_ws_bytes(N, K) && rbm_aligned16(ws) &&
+      rbm_tc_linear_supported(M, K, N, lddpre, dpre, ws)) {
+    float* wt = (float*)ws;
+    dim3 tg((unsigned)rbm_cdiv(K, 32), (unsigned)rbm_cdiv(N, 32)), tb(32, 8);
+    transpose_kernel<<<tg, tb, 0, (cudaStream_t)stream>>>(w, wt, N, K);
+    RBM_LAUNCH_CHECK("rbm_linear_bwd_data(transpose)");
+    RbmTcEpilogue te{};
+    te.y = dx;
+    te.ldy = lddx;
+    te.invA = te.invB = 1.f;
+    return rbm_tc_linear_launch(dpre, lddpre, wt, M, K, N, te, (cudaStream_t)stream);
+  }
   Epilogue ep{};
   dim3 grid((unsigned)rbm_cdiv(M, 128), (unsigned)rbm_cdiv(K, 64));
   // C[M,K] = dpre[M,N] . w[N,K]  -> reduction length N, B = w as [Kred=N, Nout=K]

@@ -1,0 +1,568 @@
+// tc_gemm.cu -- Blackwell-native GEMM for the Linear layers:  D[M,N] = A[M,K] . B[N,K]^T  (+ fused epilogue)
+//   * operands stay fp32 in HBM and are consumed as TF32 by tcgen05.mma (kind::tf32, fp32 accumulation in TMEM);
+//   * A and B tiles are staged by TMA (cp.async.bulk.tensor.2d, 128-byte swizzle, K-major) into a ring of
+//     shared-memory stages guarded by full/empty mbarriers;
+//   * warp-specialised CTA: warp 0 = TMA producer, warp 1 = TMEM allocator + single-thread MMA issuer,
+//     warps 2..5 = epilogue (tcgen05.ld 32x32b: one accumulator row per thread) applying
+//     bias / GELU-ReLU / dropout / residual / dropout / pad-row zeroing and writing y (and the pre-activation).
+// One CTA per (128-row M tile, N tile <= 256).  Used by rbm_linear_fwd and rbm_linear_bwd_data (with the weight
+// transposed by the caller); shapes that do not meet the TMA/UMMA constraints take the SIMT kernels of linear.cu.
+#include <stdlib.h>
+#include <string.h>
+#include <cuda.h>  // CUtensorMap types only; the encode function is fetched at run time (no libcuda link dependency)
+#include "common.cuh"
+#include "tc_gemm.cuh"
+
+namespace {
+
+constexpr int BM = 128;      // UMMA_M (cta_group::1)
+constexpr int BKE = 32;      // K elements per stage = one 128-byte swizzle row of fp32/tf32
+constexpr int UMMA_K = 8;    // tf32
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded wait: a protocol bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  for (uint32_t it = 0; !mbar_try_wait(bar, parity); ++it)
+    if (it > 50000000u) __trap();
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+               "l"(map), "r"(bar), "r"(c0), "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+  uint32_t r[32];
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+        "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]),
+        "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]),
+        "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// K-major, 128-byte-swizzled UMMA shared-memory descriptor (cute::UMMA::SmemDescriptor): start address >> 4 in
+// bits [0,14), LBO >> 4 in [16,30) (unused for swizzled K-major: 1), SBO >> 4 = 1024 B >> 4 in [32,46) (distance
+// between 8-row groups), version = 1 in [46,48), layout type SWIZZLE_128B = 2 in [61,64).
+__device__ __forceinline__ uint64_t make_sw128_desc(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// cute::UMMA::InstrDescriptor for kind::tf32, fp32 accumulate, both operands K-major
+__host__ __device__ constexpr uint32_t make_idesc_tf32(int M, int N) {
+  return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ float act_apply(float v, int act) {
+  if (act == RBM_ACT_RELU) return fmaxf(v, 0.f);
+  if (act == RBM_ACT_GELU_TANH) return gelu_tanh_f(v);
+  return v;
+}
+
+struct TcParams {
+  float* y;
+  int64_t ldy;
+  float* pre;
+  const float* bias;
+  const float* residual;
+  int64_t ldres;
+  const int64_t* row_tok;
+  int64_t M;
+  int N, K, BN, nstage, act;
+  uint32_t thrA, thrB;
+  float invA, invB;
+  uint64_t siteA, siteB, seed;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                           const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[16], empty_bar[16], tmem_full_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t m0 = (int64_t)blockIdx.x * BM;
+  const int n0 = blockIdx.y * p.BN;
+  const int KB = p.K / BKE;
+  const uint32_t a_bytes = BM * BKE * 4, b_bytes = (uint32_t)p.BN * BKE * 4, stage_bytes = a_bytes + b_bytes;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;  // 128B-swizzle atoms need 1024-byte alignment
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&tmem_full_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.nstage;
+        if (kb >= p.nstage) mbar_wait(smem_u32(&empty_bar[s]), ((kb / p.nstage) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t sa = smem_base + s * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
+        tma_load_2d(sa, &mapA, bar, kb * BKE, (int)m0);
+        tma_load_2d(sa + a_bytes, &mapB, bar, kb * BKE, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(BM, p.BN);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % p.nstage;
+        mbar_wait(smem_u32(&full_bar[s]), (kb / p.nstage) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        const uint64_t adesc = make_sw128_desc(sa), bdesc = make_sw128_desc(sa + a_bytes);
+#pragma unroll
+        for (int k = 0; k < BKE / UMMA_K; ++k)  // +32 bytes (>>4 = 2) per UMMA_K step inside the 128-byte swizzle row
+          umma_tf32(tmem_d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(smem_u32(&empty_bar[s]));  // stage is free once these MMAs have read it
+      }
+      umma_commit(smem_u32(&tmem_full_bar));   // accumulator complete
+    }
+    __syncwarp();
+  } else {
+    // ---- epilogue: warp w may touch TMEM lanes [32*(w%4), +32); thread <-> accumulator row
+    const int q = warp & 3;
+    const int64_t row = m0 + q * 32 + lane;
+    mbar_wait(smem_u32(&tmem_full_bar), 0);
+    tc_fence_after();
+    const bool live = row < p.M;
+    const bool keep_row = !(p.row_tok && live && p.row_tok[row] == 0);
+    for (int c0 = 0; c0 < p.BN; c0 += 32) {
+      float v[32];
+      tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)c0, v);  // warp-collective: all lanes take part
+      if (!live) continue;
+      const int col0 = n0 + c0;
+#pragma unroll
+      for (int j = 0; j < 32; j += 4) {
+        const int col = col0 + j;
+        if (col >= p.N) break;
+        float4 x = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        if (p.bias) {
+          float4 b = ld4(p.bias + col);
+          x.x += b.x; x.y += b.y; x.z += b.z; x.w += b.w;
+        }
+        if (p.pre) st4(p.pre + row * p.N + col, x);
+        x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
+        const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
+        if (p.thrA) {
+          float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+          x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+        }
+        if (p.residual) {
+          float4 r = ld4(p.residual + row * p.ldres + col);
+          x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
+        }
+        if (p.thrB) {
+          float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+          x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+        }
+        if (!keep_row) x = make_float4(0.f, 0.f, 0.f, 0.f);
+        st4(p.y + row * p.ldy + col, x);
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, p.tmem_cols);
+  }
+}
+
+// =====================================================================================================
+// v2: persistent, weight-resident, 3xTF32.
+//   * one persistent CTA per SM walks M tiles (tile = blockIdx.x + i*gridDim.x);
+//   * the whole weight B[N<=256, K] is TMA-loaded ONCE per CTA and stays in shared memory (raw + lo copy);
+//   * A streams through a ring of 32-wide K-block stages; two "split" warps derive A_lo = A - trunc_tf32(A) next to
+//     each raw stage, so that  D = A_raw.B_lo + A_lo.B_raw + A_raw.B_raw  (three tcgen05.mma per K step) carries
+//     fp32-level accuracy while the tensor core only ever sees TF32 operands;
+//   * accumulators are double-buffered in TMEM: the epilogue of tile i overlaps TMA + MMA of tile i+1;
+//   * the epilogue transposes 32x32 accumulator chunks through a per-warp staging tile so that every global load
+//     (residual) and store (y, pre-activation) is a fully coalesced 128-byte row segment.
+// warps: 0 = TMA producer, 1 = TMEM alloc + MMA issuer, 2-3 = operand split, 4-11 = epilogue (two per TMEM quarter,
+// alternating 32-column chunks).
+// =====================================================================================================
+constexpr int STG_LD = 32;  // staging tile: 32x32 floats per warp, 16-byte chunks XOR-swizzled by (row & 7): conflict-free both ways
+
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+// dst = src - trunc_tf32(src), elementwise over n4 float4 (layout-agnostic: the swizzle is preserved)
+__device__ __forceinline__ void split_lo(const float* src, float* dst, int n4, int tid, int nthr) {
+  for (int i = tid; i < n4; i += nthr) {
+    float4 v = ld4(src + i * 4), o;
+    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    st4(dst + i * 4, o);
+  }
+}
+
+constexpr int EPI_WARPS = 8;
+__global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
+                                                                      const __grid_constant__ CUtensorMap mapB, const TcParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], split_bar[8], empty_bar[8], tfull_bar[2], tempty_bar[2], bfull_bar, bsplit_bar;
+  __shared__ uint32_t tmem_base_slot;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.K / BKE, BN = p.BN, ns = p.nstage;
+  const int tiles = (int)((p.M + BM - 1) / BM);
+  const uint32_t a_bytes = BM * BKE * 4, bk_bytes = (uint32_t)BN * BKE * 4, b_bytes = bk_bytes * KB;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
+  const uint32_t off_blo = b_bytes, off_stage = 2 * b_bytes, off_stg = off_stage + (uint32_t)ns * 2 * a_bytes;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&split_bar[s]), 2);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull_bar[b]), 1);
+      mbar_init(smem_u32(&tempty_bar[b]), EPI_WARPS);
+    }
+    mbar_init(smem_u32(&bfull_bar), 1);
+    mbar_init(smem_u32(&bsplit_bar), 2);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      const uint32_t bb = smem_u32(&bfull_bar);
+      mbar_expect_tx(bb, b_bytes);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_base + kb * bk_bytes, &mapB, bb, kb * BKE, 0);
+      int g = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % ns;
+          if (g >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((g / ns) - 1) & 1);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, a_bytes);
+          tma_load_2d(smem_base + off_stage + s * 2 * a_bytes, &mapA, bar, kb * BKE, tile * BM);
+        }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(BM, BN);
+      mbar_wait(smem_u32(&bsplit_bar), 0);
+      tc_fence_after();
+      int g = 0, it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int buf = it & 1;
+        if (it >= 2) {
+          mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        const uint32_t d = tmem_d + (uint32_t)(buf * BN);
+        for (int kb = 0; kb < KB; ++kb, ++g) {
+          const int s = g % ns;
+          mbar_wait(smem_u32(&full_bar[s]), (g / ns) & 1);
+          mbar_wait(smem_u32(&split_bar[s]), (g / ns) & 1);
+          tc_fence_after();
+          const uint32_t sa = smem_base + off_stage + s * 2 * a_bytes;
+          const uint64_t a_raw = make_sw128_desc(sa), a_lo = make_sw128_desc(sa + a_bytes);
+          const uint64_t b_raw = make_sw128_desc(smem_base + kb * bk_bytes), b_lo = make_sw128_desc(smem_base + off_blo + kb * bk_bytes);
+#pragma unroll
+          for (int k = 0; k < BKE / UMMA_K; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32(d, a_raw + o, b_lo + o, idesc, (kb | k) != 0);
+            umma_tf32(d, a_lo + o, b_raw + o, idesc, 1);
+            umma_tf32(d, a_raw + o, b_raw + o, idesc, 1);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+        }
+        umma_commit(smem_u32(&tfull_bar[buf]));
+      }
+    }
+    __syncwarp();
+  } else if (warp < 4) {
+    const int tid = threadIdx.x - 64;
+    mbar_wait(smem_u32(&bfull_bar), 0);
+    split_lo(reinterpret_cast<const float*>(gen_base), reinterpret_cast<float*>(gen_base + off_blo), (int)(b_bytes / 16), tid, 64);
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&bsplit_bar));
+    int g = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+      for (int kb = 0; kb < KB; ++kb, ++g) {
+        const int s = g % ns;
+        mbar_wait(smem_u32(&full_bar[s]), (g / ns) & 1);
+        uint8_t* st = gen_base + off_stage + (size_t)s * 2 * a_bytes;
+        split_lo(reinterpret_cast<const float*>(st), reinterpret_cast<float*>(st + a_bytes), (int)(a_bytes / 16), tid, 64);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+      }
+  } else {
+    const int q = warp & 3, half = (warp - 4) >> 2;
+    float* stg = reinterpret_cast<float*>(gen_base + off_stg) + (warp - 4) * 32 * STG_LD;
+    const int rsub = lane >> 3, cg = (lane & 7) * 4;
+    const float* __restrict__ resid = p.residual;
+    const float* __restrict__ biasp = p.bias;
+    float* __restrict__ yout = p.y;
+    float* __restrict__ preout = p.pre;
+    const int last_c0 = ((BN / 32 - 1 - half) / 2) * 64 + half * 32;  // this warp's last chunk
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
+      tc_fence_after();
+      const int64_t rbase = (int64_t)tile * BM + q * 32;
+      if (half * 32 >= BN) {  // BN == 16/32: the second warp of the pair has no chunk, it only releases the buffer
+        if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        continue;
+      }
+      for (int c0 = half * 32; c0 < BN; c0 += 64) {
+        float v[32];
+        tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + c0), v);
+        if (c0 == last_c0) {  // last read of this accumulator by this warp: hand the TMEM buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
+        }
+        const int col = c0 + cg;
+        const bool col_ok = col < p.N;
+        // all residual loads of the chunk are issued before anything depends on them
+        float4 res[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int64_t row = rbase + i * 4 + rsub;
+          res[i] = (resid && col_ok && row < p.M) ? ld4(resid + row * p.ldres + col) : make_float4(0.f, 0.f, 0.f, 0.f);
+        }
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) st4(stg + lane * STG_LD + (((j >> 2) ^ (lane & 7)) << 2), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        __syncwarp();
+        if (col_ok) {
+          float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (biasp) bias4 = ld4(biasp + col);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rl = i * 4 + rsub;
+            const int64_t row = rbase + rl;
+            if (row < p.M) {
+              float4 x = ld4(stg + rl * STG_LD + (((cg >> 2) ^ (rl & 7)) << 2));
+              x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+              if (preout) st4(preout + row * p.N + col, x);
+              x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
+              const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
+              if (p.thrA) {
+                float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+                x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+              }
+              x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+              if (p.thrB) {
+                float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+                x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+              }
+              if (p.row_tok && p.row_tok[row] == 0) x = make_float4(0.f, 0.f, 0.f, 0.f);
+              st4(yout + row * p.ldy + col, x);
+            }
+          }
+        }
+        __syncwarp();
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+
+// 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 32 cols], 128-byte swizzle
+bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+int pick_bn(int N) {
+  if (N <= 256) return N;
+  for (int bn = 256; bn >= 16; bn -= 16)
+    if (N % bn == 0) return bn;
+  return 0;
+}
+
+}  // namespace
+
+// mode: 0 = auto (v2 persistent 3xTF32 when it fits, else refuse), 1 = v1 single-pass TF32 (RBM_LINEAR_IMPL=tf32x1)
+static int tc_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RBM_LINEAR_IMPL");
+    v = (e && strcmp(e, "tf32x1") == 0) ? 1 : 0;
+  }
+  return v;
+}
+
+static bool v2_fits(int N, int K, int* nstage_out) {
+  if (N > 256) return false;
+  const size_t b_bytes = (size_t)N * K * 4, a_stage = (size_t)2 * BM * BKE * 4, stg = (size_t)EPI_WARPS * 32 * STG_LD * 4;
+  const size_t budget = (size_t)231424 - 1024;  // 227 KB per block minus static barriers and alignment slack
+  if (2 * b_bytes + stg + 2 * a_stage > budget) return false;
+  int ns = (int)((budget - 2 * b_bytes - stg) / a_stage);
+  if (ns > 8) ns = 8;
+  *nstage_out = ns;
+  return ns >= 2;
+}
+
+bool rbm_tc_linear_supported(int64_t M, int N, int K, int64_t lda, const void* a, const void* b) {
+  if (M < 1 || N % 16 != 0 || K % BKE != 0 || K < BKE || N < 16) return false;
+  if (lda % 4 != 0 || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return false;
+  if (get_encode() == nullptr) return false;
+  int ns;
+  if (tc_mode() == 0) return v2_fits(N, K, &ns);
+  return pick_bn(N) != 0;
+}
+
+int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M, int N, int K, const RbmTcEpilogue& ep,
+                         cudaStream_t st) {
+  const bool v2 = tc_mode() == 0;
+  const int BN = v2 ? N : pick_bn(N);
+  CUtensorMap mapA, mapB;
+  if (!encode_map(&mapA, a, M, K, lda, BM) || !encode_map(&mapB, b, N, K, K, BN)) {
+    rbm_set_error("rbm_linear(tcgen05): cuTensorMapEncodeTiled failed (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
+    return -1;
+  }
+  TcParams p{};
+  p.y = ep.y; p.ldy = ep.ldy; p.pre = ep.pre; p.bias = ep.bias; p.residual = ep.residual; p.ldres = ep.ldres; p.row_tok = ep.row_tok;
+  p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = ep.act;
+  p.thrA = ep.thrA; p.thrB = ep.thrB; p.invA = ep.invA; p.invB = ep.invB; p.siteA = ep.siteA; p.siteB = ep.siteB; p.seed = ep.seed;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_linear(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  if (v2) {
+    int ns = 2;
+    v2_fits(N, K, &ns);
+    p.nstage = ns;
+    uint32_t cols = 32;
+    while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+    p.tmem_cols = cols;
+    size_t smem = (size_t)2 * N * K * 4 + (size_t)ns * 2 * BM * BKE * 4 + (size_t)EPI_WARPS * 32 * STG_LD * 4 + 1024;
+    int tiles = (int)rbm_cdiv(M, BM);
+    int grid = tiles < RBM_NUM_SMS ? tiles : RBM_NUM_SMS;
+    tc_linear_persistent_kernel<<<grid, 128 + 32 * EPI_WARPS, smem, st>>>(mapA, mapB, p);
+    RBM_LAUNCH_CHECK("rbm_linear(tcgen05 persistent)");
+    return 0;
+  }
+  const uint32_t stage_bytes = (uint32_t)(BM + BN) * BKE * 4;
+  int nstage = (int)((200u * 1024u) / stage_bytes);
+  if (nstage > K / BKE) nstage = K / BKE;
+  if (nstage > 16) nstage = 16;
+  p.nstage = nstage;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)BN) cols <<= 1;
+  p.tmem_cols = cols;
+  size_t smem = (size_t)nstage * stage_bytes + 1024;
+  dim3 grid((unsigned)rbm_cdiv(M, BM), (unsigned)(N / BN));
+  tc_linear_kernel<<<grid, 192, smem, st>>>(mapA, mapB, p);
+  RBM_LAUNCH_CHECK("rbm_linear(tcgen05)");
+  return 0;
+}

@@ -1,0 +1,23 @@
+// tc_gemm.cuh -- internal interface of the tcgen05 GEMM (tc_gemm.cu) used by the Linear entry points (linear.cu).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+struct RbmTcEpilogue {
+  float* y;
+  int64_t ldy;
+  float* pre;
+  const float* bias;
+  const float* residual;
+  int64_t ldres;
+  const int64_t* row_tok;
+  int act;
+  uint32_t thrA, thrB;
+  float invA, invB;
+  uint64_t siteA, siteB, seed;
+};
+
+// D[M,N] = A[M,K] . B[N,K]^T: shapes/alignments the TMA + UMMA path accepts (K % 32 == 0, N % 16 == 0, ...)
+bool rbm_tc_linear_supported(int64_t M, int N, int K, int64_t lda, const void* a, const void* b);
+int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M, int N, int K, const RbmTcEpilogue& ep,
+                         cudaStream_t st);

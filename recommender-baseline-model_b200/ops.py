@@ -169,8 +169,10 @@ class LinearFn(torch.autograd.Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             dx = torch.empty(M, K, device=dy.device, dtype=torch.float32)
-            check(lib.rbm_linear_bwd_data(ptr(dpre), N, ptr(w), ptr(dx), K, M, N, K, stream()), "linear_bwd_data")
-            count_launches()
+            nbd = lib.rbm_linear_bwd_data_ws_bytes(N, K)
+            wsd = _ws("lin_dx", nbd, dy.device)
+            check(lib.rbm_linear_bwd_data(ptr(dpre), N, ptr(w), ptr(dx), K, M, N, K, ptr(wsd), nbd, stream()), "linear_bwd_data")
+            count_launches(2)
             dx = dx.view(xshape)
         if ctx.needs_input_grad[1] or (has_bias and ctx.needs_input_grad[2]):
             dw = torch.empty_like(w)
