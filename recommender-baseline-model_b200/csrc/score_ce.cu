@@ -1,17 +1,19 @@
 // score_ce.cu -- BERT4Rec output scoring fused with masked cross-entropy; logits are never written to HBM.
 // Replaces  logits = self.out(h)  (NN/models/bert.py:16, materialises [B,L,V+1]) followed by
 // CrossEntropyLoss(ignore_index=0) (NN/trainers/bert.py:11,36-40) and their autograd.
-//   fwd : per compacted (labels != 0) row, stream 64-wide vocab tiles, online (max, sum-exp), capture target logit.
-//   bwd : logits are recomputed tile-wise;  dH = G.W  (CTA per row tile),  dW = G^T.H, db = colsum(G) (CTA per
-//         vocab tile x row split, fixed-order split reduction)  with  G = (softmax - onehot) * dloss / count.
-// Round-1 implementation: register-tiled SIMT fp32 (exact-parity baseline for the tcgen05 version).
+//   fwd : rows with labels != 0 are compacted; each warp owns 16 of them, the [V+1, d] weight streams through shared
+//         memory in 64-row swizzled panels (cp.async double buffer); 16x64 logit tiles are produced on tensor cores
+//         (mma.sync TF32, 3xTF32 compensated), an online (max, sum-exp) in the log2 domain and the target logit are
+//         kept in registers.
+//   bwd : logits are recomputed tile-wise;  dH = G.W  (warp per 16 rows, the same panel serves both MMAs),
+//         dW = G^T.H, db = colsum(G)  (warp per 16 vocab rows, gathered H panels stream, row chunks split over
+//         blockIdx.y with a fixed-order reduction), G = (softmax - onehot) * dloss / count.
 #include "common.cuh"
+#include "mma_tiles.cuh"
 
 namespace {
 
-constexpr int T = 64;        // tile edge (rows and vocab columns)
-constexpr int LDT = T + 4;   // padded smem row length (16B aligned)
-constexpr int KC = 16;       // k-chunk for streamed operands
+using namespace rbm_mma;
 
 // ---------------------------------------------------------------------------------------------- compaction
 __global__ void __launch_bounds__(256) compact_count_kernel(const int64_t* __restrict__ labels, int64_t n, int32_t* __restrict__ blk_cnt) {
@@ -76,152 +78,148 @@ __global__ void __launch_bounds__(256) compact_write_kernel(const int64_t* __res
   }
 }
 
-// ------------------------------------------------------------------------------------------ shared helpers
-// Hst[k][r] <- h[rows[r0+r], k]  (transposed; rows >= count zero-filled)
-__device__ __forceinline__ void load_h_transposed(float* Hst, const float* __restrict__ h, const int32_t* __restrict__ rows,
-                                                  int r0, int count, int d) {
+// ------------------------------------------------------------------------------------------ async panel loads
+__device__ __forceinline__ void cp_async16(float* dst, const float* src, bool valid) {
+  uint32_t d = (uint32_t)__cvta_generic_to_shared(dst);
+  int sz = valid ? 16 : 0;  // src-size 0: zero-fill
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(d), "l"(src), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// panel[64][LD] (swizzled) <- rows r0.. of src; row index through `rows` when given; rows >= limit zero-filled
+__device__ __forceinline__ void panel_load_async(float* panel, const float* __restrict__ src, const int32_t* __restrict__ rows,
+                                                 int64_t r0, int64_t limit, int d, int LD) {
   int d4 = d >> 2;
-  for (int idx = threadIdx.x; idx < T * d4; idx += blockDim.x) {
+  for (int idx = threadIdx.x; idx < CH * d4; idx += blockDim.x) {
     int r = idx / d4, c4 = idx - r * d4;
-    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-    if (r0 + r < count) v = ld4(h + (int64_t)rows[r0 + r] * d + c4 * 4);
-    Hst[(c4 * 4 + 0) * LDT + r] = v.x;
-    Hst[(c4 * 4 + 1) * LDT + r] = v.y;
-    Hst[(c4 * 4 + 2) * LDT + r] = v.z;
-    Hst[(c4 * 4 + 3) * LDT + r] = v.w;
+    bool ok = r0 + r < limit;
+    int64_t gr = ok ? (rows ? (int64_t)rows[r0 + r] : (r0 + r)) : 0;
+    cp_async16(panel + r * LD + ((c4 * 4) ^ swz(r)), src + gr * d + c4 * 4, ok);
   }
 }
-// Xrow[r][k] (row stride ldr) <- src rows; gather via rows[] when given, zero-fill invalid
-__device__ __forceinline__ void load_rows_rowmajor(float* X, int ldr, const float* __restrict__ src, const int32_t* __restrict__ rows,
-                                                   int64_t r0, int64_t limit, int d) {
+// per-warp tile[16][ldt] <- rows (r0 + r) of src (through `rows` when given) times mul; rows >= limit zero
+__device__ __forceinline__ void stage_rows(float* dst, int ldt, const float* __restrict__ src, const int32_t* __restrict__ rows,
+                                           int64_t r0, int64_t limit, int d, float mul, int lane) {
   int d4 = d >> 2;
-  for (int idx = threadIdx.x; idx < T * d4; idx += blockDim.x) {
+  for (int idx = lane; idx < 16 * d4; idx += 32) {
     int r = idx / d4, c4 = idx - r * d4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
     if (r0 + r < limit) {
       int64_t gr = rows ? (int64_t)rows[r0 + r] : (r0 + r);
       v = ld4(src + gr * d + c4 * 4);
     }
-    st4(X + r * ldr + c4 * 4, v);
+    st4(dst + r * ldt + c4 * 4, make_float4(v.x * mul, v.y * mul, v.z * mul, v.w * mul));
   }
 }
-// Wst chunk [KC][LDT] <- w[v0 + c, k0 + kk]  (transposed), 256 threads, one float4 each
-__device__ __forceinline__ void load_w_chunk(float* Wc, const float* __restrict__ w, int v0, int V1, int k0, int d) {
-  int c = threadIdx.x >> 2, kq = threadIdx.x & 3;
-  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (v0 + c < V1 && k0 + kq * 4 < d) v = ld4(w + (int64_t)(v0 + c) * d + k0 + kq * 4);
-  Wc[(kq * 4 + 0) * LDT + c] = v.x;
-  Wc[(kq * 4 + 1) * LDT + c] = v.y;
-  Wc[(kq * 4 + 2) * LDT + c] = v.z;
-  Wc[(kq * 4 + 3) * LDT + c] = v.w;
-}
 
-#define FMA44(acc, a, b)                                                                       \
-  do {                                                                                         \
-    float _a[4] = {a.x, a.y, a.z, a.w}, _b[4] = {b.x, b.y, b.z, b.w};                          \
-    _Pragma("unroll") for (int _i = 0; _i < 4; ++_i) _Pragma("unroll") for (int _j = 0; _j < 4; ++_j) acc[_i][_j] = \
-        fmaf(_a[_i], _b[_j], acc[_i][_j]);                                                     \
-  } while (0)
-
-__device__ __forceinline__ float half_sum(float v) {  // across the 16 tx lanes that share a row
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
-  return v;
-}
-__device__ __forceinline__ float half_max(float v) {
-#pragma unroll
-  for (int o = 8; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
-  return v;
-}
-
-// logits tile acc[4][4] (rows ty*4+i, cols tx*4+j) = Hst^T . W[v0:v0+64]^T, W streamed in KC-chunks through Wc
-__device__ __forceinline__ void logits_tile_streamW(float (&acc)[4][4], const float* Hst, float* Wc, const float* __restrict__ w,
-                                                    int v0, int V1, int d, int tx, int ty) {
-#pragma unroll
-  for (int i = 0; i < 4; ++i)
-#pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-  for (int k0 = 0; k0 < d; k0 += KC) {
-    __syncthreads();
-    load_w_chunk(Wc, w, v0, V1, k0, d);
-    __syncthreads();
-    int kmax = d - k0 < KC ? d - k0 : KC;
-    for (int kk = 0; kk < kmax; ++kk) {
-      float4 a = ld4(Hst + (k0 + kk) * LDT + ty * 4);
-      float4 b = ld4(Wc + kk * LDT + tx * 4);
-      FMA44(acc, a, b);
-    }
-  }
-}
+struct CeArgs {
+  const float* h;
+  const int32_t* rows;
+  const int64_t* tgt;
+  const int32_t* count;
+  const float* w;
+  const float* bias;
+  const float* lse_in;
+  const float* dloss;
+  float *lse_out, *partial, *dh_full, *part_w, *part_b;
+  int V1, d;
+};
 
 // ------------------------------------------------------------------------------------------------ forward
-__global__ void __launch_bounds__(256) ce_fwd_kernel(const float* __restrict__ h, const int32_t* __restrict__ rows,
-                                                     const int64_t* __restrict__ tgt, const int32_t* __restrict__ count_p,
-                                                     const float* __restrict__ w, const float* __restrict__ bias,
-                                                     float* __restrict__ lse_out, float* __restrict__ partial, int V1, int d) {
+__global__ void __launch_bounds__(256) ce_fwd_kernel(CeArgs a) {
   extern __shared__ __align__(16) float sm[];
-  float* Hst = sm;             // [d][LDT]
-  float* Wc = Hst + d * LDT;   // [KC][LDT]
-  float* contrib = Wc + KC * LDT;  // [T]
-  const int count = *count_p;
-  const int r0 = blockIdx.x * T;
-  if (r0 >= count) {
-    if (threadIdx.x == 0) partial[blockIdx.x] = 0.f;
+  const int d = a.d, V1 = a.V1, LD = (d + 31) & ~31, QLD = d + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int count = *a.count;
+  const int r0cta = blockIdx.x * nwarps * 16;
+  if (r0cta >= count) {
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = 0.f;
     return;
   }
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  load_h_transposed(Hst, h, rows, r0, count, d);
-  int64_t rt[4];
-  float m[4], l[4], tl[4];
+  float* panel = sm;                      // [2][64][LD]
+  float* bias_s = panel + 2 * CH * LD;    // [2][64]
+  float* contrib = bias_s + 2 * CH;       // [nwarps*16]
+  float* Hs = contrib + nwarps * 16 + (size_t)warp * 16 * QLD;
+  const int r0 = r0cta + warp * 16;
+  stage_rows(Hs, QLD, a.h, a.rows, r0, count, d, RBM_LOG2E, lane);
+  int64_t tg[2];
+  float m[2] = {-INFINITY, -INFINITY}, l[2] = {0.f, 0.f}, tl[2] = {0.f, 0.f};
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int r = r0 + ty * 4 + i;
-    rt[i] = r < count ? tgt[r] : -1;
-    m[i] = -INFINITY;
-    l[i] = 0.f;
-    tl[i] = 0.f;
+  for (int hr = 0; hr < 2; ++hr) {
+    int r = r0 + g + 8 * hr;
+    tg[hr] = r < count ? a.tgt[r] : -1;
   }
-  for (int v0 = 0; v0 < V1; v0 += T) {
-    float acc[4][4];
-    logits_tile_streamW(acc, Hst, Wc, w, v0, V1, d, tx, ty);
-    int cb = v0 + tx * 4;
-    float bv[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) bv[j] = (bias && cb + j < V1) ? bias[cb + j] : 0.f;
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float lg[4], tmax = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        lg[j] = cb + j < V1 ? acc[i][j] + bv[j] : -INFINITY;
-        tmax = fmaxf(tmax, lg[j]);
-        if ((int64_t)(cb + j) == rt[i]) tl[i] += lg[j];
-      }
-      tmax = half_max(tmax);
-      float mn = fmaxf(m[i], tmax);
-      float ps = 0.f;
-#pragma unroll
-      for (int j = 0; j < 4; ++j) ps += expf(lg[j] - mn);
-      ps = half_sum(ps);
-      l[i] = l[i] * expf(m[i] - mn) + ps;
-      m[i] = mn;
+  const int NC = (V1 + CH - 1) / CH;
+  auto issue = [&](int c) {
+    panel_load_async(panel + (c & 1) * CH * LD, a.w, nullptr, (int64_t)c * CH, V1, d, LD);
+    for (int j = threadIdx.x; j < CH; j += blockDim.x) {
+      int v = c * CH + j;
+      bias_s[(c & 1) * CH + j] = (a.bias && v < V1) ? a.bias[v] * RBM_LOG2E : 0.f;
     }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) {
+      issue(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
+    }
+    __syncthreads();
+    const float* pn = panel + (c & 1) * CH * LD;
+    const float* bs = bias_s + (c & 1) * CH;
+    float s[8][4];
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    tile_dot_panel(s, Hs, QLD, pn, LD, 0, CH, d, g, t);
+    float cm[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float2 b2 = *reinterpret_cast<const float2*>(bs + nt * 8 + 2 * t);
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        int v = c * CH + nt * 8 + 2 * t + (cc & 1);
+        float x = v < V1 ? s[nt][cc] + ((cc & 1) ? b2.y : b2.x) : -INFINITY;
+        if ((int64_t)v == tg[cc >> 1]) tl[cc >> 1] += x;
+        s[nt][cc] = x;
+        cm[cc >> 1] = fmaxf(cm[cc >> 1], x);
+      }
+    }
+    float base[2], ps[2] = {0.f, 0.f};
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) {
+      float mn = fmaxf(m[hr], quad_max(cm[hr]));
+      l[hr] *= (m[hr] == -INFINITY ? 0.f : ex2(m[hr] - mn));
+      base[hr] = mn;
+      m[hr] = mn;
+    }
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt)
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) ps[cc >> 1] += ex2(s[nt][cc] - base[cc >> 1]);
+#pragma unroll
+    for (int hr = 0; hr < 2; ++hr) l[hr] += quad_sum(ps[hr]);
+    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    float t = half_sum(tl[i]);
-    int r = r0 + ty * 4 + i;
-    float lse = m[i] + logf(l[i]);
-    if (tx == 0) {
-      if (r < count) lse_out[r] = lse;
-      contrib[ty * 4 + i] = r < count ? lse - t : 0.f;
+  for (int hr = 0; hr < 2; ++hr) {
+    int r = r0 + g + 8 * hr;
+    float tsum = quad_sum(tl[hr]);
+    float lse = (m[hr] + log2f(l[hr])) * RBM_LN2;
+    if (t == 0) {
+      if (r < count) a.lse_out[r] = lse;
+      contrib[warp * 16 + g + 8 * hr] = r < count ? lse - tsum * RBM_LN2 : 0.f;
     }
   }
   __syncthreads();
   if (threadIdx.x == 0) {
-    float s = 0.f;
-    for (int r = 0; r < T; ++r) s += contrib[r];
-    partial[blockIdx.x] = s;
+    float sacc = 0.f;
+    for (int r = 0; r < nwarps * 16; ++r) sacc += contrib[r];
+    a.partial[blockIdx.x] = sacc;
   }
 }
 
@@ -240,186 +238,173 @@ __global__ void __launch_bounds__(256) ce_loss_finalize_kernel(const float* __re
 }
 
 // ---------------------------------------------------------------------------------------- backward: dH
-template <int NT2>
-__global__ void __launch_bounds__(256) ce_bwd_dh_kernel(const float* __restrict__ h, const int32_t* __restrict__ rows,
-                                                        const int64_t* __restrict__ tgt, const int32_t* __restrict__ count_p,
-                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                        const float* __restrict__ lse, const float* __restrict__ dloss,
-                                                        float* __restrict__ dh_full, int V1, int d) {
+template <int DT>
+__global__ void __launch_bounds__(256) ce_bwd_dh_kernel(CeArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int ldw = d + 4;
-  float* Hst = sm;               // [d][LDT]
-  float* Wc = Hst + d * LDT;     // [KC][LDT]
-  float* Gst = Wc + KC * LDT;    // [T cols][LDT]  G transposed: Gst[c][r]
-  float* Wrow = Gst + T * LDT;   // [T cols][ldw]  row-major W tile
-  const int count = *count_p;
-  const int r0 = blockIdx.x * T;
-  if (r0 >= count) return;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const float gscale = *dloss / (float)count;
-  load_h_transposed(Hst, h, rows, r0, count, d);
-  int64_t rt[4];
-  float rl[4];
+  const int d = a.d, V1 = a.V1, LD = (d + 31) & ~31, QLD = d + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int count = *a.count;
+  const int r0cta = blockIdx.x * nwarps * 16;
+  if (r0cta >= count) return;
+  float* panel = sm;
+  float* bias_s = panel + 2 * CH * LD;
+  float* wbase = bias_s + 2 * CH + (size_t)warp * (16 * QLD + 16 * PB_LD);
+  float* Hs = wbase;
+  float* Pb = wbase + 16 * QLD;
+  const int r0 = r0cta + warp * 16;
+  const float gscale = *a.dloss / (float)count;
+  stage_rows(Hs, QLD, a.h, a.rows, r0, count, d, RBM_LOG2E, lane);
+  int64_t tg[2];
+  float lse2[2];
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int r = r0 + ty * 4 + i;
-    rt[i] = r < count ? tgt[r] : -1;
-    rl[i] = r < count ? lse[r] : 0.f;
+  for (int hr = 0; hr < 2; ++hr) {
+    int r = r0 + g + 8 * hr;
+    tg[hr] = r < count ? a.tgt[r] : -1;
+    lse2[hr] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
   }
-  float acc2[NT2][4][4];
+  float acc[DT][4];
 #pragma unroll
-  for (int t = 0; t < NT2; ++t)
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc2[t][i][j] = 0.f;
-
-  for (int v0 = 0; v0 < V1; v0 += T) {
-    float acc[4][4];
-    logits_tile_streamW(acc, Hst, Wc, w, v0, V1, d, tx, ty);  // starts with __syncthreads(): previous GEMM2 finished
-    load_rows_rowmajor(Wrow, ldw, w, nullptr, v0, V1, d);
-    int cb = v0 + tx * 4;
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      float bj = (bias && cb + j < V1) ? bias[cb + j] : 0.f;
-      float g[4];
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        float p = (cb + j < V1 && rt[i] >= 0) ? expf(acc[i][j] + bj - rl[i]) : 0.f;
-        if ((int64_t)(cb + j) == rt[i]) p -= 1.f;
-        g[i] = p * gscale;
-      }
-      st4(Gst + (tx * 4 + j) * LDT + ty * 4, make_float4(g[0], g[1], g[2], g[3]));
+  for (int dt = 0; dt < DT; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
+  const int NC = (V1 + CH - 1) / CH;
+  auto issue = [&](int c) {
+    panel_load_async(panel + (c & 1) * CH * LD, a.w, nullptr, (int64_t)c * CH, V1, d, LD);
+    for (int j = threadIdx.x; j < CH; j += blockDim.x) {
+      int v = c * CH + j;
+      bias_s[(c & 1) * CH + j] = (a.bias && v < V1) ? a.bias[v] * RBM_LOG2E : 0.f;
+    }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int c = 0; c < NC; ++c) {
+    if (c + 1 < NC) {
+      issue(c + 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    // GEMM2: dH[r][kk] += sum_c G[r][c] * W[c][kk];  thread owns rows ty*4.., cols tx*4 + 64*t ..
-    for (int c = 0; c < T; ++c) {
-      float4 a = ld4(Gst + c * LDT + ty * 4);
+    const float* pn = panel + (c & 1) * CH * LD;
+    const float* bs = bias_s + (c & 1) * CH;
+    float s[8][4];
 #pragma unroll
-      for (int t = 0; t < NT2; ++t) {
-        int kk = tx * 4 + 64 * t;
-        if (kk < d) {
-          float4 b = ld4(Wrow + c * ldw + kk);
-          FMA44(acc2[t], a, b);
-        }
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    tile_dot_panel(s, Hs, QLD, pn, LD, 0, CH, d, g, t);
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float2 b2 = *reinterpret_cast<const float2*>(bs + nt * 8 + 2 * t);
+      float gg[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        int v = c * CH + nt * 8 + 2 * t + (cc & 1), hr = cc >> 1;
+        float p = (v < V1 && tg[hr] >= 0) ? ex2(s[nt][cc] + ((cc & 1) ? b2.y : b2.x) - lse2[hr]) : 0.f;
+        if ((int64_t)v == tg[hr]) p -= 1.f;
+        gg[cc] = p * gscale;
       }
+      *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(gg[0], gg[1]);
+      *reinterpret_cast<float2*>(Pb + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(gg[2], gg[3]);
     }
+    __syncwarp();
+    ptile_times_panel<DT>(acc, Pb, pn, LD, 0, CH, d, g, t);  // dH += G . W[chunk]
+    __syncthreads();
   }
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int r = r0 + ty * 4 + i;
+  for (int hr = 0; hr < 2; ++hr) {
+    int r = r0 + g + 8 * hr;
     if (r < count) {
+      float* dst = a.dh_full + (int64_t)a.rows[r] * d;
 #pragma unroll
-      for (int t = 0; t < NT2; ++t) {
-        int kk = tx * 4 + 64 * t;
-        if (kk < d) st4(dh_full + (int64_t)rows[r] * d + kk, make_float4(acc2[t][i][0], acc2[t][i][1], acc2[t][i][2], acc2[t][i][3]));
-      }
+      for (int dt = 0; dt < DT; ++dt)
+        if (dt * 8 < d) *reinterpret_cast<float2*>(dst + dt * 8 + 2 * t) = make_float2(acc[dt][2 * hr], acc[dt][2 * hr + 1]);
     }
   }
 }
 
 // ------------------------------------------------------------------------------------ backward: dW and db
-// grid (vocab tiles, S): CTA owns vocab rows [v0, v0+64) and row tiles  {s, s+S, s+2S, ...}.
-template <int NT2>
-__global__ void __launch_bounds__(256) ce_bwd_dw_kernel(const float* __restrict__ h, const int32_t* __restrict__ rows,
-                                                        const int64_t* __restrict__ tgt, const int32_t* __restrict__ count_p,
-                                                        const float* __restrict__ w, const float* __restrict__ bias,
-                                                        const float* __restrict__ lse, const float* __restrict__ dloss,
-                                                        float* __restrict__ part_w, float* __restrict__ part_b, int V1, int d) {
+// grid (vocab tiles of 16*nwarps rows, S): row chunks {s, s+S, ...} of 64 compacted rows each
+template <int DT>
+__global__ void __launch_bounds__(256) ce_bwd_dw_kernel(CeArgs a) {
   extern __shared__ __align__(16) float sm[];
-  const int ldh = d + 4;
-  float* Wst = sm;               // [d][LDT]   fixed vocab tile, transposed: Wst[k][c]
-  float* Hrow = Wst + d * LDT;   // [T rows][ldh] row-major gathered H tile
-  float* Gs = Hrow + T * ldh;    // [T rows][LDT]  G[r][c]
-  const int count = *count_p;
-  const int v0 = blockIdx.x * T;
-  const int S = gridDim.y, s = blockIdx.y;
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const float gscale = *dloss / (float)count;
-  // W tile transposed (zero beyond V1)
-  {
-    int d4 = d >> 2;
-    for (int idx = threadIdx.x; idx < T * d4; idx += blockDim.x) {
-      int c = idx / d4, k4 = idx - c * d4;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (v0 + c < V1) v = ld4(w + (int64_t)(v0 + c) * d + k4 * 4);
-      Wst[(k4 * 4 + 0) * LDT + c] = v.x;
-      Wst[(k4 * 4 + 1) * LDT + c] = v.y;
-      Wst[(k4 * 4 + 2) * LDT + c] = v.z;
-      Wst[(k4 * 4 + 3) * LDT + c] = v.w;
-    }
+  const int d = a.d, V1 = a.V1, LD = (d + 31) & ~31, QLD = d + 4;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarps = blockDim.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int count = *a.count;
+  const int S = gridDim.y, sp = blockIdx.y;
+  float* panel = sm;                       // [2][64][LD] gathered H rows
+  float* lse_s = panel + 2 * CH * LD;      // [2][64] lse (log2 domain)
+  float* tgt_s = lse_s + 2 * CH;           // [2][64] target id as float (exact below 2^24) or -1
+  float* wbase = tgt_s + 2 * CH + (size_t)warp * (16 * QLD + 16 * PB_LD);
+  float* Ws = wbase;
+  float* Pb = wbase + 16 * QLD;
+  const int v0 = (blockIdx.x * nwarps + warp) * 16;
+  const float gscale = *a.dloss / (float)count;
+  stage_rows(Ws, QLD, a.w, nullptr, v0, V1, d, RBM_LOG2E, lane);
+  float b2[2];
+  int vrow[2];
+#pragma unroll
+  for (int hr = 0; hr < 2; ++hr) {
+    vrow[hr] = v0 + g + 8 * hr;
+    b2[hr] = (a.bias && vrow[hr] < V1) ? a.bias[vrow[hr]] * RBM_LOG2E : 0.f;
   }
-  const int cb = v0 + tx * 4;
-  float bv[4];
+  float acc[DT][4], bsum[2] = {0.f, 0.f};
 #pragma unroll
-  for (int j = 0; j < 4; ++j) bv[j] = (bias && cb + j < V1) ? bias[cb + j] : 0.f;
-  float acc2[NT2][4][4];  // dW rows (vocab) ty*4+i, cols tx*4 + 64*t + j
-  float bsum[4] = {0.f, 0.f, 0.f, 0.f};
-#pragma unroll
-  for (int t = 0; t < NT2; ++t)
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc2[t][i][j] = 0.f;
-
-  const int ntiles = (count + T - 1) / T;
-  for (int rt_ = s; rt_ < ntiles; rt_ += S) {
-    const int r0 = rt_ * T;
-    __syncthreads();  // previous iteration's GEMM2 is done with Hrow / Gs
-    load_rows_rowmajor(Hrow, ldh, h, rows, r0, count, d);
-    __syncthreads();
-    // GEMM1: logits[r][c] for rows ty*4+i, cols tx*4+j
-    float acc[4][4];
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-#pragma unroll
-      for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
-    for (int k = 0; k < d; ++k) {
-      float4 b = ld4(Wst + k * LDT + tx * 4);
-      float4 a = make_float4(Hrow[(ty * 4 + 0) * ldh + k], Hrow[(ty * 4 + 1) * ldh + k], Hrow[(ty * 4 + 2) * ldh + k],
-                             Hrow[(ty * 4 + 3) * ldh + k]);
-      FMA44(acc, a, b);
+  for (int dt = 0; dt < DT; ++dt) acc[dt][0] = acc[dt][1] = acc[dt][2] = acc[dt][3] = 0.f;
+  const int NC = (count + CH - 1) / CH;
+  auto issue = [&](int c, int buf) {
+    panel_load_async(panel + buf * CH * LD, a.h, a.rows, (int64_t)c * CH, count, d, LD);
+    for (int j = threadIdx.x; j < CH; j += blockDim.x) {
+      int r = c * CH + j;
+      lse_s[buf * CH + j] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
+      tgt_s[buf * CH + j] = r < count ? (float)a.tgt[r] : -1.f;
     }
-#pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      int r = r0 + ty * 4 + i;
-      int64_t tg = r < count ? tgt[r] : -1;
-      float rl = r < count ? lse[r] : 0.f;
-      float g[4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        float p = (cb + j < V1 && tg >= 0) ? expf(acc[i][j] + bv[j] - rl) : 0.f;
-        if ((int64_t)(cb + j) == tg) p -= 1.f;
-        g[j] = p * gscale;
-      }
-      st4(Gs + (ty * 4 + i) * LDT + tx * 4, make_float4(g[0], g[1], g[2], g[3]));
+    cp_async_commit();
+  };
+  int it = 0;
+  if (sp < NC) issue(sp, 0);
+  for (int c = sp; c < NC; c += S, ++it) {
+    const int buf = it & 1;
+    if (c + S < NC) {
+      issue(c + S, buf ^ 1);
+      cp_async_wait<1>();
+    } else {
+      cp_async_wait<0>();
     }
     __syncthreads();
-    // GEMM2: dW[c][kk] += sum_r G[r][c] * H[r][kk];  thread owns vocab rows ty*4.., cols tx*4 + 64*t ..
-    for (int r = 0; r < T; ++r) {
-      float4 a = ld4(Gs + r * LDT + ty * 4);
-      bsum[0] += a.x; bsum[1] += a.y; bsum[2] += a.z; bsum[3] += a.w;
+    const float* pn = panel + buf * CH * LD;
+    float s[8][4];
 #pragma unroll
-      for (int t = 0; t < NT2; ++t) {
-        int kk = tx * 4 + 64 * t;
-        if (kk < d) {
-          float4 b = ld4(Hrow + r * ldh + kk);
-          FMA44(acc2[t], a, b);
-        }
+    for (int nt = 0; nt < 8; ++nt) s[nt][0] = s[nt][1] = s[nt][2] = s[nt][3] = 0.f;
+    tile_dot_panel(s, Ws, QLD, pn, LD, 0, CH, d, g, t);  // S^T: rows = vocab, cols = compacted rows
+#pragma unroll
+    for (int nt = 0; nt < 8; ++nt) {
+      float2 ls = *reinterpret_cast<const float2*>(lse_s + buf * CH + nt * 8 + 2 * t);
+      float2 ts = *reinterpret_cast<const float2*>(tgt_s + buf * CH + nt * 8 + 2 * t);
+      float gg[4];
+#pragma unroll
+      for (int cc = 0; cc < 4; ++cc) {
+        int hr = cc >> 1;
+        float tcol = (cc & 1) ? ts.y : ts.x, lcol = (cc & 1) ? ls.y : ls.x;
+        float p = (vrow[hr] < V1 && tcol >= 0.f) ? ex2(s[nt][cc] + b2[hr] - lcol) : 0.f;
+        if (tcol == (float)vrow[hr]) p -= 1.f;
+        gg[cc] = p * gscale;
+        bsum[hr] += gg[cc];
       }
+      *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(gg[0], gg[1]);
+      *reinterpret_cast<float2*>(Pb + (g + 8) * PB_LD + nt * 8 + 2 * t) = make_float2(gg[2], gg[3]);
     }
+    __syncwarp();
+    ptile_times_panel<DT>(acc, Pb, pn, LD, 0, CH, d, g, t);  // dW += G^T . H[chunk]
+    __syncthreads();
   }
-  float* pw = part_w + (int64_t)s * V1 * d;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    int c = v0 + ty * 4 + i;
-    if (c < V1) {
+  for (int hr = 0; hr < 2; ++hr) {
+    float bs = quad_sum(bsum[hr]);
+    if (vrow[hr] < V1) {
+      float* dst = a.part_w + ((int64_t)sp * V1 + vrow[hr]) * d;
 #pragma unroll
-      for (int t = 0; t < NT2; ++t) {
-        int kk = tx * 4 + 64 * t;
-        if (kk < d) st4(pw + (int64_t)c * d + kk, make_float4(acc2[t][i][0], acc2[t][i][1], acc2[t][i][2], acc2[t][i][3]));
-      }
-      if (tx == 0) part_b[(int64_t)s * V1 + c] = bsum[i];
+      for (int dt = 0; dt < DT; ++dt)
+        if (dt * 8 < d) *reinterpret_cast<float2*>(dst + dt * 8 + 2 * t) = make_float2(acc[dt][2 * hr], acc[dt][2 * hr + 1]);
+      if (t == 0) a.part_b[(int64_t)sp * V1 + vrow[hr]] = bs;
     }
   }
 }
@@ -432,13 +417,24 @@ __global__ void ce_reduce_splits_kernel(const float* __restrict__ part, float* _
   out[i] = s;
 }
 
-int dw_splits(int64_t cap, int V1) {
-  int64_t vt = rbm_cdiv(V1, T), rtiles = rbm_cdiv(cap, T);
+// warps per CTA so that the tiles fit in shared memory (fewer warps for wide hidden sizes)
+size_t ce_smem(int d, int warps, bool with_pb) {
+  int LD = (d + 31) & ~31;
+  return sizeof(float) * ((size_t)2 * CH * LD + 4 * CH + warps * 16 + (size_t)warps * (16 * (d + 4) + (with_pb ? 16 * PB_LD : 0)));
+}
+int ce_warps(int d, bool with_pb) {
+  int w = 8;
+  while (w > 1 && ce_smem(d, w, with_pb) > 100 * 1024) w >>= 1;  // <= 100 KB: two CTAs per SM
+  while (w > 1 && ce_smem(d, w, with_pb) > 227 * 1024) w >>= 1;
+  return w;
+}
+int dw_splits(int64_t cap, int V1, int warps) {
+  int64_t vt = rbm_cdiv(V1, 16 * warps), chunks = rbm_cdiv(cap, CH);
   int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS * 4, vt);
-  if (s > rtiles) s = rtiles;
+  if (s > chunks) s = chunks;
+  if (s > 64) s = 64;
   return (int)(s < 1 ? 1 : s);
 }
-int nt2_of(int d) { return d <= 64 ? 1 : d <= 128 ? 2 : 4; }
 
 }  // namespace
 
@@ -460,14 +456,15 @@ extern "C" int rbm_compact_labels(const int64_t* labels, int64_t n, int32_t* row
 }
 
 extern "C" size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d) {
-  size_t nblk = (size_t)rbm_cdiv(cap, T);
-  size_t S = (size_t)dw_splits(cap, V1);
+  size_t nblk = (size_t)rbm_cdiv(cap, 16);  // upper bound for any warps-per-CTA choice
+  size_t S = (size_t)dw_splits(cap, V1, 1);
+  if (S < (size_t)dw_splits(cap, V1, 8)) S = (size_t)dw_splits(cap, V1, 8);
   return (nblk + S * ((size_t)V1 * d + V1)) * sizeof(float) + 64;
 }
 
 static int ce_check(const char* name, int64_t cap, int V1, int d) {
-  RBM_REQUIRE(cap > 0 && cap < (int64_t)1 << 31 && V1 > 0, "%s: bad sizes cap=%lld V1=%d", name, (long long)cap, V1);
-  RBM_REQUIRE(d >= 4 && d % 4 == 0 && d <= 256, "%s: unsupported hidden size d=%d (need d%%4==0, d<=256)", name, d);
+  RBM_REQUIRE(cap > 0 && cap < (int64_t)1 << 31 && V1 > 0 && V1 < (1 << 24), "%s: bad sizes cap=%lld V1=%d (V1 < 2^24)", name, (long long)cap, V1);
+  RBM_REQUIRE(d >= 8 && d % 8 == 0 && d <= 256, "%s: unsupported hidden size d=%d (need d%%8==0, d<=256)", name, d);
   return 0;
 }
 
@@ -479,10 +476,13 @@ extern "C" int rbm_ce_fwd(const float* h, const int32_t* rows, const int64_t* tg
   RBM_REQUIRE(ws_bytes >= rbm_ce_ws_bytes(cap, V1, d), "rbm_ce_fwd: workspace too small");
   RBM_REQUIRE(rbm_aligned16(h) && rbm_aligned16(w) && rbm_aligned16(ws), "rbm_ce_fwd: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  int nblk = (int)rbm_cdiv(cap, T);
-  size_t smem = sizeof(float) * ((size_t)d * LDT + KC * LDT + T);
+  int warps = ce_warps(d, false);
+  int nblk = (int)rbm_cdiv(cap, 16 * warps);
+  size_t smem = ce_smem(d, warps, false);
   cudaFuncSetAttribute(ce_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  ce_fwd_kernel<<<nblk, 256, smem, st>>>(h, rows, tgt, count, w, bias, lse, (float*)ws, V1, d);
+  CeArgs a{};
+  a.h = h; a.rows = rows; a.tgt = tgt; a.count = count; a.w = w; a.bias = bias; a.lse_out = lse; a.partial = (float*)ws; a.V1 = V1; a.d = d;
+  ce_fwd_kernel<<<nblk, 32 * warps, smem, st>>>(a);
   RBM_LAUNCH_CHECK("rbm_ce_fwd");
   ce_loss_finalize_kernel<<<1, 256, 0, st>>>((const float*)ws, nblk, count, loss);
   RBM_LAUNCH_CHECK("rbm_ce_fwd(finalize)");
@@ -498,25 +498,28 @@ extern "C" int rbm_ce_bwd(const float* h, const int32_t* rows, const int64_t* tg
   RBM_REQUIRE(rbm_aligned16(h) && rbm_aligned16(w) && rbm_aligned16(ws) && rbm_aligned16(dh_full) && rbm_aligned16(dw),
               "rbm_ce_bwd: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
-  int nblk = (int)rbm_cdiv(cap, T);
-  int S = dw_splits(cap, V1);
-  int nt2 = nt2_of(d);
-  size_t smem_dh = sizeof(float) * ((size_t)d * LDT + KC * LDT + T * LDT + (size_t)T * (d + 4));
-  size_t smem_dw = sizeof(float) * ((size_t)d * LDT + (size_t)T * (d + 4) + T * LDT);
-  float* part_w = (float*)ws + nblk;
+  int warps = ce_warps(d, true);
+  int nblk = (int)rbm_cdiv(cap, 16 * warps);
+  int S = dw_splits(cap, V1, warps);
+  size_t smem = ce_smem(d, warps, true);
+  float* part_w = (float*)ws + rbm_cdiv(cap, 16);
   part_w = (float*)(((uintptr_t)part_w + 15) & ~(uintptr_t)15);
   float* part_b = part_w + (size_t)S * V1 * d;
-  dim3 gdw((unsigned)rbm_cdiv(V1, T), S);
-#define CE_BWD(NT2)                                                                                                   \
-  do {                                                                                                                \
-    cudaFuncSetAttribute(ce_bwd_dh_kernel<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dh);           \
-    ce_bwd_dh_kernel<NT2><<<nblk, 256, smem_dh, st>>>(h, rows, tgt, count, w, bias, lse, dloss, dh_full, V1, d);      \
-    cudaFuncSetAttribute(ce_bwd_dw_kernel<NT2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_dw);           \
-    ce_bwd_dw_kernel<NT2><<<gdw, 256, smem_dw, st>>>(h, rows, tgt, count, w, bias, lse, dloss, part_w, part_b, V1, d); \
+  CeArgs a{};
+  a.h = h; a.rows = rows; a.tgt = tgt; a.count = count; a.w = w; a.bias = bias; a.lse_in = lse; a.dloss = dloss;
+  a.dh_full = dh_full; a.part_w = part_w; a.part_b = part_b; a.V1 = V1; a.d = d;
+  dim3 gdw((unsigned)rbm_cdiv(V1, 16 * warps), S);
+#define CE_BWD(DT)                                                                                          \
+  do {                                                                                                      \
+    cudaFuncSetAttribute(ce_bwd_dh_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    ce_bwd_dh_kernel<DT><<<nblk, 32 * warps, smem, st>>>(a);                                                \
+    cudaFuncSetAttribute(ce_bwd_dw_kernel<DT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
+    ce_bwd_dw_kernel<DT><<<gdw, 32 * warps, smem, st>>>(a);                                                 \
   } while (0)
-  if (nt2 == 1) CE_BWD(1);
-  else if (nt2 == 2) CE_BWD(2);
-  else CE_BWD(4);
+  if (d <= 32) CE_BWD(4);
+  else if (d <= 64) CE_BWD(8);
+  else if (d <= 128) CE_BWD(16);
+  else CE_BWD(32);
 #undef CE_BWD
   RBM_LAUNCH_CHECK("rbm_ce_bwd");
   int64_t n = (int64_t)V1 * d;
