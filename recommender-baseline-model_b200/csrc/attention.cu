@@ -14,6 +14,7 @@
 // are bit-deterministic.  A tcgen05/TMEM formulation of these L<=256 tiles is tracked in DESIGN.md ("next").
 #include "common.cuh"
 #include "mma_tiles.cuh"
+#include "attention_tc.cuh"
 
 namespace {
 
@@ -443,6 +444,9 @@ extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t
   RBM_REQUIRE(ldq % 4 == 0 && ldk % 4 == 0 && ldv % 4 == 0 && ldo % 2 == 0 && rbm_aligned16(q) && rbm_aligned16(k) && rbm_aligned16(v) &&
                   ((uintptr_t)out & 7) == 0,
               "rbm_attn_fwd: q/k/v must be 16B aligned with strides %% 4 == 0 (out: 8B, stride %% 2)");
+  if (rbm_attn_fwd_tc_supported(L, dk, ldq, ldk, ldv, ldo, q, k, v, out))  // Blackwell tensor path (d_k == 32)
+    return rbm_attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site,
+                                  (cudaStream_t)stream);
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.stats = stats; a.tok = tok;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;

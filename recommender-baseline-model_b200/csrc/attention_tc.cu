@@ -1,0 +1,351 @@
+// attention_tc.cu -- attention FORWARD on the Blackwell tensor path for d_k = 32, L <= 240 (the cfg2 BERT4Rec shape).
+//
+// One CTA per (sequence, head).  TMA (3-D maps over [B, L, cols], 128-byte swizzle) brings the head's K, V and Q rows
+// into shared memory (one 128-byte swizzle row per token: d_k = 32 fp32); the same tiles serve as K-major operands
+// (q.k^T, contraction along the row) and MN-major operands (P.v, contraction along tokens).  Per 128-query tile:
+//     S = Q.K^T            tcgen05.mma kind::tf32, SMEM x SMEM -> TMEM [128 x Lp]
+//     softmax in place     8 warps, one thread per query row (tcgen05.ld 32x32b), masks, log2-domain ex2, dropout
+//                          (Philox), P and its TF32 residual written back to TMEM (tcgen05.st)
+//     O = P.V              tcgen05.mma with the A operand read from TMEM, V MN-major from SMEM -> TMEM [128 x 32]
+// Every product is 3xTF32-compensated (raw/lo copies of Q, K, V in SMEM, of P in TMEM): fp32-level accuracy.
+// Scores/probabilities never leave the SM.  Shapes outside (d_k == 32, L <= 240) use the mma.sync kernels (attention.cu).
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "mma_tiles.cuh"  // ex2, RBM_LOG2E, RBM_PADFILL
+#include "tc_ptx.cuh"
+#include "attention_tc.cuh"
+
+namespace {
+
+using namespace rbm_tc;
+using rbm_mma::ex2;
+
+constexpr int DK = 32;
+constexpr int ROWB = DK * 4;     // 128 bytes per token row
+constexpr int SPLITC = 112;      // column split between the two softmax warps of a TMEM quarter
+constexpr int NSW = 8;           // softmax warps
+
+struct TcAttnArgs {
+  const int64_t* tok;
+  float* out;
+  float* stats;
+  int64_t ldo;
+  int L, LPK, h, NT, mask_mode;
+  float scale_log2;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+  int dbg;  // bring-up bisect mask (RBM_TC_ATTN_DEBUG): 1 skip S mma, 2 skip PV mma, 4 skip tmem st, 8 skip tmem ld, 16 skip TMA, 32 skip split
+};
+
+__device__ __forceinline__ void split_lo_bytes(const uint8_t* src, uint8_t* dst, int n4, int tid, int nthr) {
+  for (int i = tid; i < n4; i += nthr) {
+    float4 v = ld4(reinterpret_cast<const float*>(src) + i * 4), o;
+    o.x = v.x - __uint_as_float(__float_as_uint(v.x) & 0xffffe000u);
+    o.y = v.y - __uint_as_float(__float_as_uint(v.y) & 0xffffe000u);
+    o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
+    o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
+    st4(reinterpret_cast<float*>(dst) + i * 4, o);
+  }
+}
+
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                       const __grid_constant__ CUtensorMap mapK,
+                                                                       const __grid_constant__ CUtensorMap mapV, const TcAttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t load_bar, split_bar, s_full[2], p_full[2], o_full[2];
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float padk[256];
+  __shared__ float xmax[2][128], xsum[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
+  const int L = a.L, LPK = a.LPK, NT = a.NT;
+  const uint32_t kv_bytes = (uint32_t)LPK * ROWB, q_bytes = (uint32_t)NT * 128 * ROWB;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  // layout: K raw | K lo | V raw | V lo | Q raw | Q lo     (kv_bytes is a multiple of 2048: LPK % 16 == 0)
+  const uint32_t oK = 0, oKl = kv_bytes, oV = 2 * kv_bytes, oVl = 3 * kv_bytes, oQ = 4 * kv_bytes, oQl = 4 * kv_bytes + q_bytes;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&load_bar), 1);
+    mbar_init(smem_u32(&split_bar), NSW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&p_full[i]), NSW);
+      mbar_init(smem_u32(&o_full[i]), 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tS = tmem, tPl = tmem + (uint32_t)LPK, tO = tmem + (uint32_t)(2 * LPK);
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(&load_bar);
+      if (a.dbg & 16) {
+        mbar_arrive(bar);
+      } else {
+        mbar_expect_tx(bar, 2 * kv_bytes + q_bytes);
+        tma_load_3d(smem_base + oK, &mapK, bar, hh * DK, 0, b);
+        tma_load_3d(smem_base + oV, &mapV, bar, hh * DK, 0, b);
+        for (int mt = 0; mt < NT; ++mt) tma_load_3d(smem_base + oQ + mt * 128 * ROWB, &mapQ, bar, hh * DK, mt * 128, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idS = make_idesc_tf32_ex(128, LPK, 0, 0);  // both operands K-major
+      const uint32_t idO = make_idesc_tf32_ex(128, DK, 0, 1);   // A from TMEM, V MN-major
+      mbar_wait(smem_u32(&load_bar), 0);
+      mbar_wait(smem_u32(&split_bar), 0);
+      tc_fence_after();
+      const uint64_t dK = make_sw128_desc(smem_base + oK), dKl = make_sw128_desc(smem_base + oKl);
+      for (int mt = 0; mt < NT; ++mt) {
+        const int ph = mt & 1, par = (mt >> 1) & 1;
+        const uint64_t dQ = make_sw128_desc(smem_base + oQ + mt * 128 * ROWB), dQl = make_sw128_desc(smem_base + oQl + mt * 128 * ROWB);
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          if (a.dbg & 1) break;
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32(tS, dQ + o, dKl + o, idS, k != 0);
+          umma_tf32(tS, dQl + o, dK + o, idS, 1);
+          umma_tf32(tS, dQ + o, dK + o, idS, 1);
+        }
+        umma_commit(smem_u32(&s_full[ph]));
+        mbar_wait(smem_u32(&p_full[ph]), par);
+        tc_fence_after();
+        for (int kk = 0; kk < LPK / 8; ++kk) {
+          if (a.dbg & 2) break;
+          // 8 keys per step: one 8-row (1024-byte) swizzle atom of V; 8 TMEM columns of P
+          const uint64_t dV = make_sw128_desc_mn(smem_base + oV + kk * 1024, 0), dVl = make_sw128_desc_mn(smem_base + oVl + kk * 1024, 0);
+          umma_tf32_ts(tO, tS + kk * 8, dVl, idO, kk != 0);
+          umma_tf32_ts(tO, tPl + kk * 8, dV, idO, 1);
+          umma_tf32_ts(tO, tS + kk * 8, dV, idO, 1);
+        }
+        umma_commit(smem_u32(&o_full[ph]));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int tid = sw * 32 + lane;
+    const int64_t row0 = (int64_t)b * L;
+    for (int j = tid; j < 256; j += NSW * 32) padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
+    // TF32 residual copies of K, V, Q
+    mbar_wait(smem_u32(&load_bar), 0);
+    if (!(a.dbg & 32)) {
+      split_lo_bytes(gen + oK, gen + oKl, (int)(kv_bytes / 16), tid, NSW * 32);
+      split_lo_bytes(gen + oV, gen + oVl, (int)(kv_bytes / 16), tid, NSW * 32);
+      split_lo_bytes(gen + oQ, gen + oQl, (int)(q_bytes / 16), tid, NSW * 32);
+    }
+    fence_proxy_async();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&split_bar));
+    named_bar_sync(1, NSW * 32);  // padk visible to all softmax warps
+
+    const int cbeg = half == 0 ? 0 : SPLITC;
+    const int cend = half == 0 ? (LPK < SPLITC ? LPK : SPLITC) : LPK;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int rl = q * 32 + lane;  // row within the 128-row tile
+    for (int mt = 0; mt < NT; ++mt) {
+      const int ph = mt & 1, par = (mt >> 1) & 1;
+      const int i = mt * 128 + rl;
+      mbar_wait(smem_u32(&s_full[ph]), par);
+      tc_fence_after();
+      // ---- pass 1: row maximum (log2 domain)
+      float mx = -INFINITY;
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16];
+        if (a.dbg & 8) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+        } else {
+          tmem_ld16(tS + lane_sel + (uint32_t)c0, v);
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = c0 + jj;
+          float x = v[jj] * a.scale_log2;
+          if (padk[j] != 0.f) x = RBM_PADFILL;
+          if (j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i)) x = -INFINITY;
+          mx = fmaxf(mx, x);
+        }
+      }
+      xmax[half][rl] = mx;
+      named_bar_sync(2 + q, 64);
+      mx = fmaxf(xmax[0][rl], xmax[1][rl]);
+      const float base = mx == -INFINITY ? 0.f : mx;
+      // ---- pass 2: probabilities, dropout, write P (raw + TF32 residual) back to TMEM
+      float sum = 0.f;
+      const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float v[16], lo[16];
+        if (a.dbg & 8) {
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
+        } else {
+          tmem_ld16(tS + lane_sel + (uint32_t)c0, v);
+        }
+        uint4 calls[4];
+        if (a.thr16) {
+          // rows i and i^8 (lanes l, l^8) share their Philox calls: each lane computes two and they are exchanged
+          uint4 c0r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, tile, g, rh * 2 + 0, c0 >> 4));
+          uint4 c1r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, tile, g, rh * 2 + 1, c0 >> 4));
+          uint4 o0, o1;
+          o0.x = __shfl_xor_sync(0xffffffffu, c0r.x, 8); o0.y = __shfl_xor_sync(0xffffffffu, c0r.y, 8);
+          o0.z = __shfl_xor_sync(0xffffffffu, c0r.z, 8); o0.w = __shfl_xor_sync(0xffffffffu, c0r.w, 8);
+          o1.x = __shfl_xor_sync(0xffffffffu, c1r.x, 8); o1.y = __shfl_xor_sync(0xffffffffu, c1r.y, 8);
+          o1.z = __shfl_xor_sync(0xffffffffu, c1r.z, 8); o1.w = __shfl_xor_sync(0xffffffffu, c1r.w, 8);
+          calls[0] = rh ? o0 : c0r; calls[1] = rh ? o1 : c1r; calls[2] = rh ? c0r : o0; calls[3] = rh ? c1r : o1;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = c0 + jj;
+          float x = v[jj] * a.scale_log2;
+          if (padk[j] != 0.f) x = RBM_PADFILL;
+          if (j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i)) x = -INFINITY;
+          float p = ex2(x - base);
+          sum += p;
+          if (a.thr16) {
+            const int f = rh * 4 + (jj & 1) * 2 + ((jj >> 3) & 1);
+            p = rbm_attn_field(calls[(jj & 7) >> 1], f) >= a.thr16 ? p * a.inv_keep : 0.f;
+          }
+          v[jj] = p;
+          lo[jj] = p - __uint_as_float(__float_as_uint(p) & 0xffffe000u);
+        }
+        if (!(a.dbg & 4)) {
+          tmem_st16(tS + lane_sel + (uint32_t)c0, v);
+          tmem_st16(tPl + lane_sel + (uint32_t)c0, lo);
+        }
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      xsum[half][rl] = sum;
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&p_full[ph]));
+      named_bar_sync(2 + q, 64);
+      const float inv = 1.f / (xsum[0][rl] + xsum[1][rl]);
+      // ---- epilogue: O (16 columns per warp of the pair) scaled by 1/rowsum
+      mbar_wait(smem_u32(&o_full[ph]), par);
+      tc_fence_after();
+      float o[16];
+      if (a.dbg & 8) {
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) o[jj] = 0.f;
+      } else {
+        tmem_ld16(tO + lane_sel + (uint32_t)(half * 16), o);
+      }
+      float sv[16];
+      if (a.dbg & 64) tmem_ld16(tS + lane_sel, sv);  // warp-uniform
+      if ((a.dbg & 64) && i < L && half == 0) {  // bring-up: expose internals in the first output columns
+        o[0] = mx; o[1] = xsum[0][rl] + xsum[1][rl]; o[2] = sv[0]; o[3] = sv[1]; o[4] = o[4]; o[5] = (float)tmem; o[6] = (float)i;
+        float* dst = a.out + (row0 + i) * a.ldo + hh * DK;
+        for (int jj = 0; jj < 16; ++jj) dst[jj] = o[jj];
+      } else if (i < L) {
+        float* dst = a.out + (row0 + i) * a.ldo + hh * DK + half * 16;
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) st4(dst + jj, make_float4(o[jj] * inv, o[jj + 1] * inv, o[jj + 2] * inv, o[jj + 3] * inv));
+        if (half == 0 && a.stats) {
+          const int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
+          a.stats[sr] = mx;
+          a.stats[sr + 1] = inv;
+        }
+      }
+      tc_fence_before();
+      named_bar_sync(2 + q, 64);  // xmax/xsum reuse by the next tile
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+// [B, L, width] fp32 view of a token-major buffer with row stride ld; box = [1, box_rows, 32], 128-byte swizzle
+bool encode_map3(CUtensorMap* map, const float* base, int B, int L, int width, int64_t ld, int box_rows, bool mn_major) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)L, (cuuint64_t)B};
+  cuuint64_t gstride[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)L * ld * sizeof(float)};
+  cuuint32_t box[3] = {(cuuint32_t)DK, (cuuint32_t)box_rows, 1};
+  cuuint32_t estr[3] = {1, 1, 1};
+  // K-major consumers read the classic 128-byte swizzle; MN-major TF32 consumers need the 32-byte-atom variant
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RBM_ATTN_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+
+}  // namespace
+
+bool rbm_attn_fwd_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
+                               const void* v, const void* out) {
+  if (!tc_enabled() || dk != DK || L < 1 || L > 240) return false;  // TMEM: 2*Lp (P raw + residual) + 32 (O) <= 512 columns
+  if (ldq % 4 || ldk % 4 || ldv % 4 || ldo % 4) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) return false;
+  return get_encode() != nullptr;
+}
+
+int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
+                           float* out, int64_t ldo, float* stats, int B, int L, int h, int mask_mode, float scale, float p,
+                           uint64_t seed, uint64_t site, cudaStream_t st) {
+  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+  CUtensorMap mapQ, mapK, mapV;
+  if (!encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) || !encode_map3(&mapK, k, B, L, h * DK, ldk, LPK, false) ||
+      !encode_map3(&mapV, v, B, L, h * DK, ldv, LPK, true)) {
+    rbm_set_error("rbm_attn_fwd(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  TcAttnArgs a{};
+  a.tok = tok; a.out = out; a.stats = stats; a.ldo = ldo; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode;
+  a.scale_log2 = scale * RBM_LOG2E;
+  a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
+  {
+    const char* e = getenv("RBM_TC_ATTN_DEBUG");
+    a.dbg = e ? atoi(e) : 0;
+  }
+  size_t smem = (size_t)4 * LPK * ROWB + (size_t)2 * NT * 128 * ROWB + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_attn_fwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  attn_fwd_tc_kernel<<<B * h, 64 + 32 * NSW, smem, st>>>(mapQ, mapK, mapV, a);
+  RBM_LAUNCH_CHECK("rbm_attn_fwd(tcgen05)");
+  return 0;
+}

@@ -1,0 +1,10 @@
+// attention_tc.cuh -- internal interface of the tcgen05 attention forward (attention_tc.cu), dispatched from attention.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+bool rbm_attn_fwd_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
+                               const void* v, const void* out);
+int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
+                           float* out, int64_t ldo, float* stats, int B, int L, int h, int mask_mode, float scale, float p,
+                           uint64_t seed, uint64_t site, cudaStream_t st);
