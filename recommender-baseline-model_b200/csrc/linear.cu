@@ -282,6 +282,32 @@ __global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict_
     if (c0 + i < cols && r < rows) dst[(int64_t)(c0 + i) * rows + r] = tile[threadIdx.x][i];
 }
 
+// column sums of dpre (bias gradient) for the tcgen05 dW path: block b sums rows [b*rpb, ...) -> part_b[b][N]
+__global__ void __launch_bounds__(256) colsum_split_kernel(const float* __restrict__ a, int64_t lda, float* __restrict__ part_b, int64_t M, int N,
+                                                           int64_t rows_per_block) {
+  __shared__ float4 red[256];
+  const int n4 = N >> 2;                 // <= 64 float4 columns
+  const int groups = 256 / n4;           // row groups working in parallel
+  const int c4 = threadIdx.x % n4, rg = threadIdx.x / n4;
+  int64_t r0 = (int64_t)blockIdx.x * rows_per_block, r1 = r0 + rows_per_block < M ? r0 + rows_per_block : M;
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (rg < groups)
+    for (int64_t r = r0 + rg; r < r1; r += groups) {
+      float4 v = ld4(a + r * lda + c4 * 4);
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    }
+  red[threadIdx.x] = s;
+  __syncthreads();
+  if (threadIdx.x < n4) {
+    float4 t = red[threadIdx.x];
+    for (int gq = 1; gq < groups; ++gq) {
+      float4 v = red[gq * n4 + threadIdx.x];
+      t.x += v.x; t.y += v.y; t.z += v.z; t.w += v.w;
+    }
+    st4(part_b + (int64_t)blockIdx.x * N + threadIdx.x * 4, t);
+  }
+}
+
 int tn_splits(int64_t M, int N, int K) {
   int64_t tiles = rbm_cdiv(N, 64) * rbm_cdiv(K, 64);
   int64_t want = rbm_cdiv((int64_t)RBM_NUM_SMS * 4, tiles);
@@ -368,6 +394,8 @@ extern "C" int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const floa
 
 extern "C" size_t rbm_linear_bwd_weight_ws_bytes(int64_t M, int N, int K) {
   int S = tn_splits(M, N, K);
+  int S2 = rbm_tc_dw_splits(M);
+  if (S2 > S) S = S2;
   return (size_t)S * ((size_t)N * K + N) * sizeof(float);
 }
 
@@ -378,6 +406,23 @@ extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const fl
   RBM_REQUIRE(lddpre % 4 == 0 && ldx % 4 == 0 && lddpre >= N && ldx >= K, "rbm_linear_bwd_weight: bad leading dimensions");
   RBM_REQUIRE(ws_bytes >= rbm_linear_bwd_weight_ws_bytes(M, N, K), "rbm_linear_bwd_weight: workspace too small");
   RBM_REQUIRE(rbm_aligned16(dpre) && rbm_aligned16(x) && rbm_aligned16(dw) && rbm_aligned16(ws), "rbm_linear_bwd_weight: pointers must be 16B aligned");
+  if (use_tc() && rbm_tc_dw_supported(M, N, K, lddpre, ldx, dpre, x)) {
+    const int S = rbm_tc_dw_splits(M);
+    float* part = (float*)ws;
+    float* part_b = part + (size_t)S * N * K;
+    int rc = rbm_tc_dw_launch(dpre, lddpre, x, ldx, part, M, N, K, (cudaStream_t)stream);
+    if (rc) return rc;
+    int64_t n = (int64_t)N * K;
+    reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(part, dw, n, S);
+    RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
+    if (db) {
+      int64_t rpb = rbm_cdiv(M, S);
+      colsum_split_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(dpre, lddpre, part_b, M, N, rpb);
+      reduce_splits_kernel<<<(unsigned)rbm_cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(part_b, db, N, S);
+      RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(bias)");
+    }
+    return 0;
+  }
   int S = tn_splits(M, N, K);
   int64_t rps = rbm_cdiv(rbm_cdiv(M, S), BK) * BK;
   float* part = (float*)ws;

@@ -362,6 +362,150 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
   }
 }
 
+// =====================================================================================================
+// Weight gradient:  dW[N, K] = dpre[M, N]^T . x[M, K]   (contraction over the M tokens)
+// Both operands are token-major in HBM, i.e. MN-major for the tensor core: TMA (128-byte swizzle with 32-byte atoms,
+// the only MN-major layout for 32-bit operands) stages [32 tokens x 32 columns] blocks, tcgen05.mma runs with
+// a_major = b_major = MN.  Each persistent CTA owns a contiguous slab of tokens and accumulates its partial dW in
+// TMEM (one or two 128-row M tiles x K columns); partials are summed in fixed order by reduce_splits (linear.cu).
+// 3xTF32: split warps derive the TF32 residual of every staged block.
+// warps: 0 = TMA, 1 = MMA, 2-5 = split, then all of 2-5 read the accumulators out at the end.
+// =====================================================================================================
+constexpr int DW_TOK = 32;                 // tokens per stage
+constexpr int DW_BLK = DW_TOK * 128;       // bytes of one [32 tokens x 32 columns] block
+
+struct DwParams {
+  float* part;     // [S][N][K]
+  int64_t M, tok_per_cta;
+  int N, K, nblkA, nblkB, mtiles, nstage;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                       const DwParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], split_bar[8], empty_bar[8], done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int nblkA_pad = p.mtiles * 4;  // A blocks incl. zero padding up to a multiple of 128 rows of dW
+  const uint32_t a_bytes = (uint32_t)nblkA_pad * DW_BLK, b_bytes = (uint32_t)p.nblkB * DW_BLK;
+  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);  // raw A | raw B | lo A | lo B
+  const int64_t t0 = (int64_t)blockIdx.x * p.tok_per_cta;
+  int64_t t1 = t0 + p.tok_per_cta;
+  if (t1 > p.M) t1 = p.M;
+  const int nst = t1 > t0 ? (int)((t1 - t0 + DW_TOK - 1) / DW_TOK) : 0;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.nstage; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&split_bar[s]), 4);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  // padding blocks of A (columns >= N) are never written by TMA: zero them once (raw and lo)
+  if (nblkA_pad > p.nblkA)
+    for (int s = 0; s < p.nstage; ++s)
+      for (int half = 0; half < 2; ++half) {
+        float4* z = reinterpret_cast<float4*>(gen + (size_t)s * stage_bytes + (size_t)half * (a_bytes + b_bytes) + (size_t)p.nblkA * DW_BLK);
+        const int n4 = (nblkA_pad - p.nblkA) * DW_BLK / 16;
+        for (int i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+  fence_proxy_async();
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      for (int g = 0; g < nst; ++g) {
+        const int s = g % p.nstage;
+        if (g >= p.nstage) mbar_wait(smem_u32(&empty_bar[s]), ((g / p.nstage) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t sa = smem_base + s * stage_bytes;
+        mbar_expect_tx(bar, (uint32_t)(p.nblkA + p.nblkB) * DW_BLK);
+        const int tok = (int)(t0 + (int64_t)g * DW_TOK);
+        for (int j = 0; j < p.nblkA; ++j) tma_load_2d(sa + j * DW_BLK, &mapA, bar, j * 32, tok);
+        for (int j = 0; j < p.nblkB; ++j) tma_load_2d(sa + a_bytes + j * DW_BLK, &mapB, bar, j * 32, tok);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32_ex(BM, p.K, 1, 1);
+      for (int g = 0; g < nst; ++g) {
+        const int s = g % p.nstage;
+        mbar_wait(smem_u32(&full_bar[s]), (g / p.nstage) & 1);
+        mbar_wait(smem_u32(&split_bar[s]), (g / p.nstage) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes, sl = sa + a_bytes + b_bytes;
+        for (int mt = 0; mt < p.mtiles; ++mt) {
+          const uint32_t d = tmem_d + (uint32_t)(mt * p.K);
+#pragma unroll
+          for (int k = 0; k < DW_TOK / UMMA_K; ++k) {  // 8 tokens = 1024 bytes inside every block
+            const uint64_t a_raw = make_sw128_desc_mn(sa + mt * 4 * DW_BLK + k * 1024, DW_BLK);
+            const uint64_t a_lo = make_sw128_desc_mn(sl + mt * 4 * DW_BLK + k * 1024, DW_BLK);
+            const uint64_t b_raw = make_sw128_desc_mn(sa + a_bytes + k * 1024, DW_BLK);
+            const uint64_t b_lo = make_sw128_desc_mn(sl + a_bytes + k * 1024, DW_BLK);
+            umma_tf32(d, a_raw, b_lo, idesc, (g | k) != 0);
+            umma_tf32(d, a_lo, b_raw, idesc, 1);
+            umma_tf32(d, a_raw, b_raw, idesc, 1);
+          }
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else {
+    const int tid = threadIdx.x - 64;
+    for (int g = 0; g < nst; ++g) {
+      const int s = g % p.nstage;
+      mbar_wait(smem_u32(&full_bar[s]), (g / p.nstage) & 1);
+      uint8_t* st = gen + (size_t)s * stage_bytes;
+      // residuals of the blocks TMA wrote (A valid blocks, then B)
+      split_lo(reinterpret_cast<const float*>(st), reinterpret_cast<float*>(st + a_bytes + b_bytes), p.nblkA * DW_BLK / 16, tid, 128);
+      split_lo(reinterpret_cast<const float*>(st + a_bytes), reinterpret_cast<float*>(st + 2 * a_bytes + b_bytes), (int)(b_bytes / 16), tid, 128);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+    }
+    // ---- read the partial dW out: warp w owns TMEM lanes [32*(w%4), +32)
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    const int q = warp & 3;
+    float* part = p.part + (int64_t)blockIdx.x * p.N * p.K;
+    for (int mt = 0; mt < p.mtiles; ++mt) {
+      const int n = mt * BM + q * 32 + lane;
+      for (int c0 = 0; c0 < p.K; c0 += 32) {
+        float v[32];
+        if (nst > 0) {
+          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.K + c0), v);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = 0.f;
+        }
+        if (n < p.N) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) st4(part + (int64_t)n * p.K + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, p.tmem_cols);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ host side
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -482,5 +626,70 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
   dim3 grid((unsigned)rbm_cdiv(M, BM), (unsigned)(N / BN));
   tc_linear_kernel<<<grid, 192, smem, st>>>(mapA, mapB, p);
   RBM_LAUNCH_CHECK("rbm_linear(tcgen05)");
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ weight gradient launch
+namespace {
+bool encode_map_mn(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)DW_TOK};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+int dw_stages(int N, int K, int* mtiles_out) {
+  int mtiles = (N + BM - 1) / BM;
+  size_t stage = (size_t)2 * ((size_t)mtiles * 4 + K / 32) * DW_BLK;
+  int ns = (int)(((size_t)231424 - 1024) / stage);
+  if (ns > 8) ns = 8;
+  *mtiles_out = mtiles;
+  return ns;
+}
+}  // namespace
+
+int rbm_tc_dw_splits(int64_t M) {
+  int64_t s = rbm_cdiv(M, 4 * DW_TOK);  // at least 4 stages of work per CTA
+  return (int)(s < 1 ? 1 : (s > RBM_NUM_SMS ? RBM_NUM_SMS : s));
+}
+
+bool rbm_tc_dw_supported(int64_t M, int N, int K, int64_t lda, int64_t ldb, const void* a, const void* b) {
+  if (tc_mode() != 0 || M < 1 || N % 32 != 0 || K % 32 != 0 || N > 256 || K > 256 || K < 32 || N < 32) return false;
+  if (lda % 4 != 0 || ldb % 4 != 0 || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return false;
+  int mt;
+  if (dw_stages(N, K, &mt) < 2 || mt * K > 512) return false;
+  return get_encode() != nullptr;
+}
+
+// part: [rbm_tc_dw_splits(M)][N][K] partial sums (every slot is written)
+int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb, float* part, int64_t M, int N, int K, cudaStream_t st) {
+  CUtensorMap mapA, mapB;
+  if (!encode_map_mn(&mapA, dpre, M, N, lda) || !encode_map_mn(&mapB, x, M, K, ldb)) {
+    rbm_set_error("rbm_linear_bwd_weight(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  DwParams p{};
+  p.part = part; p.M = M; p.N = N; p.K = K; p.nblkA = N / 32; p.nblkB = K / 32;
+  p.nstage = dw_stages(N, K, &p.mtiles);
+  const int S = rbm_tc_dw_splits(M);
+  p.tok_per_cta = rbm_cdiv(rbm_cdiv(M, S), DW_TOK) * DW_TOK;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(p.mtiles * K)) cols <<= 1;
+  p.tmem_cols = cols;
+  size_t smem = (size_t)p.nstage * 2 * ((size_t)p.mtiles * 4 + p.nblkB) * DW_BLK + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_linear_bwd_weight(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  tc_dw_kernel<<<S, 192, smem, st>>>(mapA, mapB, p);
+  RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(tcgen05)");
   return 0;
 }
