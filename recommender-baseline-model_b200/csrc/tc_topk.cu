@@ -1,0 +1,393 @@
+// tc_topk.cu -- full-catalogue scoring fused with candidate selection on the Blackwell tensor path, plus the exact
+// fp32 re-scoring of the survivors.  Replaces, at catalogue scale, SAS.predict's gather+matvec / BERT's last-position
+// logits followed by argsort(-scores)[:, :k] (NN/models/sas_model/sas.py:110-114, NN/trainers/bert.py:47-49,
+// NN/trainers/utils.py:36-38): the [U, V] score matrix never exists anywhere but in tensor memory.
+//
+//   stage 1 (tc_topk_kernel): persistent CTAs walk (128-user tile, item split) units.  The user tile is TMA-loaded once
+//     per unit and stays in shared memory; item-table tiles ([BN items x d], K-major, 128-byte swizzle) stream through
+//     a TMA ring; tcgen05.mma kind::tf32 (single pass: this stage only has to be right about WHO is near the top)
+//     writes [128 x BN] score tiles into double-buffered TMEM; 8 epilogue warps (one thread per user row, tcgen05.ld)
+//     compare every score with the thread's running KC-th best (one FMNMX per score) and insert the rare survivors into
+//     a register-resident sorted list of KC = 16 (approx score, item id) candidates per (item split, column half).
+//   stage 2 (topk_rescore_kernel): one warp per user recomputes the EXACT fp32 score of every candidate (sequential
+//     fp32 FMA over d) and selects the final top-k under the canonical order (score desc, id asc).
+// Stage 1's TF32 error (<= ~1e-3 relative) only matters if more than KC - k items crowd within that margin of the
+// k-th best score; the final scores and their order are exact fp32.
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "tc_ptx.cuh"
+#include "tc_topk.cuh"
+
+namespace {
+
+using namespace rbm_tc;
+
+constexpr int BM = 128;
+constexpr int BKE = 32;
+constexpr int KC = 16;       // candidates kept per (user, item split, column half)
+constexpr int EPI = 8;       // epilogue warps
+
+struct TopkParams {
+  const float* bias;
+  float* cand_s;     // [S*2][U][KC]
+  int64_t* cand_i;   // [S*2][U][KC]
+  int64_t U, v_begin, v_end, id_offset, tiles_per_split;
+  int d, BN, nstage, S, n_utiles;
+  uint32_t tmem_cols;
+};
+
+__global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                                                                   const TopkParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t a_full, a_empty, full_bar[4], empty_bar[4], tfull[2], tempty[2];
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.d / BKE, BN = p.BN, ns = p.nstage;
+  const uint32_t a_bytes = (uint32_t)KB * BM * BKE * 4, kb_bytes = (uint32_t)BN * BKE * 4, stage_bytes = kb_bytes * KB;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const int64_t n_items = p.v_end - p.v_begin;
+  const int64_t n_tiles = (n_items + BN - 1) / BN;
+  const int n_units = p.n_utiles * p.S;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&a_full), 1);
+    mbar_init(smem_u32(&a_empty), 1);
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(smem_u32(&tfull[b]), 1);
+      mbar_init(smem_u32(&tempty[b]), EPI);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_d = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
+      int g = 0, un = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++un) {
+        const int ut = u / p.S, sp = u % p.S;
+        if (un > 0) mbar_wait(smem_u32(&a_empty), (un - 1) & 1);  // the previous unit's MMAs no longer read the user tile
+        mbar_expect_tx(smem_u32(&a_full), a_bytes);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_base + kb * BM * BKE * 4, &mapA, smem_u32(&a_full), kb * BKE, ut * BM);
+        const int64_t tb = (int64_t)sp * p.tiles_per_split;
+        const int64_t te = tb + p.tiles_per_split < n_tiles ? tb + p.tiles_per_split : n_tiles;
+        for (int64_t t = tb; t < te; ++t, ++g) {
+          const int s = g % ns;
+          if (g >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((g / ns) - 1) & 1);
+          const uint32_t bar = smem_u32(&full_bar[s]);
+          mbar_expect_tx(bar, stage_bytes);
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(smem_base + a_bytes + s * stage_bytes + kb * kb_bytes, &mapB, bar, kb * BKE, (int)(p.v_begin + t * BN));
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idesc = make_idesc_tf32(BM, BN);
+      int g = 0, it = 0, un = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++un) {
+        const int sp = u % p.S;
+        mbar_wait(smem_u32(&a_full), un & 1);
+        const int64_t tb = (int64_t)sp * p.tiles_per_split;
+        const int64_t te = tb + p.tiles_per_split < n_tiles ? tb + p.tiles_per_split : n_tiles;
+        for (int64_t t = tb; t < te; ++t, ++g, ++it) {
+          const int s = g % ns, buf = it & 1;
+          if (it >= 2) {
+            mbar_wait(smem_u32(&tempty[buf]), ((it >> 1) - 1) & 1);
+            tc_fence_after();
+          }
+          mbar_wait(smem_u32(&full_bar[s]), (g / ns) & 1);
+          tc_fence_after();
+          const uint32_t d = tmem_d + (uint32_t)(buf * BN);
+          for (int kb = 0; kb < KB; ++kb) {
+            const uint64_t adesc = make_sw128_desc(smem_base + kb * BM * BKE * 4);
+            const uint64_t bdesc = make_sw128_desc(smem_base + a_bytes + s * stage_bytes + kb * kb_bytes);
+#pragma unroll
+            for (int k = 0; k < BKE / UMMA_K_TF32; ++k) umma_tf32(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
+          umma_commit(smem_u32(&empty_bar[s]));
+          umma_commit(smem_u32(&tfull[buf]));
+        }
+        umma_commit(smem_u32(&a_empty));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int hw = BN / 2;  // columns per half
+    int it = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int ut = u / p.S, sp = u % p.S;
+      const int64_t user = (int64_t)ut * BM + q * 32 + lane;
+      float ls[KC];
+      int li[KC];
+#pragma unroll
+      for (int t = 0; t < KC; ++t) {
+        ls[t] = -INFINITY;
+        li[t] = -1;
+      }
+      const int64_t tb = (int64_t)sp * p.tiles_per_split;
+      const int64_t te = tb + p.tiles_per_split < n_tiles ? tb + p.tiles_per_split : n_tiles;
+      for (int64_t t = tb; t < te; ++t, ++it) {
+        const int buf = it & 1;
+        mbar_wait(smem_u32(&tfull[buf]), (it >> 1) & 1);
+        tc_fence_after();
+        const int64_t item0 = p.v_begin + t * BN + half * hw;  // table row of this thread's first column
+        for (int c0 = 0; c0 < hw; c0 += 32) {
+          float v[32];
+          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * hw + c0), v);
+          if (c0 + 32 >= hw) {  // this warp's last read of the buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&tempty[buf]));
+          }
+          const int64_t r0 = item0 + c0;
+          if (p.bias) {
+#pragma unroll
+            for (int j = 0; j < 32; j += 4) {
+              if (r0 + j + 3 < p.v_end) {
+                float4 b4 = make_float4(p.bias[r0 + j], p.bias[r0 + j + 1], p.bias[r0 + j + 2], p.bias[r0 + j + 3]);
+                v[j] += b4.x; v[j + 1] += b4.y; v[j + 2] += b4.z; v[j + 3] += b4.w;
+              } else {
+                for (int e = 0; e < 4; ++e)
+                  if (r0 + j + e < p.v_end) v[j + e] += p.bias[r0 + j + e];
+              }
+            }
+          }
+          if (r0 + 32 > p.v_end) {  // ragged end of the item range: rows beyond it must never win
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (r0 + j >= p.v_end) v[j] = -INFINITY;
+          }
+          float mx = v[0];
+#pragma unroll
+          for (int j = 1; j < 32; ++j) mx = fmaxf(mx, v[j]);
+          if (mx > ls[KC - 1]) {  // rare: some score of this chunk beats the running 32nd best
+            float loc[32];        // dynamically indexed -> local memory, only touched on this path
+            unsigned m = 0;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              loc[j] = v[j];
+              m |= (v[j] > ls[KC - 1] ? 1u : 0u) << j;
+            }
+            for (; m; m &= m - 1) {
+              const int j = __ffs(m) - 1;
+              const float x = loc[j];
+              if (x > ls[KC - 1]) {
+                const int id = (int)(r0 + j);
+                bool placed = false;
+#pragma unroll
+                for (int tt = KC - 1; tt > 0; --tt) {
+                  if (!placed) {
+                    if (ls[tt - 1] < x) {
+                      ls[tt] = ls[tt - 1];
+                      li[tt] = li[tt - 1];
+                    } else {
+                      ls[tt] = x;
+                      li[tt] = id;
+                      placed = true;
+                    }
+                  }
+                }
+                if (!placed) {
+                  ls[0] = x;
+                  li[0] = id;
+                }
+              }
+            }
+          }
+        }
+      }
+      if (user < p.U) {
+        const int64_t base = ((int64_t)(sp * 2 + half) * p.U + user) * KC;
+#pragma unroll
+        for (int t = 0; t < KC; ++t) {
+          p.cand_s[base + t] = ls[t];
+          p.cand_i[base + t] = li[t] < 0 ? -1 : (int64_t)li[t];
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_d, p.tmem_cols);
+  }
+}
+
+// ----------------------------------------------------------------------------- exact re-score + final top-k
+__device__ __forceinline__ bool better(float s, int64_t id, float ts, int64_t tid) { return s > ts || (s == ts && id < tid); }
+
+__global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restrict__ f, int64_t ldf, const float* __restrict__ table,
+                                                           const float* __restrict__ bias, const int64_t* __restrict__ cand_i, int n_lists,
+                                                           int64_t id_offset, float* __restrict__ out_s, int64_t* __restrict__ out_i, int64_t U,
+                                                           int d, int k) {
+  extern __shared__ float fs[];  // [8 warps][d]
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int64_t u = (int64_t)blockIdx.x * 8 + wib;
+  if (u >= U) return;
+  float* fu = fs + wib * d;
+  for (int c = lane; c < d; c += 32) fu[c] = f[u * ldf + c];
+  __syncwarp();
+  float ms = -INFINITY;       // lane t holds the t-th best (t < k)
+  int64_t mi = INT64_MAX;
+  const int NC = n_lists * KC;
+  for (int c0 = 0; c0 < NC; c0 += 32) {
+    const int c = c0 + lane;
+    int64_t row = -1;
+    if (c < NC) row = cand_i[((int64_t)(c / KC) * U + u) * KC + (c % KC)];
+    float s = 0.f;
+    if (row >= 0) {
+      const float* tr = table + row * d;
+      for (int kk = 0; kk < d; kk += 4) {
+        float4 t4 = ld4(tr + kk);
+        s = fmaf(fu[kk], t4.x, s); s = fmaf(fu[kk + 1], t4.y, s); s = fmaf(fu[kk + 2], t4.z, s); s = fmaf(fu[kk + 3], t4.w, s);
+      }
+      if (bias) s += bias[row];
+    }
+    const int64_t id = row + id_offset;
+    // offer every valid candidate to the warp-distributed sorted list
+    const float ts = __shfl_sync(0xffffffffu, ms, k - 1);
+    const int64_t tid = __shfl_sync(0xffffffffu, mi, k - 1);
+    unsigned m = __ballot_sync(0xffffffffu, row >= 0 && better(s, id, ts, tid));
+    while (m) {
+      const int src = __ffs(m) - 1;
+      m &= m - 1;
+      const float cs = __shfl_sync(0xffffffffu, s, src);
+      const int64_t cid = __shfl_sync(0xffffffffu, id, src);
+      const bool beats_me = better(cs, cid, ms, mi);
+      const int pos = __popc(__ballot_sync(0xffffffffu, lane < k && !beats_me));
+      const float up_s = __shfl_up_sync(0xffffffffu, ms, 1);
+      const int64_t up_i = __shfl_up_sync(0xffffffffu, mi, 1);
+      if (lane < k) {
+        if (lane == pos) {
+          ms = cs;
+          mi = cid;
+        } else if (lane > pos) {
+          ms = up_s;
+          mi = up_i;
+        }
+      }
+    }
+  }
+  if (lane < k) {
+    out_s[u * k + lane] = mi == INT64_MAX ? -INFINITY : ms;
+    out_i[u * k + lane] = mi == INT64_MAX ? -1 : mi;
+  }
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
+  cuuint32_t box[2] = {(cuuint32_t)BKE, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RBM_TOPK_IMPL");
+    v = (e && strcmp(e, "simt") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+int pick_bn(int d) { return d <= 64 ? 256 : (d <= 128 ? 128 : 64); }
+
+}  // namespace
+
+int rbm_tc_topk_splits(int64_t U, int64_t n_items, int d) {
+  int64_t ut = rbm_cdiv(U, BM), tiles = rbm_cdiv(n_items, pick_bn(d));
+  int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS * 3, ut);
+  if (s > tiles / 8) s = tiles / 8;  // at least 8 item tiles per unit
+  if (s > 32) s = 32;
+  return (int)(s < 1 ? 1 : s);
+}
+
+size_t rbm_tc_topk_ws_bytes(int64_t U, int64_t n_items, int d) {
+  size_t S = (size_t)rbm_tc_topk_splits(U, n_items, d);
+  return S * 2 * (size_t)U * KC * (sizeof(float) + sizeof(int64_t)) + 256;
+}
+
+bool rbm_tc_topk_supported(int64_t U, int64_t n_items, int d, int k, int64_t ldf, const void* f, const void* table) {
+  if (!tc_enabled() || d % BKE != 0 || d < BKE || d > 256 || k > 16 || U < 1) return false;
+  if (n_items < 8192) return false;  // small catalogues: the fp32 tile kernel is already latency-bound
+  if (ldf % 4 != 0 || ((uintptr_t)f & 15) || ((uintptr_t)table & 15)) return false;
+  return get_encode() != nullptr;
+}
+
+int rbm_tc_topk_launch(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin, int64_t v_end,
+                       int64_t id_offset, float* top_scores, int64_t* top_ids, int64_t U, int d, int k, void* ws, cudaStream_t st) {
+  const int BN = pick_bn(d);
+  const int64_t n_items = v_end - v_begin;
+  CUtensorMap mapA, mapB;
+  if (!encode_map(&mapA, f, U, d, ldf, BM) || !encode_map(&mapB, table, v_end, d, d, BN)) {
+    rbm_set_error("rbm_score_topk(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  TopkParams p{};
+  p.bias = bias; p.U = U; p.v_begin = v_begin; p.v_end = v_end; p.id_offset = id_offset; p.d = d; p.BN = BN;
+  p.S = rbm_tc_topk_splits(U, n_items, d);
+  p.n_utiles = (int)rbm_cdiv(U, BM);
+  p.tiles_per_split = rbm_cdiv(rbm_cdiv(n_items, BN), p.S);
+  p.cand_i = (int64_t*)ws;
+  p.cand_s = (float*)(p.cand_i + (size_t)p.S * 2 * U * KC);
+  const size_t a_bytes = (size_t)BM * d * 4, stage = (size_t)BN * d * 4;
+  int ns = (int)(((size_t)231424 - 1024 - a_bytes) / stage);
+  if (ns > 4) ns = 4;
+  if (ns < 2) {
+    rbm_set_error("rbm_score_topk(tcgen05): d=%d leaves no room for a 2-stage ring", d);
+    return -1;
+  }
+  p.nstage = ns;
+  uint32_t cols = 32;
+  while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+  p.tmem_cols = cols;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(tc_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_score_topk(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  size_t smem = a_bytes + (size_t)ns * stage + 1024;
+  int units = p.n_utiles * p.S;
+  int grid = units < RBM_NUM_SMS ? units : RBM_NUM_SMS;
+  tc_topk_kernel<<<grid, 64 + 32 * EPI, smem, st>>>(mapA, mapB, p);
+  RBM_LAUNCH_CHECK("rbm_score_topk(tcgen05)");
+  topk_rescore_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 8 * d * sizeof(float), st>>>(f, ldf, table, bias, p.cand_i, p.S * 2, id_offset,
+                                                                                   top_scores, top_ids, U, d, k);
+  RBM_LAUNCH_CHECK("rbm_score_topk(rescore)");
+  return 0;
+}

@@ -6,6 +6,7 @@
 // the rare survivors are inserted into a per-user sorted list that lives in the registers of one warp.
 // Order rule everywhere: score descending, item id ascending  (canonical form of the reference's argsort).
 #include "common.cuh"
+#include "tc_topk.cuh"
 
 namespace {
 
@@ -262,7 +263,13 @@ int topk_splits(int64_t U, int64_t n_items) {
 
 extern "C" size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k) {
   size_t S = (size_t)topk_splits(U, n_items);
-  return S * (size_t)U * k * (sizeof(float) + sizeof(int64_t)) + 256;
+  size_t simt = S * (size_t)U * k * (sizeof(float) + sizeof(int64_t)) + 256;
+  size_t tc = 0;
+  for (int d = 32; d <= 256; d *= 2) {  // d is not part of this query: cover every hidden size the tcgen05 path takes
+    size_t b = rbm_tc_topk_ws_bytes(U, n_items, d);
+    if (b > tc) tc = b;
+  }
+  return simt > tc ? simt : tc;
 }
 
 extern "C" int rbm_score_topk(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin, int64_t v_end,
@@ -276,6 +283,9 @@ extern "C" int rbm_score_topk(const float* f, int64_t ldf, const float* table, c
   RBM_REQUIRE(rbm_aligned16(f) && rbm_aligned16(table) && rbm_aligned16(ws), "rbm_score_topk: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n_items = v_end - v_begin;
+  // catalogue-scale path: tcgen05 candidate selection + exact fp32 re-score (tc_topk.cu)
+  if (rbm_tc_topk_supported(U, n_items, d, k, ldf, f, table))
+    return rbm_tc_topk_launch(f, ldf, table, bias, v_begin, v_end, id_offset, top_scores, top_ids, U, d, k, ws, st);
   int S = topk_splits(U, n_items);
   int64_t tps = rbm_cdiv(rbm_cdiv(n_items, T), S);
   size_t smem = sizeof(float) * ((size_t)d * LDT + KC * LDT + T * LDT);
