@@ -481,7 +481,12 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   cudaStream_t st = (cudaStream_t)stream;
   int warps = pick_warps(L), rc;
-  ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq, "rbm_attn_bwd(dq)");
+  if (rbm_attn_bwd_dq_tc_supported(L, dk, ldq, ldk, ldv, ldo, lddo, lddq, q, k, v, out, dout, dq)) {
+    rc = rbm_attn_bwd_dq_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, dout, lddo, stats, dq, lddq, (float*)ws, B, L, h, mask_mode,
+                                   scale, p, seed, site, st);
+  } else {
+    ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq, "rbm_attn_bwd(dq)");
+  }
   if (rc) return rc;
   ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
   return rc;

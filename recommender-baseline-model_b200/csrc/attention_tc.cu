@@ -268,6 +268,236 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __g
   }
 }
 
+// =====================================================================================================
+// Backward pass A (dQ and delta) on the tensor path, one CTA per (sequence, head, 128-query tile).
+//   TMEM columns: S_h [0,112) | dP_h [112,224) | Q raw,lo [224,288) | dO raw,lo [288,352) | dQ [352,384)
+//   SMEM: K (K-major), K (MN-major, 32-byte-atom swizzle), V (K-major), each with its TF32 residual copy.
+//   Keys are processed in two halves (112 + rest) so S and dP fit; dS and its residual overwrite them in place and
+//   feed  dQ += dS.K  as the TMEM A operand.  delta_i = <dO_i, O_i> is also written for pass B.
+// =====================================================================================================
+constexpr int HALF = 112;
+constexpr uint32_t T_S = 0, T_DP = 112, T_Q = 224, T_QL = 256, T_DO = 288, T_DOL = 320, T_DQ = 352;
+
+struct TcBwdArgs {
+  const float *q, *o, *dout, *stats;
+  float *dq, *delta;
+  int64_t ldq, ldo, lddo, lddq;
+  const int64_t* tok;
+  int L, LPK, h, NT, mask_mode;
+  float scale, scale_log2;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+};
+
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapKk,
+                                                                          const __grid_constant__ CUtensorMap mapKm,
+                                                                          const __grid_constant__ CUtensorMap mapVk, const TcBwdArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t load_bar, split_bar, s_full[2], ds_full[2], dq_full;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float padk[256];
+  __shared__ float xdelta[128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x / a.NT, mt = blockIdx.x % a.NT;
+  const int b = bh / a.h, hh = bh % a.h;
+  const int L = a.L, LPK = a.LPK;
+  const int NH = LPK > HALF ? 2 : 1;
+  const uint32_t kv_bytes = (uint32_t)LPK * ROWB;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t oKk = 0, oKkl = kv_bytes, oKm = 2 * kv_bytes, oKml = 3 * kv_bytes, oVk = 4 * kv_bytes, oVkl = 5 * kv_bytes;
+
+  if (threadIdx.x == 0) {
+    mbar_init(smem_u32(&load_bar), 1);
+    mbar_init(smem_u32(&split_bar), NSW);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&ds_full[i]), NSW);
+    }
+    mbar_init(smem_u32(&dq_full), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      const uint32_t bar = smem_u32(&load_bar);
+      mbar_expect_tx(bar, 3 * kv_bytes);
+      tma_load_3d(smem_base + oKk, &mapKk, bar, hh * DK, 0, b);
+      tma_load_3d(smem_base + oKm, &mapKm, bar, hh * DK, 0, b);
+      tma_load_3d(smem_base + oVk, &mapVk, bar, hh * DK, 0, b);
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&load_bar), 0);
+      mbar_wait(smem_u32(&split_bar), 0);
+      tc_fence_after();
+      const uint32_t idQ = make_idesc_tf32_ex(128, DK, 0, 1);  // dQ: A from TMEM, K MN-major
+      for (int hf = 0; hf < NH; ++hf) {
+        const int k0 = hf * HALF, nh = (hf == 0 ? (LPK < HALF ? LPK : HALF) : LPK - HALF);
+        const uint32_t idS = make_idesc_tf32_ex(128, nh, 0, 0);
+        const uint64_t dK = make_sw128_desc(smem_base + oKk + k0 * ROWB), dKl = make_sw128_desc(smem_base + oKkl + k0 * ROWB);
+        const uint64_t dV = make_sw128_desc(smem_base + oVk + k0 * ROWB), dVl = make_sw128_desc(smem_base + oVkl + k0 * ROWB);
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32_ts(tmem + T_S, tmem + T_Q + k * 8, dKl + o, idS, k != 0);
+          umma_tf32_ts(tmem + T_S, tmem + T_QL + k * 8, dK + o, idS, 1);
+          umma_tf32_ts(tmem + T_S, tmem + T_Q + k * 8, dK + o, idS, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32_ts(tmem + T_DP, tmem + T_DO + k * 8, dVl + o, idS, k != 0);
+          umma_tf32_ts(tmem + T_DP, tmem + T_DOL + k * 8, dV + o, idS, 1);
+          umma_tf32_ts(tmem + T_DP, tmem + T_DO + k * 8, dV + o, idS, 1);
+        }
+        umma_commit(smem_u32(&s_full[hf]));
+        mbar_wait(smem_u32(&ds_full[hf]), 0);
+        tc_fence_after();
+        for (int kk = 0; kk < nh / 8; ++kk) {
+          const uint64_t dKm = make_sw128_desc_mn(smem_base + oKm + (k0 + kk * 8) * ROWB, 0);
+          const uint64_t dKml = make_sw128_desc_mn(smem_base + oKml + (k0 + kk * 8) * ROWB, 0);
+          umma_tf32_ts(tmem + T_DQ, tmem + T_S + kk * 8, dKml, idQ, (hf | kk) != 0);
+          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + kk * 8, dKm, idQ, 1);
+          umma_tf32_ts(tmem + T_DQ, tmem + T_S + kk * 8, dKm, idQ, 1);
+        }
+      }
+      umma_commit(smem_u32(&dq_full));
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int tid = sw * 32 + lane;
+    const int64_t row0 = (int64_t)b * L;
+    const int rl = q * 32 + lane;
+    const int i = mt * 128 + rl;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    for (int j = tid; j < 256; j += NSW * 32) padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
+    // ---- operand rows into TMEM: warps of half 0 take Q (pre-scaled to the log2 domain), half 1 take dO and delta
+    {
+      float v[32], lo[32];
+      const float* src = half == 0 ? a.q + (row0 + i) * a.ldq + hh * DK : a.dout + (row0 + i) * a.lddo + hh * DK;
+      const float mul = half == 0 ? a.scale_log2 : 1.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 x = i < L ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
+      }
+      if (half == 1) {
+        float dl = 0.f;
+        if (i < L) {
+          const float* orow = a.o + (row0 + i) * a.ldo + hh * DK;
+#pragma unroll
+          for (int c = 0; c < 32; c += 4) {
+            float4 x = ld4(orow + c);
+            dl = fmaf(v[c], x.x, dl); dl = fmaf(v[c + 1], x.y, dl); dl = fmaf(v[c + 2], x.z, dl); dl = fmaf(v[c + 3], x.w, dl);
+          }
+          a.delta[(int64_t)bh * L + i] = dl;
+        }
+        xdelta[rl] = dl;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) lo[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xffffe000u);
+      const uint32_t tr = half == 0 ? T_Q : T_DO, tl = half == 0 ? T_QL : T_DOL;
+      float t16[16];
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t16[c] = v[part * 16 + c];
+        tmem_st16(tmem + lane_sel + tr + part * 16, t16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t16[c] = lo[part * 16 + c];
+        tmem_st16(tmem + lane_sel + tl + part * 16, t16);
+      }
+      tmem_st_wait();
+    }
+    // ---- TF32 residual copies of the three K/V tiles
+    mbar_wait(smem_u32(&load_bar), 0);
+    split_lo_bytes(gen + oKk, gen + oKkl, (int)(kv_bytes / 16), tid, NSW * 32);
+    split_lo_bytes(gen + oKm, gen + oKml, (int)(kv_bytes / 16), tid, NSW * 32);
+    split_lo_bytes(gen + oVk, gen + oVkl, (int)(kv_bytes / 16), tid, NSW * 32);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&split_bar));
+    named_bar_sync(1, NSW * 32);  // padk, xdelta visible
+
+    float mx = 0.f, inv = 0.f;
+    if (i < L) {
+      const int64_t sr = ((int64_t)bh * L + i) * 2;
+      mx = a.stats[sr];
+      inv = a.stats[sr + 1];
+    }
+    const float delta = xdelta[rl];
+    const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
+    for (int hf = 0; hf < NH; ++hf) {
+      const int k0 = hf * HALF, nh = (hf == 0 ? (LPK < HALF ? LPK : HALF) : LPK - HALF);
+      const int cbeg = half == 0 ? 0 : 64, cend = half == 0 ? (nh < 64 ? nh : 64) : nh;
+      mbar_wait(smem_u32(&s_full[hf]), 0);
+      tc_fence_after();
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float sv[16], dp[16], lo[16];
+        tmem_ld16(tmem + lane_sel + T_S + (uint32_t)c0, sv);
+        tmem_ld16(tmem + lane_sel + T_DP + (uint32_t)c0, dp);
+        const int j0 = k0 + c0;
+        uint4 calls[4];
+        if (a.thr16) {
+          uint4 c0r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, tile, g, rh * 2 + 0, j0 >> 4));
+          uint4 c1r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, tile, g, rh * 2 + 1, j0 >> 4));
+          uint4 o0, o1;
+          o0.x = __shfl_xor_sync(0xffffffffu, c0r.x, 8); o0.y = __shfl_xor_sync(0xffffffffu, c0r.y, 8);
+          o0.z = __shfl_xor_sync(0xffffffffu, c0r.z, 8); o0.w = __shfl_xor_sync(0xffffffffu, c0r.w, 8);
+          o1.x = __shfl_xor_sync(0xffffffffu, c1r.x, 8); o1.y = __shfl_xor_sync(0xffffffffu, c1r.y, 8);
+          o1.z = __shfl_xor_sync(0xffffffffu, c1r.z, 8); o1.w = __shfl_xor_sync(0xffffffffu, c1r.w, 8);
+          calls[0] = rh ? o0 : c0r; calls[1] = rh ? o1 : c1r; calls[2] = rh ? c0r : o0; calls[3] = rh ? c1r : o1;
+        }
+#pragma unroll
+        for (int jj = 0; jj < 16; ++jj) {
+          const int j = j0 + jj;
+          const bool pad = padk[j] != 0.f;
+          const float x = pad ? RBM_PADFILL : sv[jj];
+          const bool dead = i >= L || j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i);
+          const float p = dead ? 0.f : ex2(x - mx) * inv;
+          float mk = 1.f;
+          if (a.thr16) mk = rbm_attn_field(calls[(jj & 7) >> 1], rh * 4 + (jj & 1) * 2 + ((jj >> 3) & 1)) >= a.thr16 ? a.inv_keep : 0.f;
+          const float ds = pad ? 0.f : p * (mk * dp[jj] - delta);  // no score gradient through a padded key
+          sv[jj] = ds;
+          lo[jj] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
+        }
+        tmem_st16(tmem + lane_sel + T_S + (uint32_t)c0, sv);
+        tmem_st16(tmem + lane_sel + T_DP + (uint32_t)c0, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_full[hf]));
+    }
+    mbar_wait(smem_u32(&dq_full), 0);
+    tc_fence_after();
+    float o[16];
+    tmem_ld16(tmem + lane_sel + T_DQ + (uint32_t)(half * 16), o);
+    if (i < L) {
+      float* dst = a.dq + (row0 + i) * a.lddq + hh * DK + half * 16;
+#pragma unroll
+      for (int jj = 0; jj < 16; jj += 4)
+        st4(dst + jj, make_float4(o[jj] * a.scale, o[jj + 1] * a.scale, o[jj + 2] * a.scale, o[jj + 3] * a.scale));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -347,5 +577,43 @@ int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t 
   }
   attn_fwd_tc_kernel<<<B * h, 64 + 32 * NSW, smem, st>>>(mapQ, mapK, mapV, a);
   RBM_LAUNCH_CHECK("rbm_attn_fwd(tcgen05)");
+  return 0;
+}
+
+bool rbm_attn_bwd_dq_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
+                                  const void* q, const void* k, const void* v, const void* o, const void* dout, const void* dq) {
+  if (!tc_enabled() || dk != DK || L < 1 || L > 224) return false;  // TMEM: two key halves of <= 112 columns
+  if (ldq % 4 || ldk % 4 || ldv % 4 || ldo % 4 || lddo % 4 || lddq % 4) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq) & 15) return false;
+  return get_encode() != nullptr;
+}
+
+int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
+                              const float* o, int64_t ldo, const float* dout, int64_t lddo, const float* stats, float* dq, int64_t lddq,
+                              float* delta, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed, uint64_t site,
+                              cudaStream_t st) {
+  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+  CUtensorMap mapKk, mapKm, mapVk;
+  if (!encode_map3(&mapKk, k, B, L, h * DK, ldk, LPK, false) || !encode_map3(&mapKm, k, B, L, h * DK, ldk, LPK, true) ||
+      !encode_map3(&mapVk, v, B, L, h * DK, ldv, LPK, false)) {
+    rbm_set_error("rbm_attn_bwd(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  TcBwdArgs a{};
+  a.q = q; a.o = o; a.dout = dout; a.stats = stats; a.dq = dq; a.delta = delta; a.ldq = ldq; a.ldo = ldo; a.lddo = lddo; a.lddq = lddq;
+  a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
+  a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
+  size_t smem = (size_t)6 * LPK * ROWB + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_attn_bwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  attn_bwd_dq_tc_kernel<<<B * h * NT, 64 + 32 * NSW, smem, st>>>(mapKk, mapKm, mapVk, a);
+  RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dq)");
   return 0;
 }
