@@ -488,6 +488,9 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
     ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq, "rbm_attn_bwd(dq)");
   }
   if (rc) return rc;
+  if (rbm_attn_bwd_dkv_tc_supported(L, dk, ldq, ldk, ldv, lddo, lddk, lddv, q, k, v, dout, dk_, dv))
+    return rbm_attn_bwd_dkv_tc_launch(q, ldq, k, ldk, v, ldv, tok, dout, lddo, stats, (const float*)ws, dk_, lddk, dv, lddv, B, L, h,
+                                      mask_mode, scale, p, seed, site, st);
   ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
   return rc;
 }

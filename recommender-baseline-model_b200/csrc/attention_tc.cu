@@ -498,6 +498,279 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
   }
 }
 
+// =====================================================================================================
+// Backward pass B (dK, dV) on the tensor path, one CTA per (sequence, head, 128-key tile); rows = keys.
+//   TMEM columns: K raw,lo [0,64) | V raw,lo [64,128) | S^T_c [128,192) | dP^T_c [192,256) | P~^T raw,lo [256,384)
+//                 | dK [384,416) | dV [416,448)
+//   Queries stream in chunks of 64 through a 2-stage TMA ring; every chunk arrives twice, as K-major tiles (B operand
+//   of S^T = K.Q^T and dP^T = V.dO^T) and as MN-major tiles (B operand of dK += dS^T.Q and dV += P~^T.dO), and gets
+//   TF32 residual copies from the softmax warps.  dS^T and its residual overwrite S^T / dP^T in place.
+// =====================================================================================================
+constexpr int QC = 64;                     // queries per chunk
+constexpr uint32_t CH_TILE = QC * ROWB;    // 8 KB: one [64 x 32] fp32 tile
+constexpr uint32_t CH_STAGE = 8 * CH_TILE; // Qk, Qm, dOk, dOm (raw) + the same four (lo)
+constexpr uint32_t B_K = 0, B_KL = 32, B_V = 64, B_VL = 96, B_ST = 128, B_DPT = 192, B_P = 256, B_PL = 320, B_DK = 384, B_DV = 416;
+
+struct TcBwdKvArgs {
+  const float *k, *v, *stats, *delta;
+  float *dk, *dv;
+  int64_t ldk, ldv, lddk, lddv;
+  const int64_t* tok;
+  int L, LPK, h, NT, mask_mode;
+  float scale, scale_log2;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+};
+
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQk,
+                                                                           const __grid_constant__ CUtensorMap mapQm,
+                                                                           const __grid_constant__ CUtensorMap mapOk,
+                                                                           const __grid_constant__ CUtensorMap mapOm, const TcBwdKvArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[2], split_bar[2], empty_bar[2], s_full[2], ds_full[2], kv_bar, done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float st_m[256], st_i[256], st_d[256];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int bh = blockIdx.x / a.NT, kt = blockIdx.x % a.NT;
+  const int b = bh / a.h, hh = bh % a.h;
+  const int L = a.L, LPK = a.LPK;
+  const int NC = (LPK + QC - 1) / QC;
+  // causal: queries before this key tile never attend to it
+  const int c_first = a.mask_mode == RBM_MASK_CAUSAL ? (kt * 128) / QC : 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&split_bar[i]), NSW);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&ds_full[i]), NSW);
+    }
+    mbar_init(smem_u32(&kv_bar), NSW);
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int c = c_first; c < NC; ++c, ++n) {
+        const int s = n & 1;
+        if (n >= 2) mbar_wait(smem_u32(&empty_bar[s]), ((n >> 1) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]);
+        const uint32_t sa = smem_base + s * CH_STAGE;
+        mbar_expect_tx(bar, 4 * CH_TILE);
+        tma_load_3d(sa + 0 * CH_TILE, &mapQk, bar, hh * DK, c * QC, b);
+        tma_load_3d(sa + 1 * CH_TILE, &mapQm, bar, hh * DK, c * QC, b);
+        tma_load_3d(sa + 2 * CH_TILE, &mapOk, bar, hh * DK, c * QC, b);
+        tma_load_3d(sa + 3 * CH_TILE, &mapOm, bar, hh * DK, c * QC, b);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      mbar_wait(smem_u32(&kv_bar), 0);
+      tc_fence_after();
+      const uint32_t idA = make_idesc_tf32_ex(128, DK, 0, 1);  // dK / dV: A from TMEM, B MN-major, N = 32
+      int n = 0;
+      for (int c = c_first; c < NC; ++c, ++n) {
+        const int s = n & 1, par = (n >> 1) & 1;
+        const int nq = LPK - c * QC < QC ? LPK - c * QC : QC;  // valid (16-multiple) query columns of this chunk
+        const uint32_t idS = make_idesc_tf32_ex(128, nq, 0, 0);
+        mbar_wait(smem_u32(&full_bar[s]), par);
+        mbar_wait(smem_u32(&split_bar[s]), par);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * CH_STAGE, sl = sa + 4 * CH_TILE;
+        const uint64_t dQk = make_sw128_desc(sa + 0 * CH_TILE), dQkl = make_sw128_desc(sl + 0 * CH_TILE);
+        const uint64_t dOk = make_sw128_desc(sa + 2 * CH_TILE), dOkl = make_sw128_desc(sl + 2 * CH_TILE);
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32_ts(tmem + B_ST, tmem + B_K + k * 8, dQkl + o, idS, k != 0);
+          umma_tf32_ts(tmem + B_ST, tmem + B_KL + k * 8, dQk + o, idS, 1);
+          umma_tf32_ts(tmem + B_ST, tmem + B_K + k * 8, dQk + o, idS, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32_ts(tmem + B_DPT, tmem + B_V + k * 8, dOkl + o, idS, k != 0);
+          umma_tf32_ts(tmem + B_DPT, tmem + B_VL + k * 8, dOk + o, idS, 1);
+          umma_tf32_ts(tmem + B_DPT, tmem + B_V + k * 8, dOk + o, idS, 1);
+        }
+        umma_commit(smem_u32(&s_full[s]));
+        mbar_wait(smem_u32(&ds_full[s]), par);
+        tc_fence_after();
+        for (int kk = 0; kk < nq / 8; ++kk) {
+          const uint64_t dQm = make_sw128_desc_mn(sa + 1 * CH_TILE + kk * 1024, 0), dQml = make_sw128_desc_mn(sl + 1 * CH_TILE + kk * 1024, 0);
+          const uint64_t dOm = make_sw128_desc_mn(sa + 3 * CH_TILE + kk * 1024, 0), dOml = make_sw128_desc_mn(sl + 3 * CH_TILE + kk * 1024, 0);
+          const uint32_t acc = (n | kk) != 0;
+          umma_tf32_ts(tmem + B_DK, tmem + B_ST + kk * 8, dQml, idA, acc);
+          umma_tf32_ts(tmem + B_DK, tmem + B_DPT + kk * 8, dQm, idA, 1);
+          umma_tf32_ts(tmem + B_DK, tmem + B_ST + kk * 8, dQm, idA, 1);
+          umma_tf32_ts(tmem + B_DV, tmem + B_P + kk * 8, dOml, idA, acc);
+          umma_tf32_ts(tmem + B_DV, tmem + B_PL + kk * 8, dOm, idA, 1);
+          umma_tf32_ts(tmem + B_DV, tmem + B_P + kk * 8, dOm, idA, 1);
+        }
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int tid = sw * 32 + lane;
+    const int64_t row0 = (int64_t)b * L;
+    const int rl = q * 32 + lane;
+    const int j = kt * 128 + rl;  // this thread's key
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    for (int i = tid; i < 256; i += NSW * 32) {
+      const bool in = i < L;
+      st_m[i] = in ? a.stats[((int64_t)bh * L + i) * 2] : 0.f;
+      st_i[i] = in ? a.stats[((int64_t)bh * L + i) * 2 + 1] : 0.f;
+      st_d[i] = in ? a.delta[(int64_t)bh * L + i] : 0.f;
+    }
+    const bool jpad = a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0;
+    // ---- operand rows into TMEM: half 0 -> K (pre-scaled to the log2 domain), half 1 -> V
+    {
+      float v[32], lo[32];
+      const float* src = half == 0 ? a.k + (row0 + j) * a.ldk + hh * DK : a.v + (row0 + j) * a.ldv + hh * DK;
+      const float mul = half == 0 ? a.scale_log2 : 1.f;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        float4 x = j < L ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
+      }
+#pragma unroll
+      for (int c = 0; c < 32; ++c) lo[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xffffe000u);
+      const uint32_t tr = half == 0 ? B_K : B_V, tl = half == 0 ? B_KL : B_VL;
+      float t16[16];
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t16[c] = v[part * 16 + c];
+        tmem_st16(tmem + lane_sel + tr + part * 16, t16);
+#pragma unroll
+        for (int c = 0; c < 16; ++c) t16[c] = lo[part * 16 + c];
+        tmem_st16(tmem + lane_sel + tl + part * 16, t16);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&kv_bar));
+    }
+    named_bar_sync(1, NSW * 32);  // stats arrays visible
+
+    auto split_stage = [&](int n) {
+      const int s = n & 1;
+      mbar_wait(smem_u32(&full_bar[s]), (n >> 1) & 1);
+      uint8_t* st = gen + (size_t)s * CH_STAGE;
+      split_lo_bytes(st, st + 4 * CH_TILE, (int)(4 * CH_TILE / 16), tid, NSW * 32);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+    };
+    // dropout: lanes {l, l^1, l^8, l^9} hold keys that share their Philox calls; each computes two of the eight
+    const int wq = (lane & 1) | (((lane >> 3) & 1) << 1);
+    const int e_j = j & 1, nb_j = (j >> 3) & 1, t_j = (j & 7) >> 1, np_j = j >> 4;
+
+    const int n_chunks = NC - c_first;
+    if (n_chunks > 0) split_stage(0);
+    int n = 0;
+    for (int c = c_first; c < NC; ++c, ++n) {
+      const int s = n & 1, par = (n >> 1) & 1;
+      const int nq = LPK - c * QC < QC ? LPK - c * QC : QC;
+      if (n + 1 < n_chunks) split_stage(n + 1);  // overlaps the tensor core's S^T / dP^T of this chunk
+      mbar_wait(smem_u32(&s_full[s]), par);
+      tc_fence_after();
+      const int cbeg = half == 0 ? 0 : 32, cend = half == 0 ? (nq < 32 ? nq : 32) : nq;
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        float sv[16], dp[16], t16[16];
+        tmem_ld16(tmem + lane_sel + B_ST + (uint32_t)c0, sv);
+        tmem_ld16(tmem + lane_sel + B_DPT + (uint32_t)c0, dp);
+        const int i0 = c * QC + c0;  // 16 consecutive queries, one Philox "tile"
+        uint32_t w0[8], w1[8];       // per query-in-octet g: the two words (rh = 0, 1) that hold this key's fields
+        if (a.thr16) {
+          uint4 ca = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
+          uint4 cb = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
+#pragma unroll
+          for (int gq = 0; gq < 8; ++gq) {
+            // call of query-octet position gq is owned by the lane whose (bit0, bit3) = ((gq>>1)&1, (gq>>2)&1); the
+            // requester picks the words of ITS key parity e: word index = rh*2 + e
+            const int src = (lane & ~9) | ((gq >> 1) & 1) | (((gq >> 2) & 1) << 3);
+            const uint4 cc = (gq & 1) ? cb : ca;
+            const uint32_t rx = __shfl_sync(0xffffffffu, cc.x, src), ry = __shfl_sync(0xffffffffu, cc.y, src);
+            const uint32_t rz = __shfl_sync(0xffffffffu, cc.z, src), rw = __shfl_sync(0xffffffffu, cc.w, src);
+            w0[gq] = e_j ? ry : rx;
+            w1[gq] = e_j ? rw : rz;
+          }
+        }
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) {
+          const int i = i0 + ii;
+          const float x = jpad ? RBM_PADFILL : sv[ii];
+          const bool dead = i >= L || j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i);
+          const float p = dead ? 0.f : ex2(x - st_m[i]) * st_i[i];
+          float mk = 1.f;
+          if (a.thr16) {
+            const uint32_t word = (ii & 8) ? w1[ii & 7] : w0[ii & 7];  // rh = (i >> 3) & 1
+            const uint32_t fld = nb_j ? (word >> 16) : (word & 0xffffu);
+            mk = fld >= a.thr16 ? a.inv_keep : 0.f;
+          }
+          const float ds = jpad ? 0.f : p * (mk * dp[ii] - st_d[i]);
+          sv[ii] = ds;
+          dp[ii] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
+          t16[ii] = p * mk;
+        }
+        tmem_st16(tmem + lane_sel + B_ST + (uint32_t)c0, sv);
+        tmem_st16(tmem + lane_sel + B_DPT + (uint32_t)c0, dp);
+        tmem_st16(tmem + lane_sel + B_P + (uint32_t)c0, t16);
+#pragma unroll
+        for (int ii = 0; ii < 16; ++ii) t16[ii] = t16[ii] - __uint_as_float(__float_as_uint(t16[ii]) & 0xffffe000u);
+        tmem_st16(tmem + lane_sel + B_PL + (uint32_t)c0, t16);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ds_full[s]));
+    }
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    float o[16];
+    if (n_chunks > 0) {
+      // half 0 -> dK (32 columns in two loads), half 1 -> dV
+      const uint32_t tcol = half == 0 ? B_DK : B_DV;
+      float* base = half == 0 ? a.dk + (row0 + j) * a.lddk + hh * DK : a.dv + (row0 + j) * a.lddv + hh * DK;
+      const float mul = half == 0 ? a.scale : 1.f;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        tmem_ld16(tmem + lane_sel + tcol + part * 16, o);
+        if (j < L) {
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 4)
+            st4(base + part * 16 + jj, make_float4(o[jj] * mul, o[jj + 1] * mul, o[jj + 2] * mul, o[jj + 3] * mul));
+        }
+      }
+    } else if (j < L) {
+      float* base = half == 0 ? a.dk + (row0 + j) * a.lddk + hh * DK : a.dv + (row0 + j) * a.lddv + hh * DK;
+      for (int jj = 0; jj < 32; jj += 4) st4(base + jj, make_float4(0.f, 0.f, 0.f, 0.f));
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -615,5 +888,48 @@ int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64
   }
   attn_bwd_dq_tc_kernel<<<B * h * NT, 64 + 32 * NSW, smem, st>>>(mapKk, mapKm, mapVk, a);
   RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dq)");
+  return 0;
+}
+
+bool rbm_attn_bwd_dkv_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t lddo, int64_t lddk, int64_t lddv,
+                                   const void* q, const void* k, const void* v, const void* dout, const void* dk_, const void* dv) {
+  if (!tc_enabled() || dk != DK || L < 1 || L > 256) return false;
+  if (ldq % 4 || ldk % 4 || ldv % 4 || lddo % 4 || lddk % 4 || lddv % 4) return false;
+  if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)dout | (uintptr_t)dk_ | (uintptr_t)dv) & 15) return false;
+  return get_encode() != nullptr;
+}
+
+// boxes of [64 query rows x 32 columns]
+static bool encode_map3_rows(CUtensorMap* map, const float* base, int B, int L, int width, int64_t ld, int box_rows, bool mn_major) {
+  return encode_map3(map, base, B, L, width, ld, box_rows, mn_major);
+}
+
+int rbm_attn_bwd_dkv_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
+                               const float* dout, int64_t lddo, const float* stats, const float* delta, float* dk_, int64_t lddk,
+                               float* dv, int64_t lddv, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed,
+                               uint64_t site, cudaStream_t st) {
+  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+  CUtensorMap mQk, mQm, mOk, mOm;
+  if (!encode_map3_rows(&mQk, q, B, L, h * DK, ldq, QC, false) || !encode_map3_rows(&mQm, q, B, L, h * DK, ldq, QC, true) ||
+      !encode_map3_rows(&mOk, dout, B, L, h * DK, lddo, QC, false) || !encode_map3_rows(&mOm, dout, B, L, h * DK, lddo, QC, true)) {
+    rbm_set_error("rbm_attn_bwd(tcgen05 dkv): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  TcBwdKvArgs a{};
+  a.k = k; a.v = v; a.stats = stats; a.delta = delta; a.dk = dk_; a.dv = dv; a.ldk = ldk; a.ldv = ldv; a.lddk = lddk; a.lddv = lddv;
+  a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
+  a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
+  size_t smem = (size_t)2 * CH_STAGE + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    if (e != cudaSuccess) {
+      rbm_set_error("rbm_attn_bwd(tcgen05 dkv): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+      return (int)e;
+    }
+    attr_set = true;
+  }
+  attn_bwd_dkv_tc_kernel<<<B * h * NT, 64 + 32 * NSW, smem, st>>>(mQk, mQm, mOk, mOm, a);
+  RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dkv)");
   return 0;
 }
