@@ -1,0 +1,656 @@
+// ce_tc.cu -- BERT4Rec output scoring fused with masked cross-entropy on the Blackwell tensor path (d in {32,64,128}).
+// Logits only ever exist as [128 x 64] tiles in tensor memory.  3xTF32 everywhere (fp32-level accuracy): the weight and
+// the compacted hidden rows are pre-split once per call into (raw, TF32 residual) pairs in global memory so TMA streams
+// both copies; per-CTA resident operands (hidden rows / weight rows) sit in TMEM as A operands with their residuals.
+//   ce_fwd_tc     rows = 128 masked positions; vocab streams in 64-row K-major chunks; S = H.W^T into double-buffered
+//                 TMEM; 8 softmax warps (thread per row) keep an online (max, sum-exp) in the log2 domain + target logit.
+//   ce_bwd_dh_tc  same streaming; G = (softmax - onehot)*g and its residual overwrite S in TMEM and feed
+//                 dH += G.W[chunk]  (A from TMEM, W chunk MN-major).
+//   ce_bwd_dw_tc  rows = 128 vocab entries (W rows in TMEM); compacted hidden rows stream in 64-row chunks (K-major for
+//                 S^T = W.H^T, MN-major for dW += G^T.H); db = row sums of G^T; row chunks split over blockIdx.y with
+//                 a fixed-order reduction.
+#include <stdlib.h>
+#include <string.h>
+#include "common.cuh"
+#include "mma_tiles.cuh"  // ex2, RBM_LOG2E, RBM_LN2
+#include "tc_ptx.cuh"
+#include "ce_tc.cuh"
+
+namespace {
+
+using namespace rbm_tc;
+using rbm_mma::ex2;
+
+constexpr int NSW = 8;
+constexpr int CW = 64;                 // streamed rows (vocab or masked rows) per chunk
+constexpr uint32_t BLK = CW * 128;     // one [64 x 32] fp32 block = 8 KB
+
+struct CeTcArgs {
+  const float* h;        // [n, d] hidden states
+  const float* w;        // [V1, d]
+  const int32_t* rows;   // compacted row ids
+  const int64_t* tgt;
+  const int32_t* count;
+  const float* bias;
+  const float* lse_in;
+  const float* dloss;
+  float *lse_out, *partial, *dh_full, *part_w, *part_b;
+  int V1, d, KB, nstage;
+};
+
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
+
+// thread-owned row (d floats, global) -> TMEM raw / lo regions, scaled
+__device__ __forceinline__ void row_to_tmem(const float* __restrict__ src, bool valid, float mul, int d, uint32_t t_raw, uint32_t t_lo) {
+  for (int c0 = 0; c0 < d; c0 += 16) {
+    float v[16], lo[16];
+#pragma unroll
+    for (int c = 0; c < 16; c += 4) {
+      float4 x = valid ? ld4(src + c0 + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+      v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
+    }
+#pragma unroll
+    for (int c = 0; c < 16; ++c) lo[c] = lo_of(v[c]);
+    tmem_st16(t_raw + c0, v);
+    tmem_st16(t_lo + c0, lo);
+  }
+  tmem_st_wait();
+}
+
+// 3xTF32: D[tmem] (+)= A[tmem raw/lo, KB*32 columns] . B[chunk K-major raw/lo]^T
+__device__ __forceinline__ void mma_scores(uint32_t d_t, uint32_t a_raw, uint32_t a_lo, uint32_t b_raw, uint32_t b_lo, int KB, uint32_t idesc) {
+  for (int kb = 0; kb < KB; ++kb) {
+    const uint64_t br = make_sw128_desc(b_raw + kb * BLK), bl = make_sw128_desc(b_lo + kb * BLK);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const uint64_t o = (uint64_t)(k * 2);
+      const uint32_t ac = (uint32_t)(kb * 32 + k * 8);
+      umma_tf32_ts(d_t, a_raw + ac, bl + o, idesc, (kb | k) != 0);
+      umma_tf32_ts(d_t, a_lo + ac, br + o, idesc, 1);
+      umma_tf32_ts(d_t, a_raw + ac, br + o, idesc, 1);
+    }
+  }
+}
+// 3xTF32: D[tmem, N = KB*32] (+)= G[tmem raw/lo, 64 columns] . B[chunk MN-major raw/lo]
+__device__ __forceinline__ void mma_accum(uint32_t d_t, uint32_t g_raw, uint32_t g_lo, uint32_t b_raw, uint32_t b_lo, uint32_t idesc, bool first) {
+#pragma unroll
+  for (int kk = 0; kk < CW / 8; ++kk) {
+    const uint64_t br = make_sw128_desc_mn(b_raw + kk * 1024, BLK), bl = make_sw128_desc_mn(b_lo + kk * 1024, BLK);
+    umma_tf32_ts(d_t, g_raw + kk * 8, bl, idesc, !(first && kk == 0));
+    umma_tf32_ts(d_t, g_lo + kk * 8, br, idesc, 1);
+    umma_tf32_ts(d_t, g_raw + kk * 8, br, idesc, 1);
+  }
+}
+
+// --------------------------------------------------------------------------------------------------- forward
+// TMEM: H raw [0,d) | H lo [d,2d) | S buffers [2d, 2d+128)
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWl,
+                                                                     const CeTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[8], empty_bar[8], tfull[2], tempty[2], h_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float xm[2][128], xl[2][128], xt[2][128];
+  __shared__ float contrib[128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *a.count;
+  const int r0 = blockIdx.x * 128;
+  if (r0 >= count) {
+    if (threadIdx.x == 0) a.partial[blockIdx.x] = 0.f;
+    return;
+  }
+  const int d = a.d, KB = a.KB, ns = a.nstage, V1 = a.V1;
+  const int NC = (V1 + CW - 1) / CW;
+  const uint32_t stage_bytes = 2 * KB * BLK;  // raw blocks then lo blocks
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&tfull[i]), 1);
+      mbar_init(smem_u32(&tempty[i]), NSW);
+    }
+    mbar_init(smem_u32(&h_bar), NSW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tH = tmem, tHl = tmem + d, tS = tmem + 2 * d;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < NC; ++c) {
+        const int s = c % ns;
+        if (c >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((c / ns) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(sa + kb * BLK, &mapW, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (KB + kb) * BLK, &mapWl, bar, kb * 32, c * CW);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0);
+      mbar_wait(smem_u32(&h_bar), 0);
+      tc_fence_after();
+      for (int c = 0; c < NC; ++c) {
+        const int s = c % ns, buf = c & 1;
+        if (c >= 2) {
+          mbar_wait(smem_u32(&tempty[buf]), ((c >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        mbar_wait(smem_u32(&full_bar[s]), (c / ns) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        mma_scores(tS + buf * CW, tH, tHl, sa, sa + KB * BLK, KB, idS);
+        umma_commit(smem_u32(&empty_bar[s]));
+        umma_commit(smem_u32(&tfull[buf]));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int rl = q * 32 + lane, r = r0 + rl;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool valid = r < count;
+    if (half == 0) row_to_tmem(a.h + (int64_t)(valid ? a.rows[r] : 0) * d, valid, RBM_LOG2E, d, tH + lane_sel, tHl + lane_sel);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&h_bar));
+    const int64_t tg = valid ? a.tgt[r] : -1;
+    float m = -INFINITY, l = 0.f, tl = 0.f;
+    for (int c = 0; c < NC; ++c) {
+      const int buf = c & 1;
+      mbar_wait(smem_u32(&tfull[buf]), (c >> 1) & 1);
+      tc_fence_after();
+      float v[32];
+      tmem_ld32(tS + lane_sel + (uint32_t)(buf * CW + half * 32), v);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&tempty[buf]));
+      const int v0 = c * CW + half * 32;
+      float cm = -INFINITY;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        const int vv = v0 + j;
+        float x = vv < V1 ? v[j] + (a.bias ? a.bias[vv] * RBM_LOG2E : 0.f) : -INFINITY;
+        if ((int64_t)vv == tg) tl = x;
+        v[j] = x;
+        cm = fmaxf(cm, x);
+      }
+      const float mn = fmaxf(m, cm);
+      if (mn > -INFINITY) {
+        float ps = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) ps += ex2(v[j] - mn);
+        l = l * (m == -INFINITY ? 0.f : ex2(m - mn)) + ps;
+        m = mn;
+      }
+    }
+    xm[half][rl] = m; xl[half][rl] = l; xt[half][rl] = tl;
+    named_bar_sync(2 + q, 64);
+    if (half == 0) {
+      const float m0 = xm[0][rl], m1 = xm[1][rl];
+      const float mm = fmaxf(m0, m1);
+      const float ll = xl[0][rl] * (m0 == -INFINITY ? 0.f : ex2(m0 - mm)) + xl[1][rl] * (m1 == -INFINITY ? 0.f : ex2(m1 - mm));
+      const float lse = (mm + log2f(ll)) * RBM_LN2;
+      const float tsum = (xt[0][rl] + xt[1][rl]) * RBM_LN2;
+      if (valid) a.lse_out[r] = lse;
+      contrib[rl] = valid ? lse - tsum : 0.f;
+    }
+    named_bar_sync(1, NSW * 32);
+    if (warp == 2 && lane == 0) {
+      float sacc = 0.f;
+      for (int i = 0; i < 128; ++i) sacc += contrib[i];
+      a.partial[blockIdx.x] = sacc;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------- backward: dH
+// TMEM: H raw [0,d) | H lo [d,2d) | S/G raw [2d,2d+64) | G lo [2d+64,2d+128) | dH [2d+128, 3d+128)
+// stage: W chunk K-major raw | lo | W chunk MN-major raw | lo   (KB blocks each)
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWl,
+                                                                        const __grid_constant__ CUtensorMap mapWm,
+                                                                        const __grid_constant__ CUtensorMap mapWml, const CeTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], s_full[2], g_full[2], h_bar, done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *a.count;
+  const int r0 = blockIdx.x * 128;
+  if (r0 >= count) return;
+  const int d = a.d, KB = a.KB, ns = a.nstage, V1 = a.V1;
+  const int NC = (V1 + CW - 1) / CW;
+  const uint32_t stage_bytes = 4 * KB * BLK;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&g_full[i]), NSW);
+    }
+    mbar_init(smem_u32(&h_bar), NSW);
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tH = tmem, tHl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int c = 0; c < NC; ++c) {
+        const int s = c % ns;
+        if (c >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((c / ns) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(sa + kb * BLK, &mapW, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (KB + kb) * BLK, &mapWl, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (2 * KB + kb) * BLK, &mapWm, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (3 * KB + kb) * BLK, &mapWml, bar, kb * 32, c * CW);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
+      mbar_wait(smem_u32(&h_bar), 0);
+      tc_fence_after();
+      for (int c = 0; c < NC; ++c) {
+        const int s = c % ns, ph = c & 1, par = (c >> 1) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), (c / ns) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        mma_scores(tS, tH, tHl, sa, sa + KB * BLK, KB, idS);
+        umma_commit(smem_u32(&s_full[ph]));
+        mbar_wait(smem_u32(&g_full[ph]), par);
+        tc_fence_after();
+        mma_accum(tD, tS, tGl, sa + 2 * KB * BLK, sa + 3 * KB * BLK, idD, c == 0);
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int rl = q * 32 + lane, r = r0 + rl;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool valid = r < count;
+    if (half == 0) row_to_tmem(a.h + (int64_t)(valid ? a.rows[r] : 0) * d, valid, RBM_LOG2E, d, tH + lane_sel, tHl + lane_sel);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&h_bar));
+    const int64_t tg = valid ? a.tgt[r] : -1;
+    const float lse2 = valid ? a.lse_in[r] * RBM_LOG2E : 0.f;
+    const float gscale = *a.dloss / (float)count;
+    for (int c = 0; c < NC; ++c) {
+      const int ph = c & 1, par = (c >> 1) & 1;
+      mbar_wait(smem_u32(&s_full[ph]), par);
+      tc_fence_after();
+      const int v0 = c * CW + half * 32;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float v[16], lo[16];
+        tmem_ld16(tS + lane_sel + (uint32_t)(half * 32 + part * 16), v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int vv = v0 + part * 16 + j;
+          float p = (valid && vv < V1) ? ex2(v[j] + (a.bias ? a.bias[vv] * RBM_LOG2E : 0.f) - lse2) : 0.f;
+          if ((int64_t)vv == tg) p -= 1.f;
+          const float gg = p * gscale;
+          v[j] = gg;
+          lo[j] = lo_of(gg);
+        }
+        tmem_st16(tS + lane_sel + (uint32_t)(half * 32 + part * 16), v);
+        tmem_st16(tGl + lane_sel + (uint32_t)(half * 32 + part * 16), lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&g_full[ph]));
+    }
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    // dH row: the two warps of a quarter split the d columns
+    const int dc = d / 2;
+    for (int c0 = half * dc; c0 < (half + 1) * dc; c0 += 16) {
+      float o[16];
+      tmem_ld16(tD + lane_sel + (uint32_t)c0, o);
+      if (valid) {
+        float* dst = a.dh_full + (int64_t)a.rows[r] * d + c0;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st4(dst + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------- backward: dW and db
+// rows = vocab; TMEM: W raw [0,d) | W lo [d,2d) | S^T/G^T raw [2d,2d+64) | G^T lo | dW [2d+128, 3d+128)
+// stage: Hc chunk K-major raw | lo | MN-major raw | lo
+__global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapHl,
+                                                                        const __grid_constant__ CUtensorMap mapHm,
+                                                                        const __grid_constant__ CUtensorMap mapHml, const CeTcArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], s_full[2], g_full[2], w_bar, done_bar;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ float lse_s[2][CW], tgt_s[2][CW];
+  __shared__ float xb[2][128];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *a.count;
+  const int d = a.d, KB = a.KB, ns = a.nstage, V1 = a.V1;
+  const int S = gridDim.y, sp = blockIdx.y;
+  const int NC = (count + CW - 1) / CW;
+  const int v0 = blockIdx.x * 128;
+  const uint32_t stage_bytes = 4 * KB * BLK;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < ns; ++s) {
+      mbar_init(smem_u32(&full_bar[s]), 1);
+      mbar_init(smem_u32(&empty_bar[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&g_full[i]), NSW);
+    }
+    mbar_init(smem_u32(&w_bar), NSW);
+    mbar_init(smem_u32(&done_bar), 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tW = tmem, tWl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int n = 0;
+      for (int c = sp; c < NC; c += S, ++n) {
+        const int s = n % ns;
+        if (n >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((n / ns) - 1) & 1);
+        const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * stage_bytes;
+        mbar_expect_tx(bar, stage_bytes);
+        for (int kb = 0; kb < KB; ++kb) {
+          tma_load_2d(sa + kb * BLK, &mapH, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (KB + kb) * BLK, &mapHl, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (2 * KB + kb) * BLK, &mapHm, bar, kb * 32, c * CW);
+          tma_load_2d(sa + (3 * KB + kb) * BLK, &mapHml, bar, kb * 32, c * CW);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
+      mbar_wait(smem_u32(&w_bar), 0);
+      tc_fence_after();
+      int n = 0;
+      for (int c = sp; c < NC; c += S, ++n) {
+        const int s = n % ns, ph = n & 1, par = (n >> 1) & 1;
+        mbar_wait(smem_u32(&full_bar[s]), (n / ns) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + s * stage_bytes;
+        mma_scores(tS, tW, tWl, sa, sa + KB * BLK, KB, idS);
+        umma_commit(smem_u32(&s_full[ph]));
+        mbar_wait(smem_u32(&g_full[ph]), par);
+        tc_fence_after();
+        mma_accum(tD, tS, tGl, sa + 2 * KB * BLK, sa + 3 * KB * BLK, idD, n == 0);
+        umma_commit(smem_u32(&empty_bar[s]));
+      }
+      umma_commit(smem_u32(&done_bar));
+    }
+    __syncwarp();
+  } else {
+    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int tid = sw * 32 + lane;
+    const int rl = q * 32 + lane, vrow = v0 + rl;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const bool valid = vrow < V1;
+    if (half == 0) row_to_tmem(a.w + (int64_t)(valid ? vrow : 0) * d, valid, RBM_LOG2E, d, tW + lane_sel, tWl + lane_sel);
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(smem_u32(&w_bar));
+    const float b2 = (a.bias && valid) ? a.bias[vrow] * RBM_LOG2E : 0.f;
+    const float gscale = *a.dloss / (float)count;
+    float bsum = 0.f;
+    int n = 0;
+    for (int c = sp; c < NC; c += S, ++n) {
+      const int ph = n & 1, par = (n >> 1) & 1;
+      // per-column (masked row) statistics of this chunk; the previous use of slot `ph` was two chunks ago
+      if (tid < CW) {
+        const int r = c * CW + tid;
+        lse_s[ph][tid] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
+        tgt_s[ph][tid] = r < count ? (float)a.tgt[r] : -1.f;
+      }
+      named_bar_sync(1, NSW * 32);
+      mbar_wait(smem_u32(&s_full[ph]), par);
+      tc_fence_after();
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float v[16], lo[16];
+        const int cb = half * 32 + part * 16;
+        tmem_ld16(tS + lane_sel + (uint32_t)cb, v);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const float tcol = tgt_s[ph][cb + j];
+          float p = (valid && tcol >= 0.f) ? ex2(v[j] + b2 - lse_s[ph][cb + j]) : 0.f;
+          if (valid && tcol == (float)vrow) p -= 1.f;
+          const float gg = p * gscale;
+          bsum += gg;
+          v[j] = gg;
+          lo[j] = lo_of(gg);
+        }
+        tmem_st16(tS + lane_sel + (uint32_t)cb, v);
+        tmem_st16(tGl + lane_sel + (uint32_t)cb, lo);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&g_full[ph]));
+    }
+    xb[half][rl] = bsum;
+    mbar_wait(smem_u32(&done_bar), 0);
+    tc_fence_after();
+    named_bar_sync(1, NSW * 32);
+    float* pw = a.part_w + ((int64_t)sp * V1 + vrow) * d;
+    const int dc = d / 2;
+    for (int c0 = half * dc; c0 < (half + 1) * dc; c0 += 16) {
+      float o[16];
+      if (n > 0) {
+        tmem_ld16(tD + lane_sel + (uint32_t)c0, o);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o[j] = 0.f;
+      }
+      if (valid) {
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) st4(pw + c0 + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+      }
+    }
+    if (half == 0 && valid) a.part_b[(int64_t)sp * V1 + vrow] = xb[0][rl] + xb[1][rl];
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------- helper kernels
+// dst_lo = src - trunc_tf32(src)
+__global__ void __launch_bounds__(256) lo_copy_kernel(const float* __restrict__ src, float* __restrict__ lo, int64_t n4) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = ld4(src + i * 4);
+  st4(lo + i * 4, make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w)));
+}
+// Hc[r] = h[rows[r]] (r < count), zeros up to the next multiple of 128; plus its TF32 residual
+__global__ void __launch_bounds__(256) gather_split_kernel(const float* __restrict__ h, const int32_t* __restrict__ rows,
+                                                           const int32_t* __restrict__ count_p, float* __restrict__ hc, float* __restrict__ hcl,
+                                                           int64_t cap, int d4) {
+  const int count = *count_p;
+  int64_t lim = ((int64_t)count + 127) / 128 * 128;
+  if (lim > cap) lim = cap;
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= lim * d4) return;
+  int64_t r = i / d4;
+  int c4 = (int)(i - r * d4);
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < count) v = ld4(h + ((int64_t)rows[r] * d4 + c4) * 4);
+  st4(hc + i * 4, v);
+  st4(hcl + i * 4, make_float4(lo_of(v.x), lo_of(v.y), lo_of(v.z), lo_of(v.w)));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* sym = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &sym, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)sym;
+  }
+  return fn;
+}
+// [rows, d] fp32, box [64 rows x 32 cols]; K-major consumers: 128B swizzle, MN-major consumers: 32-byte-atom variant
+bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int d, bool mn) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return false;
+  cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(float)};
+  cuuint32_t box[2] = {32, (cuuint32_t)CW};
+  cuuint32_t estr[2] = {1, 1};
+  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+             mn ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool tc_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("RBM_CE_IMPL");
+    v = (e && strcmp(e, "mma") == 0) ? 0 : 1;
+  }
+  return v == 1;
+}
+template <typename K>
+bool set_smem(K kern, size_t bytes, const char* name) {
+  cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    rbm_set_error("%s: cudaFuncSetAttribute: %s", name, cudaGetErrorString(e));
+    return false;
+  }
+  return true;
+}
+
+}  // namespace
+
+bool rbm_ce_tc_supported(int V1, int d, const void* h, const void* w) {
+  if (!tc_enabled() || (d != 32 && d != 64 && d != 128) || V1 < CW) return false;
+  if (((uintptr_t)h | (uintptr_t)w) & 15) return false;
+  return get_encode() != nullptr;
+}
+
+// extra workspace (floats): W_lo [V1*d] + Hc [cap128*d] + Hc_lo [cap128*d]
+size_t rbm_ce_tc_ws_floats(int64_t cap, int V1, int d) {
+  int64_t cap128 = (cap + 127) / 128 * 128;
+  return (size_t)V1 * d + 2 * (size_t)cap128 * d + 64;
+}
+
+int rbm_ce_tc_dw_splits(int64_t cap, int V1) {
+  int64_t vt = rbm_cdiv(V1, 128), chunks = rbm_cdiv(cap, CW);
+  int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS, vt);
+  if (s > chunks) s = chunks;
+  if (s > 32) s = 32;
+  return (int)(s < 1 ? 1 : s);
+}
+
+int rbm_ce_tc_fwd(const float* h, const int32_t* rows, const int64_t* tgt, const int32_t* count, const float* w, const float* bias,
+                  float* lse, float* partial, int64_t cap, int V1, int d, float* extra_ws, int* nblk_out, cudaStream_t st) {
+  float* w_lo = extra_ws;
+  const int64_t nw4 = (int64_t)V1 * d / 4;
+  lo_copy_kernel<<<(unsigned)rbm_cdiv(nw4, 256), 256, 0, st>>>(w, w_lo, nw4);
+  CUtensorMap mW, mWl;
+  if (!encode_map(&mW, w, V1, d, false) || !encode_map(&mWl, w_lo, V1, d, false)) {
+    rbm_set_error("rbm_ce_fwd(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  CeTcArgs a{};
+  a.h = h; a.w = w; a.rows = rows; a.tgt = tgt; a.count = count; a.bias = bias; a.lse_out = lse; a.partial = partial; a.V1 = V1; a.d = d;
+  a.KB = d / 32;
+  const size_t stage = (size_t)2 * a.KB * BLK;
+  int ns = (int)((180 * 1024) / stage);
+  a.nstage = ns > 8 ? 8 : ns;
+  const size_t smem = (size_t)a.nstage * stage + 1024;
+  if (!set_smem(ce_fwd_tc_kernel, smem, "rbm_ce_fwd(tcgen05)")) return -1;
+  const int nblk = (int)rbm_cdiv(cap, 128);
+  *nblk_out = nblk;
+  ce_fwd_tc_kernel<<<nblk, 64 + 32 * NSW, smem, st>>>(mW, mWl, a);
+  RBM_LAUNCH_CHECK("rbm_ce_fwd(tcgen05)");
+  return 0;
+}
+
+int rbm_ce_tc_bwd(const float* h, const int32_t* rows, const int64_t* tgt, const int32_t* count, const float* w, const float* bias,
+                  const float* lse, const float* dloss, float* dh_full, float* part_w, float* part_b, int S, int64_t cap, int V1, int d,
+                  float* extra_ws, cudaStream_t st) {
+  const int64_t cap128 = (cap + 127) / 128 * 128;
+  float* w_lo = extra_ws;
+  float* hc = w_lo + (size_t)V1 * d;
+  float* hcl = hc + (size_t)cap128 * d;
+  const int64_t nw4 = (int64_t)V1 * d / 4;
+  lo_copy_kernel<<<(unsigned)rbm_cdiv(nw4, 256), 256, 0, st>>>(w, w_lo, nw4);
+  gather_split_kernel<<<(unsigned)rbm_cdiv(cap128 * (d / 4), 256), 256, 0, st>>>(h, rows, count, hc, hcl, cap128, d / 4);
+  CUtensorMap mW, mWl, mWm, mWml, mH, mHl, mHm, mHml;
+  if (!encode_map(&mW, w, V1, d, false) || !encode_map(&mWl, w_lo, V1, d, false) || !encode_map(&mWm, w, V1, d, true) ||
+      !encode_map(&mWml, w_lo, V1, d, true) || !encode_map(&mH, hc, cap128, d, false) || !encode_map(&mHl, hcl, cap128, d, false) ||
+      !encode_map(&mHm, hc, cap128, d, true) || !encode_map(&mHml, hcl, cap128, d, true)) {
+    rbm_set_error("rbm_ce_bwd(tcgen05): cuTensorMapEncodeTiled failed");
+    return -1;
+  }
+  CeTcArgs a{};
+  a.h = h; a.w = w; a.rows = rows; a.tgt = tgt; a.count = count; a.bias = bias; a.lse_in = lse; a.dloss = dloss;
+  a.dh_full = dh_full; a.part_w = part_w; a.part_b = part_b; a.V1 = V1; a.d = d; a.KB = d / 32;
+  const size_t stage = (size_t)4 * a.KB * BLK;
+  int ns = (int)((192 * 1024) / stage);
+  a.nstage = ns > 4 ? 4 : ns;
+  const size_t smem = (size_t)a.nstage * stage + 1024;
+  if (!set_smem(ce_bwd_dh_tc_kernel, smem, "rbm_ce_bwd(tcgen05 dh)") || !set_smem(ce_bwd_dw_tc_kernel, smem, "rbm_ce_bwd(tcgen05 dw)")) return -1;
+  ce_bwd_dh_tc_kernel<<<(unsigned)rbm_cdiv(cap, 128), 64 + 32 * NSW, smem, st>>>(mW, mWl, mWm, mWml, a);
+  RBM_LAUNCH_CHECK("rbm_ce_bwd(tcgen05 dh)");
+  dim3 gdw((unsigned)rbm_cdiv(V1, 128), S);
+  ce_bwd_dw_tc_kernel<<<gdw, 64 + 32 * NSW, smem, st>>>(mH, mHl, mHm, mHml, a);
+  RBM_LAUNCH_CHECK("rbm_ce_bwd(tcgen05 dw)");
+  return 0;
+}

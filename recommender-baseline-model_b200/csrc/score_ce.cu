@@ -10,6 +10,7 @@
 //         blockIdx.y with a fixed-order reduction), G = (softmax - onehot) * dloss / count.
 #include "common.cuh"
 #include "mma_tiles.cuh"
+#include "ce_tc.cuh"
 
 namespace {
 
@@ -455,11 +456,18 @@ extern "C" int rbm_compact_labels(const int64_t* labels, int64_t n, int32_t* row
   return 0;
 }
 
-extern "C" size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d) {
-  size_t nblk = (size_t)rbm_cdiv(cap, 16);  // upper bound for any warps-per-CTA choice
+// workspace layout (floats): [partial: cdiv(cap,16)] [part_w: Smax*V1*d] [part_b: Smax*V1] [tcgen05 extras]
+static size_t ce_smax(int64_t cap, int V1) {
   size_t S = (size_t)dw_splits(cap, V1, 1);
   if (S < (size_t)dw_splits(cap, V1, 8)) S = (size_t)dw_splits(cap, V1, 8);
-  return (nblk + S * ((size_t)V1 * d + V1)) * sizeof(float) + 64;
+  if (S < (size_t)rbm_ce_tc_dw_splits(cap, V1)) S = (size_t)rbm_ce_tc_dw_splits(cap, V1);
+  return S;
+}
+static size_t ce_off_partw(int64_t cap) { return ((size_t)rbm_cdiv(cap, 16) + 3) & ~(size_t)3; }
+static size_t ce_off_extra(int64_t cap, int V1, int d) { return (ce_off_partw(cap) + ce_smax(cap, V1) * ((size_t)V1 * d + V1) + 3) & ~(size_t)3; }
+
+extern "C" size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d) {
+  return (ce_off_extra(cap, V1, d) + rbm_ce_tc_ws_floats(cap, V1, d)) * sizeof(float) + 64;
 }
 
 static int ce_check(const char* name, int64_t cap, int V1, int d) {
@@ -476,6 +484,14 @@ extern "C" int rbm_ce_fwd(const float* h, const int32_t* rows, const int64_t* tg
   RBM_REQUIRE(ws_bytes >= rbm_ce_ws_bytes(cap, V1, d), "rbm_ce_fwd: workspace too small");
   RBM_REQUIRE(rbm_aligned16(h) && rbm_aligned16(w) && rbm_aligned16(ws), "rbm_ce_fwd: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  if (rbm_ce_tc_supported(V1, d, h, w)) {  // Blackwell tensor path
+    int nblk_tc = 0;
+    int rc = rbm_ce_tc_fwd(h, rows, tgt, count, w, bias, lse, (float*)ws, cap, V1, d, (float*)ws + ce_off_extra(cap, V1, d), &nblk_tc, st);
+    if (rc) return rc;
+    ce_loss_finalize_kernel<<<1, 256, 0, st>>>((const float*)ws, nblk_tc, count, loss);
+    RBM_LAUNCH_CHECK("rbm_ce_fwd(finalize)");
+    return 0;
+  }
   int warps = ce_warps(d, false);
   int nblk = (int)rbm_cdiv(cap, 16 * warps);
   size_t smem = ce_smem(d, warps, false);
@@ -498,12 +514,23 @@ extern "C" int rbm_ce_bwd(const float* h, const int32_t* rows, const int64_t* tg
   RBM_REQUIRE(rbm_aligned16(h) && rbm_aligned16(w) && rbm_aligned16(ws) && rbm_aligned16(dh_full) && rbm_aligned16(dw),
               "rbm_ce_bwd: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
+  float* part_w = (float*)ws + ce_off_partw(cap);
+  if (rbm_ce_tc_supported(V1, d, h, w)) {  // Blackwell tensor path
+    const int S = rbm_ce_tc_dw_splits(cap, V1);
+    float* part_b = part_w + (size_t)S * V1 * d;
+    int rc = rbm_ce_tc_bwd(h, rows, tgt, count, w, bias, lse, dloss, dh_full, part_w, part_b, S, cap, V1, d,
+                           (float*)ws + ce_off_extra(cap, V1, d), st);
+    if (rc) return rc;
+    int64_t n = (int64_t)V1 * d;
+    ce_reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, st>>>(part_w, dw, n, S);
+    ce_reduce_splits_kernel<<<(unsigned)rbm_cdiv(V1, 256), 256, 0, st>>>(part_b, db, V1, S);
+    RBM_LAUNCH_CHECK("rbm_ce_bwd(reduce)");
+    return 0;
+  }
   int warps = ce_warps(d, true);
   int nblk = (int)rbm_cdiv(cap, 16 * warps);
   int S = dw_splits(cap, V1, warps);
   size_t smem = ce_smem(d, warps, true);
-  float* part_w = (float*)ws + rbm_cdiv(cap, 16);
-  part_w = (float*)(((uintptr_t)part_w + 15) & ~(uintptr_t)15);
   float* part_b = part_w + (size_t)S * V1 * d;
   CeArgs a{};
   a.h = h; a.rows = rows; a.tgt = tgt; a.count = count; a.w = w; a.bias = bias; a.lse_in = lse; a.dloss = dloss;
