@@ -181,6 +181,9 @@ __device__ __forceinline__ void split_lo(const float* src, float* dst, int n4, i
 }
 
 constexpr int EPI_WARPS = 8;
+// HAS_ACT: pre-activation store + activation compiled in; HAS_DROP: the two Philox dropout sites compiled in.  The
+// epilogue loop is fully unrolled, so leaving the unused branches out keeps its body inside the instruction cache.
+template <bool HAS_ACT, bool HAS_DROP>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                       const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -320,6 +323,14 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
           const int64_t row = rbase + i * 4 + rsub;
           res[i] = (resid && col_ok && row < p.M) ? ld4(resid + row * p.ldres + col) : make_float4(0.f, 0.f, 0.f, 0.f);
         }
+        uint32_t zero_rows = 0;  // bit i: row i*4+rsub is a padding token whose output is forced to zero
+        if (p.row_tok) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int64_t row = rbase + i * 4 + rsub;
+            if (row < p.M && p.row_tok[row] == 0) zero_rows |= 1u << i;
+          }
+        }
 #pragma unroll
         for (int j = 0; j < 32; j += 4) st4(stg + lane * STG_LD + (((j >> 2) ^ (lane & 7)) << 2), make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         __syncwarp();
@@ -333,19 +344,25 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
             if (row < p.M) {
               float4 x = ld4(stg + rl * STG_LD + (((cg >> 2) ^ (rl & 7)) << 2));
               x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-              if (preout) st4(preout + row * p.N + col, x);
-              x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
+              if constexpr (HAS_ACT) {
+                if (preout) st4(preout + row * p.N + col, x);
+                x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
+              }
               const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
-              if (p.thrA) {
-                float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
-                x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+              if constexpr (HAS_DROP) {
+                if (p.thrA) {
+                  float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+                  x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+                }
               }
               x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
-              if (p.thrB) {
-                float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
-                x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+              if constexpr (HAS_DROP) {
+                if (p.thrB) {
+                  float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+                  x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+                }
               }
-              if (p.row_tok && p.row_tok[row] == 0) x = make_float4(0.f, 0.f, 0.f, 0.f);
+              if ((zero_rows >> i) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
               st4(yout + row * p.ldy + col, x);
             }
           }
@@ -593,7 +610,10 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
     if (e != cudaSuccess) {
       rbm_set_error("rbm_linear(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -610,7 +630,12 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
     size_t smem = (size_t)2 * N * K * 4 + (size_t)ns * 2 * BM * BKE * 4 + (size_t)EPI_WARPS * 32 * STG_LD * 4 + 1024;
     int tiles = (int)rbm_cdiv(M, BM);
     int grid = tiles < RBM_NUM_SMS ? tiles : RBM_NUM_SMS;
-    tc_linear_persistent_kernel<<<grid, 128 + 32 * EPI_WARPS, smem, st>>>(mapA, mapB, p);
+    const bool has_act = p.act != 0 || p.pre != nullptr, has_drop = p.thrA != 0 || p.thrB != 0;
+    const int nthr = 128 + 32 * EPI_WARPS;
+    if (has_act && has_drop) tc_linear_persistent_kernel<true, true><<<grid, nthr, smem, st>>>(mapA, mapB, p);
+    else if (has_act) tc_linear_persistent_kernel<true, false><<<grid, nthr, smem, st>>>(mapA, mapB, p);
+    else if (has_drop) tc_linear_persistent_kernel<false, true><<<grid, nthr, smem, st>>>(mapA, mapB, p);
+    else tc_linear_persistent_kernel<false, false><<<grid, nthr, smem, st>>>(mapA, mapB, p);
     RBM_LAUNCH_CHECK("rbm_linear(tcgen05 persistent)");
     return 0;
   }
