@@ -224,13 +224,44 @@ __global__ void __launch_bounds__(256) gemm_tn_split_kernel(const float* __restr
   }
 }
 
-// out[i] = sum_{s ascending} part[s][i]
-__global__ void reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int S) {
-  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float s = 0.f;
-  for (int k = 0; k < S; ++k) s += part[(int64_t)k * n + i];
-  out[i] = s;
+// out[i] = sum_s part[s][i] in a fixed order: eight interleaved groups (s = g, g+8, ... ascending), then the groups
+// ascending.  One block = 32 float4 outputs x 8 groups; blocks [0, nblk_w) reduce the weight partials, the rest the bias
+// partials (part_b may be null).  n and nb are multiples of 4.
+__global__ void __launch_bounds__(256) reduce_splits_kernel(const float* __restrict__ part, float* __restrict__ out, int64_t n, int nblk_w,
+                                                            const float* __restrict__ part_b, float* __restrict__ out_b, int64_t nb,
+                                                            int S) {
+  __shared__ float4 acc[8][32];
+  const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
+  const bool is_b = (int)blockIdx.x >= nblk_w;
+  const float* src = is_b ? part_b : part;
+  float* dst = is_b ? out_b : out;
+  const int64_t len = is_b ? nb : n;
+  const int64_t i4 = (int64_t)(is_b ? blockIdx.x - nblk_w : blockIdx.x) * 32 + o;
+  float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (i4 * 4 < len)
+    for (int s = g; s < S; s += 8) {
+      const float4 v = ld4(src + (int64_t)s * len + i4 * 4);
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+  acc[g][o] = a;
+  __syncthreads();
+  if (g == 0 && i4 * 4 < len) {
+#pragma unroll
+    for (int k = 1; k < 8; ++k) {
+      const float4 v = acc[k][o];
+      a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+    }
+    if (is_b) {  // the bias gradient pointer is only required to be 4-byte aligned
+      dst[i4 * 4] = a.x; dst[i4 * 4 + 1] = a.y; dst[i4 * 4 + 2] = a.z; dst[i4 * 4 + 3] = a.w;
+    } else {
+      st4(dst + i4 * 4, a);
+    }
+  }
+}
+
+static void launch_reduce_splits(const float* part, float* dw, int64_t n, const float* part_b, float* db, int64_t nb, int S, cudaStream_t st) {
+  const int nblk_w = (int)rbm_cdiv(n, 128), nblk_b = part_b ? (int)rbm_cdiv(nb, 128) : 0;
+  reduce_splits_kernel<<<nblk_w + nblk_b, 256, 0, st>>>(part, dw, n, nblk_w, part_b, db, nb, S);
 }
 
 __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const float* __restrict__ dout, const float* __restrict__ pre,
@@ -410,17 +441,16 @@ extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const fl
     const int S = rbm_tc_dw_splits(M);
     float* part = (float*)ws;
     float* part_b = part + (size_t)S * N * K;
-    int rc = rbm_tc_dw_launch(dpre, lddpre, x, ldx, part, M, N, K, (cudaStream_t)stream);
+    const bool fused_b = db && rbm_tc_dw_bias_fused(N, K);
+    int rc = rbm_tc_dw_launch(dpre, lddpre, x, ldx, part, fused_b ? part_b : nullptr, M, N, K, (cudaStream_t)stream);
     if (rc) return rc;
-    int64_t n = (int64_t)N * K;
-    reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(part, dw, n, S);
-    RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
-    if (db) {
+    if (db && !fused_b) {
       int64_t rpb = rbm_cdiv(M, S);
       colsum_split_kernel<<<S, 256, 0, (cudaStream_t)stream>>>(dpre, lddpre, part_b, M, N, rpb);
-      reduce_splits_kernel<<<(unsigned)rbm_cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(part_b, db, N, S);
       RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(bias)");
     }
+    launch_reduce_splits(part, dw, (int64_t)N * K, db ? part_b : nullptr, db, N, S, (cudaStream_t)stream);
+    RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
     return 0;
   }
   int S = tn_splits(M, N, K);
@@ -430,12 +460,7 @@ extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const fl
   dim3 grid((unsigned)rbm_cdiv(N, 64), (unsigned)rbm_cdiv(K, 64), S);
   gemm_tn_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dpre, lddpre, x, ldx, part, db ? part_b : nullptr, M, N, K, rps);
   RBM_LAUNCH_CHECK("rbm_linear_bwd_weight");
-  int64_t n = (int64_t)N * K;
-  reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, (cudaStream_t)stream>>>(part, dw, n, S);
+  launch_reduce_splits(part, dw, (int64_t)N * K, db ? part_b : nullptr, db, N, S, (cudaStream_t)stream);
   RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
-  if (db) {
-    reduce_splits_kernel<<<(unsigned)rbm_cdiv(N, 256), 256, 0, (cudaStream_t)stream>>>(part_b, db, N, S);
-    RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce bias)");
-  }
   return 0;
 }

@@ -393,10 +393,12 @@ constexpr int DW_BLK = DW_TOK * 128;       // bytes of one [32 tokens x 32 colum
 
 struct DwParams {
   float* part;     // [S][N][K]
+  float* part_b;   // [S][N] column sums of A (the bias gradient), or nullptr
   int64_t M, tok_per_cta;
   int N, K, nblkA, nblkB, mtiles, nstage;
   uint32_t tmem_cols;
 };
+constexpr int DW_BIAS_N = 16;  // width of the all-ones B operand that turns the bias gradient into one more accumulator
 
 __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                        const DwParams p) {
@@ -413,6 +415,12 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
   int64_t t1 = t0 + p.tok_per_cta;
   if (t1 > p.M) t1 = p.M;
   const int nst = t1 > t0 ? (int)((t1 - t0 + DW_TOK - 1) / DW_TOK) : 0;
+  // bias gradient: db = A^T . 1 -- an all-ones [8 tokens x 32 columns] block (swizzle-invariant) after the stages, and
+  // DW_BIAS_N extra accumulator columns per M tile behind the dW accumulators
+  const uint32_t off_ones = (uint32_t)p.nstage * stage_bytes;
+  const uint32_t bias_col = (uint32_t)(p.mtiles * p.K);
+  if (p.part_b)
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float*>(gen + off_ones)[i] = 1.f;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) {
@@ -456,6 +464,8 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
   } else if (warp == 1) {
     if (lane == 0) {
       const uint32_t idesc = make_idesc_tf32_ex(BM, p.K, 1, 1);
+      const uint32_t idesc_b = make_idesc_tf32_ex(BM, DW_BIAS_N, 1, 1);
+      const uint64_t ones = make_sw128_desc_mn(smem_base + off_ones, DW_BLK);
       for (int g = 0; g < nst; ++g) {
         const int s = g % p.nstage;
         mbar_wait(smem_u32(&full_bar[s]), (g / p.nstage) & 1);
@@ -473,6 +483,11 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
             umma_tf32(d, a_raw, b_lo, idesc, (g | k) != 0);
             umma_tf32(d, a_lo, b_raw, idesc, 1);
             umma_tf32(d, a_raw, b_raw, idesc, 1);
+            if (p.part_b) {
+              const uint32_t dbias = tmem_d + bias_col + (uint32_t)(mt * DW_BIAS_N);
+              umma_tf32(dbias, a_lo, ones, idesc_b, (g | k) != 0);
+              umma_tf32(dbias, a_raw, ones, idesc_b, 1);
+            }
           }
         }
         umma_commit(smem_u32(&empty_bar[s]));
@@ -512,6 +527,12 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
 #pragma unroll
           for (int j = 0; j < 32; j += 4) st4(part + (int64_t)n * p.K + c0 + j, make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]));
         }
+      }
+      if (p.part_b) {
+        float v[16];
+        if (nst > 0) tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + bias_col + (uint32_t)(mt * DW_BIAS_N), v);
+        else v[0] = 0.f;
+        if (n < p.N) p.part_b[(int64_t)blockIdx.x * p.N + n] = v[0];
       }
     }
   }
@@ -669,7 +690,7 @@ bool encode_map_mn(CUtensorMap* map, const float* base, int64_t rows, int64_t co
 int dw_stages(int N, int K, int* mtiles_out) {
   int mtiles = (N + BM - 1) / BM;
   size_t stage = (size_t)2 * ((size_t)mtiles * 4 + K / 32) * DW_BLK;
-  int ns = (int)(((size_t)231424 - 1024) / stage);
+  int ns = (int)(((size_t)231424 - 2048) / stage);  // 1 KB alignment slack + the 1 KB all-ones block
   if (ns > 8) ns = 8;
   *mtiles_out = mtiles;
   return ns;
@@ -681,6 +702,9 @@ int rbm_tc_dw_splits(int64_t M) {
   return (int)(s < 1 ? 1 : (s > RBM_NUM_SMS ? RBM_NUM_SMS : s));
 }
 
+// the bias gradient rides along when its accumulator columns fit in TMEM next to dW
+bool rbm_tc_dw_bias_fused(int N, int K) { return ((N + BM - 1) / BM) * (K + DW_BIAS_N) <= 512; }
+
 bool rbm_tc_dw_supported(int64_t M, int N, int K, int64_t lda, int64_t ldb, const void* a, const void* b) {
   if (tc_mode() != 0 || M < 1 || N % 32 != 0 || K % 32 != 0 || N > 256 || K > 256 || K < 32 || N < 32) return false;
   if (lda % 4 != 0 || ldb % 4 != 0 || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return false;
@@ -690,21 +714,23 @@ bool rbm_tc_dw_supported(int64_t M, int N, int K, int64_t lda, int64_t ldb, cons
 }
 
 // part: [rbm_tc_dw_splits(M)][N][K] partial sums (every slot is written)
-int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb, float* part, int64_t M, int N, int K, cudaStream_t st) {
+// part_b: [rbm_tc_dw_splits(M)][N] partial column sums of dpre, or nullptr (requires rbm_tc_dw_bias_fused(N, K))
+int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb, float* part, float* part_b, int64_t M, int N, int K,
+                     cudaStream_t st) {
   CUtensorMap mapA, mapB;
   if (!encode_map_mn(&mapA, dpre, M, N, lda) || !encode_map_mn(&mapB, x, M, K, ldb)) {
     rbm_set_error("rbm_linear_bwd_weight(tcgen05): cuTensorMapEncodeTiled failed");
     return -1;
   }
   DwParams p{};
-  p.part = part; p.M = M; p.N = N; p.K = K; p.nblkA = N / 32; p.nblkB = K / 32;
+  p.part = part; p.part_b = part_b; p.M = M; p.N = N; p.K = K; p.nblkA = N / 32; p.nblkB = K / 32;
   p.nstage = dw_stages(N, K, &p.mtiles);
   const int S = rbm_tc_dw_splits(M);
   p.tok_per_cta = rbm_cdiv(rbm_cdiv(M, S), DW_TOK) * DW_TOK;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.mtiles * K)) cols <<= 1;
+  while (cols < (uint32_t)(p.mtiles * (K + (part_b ? DW_BIAS_N : 0)))) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = (size_t)p.nstage * 2 * ((size_t)p.mtiles * 4 + p.nblkB) * DW_BLK + 1024;
+  size_t smem = (size_t)p.nstage * 2 * ((size_t)p.mtiles * 4 + p.nblkB) * DW_BLK + 2048;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);

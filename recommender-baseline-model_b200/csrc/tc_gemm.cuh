@@ -25,4 +25,6 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
 // dW[N,K] = dpre[M,N]^T . x[M,K] on tcgen05 (both operands MN-major): split over tokens into rbm_tc_dw_splits(M) partials
 int rbm_tc_dw_splits(int64_t M);
 bool rbm_tc_dw_supported(int64_t M, int N, int K, int64_t lda, int64_t ldb, const void* a, const void* b);
-int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb, float* part, int64_t M, int N, int K, cudaStream_t st);
+bool rbm_tc_dw_bias_fused(int N, int K);  // the bias gradient (column sums of dpre) fits next to dW in TMEM
+int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb, float* part, float* part_b, int64_t M, int N, int K,
+                     cudaStream_t st);
