@@ -269,14 +269,46 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __g
 }
 
 // =====================================================================================================
-// Backward pass A (dQ and delta) on the tensor path, one CTA per (sequence, head, 128-query tile).
-//   TMEM columns: S_h [0,112) | dP_h [112,224) | Q raw,lo [224,288) | dO raw,lo [288,352) | dQ [352,384)
-//   SMEM: K (K-major), K (MN-major, 32-byte-atom swizzle), V (K-major), each with its TF32 residual copy.
-//   Keys are processed in two halves (112 + rest) so S and dP fit; dS and its residual overwrite them in place and
-//   feed  dQ += dS.K  as the TMEM A operand.  delta_i = <dO_i, O_i> is also written for pass B.
+// Dropout words of one query row for the 16 keys [16*npair, 16*npair + 16).  Rows i and i^8 (lanes l, l^8 of a warp
+// whose lanes hold consecutive rows) share their four Philox calls: each lane computes two and trades the words the
+// other row needs.  w[2*t + e] holds the fields of keys jj with ((jj & 7) >> 1) == t, (jj & 1) == e: low half for
+// jj < 8, high half for jj >= 8 (common.cuh, rbm_attn_call / rbm_attn_field).
 // =====================================================================================================
-constexpr int HALF = 112;
-constexpr uint32_t T_S = 0, T_DP = 112, T_Q = 224, T_QL = 256, T_DO = 288, T_DOL = 320, T_DQ = 352;
+struct KeepWords {
+  uint32_t w[8];
+};
+__device__ __forceinline__ KeepWords attn_keep_words(uint64_t seed, uint64_t site, uint64_t bh, int i, int npair) {
+  const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
+  const uint4 ca = rbm_philox(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 0, npair));
+  const uint4 cb = rbm_philox(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 1, npair));
+  // mine: words rh*2 + e; the partner row (rh ^ 1) wants the other pair
+  const uint32_t ma0 = rh ? ca.z : ca.x, ma1 = rh ? ca.w : ca.y, mb0 = rh ? cb.z : cb.x, mb1 = rh ? cb.w : cb.y;
+  const uint32_t sa0 = rh ? ca.x : ca.z, sa1 = rh ? ca.y : ca.w, sb0 = rh ? cb.x : cb.z, sb1 = rh ? cb.y : cb.w;
+  const uint32_t pa0 = __shfl_xor_sync(0xffffffffu, sa0, 8), pa1 = __shfl_xor_sync(0xffffffffu, sa1, 8);
+  const uint32_t pb0 = __shfl_xor_sync(0xffffffffu, sb0, 8), pb1 = __shfl_xor_sync(0xffffffffu, sb1, 8);
+  KeepWords k;  // my calls are t = rh*2, rh*2 + 1; the partner's are t = (rh^1)*2, (rh^1)*2 + 1
+  k.w[0] = rh ? pa0 : ma0; k.w[1] = rh ? pa1 : ma1; k.w[2] = rh ? pb0 : mb0; k.w[3] = rh ? pb1 : mb1;
+  k.w[4] = rh ? ma0 : pa0; k.w[5] = rh ? ma1 : pa1; k.w[6] = rh ? mb0 : pb0; k.w[7] = rh ? mb1 : pb1;
+  return k;
+}
+// keep decision of key jj (compile-time after unrolling); thr_hi = thr16 << 16
+__device__ __forceinline__ bool attn_keep_bit(const KeepWords& k, int jj, uint32_t thr_hi) {
+  const uint32_t w = k.w[((jj & 7) >> 1) * 2 + (jj & 1)];
+  return (jj & 8) ? (w >= thr_hi) : ((w << 16) >= thr_hi);
+}
+
+// =====================================================================================================
+// Backward pass A (dQ and delta) on the tensor path, one CTA per (sequence, head, 128-query tile).
+//   SMEM: K (K-major), K (MN-major, 32-byte-atom swizzle), V (K-major), each with its TF32 residual copy.
+//   Keys are cut into chunks of <= 64 (multiples of 16).  Two groups of four softmax warps (one warp per TMEM lane
+//   quarter, one thread per query row) take the chunks alternately, each group with its own S / dP accumulator pair:
+//   while one group turns (S, dP) into dS, the tensor core is already producing the other group's next chunk and
+//   consuming the previous dS (dQ += dS.K, dS raw/residual read back from TMEM as the A operand).
+//   TMEM columns: group g: S [128g, +64) | dP [128g + 64, +64);  Q raw,lo [256,320) | dO raw,lo [320,384) | dQ [384,416)
+//   delta_i = <dO_i, O_i> is also written for pass B.
+// =====================================================================================================
+constexpr int CW = 64;  // columns of one chunk accumulator
+constexpr uint32_t A_GRP = 128, A_DP = 64, A_Q = 256, A_QL = 288, A_DO = 320, A_DOL = 352, A_DQ = 384;
 
 struct TcBwdArgs {
   const float *q, *o, *dout, *stats;
@@ -290,20 +322,21 @@ struct TcBwdArgs {
   uint64_t seed, site;
 };
 
+template <bool CAUSAL, bool DROP>
 __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapKk,
                                                                           const __grid_constant__ CUtensorMap mapKm,
                                                                           const __grid_constant__ CUtensorMap mapVk, const TcBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t load_bar, split_bar, s_full[2], ds_full[2], dq_full;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float padk[256];
+  __shared__ __align__(16) float kvalid[256];  // 1 = key takes part (inside the sequence and not a padding token)
   __shared__ float xdelta[128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int bh = blockIdx.x / a.NT, mt = blockIdx.x % a.NT;
   const int b = bh / a.h, hh = bh % a.h;
   const int L = a.L, LPK = a.LPK;
-  const int NH = LPK > HALF ? 2 : 1;
+  const int NU = LPK >> 4, NCH = (NU + 3) >> 2;  // 16-key units; chunks of <= 4 units, sizes as even as possible
   const uint32_t kv_bytes = (uint32_t)LPK * ROWB;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -314,7 +347,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
     mbar_init(smem_u32(&split_bar), NSW);
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&ds_full[i]), NSW);
+      mbar_init(smem_u32(&ds_full[i]), NSW / 2);
     }
     mbar_init(smem_u32(&dq_full), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -330,8 +363,8 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
       const uint32_t bar = smem_u32(&load_bar);
       mbar_expect_tx(bar, 3 * kv_bytes);
       tma_load_3d(smem_base + oKk, &mapKk, bar, hh * DK, 0, b);
-      tma_load_3d(smem_base + oKm, &mapKm, bar, hh * DK, 0, b);
       tma_load_3d(smem_base + oVk, &mapVk, bar, hh * DK, 0, b);
+      tma_load_3d(smem_base + oKm, &mapKm, bar, hh * DK, 0, b);
     }
   } else if (warp == 1) {
     if (lane == 0) {
@@ -339,58 +372,69 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
       mbar_wait(smem_u32(&split_bar), 0);
       tc_fence_after();
       const uint32_t idQ = make_idesc_tf32_ex(128, DK, 0, 1);  // dQ: A from TMEM, K MN-major
-      for (int hf = 0; hf < NH; ++hf) {
-        const int k0 = hf * HALF, nh = (hf == 0 ? (LPK < HALF ? LPK : HALF) : LPK - HALF);
+      auto issue_sdp = [&](int c) {
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        const uint32_t tS = tmem + (uint32_t)(c & 1) * A_GRP, tP = tS + A_DP;
         const uint32_t idS = make_idesc_tf32_ex(128, nh, 0, 0);
         const uint64_t dK = make_sw128_desc(smem_base + oKk + k0 * ROWB), dKl = make_sw128_desc(smem_base + oKkl + k0 * ROWB);
         const uint64_t dV = make_sw128_desc(smem_base + oVk + k0 * ROWB), dVl = make_sw128_desc(smem_base + oVkl + k0 * ROWB);
 #pragma unroll
         for (int k = 0; k < DK / 8; ++k) {
           const uint64_t o = (uint64_t)(k * 2);
-          umma_tf32_ts(tmem + T_S, tmem + T_Q + k * 8, dKl + o, idS, k != 0);
-          umma_tf32_ts(tmem + T_S, tmem + T_QL + k * 8, dK + o, idS, 1);
-          umma_tf32_ts(tmem + T_S, tmem + T_Q + k * 8, dK + o, idS, 1);
+          umma_tf32_ts(tS, tmem + A_Q + k * 8, dKl + o, idS, k != 0);
+          umma_tf32_ts(tS, tmem + A_QL + k * 8, dK + o, idS, 1);
+          umma_tf32_ts(tS, tmem + A_Q + k * 8, dK + o, idS, 1);
         }
 #pragma unroll
         for (int k = 0; k < DK / 8; ++k) {
           const uint64_t o = (uint64_t)(k * 2);
-          umma_tf32_ts(tmem + T_DP, tmem + T_DO + k * 8, dVl + o, idS, k != 0);
-          umma_tf32_ts(tmem + T_DP, tmem + T_DOL + k * 8, dV + o, idS, 1);
-          umma_tf32_ts(tmem + T_DP, tmem + T_DO + k * 8, dV + o, idS, 1);
+          umma_tf32_ts(tP, tmem + A_DO + k * 8, dVl + o, idS, k != 0);
+          umma_tf32_ts(tP, tmem + A_DOL + k * 8, dV + o, idS, 1);
+          umma_tf32_ts(tP, tmem + A_DO + k * 8, dV + o, idS, 1);
         }
-        umma_commit(smem_u32(&s_full[hf]));
-        mbar_wait(smem_u32(&ds_full[hf]), 0);
+        umma_commit(smem_u32(&s_full[c & 1]));
+      };
+      auto issue_dq = [&](int c) {
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        const uint32_t tS = tmem + (uint32_t)(c & 1) * A_GRP, tP = tS + A_DP;
+        mbar_wait(smem_u32(&ds_full[c & 1]), (c >> 1) & 1);
         tc_fence_after();
         for (int kk = 0; kk < nh / 8; ++kk) {
           const uint64_t dKm = make_sw128_desc_mn(smem_base + oKm + (k0 + kk * 8) * ROWB, 0);
           const uint64_t dKml = make_sw128_desc_mn(smem_base + oKml + (k0 + kk * 8) * ROWB, 0);
-          umma_tf32_ts(tmem + T_DQ, tmem + T_S + kk * 8, dKml, idQ, (hf | kk) != 0);
-          umma_tf32_ts(tmem + T_DQ, tmem + T_DP + kk * 8, dKm, idQ, 1);
-          umma_tf32_ts(tmem + T_DQ, tmem + T_S + kk * 8, dKm, idQ, 1);
+          umma_tf32_ts(tmem + A_DQ, tS + kk * 8, dKml, idQ, (c | kk) != 0);
+          umma_tf32_ts(tmem + A_DQ, tP + kk * 8, dKm, idQ, 1);
+          umma_tf32_ts(tmem + A_DQ, tS + kk * 8, dKm, idQ, 1);
         }
+      };
+      for (int c = 0; c < NCH; ++c) {
+        if (c >= 2) issue_dq(c - 2);  // frees this group's accumulators (the tensor pipe runs in order)
+        issue_sdp(c);
       }
+      for (int c = NCH >= 2 ? NCH - 2 : 0; c < NCH; ++c) issue_dq(c);
       umma_commit(smem_u32(&dq_full));
     }
     __syncwarp();
   } else {
-    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int sw = warp - 2, q = warp & 3, grp = sw >> 2;
     const int tid = sw * 32 + lane;
     const int64_t row0 = (int64_t)b * L;
     const int rl = q * 32 + lane;
     const int i = mt * 128 + rl;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int j = tid; j < 256; j += NSW * 32) padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
-    // ---- operand rows into TMEM: warps of half 0 take Q (pre-scaled to the log2 domain), half 1 take dO and delta
+    for (int j = tid; j < 256; j += NSW * 32)
+      kvalid[j] = (j < L && !(a.mask_mode == RBM_MASK_KEYPAD && a.tok[row0 + j] == 0)) ? 1.f : 0.f;
+    // ---- operand rows into TMEM: group 0 takes Q (pre-scaled to the log2 domain), group 1 takes dO and delta
     {
       float v[32], lo[32];
-      const float* src = half == 0 ? a.q + (row0 + i) * a.ldq + hh * DK : a.dout + (row0 + i) * a.lddo + hh * DK;
-      const float mul = half == 0 ? a.scale_log2 : 1.f;
+      const float* src = grp == 0 ? a.q + (row0 + i) * a.ldq + hh * DK : a.dout + (row0 + i) * a.lddo + hh * DK;
+      const float mul = grp == 0 ? a.scale_log2 : 1.f;
 #pragma unroll
       for (int c = 0; c < 32; c += 4) {
         float4 x = i < L ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
         v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
       }
-      if (half == 1) {
+      if (grp == 1) {
         float dl = 0.f;
         if (i < L) {
           const float* orow = a.o + (row0 + i) * a.ldo + hh * DK;
@@ -405,7 +449,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
       }
 #pragma unroll
       for (int c = 0; c < 32; ++c) lo[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xffffe000u);
-      const uint32_t tr = half == 0 ? T_Q : T_DO, tl = half == 0 ? T_QL : T_DOL;
+      const uint32_t tr = grp == 0 ? A_Q : A_DO, tl = grp == 0 ? A_QL : A_DOL;
       float t16[16];
 #pragma unroll
       for (int part = 0; part < 2; ++part) {
@@ -421,70 +465,71 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
     // ---- TF32 residual copies of the three K/V tiles
     mbar_wait(smem_u32(&load_bar), 0);
     split_lo_bytes(gen + oKk, gen + oKkl, (int)(kv_bytes / 16), tid, NSW * 32);
-    split_lo_bytes(gen + oKm, gen + oKml, (int)(kv_bytes / 16), tid, NSW * 32);
     split_lo_bytes(gen + oVk, gen + oVkl, (int)(kv_bytes / 16), tid, NSW * 32);
+    split_lo_bytes(gen + oKm, gen + oKml, (int)(kv_bytes / 16), tid, NSW * 32);
     fence_proxy_async();
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&split_bar));
-    named_bar_sync(1, NSW * 32);  // padk, xdelta visible
+    named_bar_sync(1, NSW * 32);  // kvalid, xdelta visible
 
+    // rows beyond the sequence hold zero operands: mx = 0, inv = 0 makes every dS of theirs an exact zero
     float mx = 0.f, inv = 0.f;
     if (i < L) {
       const int64_t sr = ((int64_t)bh * L + i) * 2;
       mx = a.stats[sr];
       inv = a.stats[sr + 1];
     }
-    const float delta = xdelta[rl];
-    const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
-    for (int hf = 0; hf < NH; ++hf) {
-      const int k0 = hf * HALF, nh = (hf == 0 ? (LPK < HALF ? LPK : HALF) : LPK - HALF);
-      const int cbeg = half == 0 ? 0 : 64, cend = half == 0 ? (nh < 64 ? nh : 64) : nh;
-      mbar_wait(smem_u32(&s_full[hf]), 0);
+    const float ndelta = -xdelta[rl];
+    const uint32_t thr_hi = a.thr16 << 16;
+    const uint32_t tS = tmem + lane_sel + (uint32_t)grp * A_GRP, tP = tS + A_DP;
+    for (int c = grp; c < NCH; c += 2) {
+      const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+      mbar_wait(smem_u32(&s_full[grp]), (c >> 1) & 1);
       tc_fence_after();
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float sv[16], dp[16], lo[16];
-        tmem_ld16(tmem + lane_sel + T_S + (uint32_t)c0, sv);
-        tmem_ld16(tmem + lane_sel + T_DP + (uint32_t)c0, dp);
+      for (int c0 = 0; c0 < nh; c0 += 16) {
+        uint32_t rs[16], rd[16];
+        tmem_ld16_issue(tS + (uint32_t)c0, rs);
+        tmem_ld16_issue(tP + (uint32_t)c0, rd);
         const int j0 = k0 + c0;
-        uint4 calls[4];
-        if (a.thr16) {
-          uint4 c0r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, tile, g, rh * 2 + 0, j0 >> 4));
-          uint4 c1r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, tile, g, rh * 2 + 1, j0 >> 4));
-          uint4 o0, o1;
-          o0.x = __shfl_xor_sync(0xffffffffu, c0r.x, 8); o0.y = __shfl_xor_sync(0xffffffffu, c0r.y, 8);
-          o0.z = __shfl_xor_sync(0xffffffffu, c0r.z, 8); o0.w = __shfl_xor_sync(0xffffffffu, c0r.w, 8);
-          o1.x = __shfl_xor_sync(0xffffffffu, c1r.x, 8); o1.y = __shfl_xor_sync(0xffffffffu, c1r.y, 8);
-          o1.z = __shfl_xor_sync(0xffffffffu, c1r.z, 8); o1.w = __shfl_xor_sync(0xffffffffu, c1r.w, 8);
-          calls[0] = rh ? o0 : c0r; calls[1] = rh ? o1 : c1r; calls[2] = rh ? c0r : o0; calls[3] = rh ? c1r : o1;
+        KeepWords kw;
+        if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM reads
+        float kv[16];
+#pragma unroll
+        for (int jj = 0; jj < 16; jj += 4) {
+          const float4 t = ld4(kvalid + j0 + jj);
+          kv[jj] = t.x; kv[jj + 1] = t.y; kv[jj + 2] = t.z; kv[jj + 3] = t.w;
         }
+        tmem_ld_wait16(rs);
+        tmem_ld_wait16(rd);
+        float sv[16], lo[16];
 #pragma unroll
         for (int jj = 0; jj < 16; ++jj) {
-          const int j = j0 + jj;
-          const bool pad = padk[j] != 0.f;
-          const float x = pad ? RBM_PADFILL : sv[jj];
-          const bool dead = i >= L || j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i);
-          const float p = dead ? 0.f : ex2(x - mx) * inv;
-          float mk = 1.f;
-          if (a.thr16) mk = rbm_attn_field(calls[(jj & 7) >> 1], rh * 4 + (jj & 1) * 2 + ((jj >> 3) & 1)) >= a.thr16 ? a.inv_keep : 0.f;
-          const float ds = pad ? 0.f : p * (mk * dp[jj] - delta);  // no score gradient through a padded key
+          const float p = ex2(__uint_as_float(rs[jj]) - mx) * inv;
+          const float dpv = __uint_as_float(rd[jj]);
+          float t;
+          if (DROP) t = attn_keep_bit(kw, jj, thr_hi) ? fmaf(dpv, a.inv_keep, ndelta) : ndelta;
+          else t = dpv + ndelta;
+          bool live = kv[jj] != 0.f;  // no score gradient through a padded key (its probability is an exact zero)
+          if (CAUSAL) live = live && (j0 + jj <= i);
+          const float ds = live ? p * t : 0.f;
           sv[jj] = ds;
           lo[jj] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
         }
-        tmem_st16(tmem + lane_sel + T_S + (uint32_t)c0, sv);
-        tmem_st16(tmem + lane_sel + T_DP + (uint32_t)c0, lo);
+        tmem_st16(tS + (uint32_t)c0, sv);
+        tmem_st16(tP + (uint32_t)c0, lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ds_full[hf]));
+      if (lane == 0) mbar_arrive(smem_u32(&ds_full[grp]));
     }
     mbar_wait(smem_u32(&dq_full), 0);
     tc_fence_after();
     float o[16];
-    tmem_ld16(tmem + lane_sel + T_DQ + (uint32_t)(half * 16), o);
+    tmem_ld16(tmem + lane_sel + A_DQ + (uint32_t)(grp * 16), o);
     if (i < L) {
-      float* dst = a.dq + (row0 + i) * a.lddq + hh * DK + half * 16;
+      float* dst = a.dq + (row0 + i) * a.lddq + hh * DK + grp * 16;
 #pragma unroll
       for (int jj = 0; jj < 16; jj += 4)
         st4(dst + jj, make_float4(o[jj] * a.scale, o[jj + 1] * a.scale, o[jj + 2] * a.scale, o[jj + 3] * a.scale));
@@ -855,7 +900,7 @@ int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t 
 
 bool rbm_attn_bwd_dq_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, int64_t lddo, int64_t lddq,
                                   const void* q, const void* k, const void* v, const void* o, const void* dout, const void* dq) {
-  if (!tc_enabled() || dk != DK || L < 1 || L > 224) return false;  // TMEM: two key halves of <= 112 columns
+  if (!tc_enabled() || dk != DK || L < 1 || L > 256) return false;
   if (ldq % 4 || ldk % 4 || ldv % 4 || ldo % 4 || lddo % 4 || lddq % 4) return false;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)o | (uintptr_t)dout | (uintptr_t)dq) & 15) return false;
   return get_encode() != nullptr;
@@ -879,14 +924,22 @@ int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64
   size_t smem = (size_t)6 * LPK * ROWB + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
     if (e != cudaSuccess) {
       rbm_set_error("rbm_attn_bwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  attn_bwd_dq_tc_kernel<<<B * h * NT, 64 + 32 * NSW, smem, st>>>(mapKk, mapKm, mapVk, a);
+  const bool causal = mask_mode == RBM_MASK_CAUSAL, drop = a.thr16 != 0;
+  const int nthr = 64 + 32 * NSW, grid = B * h * NT;
+  if (causal && drop) attn_bwd_dq_tc_kernel<true, true><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
+  else if (causal) attn_bwd_dq_tc_kernel<true, false><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
+  else if (drop) attn_bwd_dq_tc_kernel<false, true><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
+  else attn_bwd_dq_tc_kernel<false, false><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
   RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dq)");
   return 0;
 }
