@@ -9,6 +9,7 @@
 //     O = P.V              tcgen05.mma with the A operand read from TMEM, V MN-major from SMEM -> TMEM [128 x 32]
 // Every product is 3xTF32-compensated (raw/lo copies of Q, K, V in SMEM, of P in TMEM): fp32-level accuracy.
 // Scores/probabilities never leave the SM.  Shapes outside (d_k == 32, L <= 240) use the mma.sync kernels (attention.cu).
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -86,7 +87,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __g
   const uint32_t tS = tmem, tPl = tmem + (uint32_t)LPK, tO = tmem + (uint32_t)(2 * LPK);
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t bar = smem_u32(&load_bar);
       if (a.dbg & 16) {
         mbar_arrive(bar);
@@ -98,7 +99,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __g
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idS = make_idesc_tf32_ex(128, LPK, 0, 0);  // both operands K-major
       const uint32_t idO = make_idesc_tf32_ex(128, DK, 0, 1);   // A from TMEM, V MN-major
       mbar_wait(smem_u32(&load_bar), 0);
@@ -297,59 +298,117 @@ __device__ __forceinline__ bool attn_keep_bit(const KeepWords& k, int jj, uint32
   return (jj & 8) ? (w >= thr_hi) : ((w << 16) >= thr_hi);
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Bring-up timeline (RBM_TC_ATTN_TRACE=<file>): CTA 0 appends (clock64, event, argument) records to a device buffer that
+// the launcher dumps after the kernel.  trace == nullptr (the default) compiles down to one predictable branch.
+// ---------------------------------------------------------------------------------------------------------
+constexpr int TRACE_WARPS = 16, TRACE_PER_WARP = 500, TRACE_CAP = TRACE_WARPS * TRACE_PER_WARP;
+// every warp owns a slice of the buffer and a private counter: a record costs one clock read and one plain store
+__device__ __forceinline__ void tc_trace(unsigned long long* trace, int& cnt, int ev, int arg) {
+  if (trace != nullptr && blockIdx.x == 0 && (threadIdx.x & 31) == 0 && cnt < TRACE_PER_WARP) {
+    const int w = (threadIdx.x >> 5) % TRACE_WARPS;
+    trace[1 + w * TRACE_PER_WARP + cnt] = ((unsigned long long)clock64() << 24) | ((unsigned long long)(ev & 0xff) << 16) | (unsigned)(arg & 0xffff);
+    ++cnt;
+  }
+}
+static unsigned long long* trace_begin() {
+  const char* path = getenv("RBM_TC_ATTN_TRACE");
+  if (!path) return nullptr;
+  unsigned long long* buf = nullptr;
+  if (cudaMalloc(&buf, (TRACE_CAP + 1) * sizeof(unsigned long long)) != cudaSuccess) return nullptr;
+  cudaMemset(buf, 0, (TRACE_CAP + 1) * sizeof(unsigned long long));
+  return buf;
+}
+static void trace_end(unsigned long long* buf, const char* tag, cudaStream_t st) {
+  if (!buf) return;
+  cudaStreamSynchronize(st);
+  static unsigned long long host[TRACE_CAP + 1];
+  cudaMemcpy(host, buf, sizeof(host), cudaMemcpyDeviceToHost);
+  cudaFree(buf);
+  char name[512];
+  snprintf(name, sizeof(name), "%s.%s", getenv("RBM_TC_ATTN_TRACE"), tag);
+  if (FILE* f = fopen(name, "wb")) {
+    fwrite(host, sizeof(unsigned long long), TRACE_CAP + 1, f);
+    fclose(f);
+  }
+}
+
 // =====================================================================================================
-// Backward pass A (dQ and delta) on the tensor path, one CTA per (sequence, head, 128-query tile).
-//   SMEM: K (K-major), K (MN-major, 32-byte-atom swizzle), V (K-major), each with its TF32 residual copy.
-//   Keys are cut into chunks of <= 64 (multiples of 16).  Two groups of four softmax warps (one warp per TMEM lane
-//   quarter, one thread per query row) take the chunks alternately, each group with its own S / dP accumulator pair:
-//   while one group turns (S, dP) into dS, the tensor core is already producing the other group's next chunk and
-//   consuming the previous dS (dQ += dS.K, dS raw/residual read back from TMEM as the A operand).
-//   TMEM columns: group g: S [128g, +64) | dP [128g + 64, +64);  Q raw,lo [256,320) | dO raw,lo [320,384) | dQ [384,416)
-//   delta_i = <dO_i, O_i> is also written for pass B.
+// Backward pass A (dQ and delta) on the tensor path: a persistent kernel, one CTA per SM walking the work items
+// (sequence, head, 128-query tile).  Every stage of the pipeline belongs to its own warps, and all of them run ahead
+// across item boundaries, so TMA latency, operand staging, tensor work, softmax arithmetic and the dQ write-back of
+// neighbouring items overlap:
+//   warp 0      TMA: keys stream in chunks of <= 64 (multiples of 16) through a 4-stage ring; a stage holds the chunk's
+//               K rows twice (K-major for S = Q.K^T, MN-major / 32-byte-atom swizzle for dQ += dS.K) and its V rows
+//   warps 14-15 derive the TF32 residual copy of every staged tile (3xTF32)
+//   warp 1      issues tcgen05.mma: S and dP of a chunk into the accumulator pair of the chunk's softmax group, then --
+//               once that group has replaced them by dS (raw + residual) -- dQ += dS.K with dS as the TMEM A operand
+//   warps 2-9   two softmax groups (one warp per TMEM lane quarter, one thread per query row) taking chunks alternately
+//   warps 10-13 per item: Q and dO rows (raw + residual) into TMEM as A operands, delta_i = <dO_i, O_i>, key validity;
+//               and the finished dQ accumulator (double-buffered) out to HBM
+//   TMEM columns: group g: S [128g, +64) | dP [128g + 64, +64);  Q raw,lo [256,320) | dO raw,lo [320,384) |
+//                 dQ [384 + 64*(item & 1), +64): columns [0,32) dS.K + dS_lo.K, [32,64) dS.K_lo, added on the way out
 // =====================================================================================================
-constexpr int CW = 64;  // columns of one chunk accumulator
+constexpr int CW = 64;        // columns of one chunk accumulator / key rows of one staged tile
+constexpr int A_NSTG = 3;
+constexpr uint32_t A_TILE = CW * ROWB;      // 8 KB
+constexpr uint32_t A_STAGE = 6 * A_TILE;    // Kk | Vk | Km raw, then the three residual copies
 constexpr uint32_t A_GRP = 128, A_DP = 64, A_Q = 256, A_QL = 288, A_DO = 320, A_DOL = 352, A_DQ = 384;
+constexpr int A_THREADS = 512;
+constexpr uint32_t A_ROWS = 128 * ROWB;     // 16 KB: the Q / dO / O rows of one 128-query tile
 
 struct TcBwdArgs {
   const float *q, *o, *dout, *stats;
   float *dq, *delta;
   int64_t ldq, ldo, lddo, lddq;
   const int64_t* tok;
-  int L, LPK, h, NT, mask_mode;
+  int L, LPK, h, NT, mask_mode, items;
   float scale, scale_log2;
   uint32_t thr16;
   float inv_keep;
   uint64_t seed, site;
+  unsigned long long* trace;
 };
 
 template <bool CAUSAL, bool DROP>
-__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapKk,
-                                                                          const __grid_constant__ CUtensorMap mapKm,
-                                                                          const __grid_constant__ CUtensorMap mapVk, const TcBwdArgs a) {
+__global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap mapKk,
+                                                                      const __grid_constant__ CUtensorMap mapKm,
+                                                                      const __grid_constant__ CUtensorMap mapVk,
+                                                                      const __grid_constant__ CUtensorMap mapQ,
+                                                                      const __grid_constant__ CUtensorMap mapDO,
+                                                                      const __grid_constant__ CUtensorMap mapO, const TcBwdArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t load_bar, split_bar, s_full[2], ds_full[2], dq_full;
+  __shared__ __align__(8) uint64_t full_bar[A_NSTG], split_bar[A_NSTG], empty_bar[A_NSTG], s_full[2], ds_full[2], ops_free, ops_full,
+      dq_full[2], dq_free[2], rows_full, rows_free;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ __align__(16) float kvalid[256];  // 1 = key takes part (inside the sequence and not a padding token)
-  __shared__ float xdelta[128];
+  __shared__ __align__(16) float kvalid[2][256];  // 1 = key takes part (inside the sequence and not a padding token)
+  __shared__ float xdelta[2][128];
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x / a.NT, mt = blockIdx.x % a.NT;
-  const int b = bh / a.h, hh = bh % a.h;
   const int L = a.L, LPK = a.LPK;
   const int NU = LPK >> 4, NCH = (NU + 3) >> 2;  // 16-key units; chunks of <= 4 units, sizes as even as possible
-  const uint32_t kv_bytes = (uint32_t)LPK * ROWB;
+  const int n_items = a.items > (int)blockIdx.x ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const int n_chunks = n_items * NCH;
+  int tcnt = 0;  // bring-up timeline cursor of this warp
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t oKk = 0, oKkl = kv_bytes, oKm = 2 * kv_bytes, oKml = 3 * kv_bytes, oVk = 4 * kv_bytes, oVkl = 5 * kv_bytes;
 
   if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&load_bar), 1);
-    mbar_init(smem_u32(&split_bar), NSW);
+    for (int i = 0; i < A_NSTG; ++i) {
+      mbar_init(smem_u32(&full_bar[i]), 1);
+      mbar_init(smem_u32(&split_bar[i]), 2);
+      mbar_init(smem_u32(&empty_bar[i]), 1);
+    }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&ds_full[i]), NSW / 2);
+      mbar_init(smem_u32(&ds_full[i]), 4);
+      mbar_init(smem_u32(&dq_full[i]), 1);
+      mbar_init(smem_u32(&dq_free[i]), 4);
     }
-    mbar_init(smem_u32(&dq_full), 1);
+    mbar_init(smem_u32(&ops_free), 1);
+    mbar_init(smem_u32(&ops_full), 4);
+    mbar_init(smem_u32(&rows_full), 1);
+    mbar_init(smem_u32(&rows_free), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
@@ -359,25 +418,96 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
   const uint32_t tmem = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
-      const uint32_t bar = smem_u32(&load_bar);
-      mbar_expect_tx(bar, 3 * kv_bytes);
-      tma_load_3d(smem_base + oKk, &mapKk, bar, hh * DK, 0, b);
-      tma_load_3d(smem_base + oVk, &mapVk, bar, hh * DK, 0, b);
-      tma_load_3d(smem_base + oKm, &mapKm, bar, hh * DK, 0, b);
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapKk) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapKm) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapVk) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapDO) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapO) : "memory");
+      // the Q / dO / O rows of an item land in one single-buffered 48 KB area (the operand warps copy them to registers
+      // as soon as they arrive); a tile's rows beyond the sequence are zero-filled by TMA
+      auto issue_rows = [&](int n) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int bh = item / a.NT, mt = item - bh * a.NT, b = bh / a.h, hh = bh % a.h;
+        if (n >= 1) mbar_wait(smem_u32(&rows_free), (n - 1) & 1);
+        const uint32_t bar = smem_u32(&rows_full), dst = smem_base + A_NSTG * A_STAGE;
+        mbar_expect_tx(bar, 3 * A_ROWS);
+        tma_load_3d(dst, &mapQ, bar, hh * DK, mt * 128, b);
+        tma_load_3d(dst + A_ROWS, &mapDO, bar, hh * DK, mt * 128, b);
+        tma_load_3d(dst + 2 * A_ROWS, &mapO, bar, hh * DK, mt * 128, b);
+      };
+      if (n_items > 0) issue_rows(0);
+      int g = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int bh = item / a.NT, b = bh / a.h, hh = bh % a.h;
+        for (int c = 0; c < NCH; ++c, ++g) {
+          const int s = g % A_NSTG, k0 = ((c * NU) / NCH) << 4;
+          if (g >= A_NSTG) mbar_wait(smem_u32(&empty_bar[s]), ((g / A_NSTG) - 1) & 1);
+          const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * A_STAGE;
+          mbar_expect_tx(bar, 3 * A_TILE);
+          tma_load_3d(sa, &mapKk, bar, hh * DK, k0, b);
+          tma_load_3d(sa + A_TILE, &mapVk, bar, hh * DK, k0, b);
+          tma_load_3d(sa + 2 * A_TILE, &mapKm, bar, hh * DK, k0, b);
+          tc_trace(a.trace, tcnt, 10, g);
+        }
+        if (n + 1 < n_items) issue_rows(n + 1);
+      }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
-      mbar_wait(smem_u32(&load_bar), 0);
-      mbar_wait(smem_u32(&split_bar), 0);
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    // The CTA owns all 512 TMEM columns, so the allocation starts at column 0, lane 0: using the literal keeps every
+    // operand of the issue loop on the uniform datapath (a value read back from shared memory would not be).
+    if (tmem != 0) __trap();
+    if (elect_one()) {
+    constexpr uint32_t tmem = 0;
+    // All 32 lanes run the loop in lockstep; one elected lane issues each tcgen05 instruction.  A tcgen05.mma of this
+    // size costs the issuing warp (and the pipe) ~64 cycles whatever its N <= 128, so the count of instructions is what
+    // matters: the two products that share the A operand dS_raw run as one N = 64 instruction against [K_raw | K_lo].
+    const uint32_t idQ2 = make_idesc_tf32_ex(128, 2 * DK, 0, 1);  // dQ: A from TMEM, [K | K_lo] MN-major, N = 64
+    const uint32_t idQ1 = make_idesc_tf32_ex(128, DK, 0, 1);
+    auto issue_dq = [&](int g) {
+      const int n = g / NCH, c = g - n * NCH, s = g % A_NSTG;
+      const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+      const uint32_t tS = tmem + (uint32_t)(g & 1) * A_GRP, tP = tS + A_DP, tD = tmem + A_DQ + (uint32_t)(n & 1) * (2 * DK);
+      const uint32_t sa = smem_base + s * A_STAGE;
+      tc_trace(a.trace, tcnt, 1, g);
+      mbar_wait(smem_u32(&ds_full[g & 1]), (g >> 1) & 1);
+      if (c == 0 && n >= 2) mbar_wait(smem_u32(&dq_free[n & 1]), ((n >> 1) - 1) & 1);
       tc_fence_after();
-      const uint32_t idQ = make_idesc_tf32_ex(128, DK, 0, 1);  // dQ: A from TMEM, K MN-major
-      auto issue_sdp = [&](int c) {
+      tc_trace(a.trace, tcnt, 2, g);
+      for (int kk = 0; kk < nh / 8; ++kk) {
+        const uint64_t dKm2 = make_sw128_desc_mn(sa + 2 * A_TILE + kk * 1024, 3 * A_TILE);  // second MN block = the residual tile
+        const uint64_t dKm = make_sw128_desc_mn(sa + 2 * A_TILE + kk * 1024, 0);
+        umma_tf32_ts(tD, tS + kk * 8, dKm2, idQ2, (c | kk) != 0);  // [dS.K | dS.K_lo]
+        umma_tf32_ts(tD, tP + kk * 8, dKm, idQ1, 1);               // dS_lo.K
+      }
+      umma_commit(smem_u32(&empty_bar[s]));
+      if (c == NCH - 1) umma_commit(smem_u32(&dq_full[n & 1]));
+      tc_trace(a.trace, tcnt, 3, g);
+    };
+    int g = 0;
+    for (int n = 0; n < n_items; ++n) {
+      for (int c = 0; c < NCH; ++c, ++g) {
+        if (g >= 2) issue_dq(g - 2);  // frees this group's accumulators (the tensor pipe runs in order)
+        const int s = g % A_NSTG;
         const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
-        const uint32_t tS = tmem + (uint32_t)(c & 1) * A_GRP, tP = tS + A_DP;
+        if (c == 0) {
+          tc_trace(a.trace, tcnt, 12, n);
+          mbar_wait(smem_u32(&ops_full), n & 1);
+          tc_trace(a.trace, tcnt, 13, n);
+        }
+        mbar_wait(smem_u32(&full_bar[s]), (g / A_NSTG) & 1);
+        mbar_wait(smem_u32(&split_bar[s]), (g / A_NSTG) & 1);
+        tc_fence_after();
+        tc_trace(a.trace, tcnt, 4, g);
+        const uint32_t tS = tmem + (uint32_t)(g & 1) * A_GRP, tP = tS + A_DP;
         const uint32_t idS = make_idesc_tf32_ex(128, nh, 0, 0);
-        const uint64_t dK = make_sw128_desc(smem_base + oKk + k0 * ROWB), dKl = make_sw128_desc(smem_base + oKkl + k0 * ROWB);
-        const uint64_t dV = make_sw128_desc(smem_base + oVk + k0 * ROWB), dVl = make_sw128_desc(smem_base + oVkl + k0 * ROWB);
+        const uint32_t sa = smem_base + s * A_STAGE;
+        const uint64_t dK = make_sw128_desc(sa), dKl = make_sw128_desc(sa + 3 * A_TILE);
+        const uint64_t dV = make_sw128_desc(sa + A_TILE), dVl = make_sw128_desc(sa + 4 * A_TILE);
 #pragma unroll
         for (int k = 0; k < DK / 8; ++k) {
           const uint64_t o = (uint64_t)(k * 2);
@@ -392,147 +522,201 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dq_tc_kernel(const 
           umma_tf32_ts(tP, tmem + A_DOL + k * 8, dV + o, idS, 1);
           umma_tf32_ts(tP, tmem + A_DO + k * 8, dV + o, idS, 1);
         }
-        umma_commit(smem_u32(&s_full[c & 1]));
-      };
-      auto issue_dq = [&](int c) {
-        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
-        const uint32_t tS = tmem + (uint32_t)(c & 1) * A_GRP, tP = tS + A_DP;
-        mbar_wait(smem_u32(&ds_full[c & 1]), (c >> 1) & 1);
-        tc_fence_after();
-        for (int kk = 0; kk < nh / 8; ++kk) {
-          const uint64_t dKm = make_sw128_desc_mn(smem_base + oKm + (k0 + kk * 8) * ROWB, 0);
-          const uint64_t dKml = make_sw128_desc_mn(smem_base + oKml + (k0 + kk * 8) * ROWB, 0);
-          umma_tf32_ts(tmem + A_DQ, tS + kk * 8, dKml, idQ, (c | kk) != 0);
-          umma_tf32_ts(tmem + A_DQ, tP + kk * 8, dKm, idQ, 1);
-          umma_tf32_ts(tmem + A_DQ, tS + kk * 8, dKm, idQ, 1);
-        }
-      };
-      for (int c = 0; c < NCH; ++c) {
-        if (c >= 2) issue_dq(c - 2);  // frees this group's accumulators (the tensor pipe runs in order)
-        issue_sdp(c);
+        umma_commit(smem_u32(&s_full[g & 1]));
+        if (c == NCH - 1) umma_commit(smem_u32(&ops_free));  // Q / dO of this item have been consumed
+        tc_trace(a.trace, tcnt, 5, g);
       }
-      for (int c = NCH >= 2 ? NCH - 2 : 0; c < NCH; ++c) issue_dq(c);
-      umma_commit(smem_u32(&dq_full));
+    }
+    for (int gg = n_chunks >= 2 ? n_chunks - 2 : 0; gg < n_chunks; ++gg) issue_dq(gg);
     }
     __syncwarp();
-  } else {
-    const int sw = warp - 2, q = warp & 3, grp = sw >> 2;
-    const int tid = sw * 32 + lane;
-    const int64_t row0 = (int64_t)b * L;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------------------------------ softmax groups
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const int rl = q * 32 + lane;
-    const int i = mt * 128 + rl;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int j = tid; j < 256; j += NSW * 32)
-      kvalid[j] = (j < L && !(a.mask_mode == RBM_MASK_KEYPAD && a.tok[row0 + j] == 0)) ? 1.f : 0.f;
-    // ---- operand rows into TMEM: group 0 takes Q (pre-scaled to the log2 domain), group 1 takes dO and delta
-    {
-      float v[32], lo[32];
-      const float* src = grp == 0 ? a.q + (row0 + i) * a.ldq + hh * DK : a.dout + (row0 + i) * a.lddo + hh * DK;
-      const float mul = grp == 0 ? a.scale_log2 : 1.f;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 x = i < L ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
-      }
-      if (grp == 1) {
-        float dl = 0.f;
-        if (i < L) {
-          const float* orow = a.o + (row0 + i) * a.ldo + hh * DK;
-#pragma unroll
-          for (int c = 0; c < 32; c += 4) {
-            float4 x = ld4(orow + c);
-            dl = fmaf(v[c], x.x, dl); dl = fmaf(v[c + 1], x.y, dl); dl = fmaf(v[c + 2], x.z, dl); dl = fmaf(v[c + 3], x.w, dl);
-          }
-          a.delta[(int64_t)bh * L + i] = dl;
-        }
-        xdelta[rl] = dl;
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) lo[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xffffe000u);
-      const uint32_t tr = grp == 0 ? A_Q : A_DO, tl = grp == 0 ? A_QL : A_DOL;
-      float t16[16];
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) t16[c] = v[part * 16 + c];
-        tmem_st16(tmem + lane_sel + tr + part * 16, t16);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) t16[c] = lo[part * 16 + c];
-        tmem_st16(tmem + lane_sel + tl + part * 16, t16);
-      }
-      tmem_st_wait();
-    }
-    // ---- TF32 residual copies of the three K/V tiles
-    mbar_wait(smem_u32(&load_bar), 0);
-    split_lo_bytes(gen + oKk, gen + oKkl, (int)(kv_bytes / 16), tid, NSW * 32);
-    split_lo_bytes(gen + oVk, gen + oVkl, (int)(kv_bytes / 16), tid, NSW * 32);
-    split_lo_bytes(gen + oKm, gen + oKml, (int)(kv_bytes / 16), tid, NSW * 32);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&split_bar));
-    named_bar_sync(1, NSW * 32);  // kvalid, xdelta visible
-
-    // rows beyond the sequence hold zero operands: mx = 0, inv = 0 makes every dS of theirs an exact zero
-    float mx = 0.f, inv = 0.f;
-    if (i < L) {
-      const int64_t sr = ((int64_t)bh * L + i) * 2;
-      mx = a.stats[sr];
-      inv = a.stats[sr + 1];
-    }
-    const float ndelta = -xdelta[rl];
     const uint32_t thr_hi = a.thr16 << 16;
     const uint32_t tS = tmem + lane_sel + (uint32_t)grp * A_GRP, tP = tS + A_DP;
-    for (int c = grp; c < NCH; c += 2) {
+    int cur_n = -1, bh = 0, i = 0;
+    bool warp_live = false;
+    float mx = 0.f, inv = 0.f, ndelta = 0.f;
+    for (int g = grp; g < n_chunks; g += 2) {
+      const int n = g / NCH, c = g - n * NCH;
       const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
-      mbar_wait(smem_u32(&s_full[grp]), (c >> 1) & 1);
-      tc_fence_after();
-      for (int c0 = 0; c0 < nh; c0 += 16) {
-        uint32_t rs[16], rd[16];
-        tmem_ld16_issue(tS + (uint32_t)c0, rs);
-        tmem_ld16_issue(tP + (uint32_t)c0, rd);
-        const int j0 = k0 + c0;
-        KeepWords kw;
-        if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM reads
-        float kv[16];
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 4) {
-          const float4 t = ld4(kvalid + j0 + jj);
-          kv[jj] = t.x; kv[jj + 1] = t.y; kv[jj + 2] = t.z; kv[jj + 3] = t.w;
+      const bool new_item = n != cur_n;
+      if (new_item) {  // the row statistics do not depend on the barrier: fetch them ahead of the wait
+        cur_n = n;
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        bh = item / a.NT;
+        const int mt = item - bh * a.NT;
+        i = mt * 128 + rl;
+        warp_live = mt * 128 + q * 32 < L;  // a warp whose 32 rows all lie beyond the sequence has nothing to do
+        // rows beyond the sequence hold zero operands: mx = 0, inv = 0 makes every dS of theirs an exact zero
+        mx = 0.f; inv = 0.f;
+        if (i < L) {
+          const int64_t sr = ((int64_t)bh * L + i) * 2;
+          mx = a.stats[sr];
+          inv = a.stats[sr + 1];
         }
-        tmem_ld_wait16(rs);
-        tmem_ld_wait16(rd);
-        float sv[16], lo[16];
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const float p = ex2(__uint_as_float(rs[jj]) - mx) * inv;
-          const float dpv = __uint_as_float(rd[jj]);
-          float t;
-          if (DROP) t = attn_keep_bit(kw, jj, thr_hi) ? fmaf(dpv, a.inv_keep, ndelta) : ndelta;
-          else t = dpv + ndelta;
-          bool live = kv[jj] != 0.f;  // no score gradient through a padded key (its probability is an exact zero)
-          if (CAUSAL) live = live && (j0 + jj <= i);
-          const float ds = live ? p * t : 0.f;
-          sv[jj] = ds;
-          lo[jj] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
-        }
-        tmem_st16(tS + (uint32_t)c0, sv);
-        tmem_st16(tP + (uint32_t)c0, lo);
       }
-      tmem_st_wait();
+      mbar_wait(smem_u32(&s_full[grp]), (g >> 1) & 1);
+      tc_fence_after();
+      tc_trace(a.trace, tcnt, 6, g * 4 + q);
+      if (new_item) ndelta = -xdelta[n & 1][rl];
+      if (warp_live) {
+        const float* kvp = kvalid[n & 1];
+        for (int c0 = 0; c0 < nh; c0 += 16) {
+          uint32_t rs[16], rd[16];
+          tmem_ld16_issue(tS + (uint32_t)c0, rs);
+          tmem_ld16_issue(tP + (uint32_t)c0, rd);
+          const int j0 = k0 + c0;
+          KeepWords kw;
+          if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM reads
+          float kv[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; jj += 4) {
+            const float4 t = ld4(kvp + j0 + jj);
+            kv[jj] = t.x; kv[jj + 1] = t.y; kv[jj + 2] = t.z; kv[jj + 3] = t.w;
+          }
+          tmem_ld_wait16(rs);
+          tmem_ld_wait16(rd);
+          float sv[16], lo[16];
+#pragma unroll
+          for (int jj = 0; jj < 16; ++jj) {
+            const float p = ex2(__uint_as_float(rs[jj]) - mx) * inv;
+            const float dpv = __uint_as_float(rd[jj]);
+            float t;
+            if (DROP) t = attn_keep_bit(kw, jj, thr_hi) ? fmaf(dpv, a.inv_keep, ndelta) : ndelta;
+            else t = dpv + ndelta;
+            bool live = kv[jj] != 0.f;  // no score gradient through a padded key (its probability is an exact zero)
+            if (CAUSAL) live = live && (j0 + jj <= i);
+            const float ds = live ? p * t : 0.f;
+            sv[jj] = ds;
+            lo[jj] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
+          }
+          tmem_st16(tS + (uint32_t)c0, sv);
+          tmem_st16(tP + (uint32_t)c0, lo);
+        }
+        tmem_st_wait();
+      }
       tc_fence_before();
       __syncwarp();
+      tc_trace(a.trace, tcnt, 7, g * 4 + q);
       if (lane == 0) mbar_arrive(smem_u32(&ds_full[grp]));
     }
-    mbar_wait(smem_u32(&dq_full), 0);
-    tc_fence_after();
-    float o[16];
-    tmem_ld16(tmem + lane_sel + A_DQ + (uint32_t)(grp * 16), o);
-    if (i < L) {
-      float* dst = a.dq + (row0 + i) * a.lddq + hh * DK + grp * 16;
+  } else if (warp < 14) {
+    // ------------------------------------------------------------------------------------------ operand / dQ warps
+    const int q = warp & 3, rl = q * 32 + lane, t128 = (warp - 10) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float qv[32], dv[32];
+    float dl = 0.f;
+    bool kval0 = false, kval1 = false;  // validity of keys t128 and t128 + 128 of the item being staged
+    // this thread's Q, dO, O rows out of the TMA tiles (128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7))
+    auto load_rows = [&](int n) {
+      {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int b = (item / a.NT) / a.h;
+        const bool keypad = a.mask_mode == RBM_MASK_KEYPAD;
+        kval0 = t128 < L && !(keypad && a.tok[(int64_t)b * L + t128] == 0);
+        kval1 = t128 + 128 < L && !(keypad && a.tok[(int64_t)b * L + t128 + 128] == 0);
+      }
+      mbar_wait(smem_u32(&rows_full), n & 1);
+      const float* qs = reinterpret_cast<const float*>(gen + A_NSTG * A_STAGE) + rl * DK;
+      const float* ds = qs + A_ROWS / 4;
+      const float* os = ds + A_ROWS / 4;
+      dl = 0.f;
 #pragma unroll
-      for (int jj = 0; jj < 16; jj += 4)
-        st4(dst + jj, make_float4(o[jj] * a.scale, o[jj + 1] * a.scale, o[jj + 2] * a.scale, o[jj + 3] * a.scale));
+      for (int c = 0; c < 32; c += 4) {
+        const int sc = ((c >> 2) ^ (rl & 7)) << 2;
+        const float4 x = ld4(qs + sc), y = ld4(ds + sc), z = ld4(os + sc);
+        qv[c] = x.x * a.scale_log2; qv[c + 1] = x.y * a.scale_log2; qv[c + 2] = x.z * a.scale_log2; qv[c + 3] = x.w * a.scale_log2;
+        dv[c] = y.x; dv[c + 1] = y.y; dv[c + 2] = y.z; dv[c + 3] = y.w;
+        dl = fmaf(y.x, z.x, dl); dl = fmaf(y.y, z.y, dl); dl = fmaf(y.z, z.z, dl); dl = fmaf(y.w, z.w, dl);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rows_free));
+    };
+    auto store_dq = [&](int n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, mt = item - bh * a.NT, b = bh / a.h, hh = bh - b * a.h;
+      const int i = mt * 128 + rl;
+      mbar_wait(smem_u32(&dq_full[n & 1]), (n >> 1) & 1);
+      tc_fence_after();
+      float o[32];
+      {  // dQ = [dS.K + dS_lo.K] + [dS.K_lo]
+        float o1[32];
+        tmem_ld32(tmem + lane_sel + A_DQ + (uint32_t)(n & 1) * (2 * DK), o);
+        tmem_ld32(tmem + lane_sel + A_DQ + (uint32_t)(n & 1) * (2 * DK) + DK, o1);
+#pragma unroll
+        for (int jj = 0; jj < 32; ++jj) o[jj] += o1[jj];
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&dq_free[n & 1]));
+      if (q == 0) tc_trace(a.trace, tcnt, 9, n);
+      if (i < L) {
+        float* dst = a.dq + ((int64_t)b * L + i) * a.lddq + hh * DK;
+#pragma unroll
+        for (int jj = 0; jj < 32; jj += 4)
+          st4(dst + jj, make_float4(o[jj] * a.scale, o[jj + 1] * a.scale, o[jj + 2] * a.scale, o[jj + 3] * a.scale));
+      }
+    };
+    if (n_items > 0) load_rows(0);
+    for (int n = 0; n < n_items; ++n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, mt = item - bh * a.NT;
+      const int i = mt * 128 + rl;
+      // key validity of this item's sequence, delta of its rows
+      kvalid[n & 1][t128] = kval0 ? 1.f : 0.f;
+      kvalid[n & 1][t128 + 128] = kval1 ? 1.f : 0.f;
+      xdelta[n & 1][rl] = dl;
+      if (i < L) a.delta[(int64_t)bh * L + i] = dl;
+      if (q == 0) tc_trace(a.trace, tcnt, 14, n);
+      if (n >= 1) {
+        mbar_wait(smem_u32(&ops_free), (n - 1) & 1);  // every S / dP of the previous item has read its Q / dO
+        tc_fence_after();
+      }
+      if (q == 0) tc_trace(a.trace, tcnt, 15, n);
+      {
+        float t16[16];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = qv[part * 16 + c];
+          tmem_st16(tmem + lane_sel + A_Q + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = t16[c] - __uint_as_float(__float_as_uint(t16[c]) & 0xffffe000u);
+          tmem_st16(tmem + lane_sel + A_QL + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = dv[part * 16 + c];
+          tmem_st16(tmem + lane_sel + A_DO + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = t16[c] - __uint_as_float(__float_as_uint(t16[c]) & 0xffffe000u);
+          tmem_st16(tmem + lane_sel + A_DOL + part * 16, t16);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ops_full));
+      tc_trace(a.trace, tcnt, 8, n * 4 + q);
+      if (n + 1 < n_items) load_rows(n + 1);  // in flight while this item is being worked on
+      if (q == 0) tc_trace(a.trace, tcnt, 16, n);
+      if (n >= 1) store_dq(n - 1);
+    }
+    if (n_items > 0) store_dq(n_items - 1);
+  } else {
+    // ------------------------------------------------------------------------------------------ TF32 residual copies
+    const int tid = (warp - 14) * 32 + lane;  // warps 14, 15
+    for (int g = 0; g < n_chunks; ++g) {
+      const int s = g % A_NSTG;
+      mbar_wait(smem_u32(&full_bar[s]), (g / A_NSTG) & 1);
+      uint8_t* st = gen + (size_t)s * A_STAGE;
+      split_lo_bytes(st, st + 3 * A_TILE, (int)(3 * A_TILE / 16), tid, 64);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+      tc_trace(a.trace, tcnt, 11, g);
     }
   }
   tc_fence_before();
@@ -606,7 +790,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dkv_tc_kernel(const
   const uint32_t tmem = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int n = 0;
       for (int c = c_first; c < NC; ++c, ++n) {
         const int s = n & 1;
@@ -621,7 +805,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dkv_tc_kernel(const
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       mbar_wait(smem_u32(&kv_bar), 0);
       tc_fence_after();
       const uint32_t idA = make_idesc_tf32_ex(128, DK, 0, 1);  // dK / dV: A from TMEM, B MN-major, N = 32
@@ -911,9 +1095,10 @@ int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64
                               float* delta, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed, uint64_t site,
                               cudaStream_t st) {
   const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
-  CUtensorMap mapKk, mapKm, mapVk;
-  if (!encode_map3(&mapKk, k, B, L, h * DK, ldk, LPK, false) || !encode_map3(&mapKm, k, B, L, h * DK, ldk, LPK, true) ||
-      !encode_map3(&mapVk, v, B, L, h * DK, ldv, LPK, false)) {
+  CUtensorMap mapKk, mapKm, mapVk, mapQ, mapDO, mapO;
+  if (!encode_map3(&mapKk, k, B, L, h * DK, ldk, CW, false) || !encode_map3(&mapKm, k, B, L, h * DK, ldk, CW, true) ||
+      !encode_map3(&mapVk, v, B, L, h * DK, ldv, CW, false) || !encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) ||
+      !encode_map3(&mapDO, dout, B, L, h * DK, lddo, 128, false) || !encode_map3(&mapO, o, B, L, h * DK, ldo, 128, false)) {
     rbm_set_error("rbm_attn_bwd(tcgen05): cuTensorMapEncodeTiled failed");
     return -1;
   }
@@ -921,13 +1106,15 @@ int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64
   a.q = q; a.o = o; a.dout = dout; a.stats = stats; a.dq = dq; a.delta = delta; a.ldq = ldq; a.ldo = ldo; a.lddo = lddo; a.lddq = lddq;
   a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
-  size_t smem = (size_t)6 * LPK * ROWB + 1024;
+  a.items = B * h * NT;
+  a.trace = trace_begin();
+  const size_t smem = (size_t)A_NSTG * A_STAGE + 3 * A_ROWS + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dq_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       rbm_set_error("rbm_attn_bwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -935,12 +1122,13 @@ int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64
     attr_set = true;
   }
   const bool causal = mask_mode == RBM_MASK_CAUSAL, drop = a.thr16 != 0;
-  const int nthr = 64 + 32 * NSW, grid = B * h * NT;
-  if (causal && drop) attn_bwd_dq_tc_kernel<true, true><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
-  else if (causal) attn_bwd_dq_tc_kernel<true, false><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
-  else if (drop) attn_bwd_dq_tc_kernel<false, true><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
-  else attn_bwd_dq_tc_kernel<false, false><<<grid, nthr, smem, st>>>(mapKk, mapKm, mapVk, a);
+  const int grid = a.items < RBM_NUM_SMS ? a.items : RBM_NUM_SMS;
+  if (causal && drop) attn_bwd_dq_tc_kernel<true, true><<<grid, A_THREADS, smem, st>>>(mapKk, mapKm, mapVk, mapQ, mapDO, mapO, a);
+  else if (causal) attn_bwd_dq_tc_kernel<true, false><<<grid, A_THREADS, smem, st>>>(mapKk, mapKm, mapVk, mapQ, mapDO, mapO, a);
+  else if (drop) attn_bwd_dq_tc_kernel<false, true><<<grid, A_THREADS, smem, st>>>(mapKk, mapKm, mapVk, mapQ, mapDO, mapO, a);
+  else attn_bwd_dq_tc_kernel<false, false><<<grid, A_THREADS, smem, st>>>(mapKk, mapKm, mapVk, mapQ, mapDO, mapO, a);
   RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dq)");
+  trace_end(a.trace, "dq", st);
   return 0;
 }
 

@@ -122,7 +122,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
   const uint32_t tH = tmem, tHl = tmem + d, tS = tmem + 2 * d;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int c = 0; c < NC; ++c) {
         const int s = c % ns;
         if (c >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((c / ns) - 1) & 1);
@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0);
       mbar_wait(smem_u32(&h_bar), 0);
       tc_fence_after();
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
   const uint32_t tH = tmem, tHl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       for (int c = 0; c < NC; ++c) {
         const int s = c % ns;
         if (c >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((c / ns) - 1) & 1);
@@ -272,7 +272,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
       mbar_wait(smem_u32(&h_bar), 0);
       tc_fence_after();
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
   const uint32_t tW = tmem, tWl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       int n = 0;
       for (int c = sp; c < NC; c += S, ++n) {
         const int s = n % ns;
@@ -407,7 +407,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
       mbar_wait(smem_u32(&w_bar), 0);
       tc_fence_after();

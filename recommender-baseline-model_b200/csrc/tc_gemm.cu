@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       for (int kb = 0; kb < KB; ++kb) {
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(BM, p.BN);
       for (int kb = 0; kb < KB; ++kb) {
         const int s = kb % p.nstage;
@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       const uint32_t bb = smem_u32(&bfull_bar);
@@ -236,7 +236,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
         }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(BM, BN);
       mbar_wait(smem_u32(&bsplit_bar), 0);
       tc_fence_after();
@@ -447,7 +447,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       for (int g = 0; g < nst; ++g) {
@@ -462,7 +462,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32_ex(BM, p.K, 1, 1);
       const uint32_t idesc_b = make_idesc_tf32_ex(BM, DW_BIAS_N, 1, 1);
       const uint64_t ones = make_sw128_desc_mn(smem_base + off_ones, DW_BLK);

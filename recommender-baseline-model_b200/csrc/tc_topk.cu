@@ -70,7 +70,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
   const uint32_t tmem_d = tmem_base_slot;
 
   if (warp == 0) {
-    if (lane == 0) {
+    if (elect_one()) {
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapA) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       int g = 0, un = 0;
@@ -92,7 +92,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
       }
     }
   } else if (warp == 1) {
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t idesc = make_idesc_tf32(BM, BN);
       int g = 0, it = 0, un = 0;
       for (int u = blockIdx.x; u < n_units; u += gridDim.x, ++un) {
