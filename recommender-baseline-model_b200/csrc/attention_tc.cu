@@ -728,59 +728,84 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
 }
 
 // =====================================================================================================
-// Backward pass B (dK, dV) on the tensor path, one CTA per (sequence, head, 128-key tile); rows = keys.
-//   TMEM columns: K raw,lo [0,64) | V raw,lo [64,128) | S^T_c [128,192) | dP^T_c [192,256) | P~^T raw,lo [256,384)
-//                 | dK [384,416) | dV [416,448)
-//   Queries stream in chunks of 64 through a 2-stage TMA ring; every chunk arrives twice, as K-major tiles (B operand
-//   of S^T = K.Q^T and dP^T = V.dO^T) and as MN-major tiles (B operand of dK += dS^T.Q and dV += P~^T.dO), and gets
-//   TF32 residual copies from the softmax warps.  dS^T and its residual overwrite S^T / dP^T in place.
+// Backward pass B (dK, dV) on the tensor path: persistent, one CTA per SM walking the work items (sequence, head,
+// 128-key tile); accumulator rows = keys.  Same division of labour as pass A:
+//   warp 0      TMA: the item's K and V rows (one 128-row tile each) and the query stream -- sub-chunks of 32 queries
+//               through a 4-stage ring, every sub-chunk twice: Q and dO as K-major tiles (B operands of S^T = K.Q^T and
+//               dP^T = V.dO^T) and as MN-major tiles (B operands of dK += dS^T.Q and dV += P~^T.dO)
+//   warps 14-15 TF32 residual copy of every staged tile
+//   warp 1      tcgen05.mma issue (K and V rows are the TMEM A operands of S^T / dP^T; dS^T and P~^T, written back by
+//               the softmax warps, are the TMEM A operands of the dK / dV updates)
+//   warps 2-9   two softmax groups (one warp per TMEM lane quarter, one thread per key) taking sub-chunks alternately,
+//               each with its own S^T / dP^T / P~^T column block
+//   warps 10-13 per item: K and V rows (raw + residual) into TMEM, the row statistics (max, 1/sum, delta) of the
+//               sequence into shared memory; finished dK / dV out to HBM through a swizzled staging tile (coalesced)
+//   TMEM columns: K raw,lo [0,64) | V raw,lo [64,128) | group g at 128 + 128g: S^T [+0,32) dP^T [+32,64) P~ [+64,96)
+//                 P~_lo [+96,128) | dK [384,448) | dV [448,512); dK / dV hold [x.B + x_lo.B | x.B_lo], added on the way out
 // =====================================================================================================
-constexpr int QC = 64;                     // queries per chunk
-constexpr uint32_t CH_TILE = QC * ROWB;    // 8 KB: one [64 x 32] fp32 tile
-constexpr uint32_t CH_STAGE = 8 * CH_TILE; // Qk, Qm, dOk, dOm (raw) + the same four (lo)
-constexpr uint32_t B_K = 0, B_KL = 32, B_V = 64, B_VL = 96, B_ST = 128, B_DPT = 192, B_P = 256, B_PL = 320, B_DK = 384, B_DV = 416;
+constexpr int SQ = 32;                      // queries per sub-chunk / ring stage
+constexpr int B_NSTG = 4;
+constexpr uint32_t B_TILE = SQ * ROWB;      // 4 KB: one [32 x 32] fp32 tile
+constexpr uint32_t B_STAGE = 8 * B_TILE;    // Qk, Qm, dOk, dOm (raw) + the same four (residual)
+constexpr uint32_t B_ROWS = 128 * ROWB;     // 16 KB: the K (or V) rows of one 128-key tile
+constexpr uint32_t B_OUT = 32 * ROWB;       // 4 KB: staging tile for coalesced stores (two per operand warp: dK, dV)
+constexpr uint32_t B_K = 0, B_KL = 32, B_V = 64, B_VL = 96, B_GRP0 = 128, B_GRP = 128, B_DPT = 32, B_P = 64, B_PL = 96, B_DK = 384,
+                   B_DV = 448;
+constexpr int B_THREADS = 512;
 
 struct TcBwdKvArgs {
-  const float *k, *v, *stats, *delta;
+  const float *stats, *delta;
   float *dk, *dv;
-  int64_t ldk, ldv, lddk, lddv;
+  int64_t lddk, lddv;
   const int64_t* tok;
-  int L, LPK, h, NT, mask_mode;
+  int L, LPK, h, NT, mask_mode, items;
   float scale, scale_log2;
   uint32_t thr16;
   float inv_keep;
   uint64_t seed, site;
+  unsigned long long* trace;
 };
 
-__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQk,
-                                                                           const __grid_constant__ CUtensorMap mapQm,
-                                                                           const __grid_constant__ CUtensorMap mapOk,
-                                                                           const __grid_constant__ CUtensorMap mapOm, const TcBwdKvArgs a) {
+template <bool CAUSAL, bool DROP>
+__global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap mapQk,
+                                                                       const __grid_constant__ CUtensorMap mapQm,
+                                                                       const __grid_constant__ CUtensorMap mapOk,
+                                                                       const __grid_constant__ CUtensorMap mapOm,
+                                                                       const __grid_constant__ CUtensorMap mapK,
+                                                                       const __grid_constant__ CUtensorMap mapV, const TcBwdKvArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[2], split_bar[2], empty_bar[2], s_full[2], ds_full[2], kv_bar, done_bar;
+  __shared__ __align__(8) uint64_t full_bar[B_NSTG], split_bar[B_NSTG], empty_bar[B_NSTG], s_full[2], ds_full[2], ops_free, ops_full,
+      dkv_full, dkv_free, rows_full, rows_free;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float st_m[256], st_i[256], st_d[256];
+  __shared__ float st_m[2][256], st_i[2][256], st_d[2][256];  // per query: row max (log2 domain), 1/rowsum, delta
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int bh = blockIdx.x / a.NT, kt = blockIdx.x % a.NT;
-  const int b = bh / a.h, hh = bh % a.h;
   const int L = a.L, LPK = a.LPK;
-  const int NC = (LPK + QC - 1) / QC;
-  // causal: queries before this key tile never attend to it
-  const int c_first = a.mask_mode == RBM_MASK_CAUSAL ? (kt * 128) / QC : 0;
+  const int NSC = (LPK + SQ - 1) / SQ;  // sub-chunks per sequence
+  const int n_items = a.items > (int)blockIdx.x ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  int tcnt = 0;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t off_rows = B_NSTG * B_STAGE, off_out = off_rows + 2 * B_ROWS;
+  // causal: queries before a key tile never attend to it
+  auto first_chunk = [&](int kt) { return CAUSAL ? (kt * 128) / SQ : 0; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < B_NSTG; ++i) {
       mbar_init(smem_u32(&full_bar[i]), 1);
-      mbar_init(smem_u32(&split_bar[i]), NSW);
+      mbar_init(smem_u32(&split_bar[i]), 2);
       mbar_init(smem_u32(&empty_bar[i]), 1);
-      mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&ds_full[i]), NSW);
     }
-    mbar_init(smem_u32(&kv_bar), NSW);
-    mbar_init(smem_u32(&done_bar), 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&ds_full[i]), 4);
+    }
+    mbar_init(smem_u32(&ops_free), 1);
+    mbar_init(smem_u32(&ops_full), 4);
+    mbar_init(smem_u32(&dkv_full), 1);
+    mbar_init(smem_u32(&dkv_free), 4);
+    mbar_init(smem_u32(&rows_full), 1);
+    mbar_init(smem_u32(&rows_free), 4);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
@@ -790,208 +815,338 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_bwd_dkv_tc_kernel(const
   const uint32_t tmem = tmem_base_slot;
 
   if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      int n = 0;
-      for (int c = c_first; c < NC; ++c, ++n) {
-        const int s = n & 1;
-        if (n >= 2) mbar_wait(smem_u32(&empty_bar[s]), ((n >> 1) - 1) & 1);
-        const uint32_t bar = smem_u32(&full_bar[s]);
-        const uint32_t sa = smem_base + s * CH_STAGE;
-        mbar_expect_tx(bar, 4 * CH_TILE);
-        tma_load_3d(sa + 0 * CH_TILE, &mapQk, bar, hh * DK, c * QC, b);
-        tma_load_3d(sa + 1 * CH_TILE, &mapQm, bar, hh * DK, c * QC, b);
-        tma_load_3d(sa + 2 * CH_TILE, &mapOk, bar, hh * DK, c * QC, b);
-        tma_load_3d(sa + 3 * CH_TILE, &mapOm, bar, hh * DK, c * QC, b);
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQk) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQm) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOk) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapOm) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapK) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+      auto issue_rows = [&](int n) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int bh = item / a.NT, kt = item - bh * a.NT, b = bh / a.h, hh = bh % a.h;
+        if (n >= 1) mbar_wait(smem_u32(&rows_free), (n - 1) & 1);
+        const uint32_t bar = smem_u32(&rows_full), dst = smem_base + off_rows;
+        mbar_expect_tx(bar, 2 * B_ROWS);
+        tma_load_3d(dst, &mapK, bar, hh * DK, kt * 128, b);
+        tma_load_3d(dst + B_ROWS, &mapV, bar, hh * DK, kt * 128, b);
+      };
+      if (n_items > 0) issue_rows(0);
+      int g = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int bh = item / a.NT, kt = item - bh * a.NT, b = bh / a.h, hh = bh % a.h;
+        for (int c = first_chunk(kt); c < NSC; ++c, ++g) {
+          const int s = g % B_NSTG;
+          if (g >= B_NSTG) mbar_wait(smem_u32(&empty_bar[s]), ((g / B_NSTG) - 1) & 1);
+          const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * B_STAGE;
+          mbar_expect_tx(bar, 4 * B_TILE);
+          tma_load_3d(sa + 0 * B_TILE, &mapQk, bar, hh * DK, c * SQ, b);
+          tma_load_3d(sa + 1 * B_TILE, &mapQm, bar, hh * DK, c * SQ, b);
+          tma_load_3d(sa + 2 * B_TILE, &mapOk, bar, hh * DK, c * SQ, b);
+          tma_load_3d(sa + 3 * B_TILE, &mapOm, bar, hh * DK, c * SQ, b);
+        }
+        if (n + 1 < n_items) issue_rows(n + 1);
       }
     }
   } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (tmem != 0) __trap();  // the CTA owns all 512 columns: literal addresses keep the issue loop on the uniform datapath
     if (elect_one()) {
-      mbar_wait(smem_u32(&kv_bar), 0);
-      tc_fence_after();
-      const uint32_t idA = make_idesc_tf32_ex(128, DK, 0, 1);  // dK / dV: A from TMEM, B MN-major, N = 32
-      int n = 0;
-      for (int c = c_first; c < NC; ++c, ++n) {
-        const int s = n & 1, par = (n >> 1) & 1;
-        const int nq = LPK - c * QC < QC ? LPK - c * QC : QC;  // valid (16-multiple) query columns of this chunk
-        const uint32_t idS = make_idesc_tf32_ex(128, nq, 0, 0);
-        mbar_wait(smem_u32(&full_bar[s]), par);
-        mbar_wait(smem_u32(&split_bar[s]), par);
-        tc_fence_after();
-        const uint32_t sa = smem_base + s * CH_STAGE, sl = sa + 4 * CH_TILE;
-        const uint64_t dQk = make_sw128_desc(sa + 0 * CH_TILE), dQkl = make_sw128_desc(sl + 0 * CH_TILE);
-        const uint64_t dOk = make_sw128_desc(sa + 2 * CH_TILE), dOkl = make_sw128_desc(sl + 2 * CH_TILE);
-#pragma unroll
-        for (int k = 0; k < DK / 8; ++k) {
-          const uint64_t o = (uint64_t)(k * 2);
-          umma_tf32_ts(tmem + B_ST, tmem + B_K + k * 8, dQkl + o, idS, k != 0);
-          umma_tf32_ts(tmem + B_ST, tmem + B_KL + k * 8, dQk + o, idS, 1);
-          umma_tf32_ts(tmem + B_ST, tmem + B_K + k * 8, dQk + o, idS, 1);
-        }
-#pragma unroll
-        for (int k = 0; k < DK / 8; ++k) {
-          const uint64_t o = (uint64_t)(k * 2);
-          umma_tf32_ts(tmem + B_DPT, tmem + B_V + k * 8, dOkl + o, idS, k != 0);
-          umma_tf32_ts(tmem + B_DPT, tmem + B_VL + k * 8, dOk + o, idS, 1);
-          umma_tf32_ts(tmem + B_DPT, tmem + B_V + k * 8, dOk + o, idS, 1);
-        }
-        umma_commit(smem_u32(&s_full[s]));
-        mbar_wait(smem_u32(&ds_full[s]), par);
+      constexpr uint32_t tmem = 0;
+      const uint32_t idA2 = make_idesc_tf32_ex(128, 2 * DK, 0, 1);  // A from TMEM, [B | B_lo] MN-major, N = 64
+      const uint32_t idA1 = make_idesc_tf32_ex(128, DK, 0, 1);
+      // the two most recent sub-chunks (one per group) whose dK / dV update is still to be issued
+      int p_g[2] = {-1, -1}, p_nq[2] = {0, 0}, p_n[2] = {0, 0};
+      bool p_first[2] = {false, false}, p_last[2] = {false, false};
+      auto issue_dkv = [&](int grp) {
+        const int g = p_g[grp], nq = p_nq[grp], n = p_n[grp], s = g % B_NSTG;
+        const uint32_t tG = tmem + B_GRP0 + (uint32_t)grp * B_GRP;
+        const uint32_t sa = smem_base + s * B_STAGE;
+        mbar_wait(smem_u32(&ds_full[grp]), (g >> 1) & 1);
+        if (p_first[grp] && n >= 1) mbar_wait(smem_u32(&dkv_free), (n - 1) & 1);
         tc_fence_after();
         for (int kk = 0; kk < nq / 8; ++kk) {
-          const uint64_t dQm = make_sw128_desc_mn(sa + 1 * CH_TILE + kk * 1024, 0), dQml = make_sw128_desc_mn(sl + 1 * CH_TILE + kk * 1024, 0);
-          const uint64_t dOm = make_sw128_desc_mn(sa + 3 * CH_TILE + kk * 1024, 0), dOml = make_sw128_desc_mn(sl + 3 * CH_TILE + kk * 1024, 0);
-          const uint32_t acc = (n | kk) != 0;
-          umma_tf32_ts(tmem + B_DK, tmem + B_ST + kk * 8, dQml, idA, acc);
-          umma_tf32_ts(tmem + B_DK, tmem + B_DPT + kk * 8, dQm, idA, 1);
-          umma_tf32_ts(tmem + B_DK, tmem + B_ST + kk * 8, dQm, idA, 1);
-          umma_tf32_ts(tmem + B_DV, tmem + B_P + kk * 8, dOml, idA, acc);
-          umma_tf32_ts(tmem + B_DV, tmem + B_PL + kk * 8, dOm, idA, 1);
-          umma_tf32_ts(tmem + B_DV, tmem + B_P + kk * 8, dOm, idA, 1);
+          const uint64_t dQ2 = make_sw128_desc_mn(sa + 1 * B_TILE + kk * 1024, 4 * B_TILE);  // second MN block = the residual tile
+          const uint64_t dQ1 = make_sw128_desc_mn(sa + 1 * B_TILE + kk * 1024, 0);
+          const uint64_t dO2 = make_sw128_desc_mn(sa + 3 * B_TILE + kk * 1024, 4 * B_TILE);
+          const uint64_t dO1 = make_sw128_desc_mn(sa + 3 * B_TILE + kk * 1024, 0);
+          const uint32_t acc = !(p_first[grp] && kk == 0);
+          umma_tf32_ts(tmem + B_DK, tG + kk * 8, dQ2, idA2, acc);          // [dS^T.Q | dS^T.Q_lo]
+          umma_tf32_ts(tmem + B_DK, tG + B_DPT + kk * 8, dQ1, idA1, 1);    // dS^T_lo.Q
+          umma_tf32_ts(tmem + B_DV, tG + B_P + kk * 8, dO2, idA2, acc);    // [P~^T.dO | P~^T.dO_lo]
+          umma_tf32_ts(tmem + B_DV, tG + B_PL + kk * 8, dO1, idA1, 1);     // P~^T_lo.dO
         }
         umma_commit(smem_u32(&empty_bar[s]));
+        if (p_last[grp]) umma_commit(smem_u32(&dkv_full));
+        p_g[grp] = -1;
+      };
+      int g = 0;
+      for (int n = 0; n < n_items; ++n) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int kt = item % a.NT;
+        const int c0 = first_chunk(kt);
+        for (int c = c0; c < NSC; ++c, ++g) {
+          const int grp = g & 1, s = g % B_NSTG;
+          if (p_g[grp] >= 0) issue_dkv(grp);  // frees this group's column block (the tensor pipe runs in order)
+          const int nq = LPK - c * SQ < SQ ? LPK - c * SQ : SQ;  // valid (16-multiple) queries of this sub-chunk
+          if (c == c0) mbar_wait(smem_u32(&ops_full), n & 1);
+          mbar_wait(smem_u32(&full_bar[s]), (g / B_NSTG) & 1);
+          mbar_wait(smem_u32(&split_bar[s]), (g / B_NSTG) & 1);
+          tc_fence_after();
+          const uint32_t tG = tmem + B_GRP0 + (uint32_t)grp * B_GRP;
+          const uint32_t idS = make_idesc_tf32_ex(128, nq, 0, 0);
+          const uint32_t sa = smem_base + s * B_STAGE, sl = sa + 4 * B_TILE;
+          const uint64_t dQk = make_sw128_desc(sa + 0 * B_TILE), dQkl = make_sw128_desc(sl + 0 * B_TILE);
+          const uint64_t dOk = make_sw128_desc(sa + 2 * B_TILE), dOkl = make_sw128_desc(sl + 2 * B_TILE);
+#pragma unroll
+          for (int k = 0; k < DK / 8; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32_ts(tG, tmem + B_K + k * 8, dQkl + o, idS, k != 0);
+            umma_tf32_ts(tG, tmem + B_KL + k * 8, dQk + o, idS, 1);
+            umma_tf32_ts(tG, tmem + B_K + k * 8, dQk + o, idS, 1);
+          }
+#pragma unroll
+          for (int k = 0; k < DK / 8; ++k) {
+            const uint64_t o = (uint64_t)(k * 2);
+            umma_tf32_ts(tG + B_DPT, tmem + B_V + k * 8, dOkl + o, idS, k != 0);
+            umma_tf32_ts(tG + B_DPT, tmem + B_VL + k * 8, dOk + o, idS, 1);
+            umma_tf32_ts(tG + B_DPT, tmem + B_V + k * 8, dOk + o, idS, 1);
+          }
+          umma_commit(smem_u32(&s_full[grp]));
+          if (c == NSC - 1) umma_commit(smem_u32(&ops_free));  // K / V of this item have been consumed
+          p_g[grp] = g; p_nq[grp] = nq; p_n[grp] = n; p_first[grp] = false; p_last[grp] = false;
+          if (c == c0) p_first[grp] = true;
+          if (c == NSC - 1) p_last[grp] = true;
+        }
       }
-      umma_commit(smem_u32(&done_bar));
+      // drain in issue order
+      if (p_g[0] >= 0 && p_g[1] >= 0) {
+        const int firstg = p_g[0] < p_g[1] ? 0 : 1;
+        issue_dkv(firstg);
+        issue_dkv(firstg ^ 1);
+      } else if (p_g[0] >= 0) {
+        issue_dkv(0);
+      } else if (p_g[1] >= 0) {
+        issue_dkv(1);
+      }
     }
     __syncwarp();
-  } else {
-    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
-    const int tid = sw * 32 + lane;
-    const int64_t row0 = (int64_t)b * L;
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------------------------------ softmax groups
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const int rl = q * 32 + lane;
-    const int j = kt * 128 + rl;  // this thread's key
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    for (int i = tid; i < 256; i += NSW * 32) {
-      const bool in = i < L;
-      st_m[i] = in ? a.stats[((int64_t)bh * L + i) * 2] : 0.f;
-      st_i[i] = in ? a.stats[((int64_t)bh * L + i) * 2 + 1] : 0.f;
-      st_d[i] = in ? a.delta[(int64_t)bh * L + i] : 0.f;
-    }
-    const bool jpad = a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0;
-    // ---- operand rows into TMEM: half 0 -> K (pre-scaled to the log2 domain), half 1 -> V
-    {
-      float v[32], lo[32];
-      const float* src = half == 0 ? a.k + (row0 + j) * a.ldk + hh * DK : a.v + (row0 + j) * a.ldv + hh * DK;
-      const float mul = half == 0 ? a.scale_log2 : 1.f;
-#pragma unroll
-      for (int c = 0; c < 32; c += 4) {
-        float4 x = j < L ? ld4(src + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-        v[c] = x.x * mul; v[c + 1] = x.y * mul; v[c + 2] = x.z * mul; v[c + 3] = x.w * mul;
-      }
-#pragma unroll
-      for (int c = 0; c < 32; ++c) lo[c] = v[c] - __uint_as_float(__float_as_uint(v[c]) & 0xffffe000u);
-      const uint32_t tr = half == 0 ? B_K : B_V, tl = half == 0 ? B_KL : B_VL;
-      float t16[16];
-#pragma unroll
-      for (int part = 0; part < 2; ++part) {
-#pragma unroll
-        for (int c = 0; c < 16; ++c) t16[c] = v[part * 16 + c];
-        tmem_st16(tmem + lane_sel + tr + part * 16, t16);
-#pragma unroll
-        for (int c = 0; c < 16; ++c) t16[c] = lo[part * 16 + c];
-        tmem_st16(tmem + lane_sel + tl + part * 16, t16);
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&kv_bar));
-    }
-    named_bar_sync(1, NSW * 32);  // stats arrays visible
-
-    auto split_stage = [&](int n) {
-      const int s = n & 1;
-      mbar_wait(smem_u32(&full_bar[s]), (n >> 1) & 1);
-      uint8_t* st = gen + (size_t)s * CH_STAGE;
-      split_lo_bytes(st, st + 4 * CH_TILE, (int)(4 * CH_TILE / 16), tid, NSW * 32);
-      fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
-    };
+    const uint32_t tG = tmem + lane_sel + B_GRP0 + (uint32_t)grp * B_GRP;
     // dropout: lanes {l, l^1, l^8, l^9} hold keys that share their Philox calls; each computes two of the eight
     const int wq = (lane & 1) | (((lane >> 3) & 1) << 1);
-    const int e_j = j & 1, nb_j = (j >> 3) & 1, t_j = (j & 7) >> 1, np_j = j >> 4;
-
-    const int n_chunks = NC - c_first;
-    if (n_chunks > 0) split_stage(0);
-    int n = 0;
-    for (int c = c_first; c < NC; ++c, ++n) {
-      const int s = n & 1, par = (n >> 1) & 1;
-      const int nq = LPK - c * QC < QC ? LPK - c * QC : QC;
-      if (n + 1 < n_chunks) split_stage(n + 1);  // overlaps the tensor core's S^T / dP^T of this chunk
-      mbar_wait(smem_u32(&s_full[s]), par);
-      tc_fence_after();
-      const int cbeg = half == 0 ? 0 : 32, cend = half == 0 ? (nq < 32 ? nq : 32) : nq;
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float sv[16], dp[16], t16[16];
-        tmem_ld16(tmem + lane_sel + B_ST + (uint32_t)c0, sv);
-        tmem_ld16(tmem + lane_sel + B_DPT + (uint32_t)c0, dp);
-        const int i0 = c * QC + c0;  // 16 consecutive queries, one Philox "tile"
-        uint32_t w0[8], w1[8];       // per query-in-octet g: the two words (rh = 0, 1) that hold this key's fields
-        if (a.thr16) {
-          uint4 ca = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
-          uint4 cb = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
+    int g = 0;
+    for (int n = 0; n < n_items; ++n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, kt = item - bh * a.NT, b = bh / a.h;
+      const int j = kt * 128 + rl;  // this thread's key
+      const bool warp_live = kt * 128 + q * 32 < L;
+      // a padded key keeps the reference's score of -1e9: probability 0, unless the whole row is padding (then the
+      // row is uniform and still feeds dV); no score gradient flows through it either way
+      const bool jpad = j < L && a.mask_mode == RBM_MASK_KEYPAD && a.tok[(int64_t)b * L + j] == 0;
+      const bool jin = j < L;
+      const int e_j = j & 1, nb_j = (j >> 3) & 1, t_j = (j & 7) >> 1, np_j = j >> 4;
+      const float* sm = st_m[n & 1];
+      const float* si = st_i[n & 1];
+      const float* sd = st_d[n & 1];
+      for (int c = first_chunk(kt); c < NSC; ++c, ++g) {
+        if ((g & 1) != grp) continue;
+        const int nq = LPK - c * SQ < SQ ? LPK - c * SQ : SQ;
+        mbar_wait(smem_u32(&s_full[grp]), (g >> 1) & 1);
+        tc_fence_after();
+        if (warp_live) {
+          for (int c0 = 0; c0 < nq; c0 += 16) {
+            uint32_t rs[16], rd[16];
+            tmem_ld16_issue(tG + (uint32_t)c0, rs);
+            tmem_ld16_issue(tG + B_DPT + (uint32_t)c0, rd);
+            const int i0 = c * SQ + c0;  // 16 consecutive queries, one Philox "tile"
+            uint32_t w0[8], w1[8];       // per query-in-octet g: the two words (rh = 0, 1) that hold this key's fields
+            if (DROP) {
+              uint4 ca = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
+              uint4 cb = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
 #pragma unroll
-          for (int gq = 0; gq < 8; ++gq) {
-            // call of query-octet position gq is owned by the lane whose (bit0, bit3) = ((gq>>1)&1, (gq>>2)&1); the
-            // requester picks the words of ITS key parity e: word index = rh*2 + e
-            const int src = (lane & ~9) | ((gq >> 1) & 1) | (((gq >> 2) & 1) << 3);
-            const uint4 cc = (gq & 1) ? cb : ca;
-            const uint32_t rx = __shfl_sync(0xffffffffu, cc.x, src), ry = __shfl_sync(0xffffffffu, cc.y, src);
-            const uint32_t rz = __shfl_sync(0xffffffffu, cc.z, src), rw = __shfl_sync(0xffffffffu, cc.w, src);
-            w0[gq] = e_j ? ry : rx;
-            w1[gq] = e_j ? rw : rz;
+              for (int gq = 0; gq < 8; ++gq) {
+                // call of query-octet position gq is owned by the lane whose (bit0, bit3) = ((gq>>1)&1, (gq>>2)&1); the
+                // requester picks the words of ITS key parity e: word index = rh*2 + e
+                const int src = (lane & ~9) | ((gq >> 1) & 1) | (((gq >> 2) & 1) << 3);
+                const uint4 cc = (gq & 1) ? cb : ca;
+                const uint32_t rx = __shfl_sync(0xffffffffu, cc.x, src), ry = __shfl_sync(0xffffffffu, cc.y, src);
+                const uint32_t rz = __shfl_sync(0xffffffffu, cc.z, src), rw = __shfl_sync(0xffffffffu, cc.w, src);
+                w0[gq] = e_j ? ry : rx;
+                w1[gq] = e_j ? rw : rz;
+              }
+            }
+            tmem_ld_wait16(rs);
+            tmem_ld_wait16(rd);
+            float sv[16], dlo[16], t16[16];
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) {
+              const int i = i0 + ii;
+              bool live = jin;
+              if (CAUSAL) live = live && (j <= i);
+              // queries beyond the sequence hold zero rows and zero statistics: p = 2^0 * 0
+              const float x = jpad ? RBM_PADFILL : __uint_as_float(rs[ii]);
+              const float p = live ? ex2(x - sm[i]) * si[i] : 0.f;
+              float mk = 1.f;
+              if (DROP) {
+                const uint32_t word = (ii & 8) ? w1[ii & 7] : w0[ii & 7];  // rh = (i >> 3) & 1
+                const uint32_t fld = nb_j ? (word >> 16) : (word & 0xffffu);
+                mk = fld >= a.thr16 ? a.inv_keep : 0.f;
+              }
+              const float ds = jpad ? 0.f : p * (mk * __uint_as_float(rd[ii]) - sd[i]);
+              sv[ii] = ds;
+              dlo[ii] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
+              t16[ii] = p * mk;
+            }
+            tmem_st16(tG + (uint32_t)c0, sv);
+            tmem_st16(tG + B_DPT + (uint32_t)c0, dlo);
+            tmem_st16(tG + B_P + (uint32_t)c0, t16);
+#pragma unroll
+            for (int ii = 0; ii < 16; ++ii) t16[ii] = t16[ii] - __uint_as_float(__float_as_uint(t16[ii]) & 0xffffe000u);
+            tmem_st16(tG + B_PL + (uint32_t)c0, t16);
           }
+          tmem_st_wait();
         }
-#pragma unroll
-        for (int ii = 0; ii < 16; ++ii) {
-          const int i = i0 + ii;
-          const float x = jpad ? RBM_PADFILL : sv[ii];
-          const bool dead = i >= L || j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i);
-          const float p = dead ? 0.f : ex2(x - st_m[i]) * st_i[i];
-          float mk = 1.f;
-          if (a.thr16) {
-            const uint32_t word = (ii & 8) ? w1[ii & 7] : w0[ii & 7];  // rh = (i >> 3) & 1
-            const uint32_t fld = nb_j ? (word >> 16) : (word & 0xffffu);
-            mk = fld >= a.thr16 ? a.inv_keep : 0.f;
-          }
-          const float ds = jpad ? 0.f : p * (mk * dp[ii] - st_d[i]);
-          sv[ii] = ds;
-          dp[ii] = ds - __uint_as_float(__float_as_uint(ds) & 0xffffe000u);
-          t16[ii] = p * mk;
-        }
-        tmem_st16(tmem + lane_sel + B_ST + (uint32_t)c0, sv);
-        tmem_st16(tmem + lane_sel + B_DPT + (uint32_t)c0, dp);
-        tmem_st16(tmem + lane_sel + B_P + (uint32_t)c0, t16);
-#pragma unroll
-        for (int ii = 0; ii < 16; ++ii) t16[ii] = t16[ii] - __uint_as_float(__float_as_uint(t16[ii]) & 0xffffe000u);
-        tmem_st16(tmem + lane_sel + B_PL + (uint32_t)c0, t16);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&ds_full[grp]));
       }
-      tmem_st_wait();
+    }
+  } else if (warp < 14) {
+    // ------------------------------------------------------------------------------------------ operand / output warps
+    const int q = warp & 3, rl = q * 32 + lane, t128 = (warp - 10) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float* stage = reinterpret_cast<float*>(gen + off_out + (warp - 10) * 2 * B_OUT);
+    float kv[32], vv[32];
+    float m0 = 0.f, i0 = 0.f, d0 = 0.f, m1 = 0.f, i1 = 0.f, d1 = 0.f;  // statistics of queries t128 and t128 + 128
+    auto load_item = [&](int n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT;
+      m0 = i0 = d0 = m1 = i1 = d1 = 0.f;
+      if (t128 < L) {
+        const int64_t r = (int64_t)bh * L + t128;
+        m0 = a.stats[r * 2]; i0 = a.stats[r * 2 + 1]; d0 = a.delta[r];
+      }
+      if (t128 + 128 < L) {
+        const int64_t r = (int64_t)bh * L + t128 + 128;
+        m1 = a.stats[r * 2]; i1 = a.stats[r * 2 + 1]; d1 = a.delta[r];
+      }
+      mbar_wait(smem_u32(&rows_full), n & 1);
+      const float* ks = reinterpret_cast<const float*>(gen + off_rows) + rl * DK;
+      const float* vs = ks + B_ROWS / 4;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const int sc = ((c >> 2) ^ (rl & 7)) << 2;  // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+        const float4 x = ld4(ks + sc), y = ld4(vs + sc);
+        kv[c] = x.x * a.scale_log2; kv[c + 1] = x.y * a.scale_log2; kv[c + 2] = x.z * a.scale_log2; kv[c + 3] = x.w * a.scale_log2;
+        vv[c] = y.x; vv[c + 1] = y.y; vv[c + 2] = y.z; vv[c + 3] = y.w;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rows_free));
+    };
+    auto store_dkv = [&](int n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, kt = item - bh * a.NT, b = bh / a.h, hh = bh - b * a.h;
+      mbar_wait(smem_u32(&dkv_full), n & 1);
+      tc_fence_after();
+      // [x.B + x_lo.B | x.B_lo] halves added, dK scaled, into the warp's staging tiles (16-byte chunks XOR-swizzled by
+      // row) so that every global store below is a full 128-byte row
+#pragma unroll
+      for (int which = 0; which < 2; ++which) {
+        const uint32_t tcol = tmem + lane_sel + (which == 0 ? B_DK : B_DV);
+        const float mul = which == 0 ? a.scale : 1.f;
+        float* dst = stage + which * (B_OUT / 4) + lane * DK;
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+          float x[16], y[16];
+          tmem_ld16(tcol + part * 16, x);
+          tmem_ld16(tcol + DK + part * 16, y);
+#pragma unroll
+          for (int c = 0; c < 16; c += 4) {
+            const int ch = part * 4 + (c >> 2);
+            st4(dst + ((ch ^ (lane & 7)) << 2), make_float4((x[c] + y[c]) * mul, (x[c + 1] + y[c + 1]) * mul, (x[c + 2] + y[c + 2]) * mul,
+                                                            (x[c + 3] + y[c + 3]) * mul));
+          }
+        }
+      }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&ds_full[s]));
-    }
-    mbar_wait(smem_u32(&done_bar), 0);
-    tc_fence_after();
-    float o[16];
-    if (n_chunks > 0) {
-      // half 0 -> dK (32 columns in two loads), half 1 -> dV
-      const uint32_t tcol = half == 0 ? B_DK : B_DV;
-      float* base = half == 0 ? a.dk + (row0 + j) * a.lddk + hh * DK : a.dv + (row0 + j) * a.lddv + hh * DK;
-      const float mul = half == 0 ? a.scale : 1.f;
+      if (lane == 0) mbar_arrive(smem_u32(&dkv_free));
+      const int64_t row0 = (int64_t)b * L + kt * 128 + q * 32;
+      const int rows_ok = L - (kt * 128 + q * 32);  // rows of this warp inside the sequence
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        tmem_ld16(tmem + lane_sel + tcol + part * 16, o);
-        if (j < L) {
+      for (int which = 0; which < 2; ++which) {
+        const float* src = stage + which * (B_OUT / 4);
+        float* base = which == 0 ? a.dk + row0 * a.lddk + hh * DK : a.dv + row0 * a.lddv + hh * DK;
+        const int64_t ld = which == 0 ? a.lddk : a.lddv;
 #pragma unroll
-          for (int jj = 0; jj < 16; jj += 4)
-            st4(base + part * 16 + jj, make_float4(o[jj] * mul, o[jj + 1] * mul, o[jj + 2] * mul, o[jj + 3] * mul));
+        for (int it = 0; it < 8; ++it) {
+          const int r = it * 4 + (lane >> 3), ch = lane & 7;
+          if (r < rows_ok) st4(base + r * ld + ch * 4, ld4(src + r * DK + ((ch ^ (r & 7)) << 2)));
         }
       }
-    } else if (j < L) {
-      float* base = half == 0 ? a.dk + (row0 + j) * a.lddk + hh * DK : a.dv + (row0 + j) * a.lddv + hh * DK;
-      for (int jj = 0; jj < 32; jj += 4) st4(base + jj, make_float4(0.f, 0.f, 0.f, 0.f));
+      __syncwarp();
+    };
+    if (n_items > 0) load_item(0);
+    for (int n = 0; n < n_items; ++n) {
+      st_m[n & 1][t128] = m0; st_i[n & 1][t128] = i0; st_d[n & 1][t128] = d0;
+      st_m[n & 1][t128 + 128] = m1; st_i[n & 1][t128 + 128] = i1; st_d[n & 1][t128 + 128] = d1;
+      if (n >= 1) {
+        mbar_wait(smem_u32(&ops_free), (n - 1) & 1);  // every S^T / dP^T of the previous item has read its K / V
+        tc_fence_after();
+      }
+      {
+        float t16[16];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = kv[part * 16 + c];
+          tmem_st16(tmem + lane_sel + B_K + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = t16[c] - __uint_as_float(__float_as_uint(t16[c]) & 0xffffe000u);
+          tmem_st16(tmem + lane_sel + B_KL + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = vv[part * 16 + c];
+          tmem_st16(tmem + lane_sel + B_V + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = t16[c] - __uint_as_float(__float_as_uint(t16[c]) & 0xffffe000u);
+          tmem_st16(tmem + lane_sel + B_VL + part * 16, t16);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&ops_full));
+      // dK / dV are single-buffered: the previous item's result must leave before this item's first update, and the
+      // producer only reaches the next item's K / V rows once this item's query stream has drained -- so this order
+      if (n >= 1) store_dkv(n - 1);
+      if (n + 1 < n_items) load_item(n + 1);
+    }
+    if (n_items > 0) store_dkv(n_items - 1);
+  } else {
+    // ------------------------------------------------------------------------------------------ TF32 residual copies
+    const int tid = (warp - 14) * 32 + lane;
+    int g = 0;
+    for (int n = 0; n < n_items; ++n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      for (int c = first_chunk(item % a.NT); c < NSC; ++c, ++g) {
+        const int s = g % B_NSTG;
+        mbar_wait(smem_u32(&full_bar[s]), (g / B_NSTG) & 1);
+        uint8_t* st = gen + (size_t)s * B_STAGE;
+        split_lo_bytes(st, st + 4 * B_TILE, (int)(4 * B_TILE / 16), tid, 64);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
+      }
     }
   }
+  (void)tcnt;
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
@@ -1019,15 +1174,20 @@ EncodeTiledFn get_encode() {
 // [B, L, width] fp32 view of a token-major buffer with row stride ld; box = [1, box_rows, 32], 128-byte swizzle
 bool encode_map3(CUtensorMap* map, const float* base, int B, int L, int width, int64_t ld, int box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode();
+  rbm_bind_context();
   if (!enc) return false;
   cuuint64_t gdim[3] = {(cuuint64_t)width, (cuuint64_t)L, (cuuint64_t)B};
   cuuint64_t gstride[2] = {(cuuint64_t)ld * sizeof(float), (cuuint64_t)L * ld * sizeof(float)};
   cuuint32_t box[3] = {(cuuint32_t)DK, (cuuint32_t)box_rows, 1};
   cuuint32_t estr[3] = {1, 1, 1};
   // K-major consumers read the classic 128-byte swizzle; MN-major TF32 consumers need the 32-byte-atom variant
-  return enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-             mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-             CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  const CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, (void*)base, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                         mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                         CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    fprintf(stderr, "librbm_b200: cuTensorMapEncodeTiled rc=%d base=%p dims=(%d,%d,%d) ld=%lld box_rows=%d mn=%d\n", (int)r, (const void*)base,
+            width, L, B, (long long)ld, box_rows, (int)mn_major);
+  return r == CUDA_SUCCESS;
 }
 
 bool tc_enabled() {
@@ -1140,37 +1300,43 @@ bool rbm_attn_bwd_dkv_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int6
   return get_encode() != nullptr;
 }
 
-// boxes of [64 query rows x 32 columns]
-static bool encode_map3_rows(CUtensorMap* map, const float* base, int B, int L, int width, int64_t ld, int box_rows, bool mn_major) {
-  return encode_map3(map, base, B, L, width, ld, box_rows, mn_major);
-}
-
 int rbm_attn_bwd_dkv_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
                                const float* dout, int64_t lddo, const float* stats, const float* delta, float* dk_, int64_t lddk,
                                float* dv, int64_t lddv, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed,
                                uint64_t site, cudaStream_t st) {
   const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
-  CUtensorMap mQk, mQm, mOk, mOm;
-  if (!encode_map3_rows(&mQk, q, B, L, h * DK, ldq, QC, false) || !encode_map3_rows(&mQm, q, B, L, h * DK, ldq, QC, true) ||
-      !encode_map3_rows(&mOk, dout, B, L, h * DK, lddo, QC, false) || !encode_map3_rows(&mOm, dout, B, L, h * DK, lddo, QC, true)) {
+  CUtensorMap mQk, mQm, mOk, mOm, mK, mV;
+  if (!encode_map3(&mQk, q, B, L, h * DK, ldq, SQ, false) || !encode_map3(&mQm, q, B, L, h * DK, ldq, SQ, true) ||
+      !encode_map3(&mOk, dout, B, L, h * DK, lddo, SQ, false) || !encode_map3(&mOm, dout, B, L, h * DK, lddo, SQ, true) ||
+      !encode_map3(&mK, k, B, L, h * DK, ldk, 128, false) || !encode_map3(&mV, v, B, L, h * DK, ldv, 128, false)) {
     rbm_set_error("rbm_attn_bwd(tcgen05 dkv): cuTensorMapEncodeTiled failed");
     return -1;
   }
   TcBwdKvArgs a{};
-  a.k = k; a.v = v; a.stats = stats; a.delta = delta; a.dk = dk_; a.dv = dv; a.ldk = ldk; a.ldv = ldv; a.lddk = lddk; a.lddv = lddv;
+  a.stats = stats; a.delta = delta; a.dk = dk_; a.dv = dv; a.lddk = lddk; a.lddv = lddv;
   a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
-  size_t smem = (size_t)2 * CH_STAGE + 1024;
+  a.items = B * h * NT;
+  a.trace = nullptr;
+  const size_t smem = (size_t)B_NSTG * B_STAGE + 2 * B_ROWS + 8 * B_OUT + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_bwd_dkv_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       rbm_set_error("rbm_attn_bwd(tcgen05 dkv): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  attn_bwd_dkv_tc_kernel<<<B * h * NT, 64 + 32 * NSW, smem, st>>>(mQk, mQm, mOk, mOm, a);
+  const bool causal = mask_mode == RBM_MASK_CAUSAL, drop = a.thr16 != 0;
+  const int grid = a.items < RBM_NUM_SMS ? a.items : RBM_NUM_SMS;
+  if (causal && drop) attn_bwd_dkv_tc_kernel<true, true><<<grid, B_THREADS, smem, st>>>(mQk, mQm, mOk, mOm, mK, mV, a);
+  else if (causal) attn_bwd_dkv_tc_kernel<true, false><<<grid, B_THREADS, smem, st>>>(mQk, mQm, mOk, mOm, mK, mV, a);
+  else if (drop) attn_bwd_dkv_tc_kernel<false, true><<<grid, B_THREADS, smem, st>>>(mQk, mQm, mOk, mOm, mK, mV, a);
+  else attn_bwd_dkv_tc_kernel<false, false><<<grid, B_THREADS, smem, st>>>(mQk, mQm, mOk, mOm, mK, mV, a);
   RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dkv)");
   return 0;
 }

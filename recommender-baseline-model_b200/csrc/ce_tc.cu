@@ -548,6 +548,7 @@ EncodeTiledFn get_encode() {
 // [rows, d] fp32, box [64 rows x 32 cols]; K-major consumers: 128B swizzle, MN-major consumers: 32-byte-atom variant
 bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int d, bool mn) {
   EncodeTiledFn enc = get_encode();
+  rbm_bind_context();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)d, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)d * sizeof(float)};

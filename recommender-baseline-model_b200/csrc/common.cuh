@@ -98,6 +98,17 @@ __host__ __device__ __forceinline__ bool rbm_attn_keep(uint64_t seed, uint64_t s
   return rbm_attn_field(r, ((i >> 3) & 1) * 4 + (j & 1) * 2 + ((j >> 3) & 1)) >= thr16;
 }
 
+// cuTensorMapEncodeTiled is a driver-API call: it needs the primary context current on the CALLING thread.  A thread that
+// has not made a context-binding runtime call yet (an autograd worker whose allocations all came from the cache) fails it
+// with CUDA_ERROR_INVALID_CONTEXT, so every host thread binds once before its first encode.
+inline void rbm_bind_context() {
+  static thread_local bool bound = false;
+  if (!bound) {
+    cudaFree(0);
+    bound = true;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------
 // warp helpers
 // ---------------------------------------------------------------------------------------------

@@ -566,6 +566,7 @@ EncodeTiledFn get_encode() {
 // 2-D fp32 tensor [rows, cols] with row stride ld (elements); box = [box_rows, 32 cols], 128-byte swizzle
 bool encode_map(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld, int box_rows) {
   EncodeTiledFn enc = get_encode();
+  rbm_bind_context();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};
@@ -679,6 +680,7 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
 namespace {
 bool encode_map_mn(CUtensorMap* map, const float* base, int64_t rows, int64_t cols, int64_t ld) {
   EncodeTiledFn enc = get_encode();
+  rbm_bind_context();
   if (!enc) return false;
   cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
   cuuint64_t gstride[1] = {(cuuint64_t)ld * sizeof(float)};

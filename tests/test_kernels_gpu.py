@@ -205,6 +205,33 @@ def test_attention_packed(B, Ln, h, dk, mode, p):
     close(qg.grad, qr.grad, 1e-3, 2e-5)
 
 
+@pytest.mark.parametrize("mode", [L.MASK_CAUSAL, L.MASK_KEYPAD])
+def test_attention_persistent_many_items(mode):
+    """More (sequence, head, tile) work items than SMs: every persistent tcgen05 CTA walks several items, so the
+    cross-item hand-shakes (operand staging, accumulator hand-back, ring phases) are on the tested path."""
+    torch.manual_seed(7)
+    B, Ln, h, dk, p = 90, 200, 2, 32, 0.1
+    d = h * dk
+    qkv = torch.randn(B * Ln, 3 * d)
+    tok = torch.randint(1, 50, (B, Ln))
+    tok[::3, : Ln // 4] = 0
+    tok[5, :] = 0
+    tok[5, -1] = 5 if mode == L.MASK_CAUSAL else 0
+    dout = torch.randn(B * Ln, d)
+    scale = 1 / math.sqrt(dk)
+    seed, site = 9, 3
+    qg = g(qkv).requires_grad_(True)
+    out = ops.attention(qg, None, g(tok), B, Ln, h, 0, d, 2 * d, mode, scale, p, seed, site)
+    out.backward(g(dout))
+    mask = ops.dropout_mask_attn(B * h * Ln, Ln, p, seed, site, DEV).cpu().view(B, h, Ln, Ln)
+    qr = qkv.clone().requires_grad_(True)
+    q, k, v = (qr[:, i * d:(i + 1) * d].view(B, Ln, h, dk).transpose(1, 2) for i in range(3))
+    ref = _ref_attention(q, k, v, tok, mode, scale, p, mask).transpose(1, 2).reshape(B * Ln, d)
+    ref.backward(dout)
+    close(out, ref, 1e-4, 1e-5)
+    close(qg.grad, qr.grad, 1e-3, 2e-5)
+
+
 def test_attention_split_sources_and_bad_shapes():
     torch.manual_seed(0)
     B, Ln, h, dk = 2, 20, 2, 16
