@@ -1,4 +1,4 @@
-// ce_tc.cu -- BERT4Rec output scoring fused with masked cross-entropy on the Blackwell tensor path (d in {32,64,128}).
+// ce_tc.cu -- BERT4Rec output scoring fused with masked cross-entropy on the Blackwell tensor path (d in {32,64}).
 // Logits only ever exist as [128 x 64] tiles in tensor memory.  3xTF32 everywhere (fp32-level accuracy): the weight and
 // the compacted hidden rows are pre-split once per call into (raw, TF32 residual) pairs in global memory so TMA streams
 // both copies; per-CTA resident operands (hidden rows / weight rows) sit in TMEM as A operands with their residuals.
@@ -36,6 +36,8 @@ struct CeTcArgs {
   const float* dloss;
   float *lse_out, *partial, *dh_full, *part_w, *part_b;
   int V1, d, KB, nstage;
+  uint32_t tmem_cols;  // power of two >= the kernel's column need (256 lets two CTAs share an SM)
+  int bias_vec;        // bias pointer is 16-byte aligned: whole-chunk float4 loads
 };
 
 __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xffffe000u); }
@@ -71,17 +73,6 @@ __device__ __forceinline__ void mma_scores(uint32_t d_t, uint32_t a_raw, uint32_
     }
   }
 }
-// 3xTF32: D[tmem, N = KB*32] (+)= G[tmem raw/lo, 64 columns] . B[chunk MN-major raw/lo]
-__device__ __forceinline__ void mma_accum(uint32_t d_t, uint32_t g_raw, uint32_t g_lo, uint32_t b_raw, uint32_t b_lo, uint32_t idesc, bool first) {
-#pragma unroll
-  for (int kk = 0; kk < CW / 8; ++kk) {
-    const uint64_t br = make_sw128_desc_mn(b_raw + kk * 1024, BLK), bl = make_sw128_desc_mn(b_lo + kk * 1024, BLK);
-    umma_tf32_ts(d_t, g_raw + kk * 8, bl, idesc, !(first && kk == 0));
-    umma_tf32_ts(d_t, g_lo + kk * 8, br, idesc, 1);
-    umma_tf32_ts(d_t, g_raw + kk * 8, br, idesc, 1);
-  }
-}
-
 // --------------------------------------------------------------------------------------------------- forward
 // TMEM: H raw [0,d) | H lo [d,2d) | S buffers [2d, 2d+128)
 __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWl,
@@ -114,7 +105,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
     mbar_init(smem_u32(&h_bar), NSW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), a.tmem_cols);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -167,6 +158,24 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
     float m = -INFINITY, l = 0.f, tl = 0.f;
     for (int c = 0; c < NC; ++c) {
       const int buf = c & 1;
+      const int v0 = c * CW + half * 32;
+      // bias of this warp's 32 columns in the log2 domain, -inf beyond the vocabulary; fetched ahead of the wait
+      float bb[32];
+      if (v0 + 32 <= V1 && (a.bias == nullptr || a.bias_vec)) {
+        if (a.bias) {
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            const float4 t = ld4(a.bias + v0 + j);
+            bb[j] = t.x * RBM_LOG2E; bb[j + 1] = t.y * RBM_LOG2E; bb[j + 2] = t.z * RBM_LOG2E; bb[j + 3] = t.w * RBM_LOG2E;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) bb[j] = 0.f;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bb[j] = v0 + j < V1 ? (a.bias ? a.bias[v0 + j] * RBM_LOG2E : 0.f) : -INFINITY;
+      }
       mbar_wait(smem_u32(&tfull[buf]), (c >> 1) & 1);
       tc_fence_after();
       float v[32];
@@ -174,15 +183,17 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&tempty[buf]));
-      const int v0 = c * CW + half * 32;
       float cm = -INFINITY;
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
-        const int vv = v0 + j;
-        float x = vv < V1 ? v[j] + (a.bias ? a.bias[vv] * RBM_LOG2E : 0.f) : -INFINITY;
-        if ((int64_t)vv == tg) tl = x;
-        v[j] = x;
-        cm = fmaxf(cm, x);
+        v[j] += bb[j];
+        cm = fmaxf(cm, v[j]);
+      }
+      const uint32_t ts = (uint32_t)(tg - (int64_t)v0);  // this row's target column inside the slice, if < 32
+      if (__any_sync(0xffffffffu, ts < 32u)) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (ts == (uint32_t)j) tl = v[j];
       }
       const float mn = fmaxf(m, cm);
       if (mn > -INFINITY) {
@@ -215,13 +226,28 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
   __syncthreads();
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem, 512);
+    tmem_dealloc(tmem, a.tmem_cols);
   }
 }
 
-// ------------------------------------------------------------------------------------------- backward: dH
-// TMEM: H raw [0,d) | H lo [d,2d) | S/G raw [2d,2d+64) | G lo [2d+64,2d+128) | dH [2d+128, 3d+128)
-// stage: W chunk K-major raw | lo | W chunk MN-major raw | lo   (KB blocks each)
+// ------------------------------------------------------------------------------------------------ backward
+// Both backward kernels keep 128 "resident" rows as TMEM A operands (masked hidden rows for dH, weight rows for dW/db)
+// and stream the other side in 64-row chunks, each chunk as K-major tiles (scores) and MN-major tiles (update).  Two
+// groups of four warps (one warp per TMEM lane quarter, one thread per resident row) take the chunks alternately, each
+// with its own S/G column block, so the tensor core works on one group's chunk while the other group turns scores into
+// G = (softmax - onehot) * dloss/count.  The update runs as  D[:, 0:2d] += G.[B | B_lo]  (one N = 2d instruction: raw
+// and residual MN-major blocks are adjacent in the stage)  and  D[:, 0:d] += G_lo.B;  the halves are added on the way out.
+//   TMEM: R raw [0,d) | R lo [d,2d) | group g at 2d + 128g: S/G raw [+0,64) G lo [+64,128) | D [2d+256, 4d+256)   (d <= 64)
+//   stage: chunk K-major raw | lo | MN-major raw | lo   (KB blocks each)
+__device__ __forceinline__ void mma_accum2(uint32_t d_t, uint32_t g_raw, uint32_t g_lo, uint32_t b_mn_raw, uint32_t id2, uint32_t id1, bool first) {
+#pragma unroll
+  for (int kk = 0; kk < CW / 8; ++kk) {
+    const uint64_t b2 = make_sw128_desc_mn(b_mn_raw + kk * 1024, BLK);  // 2*KB blocks: raw then residual
+    umma_tf32_ts(d_t, g_raw + kk * 8, b2, id2, !(first && kk == 0));
+    umma_tf32_ts(d_t, g_lo + kk * 8, b2, id1, 1);                      // first KB blocks only (N = d)
+  }
+}
+
 __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __grid_constant__ CUtensorMap mapW, const __grid_constant__ CUtensorMap mapWl,
                                                                         const __grid_constant__ CUtensorMap mapWm,
                                                                         const __grid_constant__ CUtensorMap mapWml, const CeTcArgs a) {
@@ -243,9 +269,9 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&g_full[i]), NSW);
+      mbar_init(smem_u32(&g_full[i]), NSW / 2);
     }
-    mbar_init(smem_u32(&h_bar), NSW);
+    mbar_init(smem_u32(&h_bar), NSW / 2);
     mbar_init(smem_u32(&done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -254,7 +280,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
-  const uint32_t tH = tmem, tHl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
+  const uint32_t tH = tmem, tHl = tmem + d, tG0 = tmem + 2 * d, tD = tG0 + 4 * CW;
 
   if (warp == 0) {
     if (elect_one()) {
@@ -273,73 +299,106 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
+      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), id2 = make_idesc_tf32_ex(128, 2 * d, 0, 1), id1 = make_idesc_tf32_ex(128, d, 0, 1);
       mbar_wait(smem_u32(&h_bar), 0);
       tc_fence_after();
+      int pend[2] = {-1, -1};
+      auto accum = [&](int grp) {
+        const int c = pend[grp], s = c % ns;
+        const uint32_t tS = tG0 + (uint32_t)grp * 2 * CW;
+        mbar_wait(smem_u32(&g_full[grp]), (c >> 1) & 1);
+        tc_fence_after();
+        mma_accum2(tD, tS, tS + CW, smem_base + s * stage_bytes + 2 * KB * BLK, id2, id1, c == 0);
+        umma_commit(smem_u32(&empty_bar[s]));
+        pend[grp] = -1;
+      };
       for (int c = 0; c < NC; ++c) {
-        const int s = c % ns, ph = c & 1, par = (c >> 1) & 1;
+        const int s = c % ns, grp = c & 1;
+        if (pend[grp] >= 0) accum(grp);  // frees the group's column block (the tensor pipe runs in order)
         mbar_wait(smem_u32(&full_bar[s]), (c / ns) & 1);
         tc_fence_after();
         const uint32_t sa = smem_base + s * stage_bytes;
-        mma_scores(tS, tH, tHl, sa, sa + KB * BLK, KB, idS);
-        umma_commit(smem_u32(&s_full[ph]));
-        mbar_wait(smem_u32(&g_full[ph]), par);
-        tc_fence_after();
-        mma_accum(tD, tS, tGl, sa + 2 * KB * BLK, sa + 3 * KB * BLK, idD, c == 0);
-        umma_commit(smem_u32(&empty_bar[s]));
+        mma_scores(tG0 + (uint32_t)grp * 2 * CW, tH, tHl, sa, sa + KB * BLK, KB, idS);
+        umma_commit(smem_u32(&s_full[grp]));
+        pend[grp] = c;
+      }
+      if (pend[0] >= 0 && pend[1] >= 0) {
+        const int f = pend[0] < pend[1] ? 0 : 1;
+        accum(f);
+        accum(f ^ 1);
+      } else if (pend[0] >= 0) {
+        accum(0);
+      } else if (pend[1] >= 0) {
+        accum(1);
       }
       umma_commit(smem_u32(&done_bar));
     }
     __syncwarp();
   } else {
-    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
     const int rl = q * 32 + lane, r = r0 + rl;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const bool valid = r < count;
-    if (half == 0) row_to_tmem(a.h + (int64_t)(valid ? a.rows[r] : 0) * d, valid, RBM_LOG2E, d, tH + lane_sel, tHl + lane_sel);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&h_bar));
+    if (grp == 0) {
+      row_to_tmem(a.h + (int64_t)(valid ? a.rows[r] : 0) * d, valid, RBM_LOG2E, d, tH + lane_sel, tHl + lane_sel);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&h_bar));
+    }
     const int64_t tg = valid ? a.tgt[r] : -1;
-    const float lse2 = valid ? a.lse_in[r] * RBM_LOG2E : 0.f;
+    const float lse2 = valid ? a.lse_in[r] * RBM_LOG2E : INFINITY;  // rows beyond the count: 2^(-inf) = 0
     const float gscale = *a.dloss / (float)count;
-    for (int c = 0; c < NC; ++c) {
-      const int ph = c & 1, par = (c >> 1) & 1;
-      mbar_wait(smem_u32(&s_full[ph]), par);
+    const uint32_t tS = tG0 + lane_sel + (uint32_t)grp * 2 * CW, tGl = tS + CW;
+    for (int c = grp; c < NC; c += 2) {
+      mbar_wait(smem_u32(&s_full[grp]), (c >> 1) & 1);
       tc_fence_after();
-      const int v0 = c * CW + half * 32;
+#pragma unroll 1
+      for (int part = 0; part < CW / 16; ++part) {
+        const int v0 = c * CW + part * 16;
+        float bb[16];  // bias in the log2 domain minus the row's log-sum-exp; -inf beyond the vocabulary
+        if (v0 + 16 <= V1 && (a.bias == nullptr || a.bias_vec)) {
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t = a.bias ? ld4(a.bias + v0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bb[j] = fmaf(t.x, RBM_LOG2E, -lse2); bb[j + 1] = fmaf(t.y, RBM_LOG2E, -lse2);
+            bb[j + 2] = fmaf(t.z, RBM_LOG2E, -lse2); bb[j + 3] = fmaf(t.w, RBM_LOG2E, -lse2);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bb[j] = v0 + j < V1 ? fmaf(a.bias ? a.bias[v0 + j] : 0.f, RBM_LOG2E, -lse2) : -INFINITY;
+        }
         float v[16], lo[16];
-        tmem_ld16(tS + lane_sel + (uint32_t)(half * 32 + part * 16), v);
+        tmem_ld16(tS + (uint32_t)(part * 16), v);
+        const uint32_t ts = (uint32_t)(tg - (int64_t)v0);  // this row's target column inside the slice, if < 16
+        const bool hit = __any_sync(0xffffffffu, ts < 16u);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const int vv = v0 + part * 16 + j;
-          float p = (valid && vv < V1) ? ex2(v[j] + (a.bias ? a.bias[vv] * RBM_LOG2E : 0.f) - lse2) : 0.f;
-          if ((int64_t)vv == tg) p -= 1.f;
+          float p = ex2(v[j] + bb[j]);
+          if (hit && ts == (uint32_t)j) p -= 1.f;
           const float gg = p * gscale;
           v[j] = gg;
           lo[j] = lo_of(gg);
         }
-        tmem_st16(tS + lane_sel + (uint32_t)(half * 32 + part * 16), v);
-        tmem_st16(tGl + lane_sel + (uint32_t)(half * 32 + part * 16), lo);
+        tmem_st16(tS + (uint32_t)(part * 16), v);
+        tmem_st16(tGl + (uint32_t)(part * 16), lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&g_full[ph]));
+      if (lane == 0) mbar_arrive(smem_u32(&g_full[grp]));
     }
     mbar_wait(smem_u32(&done_bar), 0);
     tc_fence_after();
-    // dH row: the two warps of a quarter split the d columns
+    // dH row = D[:, 0:d] + D[:, d:2d]; the two groups split the d columns
     const int dc = d / 2;
-    for (int c0 = half * dc; c0 < (half + 1) * dc; c0 += 16) {
-      float o[16];
+    for (int c0 = grp * dc; c0 < (grp + 1) * dc; c0 += 16) {
+      float o[16], o2[16];
       tmem_ld16(tD + lane_sel + (uint32_t)c0, o);
+      tmem_ld16(tD + lane_sel + (uint32_t)(d + c0), o2);
       if (valid) {
         float* dst = a.dh_full + (int64_t)a.rows[r] * d + c0;
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) st4(dst + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+        for (int j = 0; j < 16; j += 4) st4(dst + j, make_float4(o[j] + o2[j], o[j + 1] + o2[j + 1], o[j + 2] + o2[j + 2], o[j + 3] + o2[j + 3]));
       }
     }
   }
@@ -351,22 +410,22 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
   }
 }
 
-// ------------------------------------------------------------------------------------- backward: dW and db
-// rows = vocab; TMEM: W raw [0,d) | W lo [d,2d) | S^T/G^T raw [2d,2d+64) | G^T lo | dW [2d+128, 3d+128)
-// stage: Hc chunk K-major raw | lo | MN-major raw | lo
+// dW and db: rows = vocab entries (W rows resident), the compacted hidden rows stream; row chunks are split over
+// blockIdx.y with a fixed-order reduction afterwards.
 __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __grid_constant__ CUtensorMap mapH, const __grid_constant__ CUtensorMap mapHl,
                                                                         const __grid_constant__ CUtensorMap mapHm,
                                                                         const __grid_constant__ CUtensorMap mapHml, const CeTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], s_full[2], g_full[2], w_bar, done_bar;
   __shared__ uint32_t tmem_base_slot;
-  __shared__ float lse_s[2][CW], tgt_s[2][CW];
+  __shared__ __align__(16) float lse_s[2][CW], tgt_s[2][CW];  // per group: statistics of the chunk's masked rows
   __shared__ float xb[2][128];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *a.count;
   const int d = a.d, KB = a.KB, ns = a.nstage, V1 = a.V1;
   const int S = gridDim.y, sp = blockIdx.y;
   const int NC = (count + CW - 1) / CW;
+  const int NL = NC > sp ? (NC - sp + S - 1) / S : 0;  // chunks of this split: sp, sp + S, ...
   const int v0 = blockIdx.x * 128;
   const uint32_t stage_bytes = 4 * KB * BLK;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -377,9 +436,9 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&g_full[i]), NSW);
+      mbar_init(smem_u32(&g_full[i]), NSW / 2);
     }
-    mbar_init(smem_u32(&w_bar), NSW);
+    mbar_init(smem_u32(&w_bar), NSW / 2);
     mbar_init(smem_u32(&done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -388,13 +447,12 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
-  const uint32_t tW = tmem, tWl = tmem + d, tS = tmem + 2 * d, tGl = tS + CW, tD = tS + 2 * CW;
+  const uint32_t tW = tmem, tWl = tmem + d, tG0 = tmem + 2 * d, tD = tG0 + 4 * CW;
 
   if (warp == 0) {
     if (elect_one()) {
-      int n = 0;
-      for (int c = sp; c < NC; c += S, ++n) {
-        const int s = n % ns;
+      for (int n = 0; n < NL; ++n) {
+        const int c = sp + n * S, s = n % ns;
         if (n >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((n / ns) - 1) & 1);
         const uint32_t bar = smem_u32(&full_bar[s]), sa = smem_base + s * stage_bytes;
         mbar_expect_tx(bar, stage_bytes);
@@ -408,93 +466,119 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), idD = make_idesc_tf32_ex(128, d, 0, 1);
+      const uint32_t idS = make_idesc_tf32_ex(128, CW, 0, 0), id2 = make_idesc_tf32_ex(128, 2 * d, 0, 1), id1 = make_idesc_tf32_ex(128, d, 0, 1);
       mbar_wait(smem_u32(&w_bar), 0);
       tc_fence_after();
-      int n = 0;
-      for (int c = sp; c < NC; c += S, ++n) {
-        const int s = n % ns, ph = n & 1, par = (n >> 1) & 1;
+      int pend[2] = {-1, -1};
+      auto accum = [&](int grp) {
+        const int n = pend[grp], s = n % ns;
+        const uint32_t tS = tG0 + (uint32_t)grp * 2 * CW;
+        mbar_wait(smem_u32(&g_full[grp]), (n >> 1) & 1);
+        tc_fence_after();
+        mma_accum2(tD, tS, tS + CW, smem_base + s * stage_bytes + 2 * KB * BLK, id2, id1, n == 0);
+        umma_commit(smem_u32(&empty_bar[s]));
+        pend[grp] = -1;
+      };
+      for (int n = 0; n < NL; ++n) {
+        const int s = n % ns, grp = n & 1;
+        if (pend[grp] >= 0) accum(grp);
         mbar_wait(smem_u32(&full_bar[s]), (n / ns) & 1);
         tc_fence_after();
         const uint32_t sa = smem_base + s * stage_bytes;
-        mma_scores(tS, tW, tWl, sa, sa + KB * BLK, KB, idS);
-        umma_commit(smem_u32(&s_full[ph]));
-        mbar_wait(smem_u32(&g_full[ph]), par);
-        tc_fence_after();
-        mma_accum(tD, tS, tGl, sa + 2 * KB * BLK, sa + 3 * KB * BLK, idD, n == 0);
-        umma_commit(smem_u32(&empty_bar[s]));
+        mma_scores(tG0 + (uint32_t)grp * 2 * CW, tW, tWl, sa, sa + KB * BLK, KB, idS);
+        umma_commit(smem_u32(&s_full[grp]));
+        pend[grp] = n;
+      }
+      if (pend[0] >= 0 && pend[1] >= 0) {
+        const int f = pend[0] < pend[1] ? 0 : 1;
+        accum(f);
+        accum(f ^ 1);
+      } else if (pend[0] >= 0) {
+        accum(0);
+      } else if (pend[1] >= 0) {
+        accum(1);
       }
       umma_commit(smem_u32(&done_bar));
     }
     __syncwarp();
   } else {
-    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
-    const int tid = sw * 32 + lane;
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int gt = q * 32 + lane;  // thread index inside the group (lane quarters arrive in warp order 2,3,0,1 -- any bijection works)
     const int rl = q * 32 + lane, vrow = v0 + rl;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const bool valid = vrow < V1;
-    if (half == 0) row_to_tmem(a.w + (int64_t)(valid ? vrow : 0) * d, valid, RBM_LOG2E, d, tW + lane_sel, tWl + lane_sel);
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&w_bar));
-    const float b2 = (a.bias && valid) ? a.bias[vrow] * RBM_LOG2E : 0.f;
+    if (grp == 0) {
+      row_to_tmem(a.w + (int64_t)(valid ? vrow : 0) * d, valid, RBM_LOG2E, d, tW + lane_sel, tWl + lane_sel);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&w_bar));
+    }
+    const float b2 = valid ? (a.bias ? a.bias[vrow] * RBM_LOG2E : 0.f) : -INFINITY;  // rows beyond the vocabulary: p = 0
     const float gscale = *a.dloss / (float)count;
+    const float frow = valid ? (float)vrow : -2.f;
+    const uint32_t tS = tG0 + lane_sel + (uint32_t)grp * 2 * CW, tGl = tS + CW;
     float bsum = 0.f;
-    int n = 0;
-    for (int c = sp; c < NC; c += S, ++n) {
-      const int ph = n & 1, par = (n >> 1) & 1;
-      // per-column (masked row) statistics of this chunk; the previous use of slot `ph` was two chunks ago
-      if (tid < CW) {
-        const int r = c * CW + tid;
-        lse_s[ph][tid] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
-        tgt_s[ph][tid] = r < count ? (float)a.tgt[r] : -1.f;
+    for (int n = grp; n < NL; n += 2) {
+      const int c = sp + n * S;
+      // statistics of the chunk's 64 masked rows (the group's previous chunk has been consumed: its g_full arrival
+      // came after the last read of these arrays)
+      named_bar_sync(1 + grp, 128);
+      if (gt < CW) {
+        const int r = c * CW + gt;
+        lse_s[grp][gt] = r < count ? a.lse_in[r] * RBM_LOG2E : INFINITY;  // columns beyond the count: p = 0
+        tgt_s[grp][gt] = r < count ? (float)a.tgt[r] : -1.f;
       }
-      named_bar_sync(1, NSW * 32);
-      mbar_wait(smem_u32(&s_full[ph]), par);
+      named_bar_sync(1 + grp, 128);
+      mbar_wait(smem_u32(&s_full[grp]), (n >> 1) & 1);
       tc_fence_after();
+#pragma unroll 1
+      for (int part = 0; part < CW / 16; ++part) {
+        float v[16], lo[16], ls[16], tc[16];
 #pragma unroll
-      for (int part = 0; part < 2; ++part) {
-        float v[16], lo[16];
-        const int cb = half * 32 + part * 16;
-        tmem_ld16(tS + lane_sel + (uint32_t)cb, v);
+        for (int j = 0; j < 16; j += 4) {
+          const float4 x = ld4(&lse_s[grp][part * 16 + j]), y = ld4(&tgt_s[grp][part * 16 + j]);
+          ls[j] = x.x; ls[j + 1] = x.y; ls[j + 2] = x.z; ls[j + 3] = x.w;
+          tc[j] = y.x; tc[j + 1] = y.y; tc[j + 2] = y.z; tc[j + 3] = y.w;
+        }
+        tmem_ld16(tS + (uint32_t)(part * 16), v);
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const float tcol = tgt_s[ph][cb + j];
-          float p = (valid && tcol >= 0.f) ? ex2(v[j] + b2 - lse_s[ph][cb + j]) : 0.f;
-          if (valid && tcol == (float)vrow) p -= 1.f;
+          float p = ex2(v[j] + b2 - ls[j]);
+          if (tc[j] == frow) p -= 1.f;
           const float gg = p * gscale;
           bsum += gg;
           v[j] = gg;
           lo[j] = lo_of(gg);
         }
-        tmem_st16(tS + lane_sel + (uint32_t)cb, v);
-        tmem_st16(tGl + lane_sel + (uint32_t)cb, lo);
+        tmem_st16(tS + (uint32_t)(part * 16), v);
+        tmem_st16(tGl + (uint32_t)(part * 16), lo);
       }
       tmem_st_wait();
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&g_full[ph]));
+      if (lane == 0) mbar_arrive(smem_u32(&g_full[grp]));
     }
-    xb[half][rl] = bsum;
+    xb[grp][rl] = bsum;
     mbar_wait(smem_u32(&done_bar), 0);
     tc_fence_after();
-    named_bar_sync(1, NSW * 32);
+    named_bar_sync(3, NSW * 32);
     float* pw = a.part_w + ((int64_t)sp * V1 + vrow) * d;
     const int dc = d / 2;
-    for (int c0 = half * dc; c0 < (half + 1) * dc; c0 += 16) {
-      float o[16];
-      if (n > 0) {
+    for (int c0 = grp * dc; c0 < (grp + 1) * dc; c0 += 16) {
+      float o[16], o2[16];
+      if (NL > 0) {
         tmem_ld16(tD + lane_sel + (uint32_t)c0, o);
+        tmem_ld16(tD + lane_sel + (uint32_t)(d + c0), o2);
       } else {
 #pragma unroll
-        for (int j = 0; j < 16; ++j) o[j] = 0.f;
+        for (int j = 0; j < 16; ++j) o[j] = o2[j] = 0.f;
       }
       if (valid) {
 #pragma unroll
-        for (int j = 0; j < 16; j += 4) st4(pw + c0 + j, make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]));
+        for (int j = 0; j < 16; j += 4) st4(pw + c0 + j, make_float4(o[j] + o2[j], o[j + 1] + o2[j + 1], o[j + 2] + o2[j + 2], o[j + 3] + o2[j + 3]));
       }
     }
-    if (half == 0 && valid) a.part_b[(int64_t)sp * V1 + vrow] = xb[0][rl] + xb[1][rl];
+    if (grp == 0 && valid) a.part_b[(int64_t)sp * V1 + vrow] = xb[0][rl] + xb[1][rl];
   }
   tc_fence_before();
   __syncthreads();
@@ -579,7 +663,7 @@ bool set_smem(K kern, size_t bytes, const char* name) {
 }  // namespace
 
 bool rbm_ce_tc_supported(int V1, int d, const void* h, const void* w) {
-  if (!tc_enabled() || (d != 32 && d != 64 && d != 128) || V1 < CW) return false;
+  if (!tc_enabled() || (d != 32 && d != 64) || V1 < CW) return false;  // backward: 4d + 256 TMEM columns
   if (((uintptr_t)h | (uintptr_t)w) & 15) return false;
   return get_encode() != nullptr;
 }
@@ -612,7 +696,11 @@ int rbm_ce_tc_fwd(const float* h, const int32_t* rows, const int64_t* tgt, const
   a.h = h; a.w = w; a.rows = rows; a.tgt = tgt; a.count = count; a.bias = bias; a.lse_out = lse; a.partial = partial; a.V1 = V1; a.d = d;
   a.KB = d / 32;
   const size_t stage = (size_t)2 * a.KB * BLK;
-  int ns = (int)((180 * 1024) / stage);
+  a.tmem_cols = 2 * d + 2 * CW <= 256 ? 256 : 512;
+  a.bias_vec = bias != nullptr && ((uintptr_t)bias & 15) == 0;
+  // d <= 64 needs 256 TMEM columns: three 32 KB stages keep the CTA under half an SM so that two CTAs co-reside (one
+  // wave for the cfg2 row count, and each CTA's waits are covered by the other)
+  int ns = a.tmem_cols == 256 ? (int)((108 * 1024) / stage) : (int)((180 * 1024) / stage);
   a.nstage = ns > 8 ? 8 : ns;
   const size_t smem = (size_t)a.nstage * stage + 1024;
   if (!set_smem(ce_fwd_tc_kernel, smem, "rbm_ce_fwd(tcgen05)")) return -1;
@@ -643,6 +731,7 @@ int rbm_ce_tc_bwd(const float* h, const int32_t* rows, const int64_t* tgt, const
   CeTcArgs a{};
   a.h = h; a.w = w; a.rows = rows; a.tgt = tgt; a.count = count; a.bias = bias; a.lse_in = lse; a.dloss = dloss;
   a.dh_full = dh_full; a.part_w = part_w; a.part_b = part_b; a.V1 = V1; a.d = d; a.KB = d / 32;
+  a.bias_vec = bias != nullptr && ((uintptr_t)bias & 15) == 0;
   const size_t stage = (size_t)4 * a.KB * BLK;
   int ns = (int)((192 * 1024) / stage);
   a.nstage = ns > 4 ? 4 : ns;
