@@ -396,10 +396,15 @@ struct DwParams {
   float* part_b;   // [S][N] column sums of A (the bias gradient), or nullptr
   int64_t M, tok_per_cta;
   int N, K, nblkA, nblkB, mtiles, nstage;
+  int wide;        // 1: one instruction per operand half against [B | B_lo | ones] (N = 2K + 32); 0: three products + bias pair
   uint32_t tmem_cols;
 };
-constexpr int DW_BIAS_N = 16;  // width of the all-ones B operand that turns the bias gradient into one more accumulator
+constexpr int DW_BIAS_N = 16;  // narrow mode: width of the all-ones B operand that turns the bias gradient into an accumulator
 
+// A tcgen05.mma costs its issuer ~40 cycles and the pipe max(N/2, ~16) cycles, so fewer and wider instructions win.  In
+// wide mode the B side of a stage is laid out as consecutive MN blocks  [x raw | x residual | all-ones]  and every 8-token
+// step needs two instructions per 128-row tile:  D += A.[x | x_lo | 1]  and  D += A_lo.[x | x_lo | 1]  (the A_lo.x_lo
+// product that comes along is below fp32 resolution).  dW = D[:, 0:K] + D[:, K:2K], db = D[:, 2K].
 __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
                                                        const DwParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -410,17 +415,15 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
   const int nblkA_pad = p.mtiles * 4;  // A blocks incl. zero padding up to a multiple of 128 rows of dW
   const uint32_t a_bytes = (uint32_t)nblkA_pad * DW_BLK, b_bytes = (uint32_t)p.nblkB * DW_BLK;
-  const uint32_t stage_bytes = 2 * (a_bytes + b_bytes);  // raw A | raw B | lo A | lo B
+  // stage: A raw | A residual | B raw | B residual | all-ones block
+  const uint32_t oAl = a_bytes, oB = 2 * a_bytes, oBl = 2 * a_bytes + b_bytes, oOnes = 2 * (a_bytes + b_bytes);
+  const uint32_t stage_bytes = oOnes + DW_BLK;
   const int64_t t0 = (int64_t)blockIdx.x * p.tok_per_cta;
   int64_t t1 = t0 + p.tok_per_cta;
   if (t1 > p.M) t1 = p.M;
   const int nst = t1 > t0 ? (int)((t1 - t0 + DW_TOK - 1) / DW_TOK) : 0;
-  // bias gradient: db = A^T . 1 -- an all-ones [8 tokens x 32 columns] block (swizzle-invariant) after the stages, and
-  // DW_BIAS_N extra accumulator columns per M tile behind the dW accumulators
-  const uint32_t off_ones = (uint32_t)p.nstage * stage_bytes;
-  const uint32_t bias_col = (uint32_t)(p.mtiles * p.K);
-  if (p.part_b)
-    for (int i = threadIdx.x; i < 256; i += blockDim.x) reinterpret_cast<float*>(gen + off_ones)[i] = 1.f;
+  const int NB = p.wide ? 2 * p.K + (p.part_b ? 32 : 0) : p.K;  // accumulator columns per M tile (narrow: + bias columns behind)
+  const uint32_t bias_col = (uint32_t)(p.mtiles * p.K);         // narrow mode
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.nstage; ++s) {
@@ -432,14 +435,18 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), p.tmem_cols);
-  // padding blocks of A (columns >= N) are never written by TMA: zero them once (raw and lo)
-  if (nblkA_pad > p.nblkA)
-    for (int s = 0; s < p.nstage; ++s)
+  for (int s = 0; s < p.nstage; ++s) {
+    uint8_t* st = gen + (size_t)s * stage_bytes;
+    // the all-ones block (swizzle-invariant) turns the bias gradient db = A^T . 1 into accumulator columns
+    for (int i = threadIdx.x; i < (int)(DW_BLK / 4); i += blockDim.x) reinterpret_cast<float*>(st + oOnes)[i] = 1.f;
+    // padding blocks of A (columns >= N) are never written by TMA: zero them once (raw and residual)
+    if (nblkA_pad > p.nblkA)
       for (int half = 0; half < 2; ++half) {
-        float4* z = reinterpret_cast<float4*>(gen + (size_t)s * stage_bytes + (size_t)half * (a_bytes + b_bytes) + (size_t)p.nblkA * DW_BLK);
+        float4* z = reinterpret_cast<float4*>(st + (size_t)half * a_bytes + (size_t)p.nblkA * DW_BLK);
         const int n4 = (nblkA_pad - p.nblkA) * DW_BLK / 16;
         for (int i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
+  }
   fence_proxy_async();
   tc_fence_before();
   __syncthreads();
@@ -458,35 +465,41 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
         mbar_expect_tx(bar, (uint32_t)(p.nblkA + p.nblkB) * DW_BLK);
         const int tok = (int)(t0 + (int64_t)g * DW_TOK);
         for (int j = 0; j < p.nblkA; ++j) tma_load_2d(sa + j * DW_BLK, &mapA, bar, j * 32, tok);
-        for (int j = 0; j < p.nblkB; ++j) tma_load_2d(sa + a_bytes + j * DW_BLK, &mapB, bar, j * 32, tok);
+        for (int j = 0; j < p.nblkB; ++j) tma_load_2d(sa + oB + j * DW_BLK, &mapB, bar, j * 32, tok);
       }
     }
   } else if (warp == 1) {
     if (elect_one()) {
-      const uint32_t idesc = make_idesc_tf32_ex(BM, p.K, 1, 1);
+      const uint32_t idesc = make_idesc_tf32_ex(BM, p.wide ? NB : p.K, 1, 1);
       const uint32_t idesc_b = make_idesc_tf32_ex(BM, DW_BIAS_N, 1, 1);
-      const uint64_t ones = make_sw128_desc_mn(smem_base + off_ones, DW_BLK);
       for (int g = 0; g < nst; ++g) {
         const int s = g % p.nstage;
         mbar_wait(smem_u32(&full_bar[s]), (g / p.nstage) & 1);
         mbar_wait(smem_u32(&split_bar[s]), (g / p.nstage) & 1);
         tc_fence_after();
-        const uint32_t sa = smem_base + s * stage_bytes, sl = sa + a_bytes + b_bytes;
+        const uint32_t sa = smem_base + s * stage_bytes;
         for (int mt = 0; mt < p.mtiles; ++mt) {
-          const uint32_t d = tmem_d + (uint32_t)(mt * p.K);
 #pragma unroll
           for (int k = 0; k < DW_TOK / UMMA_K; ++k) {  // 8 tokens = 1024 bytes inside every block
             const uint64_t a_raw = make_sw128_desc_mn(sa + mt * 4 * DW_BLK + k * 1024, DW_BLK);
-            const uint64_t a_lo = make_sw128_desc_mn(sl + mt * 4 * DW_BLK + k * 1024, DW_BLK);
-            const uint64_t b_raw = make_sw128_desc_mn(sa + a_bytes + k * 1024, DW_BLK);
-            const uint64_t b_lo = make_sw128_desc_mn(sl + a_bytes + k * 1024, DW_BLK);
-            umma_tf32(d, a_raw, b_lo, idesc, (g | k) != 0);
-            umma_tf32(d, a_lo, b_raw, idesc, 1);
-            umma_tf32(d, a_raw, b_raw, idesc, 1);
-            if (p.part_b) {
-              const uint32_t dbias = tmem_d + bias_col + (uint32_t)(mt * DW_BIAS_N);
-              umma_tf32(dbias, a_lo, ones, idesc_b, (g | k) != 0);
-              umma_tf32(dbias, a_raw, ones, idesc_b, 1);
+            const uint64_t a_lo = make_sw128_desc_mn(sa + oAl + mt * 4 * DW_BLK + k * 1024, DW_BLK);
+            const uint64_t b_raw = make_sw128_desc_mn(sa + oB + k * 1024, DW_BLK);  // wide: runs on into B residual and ones
+            if (p.wide) {
+              const uint32_t d = tmem_d + (uint32_t)(mt * NB);
+              umma_tf32(d, a_raw, b_raw, idesc, (g | k) != 0);
+              umma_tf32(d, a_lo, b_raw, idesc, 1);
+            } else {
+              const uint32_t d = tmem_d + (uint32_t)(mt * p.K);
+              const uint64_t b_lo = make_sw128_desc_mn(sa + oBl + k * 1024, DW_BLK);
+              umma_tf32(d, a_raw, b_lo, idesc, (g | k) != 0);
+              umma_tf32(d, a_lo, b_raw, idesc, 1);
+              umma_tf32(d, a_raw, b_raw, idesc, 1);
+              if (p.part_b) {
+                const uint64_t ones = make_sw128_desc_mn(sa + oOnes + k * 1024, DW_BLK);
+                const uint32_t dbias = tmem_d + bias_col + (uint32_t)(mt * DW_BIAS_N);
+                umma_tf32(dbias, a_lo, ones, idesc_b, (g | k) != 0);
+                umma_tf32(dbias, a_raw, ones, idesc_b, 1);
+              }
             }
           }
         }
@@ -502,8 +515,8 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
       mbar_wait(smem_u32(&full_bar[s]), (g / p.nstage) & 1);
       uint8_t* st = gen + (size_t)s * stage_bytes;
       // residuals of the blocks TMA wrote (A valid blocks, then B)
-      split_lo(reinterpret_cast<const float*>(st), reinterpret_cast<float*>(st + a_bytes + b_bytes), p.nblkA * DW_BLK / 16, tid, 128);
-      split_lo(reinterpret_cast<const float*>(st + a_bytes), reinterpret_cast<float*>(st + 2 * a_bytes + b_bytes), (int)(b_bytes / 16), tid, 128);
+      split_lo(reinterpret_cast<const float*>(st), reinterpret_cast<float*>(st + oAl), p.nblkA * DW_BLK / 16, tid, 128);
+      split_lo(reinterpret_cast<const float*>(st + oB), reinterpret_cast<float*>(st + oBl), (int)(b_bytes / 16), tid, 128);
       fence_proxy_async();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&split_bar[s]));
@@ -512,13 +525,21 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
     mbar_wait(smem_u32(&done_bar), 0);
     tc_fence_after();
     const int q = warp & 3;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     float* part = p.part + (int64_t)blockIdx.x * p.N * p.K;
     for (int mt = 0; mt < p.mtiles; ++mt) {
       const int n = mt * BM + q * 32 + lane;
+      const uint32_t dcol = tmem_d + lane_sel + (uint32_t)(mt * (p.wide ? NB : p.K));
       for (int c0 = 0; c0 < p.K; c0 += 32) {
         float v[32];
         if (nst > 0) {
-          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(mt * p.K + c0), v);
+          tmem_ld32(dcol + (uint32_t)c0, v);
+          if (p.wide) {
+            float v2[32];
+            tmem_ld32(dcol + (uint32_t)(p.K + c0), v2);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] += v2[j];
+          }
         } else {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 0.f;
@@ -530,7 +551,7 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
       }
       if (p.part_b) {
         float v[16];
-        if (nst > 0) tmem_ld16(tmem_d + ((uint32_t)(q * 32) << 16) + bias_col + (uint32_t)(mt * DW_BIAS_N), v);
+        if (nst > 0) tmem_ld16(p.wide ? dcol + (uint32_t)(2 * p.K) : tmem_d + lane_sel + bias_col + (uint32_t)(mt * DW_BIAS_N), v);
         else v[0] = 0.f;
         if (n < p.N) p.part_b[(int64_t)blockIdx.x * p.N + n] = v[0];
       }
@@ -691,11 +712,16 @@ bool encode_map_mn(CUtensorMap* map, const float* base, int64_t rows, int64_t co
 }
 int dw_stages(int N, int K, int* mtiles_out) {
   int mtiles = (N + BM - 1) / BM;
-  size_t stage = (size_t)2 * ((size_t)mtiles * 4 + K / 32) * DW_BLK;
-  int ns = (int)(((size_t)231424 - 2048) / stage);  // 1 KB alignment slack + the 1 KB all-ones block
+  size_t stage = (size_t)2 * ((size_t)mtiles * 4 + K / 32) * DW_BLK + DW_BLK;  // + the all-ones block
+  int ns = (int)(((size_t)231424 - 1024) / stage);
   if (ns > 8) ns = 8;
   *mtiles_out = mtiles;
   return ns;
+}
+// wide mode: accumulators [x | x_lo | ones] per 128-row tile must fit the 512 TMEM columns and one instruction (N <= 256)
+bool dw_wide(int N, int K, bool bias) {
+  const int nb = 2 * K + (bias ? 32 : 0);
+  return nb <= 256 && ((N + BM - 1) / BM) * nb <= 512;
 }
 }  // namespace
 
@@ -705,7 +731,7 @@ int rbm_tc_dw_splits(int64_t M) {
 }
 
 // the bias gradient rides along when its accumulator columns fit in TMEM next to dW
-bool rbm_tc_dw_bias_fused(int N, int K) { return ((N + BM - 1) / BM) * (K + DW_BIAS_N) <= 512; }
+bool rbm_tc_dw_bias_fused(int N, int K) { return dw_wide(N, K, true) || ((N + BM - 1) / BM) * (K + DW_BIAS_N) <= 512; }
 
 bool rbm_tc_dw_supported(int64_t M, int N, int K, int64_t lda, int64_t ldb, const void* a, const void* b) {
   if (tc_mode() != 0 || M < 1 || N % 32 != 0 || K % 32 != 0 || N > 256 || K > 256 || K < 32 || N < 32) return false;
@@ -729,10 +755,12 @@ int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb
   p.nstage = dw_stages(N, K, &p.mtiles);
   const int S = rbm_tc_dw_splits(M);
   p.tok_per_cta = rbm_cdiv(rbm_cdiv(M, S), DW_TOK) * DW_TOK;
+  p.wide = dw_wide(N, K, part_b != nullptr) ? 1 : 0;
+  const int per_tile = p.wide ? 2 * K + (part_b ? 32 : 0) : K + (part_b ? DW_BIAS_N : 0);
   uint32_t cols = 32;
-  while (cols < (uint32_t)(p.mtiles * (K + (part_b ? DW_BIAS_N : 0)))) cols <<= 1;
+  while (cols < (uint32_t)(p.mtiles * per_tile)) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = (size_t)p.nstage * 2 * ((size_t)p.mtiles * 4 + p.nblkB) * DW_BLK + 2048;
+  size_t smem = (size_t)p.nstage * (2 * ((size_t)p.mtiles * 4 + p.nblkB) + 1) * DW_BLK + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
