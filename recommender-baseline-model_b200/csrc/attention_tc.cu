@@ -1,14 +1,11 @@
-// attention_tc.cu -- attention FORWARD on the Blackwell tensor path for d_k = 32, L <= 240 (the cfg2 BERT4Rec shape).
-//
-// One CTA per (sequence, head).  TMA (3-D maps over [B, L, cols], 128-byte swizzle) brings the head's K, V and Q rows
-// into shared memory (one 128-byte swizzle row per token: d_k = 32 fp32); the same tiles serve as K-major operands
-// (q.k^T, contraction along the row) and MN-major operands (P.v, contraction along tokens).  Per 128-query tile:
-//     S = Q.K^T            tcgen05.mma kind::tf32, SMEM x SMEM -> TMEM [128 x Lp]
-//     softmax in place     8 warps, one thread per query row (tcgen05.ld 32x32b), masks, log2-domain ex2, dropout
-//                          (Philox), P and its TF32 residual written back to TMEM (tcgen05.st)
-//     O = P.V              tcgen05.mma with the A operand read from TMEM, V MN-major from SMEM -> TMEM [128 x 32]
-// Every product is 3xTF32-compensated (raw/lo copies of Q, K, V in SMEM, of P in TMEM): fp32-level accuracy.
-// Scores/probabilities never leave the SM.  Shapes outside (d_k == 32, L <= 240) use the mma.sync kernels (attention.cu).
+// attention_tc.cu -- attention forward and backward on the Blackwell tensor path for d_k = 32, L <= 256 (the cfg2
+// BERT4Rec shape).  Three persistent, warp-specialised kernels (forward, backward pass A: dQ, backward pass B: dK/dV),
+// one CTA per SM walking (sequence, head, 128-row tile) work items; see the comment block in front of each kernel.
+// Common ground: TMA (3-D maps over [B, L, cols]) streams token rows as 128-byte-swizzled tiles -- K-major tiles for
+// products that contract along d_k, MN-major (32-byte-atom swizzle) tiles for products that contract along tokens;
+// the 128 resident rows of a tile are TMEM A operands; scores / probabilities / score gradients only ever exist in
+// TMEM; every product is 3xTF32-compensated (operand = TF32 part + TF32 residual), i.e. fp32-level accuracy.
+// Shapes outside (d_k == 32, L <= 256) use the mma.sync kernels (attention.cu).
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -24,21 +21,6 @@ using rbm_mma::ex2;
 
 constexpr int DK = 32;
 constexpr int ROWB = DK * 4;     // 128 bytes per token row
-constexpr int SPLITC = 112;      // column split between the two softmax warps of a TMEM quarter
-constexpr int NSW = 8;           // softmax warps
-
-struct TcAttnArgs {
-  const int64_t* tok;
-  float* out;
-  float* stats;
-  int64_t ldo;
-  int L, LPK, h, NT, mask_mode;
-  float scale_log2;
-  uint32_t thr16;
-  float inv_keep;
-  uint64_t seed, site;
-  int dbg;  // bring-up bisect mask (RBM_TC_ATTN_DEBUG): 1 skip S mma, 2 skip PV mma, 4 skip tmem st, 8 skip tmem ld, 16 skip TMA, 32 skip split
-};
 
 __device__ __forceinline__ void split_lo_bytes(const uint8_t* src, uint8_t* dst, int n4, int tid, int nthr) {
   for (int i = tid; i < n4; i += nthr) {
@@ -48,224 +30,6 @@ __device__ __forceinline__ void split_lo_bytes(const uint8_t* src, uint8_t* dst,
     o.z = v.z - __uint_as_float(__float_as_uint(v.z) & 0xffffe000u);
     o.w = v.w - __uint_as_float(__float_as_uint(v.w) & 0xffffe000u);
     st4(reinterpret_cast<float*>(dst) + i * 4, o);
-  }
-}
-
-__global__ void __launch_bounds__(64 + 32 * NSW, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ,
-                                                                       const __grid_constant__ CUtensorMap mapK,
-                                                                       const __grid_constant__ CUtensorMap mapV, const TcAttnArgs a) {
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t load_bar, split_bar, s_full[2], p_full[2], o_full[2];
-  __shared__ uint32_t tmem_base_slot;
-  __shared__ float padk[256];
-  __shared__ float xmax[2][128], xsum[2][128];
-
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
-  const int L = a.L, LPK = a.LPK, NT = a.NT;
-  const uint32_t kv_bytes = (uint32_t)LPK * ROWB, q_bytes = (uint32_t)NT * 128 * ROWB;
-  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  // layout: K raw | K lo | V raw | V lo | Q raw | Q lo     (kv_bytes is a multiple of 2048: LPK % 16 == 0)
-  const uint32_t oK = 0, oKl = kv_bytes, oV = 2 * kv_bytes, oVl = 3 * kv_bytes, oQ = 4 * kv_bytes, oQl = 4 * kv_bytes + q_bytes;
-
-  if (threadIdx.x == 0) {
-    mbar_init(smem_u32(&load_bar), 1);
-    mbar_init(smem_u32(&split_bar), NSW);
-    for (int i = 0; i < 2; ++i) {
-      mbar_init(smem_u32(&s_full[i]), 1);
-      mbar_init(smem_u32(&p_full[i]), NSW);
-      mbar_init(smem_u32(&o_full[i]), 1);
-    }
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem = tmem_base_slot;
-  const uint32_t tS = tmem, tPl = tmem + (uint32_t)LPK, tO = tmem + (uint32_t)(2 * LPK);
-
-  if (warp == 0) {
-    if (elect_one()) {
-      const uint32_t bar = smem_u32(&load_bar);
-      if (a.dbg & 16) {
-        mbar_arrive(bar);
-      } else {
-        mbar_expect_tx(bar, 2 * kv_bytes + q_bytes);
-        tma_load_3d(smem_base + oK, &mapK, bar, hh * DK, 0, b);
-        tma_load_3d(smem_base + oV, &mapV, bar, hh * DK, 0, b);
-        for (int mt = 0; mt < NT; ++mt) tma_load_3d(smem_base + oQ + mt * 128 * ROWB, &mapQ, bar, hh * DK, mt * 128, b);
-      }
-    }
-  } else if (warp == 1) {
-    if (elect_one()) {
-      const uint32_t idS = make_idesc_tf32_ex(128, LPK, 0, 0);  // both operands K-major
-      const uint32_t idO = make_idesc_tf32_ex(128, DK, 0, 1);   // A from TMEM, V MN-major
-      mbar_wait(smem_u32(&load_bar), 0);
-      mbar_wait(smem_u32(&split_bar), 0);
-      tc_fence_after();
-      const uint64_t dK = make_sw128_desc(smem_base + oK), dKl = make_sw128_desc(smem_base + oKl);
-      for (int mt = 0; mt < NT; ++mt) {
-        const int ph = mt & 1, par = (mt >> 1) & 1;
-        const uint64_t dQ = make_sw128_desc(smem_base + oQ + mt * 128 * ROWB), dQl = make_sw128_desc(smem_base + oQl + mt * 128 * ROWB);
-#pragma unroll
-        for (int k = 0; k < DK / 8; ++k) {
-          if (a.dbg & 1) break;
-          const uint64_t o = (uint64_t)(k * 2);
-          umma_tf32(tS, dQ + o, dKl + o, idS, k != 0);
-          umma_tf32(tS, dQl + o, dK + o, idS, 1);
-          umma_tf32(tS, dQ + o, dK + o, idS, 1);
-        }
-        umma_commit(smem_u32(&s_full[ph]));
-        mbar_wait(smem_u32(&p_full[ph]), par);
-        tc_fence_after();
-        for (int kk = 0; kk < LPK / 8; ++kk) {
-          if (a.dbg & 2) break;
-          // 8 keys per step: one 8-row (1024-byte) swizzle atom of V; 8 TMEM columns of P
-          const uint64_t dV = make_sw128_desc_mn(smem_base + oV + kk * 1024, 0), dVl = make_sw128_desc_mn(smem_base + oVl + kk * 1024, 0);
-          umma_tf32_ts(tO, tS + kk * 8, dVl, idO, kk != 0);
-          umma_tf32_ts(tO, tPl + kk * 8, dV, idO, 1);
-          umma_tf32_ts(tO, tS + kk * 8, dV, idO, 1);
-        }
-        umma_commit(smem_u32(&o_full[ph]));
-      }
-    }
-    __syncwarp();
-  } else {
-    const int sw = warp - 2, q = warp & 3, half = sw >> 2;
-    const int tid = sw * 32 + lane;
-    const int64_t row0 = (int64_t)b * L;
-    for (int j = tid; j < 256; j += NSW * 32) padk[j] = (a.mask_mode == RBM_MASK_KEYPAD && j < L && a.tok[row0 + j] == 0) ? 1.f : 0.f;
-    // TF32 residual copies of K, V, Q
-    mbar_wait(smem_u32(&load_bar), 0);
-    if (!(a.dbg & 32)) {
-      split_lo_bytes(gen + oK, gen + oKl, (int)(kv_bytes / 16), tid, NSW * 32);
-      split_lo_bytes(gen + oV, gen + oVl, (int)(kv_bytes / 16), tid, NSW * 32);
-      split_lo_bytes(gen + oQ, gen + oQl, (int)(q_bytes / 16), tid, NSW * 32);
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(smem_u32(&split_bar));
-    named_bar_sync(1, NSW * 32);  // padk visible to all softmax warps
-
-    const int cbeg = half == 0 ? 0 : SPLITC;
-    const int cend = half == 0 ? (LPK < SPLITC ? LPK : SPLITC) : LPK;
-    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const int rl = q * 32 + lane;  // row within the 128-row tile
-    for (int mt = 0; mt < NT; ++mt) {
-      const int ph = mt & 1, par = (mt >> 1) & 1;
-      const int i = mt * 128 + rl;
-      mbar_wait(smem_u32(&s_full[ph]), par);
-      tc_fence_after();
-      // ---- pass 1: row maximum (log2 domain)
-      float mx = -INFINITY;
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16];
-        if (a.dbg & 8) {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
-        } else {
-          tmem_ld16(tS + lane_sel + (uint32_t)c0, v);
-        }
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int j = c0 + jj;
-          float x = v[jj] * a.scale_log2;
-          if (padk[j] != 0.f) x = RBM_PADFILL;
-          if (j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i)) x = -INFINITY;
-          mx = fmaxf(mx, x);
-        }
-      }
-      xmax[half][rl] = mx;
-      named_bar_sync(2 + q, 64);
-      mx = fmaxf(xmax[0][rl], xmax[1][rl]);
-      const float base = mx == -INFINITY ? 0.f : mx;
-      // ---- pass 2: probabilities, dropout, write P (raw + TF32 residual) back to TMEM
-      float sum = 0.f;
-      const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        float v[16], lo[16];
-        if (a.dbg & 8) {
-#pragma unroll
-          for (int jj = 0; jj < 16; ++jj) v[jj] = 0.f;
-        } else {
-          tmem_ld16(tS + lane_sel + (uint32_t)c0, v);
-        }
-        uint4 calls[4];
-        if (a.thr16) {
-          // rows i and i^8 (lanes l, l^8) share their Philox calls: each lane computes two and they are exchanged
-          uint4 c0r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, tile, g, rh * 2 + 0, c0 >> 4));
-          uint4 c1r = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, tile, g, rh * 2 + 1, c0 >> 4));
-          uint4 o0, o1;
-          o0.x = __shfl_xor_sync(0xffffffffu, c0r.x, 8); o0.y = __shfl_xor_sync(0xffffffffu, c0r.y, 8);
-          o0.z = __shfl_xor_sync(0xffffffffu, c0r.z, 8); o0.w = __shfl_xor_sync(0xffffffffu, c0r.w, 8);
-          o1.x = __shfl_xor_sync(0xffffffffu, c1r.x, 8); o1.y = __shfl_xor_sync(0xffffffffu, c1r.y, 8);
-          o1.z = __shfl_xor_sync(0xffffffffu, c1r.z, 8); o1.w = __shfl_xor_sync(0xffffffffu, c1r.w, 8);
-          calls[0] = rh ? o0 : c0r; calls[1] = rh ? o1 : c1r; calls[2] = rh ? c0r : o0; calls[3] = rh ? c1r : o1;
-        }
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) {
-          const int j = c0 + jj;
-          float x = v[jj] * a.scale_log2;
-          if (padk[j] != 0.f) x = RBM_PADFILL;
-          if (j >= L || (a.mask_mode == RBM_MASK_CAUSAL && j > i)) x = -INFINITY;
-          float p = ex2(x - base);
-          sum += p;
-          if (a.thr16) {
-            const int f = rh * 4 + (jj & 1) * 2 + ((jj >> 3) & 1);
-            p = rbm_attn_field(calls[(jj & 7) >> 1], f) >= a.thr16 ? p * a.inv_keep : 0.f;
-          }
-          v[jj] = p;
-          lo[jj] = p - __uint_as_float(__float_as_uint(p) & 0xffffe000u);
-        }
-        if (!(a.dbg & 4)) {
-          tmem_st16(tS + lane_sel + (uint32_t)c0, v);
-          tmem_st16(tPl + lane_sel + (uint32_t)c0, lo);
-        }
-      }
-      tmem_st_wait();
-      tc_fence_before();
-      xsum[half][rl] = sum;
-      __syncwarp();
-      if (lane == 0) mbar_arrive(smem_u32(&p_full[ph]));
-      named_bar_sync(2 + q, 64);
-      const float inv = 1.f / (xsum[0][rl] + xsum[1][rl]);
-      // ---- epilogue: O (16 columns per warp of the pair) scaled by 1/rowsum
-      mbar_wait(smem_u32(&o_full[ph]), par);
-      tc_fence_after();
-      float o[16];
-      if (a.dbg & 8) {
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) o[jj] = 0.f;
-      } else {
-        tmem_ld16(tO + lane_sel + (uint32_t)(half * 16), o);
-      }
-      float sv[16];
-      if (a.dbg & 64) tmem_ld16(tS + lane_sel, sv);  // warp-uniform
-      if ((a.dbg & 64) && i < L && half == 0) {  // bring-up: expose internals in the first output columns
-        o[0] = mx; o[1] = xsum[0][rl] + xsum[1][rl]; o[2] = sv[0]; o[3] = sv[1]; o[4] = o[4]; o[5] = (float)tmem; o[6] = (float)i;
-        float* dst = a.out + (row0 + i) * a.ldo + hh * DK;
-        for (int jj = 0; jj < 16; ++jj) dst[jj] = o[jj];
-      } else if (i < L) {
-        float* dst = a.out + (row0 + i) * a.ldo + hh * DK + half * 16;
-#pragma unroll
-        for (int jj = 0; jj < 16; jj += 4) st4(dst + jj, make_float4(o[jj] * inv, o[jj + 1] * inv, o[jj + 2] * inv, o[jj + 3] * inv));
-        if (half == 0 && a.stats) {
-          const int64_t sr = ((int64_t)blockIdx.x * L + i) * 2;
-          a.stats[sr] = mx;
-          a.stats[sr + 1] = inv;
-        }
-      }
-      tc_fence_before();
-      named_bar_sync(2 + q, 64);  // xmax/xsum reuse by the next tile
-    }
-  }
-  tc_fence_before();
-  __syncthreads();
-  if (warp == 1) {
-    tc_fence_after();
-    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -330,6 +94,420 @@ static void trace_end(unsigned long long* buf, const char* tag, cudaStream_t st)
   if (FILE* f = fopen(name, "wb")) {
     fwrite(host, sizeof(unsigned long long), TRACE_CAP + 1, f);
     fclose(f);
+  }
+}
+
+// =====================================================================================================
+// Forward on the tensor path: persistent, one CTA per SM walking the work items (sequence, head, 128-query tile).
+//   warp 0      TMA: the item's Q rows (one 128-row tile) and the key stream in chunks of <= 64 -- K chunks (K-major, for
+//               S = Q.K^T) and V chunks (MN-major, for O += P.V) through two 4-stage rings, issued in consumption order
+//   warps 14-15 TF32 residual copy of every staged tile
+//   warp 1      tcgen05.mma issue.  The whole score tile S [128 x Lp] lives in TMEM (exact row maxima need every key
+//               before the first exponential); the chunks of item n+1 are computed into the columns that item n's
+//               P.V products have just consumed, so the softmax warps never wait for scores at an item boundary.
+//   warps 2-9   two softmax groups (one warp per TMEM lane quarter, one thread per query row) taking chunks alternately:
+//               pass 1 row maximum over their chunks (exchanged through shared memory), pass 2 probabilities, dropout,
+//               P written over S in place and its TF32 residual into the group's own column block
+//   warps 10-13 per item: Q rows (pre-scaled to the log2 domain, raw + residual) into TMEM as the A operand, key classes
+//               (valid / padded / beyond the sequence) into shared memory; finished O scaled by 1/rowsum and written out
+//               through a swizzled staging tile (coalesced)
+//   TMEM columns: S/P [0,256) | P_lo of group g [256 + 64g, +64) | O [384,448): [P.V + P_lo.V | P.V_lo] | Q raw,lo [448,512)
+// =====================================================================================================
+constexpr int F_NSTG = 4;
+constexpr uint32_t F_TILE = 64 * ROWB;       // 8 KB: one [64 x 32] fp32 tile
+constexpr uint32_t F_STAGE = 2 * F_TILE;     // raw | residual
+constexpr uint32_t F_ROWS = 128 * ROWB;      // 16 KB: the Q rows of one tile
+constexpr uint32_t F_OUT = 32 * ROWB;        // 4 KB per operand warp: staging tile for coalesced O stores
+constexpr uint32_t F_S = 0, F_PL = 256, F_O = 384, F_Q = 448, F_QL = 480;
+constexpr int F_THREADS = 512;
+
+struct TcAttnArgs {
+  const int64_t* tok;
+  float* out;
+  float* stats;
+  int64_t ldo;
+  int L, LPK, h, NT, mask_mode, items;
+  float scale_log2;
+  uint32_t thr16;
+  float inv_keep;
+  uint64_t seed, site;
+};
+
+template <bool CAUSAL, bool DROP>
+__global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_constant__ CUtensorMap mapQ,
+                                                                   const __grid_constant__ CUtensorMap mapK,
+                                                                   const __grid_constant__ CUtensorMap mapV, const TcAttnArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t kfull[F_NSTG], ksplit[F_NSTG], kempty[F_NSTG], vfull[F_NSTG], vsplit[F_NSTG], vempty[F_NSTG], s_full[4],
+      p_full[2], pl_free[2], q_full, q_free, o_full, o_free, inv_full[2], rows_full, rows_free;
+  __shared__ uint32_t tmem_base_slot;
+  __shared__ __align__(16) float kuse[2][256], kfill[2][256];  // per key: 1 = score used as is / the value that replaces it
+  __shared__ float xmax[2][128], xsum[2][128], xinv[2][128];
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int L = a.L, LPK = a.LPK;
+  const int NU = LPK >> 4, NCH = (NU + 3) >> 2;  // 16-key units; chunks of <= 4 units, sizes as even as possible
+  const int n_items = a.items > (int)blockIdx.x ? (a.items - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t off_v = F_NSTG * F_STAGE, off_rows = 2 * F_NSTG * F_STAGE, off_out = off_rows + F_ROWS;
+
+  if (threadIdx.x == 0) {
+    for (int i = 0; i < F_NSTG; ++i) {
+      mbar_init(smem_u32(&kfull[i]), 1);
+      mbar_init(smem_u32(&ksplit[i]), 2);
+      mbar_init(smem_u32(&kempty[i]), 1);
+      mbar_init(smem_u32(&vfull[i]), 1);
+      mbar_init(smem_u32(&vsplit[i]), 2);
+      mbar_init(smem_u32(&vempty[i]), 1);
+      mbar_init(smem_u32(&s_full[i]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&p_full[i]), 4);
+      mbar_init(smem_u32(&pl_free[i]), 1);
+      mbar_init(smem_u32(&inv_full[i]), 4);
+    }
+    mbar_init(smem_u32(&q_full), 4);
+    mbar_init(smem_u32(&q_free), 1);
+    mbar_init(smem_u32(&o_full), 1);
+    mbar_init(smem_u32(&o_free), 4);
+    mbar_init(smem_u32(&rows_full), 1);
+    mbar_init(smem_u32(&rows_free), 4);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  // Work order shared by producer, split warps and issuer:  K(0,*);  then per item n, per chunk c:  V(n,c), K(n+1,c).
+  // Ring slots follow the global chunk counter g = n*NCH + c of each stream.
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------------------------------ TMA producer
+    if (elect_one()) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapQ) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapK) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&mapV) : "memory");
+      auto item_of = [&](int n, int& b, int& hh, int& mt) {
+        const int item = (int)blockIdx.x + n * (int)gridDim.x;
+        const int bh = item / a.NT;
+        mt = item - bh * a.NT; b = bh / a.h; hh = bh - b * a.h;
+      };
+      auto issue_rows = [&](int n) {
+        int b, hh, mt;
+        item_of(n, b, hh, mt);
+        if (n >= 1) mbar_wait(smem_u32(&rows_free), (n - 1) & 1);
+        mbar_expect_tx(smem_u32(&rows_full), F_ROWS);
+        tma_load_3d(smem_base + off_rows, &mapQ, smem_u32(&rows_full), hh * DK, mt * 128, b);
+      };
+      auto issue_k = [&](int n, int c) {
+        int b, hh, mt;
+        item_of(n, b, hh, mt);
+        const int g = n * NCH + c, s = g % F_NSTG, k0 = ((c * NU) / NCH) << 4;
+        if (g >= F_NSTG) mbar_wait(smem_u32(&kempty[s]), ((g / F_NSTG) - 1) & 1);
+        mbar_expect_tx(smem_u32(&kfull[s]), F_TILE);
+        tma_load_3d(smem_base + s * F_STAGE, &mapK, smem_u32(&kfull[s]), hh * DK, k0, b);
+      };
+      auto issue_v = [&](int n, int c) {
+        int b, hh, mt;
+        item_of(n, b, hh, mt);
+        const int g = n * NCH + c, s = g % F_NSTG, k0 = ((c * NU) / NCH) << 4;
+        if (g >= F_NSTG) mbar_wait(smem_u32(&vempty[s]), ((g / F_NSTG) - 1) & 1);
+        mbar_expect_tx(smem_u32(&vfull[s]), F_TILE);
+        tma_load_3d(smem_base + off_v + s * F_STAGE, &mapV, smem_u32(&vfull[s]), hh * DK, k0, b);
+      };
+      if (n_items > 0) {
+        issue_rows(0);
+        for (int c = 0; c < NCH; ++c) issue_k(0, c);
+      }
+      for (int n = 0; n < n_items; ++n) {
+        if (n + 1 < n_items) issue_rows(n + 1);
+        for (int c = 0; c < NCH; ++c) {
+          issue_v(n, c);
+          if (n + 1 < n_items) issue_k(n + 1, c);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------------------------------ MMA issuer
+    if (tmem != 0) __trap();  // the CTA owns all 512 columns: literal addresses keep the issue loop on the uniform datapath
+    if (elect_one()) {
+      constexpr uint32_t tmem = 0;
+      const uint32_t idO2 = make_idesc_tf32_ex(128, 2 * DK, 0, 1);  // A from TMEM, [V | V_lo] MN-major, N = 64
+      const uint32_t idO1 = make_idesc_tf32_ex(128, DK, 0, 1);
+      auto issue_s = [&](int n, int c) {
+        const int g = n * NCH + c, s = g % F_NSTG;
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        if (c == 0) mbar_wait(smem_u32(&q_full), n & 1);
+        mbar_wait(smem_u32(&kfull[s]), (g / F_NSTG) & 1);
+        mbar_wait(smem_u32(&ksplit[s]), (g / F_NSTG) & 1);
+        tc_fence_after();
+        const uint32_t idS = make_idesc_tf32_ex(128, nh, 0, 0);
+        const uint32_t sa = smem_base + s * F_STAGE;
+        const uint64_t dK = make_sw128_desc(sa), dKl = make_sw128_desc(sa + F_TILE);
+        const uint32_t tS = tmem + F_S + (uint32_t)k0;
+#pragma unroll
+        for (int k = 0; k < DK / 8; ++k) {
+          const uint64_t o = (uint64_t)(k * 2);
+          umma_tf32_ts(tS, tmem + F_Q + k * 8, dKl + o, idS, k != 0);
+          umma_tf32_ts(tS, tmem + F_QL + k * 8, dK + o, idS, 1);
+          umma_tf32_ts(tS, tmem + F_Q + k * 8, dK + o, idS, 1);
+        }
+        umma_commit(smem_u32(&kempty[s]));
+        umma_commit(smem_u32(&s_full[c]));
+        if (c == NCH - 1) umma_commit(smem_u32(&q_free));  // Q of this item has been consumed
+      };
+      auto issue_pv = [&](int n, int c) {
+        const int g = n * NCH + c, s = g % F_NSTG, grp = g & 1;
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        mbar_wait(smem_u32(&p_full[grp]), (g >> 1) & 1);
+        if (c == 0 && n >= 1) mbar_wait(smem_u32(&o_free), (n - 1) & 1);
+        mbar_wait(smem_u32(&vfull[s]), (g / F_NSTG) & 1);
+        mbar_wait(smem_u32(&vsplit[s]), (g / F_NSTG) & 1);
+        tc_fence_after();
+        const uint32_t sa = smem_base + off_v + s * F_STAGE;
+        const uint32_t tP = tmem + F_S + (uint32_t)k0, tPl = tmem + F_PL + (uint32_t)grp * 64;
+        for (int kk = 0; kk < nh / 8; ++kk) {
+          const uint64_t dV2 = make_sw128_desc_mn(sa + kk * 1024, F_TILE);  // second MN block = the residual tile
+          const uint64_t dV1 = make_sw128_desc_mn(sa + kk * 1024, 0);
+          umma_tf32_ts(tmem + F_O, tP + kk * 8, dV2, idO2, (c | kk) != 0);  // [P.V | P.V_lo]
+          umma_tf32_ts(tmem + F_O, tPl + kk * 8, dV1, idO1, 1);             // P_lo.V
+        }
+        umma_commit(smem_u32(&vempty[s]));
+        umma_commit(smem_u32(&pl_free[grp]));
+        if (c == NCH - 1) umma_commit(smem_u32(&o_full));
+      };
+      if (n_items > 0)
+        for (int c = 0; c < NCH; ++c) issue_s(0, c);
+      for (int n = 0; n < n_items; ++n)
+        for (int c = 0; c < NCH; ++c) {
+          issue_pv(n, c);
+          if (n + 1 < n_items) issue_s(n + 1, c);
+        }
+    }
+    __syncwarp();
+  } else if (warp < 10) {
+    // ------------------------------------------------------------------------------------------ softmax groups
+    const int q = warp & 3, grp = (warp - 2) >> 2;
+    const int rl = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const uint32_t thr_hi = a.thr16 << 16;
+    const uint32_t tS = tmem + lane_sel + F_S, tPl = tmem + lane_sel + F_PL + (uint32_t)grp * 64;
+    for (int n = 0; n < n_items; ++n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, mt = item - bh * a.NT;
+      const int i = mt * 128 + rl;
+      const bool warp_live = mt * 128 + q * 32 < L;  // a warp whose 32 rows all lie beyond the sequence only keeps the hand-shakes going
+      const float* ku = kuse[n & 1];
+      const float* kf = kfill[n & 1];
+      // ---- pass 1: row maximum (log2 domain) over this group's chunks
+      float mx = -INFINITY;
+      for (int c = 0; c < NCH; ++c) {
+        if (((n * NCH + c) & 1) != grp) continue;
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        mbar_wait(smem_u32(&s_full[c]), n & 1);
+        tc_fence_after();
+        if (warp_live) {
+          for (int c0 = 0; c0 < nh; c0 += 16) {
+            const int j0 = k0 + c0;
+            float v[16];
+            tmem_ld16(tS + (uint32_t)j0, v);
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 u = ld4(ku + j0 + jj), f = ld4(kf + j0 + jj);
+              float x0 = u.x != 0.f ? v[jj] : f.x, x1 = u.y != 0.f ? v[jj + 1] : f.y, x2 = u.z != 0.f ? v[jj + 2] : f.z,
+                    x3 = u.w != 0.f ? v[jj + 3] : f.w;
+              if (CAUSAL) {
+                if (j0 + jj > i) x0 = -INFINITY;
+                if (j0 + jj + 1 > i) x1 = -INFINITY;
+                if (j0 + jj + 2 > i) x2 = -INFINITY;
+                if (j0 + jj + 3 > i) x3 = -INFINITY;
+              }
+              mx = fmaxf(mx, fmaxf(fmaxf(x0, x1), fmaxf(x2, x3)));
+            }
+          }
+        }
+      }
+      xmax[grp][rl] = mx;
+      named_bar_sync(2 + q, 64);
+      mx = fmaxf(xmax[0][rl], xmax[1][rl]);
+      const float base = mx == -INFINITY ? 0.f : mx;
+      // ---- pass 2: probabilities, dropout, P (raw in place, residual into the group's block)
+      float sum = 0.f;
+      for (int c = 0; c < NCH; ++c) {
+        const int g = n * NCH + c;
+        if ((g & 1) != grp) continue;
+        const int k0 = ((c * NU) / NCH) << 4, nh = ((((c + 1) * NU) / NCH) << 4) - k0;
+        if (g >= 2) {  // the group's previous chunk has been multiplied into O: its residual block is free again
+          mbar_wait(smem_u32(&pl_free[grp]), ((g >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        if (warp_live) {
+          for (int c0 = 0; c0 < nh; c0 += 16) {
+            const int j0 = k0 + c0;
+            uint32_t rs[16];
+            tmem_ld16_issue(tS + (uint32_t)j0, rs);
+            KeepWords kw;
+            if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM read
+            float us[16], fs[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; jj += 4) {
+              const float4 u = ld4(ku + j0 + jj), f = ld4(kf + j0 + jj);
+              us[jj] = u.x; us[jj + 1] = u.y; us[jj + 2] = u.z; us[jj + 3] = u.w;
+              fs[jj] = f.x; fs[jj + 1] = f.y; fs[jj + 2] = f.z; fs[jj + 3] = f.w;
+            }
+            tmem_ld_wait16(rs);
+            float v[16], lo[16];
+#pragma unroll
+            for (int jj = 0; jj < 16; ++jj) {
+              float x = us[jj] != 0.f ? __uint_as_float(rs[jj]) : fs[jj];
+              if (CAUSAL && j0 + jj > i) x = -INFINITY;
+              float p = ex2(x - base);
+              sum += p;
+              if (DROP) p = attn_keep_bit(kw, jj, thr_hi) ? p * a.inv_keep : 0.f;
+              v[jj] = p;
+              lo[jj] = p - __uint_as_float(__float_as_uint(p) & 0xffffe000u);
+            }
+            tmem_st16(tS + (uint32_t)j0, v);
+            tmem_st16(tPl + (uint32_t)c0, lo);
+          }
+          tmem_st_wait();
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&p_full[grp]));
+      }
+      xsum[grp][rl] = sum;
+      named_bar_sync(2 + q, 64);
+      if (grp == 0) {
+        const float inv = 1.f / (xsum[0][rl] + xsum[1][rl]);
+        xinv[n & 1][rl] = inv;
+        if (i < L && a.stats) {
+          const int64_t sr = ((int64_t)bh * L + i) * 2;
+          a.stats[sr] = mx;
+          a.stats[sr + 1] = inv;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&inv_full[n & 1]));
+      }
+      named_bar_sync(2 + q, 64);  // xmax / xsum are free for the next item
+    }
+  } else if (warp < 14) {
+    // ------------------------------------------------------------------------------------------ operand / output warps
+    const int q = warp & 3, rl = q * 32 + lane, t128 = (warp - 10) * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    float* stage = reinterpret_cast<float*>(gen + off_out + (warp - 10) * F_OUT);
+    float qv[32];
+    float u0 = 0.f, f0 = 0.f, u1 = 0.f, f1 = 0.f;  // classes of keys t128 and t128 + 128 of the item being staged
+    auto key_class = [&](int b, int j, float& u, float& f) {
+      if (j >= L) { u = 0.f; f = -INFINITY; }                                                  // beyond the sequence
+      else if (a.mask_mode == RBM_MASK_KEYPAD && a.tok[(int64_t)b * L + j] == 0) { u = 0.f; f = RBM_PADFILL; }  // padding token: -1e9
+      else { u = 1.f; f = 0.f; }
+    };
+    auto load_item = [&](int n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int b = (item / a.NT) / a.h;
+      key_class(b, t128, u0, f0);
+      key_class(b, t128 + 128, u1, f1);
+      mbar_wait(smem_u32(&rows_full), n & 1);
+      const float* qs = reinterpret_cast<const float*>(gen + off_rows) + rl * DK;
+#pragma unroll
+      for (int c = 0; c < 32; c += 4) {
+        const int sc = ((c >> 2) ^ (rl & 7)) << 2;  // 128-byte swizzle: 16-byte chunk c of row r sits at c ^ (r & 7)
+        const float4 x = ld4(qs + sc);
+        qv[c] = x.x * a.scale_log2; qv[c + 1] = x.y * a.scale_log2; qv[c + 2] = x.z * a.scale_log2; qv[c + 3] = x.w * a.scale_log2;
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rows_free));
+    };
+    auto store_o = [&](int n) {
+      const int item = (int)blockIdx.x + n * (int)gridDim.x;
+      const int bh = item / a.NT, mt = item - bh * a.NT, b = bh / a.h, hh = bh - b * a.h;
+      mbar_wait(smem_u32(&inv_full[n & 1]), (n >> 1) & 1);
+      const float inv = xinv[n & 1][rl];
+      mbar_wait(smem_u32(&o_full), n & 1);
+      tc_fence_after();
+      float* dst = stage + lane * DK;
+#pragma unroll
+      for (int part = 0; part < 2; ++part) {
+        float x[16], y[16];
+        tmem_ld16(tmem + lane_sel + F_O + part * 16, x);
+        tmem_ld16(tmem + lane_sel + F_O + DK + part * 16, y);
+#pragma unroll
+        for (int c = 0; c < 16; c += 4) {
+          const int ch = part * 4 + (c >> 2);
+          st4(dst + ((ch ^ (lane & 7)) << 2), make_float4((x[c] + y[c]) * inv, (x[c + 1] + y[c + 1]) * inv, (x[c + 2] + y[c + 2]) * inv,
+                                                          (x[c + 3] + y[c + 3]) * inv));
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&o_free));
+      const int64_t row0 = (int64_t)b * L + mt * 128 + q * 32;
+      const int rows_ok = L - (mt * 128 + q * 32);
+      float* base = a.out + row0 * a.ldo + hh * DK;
+#pragma unroll
+      for (int it = 0; it < 8; ++it) {
+        const int r = it * 4 + (lane >> 3), ch = lane & 7;
+        if (r < rows_ok) st4(base + r * a.ldo + ch * 4, ld4(stage + r * DK + ((ch ^ (r & 7)) << 2)));
+      }
+      __syncwarp();
+    };
+    if (n_items > 0) load_item(0);
+    for (int n = 0; n < n_items; ++n) {
+      kuse[n & 1][t128] = u0; kfill[n & 1][t128] = f0;
+      kuse[n & 1][t128 + 128] = u1; kfill[n & 1][t128 + 128] = f1;
+      if (n >= 1) {
+        mbar_wait(smem_u32(&q_free), (n - 1) & 1);  // every S chunk of the previous item has read its Q
+        tc_fence_after();
+      }
+      {
+        float t16[16];
+#pragma unroll
+        for (int part = 0; part < 2; ++part) {
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = qv[part * 16 + c];
+          tmem_st16(tmem + lane_sel + F_Q + part * 16, t16);
+#pragma unroll
+          for (int c = 0; c < 16; ++c) t16[c] = t16[c] - __uint_as_float(__float_as_uint(t16[c]) & 0xffffe000u);
+          tmem_st16(tmem + lane_sel + F_QL + part * 16, t16);
+        }
+        tmem_st_wait();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&q_full));
+      // O is single-buffered: the previous item's result has to leave before this item's first P.V
+      if (n >= 1) store_o(n - 1);
+      if (n + 1 < n_items) load_item(n + 1);
+    }
+    if (n_items > 0) store_o(n_items - 1);
+  } else {
+    // ------------------------------------------------------------------------------------------ TF32 residual copies
+    const int tid = (warp - 14) * 32 + lane;
+    auto split = [&](uint64_t* full, uint64_t* done, uint32_t off, int g) {
+      const int s = g % F_NSTG;
+      mbar_wait(smem_u32(&full[s]), (g / F_NSTG) & 1);
+      uint8_t* st = gen + off + (size_t)s * F_STAGE;
+      split_lo_bytes(st, st + F_TILE, (int)(F_TILE / 16), tid, 64);
+      fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&done[s]));
+    };
+    if (n_items > 0)
+      for (int c = 0; c < NCH; ++c) split(kfull, ksplit, 0, c);
+    for (int n = 0; n < n_items; ++n)
+      for (int c = 0; c < NCH; ++c) {
+        split(vfull, vsplit, off_v, n * NCH + c);
+        if (n + 1 < n_items) split(kfull, ksplit, 0, (n + 1) * NCH + c);
+      }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
   }
 }
 
@@ -1203,7 +1381,7 @@ bool tc_enabled() {
 
 bool rbm_attn_fwd_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t ldv, int64_t ldo, const void* q, const void* k,
                                const void* v, const void* out) {
-  if (!tc_enabled() || dk != DK || L < 1 || L > 240) return false;  // TMEM: 2*Lp (P raw + residual) + 32 (O) <= 512 columns
+  if (!tc_enabled() || dk != DK || L < 1 || L > 256) return false;  // the score tile is one TMEM region of Lp <= 256 columns
   if (ldq % 4 || ldk % 4 || ldv % 4 || ldo % 4) return false;
   if (((uintptr_t)q | (uintptr_t)k | (uintptr_t)v | (uintptr_t)out) & 15) return false;
   return get_encode() != nullptr;
@@ -1214,8 +1392,8 @@ int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t 
                            uint64_t seed, uint64_t site, cudaStream_t st) {
   const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
   CUtensorMap mapQ, mapK, mapV;
-  if (!encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) || !encode_map3(&mapK, k, B, L, h * DK, ldk, LPK, false) ||
-      !encode_map3(&mapV, v, B, L, h * DK, ldv, LPK, true)) {
+  if (!encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) || !encode_map3(&mapK, k, B, L, h * DK, ldk, 64, false) ||
+      !encode_map3(&mapV, v, B, L, h * DK, ldv, 64, true)) {
     rbm_set_error("rbm_attn_fwd(tcgen05): cuTensorMapEncodeTiled failed");
     return -1;
   }
@@ -1223,21 +1401,26 @@ int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t 
   a.tok = tok; a.out = out; a.stats = stats; a.ldo = ldo; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode;
   a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
-  {
-    const char* e = getenv("RBM_TC_ATTN_DEBUG");
-    a.dbg = e ? atoi(e) : 0;
-  }
-  size_t smem = (size_t)4 * LPK * ROWB + (size_t)2 * NT * 128 * ROWB + 1024;
+  a.items = B * h * NT;
+  const size_t smem = (size_t)2 * F_NSTG * F_STAGE + F_ROWS + 4 * F_OUT + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+    cudaError_t e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(attn_fwd_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) {
       rbm_set_error("rbm_attn_fwd(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
     }
     attr_set = true;
   }
-  attn_fwd_tc_kernel<<<B * h, 64 + 32 * NSW, smem, st>>>(mapQ, mapK, mapV, a);
+  const bool causal = mask_mode == RBM_MASK_CAUSAL, drop = a.thr16 != 0;
+  const int grid = a.items < RBM_NUM_SMS ? a.items : RBM_NUM_SMS;
+  if (causal && drop) attn_fwd_tc_kernel<true, true><<<grid, F_THREADS, smem, st>>>(mapQ, mapK, mapV, a);
+  else if (causal) attn_fwd_tc_kernel<true, false><<<grid, F_THREADS, smem, st>>>(mapQ, mapK, mapV, a);
+  else if (drop) attn_fwd_tc_kernel<false, true><<<grid, F_THREADS, smem, st>>>(mapQ, mapK, mapV, a);
+  else attn_fwd_tc_kernel<false, false><<<grid, F_THREADS, smem, st>>>(mapQ, mapK, mapV, a);
   RBM_LAUNCH_CHECK("rbm_attn_fwd(tcgen05)");
   return 0;
 }
