@@ -413,8 +413,10 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const int nblkA_pad = p.mtiles * 4;  // A blocks incl. zero padding up to a multiple of 128 rows of dW
-  const uint32_t a_bytes = (uint32_t)nblkA_pad * DW_BLK, b_bytes = (uint32_t)p.nblkB * DW_BLK;
+  // No padding of A up to a multiple of 128 dW rows: the last M tile's descriptor simply runs on into the blocks that
+  // follow (A residual, B ...), which hold finite staged data; the accumulator rows they produce (n >= N) are never read.
+  // B raw + B residual + ones are >= 3 blocks, enough for the <= 3 blocks the last residual tile overruns.
+  const uint32_t a_bytes = (uint32_t)p.nblkA * DW_BLK, b_bytes = (uint32_t)p.nblkB * DW_BLK;
   // stage: A raw | A residual | B raw | B residual | all-ones block
   const uint32_t oAl = a_bytes, oB = 2 * a_bytes, oBl = 2 * a_bytes + b_bytes, oOnes = 2 * (a_bytes + b_bytes);
   const uint32_t stage_bytes = oOnes + DW_BLK;
@@ -439,13 +441,6 @@ __global__ void __launch_bounds__(192, 1) tc_dw_kernel(const __grid_constant__ C
     uint8_t* st = gen + (size_t)s * stage_bytes;
     // the all-ones block (swizzle-invariant) turns the bias gradient db = A^T . 1 into accumulator columns
     for (int i = threadIdx.x; i < (int)(DW_BLK / 4); i += blockDim.x) reinterpret_cast<float*>(st + oOnes)[i] = 1.f;
-    // padding blocks of A (columns >= N) are never written by TMA: zero them once (raw and residual)
-    if (nblkA_pad > p.nblkA)
-      for (int half = 0; half < 2; ++half) {
-        float4* z = reinterpret_cast<float4*>(st + (size_t)half * a_bytes + (size_t)p.nblkA * DW_BLK);
-        const int n4 = (nblkA_pad - p.nblkA) * DW_BLK / 16;
-        for (int i = threadIdx.x; i < n4; i += blockDim.x) z[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
   }
   fence_proxy_async();
   tc_fence_before();
@@ -712,7 +707,7 @@ bool encode_map_mn(CUtensorMap* map, const float* base, int64_t rows, int64_t co
 }
 int dw_stages(int N, int K, int* mtiles_out) {
   int mtiles = (N + BM - 1) / BM;
-  size_t stage = (size_t)2 * ((size_t)mtiles * 4 + K / 32) * DW_BLK + DW_BLK;  // + the all-ones block
+  size_t stage = (size_t)2 * ((size_t)N / 32 + K / 32) * DW_BLK + DW_BLK;  // + the all-ones block
   int ns = (int)(((size_t)231424 - 1024) / stage);
   if (ns > 8) ns = 8;
   *mtiles_out = mtiles;
@@ -760,7 +755,7 @@ int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb
   uint32_t cols = 32;
   while (cols < (uint32_t)(p.mtiles * per_tile)) cols <<= 1;
   p.tmem_cols = cols;
-  size_t smem = (size_t)p.nstage * (2 * ((size_t)p.mtiles * 4 + p.nblkB) + 1) * DW_BLK + 1024;
+  size_t smem = (size_t)p.nstage * (2 * ((size_t)p.nblkA + p.nblkB) + 1) * DW_BLK + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_dw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
