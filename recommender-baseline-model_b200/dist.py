@@ -63,7 +63,13 @@ class GradSync:
             g = p.grad if p.grad.is_contiguous() else p.grad.contiguous()
             p.grad = g
             rows.append((g.data_ptr(), n, o))
-        return torch.tensor(rows, dtype=torch.int64).to(self.bucket.device)
+        # gradient buffers keep their addresses from step to step: the device copy of the table is reused (a pageable
+        # host->device copy every step would block the host until the stream has drained)
+        key = tuple(r[0] for r in rows)
+        if getattr(self, "_tab_key", None) != key:
+            self._tab = torch.tensor(rows, dtype=torch.int64).to(self.bucket.device)
+            self._tab_key = key
+        return self._tab
 
     def allreduce_grads(self):
         if self.world == 1:

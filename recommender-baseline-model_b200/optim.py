@@ -65,7 +65,14 @@ class FusedAdam(torch.optim.Optimizer):
             if cmap is None:
                 cmap = self._chunk_map(sizes, dev)
                 self._table_cache = {key: cmap}
-            desc = torch.tensor(table, dtype=torch.int64).to(dev)  # rbm_adam_tensor[] : 5 x 8-byte fields
+            # rbm_adam_tensor[] : 5 x 8-byte fields.  Addresses rarely change from step to step (the caching allocator
+            # hands the same gradient blocks back): the device copy is reused -- a pageable host->device copy every
+            # step would block the host until the stream has drained
+            cache = self.__dict__.setdefault("_desc_cache", {})
+            dkey = tuple(table)
+            if gi not in cache or cache[gi][0] != dkey:
+                cache[gi] = (dkey, torch.tensor(table, dtype=torch.int64).to(dev))
+            desc = cache[gi][1]
             b1, b2 = group["betas"]
             check(lib.rbm_adam_multi(ptr(desc), ptr(cmap), cmap.shape[0], float(group["lr"]), float(b1), float(b2),
                                      float(group["eps"]), float(group["weight_decay"]), steps.pop(), stream()), "adam_multi")
