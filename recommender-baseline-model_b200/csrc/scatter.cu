@@ -193,11 +193,29 @@ __global__ void __launch_bounds__(256) segment_combine_kernel(const uint32_t* __
   if ((int64_t)key == padding_idx) return;
   if (s > 0 && keys[s - 1] == key) return;                 // not a head
   if (!(s + SEG_CHUNK < n && keys[s + SEG_CHUNK] == key)) return;  // single piece: already in grad
+  // Number of follow-up pieces (t = s + k*SEG_CHUNK still inside the segment): gallop, then bisect -- a popular row (the
+  // BERT mask token holds ~15 % of a batch) has hundreds of pieces, and the ordered sum below wants its loads issued in
+  // independent batches instead of one dependent load per iteration.
+  int64_t lo = 1, hi = 2;  // invariant: piece lo exists
+  while (s + hi * SEG_CHUNK < n && keys[s + hi * SEG_CHUNK] == key) { lo = hi; hi *= 2; }
+  while (hi - lo > 1) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (s + mid * SEG_CHUNK < n && keys[s + mid * SEG_CHUNK] == key) lo = mid; else hi = mid;
+  }
+  const int64_t np = lo;  // pieces 1..np follow the head piece
+  const int64_t p0 = s / SEG_CHUNK;
   for (int c4 = lane; c4 < d4; c4 += gw) {
-    float4 acc = ld4(pieces + (((s / SEG_CHUNK) * 2 + 1) * (int64_t)d4 + c4) * 4);
-    for (int64_t t = s + SEG_CHUNK; t < n && keys[t] == key; t += SEG_CHUNK) {
-      float4 v = ld4(pieces + (((t / SEG_CHUNK) * 2 + 0) * (int64_t)d4 + c4) * 4);
-      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    float4 acc = ld4(pieces + ((p0 * 2 + 1) * (int64_t)d4 + c4) * 4);
+    for (int64_t k0 = 1; k0 <= np; k0 += 16) {
+      float4 v[16];
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        v[u] = k0 + u <= np ? ld4(pieces + (((p0 + k0 + u) * 2 + 0) * (int64_t)d4 + c4) * 4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 16; ++u)
+        if (k0 + u <= np) {  // same order as the piece-tree contract: ascending, one rounding per piece
+          acc.x = __fadd_rn(acc.x, v[u].x); acc.y = __fadd_rn(acc.y, v[u].y); acc.z = __fadd_rn(acc.z, v[u].z); acc.w = __fadd_rn(acc.w, v[u].w);
+        }
     }
     float* g = grad + ((int64_t)key * d4 + c4) * 4;
     float4 o = ld4(g);
