@@ -167,11 +167,29 @@ __global__ void __launch_bounds__(256) segment_pieces_kernel(const uint32_t* __r
   int64_t e = s + SEG_CHUNK < n ? s + SEG_CHUNK : n;
   bool more = e < n && keys[e] == key;        // the segment continues past this piece
   bool single = off == 0 && !more;
+  // contributions of this piece: slots [s, s + cnt); the segment end inside the window by bisection (keys are sorted), so
+  // that the ordered sum below can issue its loads in independent batches
+  int64_t cnt = e - s;
+  if (!more && keys[e - 1] != key) {
+    int64_t lo = 0, hi = e - s - 1;  // keys[s + lo] == key, keys[s + hi] != key
+    while (hi - lo > 1) {
+      const int64_t mid = (lo + hi) >> 1;
+      if (keys[s + mid] == key) lo = mid; else hi = mid;
+    }
+    cnt = hi;
+  }
   for (int c4 = lane; c4 < d4; c4 += gw) {
     float4 acc = load_contrib(src, coef, alpha, vals[s], d4, c4);
-    for (int64_t t = s + 1; t < e && keys[t] == key; ++t) {
-      float4 v = load_contrib(src, coef, alpha, vals[t], d4, c4);
-      acc.x = __fadd_rn(acc.x, v.x); acc.y = __fadd_rn(acc.y, v.y); acc.z = __fadd_rn(acc.z, v.z); acc.w = __fadd_rn(acc.w, v.w);
+    for (int64_t k0 = 1; k0 < cnt; k0 += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        v[u] = k0 + u < cnt ? load_contrib(src, coef, alpha, vals[s + k0 + u], d4, c4) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+      for (int u = 0; u < 8; ++u)
+        if (k0 + u < cnt) {  // index order, one rounding per contribution (the CPU reference's order)
+          acc.x = __fadd_rn(acc.x, v[u].x); acc.y = __fadd_rn(acc.y, v[u].y); acc.z = __fadd_rn(acc.z, v[u].z); acc.w = __fadd_rn(acc.w, v[u].w);
+        }
     }
     if (single) {
       float* g = grad + ((int64_t)key * d4 + c4) * 4;
