@@ -233,6 +233,33 @@ def extra_benchmarks(dev):
                     "users_per_s": U / (ms * 1e-3), "ms_per_batch": ms, "logits_per_s": U * V / (ms * 1e-3)}
         del model
         torch.cuda.empty_cache()
+    # ---- device-side batch construction next to the host-side python/numpy producer of the same batch
+    try:
+        from rbm_b200.dataloaders import DeviceBertTrainLoader, BertBatcher
+        import time as _time
+        Vb, Lb, Bb = CFG["num_items"], CFG["max_len"], CFG["batch"]
+        hist = synthetic_interactions(6040, Vb, 165.0, 20, seed=1234)
+        ds = sliding_window_partition(hist, Lb, 0.3)
+        loader = DeviceBertTrainLoader(ds[0], Lb, CFG["mask_prob"], Vb, Bb, dev, seed=1)
+        users = torch.randint(0, loader.num_users, (Bb,), device=dev)
+
+        def dev_batch(i):
+            ops_mod.bert_cloze_batch(loader.ptr, loader.items, users, Lb, CFG["mask_prob"], Vb + 1, Vb, 1, i)
+
+        from rbm_b200 import ops as ops_mod
+        for i in range(3):
+            dev_batch(i)
+        ms_dev_b = ev_time(dev_batch, 50)
+        hb = BertBatcher(ds[0], Vb, Lb, CFG["mask_prob"], seed=1)
+        t0 = _time.perf_counter()
+        for _ in range(3):
+            hb.batch(Bb)
+        ms_host_b = (_time.perf_counter() - t0) * 1000 / 3
+        out["batch_construction"] = {"config": "BERT4Rec Cloze batch B=%d L=%d from a CSR of %d user windows" % (Bb, Lb, loader.num_users),
+                                     "device_ms_per_batch": ms_dev_b, "device_batches_per_s": 1000.0 / ms_dev_b,
+                                     "host_numpy_ms_per_batch": ms_host_b, "bytes_per_batch": 2 * Bb * Lb * 8}
+    except Exception as ex:
+        out["batch_construction"] = {"error": repr(ex)}
     return out
 
 
@@ -271,7 +298,7 @@ def main():
     model = rbm_b200.model_factory(margs)
     trainer = rbm_b200.trainer_factory(margs, model, None, None, None, None)
     model.train()
-    if world > 1:
+    if world > 1 and not os.environ.get("RBM_BENCH_NO_GRADSYNC"):  # diagnostic: N independent replicas (per-rank speed without the exchange)
         trainer.dist_sync = GradSync(model.parameters())
     host = [(torch.from_numpy(t).pin_memory(), torch.from_numpy(l).pin_memory()) for t, l in make_batches(N_ROT, Bsz, seed=100 + rank)]
     devb = [(t.to(dev), l.to(dev)) for t, l in host]

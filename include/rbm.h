@@ -209,6 +209,23 @@ typedef struct {
 int rbm_bucket_pack(const rbm_bucket_tensor* tensors, const int32_t* chunk_map, int total_chunks, float* bucket,
                     float scale, int unpack, rbm_stream_t stream);
 
+/* ---- device-side batch construction -------------------------------------------------
+ * User histories arrive as a CSR: hist_ptr[U+1], hist_items[nnz] (int64, ids in 1..num_items, oldest first); `users[B]`
+ * selects the rows of the batch.  Randomness is Philox4x32-10(key=seed, counter=(idx4, site)) with the field layout written
+ * in csrc/batch.cu (and restated in oracle/batches.py), so a batch is a pure function of (histories, users, seed, site).
+ *
+ * Cloze masking + left padding of BertTrainDataset.__getitem__ (NN/dataloaders/bert.py:77-110): tokens/labels [B, L] int64;
+ * a position is scored with probability mask_prob (label = item, else 0) and then shows [MASK] (80 %), a uniform item of
+ * 1..num_items (10 %) or itself (10 %). */
+int rbm_bert_cloze_batch(const int64_t* hist_ptr, const int64_t* hist_items, const int64_t* users, int B, int L,
+                         double mask_prob, int64_t mask_token, int64_t num_items, uint64_t seed, uint64_t site,
+                         int64_t* tokens, int64_t* labels, rbm_stream_t stream);
+/* (seq, pos, neg) of sample_function / random_neq (NN/dataloaders/sas.py:65-86): the window is the last L items; seq drops
+ * its last item, pos its first; neg[p] is uniform over the ids of [0, num_items] that are not in the window (L <= 256). */
+int rbm_sas_train_batch(const int64_t* hist_ptr, const int64_t* hist_items, const int64_t* users, int B, int L,
+                        int64_t num_items, uint64_t seed, uint64_t site, int64_t* seq, int64_t* pos, int64_t* neg,
+                        rbm_stream_t stream);
+
 /* ---- test / debug ---------------------------------------------------------------------------------- */
 /* materialise the keep-mask (1 = keep) the kernels use for an elementwise site over n elements */
 int rbm_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);

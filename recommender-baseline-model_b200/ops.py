@@ -485,3 +485,33 @@ def dropout_mask_attn(rows, Ln, p, seed, site, device):
     out = torch.empty(rows, Ln, device=device, dtype=torch.uint8)
     check(lib.rbm_dropout_mask_attn(ptr(out), rows, Ln, float(p), seed, site, stream()), "dropout_mask_attn")
     return out
+
+# ------------------------------------------------------------------------------------ device-side batch construction
+BATCH_SITE_BASE = 1 << 62  # Philox sites of batch construction live far away from the dropout sites (step*64 + local id)
+
+
+def bert_cloze_batch(hist_ptr, hist_items, users, max_len, mask_prob, mask_token, num_items, seed, step):
+    """(tokens, labels) int64 [B, L] on the device: Cloze masking of BertTrainDataset.__getitem__
+    (NN/dataloaders/bert.py:77-110) from a CSR of user histories; a pure function of (histories, users, seed, step)."""
+    lib = L.load()
+    L.require_cuda(hist_ptr, hist_items, users)
+    Bsz = int(users.numel())
+    tokens = torch.empty(Bsz, max_len, device=users.device, dtype=torch.int64)
+    labels = torch.empty(Bsz, max_len, device=users.device, dtype=torch.int64)
+    check(lib.rbm_bert_cloze_batch(ptr(hist_ptr), ptr(hist_items), ptr(users), Bsz, int(max_len), float(mask_prob), int(mask_token),
+                                   int(num_items), int(seed), BATCH_SITE_BASE + int(step), ptr(tokens), ptr(labels), stream()),
+          "bert_cloze_batch")
+    count_launches()
+    return tokens, labels
+
+
+def sas_train_batch(hist_ptr, hist_items, users, max_len, num_items, seed, step):
+    """(seq, pos, neg) int64 [B, L] on the device: sample_function / random_neq of NN/dataloaders/sas.py:65-86."""
+    lib = L.load()
+    L.require_cuda(hist_ptr, hist_items, users)
+    Bsz = int(users.numel())
+    out = [torch.empty(Bsz, max_len, device=users.device, dtype=torch.int64) for _ in range(3)]
+    check(lib.rbm_sas_train_batch(ptr(hist_ptr), ptr(hist_items), ptr(users), Bsz, int(max_len), int(num_items), int(seed),
+                                  BATCH_SITE_BASE + int(step), ptr(out[0]), ptr(out[1]), ptr(out[2]), stream()), "sas_train_batch")
+    count_launches()
+    return tuple(out)

@@ -254,6 +254,94 @@ def gen_scatter_adam(name="scatter_adam"):
     print(name, "written")
 
 
+def gen_batches(name="batches"):
+    """Training-batch construction of the REFERENCE dataloaders with the contract's random numbers injected:
+    ``BertTrainDataset.__getitem__`` (NN/dataloaders/bert.py:77-110) gets a fake ``rng`` whose ``rand`` / ``randint`` return
+    the Philox words of (batch row, output column); ``sample_function`` (NN/dataloaders/sas.py:73-90) runs with
+    ``np.random.randint`` patched the same way and a queue that stops it after one batch."""
+    from oracle.batches import rbm_philox
+    import dataloaders.bert as ref_bert
+    import dataloaders.sas as ref_sas
+
+    rs = np.random.RandomState(11)
+    V, U = 53, 12
+    hist = [list(rs.randint(1, V + 1, size=n)) for n in [0, 1, 2, 3, 7, 8, 9, 13, 20, 40, 5, 60]]
+    hist[10] = [4, 4, 4, 9, 4]  # repeats inside a window
+    out = {"hist_ptr": np.cumsum([0] + [len(h) for h in hist]).astype(np.int64),
+           "hist_items": np.array([i for h in hist for i in h], np.int64), "num_items": np.int64(V)}
+    seed, site = 1234567, (1 << 62) + 5
+
+    # ---- BERT Cloze
+    for L, mask_prob, tag in [(8, 0.4, "bert_L8"), (16, 1.0, "bert_L16_all"), (8, 0.0, "bert_L8_none")]:
+        users = np.array([3, 4, 5, 6, 7, 8, 9, 1, 0, 11, 10, 4], np.int64)
+
+        class FakeRng:
+            def __init__(self, b, n):
+                self.b, self.n, self.k = b, n, -1
+
+            def _words(self):
+                p = L - self.n + self.k  # output column of the element being drawn for (negative: truncated away)
+                if p < 0:
+                    return 0xFFFFFFFF, 0
+                r = rbm_philox(seed, site, self.b * 128 + (p >> 1))
+                return r[2 * (p & 1)], r[2 * (p & 1) + 1]
+
+            def rand(self):
+                self.k += 1
+                return self._words()[0] / 4294967296.0
+
+            def randint(self, lo, hi):
+                return lo + ((self._words()[1] * (hi - lo)) >> 32)
+
+        toks, labs = [], []
+        for b, u in enumerate(users):
+            ds = ref_bert.BertTrainDataset({0: hist[u]}, L, mask_prob, V + 1, V, FakeRng(b, len(hist[u])))
+            t, l = ds[0]
+            toks.append(t.numpy()); labs.append(l.numpy())
+        out[tag + ".users"], out[tag + ".mask_prob"] = users, np.float64(mask_prob)
+        out[tag + ".tokens"], out[tag + ".labels"] = np.stack(toks), np.stack(labs)
+
+    # ---- SASRec (seq, pos, neg)
+    for L, tag in [(8, "sas_L8"), (50, "sas_L50")]:
+        users = np.array([2, 3, 4, 5, 6, 7, 8, 9, 11, 10], np.int64)  # histories of >= 2 items (the reference indexes train[-1])
+        state = {"b": -1, "calls": 0}
+        real_randint = np.random.randint
+
+        def fake_randint(lo, hi=None, size=None):
+            if size is None:  # the user draw of sample(): users in the given order
+                state["b"] += 1
+                return state["b"] if state["b"] < len(users) else 0
+            b, n = state["b"], min(len(hist[users[state["b"]]]), L)
+            pad = L - n + 1
+            vals = []
+            for k in range(size):
+                p = pad + k
+                vals.append(lo + ((rbm_philox(seed, site, b * 64 + (p >> 2))[p & 3] * (hi - lo)) >> 32))
+            return np.array(vals, np.int64)
+
+        class OneBatch(Exception):
+            pass
+
+        class Q:
+            def put(self, z):
+                self.z = [list(x) for x in z]
+                raise OneBatch()
+
+        q = Q()
+        ref_sas.np.random.randint = fake_randint
+        try:
+            ref_sas.sample_function([hist[u] for u in users], V, len(users), L, q)
+        except OneBatch:
+            pass
+        finally:
+            ref_sas.np.random.randint = real_randint
+        out[tag + ".users"] = users
+        out[tag + ".seq"], out[tag + ".pos"], out[tag + ".neg"] = (np.array(x, np.int64) for x in q.z)
+    out["seed"], out["site"] = np.uint64(seed), np.uint64(site)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.parse_args()
@@ -267,6 +355,7 @@ def main():
     gen_sas(model_factory, "sas_cfg1", V=3416, L=50, d=64, nb=2, h=1, B=8, seed=1, store_sd=False, adam_steps=2)
     gen_metrics(metric_fn)
     gen_scatter_adam()
+    gen_batches()
 
 
 if __name__ == "__main__":

@@ -402,3 +402,87 @@ def test_fused_adam_matches_torch_golden():
     np.testing.assert_allclose(st["exp_avg"].cpu().numpy(), z["adam.m"], rtol=1e-5, atol=1e-8)
     np.testing.assert_allclose(st["exp_avg_sq"].cpu().numpy(), z["adam.v"], rtol=1e-5, atol=1e-12)
     assert set(opt.state_dict()["state"][0].keys()) == {"step", "exp_avg", "exp_avg_sq"}
+
+
+# ------------------------------------------------------------------------- device-side batch construction
+def _csr(hist):
+    ptr = np.cumsum([0] + [len(h) for h in hist]).astype(np.int64)
+    items = np.array([i for h in hist for i in h], np.int64)
+    return g(torch.from_numpy(ptr)), g(torch.from_numpy(items))
+
+
+def test_batch_construction_golden():
+    """The kernels reproduce what the REFERENCE dataloaders produce when fed the contract's random numbers
+    (tests/golden/batches.npz, minted by driving BertTrainDataset / sample_function with injected Philox words)."""
+    import os
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "batches.npz"))
+    ptr, items = g(torch.from_numpy(z["hist_ptr"])), g(torch.from_numpy(z["hist_items"]))
+    V, seed = int(z["num_items"]), int(z["seed"])
+    step = int(z["site"]) - ops.BATCH_SITE_BASE
+    for tag, Ln in [("bert_L8", 8), ("bert_L16_all", 16), ("bert_L8_none", 8)]:
+        t, l = ops.bert_cloze_batch(ptr, items, g(torch.from_numpy(z[tag + ".users"])), Ln, float(z[tag + ".mask_prob"]), V + 1, V, seed, step)
+        np.testing.assert_array_equal(t.cpu().numpy(), z[tag + ".tokens"])
+        np.testing.assert_array_equal(l.cpu().numpy(), z[tag + ".labels"])
+    for tag, Ln in [("sas_L8", 8), ("sas_L50", 50)]:
+        s, p, n = ops.sas_train_batch(ptr, items, g(torch.from_numpy(z[tag + ".users"])), Ln, V, seed, step)
+        np.testing.assert_array_equal(s.cpu().numpy(), z[tag + ".seq"])
+        np.testing.assert_array_equal(p.cpu().numpy(), z[tag + ".pos"])
+        np.testing.assert_array_equal(n.cpu().numpy(), z[tag + ".neg"])
+
+
+@pytest.mark.parametrize("Ln,V", [(50, 60), (200, 3416), (256, 300)])
+def test_batch_construction_ragged_vs_oracle(Ln, V):
+    """Empty, one-item, short, exactly-L and longer-than-L histories, repeated items, a user who owns (almost) every item."""
+    from oracle import batches as obt
+    rs = np.random.RandomState(Ln + V)
+    lens = [0, 1, 2, 3, Ln - 1, Ln, Ln + 1, 2 * Ln + 7] + list(rs.randint(2, 3 * Ln, size=40))
+    hist = [list(rs.randint(1, V + 1, size=n)) for n in lens]
+    hist.append(list(range(1, V + 1))[-Ln:])          # a window that covers a contiguous block of ids
+    hist.append([7] * (Ln + 3))                        # one item repeated
+    users = list(rs.randint(0, len(hist), size=64)) + list(range(len(hist)))
+    ptr, items = _csr(hist)
+    ug = g(torch.tensor(users, dtype=torch.int64))
+    seed, step = 99, 12
+    t, l = ops.bert_cloze_batch(ptr, items, ug, Ln, 0.15, V + 1, V, seed, step)
+    to, lo = obt.bert_cloze_batch(hist, users, Ln, 0.15, V + 1, V, seed, ops.BATCH_SITE_BASE + step)
+    np.testing.assert_array_equal(t.cpu().numpy(), to)
+    np.testing.assert_array_equal(l.cpu().numpy(), lo)
+    s, p, n = ops.sas_train_batch(ptr, items, ug, Ln, V, seed, step)
+    so, po, no = obt.sas_train_batch(hist, users, Ln, V, seed, ops.BATCH_SITE_BASE + step)
+    np.testing.assert_array_equal(s.cpu().numpy(), so)
+    np.testing.assert_array_equal(p.cpu().numpy(), po)
+    np.testing.assert_array_equal(n.cpu().numpy(), no)
+
+
+def test_batch_construction_properties_at_bench_size():
+    """cfg2-sized batch (B=1024, L=200): rates of the 15 % / 80-10-10 rule, structural invariants, determinism."""
+    rs = np.random.RandomState(5)
+    V, U, Ln, Bsz = 3416, 2000, 200, 1024
+    hist = [list(rs.randint(1, V + 1, size=n)) for n in rs.randint(20, 400, size=U)]
+    ptr, items = _csr(hist)
+    users = g(torch.from_numpy(rs.randint(0, U, size=Bsz).astype(np.int64)))
+    t, l = ops.bert_cloze_batch(ptr, items, users, Ln, 0.15, V + 1, V, 3, 0)
+    t2, l2 = ops.bert_cloze_batch(ptr, items, users, Ln, 0.15, V + 1, V, 3, 0)
+    assert torch.equal(t, t2) and torch.equal(l, l2)
+    t3, _ = ops.bert_cloze_batch(ptr, items, users, Ln, 0.15, V + 1, V, 3, 1)
+    assert not torch.equal(t, t3)  # another step, another mask
+    t, l = t.cpu(), l.cpu()
+    real = torch.zeros_like(t, dtype=torch.bool)
+    for b, u in enumerate(users.cpu().tolist()):
+        n = min(len(hist[u]), Ln)
+        real[b, Ln - n:] = True
+        assert torch.equal(torch.where(l[b] != 0, l[b], t[b])[Ln - n:], torch.tensor(hist[u][-n:]))  # unmasked view = history
+    assert (t[~real] == 0).all() and (l[~real] == 0).all()
+    scored = (l != 0) & real
+    rate = scored.float().sum() / real.float().sum()
+    assert abs(rate - 0.15) < 0.005
+    masked = (t == V + 1) & scored
+    assert abs(masked.float().sum() / scored.float().sum() - 0.8) < 0.02
+    kept = (t == l) & scored
+    assert abs(kept.float().sum() / scored.float().sum() - 0.1) < 0.02  # + 1/V of the random replacements
+    s, p, n = (x.cpu() for x in ops.sas_train_batch(ptr, items, users, 50, V, 3, 0))
+    assert torch.equal(s[:, 1:][p[:, :-1] != 0], p[:, :-1][p[:, :-1] != 0])  # pos is seq shifted by one
+    for b, u in enumerate(users.cpu().tolist()[:64]):
+        w = set(hist[u][-50:])
+        assert all(int(x) not in w for x in n[b][p[b] != 0].tolist())
+    assert (n[p == 0] == 0).all() and (n <= V).all() and (n >= 0).all()

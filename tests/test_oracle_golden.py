@@ -195,3 +195,41 @@ def test_injected_dropout_masks():
     d = oc.DropoutPlan(training=True, masks={4: keep})
     np.testing.assert_allclose(d(x, 0.3, 4).numpy(), (x * keep / 0.7).numpy(), rtol=1e-6)
     assert oc.DropoutPlan(training=False)(x, 0.3, 4) is x
+
+
+# ------------------------------------------------------------------------------------ batch construction
+def test_philox_known_answers():
+    """Philox4x32-10 known-answer vectors of the Random123 distribution (kat_vectors)."""
+    from oracle.batches import philox4x32_10
+    assert philox4x32_10((0, 0, 0, 0), (0, 0)) == (0x6627e8d5, 0xe169c58d, 0xbc57ac4c, 0x9b00dbd8)
+    assert philox4x32_10((0xffffffff,) * 4, (0xffffffff, 0xffffffff)) == (0x408f276d, 0x41c83b0e, 0xa20bc7c6, 0x6d5451fd)
+    assert philox4x32_10((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0)) == (
+        0xd16cfe09, 0x94fdcceb, 0x5001e420, 0x24126ea1)
+
+
+def _histories(z):
+    ptr, items = z["hist_ptr"], z["hist_items"]
+    return [items[ptr[u]:ptr[u + 1]].tolist() for u in range(len(ptr) - 1)]
+
+
+@pytest.mark.parametrize("tag,L", [("bert_L8", 8), ("bert_L16_all", 16), ("bert_L8_none", 8)])
+def test_bert_cloze_batch_vs_reference_dataset(tag, L):
+    """oracle.batches.bert_cloze_batch == the reference's BertTrainDataset driven by the same random numbers."""
+    from oracle import batches as obt
+    z = load("batches")
+    V = int(z["num_items"])
+    t, l = obt.bert_cloze_batch(_histories(z), z[tag + ".users"].tolist(), L, float(z[tag + ".mask_prob"]), V + 1, V,
+                                int(z["seed"]), int(z["site"]))
+    np.testing.assert_array_equal(t, z[tag + ".tokens"])
+    np.testing.assert_array_equal(l, z[tag + ".labels"])
+
+
+@pytest.mark.parametrize("tag,L", [("sas_L8", 8), ("sas_L50", 50)])
+def test_sas_train_batch_vs_reference_sampler(tag, L):
+    """oracle.batches.sas_train_batch == the reference's sample_function driven by the same random numbers."""
+    from oracle import batches as obt
+    z = load("batches")
+    s, p, n = obt.sas_train_batch(_histories(z), z[tag + ".users"].tolist(), L, int(z["num_items"]), int(z["seed"]), int(z["site"]))
+    np.testing.assert_array_equal(s, z[tag + ".seq"])
+    np.testing.assert_array_equal(p, z[tag + ".pos"])
+    np.testing.assert_array_equal(n, z[tag + ".neg"])
