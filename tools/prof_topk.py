@@ -12,3 +12,11 @@ for _ in range(3):
     vals, ids = ops.score_topk(f, table, None, 1, V + 1, 10)
 torch.cuda.synchronize()
 print("ok", ids[0].tolist())
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for _ in range(5):
+    vals, ids = ops.score_topk(f, table, None, 1, V + 1, 10)
+e1.record()
+torch.cuda.synchronize()
+ms = e0.elapsed_time(e1) / 5
+print("score_topk U=%d V=%d d=%d: %.2f ms = %.1f TFLOP/s logical" % (U, V, d, ms, 2.0 * U * V * d / ms / 1e9))
