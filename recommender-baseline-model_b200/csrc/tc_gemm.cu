@@ -181,9 +181,11 @@ __device__ __forceinline__ void split_lo(const float* src, float* dst, int n4, i
 }
 
 constexpr int EPI_WARPS = 8;
-// HAS_ACT: pre-activation store + activation compiled in; HAS_DROP: the two Philox dropout sites compiled in.  The
+// ACT: 0 none, 1 ReLU, 2 tanh-GELU, 3 none but the pre-activation is stored; DROPA / DROPB: the Philox dropout sites.  The
+// variant is a compile-time property so that the unrolled epilogue rows are straight-line code (uniform runtime branches
+// around every activation / Philox block kept the compiler from interleaving the eight independent rows).  The
 // epilogue loop is fully unrolled, so leaving the unused branches out keeps its body inside the instruction cache.
-template <bool HAS_ACT, bool HAS_DROP>
+template <int ACT, bool DROPA, bool DROPB>
 __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_kernel(const __grid_constant__ CUtensorMap mapA,
                                                                       const __grid_constant__ CUtensorMap mapB, const TcParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -337,34 +339,39 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
         if (col_ok) {
           float4 bias4 = make_float4(0.f, 0.f, 0.f, 0.f);
           if (biasp) bias4 = ld4(biasp + col);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
+          auto row_out = [&](int i) {
             const int rl = i * 4 + rsub;
             const int64_t row = rbase + rl;
-            if (row < p.M) {
-              float4 x = ld4(stg + rl * STG_LD + (((cg >> 2) ^ (rl & 7)) << 2));
-              x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
-              if constexpr (HAS_ACT) {
-                if (preout) st4(preout + row * p.N + col, x);
-                x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
-              }
-              const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
-              if constexpr (HAS_DROP) {
-                if (p.thrA) {
-                  float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
-                  x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
-                }
-              }
-              x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
-              if constexpr (HAS_DROP) {
-                if (p.thrB) {
-                  float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
-                  x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
-                }
-              }
-              if ((zero_rows >> i) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
-              st4(yout + row * p.ldy + col, x);
+            float4 x = ld4(stg + rl * STG_LD + (((cg >> 2) ^ (rl & 7)) << 2));
+            x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
+            if constexpr (ACT != 0) {
+              if (preout) st4(preout + row * p.N + col, x);
             }
+            if constexpr (ACT == RBM_ACT_RELU) {
+              x.x = fmaxf(x.x, 0.f); x.y = fmaxf(x.y, 0.f); x.z = fmaxf(x.z, 0.f); x.w = fmaxf(x.w, 0.f);
+            } else if constexpr (ACT == RBM_ACT_GELU_TANH) {
+              x.x = gelu_tanh_f(x.x); x.y = gelu_tanh_f(x.y); x.z = gelu_tanh_f(x.z); x.w = gelu_tanh_f(x.w);
+            }
+            const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
+            if constexpr (DROPA) {
+              const float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+              x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+            }
+            x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
+            if constexpr (DROPB) {
+              const float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+              x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
+            }
+            if ((zero_rows >> i) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
+            st4(yout + row * p.ldy + col, x);
+          };
+          if (rbase + 32 <= p.M) {  // whole 32-row slice inside the matrix: eight independent straight-line rows
+#pragma unroll
+            for (int i = 0; i < 8; ++i) row_out(i);
+          } else {
+#pragma unroll
+            for (int i = 0; i < 8; ++i)  // (unrolled too: a dynamic index would push res[] into local memory)
+              if (rbase + i * 4 + rsub < p.M) row_out(i);
           }
         }
         __syncwarp();
@@ -648,10 +655,13 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(tc_linear_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 224 * 1024);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+    // every (activation, dropout A, dropout B) variant of the persistent kernel
+#define RBM_TC_ATTR(A, DA, DB) \
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(tc_linear_persistent_kernel<A, DA, DB>, cudaFuncAttributeMaxDynamicSharedMemorySize, 231424);
+#define RBM_TC_ATTR4(A) RBM_TC_ATTR(A, false, false) RBM_TC_ATTR(A, true, false) RBM_TC_ATTR(A, false, true) RBM_TC_ATTR(A, true, true)
+    RBM_TC_ATTR4(0) RBM_TC_ATTR4(1) RBM_TC_ATTR4(2) RBM_TC_ATTR4(3)
+#undef RBM_TC_ATTR4
+#undef RBM_TC_ATTR
     if (e != cudaSuccess) {
       rbm_set_error("rbm_linear(tcgen05): cudaFuncSetAttribute: %s", cudaGetErrorString(e));
       return (int)e;
@@ -668,12 +678,23 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
     size_t smem = (size_t)2 * N * K * 4 + (size_t)ns * 2 * BM * BKE * 4 + (size_t)EPI_WARPS * 32 * STG_LD * 4 + 1024;
     int tiles = (int)rbm_cdiv(M, BM);
     int grid = tiles < RBM_NUM_SMS ? tiles : RBM_NUM_SMS;
-    const bool has_act = p.act != 0 || p.pre != nullptr, has_drop = p.thrA != 0 || p.thrB != 0;
+    const int act = p.act != 0 ? p.act : (p.pre != nullptr ? 3 : 0);  // 3: no activation, pre-activation still stored
+    const bool da = p.thrA != 0, db = p.thrB != 0;
     const int nthr = 128 + 32 * EPI_WARPS;
-    if (has_act && has_drop) tc_linear_persistent_kernel<true, true><<<grid, nthr, smem, st>>>(mapA, mapB, p);
-    else if (has_act) tc_linear_persistent_kernel<true, false><<<grid, nthr, smem, st>>>(mapA, mapB, p);
-    else if (has_drop) tc_linear_persistent_kernel<false, true><<<grid, nthr, smem, st>>>(mapA, mapB, p);
-    else tc_linear_persistent_kernel<false, false><<<grid, nthr, smem, st>>>(mapA, mapB, p);
+#define RBM_TC_GO(A, DA, DB) tc_linear_persistent_kernel<A, DA, DB><<<grid, nthr, smem, st>>>(mapA, mapB, p)
+#define RBM_TC_GO4(A)                     \
+    do {                                  \
+      if (da && db) RBM_TC_GO(A, true, true);       \
+      else if (da) RBM_TC_GO(A, true, false);       \
+      else if (db) RBM_TC_GO(A, false, true);       \
+      else RBM_TC_GO(A, false, false);              \
+    } while (0)
+    if (act == 0) RBM_TC_GO4(0);
+    else if (act == RBM_ACT_RELU) RBM_TC_GO4(1);
+    else if (act == RBM_ACT_GELU_TANH) RBM_TC_GO4(2);
+    else RBM_TC_GO4(3);
+#undef RBM_TC_GO4
+#undef RBM_TC_GO
     RBM_LAUNCH_CHECK("rbm_linear(tcgen05 persistent)");
     return 0;
   }
