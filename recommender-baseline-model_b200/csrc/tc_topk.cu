@@ -3,7 +3,8 @@
 // logits followed by argsort(-scores)[:, :k] (NN/models/sas_model/sas.py:110-114, NN/trainers/bert.py:47-49,
 // NN/trainers/utils.py:36-38): the [U, V] score matrix never exists anywhere but in tensor memory.
 //
-//   stage 1 (tc_topk_kernel): persistent CTAs walk (128-user tile, item split) units.  The user tile is TMA-loaded once
+//   stage 1 (tc_topk_kernel): persistent CTAs walk (user tile, item split) units; for d <= 64 a user tile is two 128-row
+//     sub-tiles that share every streamed item tile.  The user tile is TMA-loaded once
 //     per unit and stays in shared memory; item-table tiles ([BN items x d], K-major, 128-byte swizzle) stream through
 //     a TMA ring; tcgen05.mma kind::tf32 (single pass: this stage only has to be right about WHO is near the top)
 //     writes [128 x BN] score tiles into double-buffered TMEM; 8 epilogue warps (one thread per user row, tcgen05.ld)
@@ -34,6 +35,7 @@ struct TopkParams {
   int64_t* cand_i;   // [S*2][U][KC]
   int64_t U, v_begin, v_end, id_offset, tiles_per_split;
   int d, BN, nstage, S, n_utiles;
+  int nst;  // 128-row user sub-tiles per unit: 2 (d <= 64: 256 users share every streamed item tile) or 1
   uint32_t tmem_cols;
 };
 
@@ -44,7 +46,8 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
   __shared__ uint32_t tmem_base_slot;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.d / BKE, BN = p.BN, ns = p.nstage;
-  const uint32_t a_bytes = (uint32_t)KB * BM * BKE * 4, kb_bytes = (uint32_t)BN * BKE * 4, stage_bytes = kb_bytes * KB;
+  const int NST = p.nst;
+  const uint32_t a_sub = (uint32_t)KB * BM * BKE * 4, a_bytes = a_sub * NST, kb_bytes = (uint32_t)BN * BKE * 4, stage_bytes = kb_bytes * KB;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int64_t n_items = p.v_end - p.v_begin;
   const int64_t n_tiles = (n_items + BN - 1) / BN;
@@ -78,7 +81,9 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
         const int ut = u / p.S, sp = u % p.S;
         if (un > 0) mbar_wait(smem_u32(&a_empty), (un - 1) & 1);  // the previous unit's MMAs no longer read the user tile
         mbar_expect_tx(smem_u32(&a_full), a_bytes);
-        for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_base + kb * BM * BKE * 4, &mapA, smem_u32(&a_full), kb * BKE, ut * BM);
+        for (int st = 0; st < NST; ++st)
+          for (int kb = 0; kb < KB; ++kb)
+            tma_load_2d(smem_base + st * a_sub + kb * BM * BKE * 4, &mapA, smem_u32(&a_full), kb * BKE, (ut * NST + st) * BM);
         const int64_t tb = (int64_t)sp * p.tiles_per_split;
         const int64_t te = tb + p.tiles_per_split < n_tiles ? tb + p.tiles_per_split : n_tiles;
         for (int64_t t = tb; t < te; ++t, ++g) {
@@ -108,12 +113,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
           }
           mbar_wait(smem_u32(&full_bar[s]), (g / ns) & 1);
           tc_fence_after();
-          const uint32_t d = tmem_d + (uint32_t)(buf * BN);
-          for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t adesc = make_sw128_desc(smem_base + kb * BM * BKE * 4);
-            const uint64_t bdesc = make_sw128_desc(smem_base + a_bytes + s * stage_bytes + kb * kb_bytes);
+          for (int st = 0; st < NST; ++st) {  // every user sub-tile against the same streamed item tile
+            const uint32_t d = tmem_d + (uint32_t)((buf * NST + st) * BN);
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t adesc = make_sw128_desc(smem_base + st * a_sub + kb * BM * BKE * 4);
+              const uint64_t bdesc = make_sw128_desc(smem_base + a_bytes + s * stage_bytes + kb * kb_bytes);
 #pragma unroll
-            for (int k = 0; k < BKE / UMMA_K_TF32; ++k) umma_tf32(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+              for (int k = 0; k < BKE / UMMA_K_TF32; ++k) umma_tf32(d, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            }
           }
           umma_commit(smem_u32(&empty_bar[s]));
           umma_commit(smem_u32(&tfull[buf]));
@@ -124,11 +131,14 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
     __syncwarp();
   } else {
     const int q = warp & 3, half = (warp - 2) >> 2;
-    const int hw = BN / 2;  // columns per half
+    // two user sub-tiles: the second group of four warps owns sub-tile 1 and every thread scans all BN columns;
+    // one sub-tile: the two groups split the columns
+    const int st = NST == 2 ? half : 0, chalf = NST == 2 ? 0 : half;
+    const int hw = NST == 2 ? BN : BN / 2;  // columns per thread and tile
     int it = 0;
     for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
       const int ut = u / p.S, sp = u % p.S;
-      const int64_t user = (int64_t)ut * BM + q * 32 + lane;
+      const int64_t user = ((int64_t)ut * NST + st) * BM + q * 32 + lane;
       float ls[KC];
       int li[KC];
 #pragma unroll
@@ -142,10 +152,10 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
         const int buf = it & 1;
         mbar_wait(smem_u32(&tfull[buf]), (it >> 1) & 1);
         tc_fence_after();
-        const int64_t item0 = p.v_begin + t * BN + half * hw;  // table row of this thread's first column
+        const int64_t item0 = p.v_begin + t * BN + chalf * hw;  // table row of this thread's first column
         for (int c0 = 0; c0 < hw; c0 += 32) {
           float v[32];
-          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * BN + half * hw + c0), v);
+          tmem_ld32(tmem_d + ((uint32_t)(q * 32) << 16) + (uint32_t)((buf * NST + st) * BN + chalf * hw + c0), v);
           if (c0 + 32 >= hw) {  // this warp's last read of the buffer
             tc_fence_before();
             __syncwarp();
@@ -209,7 +219,7 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
         }
       }
       if (user < p.U) {
-        const int64_t base = ((int64_t)(sp * 2 + half) * p.U + user) * KC;
+        const int64_t base = ((int64_t)(NST == 2 ? sp : sp * 2 + half) * p.U + user) * KC;
 #pragma unroll
         for (int t = 0; t < KC; ++t) {
           p.cand_s[base + t] = ls[t];
@@ -322,12 +332,15 @@ bool tc_enabled() {
   }
   return v == 1;
 }
-int pick_bn(int d) { return d <= 64 ? 256 : (d <= 128 ? 128 : 64); }
+// d <= 64: two 128-user sub-tiles per unit against 128-item tiles (every streamed tile is used by 256 users: the kernel is
+// L2-bandwidth bound, and this halves the item-table traffic); larger d: one sub-tile
+int pick_nst(int d) { return d <= 64 ? 2 : 1; }
+int pick_bn(int d) { return d <= 128 ? 128 : 64; }
 
 }  // namespace
 
 int rbm_tc_topk_splits(int64_t U, int64_t n_items, int d) {
-  int64_t ut = rbm_cdiv(U, BM), tiles = rbm_cdiv(n_items, pick_bn(d));
+  int64_t ut = rbm_cdiv(U, BM * pick_nst(d)), tiles = rbm_cdiv(n_items, pick_bn(d));
   int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS * 3, ut);
   if (s > tiles / 8) s = tiles / 8;  // at least 8 item tiles per unit
   if (s > 32) s = 32;
@@ -358,11 +371,12 @@ int rbm_tc_topk_launch(const float* f, int64_t ldf, const float* table, const fl
   TopkParams p{};
   p.bias = bias; p.U = U; p.v_begin = v_begin; p.v_end = v_end; p.id_offset = id_offset; p.d = d; p.BN = BN;
   p.S = rbm_tc_topk_splits(U, n_items, d);
-  p.n_utiles = (int)rbm_cdiv(U, BM);
+  p.nst = pick_nst(d);
+  p.n_utiles = (int)rbm_cdiv(U, (int64_t)BM * p.nst);
   p.tiles_per_split = rbm_cdiv(rbm_cdiv(n_items, BN), p.S);
   p.cand_i = (int64_t*)ws;
   p.cand_s = (float*)(p.cand_i + (size_t)p.S * 2 * U * KC);
-  const size_t a_bytes = (size_t)BM * d * 4, stage = (size_t)BN * d * 4;
+  const size_t a_bytes = (size_t)BM * pick_nst(d) * d * 4, stage = (size_t)BN * d * 4;
   int ns = (int)(((size_t)231424 - 1024 - a_bytes) / stage);
   if (ns > 4) ns = 4;
   if (ns < 2) {
@@ -371,7 +385,7 @@ int rbm_tc_topk_launch(const float* f, int64_t ldf, const float* table, const fl
   }
   p.nstage = ns;
   uint32_t cols = 32;
-  while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+  while (cols < (uint32_t)(2 * BN * pick_nst(d))) cols <<= 1;
   p.tmem_cols = cols;
   static bool attr_set = false;
   if (!attr_set) {
@@ -387,7 +401,7 @@ int rbm_tc_topk_launch(const float* f, int64_t ldf, const float* table, const fl
   int grid = units < RBM_NUM_SMS ? units : RBM_NUM_SMS;
   tc_topk_kernel<<<grid, 64 + 32 * EPI, smem, st>>>(mapA, mapB, p);
   RBM_LAUNCH_CHECK("rbm_score_topk(tcgen05)");
-  topk_rescore_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 8 * d * sizeof(float), st>>>(f, ldf, table, bias, p.cand_i, p.S * 2, id_offset,
+  topk_rescore_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 8 * d * sizeof(float), st>>>(f, ldf, table, bias, p.cand_i, p.nst == 2 ? p.S : p.S * 2, id_offset,
                                                                                    top_scores, top_ids, U, d, k);
   RBM_LAUNCH_CHECK("rbm_score_topk(rescore)");
   return 0;
