@@ -14,7 +14,7 @@ CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "build")
 LIB = os.path.join(HERE, "librbm_b200.so")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
-FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC", "--use_fast_math=false"][:-1]
+FLAGS = ["-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC"]  # no fast-math: fp32-parity arithmetic
 
 
 def _nvcc() -> str:
