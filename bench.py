@@ -61,6 +61,11 @@ def cpu_reference_steps(steps, warmup, batch=CPU_BATCH):
     Adam as NN/trainers/base.py:228) on all host cores.  Returns (seq/s, ms/step, threads)."""
     from oracle import bert4rec as ob
     from oracle.common import DropoutPlan
+    # all the host threads this process may use (torchrun exports OMP_NUM_THREADS=1 for its workers: undo that here)
+    try:
+        torch.set_num_threads(max(1, len(os.sched_getaffinity(0))))
+    except Exception:
+        torch.set_num_threads(max(1, os.cpu_count() or 1))
     torch.manual_seed(0)
     sd = ob.random_state_dict(CFG["num_items"], CFG["max_len"], CFG["d"], CFG["nb"], seed=0)
     params = {k: torch.nn.Parameter(v.clone()) for k, v in sd.items()}
