@@ -339,10 +339,15 @@ int pick_bn(int d) { return d <= 128 ? 128 : 64; }
 
 }  // namespace
 
+// Item splits per user tile.  Every (user tile, split) unit warms its candidate lists up from scratch, and while a list
+// has seen fewer than ~16 k items nearly every 32-score chunk takes the divergent insertion path -- so as FEW splits as
+// still fill the machine, and never more units than one wave of SMs (measured at 16384 x 10^6, d = 64: 2 splits 5.2 ms,
+// 4 splits 6.2 ms, 7 splits 8.4 ms).
 int rbm_tc_topk_splits(int64_t U, int64_t n_items, int d) {
   int64_t ut = rbm_cdiv(U, BM * pick_nst(d)), tiles = rbm_cdiv(n_items, pick_bn(d));
-  int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS * 3, ut);
-  if (s > tiles / 8) s = tiles / 8;  // at least 8 item tiles per unit
+  if (const char* e = getenv("RBM_TOPK_SPLITS")) return atoi(e) < 1 ? 1 : atoi(e);  // bring-up override
+  int64_t s = (int64_t)RBM_NUM_SMS / ut;  // one wave
+  if (s > tiles / 8) s = tiles / 8;       // at least 8 item tiles per unit
   if (s > 32) s = 32;
   return (int)(s < 1 ? 1 : s);
 }
