@@ -676,7 +676,7 @@ size_t rbm_ce_tc_ws_floats(int64_t cap, int V1, int d) {
 
 int rbm_ce_tc_dw_splits(int64_t cap, int V1) {
   int64_t vt = rbm_cdiv(V1, 128), chunks = rbm_cdiv(cap, CW);
-  int64_t s = rbm_cdiv((int64_t)RBM_NUM_SMS, vt);
+  int64_t s = (int64_t)RBM_NUM_SMS / vt;  // one wave: vt * s <= #SMs (27 vocabulary tiles x 6 splits was 162 CTAs = two waves)
   if (s > chunks) s = chunks;
   if (s > 32) s = 32;
   return (int)(s < 1 ? 1 : s);
