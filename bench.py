@@ -238,6 +238,30 @@ def extra_benchmarks(dev):
                     "users_per_s": U / (ms * 1e-3), "ms_per_batch": ms, "logits_per_s": U * V / (ms * 1e-3)}
         del model
         torch.cuda.empty_cache()
+    # ---- the reference's own batch size (B = 128): eager (host-bound, ~200 launches) vs the step captured as ONE CUDA graph
+    try:
+        from rbm_b200 import model_factory as _mf, trainer_factory as _tf
+        Bs = 128
+        ma = model_args(str(dev), CFG["dropout"])
+        ma.train_batch_size = Bs
+        mdl = _mf(ma)
+        trn = _tf(ma, mdl, None, None, None, None)
+        mdl.train()
+        bs = [(torch.from_numpy(t).to(dev), torch.from_numpy(l).to(dev)) for t, l in make_batches(4, Bs, seed=55)]
+        for i in range(5):
+            trn.train_step(bs[i % 4])
+        ms_eager = ev_time(lambda i: trn.train_step(bs[i % 4]), 30)
+        trn.capture_train_step(bs[0])
+        for i in range(3):
+            trn.train_step(bs[i % 4])
+        ms_graph = ev_time(lambda i: trn.train_step(bs[i % 4]), 30)
+        trn.release_train_graph()
+        out["small_batch_cuda_graph"] = {"config": "BERT4Rec cfg2 model, B=%d (the reference's default batch size), full optimisation step" % Bs,
+                                         "eager_seq_per_s": Bs / ms_eager * 1e3, "eager_ms_per_step": ms_eager,
+                                         "graph_seq_per_s": Bs / ms_graph * 1e3, "graph_ms_per_step": ms_graph}
+        del trn, mdl
+    except Exception as ex:
+        out["small_batch_cuda_graph"] = {"error": repr(ex)}
     # ---- device-side batch construction next to the host-side python/numpy producer of the same batch
     try:
         from rbm_b200.dataloaders import DeviceBertTrainLoader, BertBatcher

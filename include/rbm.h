@@ -209,6 +209,14 @@ typedef struct {
 int rbm_bucket_pack(const rbm_bucket_tensor* tensors, const int32_t* chunk_map, int total_chunks, float* bucket,
                     float scale, int unpack, rbm_stream_t stream);
 
+/* ---- CUDA-graph support -------------------------------------------------------------------------------
+ * Dropout sites (step*64 + local id) and Adam's step arrive by value, so a captured step would replay the same masks
+ * and bias corrections for ever.  After rbm_set_step_counter(ptr) -- ptr = a device uint64, or NULL to switch it off --
+ * every kernel adds 64 * (*ptr) to its dropout sites and rbm_adam_multi adds *ptr to `step`; a captured graph
+ * increments *ptr itself.  Eager step s and replay number s of a graph captured with step 0 are bit-identical.
+ * Synchronous (cudaMemcpyToSymbol), library-wide: call it outside stream capture. */
+int rbm_set_step_counter(const uint64_t* counter);
+
 /* ---- device-side batch construction -------------------------------------------------
  * User histories arrive as a CSR: hist_ptr[U+1], hist_items[nnz] (int64, ids in 1..num_items, oldest first); `users[B]`
  * selects the rows of the batch.  Randomness is Philox4x32-10(key=seed, counter=(idx4, site)) with the field layout written

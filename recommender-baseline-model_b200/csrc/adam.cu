@@ -9,6 +9,8 @@ namespace {
 
 struct AdamHyper {
   float one_minus_b1, b2, one_minus_b2, eps, wd, neg_step_size, bc2_sqrt;
+  double lr, beta1, beta2;  // for the in-kernel bias correction under a device-side step counter (CUDA-graph replay)
+  int step;
 };
 
 __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v, const AdamHyper& h) {
@@ -21,6 +23,11 @@ __device__ __forceinline__ void adam_elem(float& p, float g, float& m, float& v,
 
 __global__ void __launch_bounds__(256) adam_multi_kernel(const rbm_adam_tensor* __restrict__ tensors, const int32_t* __restrict__ chunk_map,
                                                          AdamHyper h) {
+  if (rbm_step_ptr_dev != nullptr) {  // replayed graph: the step advances on the device (same double arithmetic as the host path)
+    const double t = (double)h.step + (double)*rbm_step_ptr_dev;
+    h.neg_step_size = (float)(-(h.lr / (1.0 - pow(h.beta1, t))));
+    h.bc2_sqrt = (float)sqrt(1.0 - pow(h.beta2, t));
+  }
   const int ti = chunk_map[blockIdx.x * 2], ci = chunk_map[blockIdx.x * 2 + 1];
   const rbm_adam_tensor t = tensors[ti];
   const int64_t b = (int64_t)ci * RBM_ADAM_CHUNK;
@@ -83,6 +90,7 @@ extern "C" int rbm_adam_multi(const rbm_adam_tensor* tensors, const int32_t* chu
   h.wd = (float)weight_decay;
   h.neg_step_size = (float)(-(lr / bc1));
   h.bc2_sqrt = (float)sqrt(bc2);
+  h.lr = lr; h.beta1 = beta1; h.beta2 = beta2; h.step = step;
   adam_multi_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(tensors, chunk_map, h);
   RBM_LAUNCH_CHECK("rbm_adam_multi");
   return 0;
@@ -95,4 +103,25 @@ extern "C" int rbm_bucket_pack(const rbm_bucket_tensor* tensors, const int32_t* 
   bucket_pack_kernel<<<total_chunks, 256, 0, (cudaStream_t)stream>>>(tensors, chunk_map, bucket, scale, unpack);
   RBM_LAUNCH_CHECK("rbm_bucket_pack");
   return 0;
+}
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_adam)
+
+// ---- public: device-side step counter (see common.cuh)
+int rbm_step_ptr_set_embed(const unsigned long long*);
+int rbm_step_ptr_set_linear(const unsigned long long*);
+int rbm_step_ptr_set_tc_gemm(const unsigned long long*);
+int rbm_step_ptr_set_attention(const unsigned long long*);
+int rbm_step_ptr_set_attention_tc(const unsigned long long*);
+
+extern "C" int rbm_set_step_counter(const uint64_t* counter) {
+  const unsigned long long* p = reinterpret_cast<const unsigned long long*>(counter);
+  int rc = rbm_step_ptr_set_embed(p);
+  if (!rc) rc = rbm_step_ptr_set_linear(p);
+  if (!rc) rc = rbm_step_ptr_set_tc_gemm(p);
+  if (!rc) rc = rbm_step_ptr_set_attention(p);
+  if (!rc) rc = rbm_step_ptr_set_attention_tc(p);
+  if (!rc) rc = rbm_step_ptr_set_adam(p);
+  if (rc) rbm_set_error("rbm_set_step_counter: cudaMemcpyToSymbol: %s", cudaGetErrorString((cudaError_t)rc));
+  return rc;
 }

@@ -36,6 +36,7 @@ struct AttnArgs {
 // ---------------------------------------------------------------------------------------------------- forward
 template <int DT>
 __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
+  const uint64_t site_e = rbm_site(a.site);
   extern __shared__ __align__(16) float sm[];
   const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
@@ -124,7 +125,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           if (jb + qd * 16 < LP8) {
-            uint4 rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
+            uint4 rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
             for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
@@ -168,6 +169,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
 // ------------------------------------------------------------------------------- backward pass A: dQ and delta
 template <int DT>
 __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a) {
+  const uint64_t site_e = rbm_site(a.site);
   extern __shared__ __align__(16) float sm[];
   const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
@@ -238,7 +240,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
       for (int qd = 0; qd < 4; ++qd) {
         uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
         if (a.thr16 && jb + qd * 16 < LP8)
-          rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
+          rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
         for (int bb = 0; bb < 2; ++bb) {
           const int nt = qd * 2 + bb;
@@ -282,6 +284,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
 // ------------------------------------------------------------------------------- backward pass B: dK and dV
 template <int DT>
 __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a) {
+  const uint64_t site_e = rbm_site(a.site);
   extern __shared__ __align__(16) float sm[];
   const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
   const int b = blockIdx.x / a.h, hh = blockIdx.x % a.h;
@@ -343,7 +346,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
         for (int e = 0; e < 2; ++e) {
           uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
           if (a.thr16 && ib + qd * 16 < LP8)
-            rnd = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)blockIdx.x, (ib >> 4) + qd, 2 * t + e, g >> 1, j0 >> 4));
+            rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, (ib >> 4) + qd, 2 * t + e, g >> 1, j0 >> 4));
 #pragma unroll
           for (int bb = 0; bb < 2; ++bb) {
             const int nt = qd * 2 + bb;
@@ -494,3 +497,5 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
   return rc;
 }
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_attention)

@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
     const int rl = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t thr_hi = a.thr16 << 16;
+    const uint64_t site_e = rbm_site(a.site);
     const uint32_t tS = tmem + lane_sel + F_S, tPl = tmem + lane_sel + F_PL + (uint32_t)grp * 64;
     for (int n = 0; n < n_items; ++n) {
       const int item = (int)blockIdx.x + n * (int)gridDim.x;
@@ -349,7 +350,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
             uint32_t rs[16];
             tmem_ld16_issue(tS + (uint32_t)j0, rs);
             KeepWords kw;
-            if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM read
+            if (DROP) kw = attn_keep_words(a.seed, site_e, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM read
             float us[16], fs[16];
 #pragma unroll
             for (int jj = 0; jj < 16; jj += 4) {
@@ -714,6 +715,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
     const int rl = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t thr_hi = a.thr16 << 16;
+    const uint64_t site_e = rbm_site(a.site);
     const uint32_t tS = tmem + lane_sel + (uint32_t)grp * A_GRP, tP = tS + A_DP;
     int cur_n = -1, bh = 0, i = 0;
     bool warp_live = false;
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
           tmem_ld16_issue(tP + (uint32_t)c0, rd);
           const int j0 = k0 + c0;
           KeepWords kw;
-          if (DROP) kw = attn_keep_words(a.seed, a.site, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM reads
+          if (DROP) kw = attn_keep_words(a.seed, site_e, (uint64_t)bh, i, j0 >> 4);  // overlaps the TMEM reads
           float kv[16];
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 4) {
@@ -1119,6 +1121,7 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_dkv_tc_kernel(const __g
     const uint32_t tG = tmem + lane_sel + B_GRP0 + (uint32_t)grp * B_GRP;
     // dropout: lanes {l, l^1, l^8, l^9} hold keys that share their Philox calls; each computes two of the eight
     const int wq = (lane & 1) | (((lane >> 3) & 1) << 1);
+    const uint64_t site_e = rbm_site(a.site);
     int g = 0;
     for (int n = 0; n < n_items; ++n) {
       const int item = (int)blockIdx.x + n * (int)gridDim.x;
@@ -1146,8 +1149,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_dkv_tc_kernel(const __g
             const int i0 = c * SQ + c0;  // 16 consecutive queries, one Philox "tile"
             uint32_t w0[8], w1[8];       // per query-in-octet g: the two words (rh = 0, 1) that hold this key's fields
             if (DROP) {
-              uint4 ca = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
-              uint4 cb = rbm_philox(a.seed, a.site, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
+              uint4 ca = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
+              uint4 cb = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
 #pragma unroll
               for (int gq = 0; gq < 8; ++gq) {
                 // call of query-octet position gq is owned by the lane whose (bit0, bit3) = ((gq>>1)&1, (gq>>2)&1); the
@@ -1523,3 +1526,5 @@ int rbm_attn_bwd_dkv_tc_launch(const float* q, int64_t ldq, const float* k, int6
   RBM_LAUNCH_CHECK("rbm_attn_bwd(tcgen05 dkv)");
   return 0;
 }
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_attention_tc)

@@ -73,6 +73,22 @@ __device__ __forceinline__ float4 rbm_drop4(uint64_t seed, uint64_t site, uint64
                      r.w >= thr ? inv_keep : 0.f);
 }
 
+// ---------------------------------------------------------------------------------------------
+// Step counter for CUDA-graph replay.  Dropout sites are step*64 + local id, with the step baked into the launch
+// arguments -- a captured graph would replay the same masks for ever.  rbm_set_step_counter(ptr) installs a device-side
+// counter instead: every kernel adds 64 * (*ptr) to its sites (and Adam adds *ptr to its step), the captured graph
+// increments the counter itself.  Eager launches (ptr = null) are unchanged, and eager step s equals replay number s of
+// a graph captured at step 0, bit for bit.  The pointer lives in one __device__ variable per translation unit.
+// ---------------------------------------------------------------------------------------------
+static __device__ const unsigned long long* rbm_step_ptr_dev = nullptr;
+__device__ __forceinline__ uint64_t rbm_step_offset() {
+  const unsigned long long* p = rbm_step_ptr_dev;
+  return p ? (uint64_t)*p : 0ull;
+}
+__device__ __forceinline__ uint64_t rbm_site(uint64_t site) { return site + 64ull * rbm_step_offset(); }
+#define RBM_DEFINE_STEP_PTR_SETTER(name) \
+  int name(const unsigned long long* p) { return (int)cudaMemcpyToSymbol(rbm_step_ptr_dev, &p, sizeof(p)); }
+
 // Attention-probability sites (L <= 256).  Element (sequence-head bh, query i, key j) takes one 16-bit field of a
 // Philox call; it is kept iff field >= p*65536.  The 8 fields of a call are laid out so that both the row-major
 // consumers (forward / dQ pass: an mma lane owns rows {g, g+8} x cols {2t, 2t+1} of two adjacent 8-key tiles) and

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restric
     float4 pe = ld4(pos + (int64_t)(r % L) * d4 * 4 + c4 * 4);
     o = make_float4(e.x * scale + pe.x, e.y * scale + pe.y, e.z * scale + pe.z, e.w * scale + pe.w);
     if (thr) {
-      float4 m = rbm_drop4(seed, site, (uint64_t)i, thr, inv_keep);
+      float4 m = rbm_drop4(seed, rbm_site(site), (uint64_t)i, thr, inv_keep);
       o.x *= m.x; o.y *= m.y; o.z *= m.z; o.w *= m.w;
     }
   }
@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
       if (zero_pad && tok[r] == 0) {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
       } else if (thr) {
-        float4 m = rbm_drop4(seed, site, (uint64_t)i, thr, inv_keep);
+        float4 m = rbm_drop4(seed, rbm_site(site), (uint64_t)i, thr, inv_keep);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
       }
       st4(g + i * 4, v);
@@ -133,3 +133,5 @@ extern "C" int rbm_dropout_mask_attn(uint8_t* out, int64_t rows, int L, float p,
   RBM_LAUNCH_CHECK("rbm_dropout_mask_attn");
   return 0;
 }
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_embed)

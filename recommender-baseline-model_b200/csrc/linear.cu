@@ -135,7 +135,7 @@ __global__ void __launch_bounds__(256) gemm_rowmajor_kernel(const float* __restr
       v.x = act_apply(v.x, ep.act); v.y = act_apply(v.y, ep.act); v.z = act_apply(v.z, ep.act); v.w = act_apply(v.w, ep.act);
       uint64_t e4 = (uint64_t)(row * N + col) >> 2;
       if (ep.thrA) {
-        float4 m = rbm_drop4(ep.seed, ep.siteA, e4, ep.thrA, ep.invA);
+        float4 m = rbm_drop4(ep.seed, rbm_site(ep.siteA), e4, ep.thrA, ep.invA);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
       }
       if (ep.residual) {
@@ -143,7 +143,7 @@ __global__ void __launch_bounds__(256) gemm_rowmajor_kernel(const float* __restr
         v.x += r.x; v.y += r.y; v.z += r.z; v.w += r.w;
       }
       if (ep.thrB) {
-        float4 m = rbm_drop4(ep.seed, ep.siteB, e4, ep.thrB, ep.invB);
+        float4 m = rbm_drop4(ep.seed, rbm_site(ep.siteB), e4, ep.thrB, ep.invB);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
       }
       if (ep.row_tok && ep.row_tok[row] == 0) v = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -274,12 +274,12 @@ __global__ void __launch_bounds__(256) epilogue_bwd_kernel(const float* __restri
   float4 g = ld4(dout + i * 4);
   if (row_tok && row_tok[i / N4] == 0) g = make_float4(0.f, 0.f, 0.f, 0.f);
   if (thrB) {
-    float4 m = rbm_drop4(seed, siteB, (uint64_t)i, thrB, invB);
+    float4 m = rbm_drop4(seed, rbm_site(siteB), (uint64_t)i, thrB, invB);
     g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
   }
   if (dres) st4(dres + i * 4, g);
   if (thrA) {
-    float4 m = rbm_drop4(seed, siteA, (uint64_t)i, thrA, invA);
+    float4 m = rbm_drop4(seed, rbm_site(siteA), (uint64_t)i, thrA, invA);
     g.x *= m.x; g.y *= m.y; g.z *= m.z; g.w *= m.w;
   }
   if (act == RBM_ACT_RELU) {
@@ -464,3 +464,5 @@ extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const fl
   RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
   return 0;
 }
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_linear)

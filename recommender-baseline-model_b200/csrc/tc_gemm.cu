@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
         x.x = act_apply(x.x, p.act); x.y = act_apply(x.y, p.act); x.z = act_apply(x.z, p.act); x.w = act_apply(x.w, p.act);
         const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
         if (p.thrA) {
-          float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+          float4 m = rbm_drop4(p.seed, rbm_site(p.siteA), e4, p.thrA, p.invA);
           x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
         }
         if (p.residual) {
@@ -136,7 +136,7 @@ __global__ void __launch_bounds__(192, 1) tc_linear_kernel(const __grid_constant
           x.x += r.x; x.y += r.y; x.z += r.z; x.w += r.w;
         }
         if (p.thrB) {
-          float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+          float4 m = rbm_drop4(p.seed, rbm_site(p.siteB), e4, p.thrB, p.invB);
           x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
         }
         if (!keep_row) x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -298,6 +298,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
     float* __restrict__ yout = p.y;
     float* __restrict__ preout = p.pre;
     const int last_c0 = ((BN / 32 - 1 - half) / 2) * 64 + half * 32;  // this warp's last chunk
+    const uint64_t siteA_e = rbm_site(p.siteA), siteB_e = rbm_site(p.siteB);
     int it = 0;
     for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
       const int buf = it & 1;
@@ -354,12 +355,12 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
             }
             const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
             if constexpr (DROPA) {
-              const float4 m = rbm_drop4(p.seed, p.siteA, e4, p.thrA, p.invA);
+              const float4 m = rbm_drop4(p.seed, rbm_site(p.siteA), e4, p.thrA, p.invA);
               x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
             }
             x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
             if constexpr (DROPB) {
-              const float4 m = rbm_drop4(p.seed, p.siteB, e4, p.thrB, p.invB);
+              const float4 m = rbm_drop4(p.seed, rbm_site(p.siteB), e4, p.thrB, p.invB);
               x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
             }
             if ((zero_rows >> i) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -790,3 +791,5 @@ int rbm_tc_dw_launch(const float* dpre, int64_t lda, const float* x, int64_t ldb
   RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(tcgen05)");
   return 0;
 }
+
+RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_tc_gemm)

@@ -64,6 +64,7 @@ SIGNATURES = {
     "rbm_column_mean": (_I, [_P, _P, _L, _I, _P, _SZ, _P]),
     "rbm_adam_multi": (_I, [_P, _P, _I, _D, _D, _D, _D, _D, _I, _P]),
     "rbm_bucket_pack": (_I, [_P, _P, _I, _P, _F, _I, _P]),
+    "rbm_set_step_counter": (_I, [_P]),
     "rbm_bert_cloze_batch": (_I, [_P, _P, _P, _I, _I, _D, _L, _L, _U64, _U64, _P, _P, _P]),
     "rbm_sas_train_batch": (_I, [_P, _P, _P, _I, _I, _L, _U64, _U64, _P, _P, _P, _P]),
     "rbm_dropout_mask": (_I, [_P, _L, _F, _U64, _U64, _P]),

@@ -51,6 +51,7 @@ class AbstractTrainer(metaclass=ABCMeta):
         self.batch_size = args.train_batch_size
         self.best_value = None
         self.dist_sync = None  # set to rbm_b200.dist.GradSync for data-parallel training
+        self._graph = None     # set by capture_train_step()
 
     @classmethod
     @abstractmethod
@@ -70,6 +71,8 @@ class AbstractTrainer(metaclass=ABCMeta):
 
     # ---------------------------------------------------------------- one optimisation step (base.py:114-123)
     def train_step(self, batch):
+        if self._graph is not None:
+            return self._replay(batch)
         self.optimizer.zero_grad()
         loss = self.calculate_loss(batch)
         loss.backward()
@@ -77,6 +80,81 @@ class AbstractTrainer(metaclass=ABCMeta):
             self.dist_sync.allreduce_grads()
         self.optimizer.step()
         return loss
+
+    # ---------------------------------------------------------------- the same step as ONE CUDA graph
+    def capture_train_step(self, example_batch, warmup: int = 3):
+        """Capture zero_grad + loss + backward + optimizer step into a CUDA graph; later ``train_step`` calls copy the batch
+        into the graph's static input buffers and replay it (one launch instead of ~200: at the reference's batch sizes of
+        64-128 the step is host-bound otherwise).  Dropout sites and Adam's bias correction advance through the library's
+        device-side step counter (``rbm_set_step_counter``), so replay number j reproduces eager step s0 + j bit for bit.
+        Single-GPU, fused Adam, fixed batch shape and learning rate (call again after the scheduler changes ``lr``)."""
+        import copy
+        from .. import lib as L
+        if self.dist_sync is not None:
+            raise RuntimeError("capture_train_step: data-parallel gradient exchange is not captured; use the eager step")
+        if not isinstance(self.optimizer, FusedAdam):
+            raise RuntimeError("capture_train_step needs the fused Adam optimizer")
+        dev = torch.device(self.device)
+        static = tuple(torch.as_tensor(x).to(dev).clone() for x in example_batch)
+        # warm-up on a side stream (lazy one-time work: function attributes, context binding, workspaces, Adam state),
+        # then put model / optimizer / step counters back so that the captured step is the next real one
+        model_sd = copy.deepcopy(self.model.state_dict())
+        opt_sd = copy.deepcopy(self.optimizer.state_dict())
+        step0 = self.model._step
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(max(1, warmup)):
+                self.optimizer.zero_grad()
+                loss = self.calculate_loss(static)
+                loss.backward()
+                self.optimizer.step()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.model.load_state_dict(model_sd)
+        self.optimizer.load_state_dict(opt_sd)
+        self.model._step = step0
+        self.optimizer.init_state()  # state buffers must exist before capture (a lazily created zero buffer would be re-zeroed by every replay)
+        # the device-side step counter: 0 now, +1 at the end of every replay
+        self._graph_counter = torch.zeros(1, dtype=torch.int64, device=dev)
+        L.check(L.load().rbm_set_step_counter(self._graph_counter.data_ptr()), "set_step_counter")
+        # persistent gradient buffers: the graph zeroes and re-accumulates them in place, so every address Adam's descriptor
+        # table holds is known (and uploaded) before capture -- no host->device copy inside the graph
+        for p in self.model.parameters():
+            if p.requires_grad:
+                p.grad = torch.zeros_like(p)
+        self.optimizer.stage_tables()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            self.optimizer.zero_grad(set_to_none=False)
+            loss = self.calculate_loss(static)
+            loss.backward()
+            self.optimizer.step()
+            self._graph_counter.add_(1)
+        self._graph, self._graph_static, self._graph_loss, self._graph_lr = graph, static, loss, self.get_lr()
+        return self
+
+    def release_train_graph(self):
+        """Back to eager steps (the python-side step counters are advanced by the number of replays)."""
+        if self._graph is None:
+            return
+        from .. import lib as L
+        done = int(self._graph_counter.item())
+        L.check(L.load().rbm_set_step_counter(None), "set_step_counter")
+        # the capture itself advanced the python counters by one step; the replays did the rest on the device
+        self.model._step += done - 1
+        for st in self.optimizer.state.values():
+            if "step" in st:
+                st["step"] += done - 1
+        self._graph = None
+
+    def _replay(self, batch):
+        if self.get_lr() != self._graph_lr:
+            raise RuntimeError("the learning rate changed since capture_train_step(): release_train_graph() and capture again")
+        for dst, src in zip(self._graph_static, batch):
+            dst.copy_(torch.as_tensor(src), non_blocking=True)
+        self._graph.replay()
+        return self._graph_loss
 
     def train(self):
         accum_iter = 0

@@ -231,3 +231,48 @@ def test_training_from_device_side_loaders():
     assert len(loader) == 4
     losses = [tr.train_step(b).item() for _ in range(12) for b in loader]
     assert np.isfinite(losses).all() and np.mean(losses[-8:]) < 0.8 * np.mean(losses[:8]), (losses[:8], losses[-8:])
+
+
+@pytest.mark.parametrize("kind", ["bert", "sas"])
+def test_cuda_graph_train_step_equals_eager(kind):
+    """The captured train step (one CUDA graph, device-side step counter for dropout sites and Adam's bias correction)
+    reproduces the eager steps bit for bit: same losses, same parameters, dropout on."""
+    V, Ln, d, B = 50, 16, 32, 24
+    rs = np.random.RandomState(1)
+    if kind == "bert":
+        mk = lambda: rbm_b200.model_factory(bert_args(V, Ln, d, 2, 2, p=0.2, seed=3))
+        def batch(i):
+            t = rs.randint(1, V + 1, size=(B, Ln)); t[:, : i % 5] = 0
+            l = np.where(rs.rand(B, Ln) < 0.3, t, 0)
+            return torch.from_numpy(np.where(l != 0, V + 1, t)).to(DEV), torch.from_numpy(l).to(DEV)
+        extra = {}
+    else:
+        mk = lambda: rbm_b200.model_factory(sas_args(V, Ln, d, 2, 1, p=0.2))
+        def batch(i):
+            s = rs.randint(1, V + 1, size=(B, Ln)); s[:, : 1 + i % 5] = 0
+            p_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+            n_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+            return tuple(torch.from_numpy(x).to(DEV) for x in (s, p_, n_))
+        extra = {"l2_emb": 0.0}
+    common = dict(optimizer="Adam", lr=2e-3, weight_decay=0, momentum=None, decay_step=50, gamma=1.0, num_epochs=1, metric_ks=[10],
+                  best_metric="NDCG@10", train_batch_size=B, resume_path=None, **extra)
+    batches = [batch(i) for i in range(6)]
+    torch.manual_seed(0)
+    m1 = mk()
+    m2 = mk()
+    m2.load_state_dict(m1.state_dict())
+    m2.dropout_seed = m1.dropout_seed  # (by default the process seed at construction time)
+    a = bert_args(V, Ln, d, 2, 2, p=0.2, seed=3) if kind == "bert" else sas_args(V, Ln, d, 2, 1, p=0.2)
+    t1 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m1, None, None, None, None)
+    t2 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m2, None, None, None, None)
+    m1.train(); m2.train()
+    eager = [t1.train_step(b).item() for b in batches]
+    t2.capture_train_step(batches[0])
+    graphed = [t2.train_step(b).item() for b in batches]
+    t2.release_train_graph()
+    assert eager == graphed, (eager, graphed)
+    for (k, v1), (_, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(v1, v2), k
+    # and eager steps continue seamlessly after the graph is released
+    nb = batch(7)
+    assert t1.train_step(nb).item() == t2.train_step(nb).item()
