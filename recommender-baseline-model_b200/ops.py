@@ -181,7 +181,7 @@ class LinearFn(torch.autograd.Function):
             ws = _ws("lin_dw", nb, dy.device)
             check(lib.rbm_linear_bwd_weight(ptr(dpre), N, ptr(x2), x2.stride(0), ptr(dw), ptr(db), M, N, K, ptr(ws), nb, stream()),
                   "linear_bwd_weight")
-            count_launches(3 if has_bias else 2)
+            count_launches(2)  # partial dW (+ fused db) and the fixed-order reduction
         return dx, dw, db, (dres.view(rshape) if has_res else None), None, None, None, None, None, None, None
 
 
