@@ -130,7 +130,9 @@ size_t rbm_compact_ws_bytes(int64_t n);
 int rbm_compact_labels(const int64_t* labels, int64_t n, int32_t* rows_out, int64_t* tgt_out, int32_t* count_out,
                        void* ws, size_t ws_bytes, rbm_stream_t stream);
 size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d);
-/* forward: lse[cap], loss (1 float).  cap = capacity (>= count); count read from device. */
+/* forward: lse[cap], loss (1 float).  cap = capacity (>= count); count read from device.  A target outside [0, V1) matches
+ * no column (its logit counts as 0): this is what a row-shard of the output layer passes for targets it does not own
+ * (tgt - v_begin; rbm_b200.dist.vocab_parallel_cross_entropy). */
 int rbm_ce_fwd(const float* h, const int32_t* rows, const int64_t* tgt, const int32_t* count, const float* w,
                const float* bias, float* lse, float* loss, int64_t cap, int V1, int d, void* ws, size_t ws_bytes,
                rbm_stream_t stream);

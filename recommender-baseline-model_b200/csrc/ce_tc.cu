@@ -154,7 +154,8 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_fwd_tc_kernel(const __gri
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&h_bar));
-    const int64_t tg = valid ? a.tgt[r] : -1;
+    int64_t tg = valid ? a.tgt[r] : -1;
+    if (tg < 0 || tg >= V1) tg = -1;  // a target outside this (shard of the) vocabulary matches no column
     float m = -INFINITY, l = 0.f, tl = 0.f;
     for (int c = 0; c < NC; ++c) {
       const int buf = c & 1;
@@ -345,7 +346,8 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dh_tc_kernel(const __
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&h_bar));
     }
-    const int64_t tg = valid ? a.tgt[r] : -1;
+    int64_t tg = valid ? a.tgt[r] : -1;
+    if (tg < 0 || tg >= V1) tg = -1;  // a target outside this (shard of the) vocabulary matches no column
     const float lse2 = valid ? a.lse_in[r] * RBM_LOG2E : INFINITY;  // rows beyond the count: 2^(-inf) = 0
     const float gscale = *a.dloss / (float)count;
     const uint32_t tS = tG0 + lane_sel + (uint32_t)grp * 2 * CW, tGl = tS + CW;
@@ -526,7 +528,7 @@ __global__ void __launch_bounds__(64 + 32 * NSW, 1) ce_bwd_dw_tc_kernel(const __
       if (gt < CW) {
         const int r = c * CW + gt;
         lse_s[grp][gt] = r < count ? a.lse_in[r] * RBM_LOG2E : INFINITY;  // columns beyond the count: p = 0
-        tgt_s[grp][gt] = r < count ? (float)a.tgt[r] : -1.f;
+        tgt_s[grp][gt] = (r < count && a.tgt[r] >= 0 && a.tgt[r] < V1) ? (float)a.tgt[r] : -1.f;
       }
       named_bar_sync(1 + grp, 128);
       mbar_wait(smem_u32(&s_full[grp]), (n >> 1) & 1);

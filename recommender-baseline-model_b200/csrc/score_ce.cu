@@ -151,7 +151,7 @@ __global__ void __launch_bounds__(256) ce_fwd_kernel(CeArgs a) {
 #pragma unroll
   for (int hr = 0; hr < 2; ++hr) {
     int r = r0 + g + 8 * hr;
-    tg[hr] = r < count ? a.tgt[r] : -1;
+    tg[hr] = (r < count && a.tgt[r] >= 0 && a.tgt[r] < a.V1) ? a.tgt[r] : -1;  // outside the (shard of the) vocabulary: no column
   }
   const int NC = (V1 + CH - 1) / CH;
   auto issue = [&](int c) {
@@ -261,7 +261,7 @@ __global__ void __launch_bounds__(256) ce_bwd_dh_kernel(CeArgs a) {
 #pragma unroll
   for (int hr = 0; hr < 2; ++hr) {
     int r = r0 + g + 8 * hr;
-    tg[hr] = r < count ? a.tgt[r] : -1;
+    tg[hr] = (r < count && a.tgt[r] >= 0 && a.tgt[r] < a.V1) ? a.tgt[r] : -1;  // outside the (shard of the) vocabulary: no column
     lse2[hr] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
   }
   float acc[DT][4];
@@ -356,7 +356,7 @@ __global__ void __launch_bounds__(256) ce_bwd_dw_kernel(CeArgs a) {
     for (int j = threadIdx.x; j < CH; j += blockDim.x) {
       int r = c * CH + j;
       lse_s[buf * CH + j] = r < count ? a.lse_in[r] * RBM_LOG2E : 0.f;
-      tgt_s[buf * CH + j] = r < count ? (float)a.tgt[r] : -1.f;
+      tgt_s[buf * CH + j] = (r < count && a.tgt[r] >= 0 && a.tgt[r] < a.V1) ? (float)a.tgt[r] : -1.f;
     }
     cp_async_commit();
   };

@@ -111,3 +111,94 @@ def sharded_full_catalogue_topk(last_hidden: torch.Tensor, table: torch.Tensor, 
         ids = torch.full((U, k), -1, device=last_hidden.device, dtype=torch.int64)
     gv, gi = gather_topk(vals, ids, group)
     return ops.topk_merge(gv, gi)
+
+
+# ------------------------------------------------------------------------------------ vocab-parallel cross-entropy
+def combine_shard_lse(lse_all: torch.Tensor, loss_all: torch.Tensor, count: torch.Tensor) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Global log-sum-exp and loss from per-shard CE results (BERT CE): ``lse_all [S, cap]`` are the
+    per-shard log-sum-exps of the first ``count`` (compacted, masked) rows, ``loss_all [S]`` the per-shard values of
+    ``mean(lse_s - target logit if the target lies in shard s else lse_s)`` as ``rbm_ce_fwd`` returns them for a shard.
+    Returns (LSE [cap] fp32, loss scalar).  Since a target lies in exactly one shard,
+    ``sum_r target_logit[r] = sum_s (sum_r lse_s[r] - count * loss_s)``."""
+    S, cap = lse_all.shape
+    live = torch.arange(cap, device=lse_all.device) < count.reshape(())
+    cnt = count.reshape(()).to(torch.float64)
+    # entries beyond `count` are uninitialised memory (possibly inf / nan): select, never multiply
+    lse64 = torch.where(live.unsqueeze(0), lse_all.to(torch.float64), torch.zeros((), dtype=torch.float64, device=lse_all.device))
+    LSE = torch.logsumexp(lse64, dim=0)
+    tgt_sum = (lse64.sum(dim=1) - cnt * loss_all.to(torch.float64)).sum()
+    loss = (torch.where(live, LSE, torch.zeros_like(LSE)).sum() - tgt_sum) / cnt
+    return LSE.to(torch.float32), loss.to(torch.float32)
+
+
+class VocabParallelCEFn(torch.autograd.Function):
+    """Masked cross-entropy with the output layer row-sharded over the ranks of `group`:
+    every rank holds the SAME hidden rows and labels and its own block ``w[v_begin:v_end]``, ``bias[v_begin:v_end]``.
+    Forward: fused scoring + online softmax against the local block (``rbm_ce_fwd``, targets shifted by ``-v_begin`` so
+    that a target outside the block matches no column), all-gather of the per-row log-sum-exps and the shard losses
+    ((1 + cap) floats per rank), combination into the global LSE / loss.  Backward: ``rbm_ce_bwd`` with the GLOBAL LSE
+    yields this block's dW / db and this block's share of dH; the dH shares are summed with one all-reduce."""
+
+    @staticmethod
+    def forward(ctx, hidden, labels, w_shard, bias_shard, v_begin, group):
+        from . import ops
+        lib = L.load()
+        L.require_cuda(hidden, labels, w_shard, bias_shard)
+        h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
+        n, d = h2.shape
+        V1 = w_shard.shape[0]
+        labels = labels.reshape(-1).contiguous()
+        dev = hidden.device
+        rows = torch.empty(n, device=dev, dtype=torch.int32)
+        tgt = torch.empty(n, device=dev, dtype=torch.int64)
+        count = torch.empty(1, device=dev, dtype=torch.int32)
+        nb = lib.rbm_compact_ws_bytes(n)
+        ws = ops._ws("compact", nb, dev)
+        check(lib.rbm_compact_labels(ptr(labels), n, ptr(rows), ptr(tgt), ptr(count), ptr(ws), nb, stream()), "compact_labels")
+        tgt_local = (tgt - int(v_begin)).contiguous()
+        lse_s = torch.empty(n, device=dev, dtype=torch.float32)
+        loss_s = torch.empty(1, device=dev, dtype=torch.float32)
+        nb = lib.rbm_ce_ws_bytes(n, V1, d)
+        ws = ops._ws("ce", nb, dev)
+        w_shard = w_shard.contiguous()
+        check(lib.rbm_ce_fwd(ptr(h2), ptr(rows), ptr(tgt_local), ptr(count), ptr(w_shard), ptr(bias_shard), ptr(lse_s), ptr(loss_s), n, V1,
+                             d, ptr(ws), nb, stream()), "ce_fwd")
+        count_launches(5)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        if world > 1:
+            lse_list = [torch.empty_like(lse_s) for _ in range(world)]
+            loss_list = [torch.empty_like(loss_s) for _ in range(world)]
+            dist.all_gather(lse_list, lse_s, group=group)
+            dist.all_gather(loss_list, loss_s, group=group)
+            lse_all, loss_all = torch.stack(lse_list), torch.cat(loss_list)
+        else:
+            lse_all, loss_all = lse_s.unsqueeze(0), loss_s
+        LSE, loss = combine_shard_lse(lse_all, loss_all, count)
+        ctx.save_for_backward(h2, rows, tgt_local, count, w_shard, bias_shard, LSE.contiguous())
+        ctx.shape, ctx.group, ctx.world = hidden.shape, group, world
+        return loss
+
+    @staticmethod
+    def backward(ctx, dloss):
+        from . import ops
+        lib = L.load()
+        h2, rows, tgt_local, count, w_shard, bias_shard, LSE = ctx.saved_tensors
+        n, d = h2.shape
+        V1 = w_shard.shape[0]
+        dloss = dloss.reshape(1).contiguous().float()
+        dh = torch.zeros_like(h2)
+        dw = torch.empty_like(w_shard)
+        db = torch.empty(V1, device=h2.device, dtype=torch.float32)
+        nb = lib.rbm_ce_ws_bytes(n, V1, d)
+        ws = ops._ws("ce", nb, h2.device)
+        check(lib.rbm_ce_bwd(ptr(h2), ptr(rows), ptr(tgt_local), ptr(count), ptr(w_shard), ptr(bias_shard), ptr(LSE), ptr(dloss), ptr(dh),
+                             ptr(dw), ptr(db), n, V1, d, ptr(ws), nb, stream()), "ce_bwd")
+        count_launches(4)
+        if ctx.world > 1:
+            dist.all_reduce(dh, op=dist.ReduceOp.SUM, group=ctx.group)  # every rank needs the full dH of the replicated rows
+        return dh.view(ctx.shape), None, dw, db, None, None
+
+
+def vocab_parallel_cross_entropy(hidden, labels, w_shard, bias_shard, v_begin: int, group=None):
+    """See VocabParallelCEFn.  ``v_begin`` = first row of the output layer held by this rank (``shard_range(V + 1, rank, world)``)."""
+    return VocabParallelCEFn.apply(hidden, labels, w_shard, bias_shard, v_begin, group)

@@ -56,6 +56,25 @@ def _worker(rank, world, port, q):
         rv, ri = om.topk_canonical(scores, k, id_offset=1)
         np.testing.assert_array_equal(mi, ri)
         np.testing.assert_array_equal(mv, rv)
+        # ---- vocab-parallel cross-entropy: per-shard (log-sum-exp, loss) -> all-gather -> global LSE / loss == full CE
+        torch.manual_seed(3)
+        P, V1, d, cap = 29, 203, 16, 40
+        hrows, wfull, bfull = torch.randn(P, d), torch.randn(V1, d), torch.randn(V1)
+        tgt = torch.randint(1, V1, (P,))
+        logits = hrows @ wfull.t() + bfull
+        lo, hi = rd.shard_range(V1, rank, world)
+        ls = torch.logsumexp(logits[:, lo:hi], 1)
+        tl = torch.where((tgt >= lo) & (tgt < hi), logits[torch.arange(P), tgt], torch.zeros(P))
+        lse_s = torch.full((cap,), float("inf") if rank == 0 else float("nan"))  # entries beyond `count` are garbage by contract
+        lse_s[:P] = ls
+        loss_s = (ls - tl).mean().reshape(1)
+        lse_list = [torch.empty_like(lse_s) for _ in range(world)]
+        loss_list = [torch.empty_like(loss_s) for _ in range(world)]
+        dist.all_gather(lse_list, lse_s)
+        dist.all_gather(loss_list, loss_s)
+        LSE, loss = rd.combine_shard_lse(torch.stack(lse_list), torch.cat(loss_list), torch.tensor([P], dtype=torch.int32))
+        assert abs(float(loss) - float(torch.nn.functional.cross_entropy(logits, tgt))) < 1e-5
+        assert torch.allclose(LSE[:P], torch.logsumexp(logits, 1), atol=1e-5)
         q.put((rank, "ok"))
     except Exception as ex:  # noqa
         import traceback

@@ -67,6 +67,27 @@ def _worker(rank, world, port, q):
             v1, i1 = rbm_b200.ops.score_topk(hl, model.out.weight, model.out.bias, 1, V + 1, 10)
             v2, i2 = sharded_full_catalogue_topk(hl, model.out.weight, model.out.bias, V, 10)
         assert torch.equal(i1, i2) and torch.equal(v1, v2)
+        # vocab-parallel cross-entropy (output layer row-sharded over the ranks, replicated rows) == single-GPU fused CE
+        from rbm_b200.dist import vocab_parallel_cross_entropy, shard_range
+        g = torch.Generator().manual_seed(11)
+        n, V1c, dc = 4096, 3417, 64
+        hid = torch.randn(n, dc, generator=g).to(dev)
+        wfull = (torch.randn(V1c, dc, generator=g) * 0.1).to(dev)
+        bfull = (torch.randn(V1c, generator=g) * 0.1).to(dev)
+        labc = torch.randint(1, V1c, (n,), generator=g)
+        labc[torch.rand(n, generator=g) > 0.15] = 0
+        labc = labc.to(dev)
+        h1, w1, b1 = hid.clone().requires_grad_(True), wfull.clone().requires_grad_(True), bfull.clone().requires_grad_(True)
+        ref = rbm_b200.ops.score_cross_entropy(h1, labc, w1, b1)
+        ref.backward()
+        lo, hi = shard_range(V1c, rank, world)
+        h2, w2, b2 = hid.clone().requires_grad_(True), wfull[lo:hi].clone().requires_grad_(True), bfull[lo:hi].clone().requires_grad_(True)
+        out = vocab_parallel_cross_entropy(h2, labc, w2, b2, lo)
+        out.backward()
+        assert abs(out.item() - ref.item()) < 1e-5 * abs(ref.item()), (out.item(), ref.item())
+        assert torch.allclose(h2.grad, h1.grad, rtol=1e-4, atol=1e-7), (h2.grad - h1.grad).abs().max()
+        assert torch.allclose(w2.grad, w1.grad[lo:hi], rtol=1e-4, atol=1e-7)
+        assert torch.allclose(b2.grad, b1.grad[lo:hi], rtol=1e-4, atol=1e-7)
         q.put((rank, "ok"))
     except Exception:  # noqa
         import traceback
