@@ -301,6 +301,10 @@ def main():
     ap.add_argument("--batch", type=int, default=CFG["batch"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extras", action="store_true")
+    ap.add_argument("--step-mode", default=os.environ.get("RBM_BENCH_STEP_MODE", "graph"), choices=["graph", "eager"],
+                    help="graph: trainer.capture_train_step (CUDA-graph replay of the whole optimisation step); eager: launch by launch")
+    ap.add_argument("--dp-collective", default=os.environ.get("RBM_BENCH_DP_COLLECTIVE", "split"), choices=["split", "graph"],
+                    help="N>1 with --step-mode graph: eager NCCL all-reduce between two graphs (split) or captured inside one graph")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -352,6 +356,16 @@ def main():
 
     # ---- device-resident leg
     step_dev = lambda i: trainer.train_step(devb[i % N_ROT])
+    step_mode = args.step_mode
+    if step_mode == "graph":
+        for i in range(2):
+            step_dev(i)  # eager first: one-time lazy work and the NCCL communicator
+        try:
+            trainer.capture_train_step(devb[0], collective=args.dp_collective)
+        except Exception as ex:  # all ranks fail alike (same code path); the eager step is the same arithmetic
+            if rank == 0:
+                print("capture_train_step failed (%r): eager steps" % (ex,), file=sys.stderr)
+            step_mode = "eager"
     for i in range(args.warmup):
         step_dev(i)
     L.launch_count = 0
@@ -379,6 +393,7 @@ def main():
         return
 
     # ---- roofline leg: per-entry-point CUDA-event timing of a few steps (rank 0)
+    trainer.release_train_graph()  # per-entry-point events need the launch-by-launch step
     trainer.dist_sync = None  # the other ranks are done: no collectives from here on
     L.profile = {}
     for i in range(3):
@@ -430,13 +445,13 @@ def main():
     shares = {k: round(v / step_ms_prof, 4) for k, v in sorted(totals.items(), key=lambda kv: -kv[1])[:8]}
 
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:
         v, ms, threads = cpu_reference_steps(steps=6, warmup=1)
         cpu = {"value": v, "unit": "seq/s", "cores": threads, "kind": "port",
                "sample": "6 steps of B=%d of the same workload (oracle port of the reference's torch CPU path, dropout %.2f, torch Adam); %.0f ms/step" % (CPU_BATCH, CFG["dropout"], ms)}
 
     extras = None
-    if not args.no_extras:
+    if not args.no_extras and world == 1:
         del trainer, model
         torch.cuda.empty_cache()
         try:
@@ -450,6 +465,9 @@ def main():
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": CFG["name"], "batch_per_gpu": Bsz, "global_batch": Bsz * world, "seq_len": CFG["max_len"],
                        "dropout": CFG["dropout"], "optimizer": "Adam (dense, fused)", "parallelism": "dp%d" % world,
+                       "step": ("one CUDA graph per step (trainer.capture_train_step)" if world == 1 else
+                                "two CUDA graphs + one eager NCCL all-reduce of the flat gradient bucket per step" if args.dp_collective == "split"
+                                else "one CUDA graph per step incl. the NCCL all-reduce") if step_mode == "graph" else "eager launches",
                        "l2_policy": "per-step working set (activations+saved tensors ~ GBs) exceeds the 126 MB L2; %d distinct batches rotate" % N_ROT},
             "e2e": {"value": total_seq / (ms_e2e * 1e-3), "unit": "seq/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / args.steps},

@@ -236,6 +236,22 @@ int rbm_sas_train_batch(const int64_t* hist_ptr, const int64_t* hist_items, cons
                         int64_t num_items, uint64_t seed, uint64_t site, int64_t* seq, int64_t* pos, int64_t* neg,
                         rbm_stream_t stream);
 
+/* Evaluation negatives: `n_samples` distinct items per user that the user has not seen, for users
+ * [user_begin, user_begin + num_users).  seen_ptr[U+1] / seen_items: CSR of each user's seen set, ASCENDING and unique.
+ * pop_cdf == NULL: uniform over 1..num_items (RandomNegativeSampler, NN/dataloaders/negative_samplers/random.py:13-37);
+ * else pop_cdf[num_items] (uint64) = inclusive prefix sums of the interaction counts of items 1..num_items and an item is
+ * drawn with probability count/total (PopularNegativeSampler, popular.py:15-44).  Rejection sampling, one thread per user;
+ * out [num_users, n_samples] int64 in acceptance order (-1 where 65536 attempts did not suffice).  Philox layout: csrc/batch.cu. */
+int rbm_negative_samples(const int64_t* seen_ptr, const int64_t* seen_items, const uint64_t* pop_cdf, int64_t user_begin,
+                         int64_t num_users, int64_t num_items, int n_samples, uint64_t seed, uint64_t site, int64_t* out,
+                         rbm_stream_t stream);
+/* Evaluation batch of BertEvalDataset / SASEvalDataset.__getitem__ (NN/dataloaders/bert.py:128-142, sas.py:136-153):
+ * seq [B, L] = last L entries of (history ++ [mask_token] if mask_token >= 0), left-padded with 0;
+ * cand [B, 1 + n_neg] = answers[u] then negatives[u, :]; labels [B, 1 + n_neg] = 1 then zeros. */
+int rbm_eval_batch(const int64_t* hist_ptr, const int64_t* hist_items, const int64_t* answers, const int64_t* negatives,
+                   const int64_t* users, int B, int L, int n_neg, int64_t mask_token, int64_t* seq, int64_t* cand,
+                   int64_t* labels, rbm_stream_t stream);
+
 /* ---- test / debug ---------------------------------------------------------------------------------- */
 /* materialise the keep-mask (1 = keep) the kernels use for an elementwise site over n elements */
 int rbm_dropout_mask(uint8_t* out, int64_t n, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);

@@ -84,3 +84,56 @@ def sas_train_batch(histories: List[List[int]], users: Sequence[int], max_len: i
                 r = rbm_philox(seed, site, b * 64 + (p >> 2))
                 neg[b, p] = a[(r[p & 3] * len(a)) >> 32]
     return seq, pos, neg
+
+
+NEG_MAX_ATTEMPTS = 65536
+
+
+def negative_samples(seen: List[Sequence[int]], num_items: int, n_samples: int, seed: int, site: int,
+                     pop_counts: Sequence[int] = None, user_begin: int = 0, num_users: int = None) -> np.ndarray:
+    """Evaluation negatives (NN/dataloaders/negative_samplers/random.py:13-37, popular.py:15-44) with the contract's numbers:
+    attempt t of user u draws r64 from Philox call u * 65536 + t (words 0, 1); uniform: item = 1 + (r64 * V >> 64)
+    (random.py:29, ``np.random.choice(item_count) + 1``); popularity: x = r64 * total >> 64, item = first id whose inclusive
+    count prefix sum exceeds x (popular.py:18-22,33: p = count / total).  An attempt is kept unless the item is in the user's
+    seen set (random.py:30, popular.py:34) or already kept; the first ``n_samples`` kept items are the row.
+    ``pop_counts[i]`` = interaction count of item i + 1."""
+    U = len(seen) - user_begin if num_users is None else num_users
+    out = np.full((U, n_samples), -1, np.int64)
+    cdf = None if pop_counts is None else np.cumsum(np.asarray(pop_counts, dtype=object))
+    for row in range(U):
+        u = user_begin + row
+        s, got = set(int(i) for i in seen[u]), []
+        for t in range(NEG_MAX_ATTEMPTS):
+            if len(got) == n_samples:
+                break
+            r = rbm_philox(seed, site, u * NEG_MAX_ATTEMPTS + t)
+            r64 = (r[0] << 32) | r[1]
+            if cdf is None:
+                item = 1 + ((r64 * num_items) >> 64)
+            else:
+                x = (r64 * int(cdf[-1])) >> 64
+                item = 1 + next(i for i in range(num_items) if cdf[i] > x)
+            if item in s or item in got:
+                continue
+            got.append(item)
+        out[row, :len(got)] = got
+    return out
+
+
+def eval_batch(histories: List[Sequence[int]], answers: Sequence[int], negatives: np.ndarray, users: Sequence[int], max_len: int,
+               mask_token: int = -1) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+    """BertEvalDataset.__getitem__ (NN/dataloaders/bert.py:128-142: seq + [mask_token], last max_len, left pad) /
+    SASEvalDataset.__getitem__ (NN/dataloaders/sas.py:136-153: no mask token, ``mask_token = -1`` here);
+    candidates = answer + negatives, labels = [1] + [0] * n."""
+    B, n_neg = len(users), negatives.shape[1]
+    seq = np.zeros((B, max_len), np.int64)
+    cand = np.zeros((B, 1 + n_neg), np.int64)
+    labels = np.zeros((B, 1 + n_neg), np.int64)
+    for b, u in enumerate(users):
+        s = list(histories[u]) + ([mask_token] if mask_token >= 0 else [])
+        s = s[-max_len:]
+        if s:
+            seq[b, max_len - len(s):] = s
+        cand[b, 0], cand[b, 1:] = answers[u], negatives[u]
+        labels[b, 0] = 1
+    return seq, cand, labels

@@ -4,4 +4,5 @@ the ``[user_train, user_valid, user_test, usernum, itemnum]`` layout of ``data_p
 are out of scope (SURVEY.md 2 row 10).  ``device`` holds the on-device batch construction (SURVEY.md 8(f) #1)."""
 from .synthetic import (synthetic_interactions, sliding_window_partition, BertBatcher, SasBatcher, eval_sequences,  # noqa: F401
                         uniform_negative_candidates)
-from .device import histories_to_csr, DeviceBertTrainLoader, DeviceSasTrainLoader  # noqa: F401,E402
+from .device import (histories_to_csr, DeviceBertTrainLoader, DeviceSasTrainLoader, seen_sets_to_csr, popularity_cdf,  # noqa: F401,E402
+                     DeviceNegativeSampler, DeviceEvalLoader)

@@ -71,16 +71,25 @@ class GradSync:
             self._tab_key = key
         return self._tab
 
+    def pack(self):
+        """Gradients -> flat bucket, scaled by 1/world (one launch)."""
+        tab = self._table()
+        check(L.load().rbm_bucket_pack(ptr(tab), ptr(self.cmap), self.cmap.shape[0], ptr(self.bucket), 1.0 / self.world, 0, stream()),
+              "bucket_pack")
+        count_launches()
+
+    def unpack(self):
+        """Flat bucket -> gradients (one launch)."""
+        tab = self._table()
+        check(L.load().rbm_bucket_pack(ptr(tab), ptr(self.cmap), self.cmap.shape[0], ptr(self.bucket), 1.0, 1, stream()), "bucket_unpack")
+        count_launches()
+
     def allreduce_grads(self):
         if self.world == 1:
             return
-        lib = L.load()
-        tab = self._table()
-        n = self.cmap.shape[0]
-        check(lib.rbm_bucket_pack(ptr(tab), ptr(self.cmap), n, ptr(self.bucket), 1.0 / self.world, 0, stream()), "bucket_pack")
+        self.pack()
         self.allreduce_bucket()
-        check(lib.rbm_bucket_pack(ptr(tab), ptr(self.cmap), n, ptr(self.bucket), 1.0, 1, stream()), "bucket_unpack")
-        count_launches(2)
+        self.unpack()
 
 
 def gather_topk(vals: torch.Tensor, ids: torch.Tensor, group=None) -> Tuple[torch.Tensor, torch.Tensor]:

@@ -67,6 +67,8 @@ SIGNATURES = {
     "rbm_set_step_counter": (_I, [_P]),
     "rbm_bert_cloze_batch": (_I, [_P, _P, _P, _I, _I, _D, _L, _L, _U64, _U64, _P, _P, _P]),
     "rbm_sas_train_batch": (_I, [_P, _P, _P, _I, _I, _L, _U64, _U64, _P, _P, _P, _P]),
+    "rbm_negative_samples": (_I, [_P, _P, _P, _L, _L, _L, _I, _U64, _U64, _P, _P]),
+    "rbm_eval_batch": (_I, [_P, _P, _P, _P, _P, _I, _I, _I, _L, _P, _P, _P, _P]),
     "rbm_dropout_mask": (_I, [_P, _L, _F, _U64, _U64, _P]),
     "rbm_dropout_mask_attn": (_I, [_P, _L, _I, _F, _U64, _U64, _P]),
 }

@@ -515,3 +515,44 @@ def sas_train_batch(hist_ptr, hist_items, users, max_len, num_items, seed, step)
                                   BATCH_SITE_BASE + int(step), ptr(out[0]), ptr(out[1]), ptr(out[2]), stream()), "sas_train_batch")
     count_launches()
     return tuple(out)
+
+
+NEG_SITE = 1 << 41  # Philox site of the evaluation-negative sampler (disjoint from dropout and batch sites)
+
+
+def negative_samples(seen_ptr, seen_items, num_items, n_samples, seed, pop_cdf=None, user_begin=0, num_users=None):
+    """[num_users, n_samples] int64 evaluation negatives on the device: Random / PopularNegativeSampler
+    (NN/dataloaders/negative_samplers/random.py:13-37, popular.py:15-44).  ``seen_items`` ascending + unique per user;
+    ``pop_cdf`` (int64/uint64 [num_items], inclusive prefix sums of item counts) selects popularity-weighted draws."""
+    lib = L.load()
+    L.require_cuda(seen_ptr, seen_items)
+    if pop_cdf is not None:
+        L.require_cuda(pop_cdf)
+        if pop_cdf.numel() != num_items or pop_cdf.dtype != torch.int64:
+            raise RuntimeError("negative_samples: pop_cdf must be int64 [num_items]")
+    U = int(seen_ptr.numel()) - 1 - int(user_begin) if num_users is None else int(num_users)
+    out = torch.empty(U, int(n_samples), device=seen_ptr.device, dtype=torch.int64)
+    check(lib.rbm_negative_samples(ptr(seen_ptr), ptr(seen_items), ptr(pop_cdf) if pop_cdf is not None else None, int(user_begin), U,
+                                   int(num_items), int(n_samples), int(seed), NEG_SITE, ptr(out), stream()), "negative_samples")
+    count_launches()
+    return out
+
+
+def eval_batch(hist_ptr, hist_items, answers, negatives, users, max_len, mask_token=-1):
+    """(seq [B,L], candidates [B,1+N], labels [B,1+N]) int64 on the device: BertEvalDataset / SASEvalDataset.__getitem__
+    (NN/dataloaders/bert.py:128-142 with ``mask_token`` appended, sas.py:136-153 with ``mask_token=-1``)."""
+    lib = L.load()
+    L.require_cuda(hist_ptr, hist_items, answers, users)
+    Bsz = int(users.numel())
+    n_neg = 0 if negatives is None else int(negatives.shape[1])
+    if negatives is not None:
+        L.require_cuda(negatives)
+        negatives = negatives.contiguous()
+    dev = users.device
+    seq = torch.empty(Bsz, int(max_len), device=dev, dtype=torch.int64)
+    cand = torch.empty(Bsz, 1 + n_neg, device=dev, dtype=torch.int64)
+    labels = torch.empty(Bsz, 1 + n_neg, device=dev, dtype=torch.int64)
+    check(lib.rbm_eval_batch(ptr(hist_ptr), ptr(hist_items), ptr(answers), ptr(negatives) if negatives is not None else None, ptr(users),
+                             Bsz, int(max_len), n_neg, int(mask_token), ptr(seq), ptr(cand), ptr(labels), stream()), "eval_batch")
+    count_launches()
+    return seq, cand, labels

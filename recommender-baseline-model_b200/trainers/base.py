@@ -52,6 +52,7 @@ class AbstractTrainer(metaclass=ABCMeta):
         self.best_value = None
         self.dist_sync = None  # set to rbm_b200.dist.GradSync for data-parallel training
         self._graph = None     # set by capture_train_step()
+        self._graph_b = None
 
     @classmethod
     @abstractmethod
@@ -82,22 +83,28 @@ class AbstractTrainer(metaclass=ABCMeta):
         return loss
 
     # ---------------------------------------------------------------- the same step as ONE CUDA graph
-    def capture_train_step(self, example_batch, warmup: int = 3):
+    def capture_train_step(self, example_batch, warmup: int = 3, collective: str = "split"):
         """Capture zero_grad + loss + backward + optimizer step into a CUDA graph; later ``train_step`` calls copy the batch
         into the graph's static input buffers and replay it (one launch instead of ~200: at the reference's batch sizes of
         64-128 the step is host-bound otherwise).  Dropout sites and Adam's bias correction advance through the library's
         device-side step counter (``rbm_set_step_counter``), so replay number j reproduces eager step s0 + j bit for bit.
-        Single-GPU, fused Adam, fixed batch shape and learning rate (call again after the scheduler changes ``lr``)."""
+        Fused Adam, fixed batch shape and learning rate (call again after the scheduler changes ``lr``).
+
+        Data-parallel (``dist_sync`` set; every rank must call this at the same point): ``collective="split"`` captures TWO
+        graphs -- [zero_grad, loss, backward, bucket pack] and [bucket unpack, Adam] -- and issues the one NCCL all-reduce of
+        the flat bucket eagerly between their replays (three host calls per step, so the ranks do not drift apart on host
+        jitter); ``collective="graph"`` captures the all-reduce too (one graph)."""
         import copy
         from .. import lib as L
-        if self.dist_sync is not None:
-            raise RuntimeError("capture_train_step: data-parallel gradient exchange is not captured; use the eager step")
+        if collective not in ("split", "graph"):
+            raise ValueError("collective must be 'split' or 'graph'")
         if not isinstance(self.optimizer, FusedAdam):
             raise RuntimeError("capture_train_step needs the fused Adam optimizer")
+        sync = self.dist_sync if (self.dist_sync is not None and self.dist_sync.world > 1) else None
         dev = torch.device(self.device)
         static = tuple(torch.as_tensor(x).to(dev).clone() for x in example_batch)
-        # warm-up on a side stream (lazy one-time work: function attributes, context binding, workspaces, Adam state),
-        # then put model / optimizer / step counters back so that the captured step is the next real one
+        # warm-up on a side stream (lazy one-time work: function attributes, context binding, workspaces, Adam state, the
+        # NCCL communicator), then put model / optimizer / step counters back so that the captured step is the next real one
         model_sd = copy.deepcopy(self.model.state_dict())
         opt_sd = copy.deepcopy(self.optimizer.state_dict())
         step0 = self.model._step
@@ -108,6 +115,8 @@ class AbstractTrainer(metaclass=ABCMeta):
                 self.optimizer.zero_grad()
                 loss = self.calculate_loss(static)
                 loss.backward()
+                if sync is not None:
+                    sync.allreduce_grads()
                 self.optimizer.step()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
@@ -119,20 +128,47 @@ class AbstractTrainer(metaclass=ABCMeta):
         self._graph_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         L.check(L.load().rbm_set_step_counter(self._graph_counter.data_ptr()), "set_step_counter")
         # persistent gradient buffers: the graph zeroes and re-accumulates them in place, so every address Adam's descriptor
-        # table holds is known (and uploaded) before capture -- no host->device copy inside the graph
+        # table (and the gradient-bucket table) holds is known (and uploaded) before capture -- no host->device copy inside the graph
         for p in self.model.parameters():
             if p.requires_grad:
                 p.grad = torch.zeros_like(p)
         self.optimizer.stage_tables()
+        if sync is not None:
+            sync._table()
+        # NCCL's watchdog thread polls CUDA events while we capture: only this thread's calls belong to the capture
+        mode = {"capture_error_mode": "thread_local"} if sync is not None else {}
+        launches0 = L.launch_count
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        graph_b = None
+        try:
+            loss = self._capture(graph, static, sync, collective, mode)
+            if sync is not None and collective == "split":
+                graph_b = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(graph_b, pool=graph.pool(), **mode):
+                    sync.unpack()
+                    self.optimizer.step()
+                    self._graph_counter.add_(1)
+        except BaseException:
+            L.load().rbm_set_step_counter(None)
+            raise
+        self._graph_launches = L.launch_count - launches0
+        self._graph, self._graph_b, self._graph_static, self._graph_loss, self._graph_lr = graph, graph_b, static, loss, self.get_lr()
+        return self
+
+    def _capture(self, graph, static, sync, collective, mode):
+        with torch.cuda.graph(graph, **mode):
             self.optimizer.zero_grad(set_to_none=False)
             loss = self.calculate_loss(static)
             loss.backward()
-            self.optimizer.step()
-            self._graph_counter.add_(1)
-        self._graph, self._graph_static, self._graph_loss, self._graph_lr = graph, static, loss, self.get_lr()
-        return self
+            if sync is not None:
+                sync.pack()
+                if collective == "graph":
+                    sync.allreduce_bucket()
+                    sync.unpack()
+            if sync is None or collective == "graph":
+                self.optimizer.step()
+                self._graph_counter.add_(1)
+        return loss
 
     def release_train_graph(self):
         """Back to eager steps (the python-side step counters are advanced by the number of replays)."""
@@ -146,14 +182,19 @@ class AbstractTrainer(metaclass=ABCMeta):
         for st in self.optimizer.state.values():
             if "step" in st:
                 st["step"] += done - 1
-        self._graph = None
+        self._graph = self._graph_b = None
 
     def _replay(self, batch):
+        from .. import lib as L
         if self.get_lr() != self._graph_lr:
             raise RuntimeError("the learning rate changed since capture_train_step(): release_train_graph() and capture again")
         for dst, src in zip(self._graph_static, batch):
             dst.copy_(torch.as_tensor(src), non_blocking=True)
         self._graph.replay()
+        if self._graph_b is not None:
+            self.dist_sync.allreduce_bucket()
+            self._graph_b.replay()
+        L.count_launches(self._graph_launches)
         return self._graph_loss
 
     def train(self):

@@ -342,11 +342,94 @@ def gen_batches(name="batches"):
     print("wrote", name)
 
 
+def gen_eval_batches(name="eval_batches"):
+    """Evaluation negatives and evaluation batches of the REFERENCE classes with the contract's random numbers injected:
+    ``RandomNegativeSampler`` / ``PopularNegativeSampler.generate_negative_samples`` (NN/dataloaders/negative_samplers/) run
+    with ``np.random.choice`` replaced by draws from the Philox stream of (user, attempt) -- for the popularity sampler the
+    fake returns ``sample_size`` DISTINCT successive inverse-CDF draws, which is what ``choice(replace=False, p=...)`` means --
+    and ``BertEvalDataset`` / ``SASEvalDataset.__getitem__`` (NN/dataloaders/bert.py:116-142, sas.py:124-153) run as they are."""
+    from oracle.batches import rbm_philox, NEG_MAX_ATTEMPTS
+    import dataloaders.negative_samplers.random as ref_rand
+    import dataloaders.negative_samplers.popular as ref_pop
+    import dataloaders.bert as ref_bert
+    import dataloaders.sas as ref_sas
+
+    rs = np.random.RandomState(5)
+    V, U, S = 61, 9, 12
+    zipf = 1.0 / np.arange(1, V + 1)
+    zipf /= zipf.sum()
+    lens = [3, 4, 6, 9, 14, 22, 30, 5, 40]
+    train = {u: [int(i) for i in rs.choice(V, size=n, p=zipf) + 1] for u, n in enumerate(lens)}
+    val = {u: [int(rs.randint(1, V + 1))] for u in range(U)}
+    test = {u: [int(rs.randint(1, V + 1))] for u in range(U)}
+    seed, site = 424242, 1 << 41
+    counts = np.zeros(V + 1, np.int64)
+    for d in (train, val, test):
+        for u in range(U):
+            np.add.at(counts, np.array(d[u]), 1)
+    cdf = [int(c) for c in np.cumsum(counts[1:])]
+    state = {"u": 0, "t": 0}
+
+    def fake_trange(a, b):
+        for u in range(a, b):
+            state["u"], state["t"] = u, 0
+            yield u
+
+    def r64():
+        r = rbm_philox(seed, site, state["u"] * NEG_MAX_ATTEMPTS + state["t"])
+        state["t"] += 1
+        return (r[0] << 32) | r[1]
+
+    def fake_choice(a, size=None, replace=True, p=None):
+        if size is None:  # random.py:29,31
+            return (r64() * int(a)) >> 64
+        got = []  # popular.py:33
+        while len(got) < size:
+            x = (r64() * cdf[-1]) >> 64
+            item = 1 + next(i for i in range(V) if cdf[i] > x)
+            if item not in got:
+                got.append(item)
+        return np.array(got)
+
+    out = {"num_items": np.int64(V), "sample_size": np.int64(S), "seed": np.uint64(seed), "site": np.uint64(site),
+           "pop_counts": counts[1:].copy()}
+    for k, d in (("train", train), ("val", val), ("test", test)):
+        out[k + "_ptr"] = np.cumsum([0] + [len(d[u]) for u in range(U)]).astype(np.int64)
+        out[k + "_items"] = np.array([i for u in range(U) for i in d[u]], np.int64)
+    real_choice = np.random.choice
+    negs = {}
+    for tag, mod, cls in (("random", ref_rand, ref_rand.RandomNegativeSampler), ("popular", ref_pop, ref_pop.PopularNegativeSampler)):
+        real_trange = mod.trange
+        mod.trange = fake_trange
+        mod.np.random.choice = fake_choice
+        try:
+            ns = cls(train, val, test, U, V, S, 7, "/tmp", "golden").generate_negative_samples()
+        finally:
+            mod.trange = real_trange
+            mod.np.random.choice = real_choice
+        negs[tag] = np.array([[int(i) for i in ns[u]] for u in range(U)], np.int64)
+        out["neg_" + tag] = negs[tag]
+    # evaluation batches (validation protocol: u2seq = train, answers = val)
+    neg_dict = {u: [int(i) for i in negs["random"][u]] for u in range(U)}
+    for L in (8, 16):
+        bd = ref_bert.BertEvalDataset(train, val, L, V + 1, neg_dict)
+        sd = ref_sas.SASEvalDataset(train, val, L, neg_dict)
+        rows_b, rows_s = [bd[u] for u in range(U)], [sd[u] for u in range(U)]
+        for j, nm in enumerate(("seq", "cand", "labels")):
+            out["bert_L%d.%s" % (L, nm)] = np.stack([np.asarray(r[j]) for r in rows_b]).astype(np.int64)
+            out["sas_L%d.%s" % (L, nm)] = np.stack([np.asarray(r[j]) for r in rows_s]).astype(np.int64)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     ap = argparse.ArgumentParser()
-    ap.parse_args()
+    ap.add_argument("--only", default=None, help="regenerate one fixture family only (eval_batches)")
+    args = ap.parse_args()
     torch.set_num_threads(1)  # fixed reduction order in the generated vectors
     model_factory, metric_fn = ref_imports()
+    if args.only == "eval_batches":
+        return gen_eval_batches()
     gen_bert(model_factory, "bert_tiny", V=37, L=8, d=16, nb=2, h=2, B=4, seed=0)
     gen_bert(model_factory, "bert_odd", V=101, L=13, d=32, nb=1, h=4, B=3, seed=3)
     gen_bert(model_factory, "bert_cfg2", V=3416, L=200, d=64, nb=2, h=2, B=4, seed=1, store_sd=False, adam_steps=2)
@@ -356,6 +439,7 @@ def main():
     gen_metrics(metric_fn)
     gen_scatter_adam()
     gen_batches()
+    gen_eval_batches()
 
 
 if __name__ == "__main__":

@@ -88,6 +88,28 @@ def _worker(rank, world, port, q):
         assert torch.allclose(h2.grad, h1.grad, rtol=1e-4, atol=1e-7), (h2.grad - h1.grad).abs().max()
         assert torch.allclose(w2.grad, w1.grad[lo:hi], rtol=1e-4, atol=1e-7)
         assert torch.allclose(b2.grad, b1.grad[lo:hi], rtol=1e-4, atol=1e-7)
+        # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
+        # bit for bit, dropout on
+        import copy
+        args.bert_dropout = args.bert_hidden_dropout = 0.1
+        batches = [(torch.from_numpy(tokm[sl]).to(dev), torch.from_numpy(lab[sl]).to(dev)),
+                   (torch.from_numpy(np.ascontiguousarray(tokm[sl][::-1])).to(dev), torch.from_numpy(np.ascontiguousarray(lab[sl][::-1])).to(dev))]
+        results = []
+        for mode in ("eager", "split"):
+            m = rbm_b200.model_factory(args)
+            t = rbm_b200.trainer_factory(args, m, None, None, None, None)
+            t.dist_sync = GradSync(m.parameters())
+            m.train()
+            ls = [t.train_step(batches[0]).item()]
+            if mode != "eager":
+                t.capture_train_step(batches[1], collective=mode)
+            for i in range(1, 5):
+                ls.append(t.train_step(batches[i % 2]).item())
+            t.release_train_graph()
+            ls.append(t.train_step(batches[1]).item())
+            results.append((ls, torch.cat([p.detach().flatten() for p in m.parameters()]).clone()))
+        assert results[0][0] == results[1][0], (results[0][0], results[1][0])
+        assert torch.equal(results[0][1], results[1][1]), "graph-replayed data-parallel step differs from the eager one"
         q.put((rank, "ok"))
     except Exception:  # noqa
         import traceback
