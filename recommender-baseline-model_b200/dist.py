@@ -211,3 +211,96 @@ class VocabParallelCEFn(torch.autograd.Function):
 def vocab_parallel_cross_entropy(hidden, labels, w_shard, bias_shard, v_begin: int, group=None):
     """See VocabParallelCEFn.  ``v_begin`` = first row of the output layer held by this rank (``shard_range(V + 1, rank, world)``)."""
     return VocabParallelCEFn.apply(hidden, labels, w_shard, bias_shard, v_begin, group)
+
+
+# ------------------------------------------------------------ data-parallel batch x vocab-parallel output layer (cfg4)
+def masked_row_slots(count: torch.Tensor, rows: torch.Tensor, tgt: torch.Tensor, capacity: int):
+    """Fixed-capacity view of a rank's compacted masked rows (``rbm_compact_labels`` output: ``rows[:count]`` are the row ids
+    with label != 0, ``tgt[:count]`` their labels; entries beyond ``count`` are uninitialised).  Returns
+    ``(live [cap] bool, rows_c [cap] int64, labels_c [cap] int64, overflow 0-dim bool)``: dead slots point at row 0 and carry
+    label 0 (= ignored by the cross-entropy), ``overflow`` says that ``count > capacity`` (rows would be dropped)."""
+    cap = int(capacity)
+    cnt = count.reshape(()).to(torch.int64)
+    live = torch.arange(cap, device=rows.device) < cnt
+    zero = torch.zeros((), dtype=torch.int64, device=rows.device)
+    rows_c = torch.where(live, rows[:cap].to(torch.int64), zero)
+    labels_c = torch.where(live, tgt[:cap].to(torch.int64), zero)
+    return live, rows_c, labels_c, cnt > cap
+
+
+def gather_slots(h2: torch.Tensor, live, rows_c, labels_c, group=None):
+    """Rows of ``h2`` named by the slots (dead slots zeroed) and their labels, all-gathered over the ranks in rank order:
+    ``([world * cap, d], [world * cap])``."""
+    slots = h2.index_select(0, rows_c) * live.unsqueeze(1).to(h2.dtype)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world == 1:
+        return slots, labels_c
+    hs = [torch.empty_like(slots) for _ in range(world)]
+    ls = [torch.empty_like(labels_c) for _ in range(world)]
+    dist.all_gather(hs, slots.contiguous(), group=group)
+    dist.all_gather(ls, labels_c.contiguous(), group=group)
+    return torch.cat(hs), torch.cat(ls)
+
+
+def scatter_slot_grads(dh_all: torch.Tensor, rows_c, live, n: int, cap: int, rank: int, scale: float):
+    """This rank's slice of the gathered rows' gradient back onto its ``n`` local rows (times ``scale``)."""
+    mine = dh_all[rank * cap:(rank + 1) * cap] * (live.unsqueeze(1).to(dh_all.dtype) * scale)
+    dh = torch.zeros(n, dh_all.shape[1], device=dh_all.device, dtype=dh_all.dtype)
+    dh.index_add_(0, rows_c, mine)  # live slots hold distinct rows; dead slots add exact zeros to row 0: order-independent
+    return dh
+
+
+class GatherMaskedRowsFn(torch.autograd.Function):
+    """SURVEY.md 8(e), BERT CE at cfg4: every rank holds ITS OWN sequences (data parallel); only the rows with a label
+    (about 15 %) take part in the vocab-parallel scoring.  Forward: compact the local masked rows on the device
+    (``rbm_compact_labels``), place them in ``capacity`` slots (no host sync: the slot count is static, dead slots carry
+    label 0), all-gather slots and labels -> ``[world * capacity, d]`` replicated rows for ``vocab_parallel_cross_entropy``.
+    Backward: this rank's slice of the (already shard-summed) dH goes back to its local rows, times ``grad_scale``."""
+
+    @staticmethod
+    def forward(ctx, hidden, labels, capacity, group, grad_scale):
+        from . import ops
+        lib = L.load()
+        L.require_cuda(hidden, labels)
+        h2 = hidden.reshape(-1, hidden.shape[-1])
+        n, d = h2.shape
+        lab = labels.reshape(-1).contiguous()
+        dev = hidden.device
+        rows = torch.empty(n, device=dev, dtype=torch.int32)
+        tgt = torch.empty(n, device=dev, dtype=torch.int64)
+        count = torch.empty(1, device=dev, dtype=torch.int32)
+        nb = lib.rbm_compact_ws_bytes(n)
+        ws = ops._ws("compact", nb, dev)
+        check(lib.rbm_compact_labels(ptr(lab), n, ptr(rows), ptr(tgt), ptr(count), ptr(ws), nb, stream()), "compact_labels")
+        count_launches(3)
+        cap = n if capacity is None else min(int(capacity), n)
+        live, rows_c, labels_c, overflow = masked_row_slots(count, rows, tgt, cap)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        h_all, l_all = gather_slots(h2, live, rows_c, labels_c, group)
+        ctx.save_for_backward(rows_c, live)
+        ctx.meta = (hidden.shape, n, d, cap, rank, float(grad_scale))
+        ctx.mark_non_differentiable(l_all, overflow)
+        return h_all, l_all, overflow
+
+    @staticmethod
+    def backward(ctx, dh_all, _dl, _do):
+        rows_c, live = ctx.saved_tensors
+        shape, n, d, cap, rank, scale = ctx.meta
+        return scatter_slot_grads(dh_all, rows_c, live, n, cap, rank, scale).view(shape), None, None, None, None
+
+
+def hybrid_vocab_parallel_loss(hidden, labels, w_shard, bias_shard, v_begin: int, capacity=None, group=None,
+                               compensate_grad_average: bool = True):
+    """Masked cross-entropy of the GLOBAL batch when sequences are data-parallel and the output layer is row-sharded
+    (BASELINE configs[3]).  ``hidden [B_local, L, d]`` / ``labels [B_local, L]`` are this rank's own; returns
+    ``(loss, overflow)``: the mean over all labelled positions of all ranks (what one GPU computes on the concatenated batch,
+    NN/trainers/bert.py:30-41), and a device flag that is true if some rank had more than ``capacity`` labelled rows
+    (``capacity=None``: B_local*L slots, never overflows; about 0.2*B_local*L keeps the exchange at the 15 % mask rate).
+    Gradients: ``w_shard`` / ``bias_shard`` get the exact global-batch gradient of their rows (keep them OUT of the
+    data-parallel bucket); ``hidden`` gets the global-batch gradient of its rows, multiplied by the world size when
+    ``compensate_grad_average`` so that ``GradSync``'s averaging of the body gradients yields the global-batch gradient."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    scale = float(world) if compensate_grad_average else 1.0
+    h_all, l_all, overflow = GatherMaskedRowsFn.apply(hidden, labels, capacity, group, scale)
+    return vocab_parallel_cross_entropy(h_all, l_all, w_shard, bias_shard, v_begin, group), overflow

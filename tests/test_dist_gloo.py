@@ -75,6 +75,35 @@ def _worker(rank, world, port, q):
         LSE, loss = rd.combine_shard_lse(torch.stack(lse_list), torch.cat(loss_list), torch.tensor([P], dtype=torch.int32))
         assert abs(float(loss) - float(torch.nn.functional.cross_entropy(logits, tgt))) < 1e-5
         assert torch.allclose(LSE[:P], torch.logsumexp(logits, 1), atol=1e-5)
+        # ---- data-parallel batch x vocab-parallel output layer: fixed-capacity slots of the labelled rows, all-gather,
+        #      gradient slices back to the owners (the compaction and the scoring are CUDA kernels: GPU test)
+        torch.manual_seed(7)
+        n_loc, dd, Vh, cap = 24, 8, 50, 10
+        H_glob = torch.randn(world * n_loc, dd)
+        lab_glob = torch.where(torch.rand(world * n_loc) < 0.25, torch.randint(1, Vh, (world * n_loc,)), torch.zeros((), dtype=torch.int64))
+        lab_glob[5] = 7  # at least one label
+        Wf = torch.randn(Vh, dd)
+        Hl = H_glob[rank * n_loc:(rank + 1) * n_loc].clone()
+        ll = lab_glob[rank * n_loc:(rank + 1) * n_loc]
+        nz = torch.nonzero(ll).flatten()
+        rows = torch.full((n_loc,), 12345, dtype=torch.int32)  # garbage beyond count, as the kernel leaves it
+        tg = torch.full((n_loc,), -99, dtype=torch.int64)
+        rows[:nz.numel()], tg[:nz.numel()] = nz.to(torch.int32), ll[nz]
+        rows[nz.numel():] = 3
+        live, rows_c, labels_c, overflow = rd.masked_row_slots(torch.tensor([nz.numel()], dtype=torch.int32), rows, tg, cap)
+        assert not bool(overflow) and int(live.sum()) == nz.numel() and (labels_c[~live] == 0).all() and (rows_c[~live] == 0).all()
+        h_all, l_all = rd.gather_slots(Hl, live, rows_c, labels_c)
+        assert h_all.shape == (world * cap, dd) and torch.equal(l_all[l_all != 0].sort().values, lab_glob[lab_glob != 0].sort().values)
+        h_all = h_all.clone().requires_grad_(True)
+        loss = torch.nn.functional.cross_entropy(h_all @ Wf.t(), l_all, ignore_index=0)
+        Hg = H_glob.clone().requires_grad_(True)
+        ref = torch.nn.functional.cross_entropy(Hg @ Wf.t(), lab_glob, ignore_index=0)
+        assert abs(float(loss) - float(ref)) < 1e-6
+        loss.backward(); ref.backward()
+        dh = rd.scatter_slot_grads(h_all.grad, rows_c, live, n_loc, cap, rank, float(world))
+        assert torch.allclose(dh, Hg.grad[rank * n_loc:(rank + 1) * n_loc] * world, atol=1e-7)
+        _, _, _, ovf = rd.masked_row_slots(torch.tensor([nz.numel()], dtype=torch.int32), rows, tg, max(1, nz.numel() - 1))
+        assert bool(ovf)
         q.put((rank, "ok"))
     except Exception as ex:  # noqa
         import traceback

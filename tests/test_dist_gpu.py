@@ -88,6 +88,31 @@ def _worker(rank, world, port, q):
         assert torch.allclose(h2.grad, h1.grad, rtol=1e-4, atol=1e-7), (h2.grad - h1.grad).abs().max()
         assert torch.allclose(w2.grad, w1.grad[lo:hi], rtol=1e-4, atol=1e-7)
         assert torch.allclose(b2.grad, b1.grad[lo:hi], rtol=1e-4, atol=1e-7)
+        # data-parallel rows x vocab-parallel output layer (cfg4 layout): == fused CE of the concatenated batch on one GPU
+        from rbm_b200.dist import hybrid_vocab_parallel_loss
+        g2 = torch.Generator().manual_seed(23)
+        Bl, Lh = 6, 40
+        hid_g = torch.randn(world * Bl, Lh, dc, generator=g2).to(dev)
+        lab_g = torch.randint(1, V1c, (world * Bl, Lh), generator=g2)
+        lab_g[torch.rand(world * Bl, Lh, generator=g2) > (0.1 if rank == 0 else 0.1)] = 0
+        lab_g[Bl:][torch.rand((world - 1) * Bl, Lh, generator=g2) > 0.5] = 0  # unequal counts per rank
+        lab_g = lab_g.to(dev)
+        hg, wg, bg = hid_g.clone().requires_grad_(True), wfull.clone().requires_grad_(True), bfull.clone().requires_grad_(True)
+        ref_h = rbm_b200.ops.score_cross_entropy(hg.reshape(-1, dc), lab_g.reshape(-1), wg, bg)
+        ref_h.backward()
+        slr = slice(rank * Bl, (rank + 1) * Bl)
+        for cap_h in (None, 64):
+            hl = hid_g[slr].clone().requires_grad_(True)
+            ws_, bs_ = wfull[lo:hi].clone().requires_grad_(True), bfull[lo:hi].clone().requires_grad_(True)
+            out_h, ovf = hybrid_vocab_parallel_loss(hl, lab_g[slr], ws_, bs_, lo, capacity=cap_h)
+            out_h.backward()
+            assert not bool(ovf)
+            assert abs(out_h.item() - ref_h.item()) < 1e-5 * abs(ref_h.item()), (out_h.item(), ref_h.item())
+            assert torch.allclose(hl.grad, hg.grad[slr] * world, rtol=1e-4, atol=1e-7), (hl.grad - hg.grad[slr] * world).abs().max()
+            assert torch.allclose(ws_.grad, wg.grad[lo:hi], rtol=1e-4, atol=1e-7)
+            assert torch.allclose(bs_.grad, bg.grad[lo:hi], rtol=1e-4, atol=1e-7)
+        _, ovf = hybrid_vocab_parallel_loss(hid_g[slr], lab_g[slr], wfull[lo:hi], bfull[lo:hi], lo, capacity=2)
+        assert bool(ovf)
         # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
         # bit for bit, dropout on
         import copy

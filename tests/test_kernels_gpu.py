@@ -486,3 +486,81 @@ def test_batch_construction_properties_at_bench_size():
         w = set(hist[u][-50:])
         assert all(int(x) not in w for x in n[b][p[b] != 0].tolist())
     assert (n[p == 0] == 0).all() and (n <= V).all() and (n >= 0).all()
+
+
+# ------------------------------------------------------------------------------------ evaluation negatives / batches
+def _gold_split(z, name):
+    ptr, items = z[name + "_ptr"], z[name + "_items"]
+    return [items[ptr[u]:ptr[u + 1]].tolist() for u in range(len(ptr) - 1)]
+
+
+def test_negative_samples_and_eval_batch_golden():
+    """rbm_negative_samples / rbm_eval_batch reproduce what the REFERENCE samplers and eval datasets produce when fed the
+    contract's random numbers (tests/golden/eval_batches.npz); also through the loader classes."""
+    import os
+    from rbm_b200.dataloaders import DeviceNegativeSampler, DeviceEvalLoader
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "eval_batches.npz"))
+    tr, va, te = _gold_split(z, "train"), _gold_split(z, "val"), _gold_split(z, "test")
+    V, S, seed = int(z["num_items"]), int(z["sample_size"]), int(z["seed"])
+    assert int(z["site"]) == ops.NEG_SITE
+    negs = {}
+    for code in ("random", "popular"):
+        smp = DeviceNegativeSampler(tr, va, te, len(tr), V, S, seed, DEV, code=code)
+        negs[code] = smp.get_negative_samples()
+        np.testing.assert_array_equal(negs[code].cpu().numpy(), z["neg_" + code])
+        part = ops.negative_samples(smp.seen_ptr, smp.seen_items, V, S, seed, smp.cdf, user_begin=3, num_users=4)
+        np.testing.assert_array_equal(part.cpu().numpy(), z["neg_" + code][3:7])
+    for model, mask in (("bert", V + 1), ("sas", -1)):
+        for Ln in (8, 16):
+            ld = DeviceEvalLoader(tr, va, negs["random"], Ln, 4, DEV, mask_token=mask)
+            parts = list(ld)
+            assert len(parts) == len(ld) == 3
+            for j, nm in enumerate(("seq", "cand", "labels")):
+                got = torch.cat([p[j] for p in parts]).cpu().numpy()
+                np.testing.assert_array_equal(got, z["%s_L%d.%s" % (model, Ln, nm)])
+
+
+@pytest.mark.parametrize("V,U,S", [(300, 500, 100), (3416, 2000, 100), (40, 64, 8)])
+def test_negative_samples_ragged_vs_oracle(V, U, S):
+    """Empty seen sets, users who have seen most of the catalogue, heavy-tailed popularity; bit-exact vs the oracle."""
+    from oracle import batches as obt
+    rs = np.random.RandomState(V + U)
+    lens = np.minimum(rs.randint(0, max(2, V // 2), size=U), V - S - 1)
+    lens[0], lens[1] = 0, V - S  # nothing seen / exactly S unseen items left
+    seen = [sorted(rs.choice(V, size=n, replace=False) + 1) for n in lens]
+    counts = np.maximum(1, (1000.0 / np.arange(1, V + 1)).astype(np.int64))
+    counts[rs.permutation(V)[: V // 10]] = 0  # items nobody interacted with are never drawn by popularity
+    ptr, items = _csr(seen)
+    cdf = g(torch.from_numpy(np.cumsum(counts)))
+    nu = 48 if V > 1000 else U  # the pure-python oracle is slow: a user sub-range at the larger sizes
+    for code, c, pc in (("random", None, None), ("popular", cdf, counts.tolist())):
+        out = ops.negative_samples(ptr, items, V, S, 77, c, user_begin=0, num_users=nu).cpu().numpy()
+        ref = obt.negative_samples(seen, V, S, 77, ops.NEG_SITE, pop_counts=pc, user_begin=0, num_users=nu)
+        np.testing.assert_array_equal(out, ref)
+        full = ops.negative_samples(ptr, items, V, S, 77, c).cpu().numpy()
+        np.testing.assert_array_equal(full[:nu], out)
+        for u in range(U):
+            row = full[u][full[u] >= 0].tolist()
+            assert len(set(row)) == len(row) and not (set(row) & set(int(i) for i in seen[u]))
+            if code == "random":
+                assert len(row) == S
+
+
+def test_eval_batch_ragged_vs_oracle():
+    from oracle import batches as obt
+    rs = np.random.RandomState(3)
+    V, Ln, N = 500, 50, 100
+    lens = [0, 1, Ln - 1, Ln, Ln + 1, 3 * Ln] + list(rs.randint(0, 120, size=60))
+    hist = [list(rs.randint(1, V + 1, size=n)) for n in lens]
+    U = len(hist)
+    answers = rs.randint(1, V + 1, size=U).astype(np.int64)
+    negatives = rs.randint(1, V + 1, size=(U, N)).astype(np.int64)
+    users = list(rs.permutation(U)) + [0, 0, 5]
+    ptr, items = _csr(hist)
+    for mask in (V + 1, -1):
+        s, c, l = ops.eval_batch(ptr, items, g(torch.from_numpy(answers)), g(torch.from_numpy(negatives)),
+                                 g(torch.tensor(users, dtype=torch.int64)), Ln, mask)
+        so, co, lo = obt.eval_batch(hist, answers, negatives, users, Ln, mask)
+        np.testing.assert_array_equal(s.cpu().numpy(), so)
+        np.testing.assert_array_equal(c.cpu().numpy(), co)
+        np.testing.assert_array_equal(l.cpu().numpy(), lo)

@@ -233,3 +233,49 @@ def test_sas_train_batch_vs_reference_sampler(tag, L):
     np.testing.assert_array_equal(s, z[tag + ".seq"])
     np.testing.assert_array_equal(p, z[tag + ".pos"])
     np.testing.assert_array_equal(n, z[tag + ".neg"])
+
+
+# ------------------------------------------------------------------------------------ evaluation negatives / batches
+def _split(z, name):
+    ptr, items = z[name + "_ptr"], z[name + "_items"]
+    return [items[ptr[u]:ptr[u + 1]].tolist() for u in range(len(ptr) - 1)]
+
+
+@pytest.mark.parametrize("code", ["random", "popular"])
+def test_negative_samples_vs_reference_sampler(code):
+    """oracle.batches.negative_samples == Random / PopularNegativeSampler.generate_negative_samples of the reference driven
+    by the same random numbers (tests/golden/eval_batches.npz)."""
+    from oracle import batches as obt
+    z = load("eval_batches")
+    tr, va, te = _split(z, "train"), _split(z, "val"), _split(z, "test")
+    seen = [sorted(set(tr[u]) | set(va[u]) | set(te[u])) for u in range(len(tr))]
+    out = obt.negative_samples(seen, int(z["num_items"]), int(z["sample_size"]), int(z["seed"]), int(z["site"]),
+                               pop_counts=z["pop_counts"].tolist() if code == "popular" else None)
+    np.testing.assert_array_equal(out, z["neg_" + code])
+    for u in range(len(tr)):  # what the samplers promise: distinct, unseen, in range
+        row = out[u].tolist()
+        assert len(set(row)) == len(row) and not (set(row) & set(seen[u])) and min(row) >= 1 and max(row) <= int(z["num_items"])
+    # a sub-range of users is the same rows (the counter is the user id, not the row)
+    part = obt.negative_samples(seen, int(z["num_items"]), int(z["sample_size"]), int(z["seed"]), int(z["site"]),
+                                pop_counts=z["pop_counts"].tolist() if code == "popular" else None, user_begin=3, num_users=4)
+    np.testing.assert_array_equal(part, out[3:7])
+
+
+@pytest.mark.parametrize("model,L", [("bert", 8), ("bert", 16), ("sas", 8), ("sas", 16)])
+def test_eval_batch_vs_reference_dataset(model, L):
+    """oracle.batches.eval_batch == BertEvalDataset / SASEvalDataset.__getitem__ of the reference."""
+    from oracle import batches as obt
+    z = load("eval_batches")
+    tr, va = _split(z, "train"), _split(z, "val")
+    V = int(z["num_items"])
+    users = list(range(len(tr)))
+    s, c, l = obt.eval_batch(tr, [v[0] for v in va], z["neg_random"], users, L, V + 1 if model == "bert" else -1)
+    np.testing.assert_array_equal(s, z["%s_L%d.seq" % (model, L)])
+    np.testing.assert_array_equal(c, z["%s_L%d.cand" % (model, L)])
+    np.testing.assert_array_equal(l, z["%s_L%d.labels" % (model, L)])
+
+
+def test_negative_samples_unfillable_row_ends_in_minus_one():
+    from oracle import batches as obt
+    out = obt.negative_samples([[1, 2, 3, 4], [2]], 5, 2, 9, 1 << 41)
+    assert out[0].tolist()[0] == 5 and out[0].tolist()[1] == -1 and (out[1] > 0).all()
