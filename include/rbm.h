@@ -80,6 +80,11 @@ size_t rbm_layernorm_ws_bytes(int64_t rows, int d);
 int rbm_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* stats, float* dx,
                       float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour, void* ws,
                       size_t ws_bytes, rbm_stream_t stream);
+/* same, plus dx += dres when dres != NULL: the gradient that reaches x through the residual branch of
+ * x + sublayer(LN(x)) (NN/models/bert_modules/utils/sublayer.py:16-18), folded into the one pass that writes dx */
+int rbm_layernorm_bwd_residual(const float* x, const float* gamma, const float* dy, const float* dres, const float* stats,
+                               float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour,
+                               void* ws, size_t ws_bytes, rbm_stream_t stream);
 
 /* ---- Linear with fused epilogue --------------------------------------------------------------------
  * pre = x[M,K] . w[N,K]^T + bias        (optionally stored to `pre` when act needs it in backward)

@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 template <int NV, int GW>
 __global__ void __launch_bounds__(32 * LN_BWD_WARPS) layernorm_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy,
-    const float* __restrict__ stats, float* __restrict__ dx, float* __restrict__ partial, int64_t rows, int d,
-    int64_t rows_per_block, float eps, int flavour) {
+    const float* __restrict__ dres, const float* __restrict__ stats, float* __restrict__ dx, float* __restrict__ partial,
+    int64_t rows, int d, int64_t rows_per_block, float eps, int flavour) {
   extern __shared__ float sm[];  // [NG][2][d]
   constexpr int NG = 32 * LN_BWD_WARPS / GW;  // row groups per block
   int lane = threadIdx.x % GW, warp = threadIdx.x / GW;
@@ -135,6 +135,10 @@ __global__ void __launch_bounds__(32 * LN_BWD_WARPS) layernorm_bwd_kernel(
       if (c4 < d4 && live) {
         float4 o = make_float4(rstd * (gy[t].x - mg) - xv[t].x * k, rstd * (gy[t].y - mg) - xv[t].y * k,
                                rstd * (gy[t].z - mg) - xv[t].z * k, rstd * (gy[t].w - mg) - xv[t].w * k);
+        if (dres != nullptr) {  // gradient of the residual branch that shares this input (x -> LN and x -> + ...)
+          const float4 r = ld4(dres + row * d + c4 * 4);
+          o.x += r.x; o.y += r.y; o.z += r.z; o.w += r.w;
+        }
         st4(dx + row * d + c4 * 4, o);
       }
     }
@@ -207,10 +211,21 @@ extern "C" int rbm_layernorm_fwd(const float* x, const float* gamma, const float
   return 0;
 }
 
+extern "C" int rbm_layernorm_bwd_residual(const float* x, const float* gamma, const float* dy, const float* dres, const float* stats,
+                                          float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour,
+                                          void* ws, size_t ws_bytes, rbm_stream_t stream);
+
 extern "C" int rbm_layernorm_bwd(const float* x, const float* gamma, const float* dy, const float* stats, float* dx,
                                  float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour, void* ws,
                                  size_t ws_bytes, rbm_stream_t stream) {
+  return rbm_layernorm_bwd_residual(x, gamma, dy, nullptr, stats, dx, dgamma, dbeta, rows, d, eps, flavour, ws, ws_bytes, stream);
+}
+
+extern "C" int rbm_layernorm_bwd_residual(const float* x, const float* gamma, const float* dy, const float* dres, const float* stats,
+                                          float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour,
+                                          void* ws, size_t ws_bytes, rbm_stream_t stream) {
   RBM_REQUIRE(x && gamma && dy && stats && dx && dgamma && dbeta && ws, "rbm_layernorm_bwd: null pointer");
+  RBM_REQUIRE(!dres || rbm_aligned16(dres), "rbm_layernorm_bwd: dres must be 16B aligned");
   RBM_REQUIRE(d >= 4 && d % 4 == 0 && d <= LN_MAXD, "rbm_layernorm_bwd: unsupported d=%d", d);
   RBM_REQUIRE(rows > 0, "rbm_layernorm_bwd: rows must be > 0");
   RBM_REQUIRE(ws_bytes >= rbm_layernorm_ws_bytes(rows, d), "rbm_layernorm_bwd: workspace too small");
@@ -224,8 +239,8 @@ extern "C" int rbm_layernorm_bwd(const float* x, const float* gamma, const float
     size_t smem = (size_t)(32 * LN_BWD_WARPS / GW) * 2 * d * sizeof(float);                                         \
     if (smem > 48 * 1024)                                                                                           \
       cudaFuncSetAttribute(layernorm_bwd_kernel<NV, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    layernorm_bwd_kernel<NV, GW><<<nblk, 32 * LN_BWD_WARPS, smem, st>>>(x, gamma, dy, stats, dx, (float*)ws, rows, d, \
-                                                                        rpb, eps, flavour);                         \
+    layernorm_bwd_kernel<NV, GW><<<nblk, 32 * LN_BWD_WARPS, smem, st>>>(x, gamma, dy, dres, stats, dx, (float*)ws, rows, \
+                                                                        d, rpb, eps, flavour);                      \
   } while (0)
   if (d4 <= 8) LN_BWD(1, 8);
   else if (d4 <= 16) LN_BWD(1, 16);

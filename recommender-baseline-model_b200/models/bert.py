@@ -134,14 +134,14 @@ class BERTModel(BaseModel):
         for b, blk in enumerate(bert.transformer_blocks):
             s = base + 1 + 5 * b
             att, ff = blk.attention, blk.feed_forward
-            n1 = ops.layernorm(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            n1, x = ops.layernorm_residual(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
             w_qkv = torch.cat([l.weight for l in att.linear_layers], 0)
             b_qkv = torch.cat([l.bias for l in att.linear_layers], 0)
             qkv = ops.linear(n1, w_qkv, b_qkv)
             ctx = ops.attention(qkv, None, tok, Bsz, Ln, h, 0, d, 2 * d, L.MASK_KEYPAD, scale, p_a, seed, s)
             x = ops.linear(ctx.view(Bsz, Ln, d), att.output_linear.weight, att.output_linear.bias, residual=x, pA=p_h,
                            siteA=s + 1, seed=seed)
-            n2 = ops.layernorm(x, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            n2, x = ops.layernorm_residual(x, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
             u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH, pA=p_h, siteA=s + 2, seed=seed)
             x = ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=x, pA=p_h, siteA=s + 3, pB=p_h, siteB=s + 4, seed=seed)
         return x

@@ -120,6 +120,54 @@ def layernorm(x, gamma, beta, eps, flavour):
     return LayerNormFn.apply(x, gamma, beta, eps, flavour)
 
 
+class LayerNormResidualFn(torch.autograd.Function):
+    """(LN(x), x) for the pre-norm sublayer x + f(LN(x)) (NN/models/bert_modules/utils/sublayer.py:16-18): the second output
+    is x itself, to be used as the residual operand, so that in backward the gradient arriving through the residual branch
+    is added inside the LayerNorm-backward pass that writes dx (one launch less and one read/write of [B*L, d] less than
+    autograd's separate accumulation)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, flavour):
+        lib = L.load()
+        L.require_cuda(x, gamma, beta)
+        x2 = _rows2d(x).contiguous()
+        rows, d = x2.shape
+        y = torch.empty_like(x2)
+        stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+        check(lib.rbm_layernorm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(y), ptr(stats), rows, d, float(eps), int(flavour),
+                                    stream()), "layernorm_fwd")
+        count_launches()
+        ctx.save_for_backward(x2, gamma, stats)
+        ctx.meta = (float(eps), int(flavour), x.shape)
+        return y.view(x.shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dres):
+        lib = L.load()
+        x2, gamma, stats = ctx.saved_tensors
+        eps, flavour, shape = ctx.meta
+        rows, d = x2.shape
+        if dy is None:
+            dy = torch.zeros(shape, device=x2.device, dtype=x2.dtype)
+        dy2 = dy.reshape(rows, d).contiguous()
+        dres2 = None if dres is None else dres.reshape(rows, d).contiguous()
+        dx = torch.empty_like(x2)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        nb = lib.rbm_layernorm_ws_bytes(rows, d)
+        ws = _ws("ln", nb, x2.device)
+        check(lib.rbm_layernorm_bwd_residual(ptr(x2), ptr(gamma), ptr(dy2), ptr(dres2) if dres2 is not None else None, ptr(stats),
+                                             ptr(dx), ptr(dgamma), ptr(dbeta), rows, d, eps, flavour, ptr(ws), nb, stream()),
+              "layernorm_bwd_residual")
+        count_launches(2)
+        return dx.view(shape), dgamma, dbeta, None, None
+
+
+def layernorm_residual(x, gamma, beta, eps, flavour):
+    """-> (LN(x), x): use the second value as the residual operand of the sublayer (see LayerNormResidualFn)."""
+    return LayerNormResidualFn.apply(x, gamma, beta, eps, flavour)
+
+
 # ------------------------------------------------------------------------------------------------ linear
 class LinearFn(torch.autograd.Function):
     """y = rowkeep * dropB(residual + dropA(act(x.w^T + b)))   (K6, K9-K12)."""

@@ -126,3 +126,114 @@ def test_two_rank_gloo():
     for p in procs:
         p.join(timeout=30)
     assert all(r[1] == "ok" for r in res), res
+
+
+# ------------------------------------------------------------------------------------ sharded checkpoints
+class _Toy(torch.nn.Module):
+    """Parameter names of the reference's SASRec tree, small: a row-sharded item table and replicated dense tensors."""
+
+    def __init__(self, rows, d, V1):
+        super().__init__()
+        self.sas = torch.nn.Module()
+        self.sas.item_emb = torch.nn.Embedding(rows, d)
+        self.sas.pos_emb = torch.nn.Embedding(5, d)
+        self.sas.last_layernorm = torch.nn.LayerNorm(d)
+
+
+def _adam_steps(model, opt, seed, n=3, rows=None):
+    g = torch.Generator().manual_seed(seed)
+    for _ in range(n):
+        for name, p in model.named_parameters():
+            full = torch.randn(*((rows[name],) + tuple(p.shape[1:]) if rows and name in rows else p.shape), generator=g)
+            p.grad = full if not (rows and name in rows) else full[rows["_begin"]:rows["_end"]].clone()
+        opt.step()
+
+
+def _ckpt_worker(rank, world, port, q, tmpdir):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from rbm_b200 import checkpoint as ck
+        from rbm_b200.dist import shard_range
+        V1, d = 11, 4  # 11 rows over 2 ranks: blocks of 6 and 5
+        key = "sas.item_emb.weight"
+        assert key in ck.ROW_SHARDED["sas"]
+        torch.manual_seed(0)
+        full = _Toy(V1, d, V1)
+        opt_full = torch.optim.Adam(full.parameters(), lr=1e-2)
+        _adam_steps(full, opt_full, seed=1)
+        ref_file = os.path.join(tmpdir, "reference_format.pth")
+        if rank == 0:  # what the reference's loggers write (NN/loggers.py:8-9, NN/trainers/base.py:255-259)
+            torch.save({"model_state_dict": full.state_dict(), "optimizer_state_dict": opt_full.state_dict(), "epoch": 3}, ref_file)
+        dist.barrier()
+        b, e = shard_range(V1, rank, world)
+        # ---- scatter on load: a reference-format file into a model that holds its row block only
+        torch.manual_seed(100 + rank)
+        mine = _Toy(e - b, d, V1)
+        opt = torch.optim.Adam(mine.parameters(), lr=1e-2)
+        epoch = ck.load_checkpoint(ref_file, mine, opt, sharded_keys=[key])
+        assert epoch == 3
+        assert torch.equal(mine.sas.item_emb.weight, full.sas.item_emb.weight[b:e])
+        assert torch.equal(mine.sas.pos_emb.weight, full.sas.pos_emb.weight)
+        st, stf = opt.state[mine.sas.item_emb.weight], opt_full.state[full.sas.item_emb.weight]
+        assert torch.equal(st["exp_avg"], stf["exp_avg"][b:e]) and torch.equal(st["exp_avg_sq"], stf["exp_avg_sq"][b:e])
+        assert float(st["step"]) == float(stf["step"]) == 3.0
+        # ---- training continues identically on the shard (Adam is element-wise) ...
+        _adam_steps(full, opt_full, seed=2, n=2)
+        _adam_steps(mine, opt, seed=2, n=2, rows={key: V1, "_begin": b, "_end": e})
+        assert torch.equal(mine.sas.item_emb.weight, full.sas.item_emb.weight[b:e])
+        # ---- ... and gather on save writes ONE file with the reference's full shapes
+        out_file = os.path.join(tmpdir, "gathered.pth")
+        ck.save_checkpoint(out_file, mine, opt, epoch=5, sharded_keys=[key], total_rows={key: V1})
+        got = torch.load(out_file, map_location="cpu", weights_only=False)
+        assert set(got) == {"model_state_dict", "optimizer_state_dict", "epoch"} and got["epoch"] == 5
+        assert list(got["model_state_dict"]) == list(full.state_dict())
+        for k, v in full.state_dict().items():
+            assert torch.equal(got["model_state_dict"][k], v), k
+        fo = opt_full.state_dict()
+        assert got["optimizer_state_dict"]["param_groups"] == fo["param_groups"]
+        for idx, stt in fo["state"].items():
+            for f, v in stt.items():
+                assert torch.equal(torch.as_tensor(got["optimizer_state_dict"]["state"][idx][f]), torch.as_tensor(v)), (idx, f)
+        fresh = _Toy(V1, d, V1)
+        fresh.load_state_dict(got["model_state_dict"])  # the reference's resume path (NN/trainers/base.py:29)
+        fresh_opt = torch.optim.Adam(fresh.parameters(), lr=1e-2)
+        fresh_opt.load_state_dict(got["optimizer_state_dict"])  # the line the reference leaves commented out (:30)
+        q.put((rank, "ok"))
+    except Exception:  # noqa
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(180)
+def test_sharded_checkpoint_roundtrip_gloo(tmp_path):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_ckpt_worker, args=(r, 2, port, q, str(tmp_path))) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    assert all(r[1] == "ok" for r in res), res
+
+
+def test_checkpoint_single_process(tmp_path):
+    """world == 1: save_checkpoint / load_checkpoint are the plain reference-format round trip."""
+    from rbm_b200 import checkpoint as ck
+    torch.manual_seed(0)
+    m = _Toy(7, 4, 7)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2)
+    _adam_steps(m, opt, seed=4)
+    f = str(tmp_path / "one.pth")
+    ck.save_checkpoint(f, m, opt, epoch=2)
+    m2 = _Toy(7, 4, 7)
+    opt2 = torch.optim.Adam(m2.parameters(), lr=1e-2)
+    assert ck.load_checkpoint(f, m2, opt2) == 2
+    for (k, a), (_, b) in zip(m.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(a, b), k
+    assert torch.equal(opt2.state[m2.sas.item_emb.weight]["exp_avg_sq"], opt.state[m.sas.item_emb.weight]["exp_avg_sq"])
