@@ -212,9 +212,20 @@ def extra_benchmarks(dev):
     model.train()
     for i in range(3):
         trainer.train_step(batches[i % 2])
-    ms = ev_time(lambda i: trainer.train_step(batches[i % 2]), 10)
-    out["sasrec_train"] = {"config": "SASRec nb=2 d=128 h=2 L=50 V=12101 B=4096 dropout 0.2 (BASELINE configs[2] shape)",
-                           "seq_per_s": B / (ms * 1e-3), "ms_per_step": ms}
+    ms_eager = ev_time(lambda i: trainer.train_step(batches[i % 2]), 10)
+    ms = ms_eager
+    try:
+        trainer.capture_train_step(batches[0])
+        for i in range(3):
+            trainer.train_step(batches[i % 2])
+        ms = ev_time(lambda i: trainer.train_step(batches[i % 2]), 20)
+        trainer.release_train_graph()
+    except Exception as ex:
+        out["sasrec_train_graph_error"] = repr(ex)
+    out["sasrec_train"] = {"config": "SASRec nb=2 d=128 h=2 L=50 V=12101 B=4096 dropout 0.2 (BASELINE configs[2] shape), step replayed from one CUDA graph",
+                           "seq_per_s": B / (ms * 1e-3), "ms_per_step": ms, "eager_ms_per_step": ms_eager}
+    del trainer, model
+    torch.cuda.empty_cache()
     # ---- full-catalogue top-10 evaluation (SASRec d=64 L=50 nb=2, reference defaults)
     for tag, V in (("eval_ml1m", 3416), ("eval_10M_items", 10_000_000)):
         U, Ln, d = 16384, 50, 64

@@ -161,22 +161,22 @@ __global__ void __launch_bounds__(32 * LN_BWD_WARPS) layernorm_bwd_kernel(
   }
 }
 
-// out[c] = sum_b partial[b][c] in a fixed order: eight interleaved groups (b = g, g+8, ... ascending), then the groups
-// ascending.  One block = 32 columns x 8 groups (the per-block partials are few hundred rows: one thread per column
-// walking all of them was a 36 us latency chain).
-__global__ void __launch_bounds__(256) colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
-                                                              float* __restrict__ out1, int nblk, int d) {
-  __shared__ float acc[8][32];
+// out[c] = sum_b partial[b][c] in a fixed order: 32 interleaved groups (b = g, g+32, ... ascending), then the groups
+// ascending.  One block = 32 columns x 32 groups (the per-block partials are a few hundred rows: fewer, longer per-thread
+// chains were latency-bound -- 18 us for 592 x 128 floats with 8 groups).
+__global__ void __launch_bounds__(1024) colsum_partials_kernel(const float* __restrict__ partial, float* __restrict__ out0,
+                                                               float* __restrict__ out1, int nblk, int d) {
+  __shared__ float acc[32][33];
   const int o = threadIdx.x & 31, g = threadIdx.x >> 5;
   const int c = blockIdx.x * 32 + o;
   float s = 0.f;
   if (c < 2 * d)
-    for (int b = g; b < nblk; b += 8) s += partial[(int64_t)b * 2 * d + c];
+    for (int b = g; b < nblk; b += 32) s += partial[(int64_t)b * 2 * d + c];
   acc[g][o] = s;
   __syncthreads();
   if (g == 0 && c < 2 * d) {
 #pragma unroll
-    for (int k = 1; k < 8; ++k) s += acc[k][o];
+    for (int k = 1; k < 32; ++k) s += acc[k][o];
     if (c < d) out0[c] = s;
     else out1[c - d] = s;
   }
@@ -250,7 +250,7 @@ extern "C" int rbm_layernorm_bwd_residual(const float* x, const float* gamma, co
   else LN_BWD(8, 32);
 #undef LN_BWD
   RBM_LAUNCH_CHECK("rbm_layernorm_bwd");
-  colsum_partials_kernel<<<(unsigned)rbm_cdiv(2 * d, 32), 256, 0, (cudaStream_t)stream>>>((const float*)ws, dgamma, dbeta, nblk, d);
+  colsum_partials_kernel<<<(unsigned)rbm_cdiv(2 * d, 32), 1024, 0, (cudaStream_t)stream>>>((const float*)ws, dgamma, dbeta, nblk, d);
   RBM_LAUNCH_CHECK("rbm_layernorm_bwd(colsum)");
   return 0;
 }

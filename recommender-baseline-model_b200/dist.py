@@ -67,9 +67,21 @@ class GradSync:
         # host->device copy every step would block the host until the stream has drained)
         key = tuple(r[0] for r in rows)
         if getattr(self, "_tab_key", None) != key:
-            self._tab = torch.tensor(rows, dtype=torch.int64).to(self.bucket.device)
+            if torch.cuda.is_current_stream_capturing():  # see FusedAdam._tables: staged through pre-allocated pinned memory
+                pinned, devbuf = self._capture_bufs
+                pinned.copy_(torch.tensor(rows, dtype=torch.int64))
+                devbuf.copy_(pinned, non_blocking=True)
+                self._tab = devbuf
+            else:
+                self._tab = torch.tensor(rows, dtype=torch.int64).to(self.bucket.device)
             self._tab_key = key
         return self._tab
+
+    def prepare_capture(self):
+        """Buffers for the gradient-address table, allocated before a CUDA-graph capture."""
+        n = len(self.params)
+        self._capture_bufs = (torch.empty(n, 3, dtype=torch.int64).pin_memory(), torch.empty(n, 3, dtype=torch.int64, device=self.bucket.device))
+        self._tab_key = None
 
     def pack(self):
         """Gradients -> flat bucket, scaled by 1/world (one launch)."""

@@ -80,8 +80,27 @@ class FusedAdam(torch.optim.Optimizer):
         cache = self.__dict__.setdefault("_desc_cache", {})
         dkey = tuple(table)  # rbm_adam_tensor[] : 5 x 8-byte fields
         if gi not in cache or cache[gi][0] != dkey:
-            cache[gi] = (dkey, torch.tensor(table, dtype=torch.int64).to(dev))
+            if torch.cuda.is_current_stream_capturing():
+                # gradients were allocated inside the capture (their addresses are final): stage the table through the pinned
+                # buffer of prepare_capture() -- a host->device copy node that every replay repeats (1.4 KB)
+                pinned, devbuf = self._capture_bufs[gi]
+                n = len(table)
+                pinned[:n] = torch.tensor(table, dtype=torch.int64)
+                devbuf[:n].copy_(pinned[:n], non_blocking=True)
+                cache[gi] = (dkey, devbuf[:n])
+            else:
+                cache[gi] = (dkey, torch.tensor(table, dtype=torch.int64).to(dev))
         return cache[gi][1], cmap, steps.pop()
+
+    def prepare_capture(self):
+        """Pinned host + device buffers for the descriptor tables, allocated BEFORE a CUDA-graph capture (no allocation of
+        pinned memory while capturing); see ``_tables``."""
+        self._capture_bufs = {}
+        for gi, group in enumerate(self.param_groups):
+            n = max(1, len(group["params"]))
+            dev = group["params"][0].device
+            self._capture_bufs[gi] = (torch.empty(n, 5, dtype=torch.int64).pin_memory(), torch.empty(n, 5, dtype=torch.int64, device=dev))
+        self.__dict__.setdefault("_desc_cache", {}).clear()
 
     @torch.no_grad()
     def stage_tables(self):

@@ -127,14 +127,12 @@ class AbstractTrainer(metaclass=ABCMeta):
         # the device-side step counter: 0 now, +1 at the end of every replay
         self._graph_counter = torch.zeros(1, dtype=torch.int64, device=dev)
         L.check(L.load().rbm_set_step_counter(self._graph_counter.data_ptr()), "set_step_counter")
-        # persistent gradient buffers: the graph zeroes and re-accumulates them in place, so every address Adam's descriptor
-        # table (and the gradient-bucket table) holds is known (and uploaded) before capture -- no host->device copy inside the graph
-        for p in self.model.parameters():
-            if p.requires_grad:
-                p.grad = torch.zeros_like(p)
-        self.optimizer.stage_tables()
+        # gradients are (re)allocated INSIDE the capture, as in an eager step (autograd hands each produced gradient over to
+        # .grad: no zero fill and no accumulation add per parameter); their addresses are final once allocated, and the
+        # descriptor tables that hold them reach the device through pre-allocated pinned buffers (a copy node per replay)
+        self.optimizer.prepare_capture()
         if sync is not None:
-            sync._table()
+            sync.prepare_capture()
         # NCCL's watchdog thread polls CUDA events while we capture: only this thread's calls belong to the capture
         mode = {"capture_error_mode": "thread_local"} if sync is not None else {}
         launches0 = L.launch_count
@@ -157,7 +155,7 @@ class AbstractTrainer(metaclass=ABCMeta):
 
     def _capture(self, graph, static, sync, collective, mode):
         with torch.cuda.graph(graph, **mode):
-            self.optimizer.zero_grad(set_to_none=False)
+            self.optimizer.zero_grad(set_to_none=True)
             loss = self.calculate_loss(static)
             loss.backward()
             if sync is not None:
