@@ -48,9 +48,13 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
   float* Vp = Kp + LP8 * LD;
   float* padk = Vp + LP8 * LD;  // [LPC]
   float* chunk_pad = padk + LPC;  // [4]: chunk contains a padded key
-  float* wbase = chunk_pad + 4 + (size_t)warp * (16 * QLD + 16 * PB_LD);
-  float* Qs = wbase;             // [16][QLD] scaled q tile
-  float* Pb = wbase + 16 * QLD;  // [16][PB_LD]
+  // L <= CH: one key chunk per query tile, the q tile is dead once the scores exist -> the probability tile reuses its
+  // shared memory (per-warp footprint halves: 3 -> 4 resident CTAs at L=50, d_k=64)
+  const bool single = L <= CH;
+  const int QPW = single ? 16 * (QLD > PB_LD ? QLD : PB_LD) : 16 * QLD;
+  float* wbase = chunk_pad + 4 + (size_t)warp * (single ? QPW : 16 * QLD + 16 * PB_LD);
+  float* Qs = wbase;                          // [16][QLD] scaled q tile
+  float* Pb = single ? wbase : wbase + 16 * QLD;  // [16][PB_LD]
 
   load_panel(Kp, a.k, a.ldk, row0, col0, L, LP8, dk, LD, 1.f);
   load_panel(Vp, a.v, a.ldv, row0, col0, L, LP8, dk, LD, 1.f);
@@ -136,6 +140,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
           }
         }
       }
+      if (single) __syncwarp();  // every lane is done reading the q tile that Pb overlays
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
@@ -181,10 +186,12 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
   float* Vp = Kp + LP8 * LD;
   float* padk = Vp + LP8 * LD;
   float* chunk_pad = padk + LPC;
-  float* wbase = chunk_pad + 4 + (size_t)warp * (32 * QLD + 16 * PB_LD);
-  float* Qs = wbase;              // [16][QLD] scaled q
-  float* dOs = wbase + 16 * QLD;  // [16][QLD]
-  float* Pb = dOs + 16 * QLD;     // [16][PB_LD] dS chunk
+  const bool single = L <= CH;  // one key chunk: the dS tile reuses the q tile's shared memory (see attn_fwd_kernel)
+  const int QPW = single ? 16 * (QLD > PB_LD ? QLD : PB_LD) : 16 * QLD;
+  float* wbase = chunk_pad + 4 + (size_t)warp * (single ? QPW + 16 * QLD : 32 * QLD + 16 * PB_LD);
+  float* Qs = wbase;                            // [16][QLD] scaled q
+  float* dOs = wbase + QPW;                     // [16][QLD]
+  float* Pb = single ? wbase : dOs + 16 * QLD;  // [16][PB_LD] dS chunk
 
   load_panel(Kp, a.k, a.ldk, row0, col0, L, LP8, dk, LD, 1.f);
   load_panel(Vp, a.v, a.ldv, row0, col0, L, LP8, dk, LD, 1.f);
@@ -202,16 +209,26 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
     stage_tile(Qs, QLD, a.q, a.ldq, row0, col0, i0, L, dk, a.scale * RBM_LOG2E, lane);
     stage_tile(dOs, QLD, a.dout, a.lddo, row0, col0, i0, L, dk, 1.f, lane);
     float delta[2] = {0.f, 0.f}, mx[2] = {0.f, 0.f}, inv[2] = {0.f, 0.f};
-    for (int r = 0; r < 16; ++r) {
-      int i = i0 + r;
-      float part = 0.f;
-      if (i < L)
-        for (int c = lane; c < dk; c += 32)
-          part = fmaf(a.dout[(row0 + i) * a.lddo + col0 + c], a.o[(row0 + i) * a.ldo + col0 + c], part);
-      part = warp_sum(part);
-      if (lane == 0 && i < L) a.delta[(int64_t)blockIdx.x * L + i] = part;
-      if (r == g) delta[0] = part;
-      if (r == g + 8) delta[1] = part;
+    {
+      // delta[i] = <dO[i], O[i]>: all sixteen rows' loads are issued before the first reduction (the row-by-row loop was a
+      // chain of sixteen global-load latencies per tile)
+      float part[16];
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const int i = i0 + r;
+        float acc = 0.f;
+        if (i < L)
+          for (int c = lane; c < dk; c += 32)
+            acc = fmaf(__ldg(a.dout + (row0 + i) * a.lddo + col0 + c), __ldg(a.o + (row0 + i) * a.ldo + col0 + c), acc);
+        part[r] = acc;
+      }
+#pragma unroll
+      for (int r = 0; r < 16; ++r) {
+        const float tot = warp_sum(part[r]);
+        if (lane == 0 && i0 + r < L) a.delta[(int64_t)blockIdx.x * L + i0 + r] = tot;
+        if (r == g) delta[0] = tot;
+        if (r == g + 8) delta[1] = tot;
+      }
     }
 #pragma unroll
     for (int hrow = 0; hrow < 2; ++hrow) {
@@ -257,6 +274,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
           }
         }
       }
+      if (single) __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         *reinterpret_cast<float2*>(Pb + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
@@ -297,11 +315,13 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
   float* st_m = dOp + LP8 * LD; // [LPC]
   float* st_i = st_m + LPC;
   float* st_d = st_i + LPC;
-  float* wbase = st_d + LPC + (size_t)warp * (32 * QLD + 32 * PB_LD);
-  float* Ks = wbase;             // [16][QLD] key tile
-  float* Vs = Ks + 16 * QLD;     // [16][QLD] value tile
-  float* P1 = Vs + 16 * QLD;     // [16][PB_LD] dS^T chunk
-  float* P2 = P1 + 16 * PB_LD;   // [16][PB_LD] P~^T chunk
+  const bool single = L <= CH;  // one query chunk: dS^T / P~^T reuse the key / value tiles' shared memory (see attn_fwd_kernel)
+  const int QPW = single ? 16 * (QLD > PB_LD ? QLD : PB_LD) : 16 * QLD;
+  float* wbase = st_d + LPC + (size_t)warp * (single ? 2 * QPW : 32 * QLD + 32 * PB_LD);
+  float* Ks = wbase;                                // [16][QLD] key tile
+  float* Vs = Ks + QPW;                             // [16][QLD] value tile
+  float* P1 = single ? Ks : Vs + 16 * QLD;          // [16][PB_LD] dS^T chunk
+  float* P2 = single ? Vs : P1 + 16 * PB_LD;        // [16][PB_LD] P~^T chunk
 
   load_panel(Qp, a.q, a.ldq, row0, col0, L, LP8, dk, LD, a.scale * RBM_LOG2E);
   load_panel(dOp, a.dout, a.lddo, row0, col0, L, LP8, dk, LD, 1.f);
@@ -365,6 +385,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a
           }
         }
       }
+      if (single) __syncwarp();
 #pragma unroll
       for (int nt = 0; nt < 8; ++nt) {
         *reinterpret_cast<float2*>(P1 + g * PB_LD + nt * 8 + 2 * t) = make_float2(s[nt][0], s[nt][1]);
@@ -399,9 +420,20 @@ int pick_warps(int L) {
   return (ntile + rounds - 1) / rounds;
 }
 size_t panel_floats(int L, int dk) { return (size_t)2 * ((L + 7) & ~7) * ((dk + 31) & ~31); }
-size_t smem_fwd(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * (16 * (dk + 4) + 16 * PB_LD)); }
-size_t smem_dq(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * (32 * (dk + 4) + 16 * PB_LD)); }
-size_t smem_dkv(int L, int dk, int w) { return sizeof(float) * (panel_floats(L, dk) + 3 * ((L + CH - 1) / CH * CH) + (size_t)w * (32 * (dk + 4) + 32 * PB_LD)); }
+// per-warp staging: with one chunk (L <= CH) the probability tiles overlay the q / k / v tiles (see the kernels)
+size_t qpw(int L, int dk) { return L <= CH ? (size_t)16 * ((dk + 4) > PB_LD ? (dk + 4) : PB_LD) : (size_t)16 * (dk + 4); }
+size_t smem_fwd(int L, int dk, int w) {
+  const size_t per = L <= CH ? qpw(L, dk) : (size_t)16 * (dk + 4) + 16 * PB_LD;
+  return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * per);
+}
+size_t smem_dq(int L, int dk, int w) {
+  const size_t per = L <= CH ? qpw(L, dk) + (size_t)16 * (dk + 4) : (size_t)32 * (dk + 4) + 16 * PB_LD;
+  return sizeof(float) * (panel_floats(L, dk) + (L + CH - 1) / CH * CH + 4 + (size_t)w * per);
+}
+size_t smem_dkv(int L, int dk, int w) {
+  const size_t per = L <= CH ? 2 * qpw(L, dk) : (size_t)32 * (dk + 4) + 32 * PB_LD;
+  return sizeof(float) * (panel_floats(L, dk) + 3 * ((L + CH - 1) / CH * CH) + (size_t)w * per);
+}
 
 template <typename Kern>
 int launch(Kern kern, const AttnArgs& a, int B, int warps, size_t (*smem_fn)(int, int, int), cudaStream_t st, const char* name) {

@@ -38,6 +38,7 @@ struct TcParams {
   const int64_t* row_tok;
   int64_t M;
   int N, K, BN, nstage, act;
+  int ngroups;  // persistent kernel: column groups of BN = N / ngroups output columns
   uint32_t thrA, thrB;
   float invA, invB;
   uint64_t siteA, siteB, seed;
@@ -195,6 +196,10 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.K / BKE, BN = p.BN, ns = p.nstage;
   const int tiles = (int)((p.M + BM - 1) / BM);
+  // column groups: CTA c serves the output columns [n0, n0 + BN) of the row tiles cta, cta + stride, ...; the groups walk
+  // the same row tiles side by side, so every A tile after its first reader comes out of L2
+  const int cta = (int)blockIdx.x / p.ngroups, stride = (int)gridDim.x / p.ngroups;
+  const int n0 = ((int)blockIdx.x % p.ngroups) * BN;
   const uint32_t a_bytes = BM * BKE * 4, bk_bytes = (uint32_t)BN * BKE * 4, b_bytes = bk_bytes * KB;
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* gen_base = smem_raw + (smem_base - smem_u32(smem_raw));  // generic pointer to the aligned base
@@ -226,9 +231,9 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
       asm volatile("prefetch.tensormap [%0];" ::"l"(&mapB) : "memory");
       const uint32_t bb = smem_u32(&bfull_bar);
       mbar_expect_tx(bb, b_bytes);
-      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_base + kb * bk_bytes, &mapB, bb, kb * BKE, 0);
+      for (int kb = 0; kb < KB; ++kb) tma_load_2d(smem_base + kb * bk_bytes, &mapB, bb, kb * BKE, n0);
       int g = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+      for (int tile = cta; tile < tiles; tile += stride)
         for (int kb = 0; kb < KB; ++kb, ++g) {
           const int s = g % ns;
           if (g >= ns) mbar_wait(smem_u32(&empty_bar[s]), ((g / ns) - 1) & 1);
@@ -243,7 +248,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
       mbar_wait(smem_u32(&bsplit_bar), 0);
       tc_fence_after();
       int g = 0, it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      for (int tile = cta; tile < tiles; tile += stride, ++it) {
         const int buf = it & 1;
         if (it >= 2) {
           mbar_wait(smem_u32(&tempty_bar[buf]), ((it >> 1) - 1) & 1);
@@ -279,7 +284,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
     __syncwarp();
     if (lane == 0) mbar_arrive(smem_u32(&bsplit_bar));
     int g = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x)
+    for (int tile = cta; tile < tiles; tile += stride)
       for (int kb = 0; kb < KB; ++kb, ++g) {
         const int s = g % ns;
         mbar_wait(smem_u32(&full_bar[s]), (g / ns) & 1);
@@ -300,7 +305,7 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
     const int last_c0 = ((BN / 32 - 1 - half) / 2) * 64 + half * 32;  // this warp's last chunk
     const uint64_t siteA_e = rbm_site(p.siteA), siteB_e = rbm_site(p.siteB);
     int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+    for (int tile = cta; tile < tiles; tile += stride, ++it) {
       const int buf = it & 1;
       mbar_wait(smem_u32(&tfull_bar[buf]), (it >> 1) & 1);
       tc_fence_after();
@@ -317,8 +322,8 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
           __syncwarp();
           if (lane == 0) mbar_arrive(smem_u32(&tempty_bar[buf]));
         }
-        const int col = c0 + cg;
-        const bool col_ok = col < p.N;
+        const int col = n0 + c0 + cg;
+        const bool col_ok = c0 + cg < BN && col < p.N;  // (a 32-column chunk may reach past a BN = 16 / 48 / ... block)
         // all residual loads of the chunk are issued before anything depends on them
         float4 res[8];
 #pragma unroll
@@ -631,19 +636,35 @@ static bool v2_fits(int N, int K, int* nstage_out) {
   return ns >= 2;
 }
 
+// Column groups of the persistent kernel: the fewest equal blocks of output columns whose weight block (raw + TF32
+// residual) stays resident in shared memory next to at least two A stages.  0 = no such split.
+static int pick_groups(int N, int K, int* nstage_out) {
+  for (int ng = 1; ng <= 32; ++ng) {
+    if (N % ng != 0 || (N / ng) % 16 != 0) continue;
+    if (v2_fits(N / ng, K, nstage_out)) return ng;
+  }
+  return 0;
+}
+
 bool rbm_tc_linear_supported(int64_t M, int N, int K, int64_t lda, const void* a, const void* b) {
   if (M < 1 || N % 16 != 0 || K % BKE != 0 || K < BKE || N < 16) return false;
   if (lda % 4 != 0 || ((uintptr_t)a & 15) || ((uintptr_t)b & 15)) return false;
   if (get_encode() == nullptr) return false;
   int ns;
-  if (tc_mode() == 0) return v2_fits(N, K, &ns);
+  if (tc_mode() == 0) return pick_groups(N, K, &ns) != 0;
   return pick_bn(N) != 0;
 }
 
 int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M, int N, int K, const RbmTcEpilogue& ep,
                          cudaStream_t st) {
   const bool v2 = tc_mode() == 0;
-  const int BN = v2 ? N : pick_bn(N);
+  int ns_v2 = 2;
+  const int NG = v2 ? pick_groups(N, K, &ns_v2) : 1;
+  const int BN = v2 ? N / (NG > 0 ? NG : 1) : pick_bn(N);
+  if (BN <= 0 || NG <= 0) {
+    rbm_set_error("rbm_linear(tcgen05): no resident-weight split for N=%d K=%d", N, K);
+    return -1;
+  }
   CUtensorMap mapA, mapB;
   if (!encode_map(&mapA, a, M, K, lda, BM) || !encode_map(&mapB, b, N, K, K, BN)) {
     rbm_set_error("rbm_linear(tcgen05): cuTensorMapEncodeTiled failed (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
@@ -651,7 +672,7 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
   }
   TcParams p{};
   p.y = ep.y; p.ldy = ep.ldy; p.pre = ep.pre; p.bias = ep.bias; p.residual = ep.residual; p.ldres = ep.ldres; p.row_tok = ep.row_tok;
-  p.M = M; p.N = N; p.K = K; p.BN = BN; p.act = ep.act;
+  p.M = M; p.N = N; p.K = K; p.BN = BN; p.ngroups = NG; p.act = ep.act;
   p.thrA = ep.thrA; p.thrB = ep.thrB; p.invA = ep.invA; p.invB = ep.invB; p.siteA = ep.siteA; p.siteB = ep.siteB; p.seed = ep.seed;
   static bool attr_set = false;
   if (!attr_set) {
@@ -670,15 +691,16 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
     attr_set = true;
   }
   if (v2) {
-    int ns = 2;
-    v2_fits(N, K, &ns);
+    const int ns = ns_v2;
     p.nstage = ns;
     uint32_t cols = 32;
-    while (cols < (uint32_t)(2 * BN)) cols <<= 1;
+    while (cols < (uint32_t)(2 * BN) || cols < (uint32_t)(BN + ((BN + 31) & ~31))) cols <<= 1;  // the epilogue reads whole 32-column chunks
     p.tmem_cols = cols;
-    size_t smem = (size_t)2 * N * K * 4 + (size_t)ns * 2 * BM * BKE * 4 + (size_t)EPI_WARPS * 32 * STG_LD * 4 + 1024;
+    size_t smem = (size_t)2 * BN * K * 4 + (size_t)ns * 2 * BM * BKE * 4 + (size_t)EPI_WARPS * 32 * STG_LD * 4 + 1024;
     int tiles = (int)rbm_cdiv(M, BM);
-    int grid = tiles < RBM_NUM_SMS ? tiles : RBM_NUM_SMS;
+    int per_group = RBM_NUM_SMS / NG;  // CTAs per column group (one CTA per SM in total)
+    if (per_group > tiles) per_group = tiles;
+    int grid = per_group * NG;
     const int act = p.act != 0 ? p.act : (p.pre != nullptr ? 3 : 0);  // 3: no activation, pre-activation still stored
     const bool da = p.thrA != 0, db = p.thrB != 0;
     const int nthr = 128 + 32 * EPI_WARPS;

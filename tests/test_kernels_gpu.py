@@ -118,7 +118,9 @@ def _ref_act(x, act):
     return {L.ACT_NONE: lambda t: t, L.ACT_RELU: torch.relu, L.ACT_GELU_TANH: oc.gelu_tanh}[act](x)
 
 
-@pytest.mark.parametrize("M,N,K", [(10, 16, 16), (300, 192, 64), (257, 64, 256), (1000, 256, 64), (131, 48, 32)])
+@pytest.mark.parametrize("M,N,K", [(10, 16, 16), (300, 192, 64), (257, 64, 256), (1000, 256, 64), (131, 48, 32),
+                                   # weight block does not fit shared memory whole: column groups of the persistent kernel
+                                   (1000, 128, 128), (700, 256, 128), (5000, 256, 128), (300, 1024, 256), (300, 256, 256)])
 @pytest.mark.parametrize("act,res,rowtok,pA,pB", [(L.ACT_NONE, False, False, 0.0, 0.0), (L.ACT_GELU_TANH, False, False, 0.2, 0.0),
                                                   (L.ACT_NONE, True, False, 0.1, 0.3), (L.ACT_RELU, False, False, 0.2, 0.0),
                                                   (L.ACT_NONE, True, True, 0.2, 0.0)])
@@ -147,8 +149,9 @@ def test_linear(M, N, K, act, res, rowtok, pA, pB):
     ref.backward(dy)
     close(y, ref, 1e-4, 1e-4)
     close(xg.grad, xr.grad, 1e-4, 1e-4)
-    close(wg.grad, wr.grad, 1e-4, 1e-3)
-    close(bg.grad, br.grad, 1e-4, 1e-3)
+    acc = 1e-3 * max(1.0, math.sqrt(M / 1000.0))  # sums over M rows: the fp32 reference's own rounding grows with sqrt(M)
+    close(wg.grad, wr.grad, 1e-4, acc)
+    close(bg.grad, br.grad, 1e-4, acc)
     if res:
         close(rg.grad, rr.grad, 1e-5, 1e-5)
 
