@@ -300,8 +300,10 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
 }
 
 // ------------------------------------------------------------------------------- backward pass B: dK and dV
-template <int DT>
-__global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dkv_kernel(AttnArgs a) {
+// MAXW = 4: the variant for CTAs of at most four warps (L <= 64); three resident CTAs are asked for, which holds ptxas to
+// 168 registers (it takes 244 when allowed to, without needing them: 12 bytes of spill) -> 2 -> 3 CTAs per SM
+template <int DT, int MAXW = MAX_WARPS>
+__global__ void __launch_bounds__(32 * MAXW, MAXW <= 4 ? 3 : 1) attn_bwd_dkv_kernel(AttnArgs a) {
   const uint64_t site_e = rbm_site(a.site);
   extern __shared__ __align__(16) float sm[];
   const int L = a.L, dk = a.dk, LP8 = (L + 7) & ~7, LPC = (L + CH - 1) / CH * CH, LD = (dk + 31) & ~31, QLD = dk + 4;
@@ -526,7 +528,12 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   if (rbm_attn_bwd_dkv_tc_supported(L, dk, ldq, ldk, ldv, lddo, lddk, lddv, q, k, v, dout, dk_, dv))
     return rbm_attn_bwd_dkv_tc_launch(q, ldq, k, ldk, v, ldv, tok, dout, lddo, stats, (const float*)ws, dk_, lddk, dv, lddv, B, L, h,
                                       mask_mode, scale, p, seed, site, st);
-  ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
+  if (warps <= 4 && dk <= 64) {  // (the d_k = 128 accumulators do not fit 168 registers: 2 KB of spills)
+    if (dk <= 32) rc = launch(attn_bwd_dkv_kernel<4, 4>, a, B, warps, smem_dkv, st, "rbm_attn_bwd(dkv)");
+    else rc = launch(attn_bwd_dkv_kernel<8, 4>, a, B, warps, smem_dkv, st, "rbm_attn_bwd(dkv)");
+  } else {
+    ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
+  }
   return rc;
 }
 
