@@ -62,6 +62,18 @@ int rbm_embed_fwd(const int64_t* tok, const float* table, const float* pos, floa
 int rbm_embed_bwd(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
                   int zero_pad, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
 
+/* Row-sharded item table (SURVEY 8e "input lookup"): `table_shard` holds rows [v_begin, v_end) of the [vocab, d] table.  Same as
+ * rbm_embed_fwd for tokens inside the shard; tokens of other shards produce exact zeros (their owner produces the value, so a
+ * sum over the shards -- reduce-scatter -- is the unsharded result bit for bit).  `tok` is the rank-ordered concatenation of the
+ * ranks' batches, so the dropout element index is the index in the global batch. */
+int rbm_embed_fwd_shard(const int64_t* tok, const float* table_shard, const float* pos, float* out, int64_t rows, int L,
+                        int d, int64_t vocab, int64_t v_begin, int64_t v_end, float scale, int zero_pad, float p,
+                        uint64_t seed, uint64_t site, rbm_stream_t stream);
+/* rbm_embed_bwd on a rank's slice of the global batch: `row_offset` = index of its first row in the global batch (dropout
+ * element indices continue from there). */
+int rbm_embed_bwd_offset(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
+                         int zero_pad, float p, uint64_t seed, uint64_t site, uint64_t row_offset, rbm_stream_t stream);
+
 /* ---- embedding-gradient scatter-add (autograd of nn.Embedding = embedding_dense_backward; triggered by
  * loss.backward() NN/trainers/base.py:121).  grad[idx[i],:] += alpha * coef[i] * src[i,:], summed over i in
  * ASCENDING i per destination row (stable LSD radix sort of idx, then one sequential fp32 segment sum per

@@ -5,9 +5,9 @@
 
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ table,
                                                         const float* __restrict__ pos, float* __restrict__ out,
-                                                        int64_t total4, int L, int d4, int64_t vocab, float scale,
-                                                        int zero_pad, uint32_t thr, float inv_keep, uint64_t seed,
-                                                        uint64_t site) {
+                                                        int64_t total4, int L, int d4, int64_t vocab, int64_t v_begin,
+                                                        int64_t v_end, float scale, int zero_pad, uint32_t thr,
+                                                        float inv_keep, uint64_t seed, uint64_t site) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   int64_t r = i / d4;
@@ -19,8 +19,10 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restric
   } else if (t < 0 || t >= vocab) {
     float n = __int_as_float(0x7fc00000);  // out-of-range index: poison the row so it cannot go unnoticed
     o = make_float4(n, n, n, n);
+  } else if (t < v_begin || t >= v_end) {
+    o = make_float4(0.f, 0.f, 0.f, 0.f);  // row held by another shard: its owner writes the value, the exchange adds zeros
   } else {
-    float4 e = ld4(table + t * (int64_t)d4 * 4 + c4 * 4);
+    float4 e = ld4(table + (t - v_begin) * (int64_t)d4 * 4 + c4 * 4);
     float4 pe = ld4(pos + (int64_t)(r % L) * d4 * 4 + c4 * 4);
     o = make_float4(e.x * scale + pe.x, e.y * scale + pe.y, e.z * scale + pe.z, e.w * scale + pe.w);
     if (thr) {
@@ -35,7 +37,7 @@ __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t* __restric
 __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restrict__ tok, const float* __restrict__ dout,
                                                         float* __restrict__ g, float* __restrict__ dpos, int B, int L,
                                                         int d4, int zero_pad, uint32_t thr, float inv_keep,
-                                                        uint64_t seed, uint64_t site) {
+                                                        uint64_t seed, uint64_t site, uint64_t elem_offset4) {
   __shared__ float4 red[16][16];
   int l = blockIdx.x;
   int c4 = blockIdx.y * 16 + threadIdx.x;
@@ -48,7 +50,7 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t* __restric
       if (zero_pad && tok[r] == 0) {
         v = make_float4(0.f, 0.f, 0.f, 0.f);
       } else if (thr) {
-        float4 m = rbm_drop4(seed, rbm_site(site), (uint64_t)i, thr, inv_keep);
+        float4 m = rbm_drop4(seed, rbm_site(site), (uint64_t)i + elem_offset4, thr, inv_keep);
         v.x *= m.x; v.y *= m.y; v.z *= m.z; v.w *= m.w;
       }
       st4(g + i * 4, v);
@@ -85,10 +87,22 @@ __global__ void dropout_mask_attn_kernel(uint8_t* out, int64_t rows, int L, uint
   out[e] = rbm_attn_keep(seed, site, (uint64_t)(R / L), (int)(R % L), j, thr16) ? 1 : 0;
 }
 
+extern "C" int rbm_embed_fwd_shard(const int64_t* tok, const float* table_shard, const float* pos, float* out, int64_t rows, int L,
+                                   int d, int64_t vocab, int64_t v_begin, int64_t v_end, float scale, int zero_pad, float p,
+                                   uint64_t seed, uint64_t site, rbm_stream_t stream);
+
 extern "C" int rbm_embed_fwd(const int64_t* tok, const float* table, const float* pos, float* out, int64_t rows, int L,
                              int d, int64_t vocab, float scale, int zero_pad, float p, uint64_t seed, uint64_t site,
                              rbm_stream_t stream) {
+  return rbm_embed_fwd_shard(tok, table, pos, out, rows, L, d, vocab, 0, vocab, scale, zero_pad, p, seed, site, stream);
+}
+
+extern "C" int rbm_embed_fwd_shard(const int64_t* tok, const float* table, const float* pos, float* out, int64_t rows, int L,
+                                   int d, int64_t vocab, int64_t v_begin, int64_t v_end, float scale, int zero_pad, float p,
+                                   uint64_t seed, uint64_t site, rbm_stream_t stream) {
   RBM_REQUIRE(tok && table && pos && out, "rbm_embed_fwd: null pointer");
+  RBM_REQUIRE(v_begin >= 0 && v_begin <= v_end && v_end <= vocab, "rbm_embed_fwd: bad shard range [%lld, %lld) of %lld rows",
+              (long long)v_begin, (long long)v_end, (long long)vocab);
   RBM_REQUIRE(d > 0 && d % 4 == 0, "rbm_embed_fwd: d=%d must be a positive multiple of 4", d);
   RBM_REQUIRE(L > 0 && rows >= 0 && rows % L == 0, "rbm_embed_fwd: rows=%lld not a multiple of L=%d", (long long)rows, L);
   RBM_REQUIRE(p >= 0.f && p < 1.f, "rbm_embed_fwd: dropout p=%f out of [0,1)", p);
@@ -97,13 +111,21 @@ extern "C" int rbm_embed_fwd(const int64_t* tok, const float* table, const float
   int64_t total4 = rows * (d / 4);
   uint32_t thr = rbm_drop_threshold(p);
   embed_fwd_kernel<<<(unsigned)rbm_cdiv(total4, 256), 256, 0, (cudaStream_t)stream>>>(
-      tok, table, pos, out, total4, L, d / 4, vocab, scale, zero_pad, thr, 1.f / (1.f - p), seed, site);
+      tok, table, pos, out, total4, L, d / 4, vocab, v_begin, v_end, scale, zero_pad, thr, 1.f / (1.f - p), seed, site);
   RBM_LAUNCH_CHECK("rbm_embed_fwd");
   return 0;
 }
 
+extern "C" int rbm_embed_bwd_offset(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
+                                    int zero_pad, float p, uint64_t seed, uint64_t site, uint64_t row_offset, rbm_stream_t stream);
+
 extern "C" int rbm_embed_bwd(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
                              int zero_pad, float p, uint64_t seed, uint64_t site, rbm_stream_t stream) {
+  return rbm_embed_bwd_offset(tok, dout, g, dpos, rows, L, d, zero_pad, p, seed, site, 0, stream);
+}
+
+extern "C" int rbm_embed_bwd_offset(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
+                                    int zero_pad, float p, uint64_t seed, uint64_t site, uint64_t row_offset, rbm_stream_t stream) {
   RBM_REQUIRE(tok && dout && g && dpos, "rbm_embed_bwd: null pointer");
   RBM_REQUIRE(d > 0 && d % 4 == 0, "rbm_embed_bwd: d=%d must be a positive multiple of 4", d);
   RBM_REQUIRE(L > 0 && rows > 0 && rows % L == 0, "rbm_embed_bwd: rows=%lld not a positive multiple of L=%d", (long long)rows, L);
@@ -112,7 +134,7 @@ extern "C" int rbm_embed_bwd(const int64_t* tok, const float* dout, float* g, fl
   int d4 = d / 4;
   dim3 grid(L, (unsigned)rbm_cdiv(d4, 16)), block(16, 16);
   embed_bwd_kernel<<<grid, block, 0, (cudaStream_t)stream>>>(tok, dout, g, dpos, (int)(rows / L), L, d4, zero_pad,
-                                                             rbm_drop_threshold(p), 1.f / (1.f - p), seed, site);
+                                                             rbm_drop_threshold(p), 1.f / (1.f - p), seed, site, row_offset * (uint64_t)d4);
   RBM_LAUNCH_CHECK("rbm_embed_bwd");
   return 0;
 }

@@ -316,3 +316,83 @@ def hybrid_vocab_parallel_loss(hidden, labels, w_shard, bias_shard, v_begin: int
     scale = float(world) if compensate_grad_average else 1.0
     h_all, l_all, overflow = GatherMaskedRowsFn.apply(hidden, labels, capacity, group, scale)
     return vocab_parallel_cross_entropy(h_all, l_all, w_shard, bias_shard, v_begin, group), overflow
+
+
+# ------------------------------------------------------------------------ row-sharded item table: input lookup
+def shard_keys(tok_all: torch.Tensor, v_begin: int, v_end: int, padding_idx: int = 0) -> torch.Tensor:
+    """Scatter keys of a shard: ``tok - v_begin`` for the tokens this shard owns, ``v_end - v_begin`` (one past the last local
+    row = the key ``rbm_scatter_add_sorted`` is told to skip) for everything else, the padding id included."""
+    own = (tok_all >= v_begin) & (tok_all < v_end) & (tok_all != padding_idx)
+    return torch.where(own, tok_all - v_begin, torch.full_like(tok_all, v_end - v_begin))
+
+
+class ShardedEmbedFn(torch.autograd.Function):
+    """Embedding stage (gather x scale + positions + dropout + pad zeroing) with the item table ROW-SHARDED over the ranks and the
+    sequences data-parallel.  Forward: all-gather the token ids (8 B per token), every rank runs the fused kernel on ALL tokens
+    against its block -- tokens of other blocks give exact zeros -- and a reduce-scatter hands every rank the rows of its own
+    sequences; exactly one addend per element is non-zero, so the result equals the unsharded kernel on the concatenated batch
+    bit for bit.  Backward: the rank masks its gradient rows (dropout / padding, global element indices) and reduces ``dpos`` over
+    its batch, the rows are all-gathered, and each rank sort/segment-reduces the rows of ITS items into the gradient of its
+    block (fixed order = global batch order).  ``grad_unscale``: divide the table gradient by this (the world size when the
+    loss pre-multiplies body gradients to compensate ``GradSync``'s averaging; sharded tensors are not averaged)."""
+
+    @staticmethod
+    def forward(ctx, tok, table_shard, pos, v_begin, vocab, scale, zero_pad, p, seed, site, group, grad_unscale):
+        from . import ops
+        lib = L.load()
+        L.require_cuda(tok, table_shard, pos)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        rank = dist.get_rank(group) if dist.is_initialized() else 0
+        Bsz, Ln = tok.shape
+        d = table_shard.shape[1]
+        v_end = int(v_begin) + table_shard.shape[0]
+        tok = tok.contiguous()
+        if world > 1:
+            tok_all = torch.empty(world * Bsz, Ln, device=tok.device, dtype=tok.dtype)
+            dist.all_gather_into_tensor(tok_all, tok, group=group)
+        else:
+            tok_all = tok
+        part = torch.empty(world * Bsz, Ln, d, device=tok.device, dtype=torch.float32)
+        check(lib.rbm_embed_fwd_shard(ptr(tok_all), ptr(table_shard), ptr(pos), ptr(part), world * Bsz * Ln, Ln, d, int(vocab), int(v_begin),
+                                      v_end, float(scale), int(zero_pad), float(p), seed, site, stream()), "embed_fwd_shard")
+        count_launches()
+        if world > 1:
+            out = torch.empty(Bsz, Ln, d, device=tok.device, dtype=torch.float32)
+            dist.reduce_scatter_tensor(out, part, op=dist.ReduceOp.SUM, group=group)
+        else:
+            out = part
+        ctx.save_for_backward(tok, tok_all)
+        ctx.meta = (table_shard.shape, pos.shape, int(v_begin), v_end, float(scale), int(zero_pad), float(p), seed, site, group, world, rank,
+                    float(grad_unscale))
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        from . import ops
+        lib = L.load()
+        tok, tok_all = ctx.saved_tensors
+        tshape, pshape, v_begin, v_end, scale, zero_pad, p, seed, site, group, world, rank, unscale = ctx.meta
+        Bsz, Ln = tok.shape
+        d = tshape[1]
+        dout = dout.contiguous()
+        g = torch.empty_like(dout)
+        dpos = torch.zeros(pshape, device=dout.device, dtype=torch.float32)
+        check(lib.rbm_embed_bwd_offset(ptr(tok), ptr(dout), ptr(g), ptr(dpos), Bsz * Ln, Ln, d, zero_pad, p, seed, site, rank * Bsz * Ln,
+                                       stream()), "embed_bwd_offset")
+        count_launches()
+        if world > 1:
+            g_all = torch.empty(world * Bsz, Ln, d, device=dout.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(g_all, g, group=group)
+        else:
+            g_all = g
+        keys = shard_keys(tok_all.reshape(-1), v_begin, v_end)
+        rows = tshape[0]
+        dtable = torch.zeros(rows, d, device=dout.device, dtype=torch.float32)
+        ops.scatter_add_sorted_(dtable, keys, g_all.reshape(-1, d), None, scale / unscale, padding_idx=rows, vocab=rows + 1)
+        return None, dtable, dpos, None, None, None, None, None, None, None, None, None
+
+
+def sharded_embedding(tok, table_shard, pos, v_begin: int, vocab: int, scale: float, zero_pad: int, p: float, seed: int, site: int,
+                      group=None, grad_unscale: float = 1.0):
+    """See ShardedEmbedFn.  ``table_shard`` = rows ``shard_range(vocab, rank, world)`` of the [vocab, d] table."""
+    return ShardedEmbedFn.apply(tok, table_shard, pos, v_begin, vocab, scale, zero_pad, p, seed, site, group, grad_unscale)

@@ -29,6 +29,8 @@ SIGNATURES = {
     "rbm_last_error": (C.c_char_p, []),
     "rbm_embed_fwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _L, _F, _I, _F, _U64, _U64, _P]),
     "rbm_embed_bwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _U64, _U64, _P]),
+    "rbm_embed_fwd_shard": (_I, [_P, _P, _P, _P, _L, _I, _I, _L, _L, _L, _F, _I, _F, _U64, _U64, _P]),
+    "rbm_embed_bwd_offset": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _F, _U64, _U64, _U64, _P]),
     "rbm_scatter_ws_bytes": (_SZ, [_L, _L]),
     "rbm_scatter_add_sorted": (_I, [_P, _P, _P, _F, _P, _L, _I, _L, _L, _P, _SZ, _P]),
     "rbm_layernorm_fwd": (_I, [_P, _P, _P, _P, _P, _L, _I, _F, _I, _P]),

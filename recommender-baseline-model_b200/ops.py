@@ -26,18 +26,22 @@ def _rows2d(x: torch.Tensor) -> torch.Tensor:
 
 # ------------------------------------------------------------------------------------------ scatter-add
 def scatter_add_sorted_(grad: torch.Tensor, idx: torch.Tensor, src: torch.Tensor, coef: Optional[torch.Tensor] = None,
-                        alpha: float = 1.0, padding_idx: int = 0) -> torch.Tensor:
-    """grad[idx[i]] += alpha*coef[i]*src[i] in ascending i per row (deterministic; K17)."""
+                        alpha: float = 1.0, padding_idx: int = 0, vocab: Optional[int] = None) -> torch.Tensor:
+    """grad[idx[i]] += alpha*coef[i]*src[i] in ascending i per row (deterministic; K17).  ``vocab`` (default: rows of ``grad``)
+    bounds the keys; a key range one larger than ``grad`` with ``padding_idx = grad.shape[0]`` gives a skip key that is not a row."""
     lib = L.load()
     L.require_cuda(grad, idx, src)
     n, d = idx.numel(), grad.shape[1]
     idx = idx.reshape(-1).contiguous()
     src = src.reshape(n, d).contiguous()
-    nb = lib.rbm_scatter_ws_bytes(n, grad.shape[0])
+    vocab = grad.shape[0] if vocab is None else int(vocab)
+    if vocab > grad.shape[0] and not (vocab == grad.shape[0] + 1 and padding_idx == grad.shape[0]):
+        raise RuntimeError("scatter_add_sorted_: keys beyond the rows of grad must be the skipped padding key")
+    nb = lib.rbm_scatter_ws_bytes(n, vocab)
     ws = _ws("scatter", nb, grad.device)
-    check(lib.rbm_scatter_add_sorted(ptr(idx), ptr(src), ptr(coef), float(alpha), ptr(grad), n, d, grad.shape[0],
+    check(lib.rbm_scatter_add_sorted(ptr(idx), ptr(src), ptr(coef), float(alpha), ptr(grad), n, d, vocab,
                                      int(padding_idx), ptr(ws), nb, stream()), "scatter_add_sorted")
-    bits = max(1, (grad.shape[0] - 1).bit_length())
+    bits = max(1, (vocab - 1).bit_length())
     count_launches(3 * ((bits + 7) // 8) + 2)
     return grad
 

@@ -104,6 +104,17 @@ def _worker(rank, world, port, q):
         assert torch.allclose(dh, Hg.grad[rank * n_loc:(rank + 1) * n_loc] * world, atol=1e-7)
         _, _, _, ovf = rd.masked_row_slots(torch.tensor([nz.numel()], dtype=torch.int32), rows, tg, max(1, nz.numel() - 1))
         assert bool(ovf)
+        # ---- row-sharded item table: scatter keys of a shard (owned ids -> local rows, everything else -> the skipped key)
+        Vt = 23
+        lo_t, hi_t = rd.shard_range(Vt, rank, world)
+        tok_all = torch.tensor([0, 1, 5, 11, 12, 22, 0, 12, 3], dtype=torch.int64)
+        keys = rd.shard_keys(tok_all, lo_t, hi_t)
+        for t_, k_ in zip(tok_all.tolist(), keys.tolist()):
+            assert k_ == (t_ - lo_t if (lo_t <= t_ < hi_t and t_ != 0) else hi_t - lo_t)
+        owned = torch.zeros(Vt, dtype=torch.int64)
+        owned[tok_all[keys < hi_t - lo_t]] = 1
+        dist.all_reduce(owned)
+        assert owned[0] == 0 and set(torch.nonzero(owned).flatten().tolist()) == {1, 3, 5, 11, 12, 22} and int(owned.max()) == 1
         q.put((rank, "ok"))
     except Exception as ex:  # noqa
         import traceback

@@ -113,6 +113,32 @@ def _worker(rank, world, port, q):
             assert torch.allclose(bs_.grad, bg.grad[lo:hi], rtol=1e-4, atol=1e-7)
         _, ovf = hybrid_vocab_parallel_loss(hid_g[slr], lab_g[slr], wfull[lo:hi], bfull[lo:hi], lo, capacity=2)
         assert bool(ovf)
+        # row-sharded item table, data-parallel sequences (SURVEY 8e input lookup): == the unsharded embedding stage on the
+        # concatenated batch -- forward bit for bit, table-shard gradient and (rank-summed) positional gradient to 1e-6
+        from rbm_b200.dist import sharded_embedding
+        ge = torch.Generator().manual_seed(31)
+        Ve, de, Le, Be = 1003, 64, 24, 5
+        table_e = torch.randn(Ve, de, generator=ge).to(dev)
+        pos_e = torch.randn(Le, de, generator=ge).to(dev)
+        tok_e = torch.randint(0, Ve, (world * Be, Le), generator=ge)
+        tok_e[:, :3] = 0
+        tok_e[1, 5:9] = 7  # repeated item, several contributions to one row
+        tok_e = tok_e.to(dev)
+        dout_e = torch.randn(world * Be, Le, de, generator=ge).to(dev)
+        for scale_e, zp_e, p_e in ((8.0, 1, 0.25), (1.0, 0, 0.0)):
+            tf, pf = table_e.clone().requires_grad_(True), pos_e.clone().requires_grad_(True)
+            full = rbm_b200.ops.EmbedFn.apply(tok_e, tf, pf, scale_e, zp_e, p_e, 77, 5)
+            full.backward(dout_e)
+            lo_e, hi_e = shard_range(Ve, rank, world)
+            ts, ps = table_e[lo_e:hi_e].clone().requires_grad_(True), pos_e.clone().requires_grad_(True)
+            sle = slice(rank * Be, (rank + 1) * Be)
+            out_e = sharded_embedding(tok_e[sle], ts, ps, lo_e, Ve, scale_e, zp_e, p_e, 77, 5)
+            assert torch.equal(out_e, full[sle]), (out_e - full[sle]).abs().max()
+            out_e.backward(dout_e[sle])
+            assert torch.allclose(ts.grad, tf.grad[lo_e:hi_e], rtol=1e-6, atol=1e-6), (ts.grad - tf.grad[lo_e:hi_e]).abs().max()
+            dp = ps.grad.clone()
+            dist.all_reduce(dp)
+            assert torch.allclose(dp, pf.grad, rtol=1e-5, atol=1e-5), (dp - pf.grad).abs().max()
         # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
         # bit for bit, dropout on
         import copy
