@@ -370,6 +370,9 @@ def main():
     model = rbm_b200.model_factory(margs)
     trainer = rbm_b200.trainer_factory(margs, model, None, None, None, None)
     model.train()
+    if world > 1:
+        from rbm_b200.dist import decorrelate_dropout
+        decorrelate_dropout(model)  # every rank its own dropout stream (the ranks are built from the same seeds)
     if world > 1 and not os.environ.get("RBM_BENCH_NO_GRADSYNC"):  # diagnostic: N independent replicas (per-rank speed without the exchange)
         trainer.dist_sync = GradSync(model.parameters())
     host = [(torch.from_numpy(t).pin_memory(), torch.from_numpy(l).pin_memory()) for t, l in make_batches(N_ROT, Bsz, seed=100 + rank)]

@@ -396,3 +396,40 @@ def sharded_embedding(tok, table_shard, pos, v_begin: int, vocab: int, scale: fl
                       group=None, grad_unscale: float = 1.0):
     """See ShardedEmbedFn.  ``table_shard`` = rows ``shard_range(vocab, rank, world)`` of the [vocab, d] table."""
     return ShardedEmbedFn.apply(tok, table_shard, pos, v_begin, vocab, scale, zero_pad, p, seed, site, group, grad_unscale)
+
+
+# ------------------------------------------------- BASELINE configs[3] layout: data-parallel body, row-sharded item tables
+def shard_bert_model(model, group=None, capacity=None):
+    """Cut ``bert.embedding.token.weight [V+2, d]``, ``out.weight [V+1, d]`` and ``out.bias`` of a BERT4Rec model down to this
+    rank's row blocks (``shard_range``), in place; ``hidden_states`` / ``loss`` then go through :func:`sharded_embedding` and
+    :func:`hybrid_vocab_parallel_loss`.  Build the model identically on every rank first (same ``model_init_seed``), shard, then
+    create the optimizer; give ``GradSync`` only :func:`replicated_parameters`.  ``capacity`` = slots for labelled rows per rank in
+    the loss exchange (None: all rows).  Dropout: the embedding site uses the common seed with global element indices, the body
+    sites a rank-specific seed (independent masks per rank).  Evaluation entry points of a sharded model are not wired yet."""
+    import types
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    tok = model.bert.embedding.token
+    tok_rows, out_rows = tok.weight.shape[0], model.out.weight.shape[0]
+    tb, te = shard_range(tok_rows, rank, world)
+    ob, oe = shard_range(out_rows, rank, world)
+    tok.weight = torch.nn.Parameter(tok.weight.data[tb:te].clone())
+    model.out.weight = torch.nn.Parameter(model.out.weight.data[ob:oe].clone())
+    model.out.bias = torch.nn.Parameter(model.out.bias.data[ob:oe].clone())
+    for p in (tok.weight, model.out.weight, model.out.bias):
+        p._rbm_sharded = True
+    model._shard = types.SimpleNamespace(group=group, rank=rank, world=world, tok_begin=tb, tok_rows=tok_rows, out_begin=ob,
+                                         out_rows=out_rows, capacity=capacity, overflow=None)
+    return model
+
+
+def replicated_parameters(model):
+    """The parameters every rank holds whole (what ``GradSync`` averages); row-sharded tensors are updated locally."""
+    return [p for p in model.parameters() if not getattr(p, "_rbm_sharded", False)]
+
+
+def decorrelate_dropout(model, group=None):
+    """Give each data-parallel rank its own dropout stream (ranks are built from the same seeds otherwise)."""
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    model.dropout_seed = (int(model.dropout_seed) + rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
+    return model

@@ -129,7 +129,15 @@ class BERTModel(BaseModel):
         p_a = bert.p_attn if train else 0.0
         seed = self.dropout_seed
         base = self._next_site_base() if train else 0
-        x = ops.EmbedFn.apply(tok, bert.embedding.token.weight, bert.embedding.position.pe.weight, 1.0, 0, p_h, seed, base)
+        sh = getattr(self, "_shard", None)
+        if sh is None:
+            x = ops.EmbedFn.apply(tok, bert.embedding.token.weight, bert.embedding.position.pe.weight, 1.0, 0, p_h, seed, base)
+        else:  # row-sharded item table (rbm_b200.dist.shard_bert_model): common seed + global element indices for this site,
+            #    a rank-specific seed for the body sites
+            from ..dist import sharded_embedding
+            x = sharded_embedding(tok, bert.embedding.token.weight, bert.embedding.position.pe.weight, sh.tok_begin, sh.tok_rows, 1.0, 0,
+                                  p_h, seed, base, sh.group, grad_unscale=float(sh.world))
+            seed = (seed + (sh.rank + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         scale = 1.0 / math.sqrt(d // h)
         for b, blk in enumerate(bert.transformer_blocks):
             s = base + 1 + 5 * b
@@ -150,6 +158,7 @@ class BERTModel(BaseModel):
     def forward(self, x):
         """NN/models/bert.py:15-16: logits [B, L, V+1].  Compatibility path that materialises the logits (small shapes,
         parity tests); training uses :meth:`loss`, evaluation :meth:`candidate_scores` / :meth:`full_catalogue_topk`."""
+        self._unsharded_only("forward")
         h = self.hidden_states(x)
         V1 = self.out.weight.shape[0]
         pad = (-V1) % 4
@@ -164,15 +173,28 @@ class BERTModel(BaseModel):
     def loss(self, x, labels):
         """CE(ignore_index=0) of NN/trainers/bert.py:30-41 without materialising [B*L, V+1] logits (K15-K16)."""
         h = self.hidden_states(x)
+        sh = getattr(self, "_shard", None)
+        if sh is not None:  # data-parallel rows x row-sharded output layer: the loss of the GLOBAL batch (SURVEY 8e)
+            from ..dist import hybrid_vocab_parallel_loss
+            loss, sh.overflow = hybrid_vocab_parallel_loss(h, self._device_long(labels), self.out.weight, self.out.bias, sh.out_begin,
+                                                           sh.capacity, sh.group)
+            return loss
         return ops.score_cross_entropy(h, self._device_long(labels), self.out.weight, self.out.bias)
 
     def last_hidden(self, x):
         return self.hidden_states(x)[:, -1, :]
 
+    def _unsharded_only(self, what):
+        if getattr(self, "_shard", None) is not None:
+            raise RuntimeError("%s: not wired for a row-sharded model yet (gather the tables with rbm_b200.checkpoint, or score the "
+                               "shards with rbm_b200.dist.sharded_full_catalogue_topk)" % what)
+
     def candidate_scores(self, x, candidates):
         """scores[:, -1, :].gather(1, candidates) of NN/trainers/bert.py:47-49, scoring only the candidates."""
+        self._unsharded_only("candidate_scores")
         return ops.candidate_scores(self.last_hidden(x), self.out.weight, self.out.bias, self._device_long(candidates))
 
     def full_catalogue_topk(self, x, k=10):
         """Top-k items (ids 1..V) of the last position, (score desc, id asc); scores never materialised (K19-K21)."""
+        self._unsharded_only("full_catalogue_topk")
         return ops.score_topk(self.last_hidden(x), self.out.weight, self.out.bias, 1, self.num_items + 1, k)

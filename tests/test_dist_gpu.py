@@ -139,6 +139,39 @@ def _worker(rank, world, port, q):
             dp = ps.grad.clone()
             dist.all_reduce(dp)
             assert torch.allclose(dp, pf.grad, rtol=1e-5, atol=1e-5), (dp - pf.grad).abs().max()
+        # BASELINE configs[3] layout end to end: data-parallel body, row-sharded token table + output layer.  One optimisation
+        # step of the sharded model on the ranks' own batches == the single-GPU model on the concatenated batch: loss, and every
+        # gradient (replicated ones after the bucket all-reduce, sharded ones against the rows of the full gradient)
+        from rbm_b200.dist import shard_bert_model, replicated_parameters
+        args_s = SimpleNamespace(**{**vars(args), "bert_hidden_units": 64, "num_items": 777, "max_len": 24})
+        Vs, Ls, Bs = 777, 24, 6
+        rs_ = np.random.RandomState(3)
+        tok_s = rs_.randint(1, Vs + 1, size=(world * Bs, Ls)).astype(np.int64)
+        tok_s[:, :2] = 0
+        lab_s = np.where((rs_.rand(world * Bs, Ls) < 0.25) & (tok_s != 0), tok_s, 0)
+        lab_s[Bs:][rs_.rand((world - 1) * Bs, Ls) > 0.5] = 0
+        tokm_s = np.where(lab_s != 0, Vs + 1, tok_s)
+        full_m = rbm_b200.model_factory(args_s)
+        full_t = rbm_b200.trainer_factory(args_s, full_m, None, None, None, None)
+        full_m.train()
+        loss_f = full_t.train_step((torch.from_numpy(tokm_s), torch.from_numpy(lab_s)))
+        gfull = {k: p.grad.clone() for k, p in full_m.named_parameters()}
+        sh_m = shard_bert_model(rbm_b200.model_factory(args_s).to(dev), capacity=64)
+        sh_t = rbm_b200.trainer_factory(args_s, sh_m, None, None, None, None)
+        sh_t.dist_sync = GradSync(replicated_parameters(sh_m))
+        sh_m.train()
+        sls = slice(rank * Bs, (rank + 1) * Bs)
+        loss_s = sh_t.train_step((torch.from_numpy(tokm_s[sls]), torch.from_numpy(lab_s[sls])))
+        assert not bool(sh_m._shard.overflow)
+        assert abs(loss_s.item() - loss_f.item()) < 1e-5 * abs(loss_f.item()), (loss_s.item(), loss_f.item())
+        gscale = max(float(g_.abs().max()) for g_ in gfull.values())
+        for k, p in sh_m.named_parameters():
+            ref_g = gfull[k]
+            if getattr(p, "_rbm_sharded", False):
+                b0, e0 = shard_range(ref_g.shape[0], rank, world)
+                ref_g = ref_g[b0:e0]
+            err = float((p.grad - ref_g).abs().max())
+            assert err <= 1e-3 * max(float(ref_g.abs().max()), 1e-3 * gscale), (k, err, float(ref_g.abs().max()))
         # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
         # bit for bit, dropout on
         import copy
