@@ -98,6 +98,12 @@ int rbm_layernorm_bwd_residual(const float* x, const float* gamma, const float* 
                                float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour,
                                void* ws, size_t ws_bytes, rbm_stream_t stream);
 
+/* same, plus dy2 (may be NULL): the gradient of a second consumer of the normalised output (SASRec: Q feeds the q-projection
+ * and the residual, NN/models/sas_model/sas.py:72-79; the FFN input feeds conv1 and the residual, :16-20): LN'(x)*(dy + dy2) + dres */
+int rbm_layernorm_bwd_fanout(const float* x, const float* gamma, const float* dy, const float* dy2, const float* dres,
+                             const float* stats, float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps,
+                             int flavour, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
 /* ---- Linear with fused epilogue --------------------------------------------------------------------
  * pre = x[M,K] . w[N,K]^T + bias        (optionally stored to `pre` when act needs it in backward)
  * y   = rowkeep * dropB( residual + dropA( act(pre) ) )      rowkeep(r) = row_tok ? row_tok[r]!=0 : 1

@@ -78,8 +78,8 @@ __global__ void __launch_bounds__(256) layernorm_fwd_kernel(const float* __restr
 template <int NV, int GW>
 __global__ void __launch_bounds__(32 * LN_BWD_WARPS) layernorm_bwd_kernel(
     const float* __restrict__ x, const float* __restrict__ gamma, const float* __restrict__ dy,
-    const float* __restrict__ dres, const float* __restrict__ stats, float* __restrict__ dx, float* __restrict__ partial,
-    int64_t rows, int d, int64_t rows_per_block, float eps, int flavour) {
+    const float* __restrict__ dy2, const float* __restrict__ dres, const float* __restrict__ stats, float* __restrict__ dx,
+    float* __restrict__ partial, int64_t rows, int d, int64_t rows_per_block, float eps, int flavour) {
   extern __shared__ float sm[];  // [NG][2][d]
   constexpr int NG = 32 * LN_BWD_WARPS / GW;  // row groups per block
   int lane = threadIdx.x % GW, warp = threadIdx.x / GW;
@@ -100,6 +100,14 @@ __global__ void __launch_bounds__(32 * LN_BWD_WARPS) layernorm_bwd_kernel(
     float4 xv[NV], gy[NV];
     ln_load_row<NV, GW>(x + row * d, d4, lane, xv);
     ln_load_row<NV, GW>(dy + row * d, d4, lane, gy);
+    if (dy2 != nullptr) {  // the normalised output feeds two consumers: their gradients are summed on the way in
+      float4 g2[NV];
+      ln_load_row<NV, GW>(dy2 + row * d, d4, lane, g2);
+#pragma unroll
+      for (int t = 0; t < NV; ++t) {
+        gy[t].x += g2[t].x; gy[t].y += g2[t].y; gy[t].z += g2[t].z; gy[t].w += g2[t].w;
+      }
+    }
     if (!live) {
 #pragma unroll
       for (int t = 0; t < NV; ++t) gy[t] = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -221,10 +229,21 @@ extern "C" int rbm_layernorm_bwd(const float* x, const float* gamma, const float
   return rbm_layernorm_bwd_residual(x, gamma, dy, nullptr, stats, dx, dgamma, dbeta, rows, d, eps, flavour, ws, ws_bytes, stream);
 }
 
+extern "C" int rbm_layernorm_bwd_fanout(const float* x, const float* gamma, const float* dy, const float* dy2, const float* dres,
+                                        const float* stats, float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps,
+                                        int flavour, void* ws, size_t ws_bytes, rbm_stream_t stream);
+
 extern "C" int rbm_layernorm_bwd_residual(const float* x, const float* gamma, const float* dy, const float* dres, const float* stats,
                                           float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps, int flavour,
                                           void* ws, size_t ws_bytes, rbm_stream_t stream) {
+  return rbm_layernorm_bwd_fanout(x, gamma, dy, nullptr, dres, stats, dx, dgamma, dbeta, rows, d, eps, flavour, ws, ws_bytes, stream);
+}
+
+extern "C" int rbm_layernorm_bwd_fanout(const float* x, const float* gamma, const float* dy, const float* dy2, const float* dres,
+                                        const float* stats, float* dx, float* dgamma, float* dbeta, int64_t rows, int d, float eps,
+                                        int flavour, void* ws, size_t ws_bytes, rbm_stream_t stream) {
   RBM_REQUIRE(x && gamma && dy && stats && dx && dgamma && dbeta && ws, "rbm_layernorm_bwd: null pointer");
+  RBM_REQUIRE(!dy2 || rbm_aligned16(dy2), "rbm_layernorm_bwd: dy2 must be 16B aligned");
   RBM_REQUIRE(!dres || rbm_aligned16(dres), "rbm_layernorm_bwd: dres must be 16B aligned");
   RBM_REQUIRE(d >= 4 && d % 4 == 0 && d <= LN_MAXD, "rbm_layernorm_bwd: unsupported d=%d", d);
   RBM_REQUIRE(rows > 0, "rbm_layernorm_bwd: rows must be > 0");
@@ -239,8 +258,8 @@ extern "C" int rbm_layernorm_bwd_residual(const float* x, const float* gamma, co
     size_t smem = (size_t)(32 * LN_BWD_WARPS / GW) * 2 * d * sizeof(float);                                         \
     if (smem > 48 * 1024)                                                                                           \
       cudaFuncSetAttribute(layernorm_bwd_kernel<NV, GW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);   \
-    layernorm_bwd_kernel<NV, GW><<<nblk, 32 * LN_BWD_WARPS, smem, st>>>(x, gamma, dy, dres, stats, dx, (float*)ws, rows, \
-                                                                        d, rpb, eps, flavour);                      \
+    layernorm_bwd_kernel<NV, GW><<<nblk, 32 * LN_BWD_WARPS, smem, st>>>(x, gamma, dy, dy2, dres, stats, dx, (float*)ws,  \
+                                                                        rows, d, rpb, eps, flavour);                \
   } while (0)
   if (d4 <= 8) LN_BWD(1, 8);
   else if (d4 <= 16) LN_BWD(1, 16);

@@ -69,15 +69,17 @@ class SASModel(BaseModel):
         for b in range(len(sas.attention_layers)):
             s = base + 1 + 3 * b
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
-            Q = ops.layernorm(x, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
+            # Q and x both have two consumers: layernorm_fanout hands out (Q, Q, x) so that the three gradients meet inside
+            # the LayerNorm-backward launch instead of autograd's elementwise adds
+            Q, Qres, xkv = ops.layernorm_fanout(x, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
             w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
             q = ops.linear(Q, w_in[:d], b_in[:d])          # q from the normalised stream
-            kv = ops.linear(x, w_in[d:], b_in[d:])         # k, v from the un-normalised stream (sas.py:75)
+            kv = ops.linear(xkv, w_in[d:], b_in[d:])       # k, v from the un-normalised stream (sas.py:75)
             ctx = ops.attention(q, kv, None, Bsz, Ln, h, 0, 0, d, L.MASK_CAUSAL, scale, p, seed, s)
-            x = ops.linear(ctx.view(Bsz, Ln, d), mha.out_proj.weight, mha.out_proj.bias, residual=Q)  # Q + mha (sas.py:79)
-            x = ops.layernorm(x, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
+            x = ops.linear(ctx.view(Bsz, Ln, d), mha.out_proj.weight, mha.out_proj.bias, residual=Qres)  # Q + mha (sas.py:79)
+            x, xres, _ = ops.layernorm_fanout(x, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
             u = ops.linear(x, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU, pA=p, siteA=s + 1, seed=seed)
-            x = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=x, row_tok=seq, pA=p, siteA=s + 2, seed=seed)
+            x = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xres, row_tok=seq, pA=p, siteA=s + 2, seed=seed)
         return ops.layernorm(x, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
 
     def forward(self, log_seqs, pos_seqs, neg_seqs):  # for training

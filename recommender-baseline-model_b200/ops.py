@@ -167,6 +167,54 @@ class LayerNormResidualFn(torch.autograd.Function):
         return dx.view(shape), dgamma, dbeta, None, None
 
 
+class LayerNormFanoutFn(torch.autograd.Function):
+    """(LN(x), LN(x), x): the normalised output for TWO consumers plus the input for a second consumer (SASRec block,
+    NN/models/sas_model/sas.py:72-84: Q feeds the q-projection and the residual, x feeds LN and the k/v projection).  All three
+    gradients meet inside one LayerNorm-backward launch (rbm_layernorm_bwd_fanout) instead of autograd's elementwise adds."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, eps, flavour):
+        lib = L.load()
+        L.require_cuda(x, gamma, beta)
+        x2 = _rows2d(x).contiguous()
+        rows, d = x2.shape
+        y = torch.empty_like(x2)
+        stats = torch.empty(rows, 2, device=x.device, dtype=torch.float32)
+        check(lib.rbm_layernorm_fwd(ptr(x2), ptr(gamma), ptr(beta), ptr(y), ptr(stats), rows, d, float(eps), int(flavour),
+                                    stream()), "layernorm_fwd")
+        count_launches()
+        ctx.save_for_backward(x2, gamma, stats)
+        ctx.meta = (float(eps), int(flavour), x.shape)
+        return y.view(x.shape), y.view(x.shape), x.view_as(x)
+
+    @staticmethod
+    def backward(ctx, dy, dy2, dres):
+        lib = L.load()
+        x2, gamma, stats = ctx.saved_tensors
+        eps, flavour, shape = ctx.meta
+        rows, d = x2.shape
+        if dy is None:
+            dy, dy2 = dy2, None
+        if dy is None:
+            dy = torch.zeros(shape, device=x2.device, dtype=x2.dtype)
+        c2 = lambda t: None if t is None else t.reshape(rows, d).contiguous()
+        dy, dy2, dres = c2(dy), c2(dy2), c2(dres)
+        dx = torch.empty_like(x2)
+        dgamma = torch.empty_like(gamma)
+        dbeta = torch.empty_like(gamma)
+        nb = lib.rbm_layernorm_ws_bytes(rows, d)
+        ws = _ws("ln", nb, x2.device)
+        check(lib.rbm_layernorm_bwd_fanout(ptr(x2), ptr(gamma), ptr(dy), ptr(dy2), ptr(dres), ptr(stats), ptr(dx), ptr(dgamma),
+                                           ptr(dbeta), rows, d, eps, flavour, ptr(ws), nb, stream()), "layernorm_bwd_fanout")
+        count_launches(2)
+        return dx.view(shape), dgamma, dbeta, None, None
+
+
+def layernorm_fanout(x, gamma, beta, eps, flavour):
+    """-> (LN(x), LN(x) again for a second consumer, x for a second consumer); see LayerNormFanoutFn."""
+    return LayerNormFanoutFn.apply(x, gamma, beta, eps, flavour)
+
+
 def layernorm_residual(x, gamma, beta, eps, flavour):
     """-> (LN(x), x): use the second value as the residual operand of the sublayer (see LayerNormResidualFn)."""
     return LayerNormResidualFn.apply(x, gamma, beta, eps, flavour)
