@@ -211,6 +211,36 @@ def _ckpt_worker(rank, world, port, q, tmpdir):
         fresh.load_state_dict(got["model_state_dict"])  # the reference's resume path (NN/trainers/base.py:29)
         fresh_opt = torch.optim.Adam(fresh.parameters(), lr=1e-2)
         fresh_opt.load_state_dict(got["optimizer_state_dict"])  # the line the reference leaves commented out (:30)
+        # ---- the real BERT4Rec parameter tree: shard_bert_model (row blocks of the token table / output layer, in place) and
+        #      gather-on-save give back exactly the unsharded state_dict; replicated_parameters leaves the shards out
+        from types import SimpleNamespace
+        import rbm_b200
+        from rbm_b200.dist import shard_bert_model, replicated_parameters
+        a = SimpleNamespace(model_code="bert", num_items=37, max_len=8, device="cpu", model_init_seed=4, bert_num_blocks=1,
+                            bert_num_heads=2, bert_hidden_units=16, bert_dropout=0.0, bert_hidden_dropout=0.0)
+        whole = rbm_b200.model_factory(a)
+        part = shard_bert_model(rbm_b200.model_factory(a))
+        keys = ck.ROW_SHARDED["bert"]
+        sd_w, sd_p = whole.state_dict(), part.state_dict()
+        assert list(sd_w) == list(sd_p)
+        for k_, v_ in sd_w.items():
+            if k_ in keys:
+                b_, e_ = shard_range(v_.shape[0], rank, world)
+                assert torch.equal(sd_p[k_], v_[b_:e_]), k_
+            else:
+                assert torch.equal(sd_p[k_], v_), k_
+        rep = replicated_parameters(part)
+        assert len(rep) == len(list(part.parameters())) - 3 and all(not getattr(p_, "_rbm_sharded", False) for p_ in rep)
+        assert part._shard.tok_rows == 39 and part._shard.out_rows == 38 and part._shard.world == world
+        f2 = os.path.join(tmpdir, "bert_gathered.pth")
+        ck.save_checkpoint(f2, part, None, epoch=1, sharded_keys=keys, total_rows={k_: sd_w[k_].shape[0] for k_ in keys})
+        got2 = torch.load(f2, map_location="cpu", weights_only=False)["model_state_dict"]
+        for k_, v_ in sd_w.items():
+            assert torch.equal(got2[k_], v_), k_
+        again = shard_bert_model(rbm_b200.model_factory(SimpleNamespace(**{**vars(a), "model_init_seed": 9})))
+        ck.load_checkpoint(f2, again, None, sharded_keys=keys)
+        for k_, v_ in again.state_dict().items():
+            assert torch.equal(v_, sd_p[k_]), k_
         q.put((rank, "ok"))
     except Exception:  # noqa
         import traceback
