@@ -405,7 +405,8 @@ def shard_bert_model(model, group=None, capacity=None):
     :func:`hybrid_vocab_parallel_loss`.  Build the model identically on every rank first (same ``model_init_seed``), shard, then
     create the optimizer; give ``GradSync`` only :func:`replicated_parameters`.  ``capacity`` = slots for labelled rows per rank in
     the loss exchange (None: all rows).  Dropout: the embedding site uses the common seed with global element indices, the body
-    sites a rank-specific seed (independent masks per rank).  Evaluation entry points of a sharded model are not wired yet."""
+    sites a rank-specific seed (independent masks per rank).  ``full_catalogue_topk`` of a sharded model goes through
+    :func:`sharded_model_topk`; the sampled-candidate paths are not wired."""
     import types
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -433,3 +434,34 @@ def decorrelate_dropout(model, group=None):
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     model.dropout_seed = (int(model.dropout_seed) + rank * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
     return model
+
+
+def sharded_model_topk(model, x, k: int = 10):
+    """Full-catalogue top-k of the last position for a model cut by :func:`shard_bert_model` (top-k eval): the last
+    hidden rows of all ranks' users are all-gathered ([B, d] per rank), every rank runs the fused scoring + top-k on ITS rows of
+    the output layer with GLOBAL item ids, the per-shard lists are exchanged with an all-to-all by user range (each rank receives
+    the lists of its own users only: k * 12 B per user and shard) and merged under the single-GPU order rule (score desc, id asc),
+    so the result equals the unsharded model's.  Every rank must pass the same number of users."""
+    from . import ops
+    sh = model._shard
+    group, world, rank = sh.group, sh.world, sh.rank
+    h = model.last_hidden(x).contiguous()
+    B, d = h.shape
+    if world > 1:
+        h_all = torch.empty(world * B, d, device=h.device, dtype=h.dtype)
+        dist.all_gather_into_tensor(h_all, h, group=group)
+    else:
+        h_all = h
+    w, b = model.out.weight, model.out.bias
+    lo = 1 if sh.out_begin == 0 else 0  # row 0 of the output layer is the padding id, not an item
+    if w.shape[0] > lo:
+        vals, ids = ops.score_topk(h_all, w, b, lo, w.shape[0], k, id_offset=sh.out_begin)
+    else:
+        vals = torch.full((world * B, k), float("-inf"), device=h.device)
+        ids = torch.full((world * B, k), -1, device=h.device, dtype=torch.int64)
+    if world == 1:
+        return vals, ids
+    rv, ri = torch.empty_like(vals), torch.empty_like(ids)
+    dist.all_to_all_single(rv, vals.contiguous(), group=group)  # chunk s of the result = shard s's lists for MY users
+    dist.all_to_all_single(ri, ids.contiguous(), group=group)
+    return ops.topk_merge(rv.view(world, B, k), ri.view(world, B, k))

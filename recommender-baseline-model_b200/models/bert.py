@@ -186,8 +186,8 @@ class BERTModel(BaseModel):
 
     def _unsharded_only(self, what):
         if getattr(self, "_shard", None) is not None:
-            raise RuntimeError("%s: not wired for a row-sharded model yet (gather the tables with rbm_b200.checkpoint, or score the "
-                               "shards with rbm_b200.dist.sharded_full_catalogue_topk)" % what)
+            raise RuntimeError("%s: not wired for a row-sharded model (use full_catalogue_topk, or gather the tables with "
+                               "rbm_b200.checkpoint)" % what)
 
     def candidate_scores(self, x, candidates):
         """scores[:, -1, :].gather(1, candidates) of NN/trainers/bert.py:47-49, scoring only the candidates."""
@@ -196,5 +196,7 @@ class BERTModel(BaseModel):
 
     def full_catalogue_topk(self, x, k=10):
         """Top-k items (ids 1..V) of the last position, (score desc, id asc); scores never materialised (K19-K21)."""
-        self._unsharded_only("full_catalogue_topk")
+        if getattr(self, "_shard", None) is not None:
+            from ..dist import sharded_model_topk
+            return sharded_model_topk(self, x, k)
         return ops.score_topk(self.last_hidden(x), self.out.weight, self.out.bias, 1, self.num_items + 1, k)

@@ -172,6 +172,16 @@ def _worker(rank, world, port, q):
                 ref_g = ref_g[b0:e0]
             err = float((p.grad - ref_g).abs().max())
             assert err <= 1e-3 * max(float(ref_g.abs().max()), 1e-3 * gscale), (k, err, float(ref_g.abs().max()))
+        # full-catalogue top-10 of the sharded model (all-gather of the last hidden rows, shard-local fused scoring with global ids,
+        # all-to-all of the lists by user range, merge) == the unsharded model on the same users: ids exactly
+        full_e = rbm_b200.model_factory(args_s).to(dev).eval()
+        sh_e = shard_bert_model(rbm_b200.model_factory(args_s).to(dev)).eval()
+        ev_tok = np.concatenate([tok_s[:, 1:], np.full((world * Bs, 1), Vs + 1, np.int64)], axis=1)  # history + [MASK]
+        with torch.no_grad():
+            fv, fi = full_e.full_catalogue_topk(torch.from_numpy(ev_tok), 10)
+            sv, si = sh_e.full_catalogue_topk(torch.from_numpy(ev_tok[sls]), 10)
+        assert torch.equal(si, fi[sls]), (si, fi[sls])
+        assert torch.allclose(sv, fv[sls], rtol=1e-6, atol=1e-6)
         # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
         # bit for bit, dropout on
         import copy
