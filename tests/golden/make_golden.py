@@ -422,6 +422,42 @@ def gen_eval_batches(name="eval_batches"):
     print("wrote", name)
 
 
+def gen_partition(name="partition"):
+    """``data_partition`` of the REFERENCE (NN/dataloaders/__init__.py:17-66) on a small interactions file; the function opens
+    ``Data/<fname>`` next to the (read-only) reference tree, so its ``open`` is redirected to an in-memory file."""
+    import io
+    import dataloaders as ref_dl
+    rs = np.random.RandomState(21)
+    lens = {7: 1, 3: 2, 12: 3, 5: 9, 40: 50, 41: 51, 2: 64, 9: 137, 30: 8, 31: 230}
+    lines = []
+    pending = {u: list(rs.randint(1, 400, size=n)) for u, n in lens.items()}
+    users = list(lens)
+    while any(pending.values()):  # interleave the users' lines: grouping must not depend on contiguity
+        u = users[rs.randint(len(users))]
+        if pending[u]:
+            lines.append("%d %d" % (u, pending[u].pop(0)))
+    text = "\n".join(lines) + "\n"
+    out = {"text": np.frombuffer(text.encode(), dtype=np.uint8)}
+    real_open = getattr(ref_dl, "open", None)
+    ref_dl.open = lambda path, mode="r": io.StringIO(text)
+    try:
+        for L, prop in ((8, 0.3), (50, 0.3), (50, -1.0), (200, 0.3)):
+            tr, va, te, n, V = ref_dl.data_partition("whatever.txt", L, prop)
+            tag = "L%d_p%s" % (L, str(prop).replace(".", "").replace("-", "m"))
+            out[tag + ".train_ptr"] = np.cumsum([0] + [len(r) for r in tr]).astype(np.int64)
+            out[tag + ".train"] = np.array([i for r in tr for i in r], np.int64)
+            out[tag + ".valid"] = np.array([r[0] for r in va], np.int64)
+            out[tag + ".test"] = np.array([r[0] for r in te], np.int64)
+            out[tag + ".n"], out[tag + ".V"] = np.int64(n), np.int64(V)
+    finally:
+        if real_open is None:
+            del ref_dl.open
+        else:
+            ref_dl.open = real_open
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--only", default=None, help="regenerate one fixture family only (eval_batches)")
@@ -430,6 +466,8 @@ def main():
     model_factory, metric_fn = ref_imports()
     if args.only == "eval_batches":
         return gen_eval_batches()
+    if args.only == "partition":
+        return gen_partition()
     gen_bert(model_factory, "bert_tiny", V=37, L=8, d=16, nb=2, h=2, B=4, seed=0)
     gen_bert(model_factory, "bert_odd", V=101, L=13, d=32, nb=1, h=4, B=3, seed=3)
     gen_bert(model_factory, "bert_cfg2", V=3416, L=200, d=64, nb=2, h=2, B=4, seed=1, store_sd=False, adam_steps=2)
@@ -440,6 +478,7 @@ def main():
     gen_scatter_adam()
     gen_batches()
     gen_eval_batches()
+    gen_partition()
 
 
 if __name__ == "__main__":

@@ -279,3 +279,21 @@ def test_negative_samples_unfillable_row_ends_in_minus_one():
     from oracle import batches as obt
     out = obt.negative_samples([[1, 2, 3, 4], [2]], 5, 2, 9, 1 << 41)
     assert out[0].tolist()[0] == 5 and out[0].tolist()[1] == -1 and (out[1] > 0).all()
+
+
+# ------------------------------------------------------------------------------------ data_partition
+@pytest.mark.parametrize("L,prop,tag", [(8, 0.3, "L8_p03"), (50, 0.3, "L50_p03"), (50, -1.0, "L50_pm10"), (200, 0.3, "L200_p03")])
+def test_data_partition_vs_reference(tmp_path, L, prop, tag):
+    """The vectorised text parser + sliding-window split == the reference's data_partition on the same file
+    (tests/golden/partition.npz: interleaved users, histories shorter than 3, equal to / just above max_len, many windows)."""
+    from rbm_b200.dataloaders import data_partition
+    z = load("partition")
+    f = tmp_path / "interactions.txt"
+    f.write_bytes(z["text"].tobytes())
+    tr, va, te, n, V = data_partition(str(f), L, prop)
+    assert n == int(z[tag + ".n"]) == len(tr) == len(va) == len(te) and V == int(z[tag + ".V"])
+    ptr = z[tag + ".train_ptr"]
+    assert [len(r) for r in tr] == np.diff(ptr).tolist()
+    np.testing.assert_array_equal(np.array([i for r in tr for i in r], np.int64), z[tag + ".train"])
+    np.testing.assert_array_equal(np.array([r[0] for r in va], np.int64), z[tag + ".valid"])
+    np.testing.assert_array_equal(np.array([r[0] for r in te], np.int64), z[tag + ".test"])
