@@ -10,6 +10,7 @@ from .models import MODELS, model_factory, BERTModel, SASModel  # noqa: F401
 from .trainers import TRAINERS, trainer_factory, BERTTrainer, SASTrainer  # noqa: F401
 from .trainers.utils import recalls_ndcgs_and_mrr_for_ks  # noqa: F401
 from .optim import FusedAdam  # noqa: F401
+from .dataloaders import DATALOADERS, dataloader_factory  # noqa: F401
 
 __all__ = ["MODELS", "model_factory", "BERTModel", "SASModel", "TRAINERS", "trainer_factory", "BERTTrainer", "SASTrainer",
-           "recalls_ndcgs_and_mrr_for_ks", "FusedAdam", "lib"]
+           "recalls_ndcgs_and_mrr_for_ks", "FusedAdam", "DATALOADERS", "dataloader_factory", "lib"]

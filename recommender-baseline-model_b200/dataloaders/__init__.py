@@ -7,3 +7,4 @@ from .synthetic import (synthetic_interactions, sliding_window_partition, BertBa
 from .device import (histories_to_csr, DeviceBertTrainLoader, DeviceSasTrainLoader, seen_sets_to_csr, popularity_cdf,  # noqa: F401,E402
                      DeviceNegativeSampler, DeviceEvalLoader)
 from .partition import load_interactions_text, data_partition  # noqa: F401,E402
+from .factory import DATALOADERS, dataloader_factory, BertDataloader, SASDataLoader  # noqa: F401,E402

@@ -178,3 +178,16 @@ def test_wire_formats_of_the_batch_builders():
     cands, labels = uniform_negative_candidates(test, V, 100)
     assert cands.shape == (n, 101) and (labels[:, 0] == 1).all() and labels[:, 1:].sum() == 0
     assert (cands[:, 1:] != cands[:, :1]).all() and cands.min() >= 1 and cands.max() <= V
+
+
+def test_registries_mirror_the_reference():
+    """MODELS / TRAINERS / DATALOADERS keys and code() classmethods (NN/models/__init__.py:4-12, NN/trainers/__init__.py:4-12,
+    NN/dataloaders/__init__.py:11-14); an unknown model code is an error, as in the reference's dict lookup."""
+    import rbm_b200
+    assert set(rbm_b200.MODELS) == set(rbm_b200.TRAINERS) == set(rbm_b200.DATALOADERS) == {"bert", "sas"}
+    for reg in (rbm_b200.MODELS, rbm_b200.TRAINERS, rbm_b200.DATALOADERS):
+        for code, cls in reg.items():
+            assert cls.code() == code
+    from types import SimpleNamespace
+    with pytest.raises(KeyError):
+        rbm_b200.dataloader_factory(SimpleNamespace(model_code="gru", max_len=5), dataset=[[], [], [], 0, 0])

@@ -322,3 +322,47 @@ def test_wide_models_vs_oracle(kind, V, Ln, d, nb, h, B):
             # hold only rounding noise there, which is judged against (1 % of) the scale of the block's query-bias gradient
             floor = 10.0 * float(sd[k.replace("linear_layers.1.bias", "linear_layers.0.bias")].grad.abs().max())
         relclose(prm.grad.cpu().numpy(), gr.numpy(), 1e-3, floor=floor, msg=k)
+
+
+@pytest.mark.parametrize("kind", ["bert", "sas"])
+def test_dataloader_factory_end_to_end(kind, tmp_path):
+    """dataloader_factory -> (train, val, test) device loaders -> trainer loops' hooks: text file in, the reference's batch wire
+    formats out (checked against the oracle's eval batches / negatives), one training step and one validation batch run."""
+    from oracle import batches as obt
+    from rbm_b200.dataloaders import data_partition
+    rs = np.random.RandomState(8)
+    V, Ln = 90, 12
+    lines = ["%d %d" % (u, i) for u in range(1, 41) for i in rs.randint(1, V + 1, size=rs.randint(3, 30))]
+    f = tmp_path / "toy.txt"
+    f.write_text("\n".join(lines) + "\n")
+    common = dict(model_code=kind, data_path=str(f), data_name="toy.txt", max_len=Ln, prop_sliding_window=0.3, device=DEV,
+                  load_processed_dataset=False, dataloader_random_seed=3, worker_number=0, train_batch_size=16, val_batch_size=8,
+                  test_batch_size=8, test_negative_sampler_code="random", test_negative_sample_size=20,
+                  test_negative_sampling_seed=98765, bert_mask_prob=0.3, optimizer="Adam", lr=1e-3, weight_decay=0, momentum=None,
+                  decay_step=10, gamma=1.0, num_epochs=1, metric_ks=[1, 5, 10], best_metric="NDCG@10", resume_path=None, l2_emb=0.0)
+    extra = vars(bert_args(0, Ln, 16, 1, 2, p=0.1, seed=1)) if kind == "bert" else vars(sas_args(0, Ln, 16, 1, 1, p=0.1))
+    args = SimpleNamespace(**{**extra, **common})
+    train, val, test = rbm_b200.dataloader_factory(args)
+    tr, va, te, n, itemnum = data_partition(str(f), Ln, 0.3)
+    assert args.num_items == itemnum and len(val) == (n + 7) // 8
+    # evaluation batches == the oracle's, with the oracle's negatives (bit-exact contract)
+    seen = [sorted(set(tr[u]) | set(va[u]) | set(te[u])) for u in range(n)]
+    negs = obt.negative_samples(seen, itemnum, 20, 98765, ops.NEG_SITE)
+    mask = itemnum + 1 if kind == "bert" else -1
+    for loader, hist, ans in ((val, tr, [v[0] for v in va]), (test, [tr[u] + va[u] for u in range(n)], [t[0] for t in te])):
+        got = [torch.cat([b[j] for b in loader]).cpu().numpy() for j in range(3)]
+        ref = obt.eval_batch(hist, ans, negs, list(range(n)), Ln, mask)
+        for g_, r_ in zip(got, ref):
+            np.testing.assert_array_equal(g_, r_)
+    model = rbm_b200.model_factory(args)
+    trainer = rbm_b200.trainer_factory(args, model, train, val, test, None)
+    model.train()
+    batch = next(iter(train))
+    assert all(t.shape == (16, Ln) and t.dtype == torch.int64 for t in batch)
+    l0 = trainer.train_step(batch).item()
+    assert np.isfinite(l0)
+    model.eval()
+    with torch.no_grad():
+        m = trainer.calculate_metrics(next(iter(val)))
+    assert set(m) == {"%s@%d" % (nm, k) for nm in ("Recall", "NDCG", "MRR") for k in (1, 5, 10)}
+    assert all(0.0 <= v <= 1.0 for v in m.values())
