@@ -100,6 +100,9 @@ class AbstractTrainer(metaclass=ABCMeta):
             raise ValueError("collective must be 'split' or 'graph'")
         if not isinstance(self.optimizer, FusedAdam):
             raise RuntimeError("capture_train_step needs the fused Adam optimizer")
+        if getattr(self.model, "_shard", None) is not None:
+            raise RuntimeError("capture_train_step: a row-sharded model exchanges rows inside the loss and its backward; those "
+                               "collectives are not captured -- use the eager step")
         sync = self.dist_sync if (self.dist_sync is not None and self.dist_sync.world > 1) else None
         dev = torch.device(self.device)
         static = tuple(torch.as_tensor(x).to(dev).clone() for x in example_batch)
