@@ -1,3 +1,5 @@
+"""Bring-up helpers for the d = 128 / 256 model shapes: `parity` (hidden states and loss against the oracle) and `prof`
+(per-entry-point device time of one BERT4Rec step at the BASELINE configs[3] shape on one GPU)."""
 import sys, os
 from types import SimpleNamespace
 import numpy as np, torch
