@@ -567,3 +567,34 @@ def test_eval_batch_ragged_vs_oracle():
         np.testing.assert_array_equal(s.cpu().numpy(), so)
         np.testing.assert_array_equal(c.cpu().numpy(), co)
         np.testing.assert_array_equal(l.cpu().numpy(), lo)
+
+
+def test_score_topk_full_size_properties():
+    """Full-catalogue scoring + top-10 at a BASELINE-sized catalogue (10^6 items, ragged end, bias): size-independent properties --
+    sorted scores, distinct in-range ids, scores equal to an exact recomputation, agreement with an fp64 ranking on a sample of
+    users, and shard-count invariance (two half-catalogue calls merged == one call)."""
+    torch.manual_seed(7)
+    U, V, d, k = 1024, 1_000_003, 64, 10
+    f = torch.randn(U, d, device=DEV)
+    table = torch.randn(V + 1, d, device=DEV)
+    b = torch.randn(V + 1, device=DEV)
+    vals, ids = ops.score_topk(f, table, b, 1, V + 1, k)
+    assert bool((vals[:, :-1] >= vals[:, 1:]).all())
+    assert int(ids.min()) >= 1 and int(ids.max()) <= V
+    assert all(len(set(r)) == k for r in ids[:64].tolist()) and int((ids.sort(1).values.diff(dim=1) == 0).sum()) == 0
+    exact = (f.double().unsqueeze(1) * table[ids].double()).sum(-1) + b[ids].double()
+    assert float((vals.double() - exact).abs().max()) < 1e-4
+    n = 256
+    sc = f[:n].double() @ table[1:].double().t() + b[1:].double()
+    rv, ri = torch.topk(sc, k + 1, dim=1)
+    same = (ids[:n] == ri[:, :k] + 1).all(1)
+    assert float(same.float().mean()) >= 0.99, float(same.float().mean())
+    clear = (rv[:, k - 1] - rv[:, k]) > 1e-3  # k-th and (k+1)-th score apart by more than fp32 noise: the SET is determined
+    got, ref = ids[:n].sort(1).values, (ri[:, :k] + 1).sort(1).values
+    assert bool((got[clear] == ref[clear]).all())
+    half = 1 + V // 2
+    v1, i1 = ops.score_topk(f, table, b, 1, half, k)
+    v2, i2 = ops.score_topk(f, table, b, half, V + 1, k)
+    mv, mi = ops.topk_merge(torch.stack([v1, v2]), torch.stack([i1, i2]))
+    assert float((mi == ids).all(1).float().mean()) >= 0.995
+    assert torch.allclose(mv, vals, rtol=0, atol=1e-4)
