@@ -468,6 +468,9 @@ def main():
         return gen_eval_batches()
     if args.only == "partition":
         return gen_partition()
+    if args.only == "wide":  # the d = 128 / 256 model shapes of BASELINE configs[2] / configs[3] (small catalogues)
+        gen_bert(model_factory, "bert_cfg4s", V=900, L=200, d=256, nb=4, h=4, B=3, seed=2, store_sd=False, adam_steps=1)
+        return gen_sas(model_factory, "sas_cfg3s", V=1200, L=50, d=128, nb=2, h=2, B=8, seed=2, store_sd=False, adam_steps=1)
     gen_bert(model_factory, "bert_tiny", V=37, L=8, d=16, nb=2, h=2, B=4, seed=0)
     gen_bert(model_factory, "bert_odd", V=101, L=13, d=32, nb=1, h=4, B=3, seed=3)
     gen_bert(model_factory, "bert_cfg2", V=3416, L=200, d=64, nb=2, h=2, B=4, seed=1, store_sd=False, adam_steps=2)
@@ -479,6 +482,10 @@ def main():
     gen_batches()
     gen_eval_batches()
     gen_partition()
+    gen_bert(model_factory, "bert_cfg4s", V=900, L=200, d=256, nb=4, h=4, B=3, seed=2, store_sd=False, adam_steps=1)
+    gen_sas(model_factory, "sas_cfg3s", V=1200, L=50, d=128, nb=2, h=2, B=8, seed=2, store_sd=False, adam_steps=1)
+    gen_bert(model_factory, "bert_cfg4s", V=900, L=200, d=256, nb=4, h=4, B=3, seed=2, store_sd=False, adam_steps=1)
+    gen_sas(model_factory, "sas_cfg3s", V=1200, L=50, d=128, nb=2, h=2, B=8, seed=2, store_sd=False, adam_steps=1)
 
 
 if __name__ == "__main__":

@@ -75,8 +75,9 @@ def test_bert_adam_steps(name):
         np.testing.assert_allclose(params[k], v.numpy(), rtol=1e-4, atol=2e-6, err_msg=k)
 
 
-def test_bert_cfg2_shape():
-    z = load("bert_cfg2")
+@pytest.mark.parametrize("name", ["bert_cfg2", "bert_cfg4s"])  # configs[1] shape; configs[3] model shape (d=256, 4 blocks, h=4)
+def test_bert_cfg2_shape(name):
+    z = load(name)
     V, L, d, nb, h, B, seed = z["cfg"].tolist()
     sd = ob.random_state_dict(V, L, d, nb, seed=seed)
     t, l = torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"])
@@ -122,8 +123,9 @@ def test_sas_adam_steps():
         np.testing.assert_allclose(a, b, rtol=1e-4, atol=2e-6, err_msg=k)
 
 
-def test_sas_cfg1_shape():
-    z = load("sas_cfg1")
+@pytest.mark.parametrize("name", ["sas_cfg1", "sas_cfg3s"])  # configs[0] shape; configs[2] model shape (d=128, h=2)
+def test_sas_cfg1_shape(name):
+    z = load(name)
     V, L, d, nb, h, B, seed = z["cfg"].tolist()
     sd = osr.random_state_dict(V, L, d, nb, seed=seed)
     seq, pos, neg = (torch.from_numpy(z[k]) for k in ("seq", "pos", "neg"))
