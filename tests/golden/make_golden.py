@@ -484,8 +484,6 @@ def main():
     gen_partition()
     gen_bert(model_factory, "bert_cfg4s", V=900, L=200, d=256, nb=4, h=4, B=3, seed=2, store_sd=False, adam_steps=1)
     gen_sas(model_factory, "sas_cfg3s", V=1200, L=50, d=128, nb=2, h=2, B=8, seed=2, store_sd=False, adam_steps=1)
-    gen_bert(model_factory, "bert_cfg4s", V=900, L=200, d=256, nb=4, h=4, B=3, seed=2, store_sd=False, adam_steps=1)
-    gen_sas(model_factory, "sas_cfg3s", V=1200, L=50, d=128, nb=2, h=2, B=8, seed=2, store_sd=False, adam_steps=1)
 
 
 if __name__ == "__main__":
