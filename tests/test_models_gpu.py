@@ -366,3 +366,26 @@ def test_dataloader_factory_end_to_end(kind, tmp_path):
         m = trainer.calculate_metrics(next(iter(val)))
     assert set(m) == {"%s@%d" % (nm, k) for nm in ("Recall", "NDCG", "MRR") for k in (1, 5, 10)}
     assert all(0.0 <= v <= 1.0 for v in m.values())
+
+
+@pytest.mark.parametrize("name", ["bert_cfg4s", "sas_cfg3s"])
+def test_wide_models_vs_reference_golden(name):
+    """The d = 256 / 128 model shapes of BASELINE configs[3] / configs[2] against numbers produced by the UNMODIFIED reference
+    (tests/golden/{bert_cfg4s,sas_cfg3s}.npz): loss within 3e-4 relative (north star: 1e-3), per-parameter gradient norms within
+    3e-3 (absolute floor 1e-5 of the largest norm: the key-projection bias gradient is pure rounding noise on both sides)."""
+    z = load(name)
+    V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
+    if name.startswith("bert"):
+        model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, seed=seed))
+        model.load_state_dict(ob.random_state_dict(V, Ln, d, nb, seed=seed))
+        model.to(DEV).train()
+        loss = model.loss(torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"]))
+    else:
+        model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h))
+        model.load_state_dict(osr.random_state_dict(V, Ln, d, nb, seed=seed))
+        model.to(DEV).train()
+        loss = model.loss(z["seq"], z["pos"], z["neg"])
+    loss.backward()
+    assert abs(loss.item() - float(z["loss"])) < 3e-4 * abs(float(z["loss"])), (loss.item(), float(z["loss"]))
+    gn = np.array([p.grad.norm().item() for _, p in model.named_parameters()])
+    np.testing.assert_allclose(gn, z["grad_norms"], rtol=3e-3, atol=1e-5 * float(z["grad_norms"].max()))
