@@ -48,6 +48,21 @@ def recalls_ndcgs_and_mrr_for_ks(scores: torch.Tensor, labels: torch.Tensor, ks:
     return metrics
 
 
+def scores_fp32_sequential(f: torch.Tensor, table: torch.Tensor, bias=None) -> torch.Tensor:
+    """The fp32 score the full-catalogue ranking is defined on: ``s = 0; for c in range(d): s = fma(f[u,c], table[v,c], s)``
+    in fp32, then ``+ bias[v]`` -- the reference's ``matmul`` (NN/models/sas_model/sas.py:114, NN/models/bert.py:16) with
+    the summation order pinned, so that "top-k of the fp32 scores" is one well-defined answer.  The FMA is emulated in
+    fp64 (the product of two fp32 values is exact there) and rounded to fp32 after every step.  [U,d] x [V,d] -> [U,V];
+    runs on whatever device the tensors live on."""
+    f64, t64 = f.double(), table.double()
+    acc = torch.zeros(f.shape[0], table.shape[0], dtype=torch.float32, device=f.device)
+    for c in range(f.shape[1]):
+        acc = (acc.double() + f64[:, c:c + 1] * t64[:, c].unsqueeze(0)).float()
+    if bias is not None:
+        acc = acc + bias.float().unsqueeze(0)
+    return acc
+
+
 def topk_canonical(scores: np.ndarray, k: int, id_offset: int = 0) -> Tuple[np.ndarray, np.ndarray]:
     """Top-k per row of ``scores`` [U,C] under (score desc, index asc); returns (values f32 [U,k],
     ids i64 [U,k]) with ids = column + id_offset.  Rows shorter than k are padded (-inf, -1)."""

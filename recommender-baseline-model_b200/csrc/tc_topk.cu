@@ -12,8 +12,14 @@
 //     a register-resident sorted list of KC = 16 (approx score, item id) candidates per (item split, column half).
 //   stage 2 (topk_rescore_kernel): one warp per user recomputes the EXACT fp32 score of every candidate (sequential
 //     fp32 FMA over d) and selects the final top-k under the canonical order (score desc, id asc).
-// Stage 1's TF32 error (<= ~1e-3 relative) only matters if more than KC - k items crowd within that margin of the
-// k-th best score; the final scores and their order are exact fp32.
+//   certificate: stage 1 ranks by single-pass TF32 scores (operands truncated to 11 significant bits: |tf32 - fp32 score|
+//     <= eps(u) = 2.1e-3 * ||f_u|| * max_v ||table_v||, Cauchy-Schwarz over the per-product truncation error 2^-9 |f_k e_k|
+//     plus the fp32 accumulation slack).  An item a list dropped has an approximate score <= tau = that list's final
+//     KC-th entry, hence an exact score <= tau + eps.  Stage 2 therefore PROVES its answer for user u when
+//     max_lists(tau) + eps(u) < (exact k-th best score); every other user is appended to a device-side list and
+//     re-ranked by the exact fp32 scan kernel of topk.cu (stage 3, no host synchronisation; its grid exits at once
+//     when the list is empty).  The result always equals the canonical (fp32 score desc, id asc) top-k, where the fp32
+//     score is the sequential FMA over the hidden dimension (the arithmetic of stage 2 and of the scan kernel).
 #include <stdlib.h>
 #include <string.h>
 #include "common.cuh"
@@ -240,9 +246,11 @@ __global__ void __launch_bounds__(64 + 32 * EPI, 1) tc_topk_kernel(const __grid_
 __device__ __forceinline__ bool better(float s, int64_t id, float ts, int64_t tid) { return s > ts || (s == ts && id < tid); }
 
 __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restrict__ f, int64_t ldf, const float* __restrict__ table,
-                                                           const float* __restrict__ bias, const int64_t* __restrict__ cand_i, int n_lists,
-                                                           int64_t id_offset, float* __restrict__ out_s, int64_t* __restrict__ out_i, int64_t U,
-                                                           int d, int k) {
+                                                           const float* __restrict__ bias, const int64_t* __restrict__ cand_i,
+                                                           const float* __restrict__ cand_s, int n_lists, int64_t id_offset,
+                                                           float* __restrict__ out_s, int64_t* __restrict__ out_i, int64_t U, int d, int k,
+                                                           const unsigned* __restrict__ emax2_bits, float eps_mul,
+                                                           int32_t* __restrict__ flag_list, int32_t* __restrict__ flag_count) {
   extern __shared__ float fs[];  // [8 warps][d]
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int64_t u = (int64_t)blockIdx.x * 8 + wib;
@@ -295,6 +303,42 @@ __global__ void __launch_bounds__(256) topk_rescore_kernel(const float* __restri
     out_s[u * k + lane] = mi == INT64_MAX ? -INFINITY : ms;
     out_i[u * k + lane] = mi == INT64_MAX ? -1 : mi;
   }
+  // certificate (see the file header): a dropped item's exact score is <= tau + eps
+  float tau = -INFINITY;
+  for (int l = lane; l < n_lists; l += 32) tau = fmaxf(tau, cand_s[((int64_t)l * U + u) * KC + (KC - 1)]);
+  tau = warp_max(tau);
+  float hn2 = 0.f;
+  for (int c = lane; c < d; c += 32) hn2 = fmaf(fu[c], fu[c], hn2);
+  hn2 = warp_sum(hn2);
+  const float sk = __shfl_sync(0xffffffffu, ms, k - 1);
+  const bool full = __shfl_sync(0xffffffffu, mi, k - 1) != INT64_MAX;
+  if (lane == 0 && tau > -INFINITY) {
+    const float eps = eps_mul * sqrtf(hn2) * sqrtf(__uint_as_float(*emax2_bits)) + 1e-6f * (fabsf(sk) + fabsf(tau));
+    if (!full || !(tau + eps < sk)) flag_list[atomicAdd(flag_count, 1)] = (int32_t)u;
+  }
+}
+
+// max over table rows [v_begin, v_end) of the squared row norm, as the bit pattern of a non-negative float (atomicMax on
+// unsigned: order-independent, hence deterministic).  LPR lanes per row, float4 per lane and step.
+__global__ void __launch_bounds__(256) row_norm_max_kernel(const float* __restrict__ table, int64_t v_begin, int64_t v_end, int d, int lpr,
+                                                           unsigned* __restrict__ out_bits) {
+  const int lane = threadIdx.x & 31;
+  const int rpw = 32 / lpr, sub = lane / lpr, li = lane % lpr;
+  const int64_t warp_g = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5), n_warps = (int64_t)gridDim.x * (blockDim.x >> 5);
+  float best = 0.f;
+  for (int64_t r0 = v_begin + warp_g * rpw; r0 < v_end; r0 += n_warps * rpw) {
+    const int64_t r = r0 + sub;
+    float s = 0.f;
+    if (r < v_end)
+      for (int c = li * 4; c < d; c += lpr * 4) {
+        const float4 t = ld4(table + r * d + c);
+        s = fmaf(t.x, t.x, s); s = fmaf(t.y, t.y, s); s = fmaf(t.z, t.z, s); s = fmaf(t.w, t.w, s);
+      }
+    for (int o = lpr >> 1; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    best = fmaxf(best, s);
+  }
+  best = warp_max(best);
+  if (lane == 0) atomicMax(out_bits, __float_as_uint(best));
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -352,13 +396,26 @@ int rbm_tc_topk_splits(int64_t U, int64_t n_items, int d) {
   return (int)(s < 1 ? 1 : s);
 }
 
-size_t rbm_tc_topk_ws_bytes(int64_t U, int64_t n_items, int d) {
+// item splits of the exact re-scan of uncertified users: as many as keep its partial lists under 128 MB
+int rbm_tc_topk_fb_splits(int64_t U, int64_t n_items, int k) {
+  int64_t s = ((int64_t)128 << 20) / (U * k * 12);
+  int64_t tiles = rbm_cdiv(n_items, 64);
+  if (s > tiles) s = tiles;
+  if (s > 64) s = 64;
+  return (int)(s < 1 ? 1 : s);
+}
+static size_t cand_bytes(int64_t U, int64_t n_items, int d) {
   size_t S = (size_t)rbm_tc_topk_splits(U, n_items, d);
-  return S * 2 * (size_t)U * KC * (sizeof(float) + sizeof(int64_t)) + 256;
+  return S * 2 * (size_t)U * KC * (sizeof(float) + sizeof(int64_t));
+}
+// [candidate ids | candidate scores | emax2 bits, flag count (16 B) | flag list U int32 (padded to 16 B) | re-scan partial lists]
+size_t rbm_tc_topk_ws_bytes(int64_t U, int64_t n_items, int d, int k) {
+  size_t fb = (size_t)rbm_tc_topk_fb_splits(U, n_items, k) * (size_t)U * k * (sizeof(float) + sizeof(int64_t));
+  return cand_bytes(U, n_items, d) + 16 + (((size_t)U * 4 + 15) & ~(size_t)15) + fb + 256;
 }
 
 bool rbm_tc_topk_supported(int64_t U, int64_t n_items, int d, int k, int64_t ldf, const void* f, const void* table) {
-  if (!tc_enabled() || d % BKE != 0 || d < BKE || d > 256 || k > 16 || U < 1) return false;
+  if (!tc_enabled() || d % BKE != 0 || d < BKE || d > 256 || k > KC - 6 || U < 1) return false;  // k <= 10: six spare list slots (larger k: exact fp32 scan kernel)
   if (n_items < 8192) return false;  // small catalogues: the fp32 tile kernel is already latency-bound
   if (ldf % 4 != 0 || ((uintptr_t)f & 15) || ((uintptr_t)table & 15)) return false;
   return get_encode() != nullptr;
@@ -406,8 +463,22 @@ int rbm_tc_topk_launch(const float* f, int64_t ldf, const float* table, const fl
   int grid = units < RBM_NUM_SMS ? units : RBM_NUM_SMS;
   tc_topk_kernel<<<grid, 64 + 32 * EPI, smem, st>>>(mapA, mapB, p);
   RBM_LAUNCH_CHECK("rbm_score_topk(tcgen05)");
-  topk_rescore_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 8 * d * sizeof(float), st>>>(f, ldf, table, bias, p.cand_i, p.nst == 2 ? p.S : p.S * 2, id_offset,
-                                                                                   top_scores, top_ids, U, d, k);
+  // certificate inputs: max squared item-row norm of the range, flag list + counter
+  uint8_t* aux = (uint8_t*)ws + cand_bytes(U, n_items, d);
+  unsigned* emax2 = (unsigned*)aux;
+  int32_t* flag_count = (int32_t*)(aux + 4);
+  int32_t* flag_list = (int32_t*)(aux + 16);
+  void* fb_ws = aux + 16 + (((size_t)U * 4 + 15) & ~(size_t)15);
+  cudaMemsetAsync(aux, 0, 16, st);
+  float eps_mul = 2.1e-3f;  // 2^-9 (two truncated operands per product) + fp32 accumulation slack
+  if (const char* e = getenv("RBM_TOPK_EPS")) eps_mul = (float)atof(e);  // tests: a huge value sends every user through stage 3
+  int lpr = d / 4 < 32 ? d / 4 : 32;
+  row_norm_max_kernel<<<RBM_NUM_SMS * 4, 256, 0, st>>>(table, v_begin, v_end, d, lpr, emax2);
+  RBM_LAUNCH_CHECK("rbm_score_topk(row norms)");
+  topk_rescore_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 8 * d * sizeof(float), st>>>(f, ldf, table, bias, p.cand_i, p.cand_s, p.nst == 2 ? p.S : p.S * 2,
+                                                                                   id_offset, top_scores, top_ids, U, d, k, emax2, eps_mul, flag_list, flag_count);
   RBM_LAUNCH_CHECK("rbm_score_topk(rescore)");
-  return 0;
+  // stage 3: users whose answer the certificate does not cover are re-ranked by the exact fp32 scan (grid exits when none)
+  return rbm_simt_topk_listed(f, ldf, table, bias, v_begin, v_end, id_offset, top_scores, top_ids, U, d, k, flag_list, flag_count, fb_ws,
+                              rbm_tc_topk_fb_splits(U, n_items, k), st);
 }

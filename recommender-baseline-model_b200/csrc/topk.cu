@@ -64,7 +64,12 @@ __device__ __forceinline__ void list_store(const Entry& mine, float* out_s, int6
 __global__ void __launch_bounds__(256) score_topk_kernel(const float* __restrict__ f, int64_t ldf, const float* __restrict__ table,
                                                          const float* __restrict__ bias, int64_t v_begin, int64_t v_end, int64_t id_offset,
                                                          float* __restrict__ out_s, int64_t* __restrict__ out_i, int64_t U, int d, int k,
-                                                         int64_t tiles_per_split) {
+                                                         int64_t tiles_per_split, const int32_t* __restrict__ ulist,
+                                                         const int32_t* __restrict__ ucount) {
+  // listed mode (ulist != null): row slot j of the launch is user ulist[j], j < *ucount (device-side count); results go
+  // to slot j of the partial lists (stride U)
+  const int64_t U_eff = ulist ? (int64_t)*ucount : U;
+  if ((int64_t)blockIdx.x * T >= U_eff) return;
   extern __shared__ __align__(16) float sm[];
   float* Hst = sm;               // [d][LDT]  users transposed
   float* Wc = Hst + d * LDT;     // [KC][LDT] item chunk transposed
@@ -77,7 +82,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const float* __restrict
     for (int idx = threadIdx.x; idx < T * d4; idx += blockDim.x) {
       int r = idx / d4, c4 = idx - r * d4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (u0 + r < U) v = ld4(f + (u0 + r) * ldf + c4 * 4);
+      if (u0 + r < U_eff) v = ld4(f + (ulist ? (int64_t)ulist[u0 + r] : u0 + r) * ldf + c4 * 4);
       Hst[(c4 * 4 + 0) * LDT + r] = v.x;
       Hst[(c4 * 4 + 1) * LDT + r] = v.y;
       Hst[(c4 * 4 + 2) * LDT + r] = v.z;
@@ -153,7 +158,7 @@ __global__ void __launch_bounds__(256) score_topk_kernel(const float* __restrict
 #pragma unroll
   for (int q = 0; q < 8; ++q) {
     int64_t u = u0 + warp * 8 + q;
-    if (u < U) list_store(lists[q], ps, pi, u, k, lane);
+    if (u < U_eff) list_store(lists[q], ps, pi, u, k, lane);
   }
 }
 
@@ -174,10 +179,11 @@ __global__ void __launch_bounds__(256) topk_rows_kernel(const float* __restrict_
 }
 
 __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict__ in_s, const int64_t* __restrict__ in_i,
-                                                         float* __restrict__ out_s, int64_t* __restrict__ out_i, int S, int64_t U, int k) {
+                                                         float* __restrict__ out_s, int64_t* __restrict__ out_i, int S, int64_t U, int k,
+                                                         const int32_t* __restrict__ ulist, const int32_t* __restrict__ ucount) {
   int lane = threadIdx.x & 31;
   int64_t u = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= U) return;
+  if (u >= (ulist ? (int64_t)*ucount : U)) return;
   Entry mine{-INFINITY, ID_NONE};
   for (int s = 0; s < S; ++s) {
     const float* ps = in_s + ((int64_t)s * U + u) * k;
@@ -186,7 +192,7 @@ __global__ void __launch_bounds__(256) topk_merge_kernel(const float* __restrict
     int64_t cid = lane < k ? pi[lane] : -1;
     list_offer(mine, cs, cid, lane < k && cid >= 0, k, lane);
   }
-  list_store(mine, out_s, out_i, u, k, lane);
+  list_store(mine, out_s, out_i, ulist ? (int64_t)ulist[u] : u, k, lane);  // listed mode: slot u holds user ulist[u]
 }
 
 // ------------------------------------------------------------------------------------- ranking metrics
@@ -266,7 +272,7 @@ extern "C" size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k) {
   size_t simt = S * (size_t)U * k * (sizeof(float) + sizeof(int64_t)) + 256;
   size_t tc = 0;
   for (int d = 32; d <= 256; d *= 2) {  // d is not part of this query: cover every hidden size the tcgen05 path takes
-    size_t b = rbm_tc_topk_ws_bytes(U, n_items, d);
+    size_t b = rbm_tc_topk_ws_bytes(U, n_items, d, k);
     if (b > tc) tc = b;
   }
   return simt > tc ? simt : tc;
@@ -294,14 +300,31 @@ extern "C" int rbm_score_topk(const float* f, int64_t ldf, const float* table, c
   float* part_s = (float*)(part_i + (size_t)S * U * k);
   dim3 grid((unsigned)rbm_cdiv(U, T), S);
   if (S == 1) {
-    score_topk_kernel<<<grid, 256, smem, st>>>(f, ldf, table, bias, v_begin, v_end, id_offset, top_scores, top_ids, U, d, k, tps);
+    score_topk_kernel<<<grid, 256, smem, st>>>(f, ldf, table, bias, v_begin, v_end, id_offset, top_scores, top_ids, U, d, k, tps, nullptr, nullptr);
     RBM_LAUNCH_CHECK("rbm_score_topk");
   } else {
-    score_topk_kernel<<<grid, 256, smem, st>>>(f, ldf, table, bias, v_begin, v_end, id_offset, part_s, part_i, U, d, k, tps);
+    score_topk_kernel<<<grid, 256, smem, st>>>(f, ldf, table, bias, v_begin, v_end, id_offset, part_s, part_i, U, d, k, tps, nullptr, nullptr);
     RBM_LAUNCH_CHECK("rbm_score_topk");
-    topk_merge_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 0, st>>>(part_s, part_i, top_scores, top_ids, S, U, k);
+    topk_merge_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 0, st>>>(part_s, part_i, top_scores, top_ids, S, U, k, nullptr, nullptr);
     RBM_LAUNCH_CHECK("rbm_score_topk(merge)");
   }
+  return 0;
+}
+
+// exact fp32 scan + top-k of the users ulist[0 .. *ucount) (tc_topk.cu stage 3): partial lists per item split, then merge
+int rbm_simt_topk_listed(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin, int64_t v_end,
+                         int64_t id_offset, float* top_scores, int64_t* top_ids, int64_t U, int d, int k, const int32_t* ulist,
+                         const int32_t* ucount, void* part_ws, int S, cudaStream_t st) {
+  int64_t tps = rbm_cdiv(rbm_cdiv(v_end - v_begin, T), S);
+  size_t smem = sizeof(float) * ((size_t)d * LDT + KC * LDT + T * LDT);
+  cudaFuncSetAttribute(score_topk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  int64_t* part_i = (int64_t*)part_ws;
+  float* part_s = (float*)(part_i + (size_t)S * U * k);
+  dim3 grid((unsigned)rbm_cdiv(U, T), S);
+  score_topk_kernel<<<grid, 256, smem, st>>>(f, ldf, table, bias, v_begin, v_end, id_offset, part_s, part_i, U, d, k, tps, ulist, ucount);
+  RBM_LAUNCH_CHECK("rbm_score_topk(exact re-scan)");
+  topk_merge_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 0, st>>>(part_s, part_i, top_scores, top_ids, S, U, k, ulist, ucount);
+  RBM_LAUNCH_CHECK("rbm_score_topk(exact re-scan merge)");
   return 0;
 }
 
@@ -318,7 +341,7 @@ extern "C" int rbm_topk_merge(const float* scores, const int64_t* ids, float* ou
                               rbm_stream_t stream) {
   RBM_REQUIRE(scores && ids && out_scores && out_ids, "rbm_topk_merge: null pointer");
   RBM_REQUIRE(S >= 1 && U > 0 && k >= 1 && k <= 32, "rbm_topk_merge: bad sizes");
-  topk_merge_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, out_scores, out_ids, S, U, k);
+  topk_merge_kernel<<<(unsigned)rbm_cdiv(U, 8), 256, 0, (cudaStream_t)stream>>>(scores, ids, out_scores, out_ids, S, U, k, nullptr, nullptr);
   RBM_LAUNCH_CHECK("rbm_topk_merge");
   return 0;
 }

@@ -327,25 +327,42 @@ def test_topk_rows_bit_exact_with_ties(U, Cn, k):
     np.testing.assert_array_equal(v.cpu().numpy(), ref_v)
 
 
-@pytest.mark.parametrize("U,V,d,k,bias", [(10, 300, 16, 10, False), (70, 3416, 64, 10, True), (130, 12101, 128, 10, False), (64, 5000, 256, 20, True)])
+@pytest.mark.parametrize("U,V,d,k,bias", [(10, 300, 16, 10, False), (70, 3416, 64, 10, True), (130, 12101, 128, 10, False), (64, 5000, 256, 20, True),
+                                          (200, 40000, 64, 10, True), (33, 9000, 32, 16, False)])
 def test_score_topk_fused(U, V, d, k, bias):
+    """ids AND scores equal to the canonical top-k of the fp32 scores (sequential-FMA contract, oracle/metrics.py) on every row:
+    the fp32 scan kernel, the tcgen05 selection + exact re-score (catalogues >= 8192 items, k <= 10), and the same with every
+    user forced through the exact re-scan (stage 3)."""
+    import os
     torch.manual_seed(U + V)
     f, table = torch.randn(U, d), torch.randn(V + 1, d)
     b = torch.randn(V + 1) if bias else None
-    vals, ids = ops.score_topk(g(f), g(table), g(b) if bias else None, 1, V + 1, k)
-    # score parity, then selection parity on the kernel's own scores (fp32 sum order differs from torch's matmul)
-    sc = f @ table[1:].t() + (b[1:] if bias else 0)
-    gathered = torch.gather(sc, 1, ids.cpu() - 1)
-    close(vals, gathered, 1e-4, 1e-4)
-    ref_v, ref_i = om.topk_canonical(sc.numpy(), k, id_offset=1)
-    kth_gap = ref_v[:, -1] - np.sort(sc.numpy(), 1)[:, -(k + 1)]
-    safe = kth_gap > 1e-3
-    assert safe.mean() > 0.8
-    # same SET where the k-th/(k+1)-th gap exceeds the fp tolerance; same ORDER where neighbouring gaps do too
-    for u in np.flatnonzero(safe):
-        assert set(ids[u].tolist()) == set(ref_i[u].tolist())
-    well_sep = safe & (np.min(-np.diff(ref_v, axis=1), axis=1) > 1e-3)
-    np.testing.assert_array_equal(ids.cpu().numpy()[well_sep], ref_i[well_sep])
+    sc = om.scores_fp32_sequential(g(f), g(table[1:]), g(b[1:]) if bias else None).cpu().numpy()
+    ref_v, ref_i = om.topk_canonical(sc, k, id_offset=1)
+    for eps in (None, "1e9"):
+        if eps:
+            os.environ["RBM_TOPK_EPS"] = eps
+        try:
+            vals, ids = ops.score_topk(g(f), g(table), g(b) if bias else None, 1, V + 1, k)
+        finally:
+            os.environ.pop("RBM_TOPK_EPS", None)
+        np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+        np.testing.assert_array_equal(vals.cpu().numpy(), ref_v)
+
+
+def test_score_topk_adversarial_near_ties():
+    """Catalogue built so that thousands of items sit within the TF32 error of each user's k-th best score: the approximate
+    candidate lists cannot contain the right answer, the certificate must notice and the exact re-scan must deliver it."""
+    torch.manual_seed(5)
+    U, V, d, k = 96, 20000, 64, 10
+    f = torch.randn(U, d)
+    base = torch.randn(d)
+    table = base.unsqueeze(0) * (1.0 + 1e-5 * torch.randn(V + 1, 1)) + 1e-5 * torch.randn(V + 1, d)  # all items nearly collinear
+    sc = om.scores_fp32_sequential(g(f), g(table[1:])).cpu().numpy()
+    ref_v, ref_i = om.topk_canonical(sc, k, id_offset=1)
+    vals, ids = ops.score_topk(g(f), g(table), None, 1, V + 1, k)
+    np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
+    np.testing.assert_array_equal(vals.cpu().numpy(), ref_v)
 
 
 def test_topk_merge_shard_invariance():
@@ -570,9 +587,10 @@ def test_eval_batch_ragged_vs_oracle():
 
 
 def test_score_topk_full_size_properties():
-    """Full-catalogue scoring + top-10 at a BASELINE-sized catalogue (10^6 items, ragged end, bias): size-independent properties --
-    sorted scores, distinct in-range ids, scores equal to an exact recomputation, agreement with an fp64 ranking on a sample of
-    users, and shard-count invariance (two half-catalogue calls merged == one call)."""
+    """Full-catalogue scoring + top-10 at a BASELINE-sized catalogue (10^6 items, ragged end, bias): sorted scores, distinct
+    in-range ids, ids and scores IDENTICAL to the canonical top-k of the fp32 scores (oracle/metrics.scores_fp32_sequential) on
+    a sample of users, the set equal to an fp64 ranking wherever the k-th gap is clear, and exact shard-count invariance (two
+    half-catalogue calls merged == one call, every row); k = 16 (exact fp32 scan path) against the same oracle."""
     torch.manual_seed(7)
     U, V, d, k = 1024, 1_000_003, 64, 10
     f = torch.randn(U, d, device=DEV)
@@ -582,22 +600,24 @@ def test_score_topk_full_size_properties():
     assert bool((vals[:, :-1] >= vals[:, 1:]).all())
     assert int(ids.min()) >= 1 and int(ids.max()) <= V
     assert all(len(set(r)) == k for r in ids[:64].tolist()) and int((ids.sort(1).values.diff(dim=1) == 0).sum()) == 0
-    exact = (f.double().unsqueeze(1) * table[ids].double()).sum(-1) + b[ids].double()
-    assert float((vals.double() - exact).abs().max()) < 1e-4
-    n = 256
+    n = 128
+    sc32 = om.scores_fp32_sequential(f[:n], table[1:], b[1:])
+    rv32, ri32 = torch.topk(sc32, 16, dim=1)  # no exact ties among the top scores of random data: topk == canonical order
+    assert bool((rv32[:, :-1] > rv32[:, 1:]).all())
+    assert torch.equal(ids[:n], ri32[:, :k] + 1)
+    assert torch.equal(vals[:n], rv32[:, :k])
     sc = f[:n].double() @ table[1:].double().t() + b[1:].double()
     rv, ri = torch.topk(sc, k + 1, dim=1)
-    same = (ids[:n] == ri[:, :k] + 1).all(1)
-    assert float(same.float().mean()) >= 0.99, float(same.float().mean())
     clear = (rv[:, k - 1] - rv[:, k]) > 1e-3  # k-th and (k+1)-th score apart by more than fp32 noise: the SET is determined
     got, ref = ids[:n].sort(1).values, (ri[:, :k] + 1).sort(1).values
-    assert bool((got[clear] == ref[clear]).all())
+    assert bool((got[clear] == ref[clear]).all()) and float(clear.float().mean()) > 0.9
     half = 1 + V // 2
     v1, i1 = ops.score_topk(f, table, b, 1, half, k)
     v2, i2 = ops.score_topk(f, table, b, half, V + 1, k)
     mv, mi = ops.topk_merge(torch.stack([v1, v2]), torch.stack([i1, i2]))
-    assert float((mi == ids).all(1).float().mean()) >= 0.995
-    assert torch.allclose(mv, vals, rtol=0, atol=1e-4)
+    assert torch.equal(mi, ids) and torch.equal(mv, vals)
+    v16, i16 = ops.score_topk(f[:64], table, b, 1, V + 1, 16)
+    assert torch.equal(i16, ri32[:64] + 1) and torch.equal(v16, rv32[:64])
 
 
 def test_score_ce_full_size_properties():
