@@ -94,9 +94,12 @@ def _param_names(model: torch.nn.Module, optimizer: torch.optim.Optimizer) -> Li
 
 
 def save_checkpoint(path: str, model: torch.nn.Module, optimizer: Optional[torch.optim.Optimizer], epoch: int,
-                    sharded_keys: Sequence[str] = (), total_rows: Optional[Dict[str, int]] = None, group=None) -> None:
+                    sharded_keys: Sequence[str] = (), total_rows: Optional[Dict[str, int]] = None, group=None,
+                    extra_steps: int = 0) -> None:
     """Write the reference's checkpoint dict.  ``sharded_keys`` name the ``state_dict`` entries of which this rank's model
-    holds only its row block; ``total_rows[key]`` is the full row count.  Collective: every rank calls it; rank 0 writes."""
+    holds only its row block; ``total_rows[key]`` is the full row count.  Collective: every rank calls it; rank 0 writes.
+    ``extra_steps``: steps a live CUDA graph has taken on the device that the python-side counters have not seen
+    (``trainer._graph_steps_done()``); folded into the saved Adam ``step`` and ``dropout_step``."""
     rank, world = _world(group)
     total_rows = dict(total_rows or {})
     msd = gather_state_dict(model.state_dict(), sharded_keys, total_rows, group)
@@ -115,11 +118,14 @@ def save_checkpoint(path: str, model: torch.nn.Module, optimizer: Optional[torch
                     ent[f] = g.cpu() if rank == 0 else None
                 else:
                     ent[f] = v.detach().cpu() if torch.is_tensor(v) else v
+                if f == "step" and extra_steps:
+                    ent[f] = ent[f] + extra_steps
             state[idx] = ent
         osd = {"state": state, "param_groups": raw["param_groups"]}
     if rank == 0:
         tmp = path + ".tmp"
-        torch.save({STATE_DICT_KEY: msd, OPTIMIZER_STATE_DICT_KEY: osd, "epoch": epoch}, tmp)
+        torch.save({STATE_DICT_KEY: msd, OPTIMIZER_STATE_DICT_KEY: osd, "epoch": epoch,
+                    "dropout_step": int(getattr(model, "_step", 0)) + extra_steps}, tmp)
         os.replace(tmp, path)  # a crash mid-write never leaves a truncated best_acc_model.pth behind
     if world > 1:
         dist.barrier(group=group)
@@ -147,4 +153,6 @@ def load_checkpoint(path: str, model: torch.nn.Module, optimizer: Optional[torch
             state[idx] = {f: (shard_rows(v, rank, world) if (torch.is_tensor(v) and v.dim() > 0 and name in keys) else v)
                           for f, v in st.items()}
         optimizer.load_state_dict({"state": state, "param_groups": osd["param_groups"]})
+    if "dropout_step" in ck and hasattr(model, "_step"):
+        model._step = int(ck["dropout_step"])  # resume the dropout stream where it stopped (trainers/base.py _create_state_dict)
     return int(ck.get("epoch", -1))

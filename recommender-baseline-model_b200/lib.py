@@ -160,15 +160,30 @@ def require_cuda(*tensors: torch.Tensor):
 
 
 class _Workspaces:
-    """Grow-only scratch buffers per (device, tag); reuse is safe because every consumer is stream-ordered."""
+    """Grow-only scratch buffers per (device, tag); reuse is safe because every consumer is stream-ordered.  A captured CUDA
+    graph has the buffer addresses baked into its kernel nodes: while any graph is alive (``freeze`` / ``unfreeze``, called by
+    ``capture_train_step`` / ``release_train_graph``) a buffer that has to grow is retired, not freed, so replays keep
+    writing into memory that is still theirs."""
 
     def __init__(self):
         self.bufs: Dict[tuple, torch.Tensor] = {}
+        self.frozen = 0
+        self.retired = []
+
+    def freeze(self):
+        self.frozen += 1
+
+    def unfreeze(self):
+        self.frozen = max(0, self.frozen - 1)
+        if self.frozen == 0:
+            self.retired.clear()
 
     def get(self, tag: str, nbytes: int, device) -> torch.Tensor:
         key = (str(device), tag)
         buf = self.bufs.get(key)
         if buf is None or buf.numel() < nbytes:
+            if buf is not None and self.frozen:
+                self.retired.append(buf)
             buf = torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
             self.bufs[key] = buf
         return buf

@@ -178,6 +178,8 @@ class BERTModel(BaseModel):
             from ..dist import hybrid_vocab_parallel_loss
             loss, sh.overflow = hybrid_vocab_parallel_loss(h, self._device_long(labels), self.out.weight, self.out.bias, sh.out_begin,
                                                            sh.capacity, sh.group)
+            # accumulated on the device; the trainer asserts it once per epoch (trainers/base.py _check_shard_overflow)
+            sh.overflow_any = sh.overflow if getattr(sh, "overflow_any", None) is None else (sh.overflow_any | sh.overflow)
             return loss
         return ops.score_cross_entropy(h, self._device_long(labels), self.out.weight, self.out.bias)
 

@@ -154,6 +154,7 @@ class AbstractTrainer(metaclass=ABCMeta):
             raise
         self._graph_launches = L.launch_count - launches0
         self._graph, self._graph_b, self._graph_static, self._graph_loss, self._graph_lr = graph, graph_b, static, loss, self.get_lr()
+        L.workspaces.freeze()  # the graph has the workspace addresses baked in: they must outlive every replay
         return self
 
     def _capture(self, graph, static, sync, collective, mode):
@@ -184,13 +185,41 @@ class AbstractTrainer(metaclass=ABCMeta):
             if "step" in st:
                 st["step"] += done - 1
         self._graph = self._graph_b = None
+        L.workspaces.unfreeze()
+
+    def _graph_steps_done(self) -> int:
+        """Optimisation steps taken since capture that the python-side counters (``optimizer.state[*]['step']``,
+        ``model._step``) have not seen yet: they advance on the device while a graph is active."""
+        return 0 if self._graph is None else int(self._graph_counter.item()) - 1
+
+    def _odd_shaped_step(self, batch):
+        """A batch whose shape differs from the captured one (typically the last batch of an epoch: like the reference's
+        ``DataLoader``, the loaders have no ``drop_last``).  One eager step at exactly the position the next replay would have
+        taken: the device-side step counter stays installed (kernels add it to their dropout sites and to Adam's step), so
+        the python-side counters are first moved back by the one step the capture advanced them, and the device counter is
+        advanced afterwards."""
+        self.model._step -= 1
+        for st in self.optimizer.state.values():
+            if "step" in st:
+                st["step"] -= 1
+        self.optimizer.zero_grad()
+        loss = self.calculate_loss(batch)
+        loss.backward()
+        if self.dist_sync is not None:
+            self.dist_sync.allreduce_grads()
+        self.optimizer.step()
+        self._graph_counter.add_(1)
+        return loss
 
     def _replay(self, batch):
         from .. import lib as L
         if self.get_lr() != self._graph_lr:
             raise RuntimeError("the learning rate changed since capture_train_step(): release_train_graph() and capture again")
+        batch = tuple(torch.as_tensor(x) for x in batch)
+        if len(batch) != len(self._graph_static) or any(tuple(s.shape) != tuple(d.shape) for s, d in zip(batch, self._graph_static)):
+            return self._odd_shaped_step(batch)  # never copy_ a mismatching batch: a 1-row remainder would broadcast silently
         for dst, src in zip(self._graph_static, batch):
-            dst.copy_(torch.as_tensor(src), non_blocking=True)
+            dst.copy_(src, non_blocking=True)
         self._graph.replay()
         if self._graph_b is not None:
             self.dist_sync.allreduce_bucket()
@@ -218,8 +247,25 @@ class AbstractTrainer(metaclass=ABCMeta):
             loss = self.train_step(batch)
             tot_loss += loss.item()
             accum_iter += self.batch_size
+        self._check_shard_overflow()
         print(tot_loss)
         return accum_iter
+
+    def _check_shard_overflow(self):
+        """Row-sharded model (rbm_b200.dist.shard_bert_model) with a slot ``capacity``: a rank that had more labelled rows than
+        slots dropped the excess from loss and gradients -- the '1 rank == N ranks' contract is broken, so fail loudly (checked
+        once per epoch: the flag is accumulated on the device, no per-step sync)."""
+        sh = getattr(self.model, "_shard", None)
+        if sh is None or getattr(sh, "overflow_any", None) is None:
+            return
+        flag = sh.overflow_any.to(torch.int32).reshape(1)
+        if sh.world > 1:  # collective: every rank reaches the end of the epoch; a rank must also learn of the OTHERS' overflow
+            import torch.distributed as dist
+            dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=sh.group)
+        sh.overflow_any = None
+        if bool(flag.item()):
+            raise RuntimeError("hybrid_vocab_parallel_loss: some rank had more labelled rows than its slot capacity (%s) during this "
+                               "epoch; rows were dropped from the loss. Raise `capacity` in shard_bert_model() or pass None." % sh.capacity)
 
     def _evaluate(self, loader):
         self.model.eval()
@@ -264,4 +310,12 @@ class AbstractTrainer(metaclass=ABCMeta):
             raise ValueError
 
     def _create_state_dict(self):
-        return {STATE_DICT_KEY: self.model.state_dict(), OPTIMIZER_STATE_DICT_KEY: self.optimizer.state_dict()}
+        """NN/trainers/base.py:255-259, plus ``dropout_step`` (the position of the dropout stream; restored by
+        ``rbm_b200.checkpoint.load_checkpoint``).  While a CUDA graph is active the real step lives in the device-side
+        counter: it is folded into the saved Adam steps and the dropout step here."""
+        extra = self._graph_steps_done()
+        osd = self.optimizer.state_dict()
+        if extra:
+            osd = {"state": {k: {f: (v + extra if f == "step" else v) for f, v in st.items()} for k, st in osd["state"].items()},
+                   "param_groups": osd["param_groups"]}
+        return {STATE_DICT_KEY: self.model.state_dict(), OPTIMIZER_STATE_DICT_KEY: osd, "dropout_step": self.model._step + extra}

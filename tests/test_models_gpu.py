@@ -276,6 +276,22 @@ def test_cuda_graph_train_step_equals_eager(kind):
     # and eager steps continue seamlessly after the graph is released
     nb = batch(7)
     assert t1.train_step(nb).item() == t2.train_step(nb).item()
+    # a batch of another shape while the graph is active (the ragged last batch of an epoch: the loaders, like the reference's
+    # DataLoader, have no drop_last) takes one eager step at the right position of the dropout / Adam streams -- also the
+    # 1-row remainder that copy_ would silently broadcast -- and the checkpoint written in graph mode carries the real steps
+    t2.capture_train_step(batches[0])
+    seq = [batches[1], tuple(x[:5] for x in batches[2]), batches[3], tuple(x[:1] for x in batches[4]), batches[5]]
+    e2 = [t1.train_step(b).item() for b in seq]
+    g2 = [t2.train_step(b).item() for b in seq]
+    assert e2 == g2, (e2, g2)
+    sd1, sd2 = t1._create_state_dict(), t2._create_state_dict()
+    assert sd1["dropout_step"] == sd2["dropout_step"] == m1._step
+    for k_, st in sd1["optimizer_state_dict"]["state"].items():
+        assert float(st["step"]) == float(sd2["optimizer_state_dict"]["state"][k_]["step"])
+    t2.release_train_graph()
+    for (k, v1), (_, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(v1, v2), k
+    assert t1.train_step(nb).item() == t2.train_step(nb).item()
 
 
 @pytest.mark.parametrize("kind,V,Ln,d,nb,h,B", [("sas", 1200, 50, 128, 2, 2, 16),     # BASELINE configs[2] model shape
