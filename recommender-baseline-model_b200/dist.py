@@ -406,7 +406,8 @@ def shard_bert_model(model, group=None, capacity=None):
     create the optimizer; give ``GradSync`` only :func:`replicated_parameters`.  ``capacity`` = slots for labelled rows per rank in
     the loss exchange (None: all rows).  Dropout: the embedding site uses the common seed with global element indices, the body
     sites a rank-specific seed (independent masks per rank).  ``full_catalogue_topk`` of a sharded model goes through
-    :func:`sharded_model_topk`; the sampled-candidate paths are not wired."""
+    :func:`sharded_model_topk`, ``candidate_scores`` through :func:`sharded_candidate_scores`; ``forward`` (materialised logits)
+    stays single-GPU only."""
     import types
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     world = dist.get_world_size(group) if dist.is_initialized() else 1
@@ -436,12 +437,22 @@ def decorrelate_dropout(model, group=None):
     return model
 
 
+def _score_layer(model):
+    """(weight shard, bias shard or None, first global row of the shard) of the layer the catalogue is scored against:
+    BERT4Rec's untied ``out`` Linear (NN/models/bert.py:10), SASRec's item table itself (NN/models/sas_model/sas.py:110)."""
+    sh = model._shard
+    if hasattr(model, "out"):
+        return model.out.weight, model.out.bias, sh.out_begin
+    return model.sas.item_emb.weight, None, sh.tok_begin
+
+
 def sharded_model_topk(model, x, k: int = 10):
-    """Full-catalogue top-k of the last position for a model cut by :func:`shard_bert_model` (top-k eval): the last
-    hidden rows of all ranks' users are all-gathered ([B, d] per rank), every rank runs the fused scoring + top-k on ITS rows of
-    the output layer with GLOBAL item ids, the per-shard lists are exchanged with an all-to-all by user range (each rank receives
-    the lists of its own users only: k * 12 B per user and shard) and merged under the single-GPU order rule (score desc, id asc),
-    so the result equals the unsharded model's.  Every rank must pass the same number of users."""
+    """Full-catalogue top-k of the last position for a model cut by :func:`shard_bert_model` / :func:`shard_sas_model`
+    (top-k eval): the last hidden rows of all ranks' users are all-gathered ([B, d] per rank), every rank runs
+    the fused scoring + top-k on ITS rows of the scored layer with GLOBAL item ids, the per-shard lists are exchanged with an
+    all-to-all by user range (each rank receives the lists of its own users only: k * 12 B per user and shard) and merged
+    under the single-GPU order rule (score desc, id asc), so the result equals the unsharded model's.  Every rank must pass
+    the same number of users."""
     from . import ops
     sh = model._shard
     group, world, rank = sh.group, sh.world, sh.rank
@@ -452,10 +463,10 @@ def sharded_model_topk(model, x, k: int = 10):
         dist.all_gather_into_tensor(h_all, h, group=group)
     else:
         h_all = h
-    w, b = model.out.weight, model.out.bias
-    lo = 1 if sh.out_begin == 0 else 0  # row 0 of the output layer is the padding id, not an item
+    w, b, begin = _score_layer(model)
+    lo = 1 if begin == 0 else 0  # row 0 is the padding id, not an item
     if w.shape[0] > lo:
-        vals, ids = ops.score_topk(h_all, w, b, lo, w.shape[0], k, id_offset=sh.out_begin)
+        vals, ids = ops.score_topk(h_all, w, b, lo, w.shape[0], k, id_offset=begin)
     else:
         vals = torch.full((world * B, k), float("-inf"), device=h.device)
         ids = torch.full((world * B, k), -1, device=h.device, dtype=torch.int64)
@@ -465,3 +476,129 @@ def sharded_model_topk(model, x, k: int = 10):
     dist.all_to_all_single(rv, vals.contiguous(), group=group)  # chunk s of the result = shard s's lists for MY users
     dist.all_to_all_single(ri, ids.contiguous(), group=group)
     return ops.topk_merge(rv.view(world, B, k), ri.view(world, B, k))
+
+
+# ------------------------------------------------------- sampled-candidate scoring / SASRec pos-neg scoring, sharded table
+def owned_local_ids(ids: torch.Tensor, v_begin: int, v_end: int):
+    """(local row index, owned mask) of global item ids against the row block [v_begin, v_end): rows of other blocks (and
+    nothing else) are redirected to local row 0 with ``owned = False`` -- their contribution is multiplied by zero."""
+    owned = (ids >= v_begin) & (ids < v_end)
+    return torch.where(owned, ids - v_begin, torch.zeros_like(ids)), owned
+
+
+def sharded_candidate_scores(model, x, candidates):
+    """``scores[u, c] = <table[cand[u, c]], h_last[u]> (+ bias)`` (NN/models/sas_model/sas.py:110-114, NN/trainers/bert.py:47-49)
+    for a row-sharded model: hidden rows and candidate ids of all ranks are all-gathered, every rank scores the candidates whose
+    rows it holds (``rbm_candidate_scores``; the others count as exact zeros), and a reduce-scatter returns each rank the
+    scores of its own users -- one non-zero addend per element, so the value equals the unsharded model's bit for bit."""
+    from . import ops
+    sh = model._shard
+    group, world = sh.group, sh.world
+    h = model.last_hidden(x).contiguous()
+    cand = model._device_long(candidates)
+    B, d = h.shape
+    if world > 1:
+        h_all = torch.empty(world * B, d, device=h.device, dtype=h.dtype)
+        c_all = torch.empty(world * B, cand.shape[1], device=h.device, dtype=cand.dtype)
+        dist.all_gather_into_tensor(h_all, h, group=group)
+        dist.all_gather_into_tensor(c_all, cand, group=group)
+    else:
+        h_all, c_all = h, cand
+    w, b, begin = _score_layer(model)
+    loc, owned = owned_local_ids(c_all, begin, begin + w.shape[0])
+    part = ops.candidate_scores(h_all, w, b, loc) * owned.to(torch.float32)
+    if world == 1:
+        return part
+    out = torch.empty(B, cand.shape[1], device=h.device, dtype=torch.float32)
+    dist.reduce_scatter_tensor(out, part.contiguous(), op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
+class ShardedSasScoreFn(torch.autograd.Function):
+    """``pos/neg logits = <f, table[pos]>, <f, table[neg]>`` (NN/models/sas_model/sas.py:93-100) with the item table row-sharded
+    and the sequences data-parallel.  Forward: feature rows and both id arrays are all-gathered, each rank takes the dot
+    products of the ids it owns (``rbm_sas_score_fwd`` on redirected local ids, masked), reduce-scatter back to the owners of
+    the sequences.  Backward: the logit gradients are all-gathered; ``df`` shares (``rbm_sas_score_bwd`` with the gradients of
+    ids the rank does not own set to zero) are reduce-scattered; the table-shard gradient is the deterministic
+    sort/segment-reduce over the gathered rows with the not-owned positions keyed to the skipped row.  ``grad_unscale`` as in
+    :class:`ShardedEmbedFn`."""
+
+    @staticmethod
+    def forward(ctx, f, table_shard, pos, neg, v_begin, group, grad_unscale):
+        from . import ops
+        lib = L.load()
+        L.require_cuda(f, table_shard, pos, neg)
+        world = dist.get_world_size(group) if dist.is_initialized() else 1
+        f2 = f.reshape(-1, f.shape[-1]).contiguous()
+        n, d = f2.shape
+        pos, neg = pos.reshape(-1).contiguous(), neg.reshape(-1).contiguous()
+        if world > 1:
+            f_all = torch.empty(world * n, d, device=f.device, dtype=torch.float32)
+            p_all, n_all = torch.empty(world * n, device=f.device, dtype=pos.dtype), torch.empty(world * n, device=f.device, dtype=neg.dtype)
+            dist.all_gather_into_tensor(f_all, f2, group=group)
+            dist.all_gather_into_tensor(p_all, pos, group=group)
+            dist.all_gather_into_tensor(n_all, neg, group=group)
+        else:
+            f_all, p_all, n_all = f2, pos, neg
+        v_end = int(v_begin) + table_shard.shape[0]
+        pl_, po = owned_local_ids(p_all, int(v_begin), v_end)
+        nl_, no = owned_local_ids(n_all, int(v_begin), v_end)
+        pl = torch.empty(world * n, device=f.device, dtype=torch.float32)
+        nl = torch.empty(world * n, device=f.device, dtype=torch.float32)
+        check(lib.rbm_sas_score_fwd(ptr(f_all), ptr(table_shard), ptr(pl_), ptr(nl_), ptr(pl), ptr(nl), world * n, d, stream()), "sas_score_fwd")
+        count_launches()
+        both = torch.stack([pl * po.to(torch.float32), nl * no.to(torch.float32)], 1)  # [world*n, 2]
+        if world > 1:
+            mine = torch.empty(n, 2, device=f.device, dtype=torch.float32)
+            dist.reduce_scatter_tensor(mine, both.contiguous(), op=dist.ReduceOp.SUM, group=group)
+        else:
+            mine = both
+        ctx.save_for_backward(f_all, table_shard, p_all, n_all, pl_, nl_, po, no)
+        ctx.meta = (f.shape, n, d, int(v_begin), v_end, group, world, float(grad_unscale))
+        return mine[:, 0].reshape(f.shape[:-1]), mine[:, 1].reshape(f.shape[:-1])
+
+    @staticmethod
+    def backward(ctx, dpl, dnl):
+        from . import ops
+        lib = L.load()
+        f_all, table_shard, p_all, n_all, pl_, nl_, po, no = ctx.saved_tensors
+        fshape, n, d, v_begin, v_end, group, world, unscale = ctx.meta
+        g = torch.stack([dpl.reshape(-1), dnl.reshape(-1)], 1).contiguous().float()
+        if world > 1:
+            g_all = torch.empty(world * n, 2, device=g.device, dtype=torch.float32)
+            dist.all_gather_into_tensor(g_all, g, group=group)
+        else:
+            g_all = g
+        dp = (g_all[:, 0] * po.to(torch.float32)).contiguous()
+        dn = (g_all[:, 1] * no.to(torch.float32)).contiguous()
+        df_all = torch.empty_like(f_all)
+        check(lib.rbm_sas_score_bwd(ptr(table_shard), ptr(pl_), ptr(nl_), ptr(dp), ptr(dn), ptr(df_all), world * n, d, stream()), "sas_score_bwd")
+        count_launches()
+        if world > 1:
+            df = torch.empty(n, d, device=g.device, dtype=torch.float32)
+            dist.reduce_scatter_tensor(df, df_all, op=dist.ReduceOp.SUM, group=group)
+        else:
+            df = df_all
+        rows = table_shard.shape[0]
+        dtable = torch.zeros(rows, d, device=g.device, dtype=torch.float32)
+        ops.scatter_add_sorted_(dtable, shard_keys(p_all, v_begin, v_end), f_all, dp, 1.0 / unscale, padding_idx=rows, vocab=rows + 1)
+        ops.scatter_add_sorted_(dtable, shard_keys(n_all, v_begin, v_end), f_all, dn, 1.0 / unscale, padding_idx=rows, vocab=rows + 1)
+        return df.view(fshape), dtable, None, None, None, None, None
+
+
+def shard_sas_model(model, group=None):
+    """Cut ``sas.item_emb.weight [V+1, d]`` of a SASRec model down to this rank's row block, in place: the input
+    lookup goes through :func:`sharded_embedding`, the pos/neg scoring through :class:`ShardedSasScoreFn`, ``predict`` through
+    :func:`sharded_candidate_scores` and ``full_catalogue_topk`` through :func:`sharded_model_topk`; sequences stay
+    data-parallel, ``GradSync(replicated_parameters(model))`` averages the dense body.  Build the model identically on every
+    rank first (same torch seed), shard, then create the optimizer."""
+    import types
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    emb = model.sas.item_emb
+    rows = emb.weight.shape[0]
+    b, e = shard_range(rows, rank, world)
+    emb.weight = torch.nn.Parameter(emb.weight.data[b:e].clone())
+    emb.weight._rbm_sharded = True
+    model._shard = types.SimpleNamespace(group=group, rank=rank, world=world, tok_begin=b, tok_rows=rows, capacity=None, overflow=None)
+    return model

@@ -193,7 +193,9 @@ class BERTModel(BaseModel):
 
     def candidate_scores(self, x, candidates):
         """scores[:, -1, :].gather(1, candidates) of NN/trainers/bert.py:47-49, scoring only the candidates."""
-        self._unsharded_only("candidate_scores")
+        if getattr(self, "_shard", None) is not None:
+            from ..dist import sharded_candidate_scores
+            return sharded_candidate_scores(self, x, candidates)
         return ops.candidate_scores(self.last_hidden(x), self.out.weight, self.out.bias, self._device_long(candidates))
 
     def full_catalogue_topk(self, x, k=10):

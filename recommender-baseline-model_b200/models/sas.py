@@ -64,7 +64,15 @@ class SASModel(BaseModel):
         p = sas.p if train else 0.0
         seed = self.dropout_seed
         base = self._next_site_base() if train else 0
-        x = ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base)
+        sh = getattr(self, "_shard", None)
+        if sh is None:
+            x = ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base)
+        else:  # row-sharded item table (rbm_b200.dist.shard_sas_model): common seed + global element indices for this site,
+            #    a rank-specific seed for the body sites
+            from ..dist import sharded_embedding
+            x = sharded_embedding(seq, sas.item_emb.weight, sas.pos_emb.weight, sh.tok_begin, sh.tok_rows, float(d ** 0.5), 1, p, seed,
+                                  base, sh.group, grad_unscale=float(sh.world))
+            seed = (seed + (sh.rank + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         scale = math.sqrt(1.0 / (d // h))
         for b in range(len(sas.attention_layers)):
             s = base + 1 + 3 * b
@@ -85,21 +93,44 @@ class SASModel(BaseModel):
     def forward(self, log_seqs, pos_seqs, neg_seqs):  # for training
         """NN/models/sas_model/sas.py:90-105 -> (pos_logits, neg_logits) [B, L]."""
         f = self.log2feats(log_seqs)
+        sh = getattr(self, "_shard", None)
+        if sh is not None:
+            from ..dist import ShardedSasScoreFn
+            return ShardedSasScoreFn.apply(f, self.sas.item_emb.weight, self._device_long(pos_seqs), self._device_long(neg_seqs),
+                                           sh.tok_begin, sh.group, float(sh.world))
         return ops.sas_scores(f, self.sas.item_emb.weight, self._device_long(pos_seqs), self._device_long(neg_seqs))
 
     def loss(self, log_seqs, pos_seqs, neg_seqs):
         """BCE part of SASTrainer.calculate_loss NN/trainers/sas.py:34-49."""
         pos = self._device_long(pos_seqs)
         pl, nl = self.forward(log_seqs, pos, neg_seqs)
-        return ops.bce_pair_loss(pl, nl, pos)
+        loss = ops.bce_pair_loss(pl, nl, pos)
+        sh = getattr(self, "_shard", None)
+        if sh is not None and sh.world > 1:
+            # data-parallel sequences: the reference's loss is the mean over the live positions of the WHOLE batch
+            # (NN/trainers/sas.py:40-49).  Value: count-weighted mean of the ranks' means.  Gradient: this rank's share,
+            # times the world size (GradSync averages the body gradients; the sharded table divides it out again).
+            import torch.distributed as dist
+            cnt = (pos != 0).sum().to(torch.float32).reshape(1)
+            both = torch.cat([loss.detach().reshape(1) * cnt, cnt])
+            dist.all_reduce(both, group=sh.group)
+            share = loss * (cnt / both[1] * sh.world).reshape(())
+            loss = (both[0] / both[1]).reshape(()) + (share - share.detach())
+        return loss
 
     def last_hidden(self, log_seqs):
         return self.log2feats(log_seqs)[:, -1, :]
 
     def predict(self, log_seqs, item_indices):  # for inference
         """NN/models/sas_model/sas.py:107-118 -> [B, C]."""
+        if getattr(self, "_shard", None) is not None:
+            from ..dist import sharded_candidate_scores
+            return sharded_candidate_scores(self, log_seqs, item_indices)
         return ops.candidate_scores(self.last_hidden(log_seqs), self.sas.item_emb.weight, None, self._device_long(item_indices))
 
     def full_catalogue_topk(self, log_seqs, k=10):
         """Top-k items (ids 1..V), (score desc, id asc); the [B, V, d] gather of ``predict`` is never built (K19-K21)."""
+        if getattr(self, "_shard", None) is not None:
+            from ..dist import sharded_model_topk
+            return sharded_model_topk(self, log_seqs, k)
         return ops.score_topk(self.last_hidden(log_seqs), self.sas.item_emb.weight, None, 1, self.sas.item_num + 1, k)

@@ -115,6 +115,57 @@ def _worker(rank, world, port, q):
         owned[tok_all[keys < hi_t - lo_t]] = 1
         dist.all_reduce(owned)
         assert owned[0] == 0 and set(torch.nonzero(owned).flatten().tolist()) == {1, 3, 5, 11, 12, 22} and int(owned.max()) == 1
+        # ---- sampled-candidate scoring / SASRec pos-neg scoring against a row-sharded table (CPU twin of
+        #      dist.sharded_candidate_scores / ShardedSasScoreFn: the dot products are CUDA kernels, the exchange is this):
+        #      owned ids -> local rows, the rest -> row 0 with a zero mask; the sum over ranks has ONE non-zero addend per element
+        torch.manual_seed(13)
+        Vc, dc2, Bc, Cc = 41, 6, 5, 7
+        table = torch.randn(Vc, dc2)
+        bias_c = torch.randn(Vc)
+        h_glob = torch.randn(world * Bc, dc2)
+        cand_glob = torch.randint(0, Vc, (world * Bc, Cc))
+        lo_c, hi_c = rd.shard_range(Vc, rank, world)
+        loc, own = rd.owned_local_ids(cand_glob, lo_c, hi_c)
+        assert bool(((loc >= 0) & (loc < hi_c - lo_c)).all()) and bool((loc[~own] == 0).all())
+        assert torch.equal(loc[own] + lo_c, cand_glob[own])
+        shard_t, shard_b = table[lo_c:hi_c], bias_c[lo_c:hi_c]
+        part = ((shard_t[loc] * h_glob.unsqueeze(1)).sum(-1) + shard_b[loc]) * own.float()
+        cnt_own = own.long().clone()
+        dist.all_reduce(cnt_own)
+        assert bool((cnt_own == 1).all())  # every candidate is owned by exactly one rank
+        mine = torch.empty(Bc, Cc)
+        dist.reduce_scatter_tensor(mine, part.contiguous())
+        ref_c = (table[cand_glob] * h_glob.unsqueeze(1)).sum(-1) + bias_c[cand_glob]
+        assert torch.equal(mine, ref_c[rank * Bc:(rank + 1) * Bc])  # one non-zero addend: bit for bit
+        # ---- top-k list exchange by user range (dist.sharded_model_topk): rank s holds the lists of ALL users against shard s;
+        #      all_to_all hands rank r the lists of ITS users from every shard, in shard order
+        Ut, kt = 4, 3
+        vals_s = torch.arange(world * Ut * kt, dtype=torch.float32).reshape(world * Ut, kt) + 1000 * rank
+        recv = torch.empty_like(vals_s)
+        dist.all_to_all_single(recv, vals_s.contiguous())
+        recv = recv.view(world, Ut, kt)
+        for s_ in range(world):
+            expect = torch.arange(world * Ut * kt, dtype=torch.float32).reshape(world * Ut, kt)[rank * Ut:(rank + 1) * Ut] + 1000 * s_
+            assert torch.equal(recv[s_], expect)
+        # ---- sharded SASRec loss (models/sas.py): value = count-weighted mean of the ranks' means = the global mean;
+        #      gradient = this rank's share x world (GradSync divides by world)
+        z = torch.randn(world * 9)
+        live_g = torch.rand(world * 9) < 0.6
+        live_g[0] = True
+        zl = z[rank * 9:(rank + 1) * 9].clone().requires_grad_(True)
+        ll_ = live_g[rank * 9:(rank + 1) * 9]
+        l_loc = torch.nn.functional.softplus(-zl[ll_]).mean() if bool(ll_.any()) else zl.sum() * 0
+        cnt_l = ll_.sum().float().reshape(1)
+        both = torch.cat([l_loc.detach().reshape(1) * cnt_l, cnt_l])
+        dist.all_reduce(both)
+        share = l_loc * (cnt_l / both[1] * world).reshape(())
+        l_glob = (both[0] / both[1]).reshape(()) + (share - share.detach())
+        zg = z.clone().requires_grad_(True)
+        ref_l = torch.nn.functional.softplus(-zg[live_g]).mean()
+        ref_l.backward()
+        l_glob.backward()
+        assert abs(float(l_glob) - float(ref_l)) < 1e-6
+        assert torch.allclose(zl.grad / world, zg.grad[rank * 9:(rank + 1) * 9], atol=1e-7)
         q.put((rank, "ok"))
     except Exception as ex:  # noqa
         import traceback

@@ -182,6 +182,55 @@ def _worker(rank, world, port, q):
             sv, si = sh_e.full_catalogue_topk(torch.from_numpy(ev_tok[sls]), 10)
         assert torch.equal(si, fi[sls]), (si, fi[sls])
         assert torch.allclose(sv, fv[sls], rtol=1e-6, atol=1e-6)
+        # sampled-candidate scores of the sharded BERT4Rec model == the unsharded model's, bit for bit
+        cand_b = torch.from_numpy(rs_.randint(1, Vs + 1, size=(world * Bs, 21)).astype(np.int64))
+        with torch.no_grad():
+            cs_full = full_e.candidate_scores(torch.from_numpy(ev_tok), cand_b)
+            cs_sh = sh_e.candidate_scores(torch.from_numpy(ev_tok[sls]), cand_b[sls])
+        assert torch.equal(cs_sh, cs_full[sls]), (cs_sh - cs_full[sls]).abs().max()
+        # SASRec with the item table row-sharded (shard_sas_model): one optimisation step on the ranks' own batches == the
+        # single-GPU model on the concatenated batch (loss 1e-5; every gradient 1e-3 of scale), predict bit for bit, top-10 ids exactly
+        from rbm_b200.dist import shard_sas_model
+        Vq, Lq, Bq, dq = 611, 20, 5, 64
+        a_q = SimpleNamespace(model_code="sas", num_items=Vq, max_len=Lq, device=dev, sas_hidden_units=dq, sas_num_blocks=2, sas_heads=2,
+                              sas_dropout=0.0, l2_emb=0.0, optimizer="Adam", lr=1e-3, weight_decay=0, momentum=None, decay_step=10, gamma=1.0,
+                              num_epochs=1, metric_ks=[10], best_metric="NDCG@10", train_batch_size=Bq, resume_path=None)
+        rq = np.random.RandomState(9)
+        seq_q = rq.randint(1, Vq + 1, size=(world * Bq, Lq)).astype(np.int64)
+        seq_q[:, :3] = 0
+        seq_q[Bq:, :9] = 0  # unequal numbers of live positions per rank
+        pos_q = np.where(seq_q != 0, rq.randint(1, Vq + 1, size=seq_q.shape), 0)
+        neg_q = np.where(seq_q != 0, rq.randint(0, Vq + 1, size=seq_q.shape), 0)
+        torch.manual_seed(21)
+        full_q = rbm_b200.model_factory(a_q).to(dev)
+        torch.manual_seed(21)
+        sh_q = shard_sas_model(rbm_b200.model_factory(a_q).to(dev))
+        full_q.train(); sh_q.train()
+        lq_full = full_q.loss(seq_q, pos_q, neg_q)
+        lq_full.backward()
+        slq = slice(rank * Bq, (rank + 1) * Bq)
+        lq_sh = sh_q.loss(seq_q[slq], pos_q[slq], neg_q[slq])  # value: the global mean; gradient: this rank's share x world
+        assert abs(lq_sh.item() - lq_full.item()) < 1e-5 * abs(lq_full.item()), (lq_sh.item(), lq_full.item())
+        lq_sh.backward()
+        gs_q = GradSync(replicated_parameters(sh_q))
+        gs_q.allreduce_grads()
+        gq = {k: p.grad for k, p in full_q.named_parameters()}
+        gscale_q = max(float(g_.abs().max()) for g_ in gq.values())
+        for k, p in sh_q.named_parameters():
+            ref_g = gq[k]
+            got_g = p.grad
+            if getattr(p, "_rbm_sharded", False):
+                b0, e0 = shard_range(ref_g.shape[0], rank, world)
+                ref_g = ref_g[b0:e0]
+            err = float((got_g - ref_g).abs().max())
+            assert err <= 1e-3 * max(float(ref_g.abs().max()), 1e-3 * gscale_q), (k, err, float(ref_g.abs().max()))
+        full_q.eval(); sh_q.eval()
+        cand_q = rq.randint(1, Vq + 1, size=(world * Bq, 17)).astype(np.int64)
+        with torch.no_grad():
+            pq_full, pq_sh = full_q.predict(seq_q, cand_q), sh_q.predict(seq_q[slq], cand_q[slq])
+            tq_full, tq_sh = full_q.full_catalogue_topk(seq_q, 10), sh_q.full_catalogue_topk(seq_q[slq], 10)
+        assert torch.equal(pq_sh, pq_full[slq]), (pq_sh - pq_full[slq]).abs().max()
+        assert torch.equal(tq_sh[1], tq_full[1][slq]) and torch.equal(tq_sh[0], tq_full[0][slq])
         # data-parallel step replayed from CUDA graphs (two graphs + one eager all-reduce) == the eager data-parallel step,
         # bit for bit, dropout on
         import copy
