@@ -11,6 +11,7 @@
 #include "common.cuh"
 #include "mma_tiles.cuh"
 #include "ce_tc.cuh"
+#include "ce_wide.cuh"
 
 namespace {
 
@@ -461,13 +462,15 @@ static size_t ce_smax(int64_t cap, int V1) {
   size_t S = (size_t)dw_splits(cap, V1, 1);
   if (S < (size_t)dw_splits(cap, V1, 8)) S = (size_t)dw_splits(cap, V1, 8);
   if (S < (size_t)rbm_ce_tc_dw_splits(cap, V1)) S = (size_t)rbm_ce_tc_dw_splits(cap, V1);
+  if (S < (size_t)rbm_ce_wide_dw_splits(cap, V1)) S = (size_t)rbm_ce_wide_dw_splits(cap, V1);
   return S;
 }
 static size_t ce_off_partw(int64_t cap) { return ((size_t)rbm_cdiv(cap, 16) + 3) & ~(size_t)3; }
 static size_t ce_off_extra(int64_t cap, int V1, int d) { return (ce_off_partw(cap) + ce_smax(cap, V1) * ((size_t)V1 * d + V1) + 3) & ~(size_t)3; }
 
 extern "C" size_t rbm_ce_ws_bytes(int64_t cap, int V1, int d) {
-  return (ce_off_extra(cap, V1, d) + rbm_ce_tc_ws_floats(cap, V1, d)) * sizeof(float) + 64;
+  size_t extra = rbm_ce_tc_ws_floats(cap, V1, d), wide = rbm_ce_wide_ws_floats(cap, V1, d);
+  return (ce_off_extra(cap, V1, d) + (extra > wide ? extra : wide)) * sizeof(float) + 64;
 }
 
 static int ce_check(const char* name, int64_t cap, int V1, int d) {
@@ -489,6 +492,14 @@ extern "C" int rbm_ce_fwd(const float* h, const int32_t* rows, const int64_t* tg
     int rc = rbm_ce_tc_fwd(h, rows, tgt, count, w, bias, lse, (float*)ws, cap, V1, d, (float*)ws + ce_off_extra(cap, V1, d), &nblk_tc, st);
     if (rc) return rc;
     ce_loss_finalize_kernel<<<1, 256, 0, st>>>((const float*)ws, nblk_tc, count, loss);
+    RBM_LAUNCH_CHECK("rbm_ce_fwd(finalize)");
+    return 0;
+  }
+  if (rbm_ce_wide_supported(V1, d, h, w)) {  // d = 128 / 256: split-fp16 tensor path (ce_wide.cu)
+    int nblk_w = 0;
+    int rc = rbm_ce_wide_fwd(h, rows, tgt, count, w, bias, lse, (float*)ws, cap, V1, d, (float*)ws + ce_off_extra(cap, V1, d), &nblk_w, st);
+    if (rc) return rc;
+    ce_loss_finalize_kernel<<<1, 256, 0, st>>>((const float*)ws, nblk_w, count, loss);
     RBM_LAUNCH_CHECK("rbm_ce_fwd(finalize)");
     return 0;
   }
@@ -520,6 +531,18 @@ extern "C" int rbm_ce_bwd(const float* h, const int32_t* rows, const int64_t* tg
     float* part_b = part_w + (size_t)S * V1 * d;
     int rc = rbm_ce_tc_bwd(h, rows, tgt, count, w, bias, lse, dloss, dh_full, part_w, part_b, S, cap, V1, d,
                            (float*)ws + ce_off_extra(cap, V1, d), st);
+    if (rc) return rc;
+    int64_t n = (int64_t)V1 * d;
+    ce_reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, st>>>(part_w, dw, n, S);
+    ce_reduce_splits_kernel<<<(unsigned)rbm_cdiv(V1, 256), 256, 0, st>>>(part_b, db, V1, S);
+    RBM_LAUNCH_CHECK("rbm_ce_bwd(reduce)");
+    return 0;
+  }
+  if (rbm_ce_wide_supported(V1, d, h, w)) {  // d = 128 / 256: split-fp16 tensor path (ce_wide.cu)
+    const int S = rbm_ce_wide_dw_splits(cap, V1);
+    float* part_b = part_w + (size_t)S * V1 * d;
+    int rc = rbm_ce_wide_bwd(h, rows, tgt, count, w, bias, lse, dloss, dh_full, part_w, part_b, S, cap, V1, d,
+                             (float*)ws + ce_off_extra(cap, V1, d), st);
     if (rc) return rc;
     int64_t n = (int64_t)V1 * d;
     ce_reduce_splits_kernel<<<(unsigned)rbm_cdiv(n, 256), 256, 0, st>>>(part_w, dw, n, S);

@@ -239,6 +239,7 @@ def _worker(rank, world, port, q):
                    (torch.from_numpy(np.ascontiguousarray(tokm[sl][::-1])).to(dev), torch.from_numpy(np.ascontiguousarray(lab[sl][::-1])).to(dev))]
         results = []
         for mode in ("eager", "split"):
+            torch.manual_seed(0)  # the models' dropout seed defaults to torch.initial_seed() at construction time
             m = rbm_b200.model_factory(args)
             t = rbm_b200.trainer_factory(args, m, None, None, None, None)
             t.dist_sync = GradSync(m.parameters())
@@ -274,4 +275,6 @@ def test_two_gpu_nccl_data_parallel_and_sharded_topk():
     res = [q.get(timeout=280) for _ in procs]
     for p in procs:
         p.join(timeout=30)
+    for r in res:
+        print("rank", r[0], r[1])  # the whole traceback (pytest shortens the assertion message)
     assert all(r[1] == "ok" for r in res), res
