@@ -54,7 +54,9 @@ struct WideArgs {
   float *st_m, *st_l, *st_t;  // FWD: per unit and resident row: running max, sum-exp (log2 domain), target logit
   float* dpart;               // DH: [unit][128][d] unscaled partial dH;  DW: part_w [S][V1][d]
   float* part_b;              // DW: [S][V1]
-  int V1, d, KB, NV, nstage, npass, S, bias_vec;
+  const __half *r_hi, *r_lo;  // pre-split resident matrix ([r_rows, d] fp16): hidden rows (FWD / DH) or the weight (DW)
+  int64_t r_rows;
+  int V1, d, KB, NV, nstage, npass, S, bias_vec, pair;
 };
 
 // vocabulary splits per row tile: the split count that fills whole waves of 148 SMs best with at most UMAX units
@@ -125,19 +127,27 @@ __device__ __forceinline__ void split_pack16(const float (&g)[16], uint32_t (&hi
 }
 
 // --------------------------------------------------------------------------------------------------- the kernel
-// TMEM columns: D [0, d) | group g at 256 + 128 g: S [+0, +NV) fp32, G hi [+64, +64 + NV/2), G lo [+96, +96 + NV/2)
-// SMEM: resident hi (KB blocks of 16 KB) | resident lo | nstage x { streamed hi (KB blocks of NV x 128 B) | streamed lo }
+// The resident operand's hi half lives in TENSOR MEMORY (16-bit A operand: two K elements per 32-bit column), written once
+// per unit by the epilogue threads from the pre-split global copy, so the score products read only the streamed tile from
+// shared memory: with both operands in shared memory a 128 x NV x 16 instruction fetches 4 KB of A + 32 NV bytes of B and
+// measured ~70 cycles whatever NV (~80 B/cycle of operand fetch), three times the tensor floor of NV/2 cycles.  The lo
+// half follows into TMEM where columns are left (FWD: no accumulator; d = 128); at d = 256 in DH / DW it stays in shared
+// memory (64 KB, K-major) and only the third pass pays the shared-memory fetch.
+//   TMEM columns: R hi [0, d/2) | group g at 128 + 64 g: S [+0, +NV) fp32, overwritten by G hi [+0, +NV/2) | G lo
+//                 [+NV/2, +NV) | D [256, 256 + d)   (FWD, no D: R lo [256, 256 + d/2);  d = 128: R lo [384, 448))
+//   SMEM: { resident lo: KB blocks of 16 KB, unless it is in TMEM } | nstage x { streamed hi (KB blocks of NV x 128 B) | lo }
 template <int MODE>
 __global__ void __launch_bounds__(64 + 32 * NSW, 1)
-ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant__ CUtensorMap mapRl, const __grid_constant__ CUtensorMap mapSh,
-               const __grid_constant__ CUtensorMap mapSl, const WideArgs a) {
+ce_wide_kernel(const __grid_constant__ CUtensorMap mapRl, const __grid_constant__ CUtensorMap mapSh, const __grid_constant__ CUtensorMap mapSl,
+               const WideArgs a) {
   extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], s_full[2], g_full[2], r_bar, done_bar;
+  __shared__ __align__(8) uint64_t full_bar[4], empty_bar[4], s_full[2], g_full[2], r_bar, rt_bar, done_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ __align__(16) float lse_s[2][64], tgt_s[2][64];  // DW: statistics of the chunk's streamed (hidden) rows, per group
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int count = *a.count;
   const int d = a.d, KB = a.KB, NV = a.NV, ns = a.nstage, V1 = a.V1;
+  const bool lo_tmem = (MODE == MODE_FWD) || d <= 128;
   // ---- unit: resident tile + chunk range [c_begin, c_end) step c_step of the streamed side
   int r_tile, c_begin, c_end, c_step, unit;
   if (MODE == MODE_DW) {
@@ -160,7 +170,7 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
   const uint32_t sblk = (uint32_t)NV * 128u;              // one streamed K-block
   const uint32_t stage_bytes = 2u * KB * sblk;            // hi blocks then lo blocks
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t sRh = smem_base, sRl = smem_base + (uint32_t)KB * RBLK, sSt = smem_base + 2u * KB * RBLK;
+  const uint32_t sRl = smem_base, sSt = smem_base + (lo_tmem ? 0u : (uint32_t)KB * RBLK);
   if (threadIdx.x == 0) {
     for (int s = 0; s < ns; ++s) {
       mbar_init(smem_u32(&full_bar[s]), 1);
@@ -171,6 +181,7 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
       mbar_init(smem_u32(&g_full[i]), NSW / 2);
     }
     mbar_init(smem_u32(&r_bar), 1);
+    mbar_init(smem_u32(&rt_bar), lo_tmem ? NSW : NSW / 2);
     mbar_init(smem_u32(&done_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -179,15 +190,14 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot;
-  const uint32_t tD = tmem, tG0 = tmem + 256;
+  const uint32_t tRh = tmem, tG0 = tmem + 128, tD = tmem + 256, tRl = tmem + ((MODE == MODE_FWD) ? 256 : 384);
 
   if (warp == 0) {
     // ------------------------------------------------------------------------------------------ TMA producer
     if (elect_one()) {
-      mbar_expect_tx(smem_u32(&r_bar), 2u * KB * RBLK);
-      for (int kb = 0; kb < KB; ++kb) {
-        tma_load_2d(sRh + kb * RBLK, &mapRh, smem_u32(&r_bar), kb * 64, r_tile * 128);
-        tma_load_2d(sRl + kb * RBLK, &mapRl, smem_u32(&r_bar), kb * 64, r_tile * 128);
+      if (!lo_tmem) {
+        mbar_expect_tx(smem_u32(&r_bar), (uint32_t)KB * RBLK);
+        for (int kb = 0; kb < KB; ++kb) tma_load_2d(sRl + kb * RBLK, &mapRl, smem_u32(&r_bar), kb * 64, r_tile * 128);
       }
       for (int n = 0; n < NL; ++n) {
         const int c = c_begin + n * c_step, s = n % ns;
@@ -204,20 +214,28 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
     // ------------------------------------------------------------------------------------------- MMA issuer
     if (elect_one()) {
       const uint32_t idS = make_idesc_f16(128, NV, 0), idU = make_idesc_f16(128, d, 1);
-      mbar_wait(smem_u32(&r_bar), 0);
+      mbar_wait(smem_u32(&rt_bar), 0);
+      if (!lo_tmem) mbar_wait(smem_u32(&r_bar), 0);
       tc_fence_after();
       // S[grp] = R . chunk^T : passes (R hi, C hi), (R hi, C lo), (R lo, C hi)
       auto scores = [&](int n) {
-        const uint32_t sa = sSt + (n % ns) * stage_bytes, tS = tG0 + (uint32_t)(n & 1) * 128;
+        const uint32_t sa = sSt + (n % ns) * stage_bytes, tS = tG0 + (uint32_t)(n & 1) * 64;
         uint32_t acc = 0;
         for (int pass = 0; pass < a.npass; ++pass) {
-          const uint32_t rb = pass == 2 ? sRl : sRh, cb = pass == 1 ? sa + KB * sblk : sa;
+          const uint32_t cb = pass == 1 ? sa + KB * sblk : sa;
           for (int kb = 0; kb < KB; ++kb) {
-            const uint64_t ad = make_sw128_desc(rb + kb * RBLK), bd = make_sw128_desc(cb + kb * sblk);
+            const uint64_t bd = make_sw128_desc(cb + kb * sblk);
+            if (pass == 2 && !lo_tmem) {
+              const uint64_t ad = make_sw128_desc(sRl + kb * RBLK);
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              umma_f16(tS, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idS, acc);
-              acc = 1;
+              for (int k = 0; k < 4; ++k) umma_f16(tS, ad + (uint64_t)(k * 2), bd + (uint64_t)(k * 2), idS, 1);
+            } else {
+              const uint32_t ta = (pass == 2 ? tRl : tRh) + (uint32_t)(kb * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_ts(tS, ta + (uint32_t)(k * 8), bd + (uint64_t)(k * 2), idS, acc);
+                acc = 1;
+              }
             }
           }
         }
@@ -230,7 +248,7 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
         mbar_wait(smem_u32(&g_full[grp]), (n >> 1) & 1);
         tc_fence_after();
         if (MODE != MODE_FWD) {
-          const uint32_t sa = sSt + s * stage_bytes, tGh = tG0 + (uint32_t)grp * 128 + 64, tGl = tGh + 32;
+          const uint32_t sa = sSt + s * stage_bytes, tGh = tG0 + (uint32_t)grp * 64, tGl = tGh + (uint32_t)(NV / 2);
           for (int pass = 0; pass < a.npass; ++pass) {
             const uint32_t ga = pass == 2 ? tGl : tGh, cb = pass == 1 ? sa + KB * sblk : sa;
             for (int ks = 0; ks < NV / 16; ++ks) {
@@ -242,6 +260,40 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
         }
         pend[grp] = -1;
       };
+      if (MODE == MODE_FWD && a.pair) {
+        // two chunks at a time, their k-steps interleaved: consecutive instructions accumulate into DIFFERENT score blocks
+        for (int n = 0; n < NL; n += 2) {
+          const bool two = n + 1 < NL;
+          if (n >= 2) {
+            mbar_wait(smem_u32(&g_full[0]), ((n >> 1) - 1) & 1);
+            if (two) mbar_wait(smem_u32(&g_full[1]), ((n >> 1) - 1) & 1);
+          }
+          mbar_wait(smem_u32(&full_bar[n % ns]), (n / ns) & 1);
+          if (two) mbar_wait(smem_u32(&full_bar[(n + 1) % ns]), ((n + 1) / ns) & 1);
+          tc_fence_after();
+          const uint32_t sa0 = sSt + (n % ns) * stage_bytes, sa1 = sSt + ((n + 1) % ns) * stage_bytes;
+          uint32_t acc = 0;
+          for (int pass = 0; pass < a.npass; ++pass) {
+            const uint32_t off = pass == 1 ? KB * sblk : 0u;
+            for (int kb = 0; kb < KB; ++kb) {
+              const uint64_t b0 = make_sw128_desc(sa0 + off + kb * sblk), b1 = make_sw128_desc(sa1 + off + kb * sblk);
+              const uint32_t ta = (pass == 2 ? tRl : tRh) + (uint32_t)(kb * 32);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                umma_f16_ts(tG0, ta + (uint32_t)(k * 8), b0 + (uint64_t)(k * 2), idS, acc);
+                if (two) umma_f16_ts(tG0 + 64, ta + (uint32_t)(k * 8), b1 + (uint64_t)(k * 2), idS, acc);
+                acc = 1;
+              }
+            }
+          }
+          umma_commit(smem_u32(&empty_bar[n % ns]));
+          umma_commit(smem_u32(&s_full[0]));
+          if (two) {
+            umma_commit(smem_u32(&empty_bar[(n + 1) % ns]));
+            umma_commit(smem_u32(&s_full[1]));
+          }
+        }
+      } else
       for (int n = 0; n < NL; ++n) {
         const int s = n % ns, grp = n & 1;
         if (pend[grp] >= 0) accum(grp);  // frees the group's column block (the tensor pipe runs in order)
@@ -270,10 +322,27 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
     const int gt = q * 32 + lane;  // thread index inside the group (= resident row; lane quarters in warp order 2,3,0,1)
     const int rl = gt;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const uint32_t tS = tG0 + lane_sel + (uint32_t)grp * 128, tGh = tS + 64, tGl = tS + 96;
+    const uint32_t tS = tG0 + lane_sel + (uint32_t)grp * 64, tGl = tS + (uint32_t)(NV / 2);
     const float sh = a.scales[0], sw = a.scales[1];
     const float c1 = RBM_LOG2E / (sh * sw);  // accumulator -> logit in the log2 domain
-    float* xch = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));  // resident region, reused after the MMAs
+    float* xch = reinterpret_cast<float*>(smem_raw + (sSt - smem_u32(smem_raw)));  // first stage, reused after the MMAs
+    // ---- resident rows -> tensor memory (group 0: hi half; group 1: lo half where it lives there)
+    if (grp == 0 || lo_tmem) {
+      const int64_t grow = (int64_t)r_tile * 128 + rl;
+      const uint4* src = reinterpret_cast<const uint4*>((grp == 0 ? a.r_hi : a.r_lo) + grow * d);
+      const bool inb = grow < a.r_rows;
+      const uint32_t dstc = (grp == 0 ? tRh : tRl) + lane_sel;
+      for (int c0 = 0; c0 < d / 2; c0 += 8) {  // 8 words = 16 fp16 = two 16-byte loads
+        uint32_t w8[8];
+        const uint4 x = inb ? src[c0 / 4] : make_uint4(0, 0, 0, 0), y = inb ? src[c0 / 4 + 1] : make_uint4(0, 0, 0, 0);
+        w8[0] = x.x; w8[1] = x.y; w8[2] = x.z; w8[3] = x.w; w8[4] = y.x; w8[5] = y.y; w8[6] = y.z; w8[7] = y.w;
+        tmem_st8(dstc + (uint32_t)c0, w8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rt_bar));
+    }
     if (MODE != MODE_DW) {
       const int r = r_tile * 128 + rl;
       const bool valid = r < count;
@@ -285,61 +354,69 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
         const int c = c_begin + n;
         mbar_wait(smem_u32(&s_full[grp]), (n >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int part = 0; part < NV / 16; ++part) {
-          const int v0 = c * NV + part * 16;
-          float bb[16];  // bias in the log2 domain (minus the row's log-sum-exp in DH); -inf beyond the vocabulary
-          if (v0 + 16 <= V1 && (a.bias == nullptr || a.bias_vec)) {
+        float sv[64];  // the chunk's scores of this row (DH: all of them are read before G overwrites the columns)
+        if (MODE == MODE_DH) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 t = a.bias ? ld4(a.bias + v0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
-              bb[j] = fmaf(t.x, RBM_LOG2E, -lse2); bb[j + 1] = fmaf(t.y, RBM_LOG2E, -lse2);
-              bb[j + 2] = fmaf(t.z, RBM_LOG2E, -lse2); bb[j + 3] = fmaf(t.w, RBM_LOG2E, -lse2);
-            }
-          } else {
+          for (int part = 0; part < 4; ++part)
+            if (part * 16 < NV) tmem_ld16(tS + (uint32_t)(part * 16), *reinterpret_cast<float(*)[16]>(&sv[part * 16]));
+        }
 #pragma unroll
-            for (int j = 0; j < 16; ++j) bb[j] = v0 + j < V1 ? fmaf(a.bias ? a.bias[v0 + j] : 0.f, RBM_LOG2E, -lse2) : -INFINITY;
-          }
-          float v[16];
-          tmem_ld16(tS + (uint32_t)(part * 16), v);
-          const uint32_t ts = (uint32_t)(tg - (int64_t)v0);  // this row's target column inside the slice, if < 16
-          const bool hit = __any_sync(0xffffffffu, ts < 16u);
-          if (MODE == MODE_FWD) {
-            if (part == NV / 16 - 1) {  // last read of this chunk's score block
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(smem_u32(&g_full[grp]));
-            }
-            float cm = -INFINITY;
+        for (int part = 0; part < 4; ++part) {
+          if (part * 16 < NV) {
+            const int v0 = c * NV + part * 16;
+            float bb[16];  // bias in the log2 domain (minus the row's log-sum-exp in DH); -inf beyond the vocabulary
+            if (v0 + 16 <= V1 && (a.bias == nullptr || a.bias_vec)) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              v[j] = fmaf(v[j], c1, bb[j]);
-              cm = fmaxf(cm, v[j]);
-            }
-            if (hit) {
+              for (int j = 0; j < 16; j += 4) {
+                const float4 t = a.bias ? ld4(a.bias + v0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+                bb[j] = fmaf(t.x, RBM_LOG2E, -lse2); bb[j + 1] = fmaf(t.y, RBM_LOG2E, -lse2);
+                bb[j + 2] = fmaf(t.z, RBM_LOG2E, -lse2); bb[j + 3] = fmaf(t.w, RBM_LOG2E, -lse2);
+              }
+            } else {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (ts == (uint32_t)j) tl = v[j];
+              for (int j = 0; j < 16; ++j) bb[j] = v0 + j < V1 ? fmaf(a.bias ? a.bias[v0 + j] : 0.f, RBM_LOG2E, -lse2) : -INFINITY;
             }
-            const float mn = fmaxf(m, cm);
-            if (mn > -INFINITY) {
-              float ps = 0.f;
+            float(&v)[16] = *reinterpret_cast<float(*)[16]>(&sv[part * 16]);
+            if (MODE == MODE_FWD) tmem_ld16(tS + (uint32_t)(part * 16), v);
+            const uint32_t ts = (uint32_t)(tg - (int64_t)v0);  // this row's target column inside the slice, if < 16
+            const bool hit = __any_sync(0xffffffffu, ts < 16u);
+            if (MODE == MODE_FWD) {
+              if ((part + 1) * 16 >= NV) {  // last read of this chunk's score block
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&g_full[grp]));
+              }
+              float cm = -INFINITY;
 #pragma unroll
-              for (int j = 0; j < 16; ++j) ps += ex2(v[j] - mn);
-              l = l * (m == -INFINITY ? 0.f : ex2(m - mn)) + ps;
-              m = mn;
-            }
-          } else {
-            uint32_t hi[8], lo[8];
+              for (int j = 0; j < 16; ++j) {
+                v[j] = fmaf(v[j], c1, bb[j]);
+                cm = fmaxf(cm, v[j]);
+              }
+              if (hit) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              float p = ex2(fmaf(v[j], c1, bb[j]));
-              if (hit && ts == (uint32_t)j) p -= 1.f;
-              v[j] = p * GSCALE;
+                for (int j = 0; j < 16; ++j)
+                  if (ts == (uint32_t)j) tl = v[j];
+              }
+              const float mn = fmaxf(m, cm);
+              if (mn > -INFINITY) {
+                float ps = 0.f;
+#pragma unroll
+                for (int j = 0; j < 16; ++j) ps += ex2(v[j] - mn);
+                l = l * (m == -INFINITY ? 0.f : ex2(m - mn)) + ps;
+                m = mn;
+              }
+            } else {
+              uint32_t hi[8], lo[8];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) {
+                float p = ex2(fmaf(v[j], c1, bb[j]));
+                if (hit && ts == (uint32_t)j) p -= 1.f;
+                v[j] = p * GSCALE;
+              }
+              split_pack16(v, hi, lo);
+              tmem_st8(tS + (uint32_t)(part * 8), hi);
+              tmem_st8(tGl + (uint32_t)(part * 8), lo);
             }
-            split_pack16(v, hi, lo);
-            tmem_st8(tGh + (uint32_t)(part * 8), hi);
-            tmem_st8(tGl + (uint32_t)(part * 8), lo);
           }
         }
         if (MODE == MODE_DH) {
@@ -350,9 +427,7 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
         }
       }
       if (MODE == MODE_FWD) {
-        // every chunk's scores have been read, hence every MMA has completed: the resident region is free -- once its TMA
-        // load has landed (a unit without chunks gets here before that)
-        mbar_wait(smem_u32(&r_bar), 0);
+        // every chunk's scores have been read, hence every MMA has completed and every stage is free
         named_bar_sync(7, NSW * 32);
         xch[(grp * 3 + 0) * 128 + rl] = m;
         xch[(grp * 3 + 1) * 128 + rl] = l;
@@ -404,27 +479,33 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
         named_bar_sync(1 + grp, 128);
         mbar_wait(smem_u32(&s_full[grp]), (n >> 1) & 1);
         tc_fence_after();
-#pragma unroll 1
-        for (int part = 0; part < NV / 16; ++part) {
-          float v[16], ls[16], tc[16];
+        float sv[64];
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 x = ld4(&lse_s[grp][part * 16 + j]), y = ld4(&tgt_s[grp][part * 16 + j]);
-            ls[j] = x.x; ls[j + 1] = x.y; ls[j + 2] = x.z; ls[j + 3] = x.w;
-            tc[j] = y.x; tc[j + 1] = y.y; tc[j + 2] = y.z; tc[j + 3] = y.w;
-          }
-          tmem_ld16(tS + (uint32_t)(part * 16), v);
-          uint32_t hi[8], lo[8];
+        for (int part = 0; part < 4; ++part)
+          if (part * 16 < NV) tmem_ld16(tS + (uint32_t)(part * 16), *reinterpret_cast<float(*)[16]>(&sv[part * 16]));
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            float p = ex2(fmaf(v[j], c1, b2) - ls[j]);
-            if (tc[j] == frow) p -= 1.f;
-            bsum += p;
-            v[j] = p * GSCALE;
+        for (int part = 0; part < 4; ++part) {
+          if (part * 16 < NV) {
+            float(&v)[16] = *reinterpret_cast<float(*)[16]>(&sv[part * 16]);
+            float ls[16], tc[16];
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 x = ld4(&lse_s[grp][part * 16 + j]), y = ld4(&tgt_s[grp][part * 16 + j]);
+              ls[j] = x.x; ls[j + 1] = x.y; ls[j + 2] = x.z; ls[j + 3] = x.w;
+              tc[j] = y.x; tc[j + 1] = y.y; tc[j + 2] = y.z; tc[j + 3] = y.w;
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              float p = ex2(fmaf(v[j], c1, b2) - ls[j]);
+              if (tc[j] == frow) p -= 1.f;
+              bsum += p;
+              v[j] = p * GSCALE;
+            }
+            split_pack16(v, hi, lo);
+            tmem_st8(tS + (uint32_t)(part * 8), hi);
+            tmem_st8(tGl + (uint32_t)(part * 8), lo);
           }
-          split_pack16(v, hi, lo);
-          tmem_st8(tGh + (uint32_t)(part * 8), hi);
-          tmem_st8(tGl + (uint32_t)(part * 8), lo);
         }
         tmem_st_wait();
         tc_fence_before();
@@ -433,12 +514,11 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRh, const __grid_constant_
       }
       mbar_wait(smem_u32(&done_bar), 0);
       tc_fence_after();
-      mbar_wait(smem_u32(&r_bar), 0);  // the resident tile's TMA load has landed: its region is reused below
       named_bar_sync(7, NSW * 32);
       xch[grp * 128 + rl] = bsum;
       named_bar_sync(7, NSW * 32);
       const float gscale = *a.dloss / (float)count;
-      const float wmul = gscale / (GSCALE * sh);  // D = sum G' . H' with G' = 2^14 G / gscale..., H' = sh H
+      const float wmul = gscale / (GSCALE * sh);  // D = sum (2^14 G) . (s_h H)
       float* pw = a.dpart + ((int64_t)blockIdx.y * V1 + vrow) * d;
       const int dc = d / 2;
       for (int c0 = grp * dc; c0 < (grp + 1) * dc; c0 += 16) {
@@ -616,11 +696,14 @@ struct Shape {
   int NV, ns, npass;
   size_t smem;
 };
-Shape pick_shape(int d) {
+// streamed rows per chunk, ring depth, shared memory: FWD (and every mode at d = 128) keeps both resident halves in tensor
+// memory -> all shared memory is ring; DH / DW at d = 256 keep the resident lo half (64 KB) in shared memory
+Shape pick_shape(int d, int mode) {
   Shape s;
-  s.NV = env_int("RBM_CE_WIDE_NV", d == 256 ? 48 : 64);
-  if (s.NV != 32 && s.NV != 48 && s.NV != 64) s.NV = d == 256 ? 48 : 64;
-  const size_t res = (size_t)2 * (d / 64) * RBLK, stage = (size_t)2 * (d / 64) * s.NV * 128;
+  const bool lo_tmem = mode == MODE_FWD || d <= 128;
+  s.NV = env_int(mode == MODE_FWD ? "RBM_CE_WIDE_NV_FWD" : "RBM_CE_WIDE_NV", lo_tmem ? 64 : 48);
+  if (s.NV != 32 && s.NV != 48 && s.NV != 64) s.NV = lo_tmem ? 64 : 48;
+  const size_t res = lo_tmem ? 0 : (size_t)(d / 64) * RBLK, stage = (size_t)2 * (d / 64) * s.NV * 128;
   int ns = (int)(((size_t)231000 - 1024 - res) / stage);
   s.ns = ns > 4 ? 4 : ns;
   s.npass = env_int("RBM_CE_WIDE_PASSES", 3) == 1 ? 1 : 3;
@@ -710,19 +793,20 @@ int rbm_ce_wide_fwd(const float* h, const int32_t* rows, const int64_t* tgt, con
   const int64_t cap128 = (cap + 127) / 128 * 128;
   const WideWs ws = carve(extra_ws, cap, V1, d);
   if (int rc = prepare(h, rows, count, w, cap, V1, d, ws, st)) return rc;
-  const Shape sh = pick_shape(d);
-  CUtensorMap mRh, mRl, mSh, mSl;
-  if (!encode_map(&mRh, ws.h_hi, cap128, d, 128) || !encode_map(&mRl, ws.h_lo, cap128, d, 128) || !encode_map(&mSh, ws.w_hi, V1, d, sh.NV) ||
-      !encode_map(&mSl, ws.w_lo, V1, d, sh.NV)) {
+  const Shape sh = pick_shape(d, MODE_FWD);
+  CUtensorMap mRl, mSh, mSl;
+  if (!encode_map(&mRl, ws.h_lo, cap128, d, 128) || !encode_map(&mSh, ws.w_hi, V1, d, sh.NV) || !encode_map(&mSl, ws.w_lo, V1, d, sh.NV)) {
     rbm_set_error("rbm_ce_fwd(wide): cuTensorMapEncodeTiled failed");
     return -1;
   }
   WideArgs a{};
   a.rows = rows; a.tgt = tgt; a.count = count; a.bias = bias; a.scales = ws.scales; a.st_m = ws.st_m; a.st_l = ws.st_l; a.st_t = ws.st_t;
+  a.r_hi = (const __half*)ws.h_hi; a.r_lo = (const __half*)ws.h_lo; a.r_rows = cap128;
   a.V1 = V1; a.d = d; a.KB = d / 64; a.NV = sh.NV; a.nstage = sh.ns; a.npass = sh.npass;
   a.bias_vec = bias != nullptr && ((uintptr_t)bias & 15) == 0;
+  a.pair = env_int("RBM_CE_WIDE_PAIR", 1);
   if (!set_smem(ce_wide_kernel<MODE_FWD>, sh.smem, "rbm_ce_fwd(wide)")) return -1;
-  ce_wide_kernel<MODE_FWD><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mRh, mRl, mSh, mSl, a);
+  ce_wide_kernel<MODE_FWD><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mRl, mSh, mSl, a);
   RBM_LAUNCH_CHECK("rbm_ce_fwd(wide)");
   const int nblk = (int)(cap128 / 128);
   fwd_combine_kernel<<<nblk, 128, 0, st>>>(ws.st_m, ws.st_l, ws.st_t, count, lse, partial);
@@ -737,11 +821,10 @@ int rbm_ce_wide_bwd(const float* h, const int32_t* rows, const int64_t* tgt, con
   const int64_t cap128 = (cap + 127) / 128 * 128;
   const WideWs ws = carve(extra_ws, cap, V1, d);
   if (int rc = prepare(h, rows, count, w, cap, V1, d, ws, st)) return rc;
-  const Shape sh = pick_shape(d);
-  CUtensorMap mHr, mHlr, mWs, mWls, mWr, mWlr, mHs, mHls;
-  if (!encode_map(&mHr, ws.h_hi, cap128, d, 128) || !encode_map(&mHlr, ws.h_lo, cap128, d, 128) || !encode_map(&mWs, ws.w_hi, V1, d, sh.NV) ||
-      !encode_map(&mWls, ws.w_lo, V1, d, sh.NV) || !encode_map(&mWr, ws.w_hi, V1, d, 128) || !encode_map(&mWlr, ws.w_lo, V1, d, 128) ||
-      !encode_map(&mHs, ws.h_hi, cap128, d, sh.NV) || !encode_map(&mHls, ws.h_lo, cap128, d, sh.NV)) {
+  const Shape sh = pick_shape(d, MODE_DH);
+  CUtensorMap mHlr, mWs, mWls, mWlr, mHs, mHls;
+  if (!encode_map(&mHlr, ws.h_lo, cap128, d, 128) || !encode_map(&mWs, ws.w_hi, V1, d, sh.NV) || !encode_map(&mWls, ws.w_lo, V1, d, sh.NV) ||
+      !encode_map(&mWlr, ws.w_lo, V1, d, 128) || !encode_map(&mHs, ws.h_hi, cap128, d, sh.NV) || !encode_map(&mHls, ws.h_lo, cap128, d, sh.NV)) {
     rbm_set_error("rbm_ce_bwd(wide): cuTensorMapEncodeTiled failed");
     return -1;
   }
@@ -752,14 +835,16 @@ int rbm_ce_wide_bwd(const float* h, const int32_t* rows, const int64_t* tgt, con
   if (!set_smem(ce_wide_kernel<MODE_DH>, sh.smem, "rbm_ce_bwd(wide dh)") || !set_smem(ce_wide_kernel<MODE_DW>, sh.smem, "rbm_ce_bwd(wide dw)"))
     return -1;
   a.dpart = ws.dpart;
-  ce_wide_kernel<MODE_DH><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mHr, mHlr, mWs, mWls, a);
+  a.r_hi = (const __half*)ws.h_hi; a.r_lo = (const __half*)ws.h_lo; a.r_rows = cap128;
+  ce_wide_kernel<MODE_DH><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mHlr, mWs, mWls, a);
   RBM_LAUNCH_CHECK("rbm_ce_bwd(wide dh)");
   dh_reduce_kernel<<<(unsigned)rbm_cdiv(cap * (d / 4), 256), 256, 0, st>>>(ws.dpart, rows, count, ws.scales, dloss, dh_full, d / 4);
   RBM_LAUNCH_CHECK("rbm_ce_bwd(wide dh reduce)");
   a.dpart = part_w;
   a.part_b = part_b;
+  a.r_hi = (const __half*)ws.w_hi; a.r_lo = (const __half*)ws.w_lo; a.r_rows = V1;
   dim3 gdw((unsigned)rbm_cdiv(V1, 128), S);
-  ce_wide_kernel<MODE_DW><<<gdw, 64 + 32 * NSW, sh.smem, st>>>(mWr, mWlr, mHs, mHls, a);
+  ce_wide_kernel<MODE_DW><<<gdw, 64 + 32 * NSW, sh.smem, st>>>(mWlr, mHs, mHls, a);
   RBM_LAUNCH_CHECK("rbm_ce_bwd(wide dw)");
   return 0;
 }
