@@ -497,7 +497,7 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRl, const __grid_constant_
             uint32_t hi[8], lo[8];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              float p = ex2(fmaf(v[j], c1, b2) - ls[j]);
+              float p = ls[j] == INFINITY ? 0.f : ex2(fmaf(v[j], c1, b2) - ls[j]);  // columns beyond the count: exactly zero
               if (tc[j] == frow) p -= 1.f;
               bsum += p;
               v[j] = p * GSCALE;
@@ -588,12 +588,14 @@ __global__ void __launch_bounds__(256) split_w_kernel(const float* __restrict__ 
   hi[i] = a;
   lo[i] = b;
 }
-// Hc[r] = h[rows[r]] * scales[0] (r < count), zeros up to the next multiple of 128, as hi/lo fp16
+// Hc[r] = h[rows[r]] * scales[0] (r < count) as hi/lo fp16; zeros up to the next multiple of 128 PLUS one more tile: the DW
+// kernel streams these rows in NV-row chunks, and the last chunk may reach past the 128-row boundary into what would
+// otherwise be stale workspace (0 x NaN = NaN inside the tensor core)
 __global__ void __launch_bounds__(256) gather_split_h_kernel(const float* __restrict__ h, const int32_t* __restrict__ rows,
                                                              const int32_t* __restrict__ count_p, const float* __restrict__ scales,
                                                              uint2* __restrict__ hi, uint2* __restrict__ lo, int64_t cap128, int d4) {
   const int count = *count_p;
-  int64_t lim = ((int64_t)count + 127) / 128 * 128;
+  int64_t lim = ((int64_t)count + 127) / 128 * 128 + 128;
   if (lim > cap128) lim = cap128;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= lim * d4) return;

@@ -256,7 +256,9 @@ def test_attention_split_sources_and_bad_shapes():
 
 
 # ----------------------------------------------------------------------------------- scoring + cross-entropy
-@pytest.mark.parametrize("n,V1,d,frac", [(40, 38, 16, 0.5), (500, 3417, 64, 0.15), (300, 1001, 128, 0.3), (130, 777, 256, 0.9), (64, 65, 32, 0.0)])
+@pytest.mark.parametrize("n,V1,d,frac", [(40, 38, 16, 0.5), (500, 3417, 64, 0.15), (300, 1001, 128, 0.3), (130, 777, 256, 0.9), (64, 65, 32, 0.0),
+                                          (700, 64, 128, 0.4), (3000, 5003, 256, 0.2), (520, 20011, 256, 0.3), (64, 300, 256, 0.0),
+                                          (900, 12101, 128, 0.15)])
 def test_score_ce(n, V1, d, frac):
     torch.manual_seed(n)
     h = torch.randn(n, d)
@@ -618,6 +620,83 @@ def test_score_topk_full_size_properties():
     assert torch.equal(mi, ids) and torch.equal(mv, vals)
     v16, i16 = ops.score_topk(f[:64], table, b, 1, V + 1, 16)
     assert torch.equal(i16, ri32[:64] + 1) and torch.equal(v16, rv32[:64])
+
+
+def _ce_ref64(h, labels, w, b, chunk=65536):
+    """fp64 torch evaluation of the masked cross-entropy and its gradients, chunked over the vocabulary (on the device the
+    tensors live on): loss, dH [n, d] (zeros at ignored rows), dW, db."""
+    sel = labels != 0
+    hc, tg = h[sel].double(), labels[sel]
+    V1 = w.shape[0]
+    lse = torch.full((hc.shape[0],), -float("inf"), dtype=torch.float64, device=h.device)
+    for v0 in range(0, V1, chunk):
+        lg = hc @ w[v0:v0 + chunk].double().t() + b[v0:v0 + chunk].double()
+        lse = torch.logaddexp(lse, torch.logsumexp(lg, 1))
+    tl = (hc * w[tg].double()).sum(1) + b[tg].double()
+    P = hc.shape[0]
+    dh_c = torch.zeros_like(hc)
+    dw = torch.zeros(V1, w.shape[1], dtype=torch.float64, device=h.device)
+    db = torch.zeros(V1, dtype=torch.float64, device=h.device)
+    for v0 in range(0, V1, chunk):
+        wc = w[v0:v0 + chunk].double()
+        G = torch.exp(hc @ wc.t() + b[v0:v0 + chunk].double() - lse[:, None])
+        inb = (tg >= v0) & (tg < v0 + chunk)
+        G[inb.nonzero(as_tuple=True)[0], tg[inb] - v0] -= 1.0
+        G /= P
+        dh_c += G @ wc
+        dw[v0:v0 + chunk] = G.t() @ hc
+        db[v0:v0 + chunk] = G.sum(0)
+    dh = torch.zeros(h.shape, dtype=torch.float64, device=h.device)
+    dh[sel] = dh_c
+    return float((lse - tl).mean()), dh, dw, db
+
+
+@pytest.mark.parametrize("passes", [3, 1])
+def test_score_ce_wide_million_items(passes):
+    """BASELINE configs[3] scoring shape: d = 256 over 10^6 + 1 output rows (split-fp16 tcgen05 kernels, csrc/ce_wide.cu) against
+    an fp64 evaluation: loss 1e-6 relative, dH / dW / db 1e-4 of their scale in the default three-pass (fp32-parity) mode; the
+    single-pass fp16 mode (RBM_CE_WIDE_PASSES=1, the optional reduced-precision line) stays within the north star's 1e-3."""
+    import os
+    torch.manual_seed(3)
+    n, V1, d = 6000, 1_000_001, 256
+    h = (torch.randn(n, d, device=DEV) * 0.5).requires_grad_(True)
+    w = (torch.randn(V1, d, device=DEV) * 0.05).requires_grad_(True)
+    b = (torch.randn(V1, device=DEV) * 0.1).requires_grad_(True)
+    labels = torch.where(torch.rand(n, device=DEV) < 0.15, torch.randint(1, V1, (n,), device=DEV), torch.zeros(n, dtype=torch.long, device=DEV))
+    labels[7], labels[8] = V1 - 1, 1
+    os.environ["RBM_CE_WIDE_PASSES"] = str(passes)
+    try:
+        loss = ops.score_cross_entropy(h, labels, w, b)
+        loss.backward()
+        torch.cuda.synchronize()
+    finally:
+        os.environ.pop("RBM_CE_WIDE_PASSES", None)
+    rl, rdh, rdw, rdb = _ce_ref64(h.detach(), labels, w.detach(), b.detach())
+    tol_l, tol_g = (1e-6, 1e-4) if passes == 3 else (1e-4, 1e-3)
+    assert abs(loss.item() - rl) < tol_l * abs(rl), (loss.item(), rl)
+    for got, ref, name in ((h.grad, rdh, "dH"), (w.grad, rdw, "dW"), (b.grad, rdb, "db")):
+        err = float((got.double() - ref).abs().max() / ref.abs().max())
+        assert err < tol_g, (name, err)
+    assert float(b.grad.sum().abs()) < 1e-5 and float(w.grad.sum(0).abs().max()) < 1e-5  # rows of softmax - onehot sum to zero
+
+
+def test_score_ce_wide_range_scaling():
+    """The split-fp16 path range-scales both operands by per-tensor powers of two: hidden states of magnitude 1e3 against weights
+    of magnitude 1e-4 (and the reverse) keep fp32-level accuracy; nothing overflows fp16."""
+    for hs, ws in ((1e3, 1e-4), (1e-3, 50.0)):
+        torch.manual_seed(5)
+        n, V1, d = 1500, 30011, 256
+        h = (torch.randn(n, d, device=DEV) * hs).requires_grad_(True)
+        w = (torch.randn(V1, d, device=DEV) * ws).requires_grad_(True)
+        b = (torch.randn(V1, device=DEV) * 0.1).requires_grad_(True)
+        labels = torch.where(torch.rand(n, device=DEV) < 0.2, torch.randint(1, V1, (n,), device=DEV), torch.zeros(n, dtype=torch.long, device=DEV))
+        loss = ops.score_cross_entropy(h, labels, w, b)
+        loss.backward()
+        rl, rdh, rdw, rdb = _ce_ref64(h.detach(), labels, w.detach(), b.detach())
+        assert abs(loss.item() - rl) < 2e-6 * abs(rl), (hs, ws, loss.item(), rl)
+        for got, ref, name in ((h.grad, rdh, "dH"), (w.grad, rdw, "dW"), (b.grad, rdb, "db")):
+            err = float((got.double() - ref).abs().max() / ref.abs().max())
+            assert err < 1e-4, (hs, ws, name, err)
 
 
 def test_score_ce_full_size_properties():

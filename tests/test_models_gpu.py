@@ -405,3 +405,35 @@ def test_wide_models_vs_reference_golden(name):
     assert abs(loss.item() - float(z["loss"])) < 3e-4 * abs(float(z["loss"])), (loss.item(), float(z["loss"]))
     gn = np.array([p.grad.norm().item() for _, p in model.named_parameters()])
     np.testing.assert_allclose(gn, z["grad_norms"], rtol=3e-3, atol=1e-5 * float(z["grad_norms"].max()))
+
+
+def test_bert_cfg4_million_items_vs_oracle():
+    """BASELINE configs[3] at its real catalogue size: BERT4Rec d = 256, h = 4, 10^6 items (2 blocks, B = 4 keeps the CPU oracle
+    to seconds) -- loss and the gradients of the output layer, the token table and a dense weight against the chunked CPU
+    restatement `oracle.bert4rec.loss_masked_only` (the reference itself cannot allocate 800 MB of logits per
+    sequence).  Tolerances: loss 1e-4 relative, gradients 1e-3 of their scale."""
+    V, Ln, d, nb, h, B = 1_000_000, 200, 256, 2, 4, 4
+    sd = ob.random_state_dict(V, Ln, d, nb, seed=11)
+    a = bert_args(V, Ln, d, nb, h, p=0.0, seed=11)
+    with torch.device(DEV):
+        model = rbm_b200.model_factory(a)
+    model = model.to(DEV)
+    model.load_state_dict(sd)
+    model.train()
+    rs = np.random.RandomState(2)
+    tok = rs.randint(1, V + 1, size=(B, Ln)).astype(np.int64)
+    tok[1, :40] = 0
+    lab = np.where((rs.rand(B, Ln) < 0.15) & (tok != 0), tok, 0)
+    tokm = np.where(lab != 0, V + 1, tok)
+    loss = model.loss(torch.from_numpy(tokm), torch.from_numpy(lab))
+    loss.backward()
+    leaves = {k: v.clone().requires_grad_(True) for k, v in sd.items()}
+    ref = ob.loss_masked_only(leaves, torch.from_numpy(tokm), torch.from_numpy(lab), nb, h)
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-4 * abs(ref.item()), (loss.item(), ref.item())
+    got = dict(model.named_parameters())
+    for k in ("out.weight", "out.bias", "bert.embedding.token.weight", "bert.transformer_blocks.1.feed_forward.w_2.weight",
+              "bert.transformer_blocks.0.attention.linear_layers.0.weight"):
+        g_ref = leaves[k].grad
+        err = float((got[k].grad.cpu() - g_ref).abs().max())
+        assert err <= 1e-3 * float(g_ref.abs().max()), (k, err, float(g_ref.abs().max()))
