@@ -13,6 +13,7 @@
 // backward is recompute-based and atomics-free (pass A: dQ by query tiles; pass B: dK, dV by key tiles), so results
 // are bit-deterministic.  A tcgen05/TMEM formulation of these L<=256 tiles is tracked in DESIGN.md ("next").
 #include "common.cuh"
+#include "attention_pair.cuh"
 #include "mma_tiles.cuh"
 #include "attention_tc.cuh"
 
@@ -484,6 +485,8 @@ extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t
   if (rbm_attn_fwd_tc_supported(L, dk, ldq, ldk, ldv, ldo, q, k, v, out))  // Blackwell tensor path (d_k == 32)
     return rbm_attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site,
                                   (cudaStream_t)stream);
+  if (rbm_attn_pair_supported(L, dk, mask_mode) && stats && ldo % 2 == 0)  // d_k = 64, L <= 64: split-fp16 tcgen05 path (attention_pair.cu)
+    return rbm_attn_pair_fwd(q, ldq, k, ldk, v, ldv, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site, (cudaStream_t)stream);
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.stats = stats; a.tok = tok;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
@@ -510,6 +513,9 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
               "rbm_attn_bwd: q/k/v/dout must be 16B aligned with strides %% 4 == 0");
   RBM_REQUIRE(lddq % 2 == 0 && lddk % 2 == 0 && lddv % 2 == 0 && (((uintptr_t)dq | (uintptr_t)dk_ | (uintptr_t)dv) & 7) == 0,
               "rbm_attn_bwd: dq/dk/dv must be 8B aligned with even strides");
+  if (rbm_attn_pair_supported(L, dk, mask_mode) && ldo % 2 == 0)  // d_k = 64, L <= 64: split-fp16 tcgen05 path (attention_pair.cu)
+    return rbm_attn_pair_bwd(q, ldq, k, ldk, v, ldv, out, ldo, dout, lddo, stats, dq, lddq, dk_, lddk, dv, lddv, B, L, h, mask_mode, scale, p,
+                             seed, site, (cudaStream_t)stream);
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.o = out; a.dout = dout; a.stats_in = stats; a.tok = tok;
   a.dq = dq; a.dk_ = dk_; a.dv = dv; a.delta = (float*)ws;
