@@ -13,8 +13,9 @@
 //   forward : S = Q.K^T -> softmax (thread per query row, exact row max), dropout -> O = P~.V
 //   backward: phase 1 (lanes = queries): S, dP~ = dO.V^T -> dS -> dQ = dS.K
 //             phase 2 (lanes = keys)   : S^T = K.Q^T, dP~^T = V.dO^T -> P~^T, dS^T -> dV = P~^T.dO, dK = dS^T.Q
-// Persistent CTAs walk the item pairs; 256 threads: all eight warps stage the tiles (global fp32 -> split fp16), warps 0-3
-// own the 128 tensor-memory lanes, one elected thread of warp 4 issues the MMAs.  Dropout follows the library's Philox
+// Persistent CTAs (one per SM) walk the item pairs; 256 threads: all eight warps stage the tiles (global fp32 -> split fp16, two
+// tiles in flight) and share the softmax work -- two threads per tensor-memory lane, each with half of the row's columns; one
+// elected thread of warp 0 issues the MMAs.  Dropout follows the library's Philox
 // contract (common.cuh, rbm_attn_keep), atomics-free and bit-deterministic.
 #include <cuda_fp16.h>
 #include <stdlib.h>
@@ -138,17 +139,12 @@ __device__ __forceinline__ void tile_store(const float (&v)[4][8], float sc, uin
     *reinterpret_cast<uint4*>(lo + off) = make_uint4(l[0], l[1], l[2], l[3]);
   }
 }
-// fetch + block max + store of one tile; writes the tile's scale to *scale_out.  Called by all THREADS threads.
-__device__ __forceinline__ void stage_tile(const float* __restrict__ src, int64_t ld, float mul, int pair, const PairArgs& a, uint8_t* hi,
-                                           uint8_t* lo, unsigned* maxbits, float* scale_out) {
-  float v[4][8];
-  float mx = warp_max(tile_fetch(v, src, ld, mul, pair, a));
+// this thread's share of the tile maximum -> block maximum (shared-memory atomicMax on the bit pattern: order-independent)
+__device__ __forceinline__ void tile_max(float mx, unsigned* maxbits) {
+  mx = warp_max(mx);
   if ((threadIdx.x & 31) == 0 && mx > 0.f) atomicMax(maxbits, __float_as_uint(mx));
-  __syncthreads();
-  const float sc = pow2_scale(__uint_as_float(*maxbits));
-  if (threadIdx.x == 0) *scale_out = sc;
-  tile_store(v, sc, hi, lo);
 }
+__device__ __forceinline__ float tile_scale_of(const unsigned* maxbits) { return pow2_scale(__uint_as_float(*maxbits)); }
 
 // 3-pass products.  SS: D = A_tile . B_tile^T (both K-major, contraction over d_k = 64: four k-steps of 16)
 __device__ __forceinline__ void mma_ss3(uint32_t d_t, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo, uint32_t idesc) {
@@ -218,28 +214,33 @@ __device__ __forceinline__ uint32_t keep_bits_col(uint64_t seed, uint64_t site, 
   return bits;
 }
 
-// 64 packed words (K = 128 tokens) of one quantity: this slot's 32 words hold values, the other slot's are zero
-__device__ __forceinline__ void store_packed_block(uint32_t t_hi, int slot, int part, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
+// Packed A operands (K = 128 tokens): hi words [0, 64), lo words [64, 128); word w = tokens (2 w, 2 w + 1); slot s owns words
+// [32 s, 32 s + 32), the other slot's words are zero.  A thread covers the 16-token parts {2 hf, 2 hf + 1} of its row.
+__device__ __forceinline__ void store_packed_part(uint32_t t_hi, int slot, int part, const uint32_t (&hi)[8], const uint32_t (&lo)[8]) {
   tmem_st8(t_hi + (uint32_t)(slot * 32 + part * 8), hi);
   tmem_st8(t_hi + 64 + (uint32_t)(slot * 32 + part * 8), lo);
 }
-__device__ __forceinline__ void store_zero_block(uint32_t t_hi, int slot) {
+__device__ __forceinline__ void store_zero_parts(uint32_t t_hi, int slot, int hf) {
   const uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
-  for (int part = 0; part < 4; ++part) {
-    tmem_st8(t_hi + (uint32_t)((1 - slot) * 32 + part * 8), z);
-    tmem_st8(t_hi + 64 + (uint32_t)((1 - slot) * 32 + part * 8), z);
+  for (int pp = 0; pp < 2; ++pp) {
+    tmem_st8(t_hi + (uint32_t)((1 - slot) * 32 + (2 * hf + pp) * 8), z);
+    tmem_st8(t_hi + 64 + (uint32_t)((1 - slot) * 32 + (2 * hf + pp) * 8), z);
   }
 }
 
+// Thread layout of both kernels: 8 warps; warp w owns tensor-memory lanes [32 (w & 3), +32) (row r = 32 (w & 3) + lane: slot
+// r >> 6, token i = r & 63) and the column half hf = w >> 2 of its row: tokens [32 hf, 32 hf + 32) of the row's own block,
+// columns [32 hf, 32 hf + 32) of the 64-wide outputs.  The two threads of a row meet through shared memory.
+
 // =================================================================================================== forward
 // TMEM columns: S [0,128) -> P~ hi [0,64) | lo [64,128);  O [128,192)
-__global__ void __launch_bounds__(THREADS, 1) attn_pair_fwd_kernel(const PairArgs a, int n_pairs) {
+__global__ void __launch_bounds__(THREADS, 2) attn_pair_fwd_kernel(const PairArgs a, int n_pairs) {
   extern __shared__ uint8_t smem_raw[];
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ unsigned maxbits[4];
-  __shared__ float tscale[4];
+  __shared__ float xmax[2][128], xsum[2][128];
   const uint64_t site_e = rbm_site(a.site);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint8_t* sm = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
@@ -248,103 +249,123 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_fwd_kernel(const PairArg
     mbar_init(smem_u32(&mma_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_slot), 256);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 256);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot, tS = tmem, tO = tmem + 128;
   const uint32_t idS = make_idesc_f16(128, 128, 0), idO = make_idesc_f16(128, DK, 1);
+  const int q4 = warp & 3, hf = warp >> 2;
+  const int r = q4 * 32 + lane, slot = r >> 6, i = r & 63;
+  const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
   uint32_t ph = 0;  // parity of the next mma_bar completion
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     if (threadIdx.x < 4) maxbits[threadIdx.x] = 0u;
     __syncthreads();
-    stage_tile(a.q, a.ldq, a.scale * RBM_LOG2E, pair, a, sm + T_QH * TILE, sm + T_QL * TILE, &maxbits[0], &tscale[0]);
-    stage_tile(a.k, a.ldk, 1.f, pair, a, sm + T_KH * TILE, sm + T_KL * TILE, &maxbits[1], &tscale[1]);
-    stage_tile(a.v, a.ldv, 1.f, pair, a, sm + T_VH * TILE, sm + T_VL * TILE, &maxbits[2], &tscale[2]);
+    float sQ, sK, sV;
+    {  // global fp32 -> split fp16 tiles, two tiles in flight
+      float va[4][8], vb[4][8];
+      tile_max(tile_fetch(va, a.q, a.ldq, a.scale * RBM_LOG2E, pair, a), &maxbits[0]);
+      tile_max(tile_fetch(vb, a.k, a.ldk, 1.f, pair, a), &maxbits[1]);
+      __syncthreads();
+      sQ = tile_scale_of(&maxbits[0]);
+      sK = tile_scale_of(&maxbits[1]);
+      tile_store(va, sQ, sm + T_QH * TILE, sm + T_QL * TILE);
+      tile_max(tile_fetch(va, a.v, a.ldv, 1.f, pair, a), &maxbits[2]);
+      tile_store(vb, sK, sm + T_KH * TILE, sm + T_KL * TILE);
+      __syncthreads();
+      sV = tile_scale_of(&maxbits[2]);
+      tile_store(va, sV, sm + T_VH * TILE, sm + T_VL * TILE);
+    }
     fence_proxy_async();
     __syncthreads();
-    if (warp == 4 && elect_one()) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ss3(tS, sb + T_QH * TILE, sb + T_QL * TILE, sb + T_KH * TILE, sb + T_KL * TILE, idS);
       umma_commit(smem_u32(&mma_bar));
     }
-    float inv_l = 0.f;
-    const int r = warp * 32 + lane, slot = r >> 6, i = r & 63, item = 2 * pair + slot;
-    const bool row_ok = warp < 4 && item < a.n_items && i < a.L;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    if (warp < 4) {
-      mbar_wait(smem_u32(&mma_bar), ph);
-      tc_fence_after();
-      float sv[64];
-#pragma unroll
-      for (int part = 0; part < 4; ++part) tmem_ld16(tS + lane_sel + (uint32_t)(slot * 64 + part * 16), *reinterpret_cast<float(*)[16]>(&sv[part * 16]));
-      const float us = 1.f / (tscale[0] * tscale[1]);
-      float m = -INFINITY;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        const bool ok = j < a.L && (!a.causal || j <= i);
-        sv[j] = ok ? sv[j] * us : -INFINITY;
-        m = fmaxf(m, sv[j]);
-      }
-      if (!row_ok) m = 0.f;
-      float l = 0.f;
-#pragma unroll
-      for (int j = 0; j < 64; ++j) {
-        sv[j] = row_ok ? ex2(sv[j] - m) : 0.f;
-        l += sv[j];
-      }
-      inv_l = row_ok ? 1.f / l : 0.f;
-      if (row_ok && a.stats) {
-        const int64_t sr = ((int64_t)item * a.L + i) * 2;
-        a.stats[sr] = m;
-        a.stats[sr + 1] = inv_l;
-      }
-#pragma unroll
-      for (int part = 0; part < 4; ++part) {
-        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&sv[part * 16]);
-        uint32_t bits = 0xffffu;
-        if (a.thr16) bits = keep_bits_row(a.seed, site_e, (uint64_t)(item < a.n_items ? item : 0), i, part, a.thr16);
-        const float keep = a.thr16 ? a.inv_keep * a.pscale : a.pscale;
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) v[jj] = ((bits >> jj) & 1u) ? v[jj] * keep : 0.f;
-        uint32_t hi[8], lo[8];
-        split_pack16(v, hi, lo);
-        store_packed_block(tS + lane_sel, slot, part, hi, lo);
-      }
-      store_zero_block(tS + lane_sel, slot);
-      tmem_st_wait();
-      tc_fence_before();
-    }
+    __syncwarp();
+    const int item = 2 * pair + slot;
+    const bool row_ok = item < a.n_items && i < a.L;
+    mbar_wait(smem_u32(&mma_bar), ph);
     ph ^= 1;
+    tc_fence_after();
+    float sv[32];
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp)
+      tmem_ld16(tS + lane_sel + (uint32_t)(slot * 64 + hf * 32 + pp * 16), *reinterpret_cast<float(*)[16]>(&sv[pp * 16]));
+    const float us = 1.f / (sQ * sK);
+    float m = -INFINITY;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      const int j = hf * 32 + jj;
+      const bool ok = j < a.L && (!a.causal || j <= i);
+      sv[jj] = ok ? sv[jj] * us : -INFINITY;
+      m = fmaxf(m, sv[jj]);
+    }
+    xmax[hf][r] = m;
+    __syncthreads();  // both halves of every row have read their scores: the score columns may be overwritten from here on
+    m = row_ok ? fmaxf(xmax[0][r], xmax[1][r]) : 0.f;
+    float l = 0.f;
+#pragma unroll
+    for (int jj = 0; jj < 32; ++jj) {
+      sv[jj] = row_ok ? ex2(sv[jj] - m) : 0.f;
+      l += sv[jj];
+    }
+    xsum[hf][r] = l;
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      const int part = 2 * hf + pp;
+      float(&v)[16] = *reinterpret_cast<float(*)[16]>(&sv[pp * 16]);
+      uint32_t bits = 0xffffu;
+      if (a.thr16) bits = keep_bits_row(a.seed, site_e, (uint64_t)(item < a.n_items ? item : 0), i, part, a.thr16);
+      const float keep = a.thr16 ? a.inv_keep * a.pscale : a.pscale;
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) v[jj] = ((bits >> jj) & 1u) ? v[jj] * keep : 0.f;
+      uint32_t hi[8], lo[8];
+      split_pack16(v, hi, lo);
+      store_packed_part(tS + lane_sel, slot, part, hi, lo);
+    }
+    store_zero_parts(tS + lane_sel, slot, hf);
+    tmem_st_wait();
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4 && elect_one()) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ts3(tO, tS, sb + T_VH * TILE, sb + T_VL * TILE, idO);
       umma_commit(smem_u32(&mma_bar));
     }
-    if (warp < 4) {
-      mbar_wait(smem_u32(&mma_bar), ph);
-      tc_fence_after();
-      const float mul = inv_l / (a.pscale * tscale[2]);
+    __syncwarp();
+    const float lsum = xsum[0][r] + xsum[1][r];
+    const float inv_l = row_ok ? 1.f / lsum : 0.f;
+    if (row_ok && hf == 0 && a.stats) {
+      const int64_t sr = ((int64_t)item * a.L + i) * 2;
+      a.stats[sr] = m;
+      a.stats[sr + 1] = inv_l;
+    }
+    mbar_wait(smem_u32(&mma_bar), ph);
+    ph ^= 1;
+    tc_fence_after();
+    {
+      const float mul = inv_l / (a.pscale * sV);
       const int b = item / a.h, hh = item - b * a.h;
-      float* dst = a.out + ((int64_t)b * a.L + i) * a.ldo + hh * DK;
+      float* dst = a.out + ((int64_t)b * a.L + i) * a.ldo + hh * DK + hf * 32;
 #pragma unroll
-      for (int c0 = 0; c0 < DK; c0 += 16) {
+      for (int c0 = 0; c0 < 32; c0 += 16) {
         float o[16];
-        tmem_ld16(tO + lane_sel + (uint32_t)c0, o);
+        tmem_ld16(tO + lane_sel + (uint32_t)(hf * 32 + c0), o);
         if (row_ok) {
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) *reinterpret_cast<float2*>(dst + c0 + jj) = make_float2(o[jj] * mul, o[jj + 1] * mul);
         }
       }
-      tc_fence_before();
     }
-    ph ^= 1;
+    tc_fence_before();
     __syncthreads();  // tensor memory and the tiles are free for the next pair
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 256);
   }
@@ -358,7 +379,6 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_bwd_kernel(const PairArg
   __shared__ __align__(8) uint64_t mma_bar;
   __shared__ uint32_t tmem_base_slot;
   __shared__ unsigned maxbits[5];   // tiles q, k, v, dO; [4] = max |dS|
-  __shared__ float tscale[4];
   __shared__ float row_m[128], row_inv[128], row_delta[128];
   const uint64_t site_e = rbm_site(a.site);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -368,38 +388,53 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_bwd_kernel(const PairArg
     mbar_init(smem_u32(&mma_bar), 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 4) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  if (warp == 0) tmem_alloc(smem_u32(&tmem_base_slot), 512);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = tmem_base_slot, tS = tmem, tP = tmem + 128, tDQ = tmem + 256, tDV = tmem + 320, tDK = tmem + 384;
   const uint32_t idS = make_idesc_f16(128, 128, 0), idO = make_idesc_f16(128, DK, 1);
+  const int q4 = warp & 3, hf = warp >> 2;
+  const int r = q4 * 32 + lane, slot = r >> 6, i = r & 63;
+  const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
   uint32_t ph = 0;
   for (int pair = blockIdx.x; pair < n_pairs; pair += gridDim.x) {
     if (threadIdx.x < 5) maxbits[threadIdx.x] = 0u;
     __syncthreads();
-    stage_tile(a.q, a.ldq, a.scale * RBM_LOG2E, pair, a, sm + T_QH * TILE, sm + T_QL * TILE, &maxbits[0], &tscale[0]);
-    stage_tile(a.k, a.ldk, 1.f, pair, a, sm + T_KH * TILE, sm + T_KL * TILE, &maxbits[1], &tscale[1]);
-    stage_tile(a.v, a.ldv, 1.f, pair, a, sm + T_VH * TILE, sm + T_VL * TILE, &maxbits[2], &tscale[2]);
-    stage_tile(a.dout, a.lddo, 1.f, pair, a, sm + T_GH * TILE, sm + T_GL * TILE, &maxbits[3], &tscale[3]);
+    const int item = 2 * pair + slot;
+    const bool it_ok = item < a.n_items, row_ok = it_ok && i < a.L;
+    const int b = it_ok ? item / a.h : 0, hh = it_ok ? item - b * a.h : 0;
+    float sQ, sK, sV, sG;
+    {  // global fp32 -> split fp16 tiles, two tiles in flight
+      float va[4][8], vb[4][8];
+      tile_max(tile_fetch(va, a.q, a.ldq, a.scale * RBM_LOG2E, pair, a), &maxbits[0]);
+      tile_max(tile_fetch(vb, a.k, a.ldk, 1.f, pair, a), &maxbits[1]);
+      __syncthreads();
+      sQ = tile_scale_of(&maxbits[0]);
+      sK = tile_scale_of(&maxbits[1]);
+      tile_store(va, sQ, sm + T_QH * TILE, sm + T_QL * TILE);
+      tile_max(tile_fetch(va, a.v, a.ldv, 1.f, pair, a), &maxbits[2]);
+      tile_store(vb, sK, sm + T_KH * TILE, sm + T_KL * TILE);
+      tile_max(tile_fetch(vb, a.dout, a.lddo, 1.f, pair, a), &maxbits[3]);
+      __syncthreads();
+      sV = tile_scale_of(&maxbits[2]);
+      sG = tile_scale_of(&maxbits[3]);
+      tile_store(va, sV, sm + T_VH * TILE, sm + T_VL * TILE);
+      tile_store(vb, sG, sm + T_GH * TILE, sm + T_GL * TILE);
+    }
     fence_proxy_async();
     __syncthreads();
     // ---------------------------------------------------------------------------------- phase 1: lanes = queries
-    if (warp == 4 && elect_one()) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ss3(tS, sb + T_QH * TILE, sb + T_QL * TILE, sb + T_KH * TILE, sb + T_KL * TILE, idS);  // S = Q.K^T
       mma_ss3(tP, sb + T_GH * TILE, sb + T_GL * TILE, sb + T_VH * TILE, sb + T_VL * TILE, idS);  // dP~ = dO.V^T
       umma_commit(smem_u32(&mma_bar));
     }
-    const int r = (warp & 3) * 32 + lane, slot = r >> 6, i = r & 63, item = 2 * pair + slot;
-    const bool it_ok = item < a.n_items, row_ok = warp < 4 && it_ok && i < a.L;
-    const uint32_t lane_sel = (uint32_t)((warp & 3) * 32) << 16;
-    const int b = it_ok ? item / a.h : 0, hh = it_ok ? item - b * a.h : 0;
-    const float us = 1.f / (tscale[0] * tscale[1]), up = 1.f / (tscale[3] * tscale[2]);
+    __syncwarp();
+    const float us = 1.f / (sQ * sK), up = 1.f / (sG * sV);
     const float keep = a.thr16 ? a.inv_keep : 1.f;
-    float ds[64];
-    if (warp < 4) {
-      // row statistics and delta_i = <dO_i, O_i> (from HBM, fp32) while the tensor core works
+    if (hf == 0) {  // row statistics and delta_i = <dO_i, O_i> (from HBM, fp32) while the tensor core works
       float m = 0.f, inv = 0.f, delta = 0.f;
       if (row_ok) {
         const int64_t sr = ((int64_t)item * a.L + i) * 2;
@@ -415,13 +450,20 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_bwd_kernel(const PairArg
         }
       }
       row_m[r] = m; row_inv[r] = inv; row_delta[r] = delta;
+    }
+    __syncthreads();
+    float ds[32];
+    {
+      const float m = row_m[r], inv = row_inv[r], delta = row_delta[r];
       mbar_wait(smem_u32(&mma_bar), ph);
+      ph ^= 1;
       tc_fence_after();
-      float dp[16];
       float mx = 0.f;
 #pragma unroll
-      for (int part = 0; part < 4; ++part) {
-        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[part * 16]);
+      for (int pp = 0; pp < 2; ++pp) {
+        const int part = 2 * hf + pp;
+        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[pp * 16]);
+        float dp[16];
         tmem_ld16(tS + lane_sel + (uint32_t)(slot * 64 + part * 16), v);
         tmem_ld16(tP + lane_sel + (uint32_t)(slot * 64 + part * 16), dp);
         uint32_t bits = 0xffffu;
@@ -438,65 +480,67 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_bwd_kernel(const PairArg
       }
       mx = warp_max(mx);
       if (lane == 0 && mx > 0.f) atomicMax(&maxbits[4], __float_as_uint(mx));
-      named_bar_sync(1, 128);
-      const float sd = pow2_scale(__uint_as_float(maxbits[4]));
-#pragma unroll
-      for (int part = 0; part < 4; ++part) {
-        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[part * 16]);
-#pragma unroll
-        for (int jj = 0; jj < 16; ++jj) v[jj] *= sd;
-        uint32_t hi[8], lo[8];
-        split_pack16(v, hi, lo);
-        store_packed_block(tS + lane_sel, slot, part, hi, lo);
-      }
-      store_zero_block(tS + lane_sel, slot);
-      tmem_st_wait();
-      tc_fence_before();
     }
-    ph ^= 1;
-    __syncthreads();
+    __syncthreads();  // max |dS| is known; every score / dP~ column has been read and may be overwritten
     const float sd = pow2_scale(__uint_as_float(maxbits[4]));
-    if (warp == 4 && elect_one()) {
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[pp * 16]);
+#pragma unroll
+      for (int jj = 0; jj < 16; ++jj) v[jj] *= sd;
+      uint32_t hi[8], lo[8];
+      split_pack16(v, hi, lo);
+      store_packed_part(tS + lane_sel, slot, 2 * hf + pp, hi, lo);
+    }
+    store_zero_parts(tS + lane_sel, slot, hf);
+    tmem_st_wait();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ts3(tDQ, tS, sb + T_KH * TILE, sb + T_KL * TILE, idO);  // dQ = dS.K
       umma_commit(smem_u32(&mma_bar));
     }
-    if (warp < 4) {
-      mbar_wait(smem_u32(&mma_bar), ph);
-      tc_fence_after();
-      const float mul = a.scale / (sd * tscale[1]);
-      float* dst = a.dq + ((int64_t)b * a.L + i) * a.lddq + hh * DK;
+    __syncwarp();
+    mbar_wait(smem_u32(&mma_bar), ph);
+    ph ^= 1;
+    tc_fence_after();
+    {
+      const float mul = a.scale / (sd * sK);
+      float* dst = a.dq + ((int64_t)b * a.L + i) * a.lddq + hh * DK + hf * 32;
 #pragma unroll
-      for (int c0 = 0; c0 < DK; c0 += 16) {
+      for (int c0 = 0; c0 < 32; c0 += 16) {
         float o[16];
-        tmem_ld16(tDQ + lane_sel + (uint32_t)c0, o);
+        tmem_ld16(tDQ + lane_sel + (uint32_t)(hf * 32 + c0), o);
         if (row_ok) {
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) *reinterpret_cast<float2*>(dst + c0 + jj) = make_float2(o[jj] * mul, o[jj + 1] * mul);
         }
       }
-      tc_fence_before();
     }
-    ph ^= 1;
+    tc_fence_before();
     __syncthreads();
     // ------------------------------------------------------------------------------------- phase 2: lanes = keys
-    if (warp == 4 && elect_one()) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ss3(tS, sb + T_KH * TILE, sb + T_KL * TILE, sb + T_QH * TILE, sb + T_QL * TILE, idS);  // S^T = K.Q^T
       mma_ss3(tP, sb + T_VH * TILE, sb + T_VL * TILE, sb + T_GH * TILE, sb + T_GL * TILE, idS);  // dP~^T = V.dO^T
       umma_commit(smem_u32(&mma_bar));
     }
-    if (warp < 4) {
+    __syncwarp();
+    float pt[32];  // P~^T of this key for the queries [32 hf, 32 hf + 32) (scaled); ds[] is reused for dS^T
+    {
       const int j = i;  // this lane's key
       const bool key_ok = it_ok && j < a.L;
       mbar_wait(smem_u32(&mma_bar), ph);
+      ph ^= 1;
       tc_fence_after();
-      float pt[64];  // P~^T values of this key (scaled); ds[] is reused for dS^T
-      float dp[16];
 #pragma unroll
-      for (int T = 0; T < 4; ++T) {
-        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[T * 16]);
-        float(&pv)[16] = *reinterpret_cast<float(*)[16]>(&pt[T * 16]);
+      for (int pp = 0; pp < 2; ++pp) {
+        const int T = 2 * hf + pp;
+        float(&v)[16] = *reinterpret_cast<float(*)[16]>(&ds[pp * 16]);
+        float(&pv)[16] = *reinterpret_cast<float(*)[16]>(&pt[pp * 16]);
+        float dp[16];
         tmem_ld16(tS + lane_sel + (uint32_t)(slot * 64 + T * 16), v);
         tmem_ld16(tP + lane_sel + (uint32_t)(slot * 64 + T * 16), dp);
         uint32_t bits = 0xffffu;
@@ -511,55 +555,56 @@ __global__ void __launch_bounds__(THREADS, 1) attn_pair_bwd_kernel(const PairArg
           v[ii] = p * (mk * dp[ii] * up - row_delta[qr]) * sd;
         }
       }
-#pragma unroll
-      for (int T = 0; T < 4; ++T) {
-        uint32_t hi[8], lo[8];
-        split_pack16(*reinterpret_cast<float(*)[16]>(&pt[T * 16]), hi, lo);
-        store_packed_block(tS + lane_sel, slot, T, hi, lo);
-        split_pack16(*reinterpret_cast<float(*)[16]>(&ds[T * 16]), hi, lo);
-        store_packed_block(tP + lane_sel, slot, T, hi, lo);
-      }
-      store_zero_block(tS + lane_sel, slot);
-      store_zero_block(tP + lane_sel, slot);
-      tmem_st_wait();
-      tc_fence_before();
     }
-    ph ^= 1;
+    __syncthreads();  // every S^T / dP~^T column has been read
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+      uint32_t hi[8], lo[8];
+      split_pack16(*reinterpret_cast<float(*)[16]>(&pt[pp * 16]), hi, lo);
+      store_packed_part(tS + lane_sel, slot, 2 * hf + pp, hi, lo);
+      split_pack16(*reinterpret_cast<float(*)[16]>(&ds[pp * 16]), hi, lo);
+      store_packed_part(tP + lane_sel, slot, 2 * hf + pp, hi, lo);
+    }
+    store_zero_parts(tS + lane_sel, slot, hf);
+    store_zero_parts(tP + lane_sel, slot, hf);
+    tmem_st_wait();
+    tc_fence_before();
     __syncthreads();
-    if (warp == 4 && elect_one()) {
+    if (warp == 0 && elect_one()) {
       tc_fence_after();
       mma_ts3(tDV, tS, sb + T_GH * TILE, sb + T_GL * TILE, idO);  // dV = P~^T.dO
       mma_ts3(tDK, tP, sb + T_QH * TILE, sb + T_QL * TILE, idO);  // dK = dS^T.Q
       umma_commit(smem_u32(&mma_bar));
     }
-    if (warp < 4) {
-      mbar_wait(smem_u32(&mma_bar), ph);
-      tc_fence_after();
+    __syncwarp();
+    mbar_wait(smem_u32(&mma_bar), ph);
+    ph ^= 1;
+    tc_fence_after();
+    {
       const bool key_ok = it_ok && i < a.L;
-      const float mv = 1.f / (a.pscale * tscale[3]), mk = 1.f / (sd * tscale[0] * RBM_LOG2E);  // the q tile holds q * scale * log2(e)
-      float* dstv = a.dv + ((int64_t)b * a.L + i) * a.lddv + hh * DK;
-      float* dstk = a.dk_ + ((int64_t)b * a.L + i) * a.lddk + hh * DK;
+      const float mv = 1.f / (a.pscale * sG), mkk = 1.f / (sd * sQ * RBM_LOG2E);  // the q tile holds q * scale * log2(e)
+      float* dstv = a.dv + ((int64_t)b * a.L + i) * a.lddv + hh * DK + hf * 32;
+      float* dstk = a.dk_ + ((int64_t)b * a.L + i) * a.lddk + hh * DK + hf * 32;
 #pragma unroll
-      for (int c0 = 0; c0 < DK; c0 += 16) {
+      for (int c0 = 0; c0 < 32; c0 += 16) {
         float o[16], o2[16];
-        tmem_ld16(tDV + lane_sel + (uint32_t)c0, o);
-        tmem_ld16(tDK + lane_sel + (uint32_t)c0, o2);
+        tmem_ld16(tDV + lane_sel + (uint32_t)(hf * 32 + c0), o);
+        tmem_ld16(tDK + lane_sel + (uint32_t)(hf * 32 + c0), o2);
         if (key_ok) {
 #pragma unroll
           for (int jj = 0; jj < 16; jj += 2) {
             *reinterpret_cast<float2*>(dstv + c0 + jj) = make_float2(o[jj] * mv, o[jj + 1] * mv);
-            *reinterpret_cast<float2*>(dstk + c0 + jj) = make_float2(o2[jj] * mk, o2[jj + 1] * mk);
+            *reinterpret_cast<float2*>(dstk + c0 + jj) = make_float2(o2[jj] * mkk, o2[jj + 1] * mkk);
           }
         }
       }
-      tc_fence_before();
     }
-    ph ^= 1;
+    tc_fence_before();
     __syncthreads();
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 0) {
     tc_fence_after();
     tmem_dealloc(tmem, 512);
   }
@@ -599,7 +644,7 @@ int rbm_attn_pair_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, 
   const int n_pairs = (a.n_items + 1) / 2;
   const size_t smem = 6 * TILE + 1024;
   if (!set_smem(attn_pair_fwd_kernel, smem, "rbm_attn_fwd(pair)")) return -1;
-  const int grid = n_pairs < 2 * RBM_NUM_SMS ? n_pairs : 2 * RBM_NUM_SMS;
+  const int grid = n_pairs < 2 * RBM_NUM_SMS ? n_pairs : 2 * RBM_NUM_SMS;  // two CTAs per SM: one stages while the other computes
   attn_pair_fwd_kernel<<<grid, THREADS, smem, st>>>(a, n_pairs);
   RBM_LAUNCH_CHECK("rbm_attn_fwd(pair)");
   return 0;

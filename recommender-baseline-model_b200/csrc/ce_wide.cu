@@ -809,7 +809,7 @@ int rbm_ce_wide_fwd(const float* h, const int32_t* rows, const int64_t* tgt, con
   a.r_hi = (const __half*)ws.h_hi; a.r_lo = (const __half*)ws.h_lo; a.r_rows = cap128;
   a.V1 = V1; a.d = d; a.KB = d / 64; a.NV = sh.NV; a.nstage = sh.ns; a.npass = sh.npass;
   a.bias_vec = bias != nullptr && ((uintptr_t)bias & 15) == 0;
-  a.pair = env_int("RBM_CE_WIDE_PAIR", 1);
+  a.pair = env_int("RBM_CE_WIDE_PAIR", 0);  // interleaving two chunks' k-steps was measured slower (32 vs 24 ms)
   if (!set_smem(ce_wide_kernel<MODE_FWD>, sh.smem, "rbm_ce_fwd(wide)")) return -1;
   ce_wide_kernel<MODE_FWD><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mRl, mSh, mSl, a);
   RBM_LAUNCH_CHECK("rbm_ce_fwd(wide)");
