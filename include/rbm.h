@@ -189,8 +189,11 @@ int rbm_candidate_scores(const float* f, int64_t ldf, const float* table, const 
 /* ---- full-catalogue scoring fused with top-k (scores never materialised) ----------------------------
  * For each user u: rank items v in [v_begin, v_end) (rows of `table`) by s = <f[u],table[v]> (+bias[v]),
  * order (score desc, id asc), id = v + id_offset; emit top_scores/top_ids [U,k] (k <= 32; unfilled slots
- * = (-inf, -1)).  ws >= rbm_score_topk_ws_bytes. */
+ * = (-inf, -1)).  ws >= rbm_score_topk_ws_bytes_d(U, v_end - v_begin, d, k). */
 size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k);
+/* the same for a known hidden size d (the catalogue-scale path keeps a range-scaled fp16 copy of the scored rows, n_items * d * 2
+ * bytes, in the workspace; the d-less query above has to assume d = 256) */
+size_t rbm_score_topk_ws_bytes_d(int64_t U, int64_t n_items, int d, int k);
 int rbm_score_topk(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin,
                    int64_t v_end, int64_t id_offset, float* top_scores, int64_t* top_ids, int64_t U, int d,
                    int k, void* ws, size_t ws_bytes, rbm_stream_t stream);

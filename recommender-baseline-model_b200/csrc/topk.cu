@@ -267,15 +267,20 @@ int topk_splits(int64_t U, int64_t n_items) {
 
 }  // namespace
 
-extern "C" size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k) {
+extern "C" size_t rbm_score_topk_ws_bytes_d(int64_t U, int64_t n_items, int d, int k) {
   size_t S = (size_t)topk_splits(U, n_items);
   size_t simt = S * (size_t)U * k * (sizeof(float) + sizeof(int64_t)) + 256;
-  size_t tc = 0;
-  for (int d = 32; d <= 256; d *= 2) {  // d is not part of this query: cover every hidden size the tcgen05 path takes
-    size_t b = rbm_tc_topk_ws_bytes(U, n_items, d, k);
-    if (b > tc) tc = b;
-  }
+  size_t tc = rbm_tc_topk_ws_bytes(U, n_items, d, k);
   return simt > tc ? simt : tc;
+}
+
+extern "C" size_t rbm_score_topk_ws_bytes(int64_t U, int64_t n_items, int k) {
+  size_t best = 0;
+  for (int d = 32; d <= 256; d *= 2) {  // d is not part of this query: cover every hidden size the tcgen05 path takes
+    size_t b = rbm_score_topk_ws_bytes_d(U, n_items, d, k);
+    if (b > best) best = b;
+  }
+  return best;
 }
 
 extern "C" int rbm_score_topk(const float* f, int64_t ldf, const float* table, const float* bias, int64_t v_begin, int64_t v_end,
@@ -285,7 +290,7 @@ extern "C" int rbm_score_topk(const float* f, int64_t ldf, const float* table, c
   RBM_REQUIRE(U > 0 && v_begin >= 0 && v_end > v_begin, "rbm_score_topk: empty user or item range");
   RBM_REQUIRE(k >= 1 && k <= 32, "rbm_score_topk: k=%d out of [1,32]", k);
   RBM_REQUIRE(d >= 4 && d % 4 == 0 && d <= 256 && ldf % 4 == 0 && ldf >= d, "rbm_score_topk: unsupported d=%d (need d%%4==0, d<=256)", d);
-  RBM_REQUIRE(ws_bytes >= rbm_score_topk_ws_bytes(U, v_end - v_begin, k), "rbm_score_topk: workspace too small");
+  RBM_REQUIRE(ws_bytes >= rbm_score_topk_ws_bytes_d(U, v_end - v_begin, d, k), "rbm_score_topk: workspace too small");
   RBM_REQUIRE(rbm_aligned16(f) && rbm_aligned16(table) && rbm_aligned16(ws), "rbm_score_topk: pointers must be 16B aligned");
   cudaStream_t st = (cudaStream_t)stream;
   int64_t n_items = v_end - v_begin;

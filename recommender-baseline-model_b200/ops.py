@@ -493,7 +493,7 @@ def score_topk(f, table, bias, v_begin, v_end, k, id_offset=0):
     U, d = f2.shape
     vals = torch.empty(U, k, device=f.device, dtype=torch.float32)
     ids = torch.empty(U, k, device=f.device, dtype=torch.int64)
-    nb = lib.rbm_score_topk_ws_bytes(U, v_end - v_begin, k)
+    nb = lib.rbm_score_topk_ws_bytes_d(U, v_end - v_begin, d, k)
     ws = _ws("topk", nb, f.device)
     check(lib.rbm_score_topk(ptr(f2), f2.stride(0), ptr(table), ptr(bias), v_begin, v_end, id_offset, ptr(vals), ptr(ids), U, d, k,
                              ptr(ws), nb, stream()), "score_topk")
