@@ -607,7 +607,7 @@ def eval_workload(ctx, steps, warmup, with_cpu=True, V=None):
 
 
 # ------------------------------------------------------------ BERT4Rec configs[3]: d=256, 1M items, row-sharded tables
-def cfg4_workload(ctx, steps=3):
+def cfg4_workload(ctx, steps=5):
     """BASELINE configs[3]: BERT4Rec nb=4 d=256 h=4 L=200, full softmax over 1M items; token table and output layer
     row-sharded over the ranks (shard_bert_model), body data-parallel, CFG4['batch_per_gpu'] sequences per GPU (weak).
     Check (eval mode, no dropout): the sharded loss of the global batch against rank 0's unsharded model."""

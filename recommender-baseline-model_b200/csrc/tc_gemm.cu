@@ -31,6 +31,7 @@ __device__ __forceinline__ float act_apply(float v, int act) {
 struct TcParams {
   float* y;
   int64_t ldy;
+  const float* acc_in;  // split-K: partial sums of the earlier K chunks (same layout as y; y itself is the accumulator)
   float* pre;
   const float* bias;
   const float* residual;
@@ -349,6 +350,10 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
             const int rl = i * 4 + rsub;
             const int64_t row = rbase + rl;
             float4 x = ld4(stg + rl * STG_LD + (((cg >> 2) ^ (rl & 7)) << 2));
+            if (p.acc_in) {  // this thread reads exactly the elements it overwrites below: y may be the accumulator
+              const float4 t = ld4(p.acc_in + row * p.ldy + col);
+              x.x += t.x; x.y += t.y; x.z += t.z; x.w += t.w;
+            }
             x.x += bias4.x; x.y += bias4.y; x.z += bias4.z; x.w += bias4.w;
             if constexpr (ACT != 0) {
               if (preout) st4(preout + row * p.N + col, x);
@@ -655,8 +660,37 @@ bool rbm_tc_linear_supported(int64_t M, int N, int K, int64_t lda, const void* a
   return pick_bn(N) != 0;
 }
 
+static int launch_single(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t M, int N, int K, const RbmTcEpilogue& ep,
+                         const float* acc_in, cudaStream_t st);
+
+// Split-K: when the whole-K weight block that fits shared memory is narrower than 64 columns (K = 1024 at d = 256: 16-column
+// blocks, i.e. N = 16 instructions at the fixed ~70-cycle cost), the contraction is cut into 256-wide chunks whose weight blocks
+// are >= 64 columns wide; chunk c adds its product to the partial sums of the chunks before it, with y itself as the accumulator
+// (every epilogue thread reads exactly the elements it overwrites), and the last chunk applies the real epilogue.
 int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M, int N, int K, const RbmTcEpilogue& ep,
                          cudaStream_t st) {
+  constexpr int KC = 256;
+  const char* e = getenv("RBM_LINEAR_SPLITK");
+  if (tc_mode() == 0 && !(e && atoi(e) == 0) && K > KC && K % KC == 0) {
+    int ns, ns2;
+    const int ng = pick_groups(N, K, &ns), ng2 = pick_groups(N, KC, &ns2);
+    if (ng > 0 && ng2 > 0 && N / ng < 64 && N / ng2 >= 64) {
+      RbmTcEpilogue plain{};
+      plain.y = ep.y;
+      plain.ldy = ep.ldy;
+      for (int c = 0; c < K / KC; ++c) {
+        const bool last = c == K / KC - 1;
+        int rc = launch_single(a + (size_t)c * KC, lda, b + (size_t)c * KC, K, M, N, KC, last ? ep : plain, c > 0 ? ep.y : nullptr, st);
+        if (rc) return rc;
+      }
+      return 0;
+    }
+  }
+  return launch_single(a, lda, b, K, M, N, K, ep, nullptr, st);
+}
+
+static int launch_single(const float* a, int64_t lda, const float* b, int64_t ldb, int64_t M, int N, int K, const RbmTcEpilogue& ep,
+                         const float* acc_in, cudaStream_t st) {
   const bool v2 = tc_mode() == 0;
   int ns_v2 = 2;
   const int NG = v2 ? pick_groups(N, K, &ns_v2) : 1;
@@ -666,12 +700,12 @@ int rbm_tc_linear_launch(const float* a, int64_t lda, const float* b, int64_t M,
     return -1;
   }
   CUtensorMap mapA, mapB;
-  if (!encode_map(&mapA, a, M, K, lda, BM) || !encode_map(&mapB, b, N, K, K, BN)) {
+  if (!encode_map(&mapA, a, M, K, lda, BM) || !encode_map(&mapB, b, N, K, ldb, BN)) {
     rbm_set_error("rbm_linear(tcgen05): cuTensorMapEncodeTiled failed (M=%lld N=%d K=%d lda=%lld)", (long long)M, N, K, (long long)lda);
     return -1;
   }
   TcParams p{};
-  p.y = ep.y; p.ldy = ep.ldy; p.pre = ep.pre; p.bias = ep.bias; p.residual = ep.residual; p.ldres = ep.ldres; p.row_tok = ep.row_tok;
+  p.y = ep.y; p.ldy = ep.ldy; p.acc_in = acc_in; p.pre = ep.pre; p.bias = ep.bias; p.residual = ep.residual; p.ldres = ep.ldres; p.row_tok = ep.row_tok;
   p.M = M; p.N = N; p.K = K; p.BN = BN; p.ngroups = NG; p.act = ep.act;
   p.thrA = ep.thrA; p.thrB = ep.thrB; p.invA = ep.invA; p.invB = ep.invB; p.siteA = ep.siteA; p.siteB = ep.siteB; p.seed = ep.seed;
   static bool attr_set = false;

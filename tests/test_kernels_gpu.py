@@ -120,7 +120,9 @@ def _ref_act(x, act):
 
 @pytest.mark.parametrize("M,N,K", [(10, 16, 16), (300, 192, 64), (257, 64, 256), (1000, 256, 64), (131, 48, 32),
                                    # weight block does not fit shared memory whole: column groups of the persistent kernel
-                                   (1000, 128, 128), (700, 256, 128), (5000, 256, 128), (300, 1024, 256), (300, 256, 256)])
+                                   (1000, 128, 128), (700, 256, 128), (5000, 256, 128), (300, 1024, 256), (300, 256, 256),
+                                   # K = 1024 / 768 at d = 256: split-K in 256-wide chunks (forward, and backward-data of the layers above)
+                                   (300, 256, 1024), (260, 768, 256), (130, 512, 512)])
 @pytest.mark.parametrize("act,res,rowtok,pA,pB", [(L.ACT_NONE, False, False, 0.0, 0.0), (L.ACT_GELU_TANH, False, False, 0.2, 0.0),
                                                   (L.ACT_NONE, True, False, 0.1, 0.3), (L.ACT_RELU, False, False, 0.2, 0.0),
                                                   (L.ACT_NONE, True, True, 0.2, 0.0)])

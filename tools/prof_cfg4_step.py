@@ -42,3 +42,14 @@ s = sum(tot.values())
 for k, v in sorted(tot.items(), key=lambda kv: -kv[1]):
     print("%-32s %8.3f ms  %5.1f %%  (%d calls)" % (k, v, 100 * v / s, len(prof[k])))
 print("sum of entry points %.2f ms" % s)
+# Linear family by shape: rbm_linear_fwd args (.., M=7, N=8, K=9), bwd_data (M=5, N=6, K=7), bwd_weight (M=6, N=7, K=8)
+import collections
+by = collections.defaultdict(lambda: [0.0, 0])
+for name, idx in (("rbm_linear_fwd", (7, 8, 9)), ("rbm_linear_bwd_data", (5, 6, 7)), ("rbm_linear_bwd_weight", (6, 7, 8))):
+    for ms, a in prof.get(name, []):
+        key = (name, a[idx[1]], a[idx[2]])
+        by[key][0] += ms
+        by[key][1] += 1
+for (name, N, K), (ms, n) in sorted(by.items(), key=lambda kv: -kv[1][0]):
+    M = B * Ln
+    print("%-24s N=%-5d K=%-5d %7.3f ms / %d calls = %.3f ms each  (%.0f TFLOP/s)" % (name, N, K, ms, n, ms / n, 2.0 * M * N * K / (ms / n) / 1e9))
