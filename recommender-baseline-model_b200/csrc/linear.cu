@@ -9,6 +9,7 @@
 #include <string.h>
 #include "common.cuh"
 #include "tc_gemm.cuh"
+#include "tc_dw16.cuh"
 
 namespace {
 
@@ -427,7 +428,11 @@ extern "C" size_t rbm_linear_bwd_weight_ws_bytes(int64_t M, int N, int K) {
   int S = tn_splits(M, N, K);
   int S2 = rbm_tc_dw_splits(M);
   if (S2 > S) S = S2;
-  return (size_t)S * ((size_t)N * K + N) * sizeof(float);
+  if (N % 128 == 0 && K % 128 == 0) {
+    int S3 = rbm_dw16_splits(M, N, K);
+    if (S3 > S) S = S3;
+  }
+  return (size_t)S * ((size_t)N * K + N) * sizeof(float) + rbm_dw16_extra_bytes();
 }
 
 extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const float* x, int64_t ldx, float* dw, float* db,
@@ -437,6 +442,17 @@ extern "C" int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const fl
   RBM_REQUIRE(lddpre % 4 == 0 && ldx % 4 == 0 && lddpre >= N && ldx >= K, "rbm_linear_bwd_weight: bad leading dimensions");
   RBM_REQUIRE(ws_bytes >= rbm_linear_bwd_weight_ws_bytes(M, N, K), "rbm_linear_bwd_weight: workspace too small");
   RBM_REQUIRE(rbm_aligned16(dpre) && rbm_aligned16(x) && rbm_aligned16(dw) && rbm_aligned16(ws), "rbm_linear_bwd_weight: pointers must be 16B aligned");
+  if (use_tc() && rbm_dw16_supported(M, N, K, lddpre, ldx, dpre, x)) {  // wide layers: split-fp16 tcgen05 kernel (tc_dw16.cu)
+    const int S = rbm_dw16_splits(M, N, K);
+    float* part = (float*)ws;
+    float* part_b = part + (size_t)S * N * K;
+    void* aux = (uint8_t*)ws + rbm_linear_bwd_weight_ws_bytes(M, N, K) - rbm_dw16_extra_bytes();
+    int rc = rbm_dw16_launch(dpre, lddpre, x, ldx, part, db ? part_b : nullptr, aux, M, N, K, (cudaStream_t)stream);  // db rides along
+    if (rc) return rc;
+    launch_reduce_splits(part, dw, (int64_t)N * K, db ? part_b : nullptr, db, N, S, (cudaStream_t)stream);
+    RBM_LAUNCH_CHECK("rbm_linear_bwd_weight(reduce)");
+    return 0;
+  }
   if (use_tc() && rbm_tc_dw_supported(M, N, K, lddpre, ldx, dpre, x)) {
     const int S = rbm_tc_dw_splits(M);
     float* part = (float*)ws;

@@ -158,6 +158,24 @@ def test_linear(M, N, K, act, res, rowtok, pA, pB):
         close(rg.grad, rr.grad, 1e-5, 1e-5)
 
 
+def test_linear_wide_many_tokens():
+    """Wide layer over many tokens (several token slabs per dW tile in the split-fp16 weight-gradient kernel, several row tiles per
+    CTA in the split-K forward / backward-data): plain Linear + bias (no ReLU: with 10^7 pre-activations a handful land within
+    rounding of zero and flip their derivative in ANY implementation), against fp64."""
+    torch.manual_seed(8)
+    M, N, K = 20000, 512, 1024
+    x, w, b = torch.randn(M, K, device=DEV), torch.randn(N, K, device=DEV) * 0.2, torch.randn(N, device=DEV)
+    dy = torch.randn(M, N, device=DEV) * 1e-4  # gradient-sized values: the range scaling of the fp16 split must cope
+    xg, wg, bg = x.clone().requires_grad_(True), w.clone().requires_grad_(True), b.clone().requires_grad_(True)
+    y = ops.linear(xg, wg, bg)
+    y.backward(dy)
+    y64 = x.double() @ w.double().t() + b.double()
+    dx64, dw64, db64 = dy.double() @ w.double(), dy.double().t() @ x.double(), dy.double().sum(0)
+    rel = lambda a, r: float((a.detach().double() - r).abs().max() / r.abs().max())
+    assert rel(y, y64) < 1e-5 and rel(xg.grad, dx64) < 1e-5, (rel(y, y64), rel(xg.grad, dx64))
+    assert rel(wg.grad, dw64) < 1e-5 and rel(bg.grad, db64) < 1e-5, (rel(wg.grad, dw64), rel(bg.grad, db64))
+
+
 def test_linear_strided_input():
     """q/k/v column blocks of a packed tensor are consumed through their row stride."""
     torch.manual_seed(1)
