@@ -14,6 +14,7 @@
 // are bit-deterministic.  A tcgen05/TMEM formulation of these L<=256 tiles is tracked in DESIGN.md ("next").
 #include "common.cuh"
 #include "attention_pair.cuh"
+#include "attention_seq.cuh"
 #include "mma_tiles.cuh"
 #include "attention_tc.cuh"
 
@@ -487,6 +488,8 @@ extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t
                                   (cudaStream_t)stream);
   if (rbm_attn_pair_supported(L, dk, mask_mode) && stats && ldo % 2 == 0)  // d_k = 64, L <= 64: split-fp16 tcgen05 path (attention_pair.cu)
     return rbm_attn_pair_fwd(q, ldq, k, ldk, v, ldv, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site, (cudaStream_t)stream);
+  if (rbm_attn_seq_supported(L, dk, mask_mode) && stats && ldo % 2 == 0)  // d_k = 64, 64 < L <= 256: split-fp16 tcgen05 path (attention_seq.cu)
+    return rbm_attn_seq_fwd(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site, (cudaStream_t)stream);
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.out = out; a.stats = stats; a.tok = tok;
   a.ldq = ldq; a.ldk = ldk; a.ldv = ldv; a.ldo = ldo;
@@ -516,6 +519,9 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   if (rbm_attn_pair_supported(L, dk, mask_mode) && ldo % 2 == 0)  // d_k = 64, L <= 64: split-fp16 tcgen05 path (attention_pair.cu)
     return rbm_attn_pair_bwd(q, ldq, k, ldk, v, ldv, out, ldo, dout, lddo, stats, dq, lddq, dk_, lddk, dv, lddv, B, L, h, mask_mode, scale, p,
                              seed, site, (cudaStream_t)stream);
+  if (rbm_attn_seq_supported(L, dk, mask_mode) && ldo % 2 == 0)  // d_k = 64, 64 < L <= 256: split-fp16 tcgen05 path (attention_seq.cu)
+    return rbm_attn_seq_bwd(q, ldq, k, ldk, v, ldv, tok, out, ldo, dout, lddo, stats, dq, lddq, dk_, lddk, dv, lddv, B, L, h, mask_mode, scale,
+                            p, seed, site, (cudaStream_t)stream);
   AttnArgs a{};
   a.q = q; a.k = k; a.v = v; a.o = out; a.dout = dout; a.stats_in = stats; a.tok = tok;
   a.dq = dq; a.dk_ = dk_; a.dv = dv; a.delta = (float*)ws;

@@ -200,7 +200,8 @@ def _ref_attention(q, k, v, tok, mode, scale, p, mask):
 
 
 @pytest.mark.parametrize("B,Ln,h,dk", [(3, 8, 2, 8), (2, 13, 4, 8), (4, 50, 1, 64), (3, 50, 2, 64), (2, 200, 2, 32), (2, 200, 4, 64), (1, 256, 1, 16), (2, 100, 2, 128),
-                                       (3, 37, 1, 64), (5, 64, 3, 64), (1, 1, 1, 64), (301, 50, 2, 64)])
+                                       (3, 37, 1, 64), (5, 64, 3, 64), (1, 1, 1, 64), (301, 50, 2, 64),
+                                       (3, 129, 2, 64), (2, 256, 1, 64), (5, 65, 1, 64), (160, 200, 1, 64)])
 @pytest.mark.parametrize("mode", [L.MASK_CAUSAL, L.MASK_KEYPAD])
 @pytest.mark.parametrize("p", [0.0, 0.2])
 def test_attention_packed(B, Ln, h, dk, mode, p):
