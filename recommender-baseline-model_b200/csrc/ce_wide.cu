@@ -548,6 +548,199 @@ ce_wide_kernel(const __grid_constant__ CUtensorMap mapRl, const __grid_constant_
   }
 }
 
+// ------------------------------------------------------------------------------------------ forward, 128-row tiles
+// The forward has no accumulator to keep, so tensor memory holds BOTH resident halves (2 x d/2 columns) and two score blocks
+// of 128 columns: the score products become 128 x 128 x 16 instructions, the smallest that run at the tensor floor (64 cycles;
+// the 64-column instructions of the template above cost ~70).  A 128-row vocabulary tile is 128 KB of hi + lo operand, too big
+// for whole-tile stages, so the ring is made of 16 KB K-block PIECES [128 rows x 64 columns], consumed in the order
+// hi[0] (x R hi, x R lo), lo[0] (x R hi), hi[1], ...: thirteen pieces (208 KB) are in flight.
+//   TMEM columns: R hi [0, d/2) | S0 [128, 256) | S1 [256, 384) | R lo [384, 384 + d/2)
+constexpr int NPIECE = 13;
+__global__ void __launch_bounds__(64 + 32 * NSW, 1)
+ce_wide_fwd128_kernel(const __grid_constant__ CUtensorMap mapSh, const __grid_constant__ CUtensorMap mapSl, const WideArgs a) {
+  extern __shared__ uint8_t smem_raw[];
+  __shared__ __align__(8) uint64_t pfull[NPIECE], pempty[NPIECE], s_full[2], g_full[2], rt_bar;
+  __shared__ uint32_t tmem_base_slot;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int count = *a.count;
+  const int d = a.d, KB = a.KB, V1 = a.V1;
+  constexpr int NV = 128;
+  const int RT = (count + 127) / 128, VS = pick_vs(RT);
+  const int unit = blockIdx.x;
+  if (unit >= RT * VS) return;
+  const int r_tile = unit / VS;
+  const int NCall = (V1 + NV - 1) / NV, cps = (NCall + VS - 1) / VS;
+  const int c_begin = (unit % VS) * cps;
+  const int c_end = c_begin + cps < NCall ? c_begin + cps : NCall;
+  const int NL = c_end > c_begin ? c_end - c_begin : 0;
+  const int ppc = (a.npass == 1 ? 1 : 2) * KB;  // pieces per chunk
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < NPIECE; ++s) {
+      mbar_init(smem_u32(&pfull[s]), 1);
+      mbar_init(smem_u32(&pempty[s]), 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&s_full[i]), 1);
+      mbar_init(smem_u32(&g_full[i]), NSW / 2);
+    }
+    mbar_init(smem_u32(&rt_bar), NSW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(smem_u32(&tmem_base_slot), 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = tmem_base_slot;
+  const uint32_t tRh = tmem, tS0 = tmem + 128, tRl = tmem + 384;
+
+  if (warp == 0) {
+    if (elect_one()) {
+      int q = 0;
+      for (int n = 0; n < NL; ++n) {
+        const int c = c_begin + n;
+        for (int pp = 0; pp < ppc; ++pp, ++q) {
+          const int slot = q % NPIECE, kb = a.npass == 1 ? pp : pp >> 1, lo = a.npass == 1 ? 0 : pp & 1;
+          if (q >= NPIECE) mbar_wait(smem_u32(&pempty[slot]), ((q / NPIECE) - 1) & 1);
+          const uint32_t bar = smem_u32(&pfull[slot]);
+          mbar_expect_tx(bar, RBLK);
+          tma_load_2d(smem_base + slot * RBLK, lo ? &mapSl : &mapSh, bar, kb * 64, c * NV);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    if (elect_one()) {
+      const uint32_t idS = make_idesc_f16(128, NV, 0);
+      mbar_wait(smem_u32(&rt_bar), 0);
+      tc_fence_after();
+      int q = 0;
+      for (int n = 0; n < NL; ++n) {
+        const int grp = n & 1;
+        const uint32_t tS = tS0 + (uint32_t)grp * 128;
+        if (n >= 2) {
+          mbar_wait(smem_u32(&g_full[grp]), ((n >> 1) - 1) & 1);
+          tc_fence_after();
+        }
+        uint32_t acc = 0;
+        for (int pp = 0; pp < ppc; ++pp, ++q) {
+          const int slot = q % NPIECE, kb = a.npass == 1 ? pp : pp >> 1, lo = a.npass == 1 ? 0 : pp & 1;
+          mbar_wait(smem_u32(&pfull[slot]), (q / NPIECE) & 1);
+          tc_fence_after();
+          const uint64_t bd = make_sw128_desc(smem_base + slot * RBLK);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {  // this piece x R hi
+            umma_f16_ts(tS, tRh + (uint32_t)(kb * 32 + k * 8), bd + (uint64_t)(k * 2), idS, acc);
+            acc = 1;
+          }
+          if (!lo && a.npass != 1) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_f16_ts(tS, tRl + (uint32_t)(kb * 32 + k * 8), bd + (uint64_t)(k * 2), idS, 1);  // hi piece x R lo
+          }
+          umma_commit(smem_u32(&pempty[slot]));
+        }
+        umma_commit(smem_u32(&s_full[grp]));
+      }
+    }
+    __syncwarp();
+  } else {
+    const int q4 = warp & 3, grp = (warp - 2) >> 2;
+    const int rl = q4 * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q4 * 32) << 16;
+    const uint32_t tS = tS0 + lane_sel + (uint32_t)grp * 128;
+    const float c1 = RBM_LOG2E / (a.scales[0] * a.scales[1]);
+    float* xch = reinterpret_cast<float*>(smem_raw + (smem_base - smem_u32(smem_raw)));
+    {  // resident rows -> tensor memory (group 0: hi half, group 1: lo half)
+      const int64_t grow = (int64_t)r_tile * 128 + rl;
+      const uint4* src = reinterpret_cast<const uint4*>((grp == 0 ? a.r_hi : a.r_lo) + grow * d);
+      const bool inb = grow < a.r_rows;
+      const uint32_t dstc = (grp == 0 ? tRh : tRl) + lane_sel;
+      for (int c0 = 0; c0 < d / 2; c0 += 8) {
+        uint32_t w8[8];
+        const uint4 x = inb ? src[c0 / 4] : make_uint4(0, 0, 0, 0), y = inb ? src[c0 / 4 + 1] : make_uint4(0, 0, 0, 0);
+        w8[0] = x.x; w8[1] = x.y; w8[2] = x.z; w8[3] = x.w; w8[4] = y.x; w8[5] = y.y; w8[6] = y.z; w8[7] = y.w;
+        tmem_st8(dstc + (uint32_t)c0, w8);
+      }
+      tmem_st_wait();
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(smem_u32(&rt_bar));
+    }
+    const int r = r_tile * 128 + rl;
+    const bool valid = r < count;
+    int64_t tg = valid ? a.tgt[r] : -1;
+    if (tg < 0 || tg >= V1) tg = -1;
+    float m = -INFINITY, l = 0.f, tl = 0.f;
+    for (int n = grp; n < NL; n += 2) {
+      const int c = c_begin + n;
+      mbar_wait(smem_u32(&s_full[grp]), (n >> 1) & 1);
+      tc_fence_after();
+#pragma unroll 1
+      for (int part = 0; part < NV / 16; ++part) {
+        const int v0 = c * NV + part * 16;
+        float bb[16];
+        if (v0 + 16 <= V1 && (a.bias == nullptr || a.bias_vec)) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 t = a.bias ? ld4(a.bias + v0 + j) : make_float4(0.f, 0.f, 0.f, 0.f);
+            bb[j] = t.x * RBM_LOG2E; bb[j + 1] = t.y * RBM_LOG2E; bb[j + 2] = t.z * RBM_LOG2E; bb[j + 3] = t.w * RBM_LOG2E;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) bb[j] = v0 + j < V1 ? (a.bias ? a.bias[v0 + j] * RBM_LOG2E : 0.f) : -INFINITY;
+        }
+        float v[16];
+        tmem_ld16(tS + (uint32_t)(part * 16), v);
+        if (part == NV / 16 - 1) {  // last read of this chunk's score block
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(smem_u32(&g_full[grp]));
+        }
+        const uint32_t ts = (uint32_t)(tg - (int64_t)v0);
+        const bool hit = __any_sync(0xffffffffu, ts < 16u);
+        float cm = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          v[j] = fmaf(v[j], c1, bb[j]);
+          cm = fmaxf(cm, v[j]);
+        }
+        if (hit) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            if (ts == (uint32_t)j) tl = v[j];
+        }
+        const float mn = fmaxf(m, cm);
+        if (mn > -INFINITY) {
+          float ps = 0.f;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) ps += ex2(v[j] - mn);
+          l = l * (m == -INFINITY ? 0.f : ex2(m - mn)) + ps;
+          m = mn;
+        }
+      }
+    }
+    // every chunk's scores have been read, hence every MMA has completed and every piece is free
+    named_bar_sync(7, NSW * 32);
+    xch[(grp * 3 + 0) * 128 + rl] = m;
+    xch[(grp * 3 + 1) * 128 + rl] = l;
+    xch[(grp * 3 + 2) * 128 + rl] = tl;
+    named_bar_sync(7, NSW * 32);
+    if (grp == 0) {
+      const float m0 = xch[rl], m1 = xch[3 * 128 + rl];
+      const float mm = fmaxf(m0, m1);
+      const float ll = xch[128 + rl] * (m0 == -INFINITY ? 0.f : ex2(m0 - mm)) + xch[4 * 128 + rl] * (m1 == -INFINITY ? 0.f : ex2(m1 - mm));
+      a.st_m[(int64_t)unit * 128 + rl] = mm;
+      a.st_l[(int64_t)unit * 128 + rl] = ll;
+      a.st_t[(int64_t)unit * 128 + rl] = xch[2 * 128 + rl] + xch[5 * 128 + rl];
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, 512);
+  }
+}
+
 // ---------------------------------------------------------------------------------------------- helper kernels
 // max |x| as the bit pattern of a non-negative float (atomicMax on unsigned: order-independent)
 __global__ void __launch_bounds__(256) maxabs_kernel(const float* __restrict__ x, int64_t n4, unsigned* __restrict__ out_bits) {
@@ -810,8 +1003,20 @@ int rbm_ce_wide_fwd(const float* h, const int32_t* rows, const int64_t* tgt, con
   a.V1 = V1; a.d = d; a.KB = d / 64; a.NV = sh.NV; a.nstage = sh.ns; a.npass = sh.npass;
   a.bias_vec = bias != nullptr && ((uintptr_t)bias & 15) == 0;
   a.pair = env_int("RBM_CE_WIDE_PAIR", 0);  // interleaving two chunks' k-steps was measured slower (32 vs 24 ms)
-  if (!set_smem(ce_wide_kernel<MODE_FWD>, sh.smem, "rbm_ce_fwd(wide)")) return -1;
-  ce_wide_kernel<MODE_FWD><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mRl, mSh, mSl, a);
+  if (env_int("RBM_CE_WIDE_FWD128", 1)) {  // 128-row vocabulary tiles through a ring of K-block pieces (N = 128 instructions)
+    CUtensorMap m128h, m128l;
+    if (!encode_map(&m128h, ws.w_hi, V1, d, 128) || !encode_map(&m128l, ws.w_lo, V1, d, 128)) {
+      rbm_set_error("rbm_ce_fwd(wide): cuTensorMapEncodeTiled failed");
+      return -1;
+    }
+    const size_t smem128 = (size_t)NPIECE * RBLK + 1024;
+    if (!set_smem(ce_wide_fwd128_kernel, smem128, "rbm_ce_fwd(wide 128)")) return -1;
+    a.NV = 128;
+    ce_wide_fwd128_kernel<<<(unsigned)grid_units(cap128), 64 + 32 * NSW, smem128, st>>>(m128h, m128l, a);
+  } else {
+    if (!set_smem(ce_wide_kernel<MODE_FWD>, sh.smem, "rbm_ce_fwd(wide)")) return -1;
+    ce_wide_kernel<MODE_FWD><<<(unsigned)grid_units(cap128), 64 + 32 * NSW, sh.smem, st>>>(mRl, mSh, mSl, a);
+  }
   RBM_LAUNCH_CHECK("rbm_ce_fwd(wide)");
   const int nblk = (int)(cap128 / 128);
   fwd_combine_kernel<<<nblk, 128, 0, st>>>(ws.st_m, ws.st_l, ws.st_t, count, lse, partial);

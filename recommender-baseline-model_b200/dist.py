@@ -161,10 +161,11 @@ class VocabParallelCEFn(torch.autograd.Function):
     yields this block's dW / db and this block's share of dH; the dH shares are summed with one all-reduce."""
 
     @staticmethod
-    def forward(ctx, hidden, labels, w_shard, bias_shard, v_begin, group):
+    def forward(ctx, hidden, labels, w_shard, bias_shard, v_begin, group, own_rows=None):
         from . import ops
         lib = L.load()
         L.require_cuda(hidden, labels, w_shard, bias_shard)
+        ctx.own_rows = own_rows
         h2 = hidden.reshape(-1, hidden.shape[-1]).contiguous()
         n, d = h2.shape
         V1 = w_shard.shape[0]
@@ -216,13 +217,24 @@ class VocabParallelCEFn(torch.autograd.Function):
                              ptr(dw), ptr(db), n, V1, d, ptr(ws), nb, stream()), "ce_bwd")
         count_launches(4)
         if ctx.world > 1:
-            dist.all_reduce(dh, op=dist.ReduceOp.SUM, group=ctx.group)  # every rank needs the full dH of the replicated rows
-        return dh.view(ctx.shape), None, dw, db, None, None
+            if ctx.own_rows is not None and n == ctx.world * ctx.own_rows:
+                # the rows are the ranks' slot blocks in rank order and each rank only needs the gradient of ITS block
+                # (hybrid_vocab_parallel_loss): reduce-scatter moves half the bytes of an all-reduce
+                mine = torch.empty(ctx.own_rows, d, device=dh.device, dtype=dh.dtype)
+                dist.reduce_scatter_tensor(mine, dh, op=dist.ReduceOp.SUM, group=ctx.group)
+                r = dist.get_rank(ctx.group)
+                dh.zero_()
+                dh[r * ctx.own_rows:(r + 1) * ctx.own_rows] = mine
+            else:
+                dist.all_reduce(dh, op=dist.ReduceOp.SUM, group=ctx.group)  # every rank needs the full dH of the replicated rows
+        return dh.view(ctx.shape), None, dw, db, None, None, None
 
 
-def vocab_parallel_cross_entropy(hidden, labels, w_shard, bias_shard, v_begin: int, group=None):
-    """See VocabParallelCEFn.  ``v_begin`` = first row of the output layer held by this rank (``shard_range(V + 1, rank, world)``)."""
-    return VocabParallelCEFn.apply(hidden, labels, w_shard, bias_shard, v_begin, group)
+def vocab_parallel_cross_entropy(hidden, labels, w_shard, bias_shard, v_begin: int, group=None, own_rows=None):
+    """See VocabParallelCEFn.  ``v_begin`` = first row of the output layer held by this rank (``shard_range(V + 1, rank, world)``).
+    ``own_rows``: the rows are ``world`` blocks of that many rows in rank order and this rank only consumes the gradient of its own
+    block (the backward then reduce-scatters the dH shares instead of all-reducing them; the other blocks' gradient reads as zero)."""
+    return VocabParallelCEFn.apply(hidden, labels, w_shard, bias_shard, v_begin, group, own_rows)
 
 
 # ------------------------------------------------------------ data-parallel batch x vocab-parallel output layer (cfg4)
@@ -315,7 +327,7 @@ def hybrid_vocab_parallel_loss(hidden, labels, w_shard, bias_shard, v_begin: int
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     scale = float(world) if compensate_grad_average else 1.0
     h_all, l_all, overflow = GatherMaskedRowsFn.apply(hidden, labels, capacity, group, scale)
-    return vocab_parallel_cross_entropy(h_all, l_all, w_shard, bias_shard, v_begin, group), overflow
+    return vocab_parallel_cross_entropy(h_all, l_all, w_shard, bias_shard, v_begin, group, own_rows=h_all.shape[0] // world), overflow
 
 
 # ------------------------------------------------------------------------ row-sharded item table: input lookup
