@@ -116,6 +116,13 @@ int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bia
                    float* pre, int64_t M, int N, int K, int act, const float* residual, int64_t ldres,
                    const int64_t* row_tok, float pA, uint64_t siteA, float pB, uint64_t siteB, uint64_t seed,
                    rbm_stream_t stream);
+/* the same call with a scratch buffer of rbm_linear_fwd_ws_bytes(M,N,K) bytes (may be 0): wide layers (N, K >= 128) with
+ * M >= 512 rows then run on the split-fp16 tiled tensor kernel, which keeps fp16 hi/lo copies of w in the scratch */
+size_t rbm_linear_fwd_ws_bytes(int64_t M, int N, int K);
+int rbm_linear_fwd_ws(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
+                      float* pre, int64_t M, int N, int K, int act, const float* residual, int64_t ldres,
+                      const int64_t* row_tok, float pA, uint64_t siteA, float pB, uint64_t siteB, uint64_t seed,
+                      void* ws, size_t ws_bytes, rbm_stream_t stream);
 /* elementwise backward of the epilogue: dres = rowkeep*maskB*dout (may be NULL), dpre = dres*maskA*act'(pre) */
 int rbm_linear_epilogue_bwd(const float* dout, const float* pre, float* dpre, float* dres, int64_t M, int N,
                             int act, const int64_t* row_tok, float pA, uint64_t siteA, float pB,

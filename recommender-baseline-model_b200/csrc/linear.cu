@@ -10,6 +10,7 @@
 #include "common.cuh"
 #include "tc_gemm.cuh"
 #include "tc_dw16.cuh"
+#include "tc_gemm16.cuh"
 
 namespace {
 
@@ -350,10 +351,27 @@ int tn_splits(int64_t M, int N, int K) {
 
 }  // namespace
 
+// wide layers with enough rows to fill the machine go to the split-fp16 tiled kernel (tc_gemm16.cu); N = output columns, K = contraction
+// length.  Measured at M = 102400 / 204800 (tools/dbg_gemm16.py): 1.5x .. 2.5x the 3xTF32 kernel from K = 256 up, slower at K = 128
+// (two MMA k-blocks per unit cannot cover the epilogue)
+static bool gemm16_wanted(int64_t M, int N, int K) { return M >= 512 && N >= 128 && K >= 256; }
+
+extern "C" size_t rbm_linear_fwd_ws_bytes(int64_t M, int N, int K) {
+  return gemm16_wanted(M, N, K) && N % 128 == 0 && K % 64 == 0 ? rbm_gemm16_ws_bytes(N, K) : 0;
+}
+
 extern "C" int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
                               float* pre, int64_t M, int N, int K, int act, const float* residual, int64_t ldres,
                               const int64_t* row_tok, float pA, uint64_t siteA, float pB, uint64_t siteB, uint64_t seed,
                               rbm_stream_t stream) {
+  return rbm_linear_fwd_ws(x, ldx, w, bias, y, ldy, pre, M, N, K, act, residual, ldres, row_tok, pA, siteA, pB, siteB, seed, nullptr, 0,
+                           stream);
+}
+
+extern "C" int rbm_linear_fwd_ws(const float* x, int64_t ldx, const float* w, const float* bias, float* y, int64_t ldy,
+                                 float* pre, int64_t M, int N, int K, int act, const float* residual, int64_t ldres,
+                                 const int64_t* row_tok, float pA, uint64_t siteA, float pB, uint64_t siteB, uint64_t seed,
+                                 void* ws, size_t ws_bytes, rbm_stream_t stream) {
   RBM_REQUIRE(x && w && y, "rbm_linear_fwd: null pointer");
   RBM_REQUIRE(M >= 0 && N > 0 && K > 0 && N % 4 == 0 && K % 4 == 0, "rbm_linear_fwd: need N%%4==0 and K%%4==0 (N=%d K=%d)", N, K);
   RBM_REQUIRE(ldx % 4 == 0 && ldy % 4 == 0 && ldx >= K && ldy >= N, "rbm_linear_fwd: bad leading dimensions");
@@ -363,6 +381,12 @@ extern "C" int rbm_linear_fwd(const float* x, int64_t ldx, const float* w, const
   RBM_REQUIRE(rbm_aligned16(x) && rbm_aligned16(w) && rbm_aligned16(y) && rbm_aligned16(bias) && rbm_aligned16(pre) && rbm_aligned16(residual),
               "rbm_linear_fwd: pointers must be 16B aligned");
   if (M == 0) return 0;
+  if (use_tc() && gemm16_wanted(M, N, K) && ws && rbm_aligned16(ws) && ws_bytes >= rbm_gemm16_ws_bytes(N, K) &&
+      rbm_gemm16_supported(M, N, K, ldx, x, w)) {
+    RbmTcEpilogue te{y, ldy, pre, bias, residual, ldres, row_tok, act, rbm_drop_threshold(pA), rbm_drop_threshold(pB),
+                     1.f / (1.f - pA), 1.f / (1.f - pB), siteA, siteB, seed};
+    return rbm_gemm16_launch(x, ldx, w, M, N, K, te, ws, (cudaStream_t)stream);
+  }
   if (use_tc() && ldy % 4 == 0 && rbm_tc_linear_supported(M, N, K, ldx, x, w)) {
     RbmTcEpilogue te{y, ldy, pre, bias, residual, ldres, row_tok, act, rbm_drop_threshold(pA), rbm_drop_threshold(pB),
                      1.f / (1.f - pA), 1.f / (1.f - pB), siteA, siteB, seed};
@@ -393,7 +417,8 @@ extern "C" int rbm_linear_epilogue_bwd(const float* dout, const float* pre, floa
   return 0;
 }
 
-extern "C" size_t rbm_linear_bwd_data_ws_bytes(int N, int K) { return (size_t)N * K * sizeof(float) + 256; }
+// transposed weight (fp32) | its fp16 hi / lo copies + scales for the split-fp16 kernel
+extern "C" size_t rbm_linear_bwd_data_ws_bytes(int N, int K) { return (size_t)N * K * sizeof(float) + 256 + rbm_gemm16_ws_bytes(K, N); }
 
 extern "C" int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const float* w, float* dx, int64_t lddx, int64_t M,
                                    int N, int K, void* ws, size_t ws_bytes, rbm_stream_t stream) {
@@ -414,6 +439,8 @@ extern "C" int rbm_linear_bwd_data(const float* dpre, int64_t lddpre, const floa
     te.y = dx;
     te.ldy = lddx;
     te.invA = te.invB = 1.f;
+    if (gemm16_wanted(M, K, N) && rbm_gemm16_supported(M, K, N, lddpre, dpre, wt))
+      return rbm_gemm16_launch(dpre, lddpre, wt, M, K, N, te, (uint8_t*)ws + (size_t)N * K * sizeof(float) + 256, (cudaStream_t)stream);
     return rbm_tc_linear_launch(dpre, lddpre, wt, M, K, N, te, (cudaStream_t)stream);
   }
   Epilogue ep{};

@@ -39,6 +39,8 @@ SIGNATURES = {
     "rbm_layernorm_bwd_residual": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _SZ, _P]),
     "rbm_layernorm_bwd_fanout": (_I, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _L, _I, _F, _I, _P, _SZ, _P]),
     "rbm_linear_fwd": (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _F, _U64, _F, _U64, _U64, _P]),
+    "rbm_linear_fwd_ws_bytes": (_SZ, [_L, _I, _I]),
+    "rbm_linear_fwd_ws": (_I, [_P, _L, _P, _P, _P, _L, _P, _L, _I, _I, _I, _P, _L, _P, _F, _U64, _F, _U64, _U64, _P, _SZ, _P]),
     "rbm_linear_epilogue_bwd": (_I, [_P, _P, _P, _P, _L, _I, _I, _P, _F, _U64, _F, _U64, _U64, _P]),
     "rbm_linear_bwd_data_ws_bytes": (_SZ, [_I, _I]),
     "rbm_linear_bwd_data": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _P, _SZ, _P]),

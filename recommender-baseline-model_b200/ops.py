@@ -238,10 +238,12 @@ class LinearFn(torch.autograd.Function):
         res2 = _rows2d(residual) if residual is not None else None
         if row_tok is not None:
             row_tok = row_tok.reshape(-1).contiguous()
-        check(lib.rbm_linear_fwd(ptr(x2), x2.stride(0), ptr(w), ptr(bias), ptr(y), N, ptr(pre), M, N, K, int(act), ptr(res2),
-                                 res2.stride(0) if res2 is not None else 0, ptr(row_tok), float(pA), siteA, float(pB), siteB,
-                                 seed, stream()), "linear_fwd")
-        count_launches()
+        nbf = lib.rbm_linear_fwd_ws_bytes(M, N, K)
+        wsf = _ws("lin_fwd", nbf, x.device) if nbf else None
+        check(lib.rbm_linear_fwd_ws(ptr(x2), x2.stride(0), ptr(w), ptr(bias), ptr(y), N, ptr(pre), M, N, K, int(act), ptr(res2),
+                                    res2.stride(0) if res2 is not None else 0, ptr(row_tok), float(pA), siteA, float(pB), siteB,
+                                    seed, ptr(wsf), nbf, stream()), "linear_fwd")
+        count_launches(6 if nbf else 1)
         ctx.save_for_backward(x2, w, pre, row_tok)
         ctx.meta = (int(act), float(pA), siteA, float(pB), siteB, seed, bias is not None, residual is not None, x.shape,
                     residual.shape if residual is not None else None)
