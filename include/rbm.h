@@ -141,6 +141,13 @@ int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const float* x, int
  * P = dropout(softmax(mask(scale * q.k^T)));  out = P.v;  stats[(b*h+hh)*L+i] = {rowmax, 1/rowsum}.
  * replaces Attention.forward NN/models/bert_modules/attention/single.py:13-35 and the core of
  * nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76. */
+/* evaluation (K20): attention of the LAST query position of every sequence only -- q/out are [B, h*dk] (row b = sequence b),
+ * k/v the [B*L, ld] rows of every position.  Same masks as rbm_attn_fwd (the causal mask leaves the last query every key), no
+ * dropout.  Replaces the `[:, -1, :]` slice of NN/trainers/bert.py:47 and NN/models/sas_model/sas.py:111 being taken AFTER the
+ * last block was computed for all L positions. */
+int rbm_attn_last_query(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                        const int64_t* tok, float* out, int64_t ldo, int B, int L, int h, int dk, int mask_mode, float scale,
+                        rbm_stream_t stream);
 int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
                  const int64_t* tok, float* out, int64_t ldo, float* stats, int B, int L, int h, int dk,
                  int mask_mode, float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);

@@ -115,8 +115,9 @@ class BERTModel(BaseModel):
         return 'bert'
 
     # ------------------------------------------------------------------ transformer body (a7-a11)
-    def hidden_states(self, x):
-        """BERT.forward NN/models/bert_modules/bert.py:36-43 -> [B, L, d]."""
+    def hidden_states(self, x, last_only=False):
+        """BERT.forward NN/models/bert_modules/bert.py:36-43 -> [B, L, d]; ``last_only`` (evaluation, K20): [B, d], the last position
+        alone, with the final block computed for that position only (keys / values still from every position)."""
         bert = self.bert
         tok = self._device_long(x)
         Bsz, Ln = tok.shape
@@ -142,6 +143,15 @@ class BERTModel(BaseModel):
         for b, blk in enumerate(bert.transformer_blocks):
             s = base + 1 + 5 * b
             att, ff = blk.attention, blk.feed_forward
+            if last_only and b == len(bert.transformer_blocks) - 1:
+                n1 = ops.layernorm(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+                lq, lk, lv = att.linear_layers
+                kv = ops.linear(n1, torch.cat([lk.weight, lv.weight], 0), torch.cat([lk.bias, lv.bias], 0))
+                ctx = ops.attention_last_query(ops.linear(n1[:, -1, :], lq.weight, lq.bias), kv, tok, Bsz, Ln, h, 0, d, L.MASK_KEYPAD, scale)
+                xl = ops.linear(ctx, att.output_linear.weight, att.output_linear.bias, residual=x[:, -1, :])
+                n2 = ops.layernorm(xl, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+                u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH)
+                return ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=xl)
             n1, x = ops.layernorm_residual(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
             w_qkv = torch.cat([l.weight for l in att.linear_layers], 0)
             b_qkv = torch.cat([l.bias for l in att.linear_layers], 0)
@@ -184,6 +194,8 @@ class BERTModel(BaseModel):
         return ops.score_cross_entropy(h, self._device_long(labels), self.out.weight, self.out.bias)
 
     def last_hidden(self, x):
+        if not self.training and not torch.is_grad_enabled():
+            return self.hidden_states(x, last_only=True)
         return self.hidden_states(x)[:, -1, :]
 
     def _unsharded_only(self, what):

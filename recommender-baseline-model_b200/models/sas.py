@@ -54,8 +54,9 @@ class SASModel(BaseModel):
     def code(cls):
         return 'sas'
 
-    def log2feats(self, log_seqs):
-        """SAS.log2feats NN/models/sas_model/sas.py:59-88 -> [B, L, d]."""
+    def log2feats(self, log_seqs, last_only=False):
+        """SAS.log2feats NN/models/sas_model/sas.py:59-88 -> [B, L, d]; ``last_only`` (evaluation, K20): [B, d], the last position's
+        features, with the final block computed for that position alone (keys / values still from every position)."""
         sas = self.sas
         seq = self._device_long(log_seqs)
         Bsz, Ln = seq.shape
@@ -79,8 +80,17 @@ class SASModel(BaseModel):
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
             # Q and x both have two consumers: layernorm_fanout hands out (Q, Q, x) so that the three gradients meet inside
             # the LayerNorm-backward launch instead of autograd's elementwise adds
-            Q, Qres, xkv = ops.layernorm_fanout(x, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
             w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
+            if last_only and b == len(sas.attention_layers) - 1:
+                Ql = ops.layernorm(x[:, -1, :], ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
+                kv = ops.linear(x, w_in[d:], b_in[d:])
+                ctx = ops.attention_last_query(ops.linear(Ql, w_in[:d], b_in[:d]), kv, None, Bsz, Ln, h, 0, d, L.MASK_CAUSAL, scale)
+                xl = ops.linear(ctx, mha.out_proj.weight, mha.out_proj.bias, residual=Ql)
+                xl = ops.layernorm(xl, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
+                u = ops.linear(xl, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU)
+                xl = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xl, row_tok=seq[:, -1])
+                return ops.layernorm(xl, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
+            Q, Qres, xkv = ops.layernorm_fanout(x, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
             q = ops.linear(Q, w_in[:d], b_in[:d])          # q from the normalised stream
             kv = ops.linear(xkv, w_in[d:], b_in[d:])       # k, v from the un-normalised stream (sas.py:75)
             ctx = ops.attention(q, kv, None, Bsz, Ln, h, 0, 0, d, L.MASK_CAUSAL, scale, p, seed, s)
@@ -119,6 +129,8 @@ class SASModel(BaseModel):
         return loss
 
     def last_hidden(self, log_seqs):
+        if not self.training and not torch.is_grad_enabled():
+            return self.log2feats(log_seqs, last_only=True)
         return self.log2feats(log_seqs)[:, -1, :]
 
     def predict(self, log_seqs, item_indices):  # for inference

