@@ -644,6 +644,8 @@ static bool v2_fits(int N, int K, int* nstage_out) {
 // Column groups of the persistent kernel: the fewest equal blocks of output columns whose weight block (raw + TF32
 // residual) stays resident in shared memory next to at least two A stages.  0 = no such split.
 static int pick_groups(int N, int K, int* nstage_out) {
+  // (measured and dropped: preferring >= 64-column blocks that leave room for the A stages of two row tiles -- N = 256, K = 64 then
+  //  runs as two groups with four stages instead of one group with two -- changed nothing: 138 vs 134 us, tools/time_linear_cfg2.py)
   for (int ng = 1; ng <= 32; ++ng) {
     if (N % ng != 0 || (N / ng) % 16 != 0) continue;
     if (v2_fits(N / ng, K, nstage_out)) return ng;
