@@ -158,6 +158,22 @@ int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
                  int64_t lddv, int B, int L, int h, int dk, int mask_mode, float scale, float p, uint64_t seed,
                  uint64_t site, void* ws, size_t ws_bytes, rbm_stream_t stream);
 
+/* ---- live-row compaction around the token-wise layers of SASRec (csrc/rows.cu) ----------------------
+ * The reference zeroes the rows of padding positions after the embedding and after every block (`seqs *= ~timeline_mask`,
+ * NN/models/sas_model/sas.py:67,86): those rows are exactly zero at every block input, their keys / values equal the projection
+ * bias, and what the block computes for them is multiplied by zero -- value and gradient.  rows / count: rbm_compact_labels applied
+ * to the token ids; cap >= *count is a host-side capacity (compact rows past *count are zero / ignored).
+ *   gather : dst[r] = r < *count ? src[rows[r]] : 0                          [n, d] -> [cap, d]
+ *   scatter: dst[rows[r]] = src[r]; rows with tok == 0 get `fill` ([d], may be NULL = zeros)   [cap, d] -> [n, d]
+ *   dead_colsum: out[c] = sum over rows with tok == 0 of src[row, c] (the gradient of `fill`), fixed summation order */
+int rbm_rows_gather(const float* src, int64_t ld, const int32_t* rows, const int32_t* count, int64_t cap, int d, float* dst,
+                    rbm_stream_t stream);
+int rbm_rows_scatter(const float* src, const int32_t* rows, const int32_t* count, int64_t cap, int d, const float* fill,
+                     const int64_t* tok, int64_t n, float* dst, int64_t ldd, rbm_stream_t stream);
+size_t rbm_rows_dead_colsum_ws_bytes(int d);
+int rbm_rows_dead_colsum(const float* src, int64_t ld, const int64_t* tok, int64_t n, int d, float* out, void* ws, size_t ws_bytes,
+                         rbm_stream_t stream);
+
 /* ---- BERT4Rec output scoring fused with masked cross-entropy (logits never materialised) ------------
  * rows with labels != 0 are compacted (ascending); for those rows logits = h.w^T + bias over V1 = V+1
  * columns; loss = mean(logsumexp - target logit).

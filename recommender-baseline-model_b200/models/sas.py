@@ -5,6 +5,7 @@ NN/models/sas_model/sas.py:24-118), computed by the sm_100a kernels of librbm_b2
 given torch seed yields the reference's initial weights); their own ``forward`` is never used.
 """
 import math
+import os
 
 import torch
 import torch.nn as nn
@@ -75,6 +76,9 @@ class SASModel(BaseModel):
                                   base, sh.group, grad_unscale=float(sh.world))
             seed = (seed + (sh.rank + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         scale = math.sqrt(1.0 / (d // h))
+        live = self._live_rows(seq) if (train and sh is None and not last_only) else None
+        if live is not None:
+            return self._blocks_live_rows(x, live, Bsz, Ln, p, seed, base, scale)
         for b in range(len(sas.attention_layers)):
             s = base + 1 + 3 * b
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
@@ -99,6 +103,62 @@ class SASModel(BaseModel):
             u = ops.linear(x, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU, pA=p, siteA=s + 1, seed=seed)
             x = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xres, row_tok=seq, pA=p, siteA=s + 2, seed=seed)
         return ops.layernorm(x, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
+
+    # ------------------------------------------------------------------ live-row path (training)
+    LIVE_ROWS_MAX_FRACTION = 0.6  # above this share of non-padding rows the dense path is used
+
+    def _live_rows(self, seq):
+        """Plan of the live-row path for this batch, or None for the dense path.  Eager steps read the number of non-padding
+        positions back (one host sync); under a CUDA graph the trainer fixes the capacity before capture (``_row_cap``: rows,
+        0 = dense) and checks every replayed batch against it."""
+        if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0":
+            return None
+        n = seq.numel()
+        cap = getattr(self, "_row_cap", None)
+        if cap is None:
+            cnt = int(torch.count_nonzero(seq).item())
+            if cnt > self.LIVE_ROWS_MAX_FRACTION * n:
+                return None
+            cap = max(128, -(-cnt // 128) * 128)
+        elif cap <= 0:
+            return None
+        return ops.LiveRows(seq, cap)
+
+    def row_capacity_for(self, seq) -> int:
+        """Capacity (rows) a captured step should be built with for batches like ``seq``: 25 % headroom over its live rows, 0 when
+        the dense path is the better choice.  ``live_row_count`` tells the trainer whether a later batch still fits."""
+        if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
+            return 0
+        n, cnt = int(seq.numel()), self.live_row_count(seq)
+        cap = -(-(cnt + cnt // 4 + 256) // 128) * 128
+        return cap if cap <= self.LIVE_ROWS_MAX_FRACTION * n else 0
+
+    @staticmethod
+    def live_row_count(seq) -> int:
+        return int(torch.count_nonzero(torch.as_tensor(seq)).item())
+
+    def _blocks_live_rows(self, x, live, Bsz, Ln, p, seed, base, scale):
+        """The block loop with LayerNorm / Linear / feed-forward on the live rows only (csrc/rows.cu explains why that is exact).
+        Attention keeps the [B, L] layout: queries are scattered back (padding rows: zeros, their outputs are never read), keys /
+        values too (padding rows: the projection bias, which is what W.0 + b gives the reference).  The element-wise dropout sites
+        of this path index their Philox stream by (live-row ordinal, column)."""
+        sas = self.sas
+        d, h = sas.hidden, sas.heads
+        xc = ops.rows_gather(x.view(-1, d), live)
+        for b in range(len(sas.attention_layers)):
+            s = base + 1 + 3 * b
+            ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
+            w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
+            Q, Qres, xkv = ops.layernorm_fanout(xc, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
+            q = ops.rows_scatter(ops.linear(Q, w_in[:d], b_in[:d]), None, live)
+            kv = ops.rows_scatter(ops.linear(xkv, w_in[d:], b_in[d:]), b_in[d:], live)
+            ctx = ops.attention(q, kv, None, Bsz, Ln, h, 0, 0, d, L.MASK_CAUSAL, scale, p, seed, s)
+            xc = ops.linear(ops.rows_gather(ctx.view(-1, d), live), mha.out_proj.weight, mha.out_proj.bias, residual=Qres)
+            xc, xres, _ = ops.layernorm_fanout(xc, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
+            u = ops.linear(xc, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU, pA=p, siteA=s + 1, seed=seed)
+            xc = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xres, pA=p, siteA=s + 2, seed=seed)
+        out = ops.layernorm(xc, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
+        return ops.rows_scatter(out, sas.last_layernorm.bias, live).view(Bsz, Ln, d)
 
     def forward(self, log_seqs, pos_seqs, neg_seqs):  # for training
         """NN/models/sas_model/sas.py:90-105 -> (pos_logits, neg_logits) [B, L]."""

@@ -46,6 +46,94 @@ def scatter_add_sorted_(grad: torch.Tensor, idx: torch.Tensor, src: torch.Tensor
     return grad
 
 
+# ------------------------------------------------------------------------------------- live-row compaction (SASRec)
+class LiveRows:
+    """The live (token != 0) rows of a [B, L] batch: ascending row ids + count on the device (rbm_compact_labels applied to the
+    token ids) and a host-side capacity ``cap`` >= count: the token-wise layers run on [cap, d] tensors (csrc/rows.cu)."""
+
+    def __init__(self, tok: torch.Tensor, cap: int):
+        lib = L.load()
+        L.require_cuda(tok)
+        self.tok = tok.reshape(-1).contiguous()
+        self.n = self.tok.numel()
+        self.cap = int(cap)
+        dev = tok.device
+        self.rows = torch.empty(self.n, device=dev, dtype=torch.int32)
+        self._tgt = torch.empty(self.n, device=dev, dtype=torch.int64)
+        self.count = torch.empty(1, device=dev, dtype=torch.int32)
+        nb = lib.rbm_compact_ws_bytes(self.n)
+        ws = _ws("compact", nb, dev)
+        check(lib.rbm_compact_labels(ptr(self.tok), self.n, ptr(self.rows), ptr(self._tgt), ptr(self.count), ptr(ws), nb, stream()),
+              "compact_labels")
+        count_launches(3)
+
+
+def _rows_gather(x2, live):
+    lib = L.load()
+    out = torch.empty(live.cap, x2.shape[1], device=x2.device, dtype=torch.float32)
+    check(lib.rbm_rows_gather(ptr(x2), x2.stride(0), ptr(live.rows), ptr(live.count), live.cap, x2.shape[1], ptr(out), stream()), "rows_gather")
+    count_launches()
+    return out
+
+
+def _rows_scatter(xc, live, fill):
+    lib = L.load()
+    d = xc.shape[1]
+    out = torch.empty(live.n, d, device=xc.device, dtype=torch.float32)
+    check(lib.rbm_rows_scatter(ptr(xc), ptr(live.rows), ptr(live.count), live.cap, d, ptr(fill), ptr(live.tok), live.n, ptr(out), d, stream()),
+          "rows_scatter")
+    count_launches()
+    return out
+
+
+class RowsGatherFn(torch.autograd.Function):
+    """[n, d] -> [cap, d]: the live rows in ascending order, zero rows after them."""
+
+    @staticmethod
+    def forward(ctx, x, live):
+        x2 = _rows2d(x)
+        ctx.live, ctx.shape = live, x.shape
+        return _rows_gather(x2, live)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return _rows_scatter(dy.contiguous(), ctx.live, None).view(ctx.shape), None
+
+
+class RowsScatterFn(torch.autograd.Function):
+    """[cap, d] -> [n, d]: live rows back in place; the rows of padding positions hold ``fill`` ([d]; None = zeros)."""
+
+    @staticmethod
+    def forward(ctx, xc, fill, live):
+        ctx.live, ctx.has_fill = live, fill is not None
+        return _rows_scatter(xc.contiguous(), live, fill.contiguous() if fill is not None else None)
+
+    @staticmethod
+    def backward(ctx, dy):
+        lib = L.load()
+        live = ctx.live
+        dy2 = _rows2d(dy)
+        dxc = _rows_gather(dy2, live)
+        dfill = None
+        if ctx.has_fill and ctx.needs_input_grad[1]:
+            d = dy2.shape[1]
+            dfill = torch.empty(d, device=dy.device, dtype=torch.float32)
+            nb = lib.rbm_rows_dead_colsum_ws_bytes(d)
+            ws = _ws("rows_colsum", nb, dy.device)
+            check(lib.rbm_rows_dead_colsum(ptr(dy2), dy2.stride(0), ptr(live.tok), live.n, d, ptr(dfill), ptr(ws), nb, stream()),
+                  "rows_dead_colsum")
+            count_launches(2)
+        return dxc, dfill, None
+
+
+def rows_gather(x, live):
+    return RowsGatherFn.apply(x, live)
+
+
+def rows_scatter(xc, fill, live):
+    return RowsScatterFn.apply(xc, fill, live)
+
+
 # --------------------------------------------------------------------------------------------- embedding
 class EmbedFn(torch.autograd.Function):
     """out = keep * dropout(table[tok]*scale + pos)   (K1-K3, K12)."""

@@ -106,6 +106,12 @@ class AbstractTrainer(metaclass=ABCMeta):
         sync = self.dist_sync if (self.dist_sync is not None and self.dist_sync.world > 1) else None
         dev = torch.device(self.device)
         static = tuple(torch.as_tensor(x).to(dev).clone() for x in example_batch)
+        # SASRec runs its token-wise layers on the non-padding rows only (models/sas.py, csrc/rows.cu): a graph needs a fixed row
+        # capacity, chosen from the example batch (0 = dense path); _replay sends a batch that does not fit through an eager step
+        self._graph_row_cap = 0
+        if hasattr(self.model, "row_capacity_for"):
+            self._graph_row_cap = self.model.row_capacity_for(static[0])
+            self.model._row_cap = self._graph_row_cap
         # warm-up on a side stream (lazy one-time work: function attributes, context binding, workspaces, Adam state, the
         # NCCL communicator), then put model / optimizer / step counters back so that the captured step is the next real one
         model_sd = copy.deepcopy(self.model.state_dict())
@@ -151,7 +157,9 @@ class AbstractTrainer(metaclass=ABCMeta):
                     self._graph_counter.add_(1)
         except BaseException:
             L.load().rbm_set_step_counter(None)
+            self.model._row_cap = None
             raise
+        self.model._row_cap = None  # eager steps (odd-shaped or over-capacity batches) size themselves
         self._graph_launches = L.launch_count - launches0
         self._graph, self._graph_b, self._graph_static, self._graph_loss, self._graph_lr = graph, graph_b, static, loss, self.get_lr()
         L.workspaces.freeze()  # the graph has the workspace addresses baked in: they must outlive every replay
@@ -218,6 +226,8 @@ class AbstractTrainer(metaclass=ABCMeta):
         batch = tuple(torch.as_tensor(x) for x in batch)
         if len(batch) != len(self._graph_static) or any(tuple(s.shape) != tuple(d.shape) for s, d in zip(batch, self._graph_static)):
             return self._odd_shaped_step(batch)  # never copy_ a mismatching batch: a 1-row remainder would broadcast silently
+        if self._graph_row_cap and self.model.live_row_count(batch[0]) > self._graph_row_cap:
+            return self._odd_shaped_step(batch)  # more non-padding rows than the captured live-row capacity
         for dst, src in zip(self._graph_static, batch):
             dst.copy_(src, non_blocking=True)
         self._graph.replay()

@@ -95,13 +95,17 @@ def test_bert_adam_trajectory():
         relclose(v.cpu().numpy(), after[k].numpy(), 2e-3, msg=k)
 
 
+@pytest.mark.parametrize("live_rows", [False, True])
 @pytest.mark.parametrize("name", ["sas_tiny", "sas_odd"])
-def test_sas_vs_reference_golden(name):
+def test_sas_vs_reference_golden(name, live_rows):
+    """``live_rows``: the token-wise layers run on the non-padding rows only (forced here whatever the padding share; off = the
+    dense path) -- same goldens, same tolerances, logits at the padding positions included."""
     z = load(name)
     V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
     model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h))
     model.load_state_dict(sd_of(z))
     model.to(DEV).train()
+    model.LIVE_ROWS_MAX_FRACTION = 1.0 if live_rows else -1.0
     pl, nl = model(z["seq"], z["pos"], z["neg"])  # numpy in, like the reference
     relclose(pl.detach().cpu().numpy(), z["pos_logits"], 1e-4, msg="pos_logits")
     relclose(nl.detach().cpu().numpy(), z["neg_logits"], 1e-4, msg="neg_logits")
@@ -475,3 +479,136 @@ def test_eval_last_position_only(kind, V, Ln, d, nb, h, B):
         relclose(sc.cpu().numpy(), ref.cpu().numpy(), 1e-5, msg="candidate scores")
     # the training-mode / grad-enabled path still computes every position
     assert model.last_hidden(x).shape == full.shape
+
+
+@pytest.mark.gpu
+def test_rows_gather_scatter():
+    """csrc/rows.cu against torch indexing: gather (zero rows past the count), scatter with / without a fill vector, and the
+    gradients (scatter backward = gather + the fixed-order column sum over the padding rows)."""
+    g = torch.Generator(device=DEV).manual_seed(3)
+    for n, d, frac in ((1000, 64, 0.2), (4097, 128, 0.9), (300, 16, 0.0), (513, 256, 1.0), (700, 100, 0.5), (260, 1024, 0.3)):
+        tok = (torch.rand(n, device=DEV, generator=g) < frac).long() * torch.randint(1, 50, (n,), device=DEV, generator=g)
+        cnt = int((tok != 0).sum())
+        cap = max(128, -(-cnt // 128) * 128) + 128
+        live = ops.LiveRows(tok, cap)
+        assert int(live.count.item()) == cnt
+        idx = torch.nonzero(tok).flatten()
+        np.testing.assert_array_equal(live.rows[:cnt].cpu().numpy(), idx.cpu().numpy())
+        x = torch.randn(n, d, device=DEV, generator=g, requires_grad=True)
+        fill = torch.randn(d, device=DEV, generator=g, requires_grad=True)
+        xc = ops.rows_gather(x, live)
+        assert xc.shape == (cap, d) and torch.equal(xc[:cnt], x[idx]) and not xc[cnt:].any()
+        y = ops.rows_scatter(xc * 2.0, fill, live)
+        ref = torch.where((tok != 0)[:, None], x * 2.0, fill[None, :].expand(n, d))
+        assert torch.equal(y, ref)
+        dy = torch.randn(n, d, device=DEV, generator=g)
+        y.backward(dy)
+        gx = torch.where((tok != 0)[:, None], dy * 2.0, torch.zeros_like(dy))
+        assert torch.equal(x.grad, gx)
+        gf = dy[tok == 0].double().sum(0)
+        relclose(fill.grad.cpu().numpy(), gf.cpu().numpy(), 1e-5, msg="fill grad")
+        y0 = ops.rows_scatter(xc.detach(), None, live)
+        assert torch.equal(y0, torch.where((tok != 0)[:, None], x.detach(), torch.zeros_like(x)))
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("V,Ln,d,nb,h,B,p", [(300, 50, 128, 2, 2, 64, 0.0), (90, 12, 32, 2, 1, 9, 0.25), (500, 50, 64, 1, 1, 300, 0.2)])
+def test_sas_live_rows_training(V, Ln, d, nb, h, B, p):
+    """SASRec with the token-wise layers on the non-padding rows only (Amazon-Beauty-like left padding: 80-90 % of the positions):
+    loss and EVERY gradient against the oracle -- dropout on: the oracle consumes the Philox masks the kernels used, the
+    element-wise sites of this path being indexed by (live-row ordinal, column) -- and against the dense path at p = 0."""
+    from oracle.common import DropoutPlan
+    rng = np.random.RandomState(V + B)
+    seq = rng.randint(1, V + 1, size=(B, Ln)).astype(np.int64)
+    for b in range(B):
+        seq[b, : Ln - rng.randint(0, max(2, Ln // 5))] = 0  # 0 .. L/5 - 1 items, right-aligned; some rows are empty
+    seq[B // 2] = rng.randint(1, V + 1, size=Ln)  # one full-length history
+    pos = np.where(seq != 0, rng.randint(1, V + 1, size=(B, Ln)), 0)
+    neg = np.where(seq != 0, rng.randint(1, V + 1, size=(B, Ln)), 0)
+    pos[0, 0] = 3  # a labelled position on a padding row: its features are the last LayerNorm's beta
+    neg[0, 0] = 5
+    model = rbm_b200.model_factory(sas_args(V, Ln, d, nb, h, p=p))
+    model.load_state_dict(osr.random_state_dict(V, Ln, d, nb, seed=11))
+    model.to(DEV).train()
+    model.dropout_seed = 777
+    assert model._live_rows(torch.from_numpy(seq).to(DEV)) is not None
+    step0 = model._step
+    launches0 = rbm_b200.lib.launch_count
+    loss = model.loss(seq, pos, neg)
+    loss.backward()
+    sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+    tseq, tpos, tneg = (torch.from_numpy(x) for x in (seq, pos, neg))
+    if p == 0.0:
+        ref = osr.loss(sd, tseq, tpos, tneg, nb, h)
+    else:
+        live = np.flatnonzero(seq.reshape(-1))
+        cap = max(128, -(-len(live) // 128) * 128)
+        base = step0 * 64
+        masks = {0: ops.dropout_mask(B * Ln * d, p, 777, base, DEV).cpu()}
+        for b in range(nb):
+            s = osr.block_sites(b)
+            masks[s["attn"]] = ops.dropout_mask_attn(B * h * Ln, Ln, p, 777, base + s["attn"], DEV).cpu()
+            for key in ("ffn1", "ffn2"):
+                mc = ops.dropout_mask(cap * d, p, 777, base + s[key], DEV).cpu().reshape(cap, d)
+                full = torch.ones(B * Ln, d, dtype=mc.dtype)  # padding rows: whatever, they are multiplied by zero
+                full[torch.from_numpy(live)] = mc[: len(live)]
+                masks[s[key]] = full
+        ref = osr.loss(sd, tseq, tpos, tneg, nb, h, p=p, drop=DropoutPlan(True, masks))
+    ref.backward()
+    assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()), (loss.item(), ref.item())
+    for k, prm in model.named_parameters():
+        gr = sd[k].grad if sd[k].grad is not None else torch.zeros_like(sd[k])
+        relclose(prm.grad.cpu().numpy(), gr.numpy(), 1e-3, msg=k)
+    if p == 0.0:  # the dense path on the same batch: same loss to rounding
+        model.zero_grad()
+        model.LIVE_ROWS_MAX_FRACTION = -1.0
+        dense = model.loss(seq, pos, neg)
+        assert abs(dense.item() - loss.item()) < 1e-6 * abs(loss.item())
+    del launches0
+
+
+@pytest.mark.gpu
+def test_sas_live_rows_cuda_graph():
+    """The captured SASRec step with a fixed live-row capacity: replays are bit-identical to eager steps run with the same
+    capacity; a batch with more non-padding rows than the capacity takes an eager step and training continues."""
+    V, Ln, d, B = 80, 20, 32, 48
+    rs = np.random.RandomState(5)
+
+    def batch(i, keep=4):
+        s = rs.randint(1, V + 1, size=(B, Ln))
+        for b in range(B):
+            s[b, : Ln - rs.randint(1, keep + 1)] = 0
+        p_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+        n_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+        return tuple(torch.from_numpy(x).to(DEV) for x in (s, p_, n_))
+
+    a = sas_args(V, Ln, d, 2, 1, p=0.2)
+    common = dict(optimizer="Adam", lr=2e-3, weight_decay=0, momentum=None, decay_step=50, gamma=1.0, num_epochs=1, metric_ks=[10],
+                  best_metric="NDCG@10", train_batch_size=B, resume_path=None, l2_emb=0.0)
+    batches = [batch(i) for i in range(5)]
+    torch.manual_seed(0)
+    m1, m2 = rbm_b200.model_factory(a), rbm_b200.model_factory(a)
+    m2.load_state_dict(m1.state_dict())
+    m2.dropout_seed = m1.dropout_seed
+    t1 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m1, None, None, None, None)
+    t2 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m2, None, None, None, None)
+    m1.train(); m2.train()
+    t2.capture_train_step(batches[0])
+    cap = t2._graph_row_cap
+    assert 0 < cap < B * Ln
+    m1._row_cap = cap  # the eager twin runs with the captured capacity
+    # a batch that does not fit the capacity: eager step inside the graphed trainer, dense / self-sized in the twin
+    sf = rs.randint(1, V + 1, size=(B, Ln))
+    big = tuple(torch.from_numpy(x).to(DEV) for x in (sf, rs.randint(1, V + 1, size=(B, Ln)), rs.randint(1, V + 1, size=(B, Ln))))
+    assert m2.live_row_count(big[0]) > cap
+    # (the twin takes all its steps first: the device-side step counter the captured trainer installs is process-wide)
+    eager = [t1.train_step(b).item() for b in batches]
+    m1._row_cap = None
+    eager.append(t1.train_step(big).item())
+    m1._row_cap = cap
+    eager.append(t1.train_step(batches[1]).item())
+    graphed = [t2.train_step(b).item() for b in batches + [big, batches[1]]]
+    assert eager == graphed, (eager, graphed)
+    t2.release_train_graph()
+    for (k, v1), (_, v2) in zip(m1.state_dict().items(), m2.state_dict().items()):
+        assert torch.equal(v1, v2), k
