@@ -173,6 +173,26 @@ int rbm_rows_scatter(const float* src, const int32_t* rows, const int32_t* count
 size_t rbm_rows_dead_colsum_ws_bytes(int d);
 int rbm_rows_dead_colsum(const float* src, int64_t ld, const int64_t* tok, int64_t n, int d, float* out, void* ws, size_t ws_bytes,
                          rbm_stream_t stream);
+/* out[c] = sum of the first *count rows of the compact [cap, d] tensor (ws: rbm_rows_dead_colsum_ws_bytes(d)) */
+int rbm_rows_live_colsum(const float* src, int64_t ld, const int32_t* count, int64_t cap, int d, float* out, void* ws,
+                         size_t ws_bytes, rbm_stream_t stream);
+
+/* ---- SASRec attention on the compact (live-row) layout (csrc/attention_live.cu) ---------------------
+ * q [cap, h*dk] and kv [cap, 2*h*dk] (k | v) hold the live rows in ascending (sequence, position) order (rows / count / tok as
+ * above); every padding position's key / value is bkv = [b_k | b_v] (the projection bias: its input row is exactly zero).  Causal
+ * softmax over the live keys j <= i plus n_dead(i) copies of the padding key; dropout fields are indexed by (sequence-head, i, j)
+ * over the [L x L] positions exactly as in rbm_attn_fwd.  L <= 64, d_k <= 128.  stats [cap, h, 2].
+ * Backward: dq [cap, h*dk], dkv [cap, 2*h*dk] and per-query rows dead [cap, 2*h*dk] whose column sum (rbm_rows_live_colsum) is the
+ * gradient of bkv; delta [cap, h] is scratch.  Replaces the core of nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76 on that layout. */
+/* seq_start[b] = first compact row of sequence b (b = 0..B: B + 1 entries), from the ascending row ids */
+int rbm_rows_seq_start(const int32_t* rows, const int32_t* count, int B, int L, int32_t* seq_start, rbm_stream_t stream);
+int rbm_attn_live_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* bkv, const int32_t* rows,
+                      const int32_t* seq_start, const int64_t* tok, float* out, float* stats, int B, int L, int h, int dk,
+                      float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
+int rbm_attn_live_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* bkv, const int32_t* rows,
+                      const int32_t* seq_start, const int64_t* tok, const float* out, const float* stats, const float* dout,
+                      float* dq, float* dkv, float* dead, float* delta, int B, int L, int h, int dk, float scale, float p,
+                      uint64_t seed, uint64_t site, rbm_stream_t stream);
 
 /* ---- BERT4Rec output scoring fused with masked cross-entropy (logits never materialised) ------------
  * rows with labels != 0 are compacted (ascending); for those rows logits = h.w^T + bias over V1 = V+1

@@ -116,6 +116,7 @@ int rbm_step_ptr_set_attention_tc(const unsigned long long*);
 int rbm_step_ptr_set_attention_pair(const unsigned long long*);
 int rbm_step_ptr_set_attention_seq(const unsigned long long*);
 int rbm_step_ptr_set_gemm16(const unsigned long long*);
+int rbm_step_ptr_set_attention_live(const unsigned long long*);
 
 extern "C" int rbm_set_step_counter(const uint64_t* counter) {
   const unsigned long long* p = reinterpret_cast<const unsigned long long*>(counter);
@@ -127,6 +128,7 @@ extern "C" int rbm_set_step_counter(const uint64_t* counter) {
   if (!rc) rc = rbm_step_ptr_set_attention_pair(p);
   if (!rc) rc = rbm_step_ptr_set_attention_seq(p);
   if (!rc) rc = rbm_step_ptr_set_gemm16(p);
+  if (!rc) rc = rbm_step_ptr_set_attention_live(p);
   if (!rc) rc = rbm_step_ptr_set_adam(p);
   if (rc) rbm_set_error("rbm_set_step_counter: cudaMemcpyToSymbol: %s", cudaGetErrorString((cudaError_t)rc));
   return rc;

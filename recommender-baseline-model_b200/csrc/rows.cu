@@ -42,16 +42,18 @@ __global__ void __launch_bounds__(256) rows_scatter_kernel(const float* __restri
 constexpr int DC_BLOCKS = 8 * RBM_NUM_SMS;
 // stage 1: block b sums the padding rows of its contiguous row range.  Thread t owns the float4 column group t % d4 of the rows
 // r0 + t / d4, + 256 / d4, ... (ascending); the 256 / d4 row lanes are then added in lane order: a fixed summation tree.
+// rows that count: tok[r] == 0 (the padding rows of a [B*L] layout), or, with tok == nullptr, the first *count rows (compact layout)
 __global__ void __launch_bounds__(256) dead_colsum_partial_kernel(const float* __restrict__ src, int64_t ld, const int64_t* __restrict__ tok,
-                                                                  int64_t n, int d, float* __restrict__ part) {
+                                                                  const int32_t* __restrict__ count, int64_t n, int d, float* __restrict__ part) {
   __shared__ float4 red[256];
   const int d4 = d >> 2, nro = 256 / d4;  // d <= 1024: at least one row lane; threads past nro * d4 idle
   const int cg = threadIdx.x % d4, ro = threadIdx.x / d4;
+  if (!tok && n > *count) n = *count;
   const int64_t per = (n + gridDim.x - 1) / gridDim.x, r0 = blockIdx.x * per, r1 = r0 + per < n ? r0 + per : n;
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (ro < nro)
     for (int64_t r = r0 + ro; r < r1; r += nro)
-      if (tok[r] == 0) {
+      if (!tok || tok[r] == 0) {
         const float4 v = ld4(src + r * ld + cg * 4);
         s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
       }
@@ -115,9 +117,24 @@ extern "C" int rbm_rows_dead_colsum(const float* src, int64_t ld, const int64_t*
               "rbm_rows_dead_colsum: need d %% 4 == 0, d <= 1024 (d=%d)", d);
   RBM_REQUIRE(ws_bytes >= rbm_rows_dead_colsum_ws_bytes(d), "rbm_rows_dead_colsum: workspace too small");
   float* part = (float*)ws;
-  dead_colsum_partial_kernel<<<DC_BLOCKS, 256, 0, (cudaStream_t)stream>>>(src, ld, tok, n, d, part);
+  dead_colsum_partial_kernel<<<DC_BLOCKS, 256, 0, (cudaStream_t)stream>>>(src, ld, tok, nullptr, n, d, part);
   RBM_LAUNCH_CHECK("rbm_rows_dead_colsum");
   dead_colsum_final_kernel<<<(unsigned)d, 256, 0, (cudaStream_t)stream>>>(part, DC_BLOCKS, d, out);
   RBM_LAUNCH_CHECK("rbm_rows_dead_colsum(final)");
+  return 0;
+}
+
+// out[c] = sum of the first *count rows of src [cap, d] (compact layout), same fixed summation tree
+extern "C" int rbm_rows_live_colsum(const float* src, int64_t ld, const int32_t* count, int64_t cap, int d, float* out, void* ws,
+                                    size_t ws_bytes, rbm_stream_t stream) {
+  RBM_REQUIRE(src && count && out && ws, "rbm_rows_live_colsum: null pointer");
+  RBM_REQUIRE(cap >= 0 && d >= 4 && d <= 1024 && d % 4 == 0 && ld >= d && ld % 4 == 0 && rbm_aligned16(src),
+              "rbm_rows_live_colsum: need d %% 4 == 0, d <= 1024 (d=%d)", d);
+  RBM_REQUIRE(ws_bytes >= rbm_rows_dead_colsum_ws_bytes(d), "rbm_rows_live_colsum: workspace too small");
+  float* part = (float*)ws;
+  dead_colsum_partial_kernel<<<DC_BLOCKS, 256, 0, (cudaStream_t)stream>>>(src, ld, nullptr, count, cap, d, part);
+  RBM_LAUNCH_CHECK("rbm_rows_live_colsum");
+  dead_colsum_final_kernel<<<(unsigned)d, 256, 0, (cudaStream_t)stream>>>(part, DC_BLOCKS, d, out);
+  RBM_LAUNCH_CHECK("rbm_rows_live_colsum(final)");
   return 0;
 }

@@ -139,9 +139,10 @@ class SASModel(BaseModel):
 
     def _blocks_live_rows(self, x, live, Bsz, Ln, p, seed, base, scale):
         """The block loop with LayerNorm / Linear / feed-forward on the live rows only (csrc/rows.cu explains why that is exact).
-        Attention keeps the [B, L] layout: queries are scattered back (padding rows: zeros, their outputs are never read), keys /
-        values too (padding rows: the projection bias, which is what W.0 + b gives the reference).  The element-wise dropout sites
-        of this path index their Philox stream by (live-row ordinal, column)."""
+        Attention runs on the same compact layout (csrc/attention_live.cu: every padding key of a sequence is the projection bias,
+        which is what W.0 + b gives the reference, so they enter as one key with a multiplicity); sequences longer than 64 keep the
+        dense kernels on the [B, L] layout (queries / keys / values scattered back).  The element-wise dropout sites of this path
+        index their Philox stream by (live-row ordinal, column); the attention site by (sequence-head, i, j) as always."""
         sas = self.sas
         d, h = sas.hidden, sas.heads
         xc = ops.rows_gather(x.view(-1, d), live)
@@ -150,10 +151,15 @@ class SASModel(BaseModel):
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
             w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
             Q, Qres, xkv = ops.layernorm_fanout(xc, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
-            q = ops.rows_scatter(ops.linear(Q, w_in[:d], b_in[:d]), None, live)
-            kv = ops.rows_scatter(ops.linear(xkv, w_in[d:], b_in[d:]), b_in[d:], live)
-            ctx = ops.attention(q, kv, None, Bsz, Ln, h, 0, 0, d, L.MASK_CAUSAL, scale, p, seed, s)
-            xc = ops.linear(ops.rows_gather(ctx.view(-1, d), live), mha.out_proj.weight, mha.out_proj.bias, residual=Qres)
+            q = ops.linear(Q, w_in[:d], b_in[:d])
+            kv = ops.linear(xkv, w_in[d:], b_in[d:])
+            if Ln <= 64 and d // h <= 128:  # compact attention: the padding keys of a sequence are one key with a multiplicity
+                ctx = ops.attention_live(q, kv, b_in[d:], live, Bsz, Ln, h, scale, p, seed, s)
+            else:  # dense attention kernels on the [B, L] layout (padding rows: zero queries, the bias as key / value)
+                ctx = ops.attention(ops.rows_scatter(q, None, live), ops.rows_scatter(kv, b_in[d:], live), None, Bsz, Ln, h, 0, 0, d,
+                                    L.MASK_CAUSAL, scale, p, seed, s)
+                ctx = ops.rows_gather(ctx.view(-1, d), live)
+            xc = ops.linear(ctx, mha.out_proj.weight, mha.out_proj.bias, residual=Qres)
             xc, xres, _ = ops.layernorm_fanout(xc, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
             u = ops.linear(xc, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU, pA=p, siteA=s + 1, seed=seed)
             xc = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xres, pA=p, siteA=s + 2, seed=seed)

@@ -66,6 +66,12 @@ class LiveRows:
         check(lib.rbm_compact_labels(ptr(self.tok), self.n, ptr(self.rows), ptr(self._tgt), ptr(self.count), ptr(ws), nb, stream()),
               "compact_labels")
         count_launches(3)
+        self.seq_start = None
+        if tok.dim() == 2:  # first compact row of every sequence (the compact attention walks a sequence's rows)
+            Bsz, Ln = tok.shape
+            self.seq_start = torch.empty(Bsz + 1, device=dev, dtype=torch.int32)
+            check(lib.rbm_rows_seq_start(ptr(self.rows), ptr(self.count), Bsz, Ln, ptr(self.seq_start), stream()), "rows_seq_start")
+            count_launches()
 
 
 def _rows_gather(x2, live):
@@ -429,6 +435,52 @@ class AttnFn(torch.autograd.Function):
 
 def attention(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p=0.0, seed=0, site=0):
     return AttnFn.apply(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p, seed, site)
+
+
+class AttnLiveFn(torch.autograd.Function):
+    """SASRec causal attention on the compact live-row layout (csrc/attention_live.cu): q [cap, d], kv [cap, 2d] (k | v), every
+    padding position's key / value = bkv [2d].  Rows past the live count stay zero."""
+
+    @staticmethod
+    def forward(ctx, q, kv, bkv, live, Bsz, Ln, h, scale, p, seed, site):
+        lib = L.load()
+        L.require_cuda(q, kv, bkv)
+        q, kv, bkv = q.contiguous(), kv.contiguous(), bkv.contiguous()
+        cap, d = q.shape
+        out = torch.zeros(cap, d, device=q.device, dtype=torch.float32)
+        stats = torch.empty(cap, h, 2, device=q.device, dtype=torch.float32)
+        check(lib.rbm_attn_live_fwd(ptr(q), d, ptr(kv), 2 * d, ptr(bkv), ptr(live.rows), ptr(live.seq_start), ptr(live.tok), ptr(out),
+                                    ptr(stats), Bsz, Ln, h, d // h, float(scale), float(p), seed, site, stream()), "attn_live_fwd")
+        count_launches(2)
+        ctx.save_for_backward(q, kv, bkv, out, stats)
+        ctx.live, ctx.meta = live, (Bsz, Ln, h, float(scale), float(p), seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        q, kv, bkv, out, stats = ctx.saved_tensors
+        live = ctx.live
+        Bsz, Ln, h, scale, p, seed, site = ctx.meta
+        cap, d = q.shape
+        dout = dout.contiguous()
+        dq = torch.zeros_like(q)
+        dkv = torch.zeros_like(kv)
+        dead = torch.zeros_like(kv)
+        delta = torch.empty(cap, h, device=q.device, dtype=torch.float32)
+        check(lib.rbm_attn_live_bwd(ptr(q), d, ptr(kv), 2 * d, ptr(bkv), ptr(live.rows), ptr(live.seq_start), ptr(live.tok), ptr(out),
+                                    ptr(stats), ptr(dout), ptr(dq), ptr(dkv), ptr(dead), ptr(delta), Bsz, Ln, h, d // h, scale, p, seed,
+                                    site, stream()), "attn_live_bwd")
+        dbkv = torch.empty(2 * d, device=q.device, dtype=torch.float32)
+        nb = lib.rbm_rows_dead_colsum_ws_bytes(2 * d)
+        ws = _ws("rows_colsum", nb, q.device)
+        check(lib.rbm_rows_live_colsum(ptr(dead), 2 * d, ptr(live.count), cap, 2 * d, ptr(dbkv), ptr(ws), nb, stream()), "rows_live_colsum")
+        count_launches(7)
+        return dq, dkv, dbkv, None, None, None, None, None, None, None, None
+
+
+def attention_live(q, kv, bkv, live, Bsz, Ln, h, scale, p=0.0, seed=0, site=0):
+    return AttnLiveFn.apply(q, kv, bkv, live, Bsz, Ln, h, scale, p, seed, site)
 
 
 def attention_last_query(q, kv, tok, Bsz, Ln, h, kc, vc, mask_mode, scale):
