@@ -69,6 +69,14 @@ int rbm_embed_bwd(const int64_t* tok, const float* dout, float* g, float* dpos, 
 int rbm_embed_fwd_shard(const int64_t* tok, const float* table_shard, const float* pos, float* out, int64_t rows, int L,
                         int d, int64_t vocab, int64_t v_begin, int64_t v_end, float scale, int zero_pad, float p,
                         uint64_t seed, uint64_t site, rbm_stream_t stream);
+/* rbm_embed_bwd (zero_pad = 1) on the live rows only: dout_c / g_c [cap, d] hold row rows[r] of the [B, L] batch in row r (csrc/rows.cu);
+ * idx_c[r] = tok[rows[r]] (0 past *count): the (idx_c, g_c) pair goes to rbm_scatter_add_sorted with cap entries.  dpos [L, d] is
+ * summed per position in ascending row order inside fixed row ranges, then over the ranges.  Dropout stream: the element's index in
+ * the full batch, as in rbm_embed_fwd.  L*d*4 <= 96 KB. */
+size_t rbm_embed_bwd_rows_ws_bytes(int L, int d);
+int rbm_embed_bwd_rows(const int64_t* tok, const int32_t* rows, const int32_t* count, int64_t cap, const float* dout_c,
+                       float* g_c, int64_t* idx_c, float* dpos, int L, int d, float p, uint64_t seed, uint64_t site,
+                       void* ws, size_t ws_bytes, rbm_stream_t stream);
 /* rbm_embed_bwd on a rank's slice of the global batch: `row_offset` = index of its first row in the global batch (dropout
  * element indices continue from there). */
 int rbm_embed_bwd_offset(const int64_t* tok, const float* dout, float* g, float* dpos, int64_t rows, int L, int d,
@@ -163,11 +171,11 @@ int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t ldk, const
  * NN/models/sas_model/sas.py:67,86): those rows are exactly zero at every block input, their keys / values equal the projection
  * bias, and what the block computes for them is multiplied by zero -- value and gradient.  rows / count: rbm_compact_labels applied
  * to the token ids; cap >= *count is a host-side capacity (compact rows past *count are zero / ignored).
- *   gather : dst[r] = r < *count ? src[rows[r]] : 0                          [n, d] -> [cap, d]
+ *   gather : dst[r] = r < *count ? (coef ? coef[rows[r]] : 1) * src[rows[r]] : 0      [n, d] -> [cap, d]
  *   scatter: dst[rows[r]] = src[r]; rows with tok == 0 get `fill` ([d], may be NULL = zeros)   [cap, d] -> [n, d]
  *   dead_colsum: out[c] = sum over rows with tok == 0 of src[row, c] (the gradient of `fill`), fixed summation order */
-int rbm_rows_gather(const float* src, int64_t ld, const int32_t* rows, const int32_t* count, int64_t cap, int d, float* dst,
-                    rbm_stream_t stream);
+int rbm_rows_gather(const float* src, int64_t ld, const int32_t* rows, const int32_t* count, int64_t cap, int d,
+                    const float* coef /* [n] per-source-row factor or NULL */, float* dst, rbm_stream_t stream);
 int rbm_rows_scatter(const float* src, const int32_t* rows, const int32_t* count, int64_t cap, int d, const float* fill,
                      const int64_t* tok, int64_t n, float* dst, int64_t ldd, rbm_stream_t stream);
 size_t rbm_rows_dead_colsum_ws_bytes(int d);
@@ -181,9 +189,9 @@ int rbm_rows_live_colsum(const float* src, int64_t ld, const int32_t* count, int
  * q [cap, h*dk] and kv [cap, 2*h*dk] (k | v) hold the live rows in ascending (sequence, position) order (rows / count / tok as
  * above); every padding position's key / value is bkv = [b_k | b_v] (the projection bias: its input row is exactly zero).  Causal
  * softmax over the live keys j <= i plus n_dead(i) copies of the padding key; dropout fields are indexed by (sequence-head, i, j)
- * over the [L x L] positions exactly as in rbm_attn_fwd.  L <= 64, d_k <= 128.  stats [cap, h, 2].
+ * over the [L x L] positions exactly as in rbm_attn_fwd.  L <= 64, d_k in {16, 32, 64, 128}.  stats [cap, h, 2].
  * Backward: dq [cap, h*dk], dkv [cap, 2*h*dk] and per-query rows dead [cap, 2*h*dk] whose column sum (rbm_rows_live_colsum) is the
- * gradient of bkv; delta [cap, h] is scratch.  Replaces the core of nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76 on that layout. */
+ * gradient of bkv; delta [cap, h] floats and keepw [cap, h] 64-bit words are scratch.  Replaces the core of nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76 on that layout. */
 /* seq_start[b] = first compact row of sequence b (b = 0..B: B + 1 entries), from the ascending row ids */
 int rbm_rows_seq_start(const int32_t* rows, const int32_t* count, int B, int L, int32_t* seq_start, rbm_stream_t stream);
 int rbm_attn_live_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* bkv, const int32_t* rows,
@@ -191,8 +199,8 @@ int rbm_attn_live_fwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv
                       float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
 int rbm_attn_live_bwd(const float* q, int64_t ldq, const float* kv, int64_t ldkv, const float* bkv, const int32_t* rows,
                       const int32_t* seq_start, const int64_t* tok, const float* out, const float* stats, const float* dout,
-                      float* dq, float* dkv, float* dead, float* delta, int B, int L, int h, int dk, float scale, float p,
-                      uint64_t seed, uint64_t site, rbm_stream_t stream);
+                      float* dq, float* dkv, float* dead, float* delta, uint64_t* keepw, int B, int L, int h, int dk, float scale,
+                      float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
 
 /* ---- BERT4Rec output scoring fused with masked cross-entropy (logits never materialised) ------------
  * rows with labels != 0 are compacted (ascending); for those rows logits = h.w^T + bias over V1 = V+1

@@ -3,7 +3,7 @@
 // positions are exactly zero at every block input, their keys / values equal the projection bias, and whatever the block computes
 // for them is multiplied by zero again -- value and gradient.  With Amazon-Beauty-like histories (mean length 9 of L = 50) 86 % of
 // the rows are such rows.  LayerNorm, the Linear layers and the feed-forward therefore run on the live rows only:
-//   rbm_rows_gather   [n, d] -> [cap, d]   compact row r = source row rows[r] (r < *count), zero rows after that
+//   rbm_rows_gather   [n, d] -> [cap, d]   compact row r = source row rows[r] (r < *count; optionally times coef[rows[r]]), zero rows after that
 //   rbm_rows_scatter  [cap, d] -> [n, d]   row rows[r] = compact row r; rows of padding positions = fill (a [d] vector: the k/v bias,
 //                                          beta of the last LayerNorm = what the reference computes there) or zero
 //   rbm_rows_dead_colsum                   sum of the rows of padding positions (gradient of `fill`), fixed summation order
@@ -13,13 +13,20 @@
 namespace {
 
 __global__ void __launch_bounds__(256) rows_gather_kernel(const float* __restrict__ src, int64_t ld, const int32_t* __restrict__ rows,
-                                                          const int32_t* __restrict__ count, int64_t cap, int d4, float* __restrict__ dst) {
+                                                          const int32_t* __restrict__ count, int64_t cap, int d4, const float* __restrict__ coef,
+                                                          float* __restrict__ dst) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= cap * d4) return;
   const int64_t r = i / d4;
   const int c = (int)(i - r * d4) * 4;
   float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (r < *count) v = ld4(src + (int64_t)rows[r] * ld + c);
+  if (r < *count) {
+    v = ld4(src + (int64_t)rows[r] * ld + c);
+    if (coef) {  // the product rbm_scatter_add_sorted would form from (coef, src) itself: same rounding
+      const float cf = coef[rows[r]];
+      v.x = __fmul_rn(cf, v.x); v.y = __fmul_rn(cf, v.y); v.z = __fmul_rn(cf, v.z); v.w = __fmul_rn(cf, v.w);
+    }
+  }
   st4(dst + r * (int64_t)d4 * 4 + c, v);
 }
 
@@ -84,14 +91,14 @@ __global__ void __launch_bounds__(256) dead_colsum_final_kernel(const float* __r
 
 }  // namespace
 
-extern "C" int rbm_rows_gather(const float* src, int64_t ld, const int32_t* rows, const int32_t* count, int64_t cap, int d, float* dst,
-                               rbm_stream_t stream) {
+extern "C" int rbm_rows_gather(const float* src, int64_t ld, const int32_t* rows, const int32_t* count, int64_t cap, int d,
+                               const float* coef, float* dst, rbm_stream_t stream) {
   RBM_REQUIRE(src && rows && count && dst, "rbm_rows_gather: null pointer");
   RBM_REQUIRE(cap >= 0 && d > 0 && d % 4 == 0 && ld % 4 == 0 && ld >= d, "rbm_rows_gather: need d %% 4 == 0 and ld >= d (d=%d)", d);
   RBM_REQUIRE(rbm_aligned16(src) && rbm_aligned16(dst), "rbm_rows_gather: pointers must be 16B aligned");
   if (cap == 0) return 0;
   const int64_t total = cap * (d / 4);
-  rows_gather_kernel<<<(unsigned)rbm_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, count, cap, d / 4, dst);
+  rows_gather_kernel<<<(unsigned)rbm_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, ld, rows, count, cap, d / 4, coef, dst);
   RBM_LAUNCH_CHECK("rbm_rows_gather");
   return 0;
 }

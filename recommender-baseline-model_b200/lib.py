@@ -46,14 +46,16 @@ SIGNATURES = {
     "rbm_linear_bwd_data": (_I, [_P, _L, _P, _P, _L, _L, _I, _I, _P, _SZ, _P]),
     "rbm_linear_bwd_weight_ws_bytes": (_SZ, [_L, _I, _I]),
     "rbm_linear_bwd_weight": (_I, [_P, _L, _P, _L, _P, _P, _L, _I, _I, _P, _SZ, _P]),
-    "rbm_rows_gather": (_I, [_P, _L, _P, _P, _L, _I, _P, _P]),
+    "rbm_embed_bwd_rows_ws_bytes": (_SZ, [_I, _I]),
+    "rbm_embed_bwd_rows": (_I, [_P, _P, _P, _L, _P, _P, _P, _P, _I, _I, _F, _U64, _U64, _P, _SZ, _P]),
+    "rbm_rows_gather": (_I, [_P, _L, _P, _P, _L, _I, _P, _P, _P]),
     "rbm_rows_scatter": (_I, [_P, _P, _P, _L, _I, _P, _P, _L, _P, _L, _P]),
     "rbm_rows_dead_colsum_ws_bytes": (_SZ, [_I]),
     "rbm_rows_dead_colsum": (_I, [_P, _L, _P, _L, _I, _P, _P, _SZ, _P]),
     "rbm_rows_live_colsum": (_I, [_P, _L, _P, _L, _I, _P, _P, _SZ, _P]),
     "rbm_rows_seq_start": (_I, [_P, _P, _I, _I, _P, _P]),
     "rbm_attn_live_fwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
-    "rbm_attn_live_bwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
+    "rbm_attn_live_bwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
     "rbm_attn_last_query": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "rbm_attn_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
     "rbm_attn_bwd_ws_bytes": (_SZ, [_I, _I, _I]),

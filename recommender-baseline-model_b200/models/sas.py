@@ -55,7 +55,7 @@ class SASModel(BaseModel):
     def code(cls):
         return 'sas'
 
-    def log2feats(self, log_seqs, last_only=False):
+    def log2feats(self, log_seqs, last_only=False, live=None):
         """SAS.log2feats NN/models/sas_model/sas.py:59-88 -> [B, L, d]; ``last_only`` (evaluation, K20): [B, d], the last position's
         features, with the final block computed for that position alone (keys / values still from every position)."""
         sas = self.sas
@@ -67,6 +67,10 @@ class SASModel(BaseModel):
         seed = self.dropout_seed
         base = self._next_site_base() if train else 0
         sh = getattr(self, "_shard", None)
+        if live is None and train and sh is None and not last_only:
+            live = self._live_rows(seq)
+        if live is not None and live is not False:  # (False: the caller already decided for the dense path)
+            return self._blocks_live_rows(seq, live, Bsz, Ln, p, seed, base, math.sqrt(1.0 / (d // h)))
         if sh is None:
             x = ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base)
         else:  # row-sharded item table (rbm_b200.dist.shard_sas_model): common seed + global element indices for this site,
@@ -76,9 +80,6 @@ class SASModel(BaseModel):
                                   base, sh.group, grad_unscale=float(sh.world))
             seed = (seed + (sh.rank + 1) * 0x9E3779B97F4A7C15) & 0x7FFFFFFFFFFFFFFF
         scale = math.sqrt(1.0 / (d // h))
-        live = self._live_rows(seq) if (train and sh is None and not last_only) else None
-        if live is not None:
-            return self._blocks_live_rows(x, live, Bsz, Ln, p, seed, base, scale)
         for b in range(len(sas.attention_layers)):
             s = base + 1 + 3 * b
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
@@ -107,37 +108,42 @@ class SASModel(BaseModel):
     # ------------------------------------------------------------------ live-row path (training)
     LIVE_ROWS_MAX_FRACTION = 0.6  # above this share of non-padding rows the dense path is used
 
-    def _live_rows(self, seq):
+    def _live_rows(self, seq, *also):
         """Plan of the live-row path for this batch, or None for the dense path.  Eager steps read the number of non-padding
         positions back (one host sync); under a CUDA graph the trainer fixes the capacity before capture (``_row_cap``: rows,
-        0 = dense) and checks every replayed batch against it."""
+        0 = dense) and checks every replayed batch against it.  ``also``: further id tensors (pos, neg) whose non-zero counts the
+        capacity must cover too (their table-gradient scatters then run on ``cap`` entries)."""
         if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0":
             return None
         n = seq.numel()
         cap = getattr(self, "_row_cap", None)
         if cap is None:
-            cnt = int(torch.count_nonzero(seq).item())
-            if cnt > self.LIVE_ROWS_MAX_FRACTION * n:
+            cnts = torch.stack([torch.count_nonzero(t) for t in (seq,) + also]).tolist()
+            if cnts[0] > self.LIVE_ROWS_MAX_FRACTION * n:
                 return None
-            cap = max(128, -(-cnt // 128) * 128)
+            cap = max(128, -(-max(cnts) // 128) * 128)
         elif cap <= 0:
             return None
-        return ops.LiveRows(seq, cap)
+        live = ops.LiveRows(seq, cap)
+        live.covers_labels = len(also) > 0
+        return live
 
-    def row_capacity_for(self, seq) -> int:
-        """Capacity (rows) a captured step should be built with for batches like ``seq``: 25 % headroom over its live rows, 0 when
-        the dense path is the better choice.  ``live_row_count`` tells the trainer whether a later batch still fits."""
+    def row_capacity_for(self, seq, *also) -> int:
+        """Capacity (rows) a captured step should be built with for batches like (seq, pos, neg): 25 % headroom over the non-zero
+        ids, 0 when the dense path is the better choice.  ``live_row_count`` tells the trainer whether a later batch still fits."""
         if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
             return 0
-        n, cnt = int(seq.numel()), self.live_row_count(seq)
+        n, cnt = int(seq.numel()), self.live_row_count(seq, *also)
         cap = -(-(cnt + cnt // 4 + 256) // 128) * 128
         return cap if cap <= self.LIVE_ROWS_MAX_FRACTION * n else 0
 
     @staticmethod
-    def live_row_count(seq) -> int:
-        return int(torch.count_nonzero(torch.as_tensor(seq)).item())
+    def live_row_count(*ids) -> int:
+        """The largest number of non-zero ids among the given tensors (seq, pos, neg of a batch)."""
+        ts = [torch.as_tensor(t) for t in ids]
+        return int(torch.stack([torch.count_nonzero(t) for t in ts]).max().item())
 
-    def _blocks_live_rows(self, x, live, Bsz, Ln, p, seed, base, scale):
+    def _blocks_live_rows(self, seq, live, Bsz, Ln, p, seed, base, scale):
         """The block loop with LayerNorm / Linear / feed-forward on the live rows only (csrc/rows.cu explains why that is exact).
         Attention runs on the same compact layout (csrc/attention_live.cu: every padding key of a sequence is the projection bias,
         which is what W.0 + b gives the reference, so they enter as one key with a multiplicity); sequences longer than 64 keep the
@@ -145,7 +151,10 @@ class SASModel(BaseModel):
         index their Philox stream by (live-row ordinal, column); the attention site by (sequence-head, i, j) as always."""
         sas = self.sas
         d, h = sas.hidden, sas.heads
-        xc = ops.rows_gather(x.view(-1, d), live)
+        if ops.embed_live_supported(Ln, d):
+            xc = ops.EmbedLiveFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, live, float(d ** 0.5), p, seed, base)
+        else:
+            xc = ops.rows_gather(ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base).view(-1, d), live)
         for b in range(len(sas.attention_layers)):
             s = base + 1 + 3 * b
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
@@ -153,7 +162,7 @@ class SASModel(BaseModel):
             Q, Qres, xkv = ops.layernorm_fanout(xc, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
             q = ops.linear(Q, w_in[:d], b_in[:d])
             kv = ops.linear(xkv, w_in[d:], b_in[d:])
-            if Ln <= 64 and d // h <= 128:  # compact attention: the padding keys of a sequence are one key with a multiplicity
+            if Ln <= 64 and d % h == 0 and d // h in (16, 32, 64, 128):  # compact attention: the padding keys of a sequence are one key with a multiplicity
                 ctx = ops.attention_live(q, kv, b_in[d:], live, Bsz, Ln, h, scale, p, seed, s)
             else:  # dense attention kernels on the [B, L] layout (padding rows: zero queries, the bias as key / value)
                 ctx = ops.attention(ops.rows_scatter(q, None, live), ops.rows_scatter(kv, b_in[d:], live), None, Bsz, Ln, h, 0, 0, d,
@@ -168,13 +177,16 @@ class SASModel(BaseModel):
 
     def forward(self, log_seqs, pos_seqs, neg_seqs):  # for training
         """NN/models/sas_model/sas.py:90-105 -> (pos_logits, neg_logits) [B, L]."""
-        f = self.log2feats(log_seqs)
         sh = getattr(self, "_shard", None)
         if sh is not None:
             from ..dist import ShardedSasScoreFn
+            f = self.log2feats(log_seqs)
             return ShardedSasScoreFn.apply(f, self.sas.item_emb.weight, self._device_long(pos_seqs), self._device_long(neg_seqs),
                                            sh.tok_begin, sh.group, float(sh.world))
-        return ops.sas_scores(f, self.sas.item_emb.weight, self._device_long(pos_seqs), self._device_long(neg_seqs))
+        pos, neg = self._device_long(pos_seqs), self._device_long(neg_seqs)
+        live = (self._live_rows(self._device_long(log_seqs), pos, neg) or False) if self.training else None
+        f = self.log2feats(log_seqs, live=live)
+        return ops.sas_scores(f, self.sas.item_emb.weight, pos, neg, cap=live.cap if live else None)
 
     def loss(self, log_seqs, pos_seqs, neg_seqs):
         """BCE part of SASTrainer.calculate_loss NN/trainers/sas.py:34-49."""

@@ -51,7 +51,7 @@ class LiveRows:
     """The live (token != 0) rows of a [B, L] batch: ascending row ids + count on the device (rbm_compact_labels applied to the
     token ids) and a host-side capacity ``cap`` >= count: the token-wise layers run on [cap, d] tensors (csrc/rows.cu)."""
 
-    def __init__(self, tok: torch.Tensor, cap: int):
+    def __init__(self, tok: torch.Tensor, cap: int, keep_ids: bool = False):
         lib = L.load()
         L.require_cuda(tok)
         self.tok = tok.reshape(-1).contiguous()
@@ -59,7 +59,9 @@ class LiveRows:
         self.cap = int(cap)
         dev = tok.device
         self.rows = torch.empty(self.n, device=dev, dtype=torch.int32)
-        self._tgt = torch.empty(self.n, device=dev, dtype=torch.int64)
+        # ids[r] = tok[rows[r]] (zeros past the count when the caller wants to use them as scatter keys)
+        self._tgt = (torch.zeros if keep_ids else torch.empty)(max(self.n, self.cap), device=dev, dtype=torch.int64)
+        self.ids = self._tgt[: self.cap]
         self.count = torch.empty(1, device=dev, dtype=torch.int32)
         nb = lib.rbm_compact_ws_bytes(self.n)
         ws = _ws("compact", nb, dev)
@@ -74,10 +76,11 @@ class LiveRows:
             count_launches()
 
 
-def _rows_gather(x2, live):
+def _rows_gather(x2, live, coef=None):
     lib = L.load()
     out = torch.empty(live.cap, x2.shape[1], device=x2.device, dtype=torch.float32)
-    check(lib.rbm_rows_gather(ptr(x2), x2.stride(0), ptr(live.rows), ptr(live.count), live.cap, x2.shape[1], ptr(out), stream()), "rows_gather")
+    check(lib.rbm_rows_gather(ptr(x2), x2.stride(0), ptr(live.rows), ptr(live.count), live.cap, x2.shape[1], ptr(coef), ptr(out), stream()),
+          "rows_gather")
     count_launches()
     return out
 
@@ -177,6 +180,53 @@ class EmbedFn(torch.autograd.Function):
         dtable = torch.zeros(tshape, device=dout.device, dtype=torch.float32)
         scatter_add_sorted_(dtable, tok, g, None, scale, padding_idx=0)
         return None, dtable, dpos, None, None, None, None, None
+
+
+class EmbedLiveFn(torch.autograd.Function):
+    """The embedding stage (zero_pad = 1) handing out the live rows only: [cap, d] = rows_gather(EmbedFn(...)).  Backward never
+    builds the [B, L, d] gradient: dropout mask, positional-table gradient and the table scatter run on the cap compact rows."""
+
+    @staticmethod
+    def forward(ctx, tok, table, pos, live, scale, p, seed, site):
+        lib = L.load()
+        L.require_cuda(tok, table, pos)
+        Bsz, Ln = tok.shape
+        d = table.shape[1]
+        if pos.shape[0] < Ln:
+            raise RuntimeError("positional table has %d rows < sequence length %d" % (pos.shape[0], Ln))
+        tok = tok.contiguous()
+        full = torch.empty(Bsz * Ln, d, device=table.device, dtype=torch.float32)
+        check(lib.rbm_embed_fwd(ptr(tok), ptr(table), ptr(pos), ptr(full), Bsz * Ln, Ln, d, table.shape[0], float(scale), 1, float(p), seed,
+                                site, stream()), "embed_fwd")
+        count_launches()
+        ctx.save_for_backward(tok)
+        ctx.live, ctx.meta = live, (table.shape, pos.shape, float(scale), float(p), seed, site)
+        return _rows_gather(full, live)
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        (tok,) = ctx.saved_tensors
+        live = ctx.live
+        tshape, pshape, scale, p, seed, site = ctx.meta
+        Bsz, Ln = tok.shape
+        d = tshape[1]
+        dout = dout.contiguous()
+        g = torch.empty_like(dout)
+        idx = torch.empty(live.cap, device=dout.device, dtype=torch.int64)
+        dpos = torch.zeros(pshape, device=dout.device, dtype=torch.float32)
+        nb = lib.rbm_embed_bwd_rows_ws_bytes(Ln, d)
+        ws = _ws("embed_rows", nb, dout.device)
+        check(lib.rbm_embed_bwd_rows(ptr(tok), ptr(live.rows), ptr(live.count), live.cap, ptr(dout), ptr(g), ptr(idx), ptr(dpos), Ln, d, p,
+                                     seed, site, ptr(ws), nb, stream()), "embed_bwd_rows")
+        count_launches(3)
+        dtable = torch.zeros(tshape, device=dout.device, dtype=torch.float32)
+        scatter_add_sorted_(dtable, idx, g, None, scale, padding_idx=0)
+        return None, dtable, dpos, None, None, None, None, None
+
+
+def embed_live_supported(Ln: int, d: int) -> bool:
+    return Ln * d * 4 <= 96 * 1024
 
 
 # --------------------------------------------------------------------------------------------- layernorm
@@ -468,9 +518,10 @@ class AttnLiveFn(torch.autograd.Function):
         dkv = torch.zeros_like(kv)
         dead = torch.zeros_like(kv)
         delta = torch.empty(cap, h, device=q.device, dtype=torch.float32)
+        keepw = torch.empty(cap, h, device=q.device, dtype=torch.int64)
         check(lib.rbm_attn_live_bwd(ptr(q), d, ptr(kv), 2 * d, ptr(bkv), ptr(live.rows), ptr(live.seq_start), ptr(live.tok), ptr(out),
-                                    ptr(stats), ptr(dout), ptr(dq), ptr(dkv), ptr(dead), ptr(delta), Bsz, Ln, h, d // h, scale, p, seed,
-                                    site, stream()), "attn_live_bwd")
+                                    ptr(stats), ptr(dout), ptr(dq), ptr(dkv), ptr(dead), ptr(delta), ptr(keepw), Bsz, Ln, h, d // h, scale,
+                                    p, seed, site, stream()), "attn_live_bwd")
         dbkv = torch.empty(2 * d, device=q.device, dtype=torch.float32)
         nb = lib.rbm_rows_dead_colsum_ws_bytes(2 * d)
         ws = _ws("rows_colsum", nb, q.device)
@@ -559,9 +610,10 @@ class SasScoreFn(torch.autograd.Function):
     """pos/neg logits = <f, table[pos]> / <f, table[neg]>   (K13)."""
 
     @staticmethod
-    def forward(ctx, f, table, pos, neg):
+    def forward(ctx, f, table, pos, neg, cap=None):
         lib = L.load()
         L.require_cuda(f, table, pos, neg)
+        ctx.cap = cap
         f2 = _rows2d(f).contiguous()
         rows, d = f2.shape
         pos = pos.reshape(-1).contiguous()
@@ -585,13 +637,22 @@ class SasScoreFn(torch.autograd.Function):
         check(lib.rbm_sas_score_bwd(ptr(table), ptr(pos), ptr(neg), ptr(dpl), ptr(dnl), ptr(df), rows, d, stream()), "sas_score_bwd")
         count_launches()
         dtable = torch.zeros_like(table)
-        scatter_add_sorted_(dtable, pos, f2, dpl, 1.0, padding_idx=0)
-        scatter_add_sorted_(dtable, neg, f2, dnl, 1.0, padding_idx=0)
-        return df.view(ctx.shape), dtable, None, None
+        if ctx.cap is None:
+            scatter_add_sorted_(dtable, pos, f2, dpl, 1.0, padding_idx=0)
+            scatter_add_sorted_(dtable, neg, f2, dnl, 1.0, padding_idx=0)
+        else:
+            # at most `cap` ids are non-zero (the caller's promise, see SASModel._live_rows): sort and reduce those entries only --
+            # same contributions (coefficient folded in with the same rounding) in the same order, so the same bits
+            for idx, coef in ((pos, dpl), (neg, dnl)):
+                lr = LiveRows(idx, ctx.cap, keep_ids=True)
+                scatter_add_sorted_(dtable, lr.ids, _rows_gather(f2, lr, coef), None, 1.0, padding_idx=0)
+        return df.view(ctx.shape), dtable, None, None, None
 
 
-def sas_scores(f, table, pos, neg):
-    return SasScoreFn.apply(f, table, pos, neg)
+def sas_scores(f, table, pos, neg, cap=None):
+    """``cap``: an upper bound (rows) on the number of non-zero ids in ``pos`` and in ``neg``; the table gradient then sorts /
+    reduces ``cap`` entries instead of B*L."""
+    return SasScoreFn.apply(f, table, pos, neg, cap)
 
 
 class BcePairFn(torch.autograd.Function):

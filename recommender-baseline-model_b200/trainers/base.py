@@ -110,7 +110,7 @@ class AbstractTrainer(metaclass=ABCMeta):
         # capacity, chosen from the example batch (0 = dense path); _replay sends a batch that does not fit through an eager step
         self._graph_row_cap = 0
         if hasattr(self.model, "row_capacity_for"):
-            self._graph_row_cap = self.model.row_capacity_for(static[0])
+            self._graph_row_cap = self.model.row_capacity_for(*static)
             self.model._row_cap = self._graph_row_cap
         # warm-up on a side stream (lazy one-time work: function attributes, context binding, workspaces, Adam state, the
         # NCCL communicator), then put model / optimizer / step counters back so that the captured step is the next real one
@@ -226,7 +226,7 @@ class AbstractTrainer(metaclass=ABCMeta):
         batch = tuple(torch.as_tensor(x) for x in batch)
         if len(batch) != len(self._graph_static) or any(tuple(s.shape) != tuple(d.shape) for s, d in zip(batch, self._graph_static)):
             return self._odd_shaped_step(batch)  # never copy_ a mismatching batch: a 1-row remainder would broadcast silently
-        if self._graph_row_cap and self.model.live_row_count(batch[0]) > self._graph_row_cap:
+        if self._graph_row_cap and self.model.live_row_count(*batch) > self._graph_row_cap:
             return self._odd_shaped_step(batch)  # more non-padding rows than the captured live-row capacity
         for dst, src in zip(self._graph_static, batch):
             dst.copy_(src, non_blocking=True)

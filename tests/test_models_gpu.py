@@ -513,7 +513,7 @@ def test_rows_gather_scatter():
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("V,Ln,d,nb,h,B,p", [(300, 50, 128, 2, 2, 64, 0.0), (90, 12, 32, 2, 1, 9, 0.25), (500, 50, 64, 1, 1, 300, 0.2),
-                                             (120, 80, 32, 1, 2, 10, 0.2), (200, 64, 256, 1, 2, 7, 0.1), (60, 33, 24, 2, 2, 5, 0.3)])
+                                             (120, 80, 32, 1, 2, 10, 0.2), (200, 64, 256, 1, 2, 7, 0.1), (60, 33, 48, 2, 2, 5, 0.3)])
 def test_sas_live_rows_training(V, Ln, d, nb, h, B, p):
     """SASRec with the token-wise layers on the non-padding rows only (Amazon-Beauty-like left padding: 80-90 % of the positions):
     loss and EVERY gradient against the oracle -- dropout on: the oracle consumes the Philox masks the kernels used, the
