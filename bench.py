@@ -258,7 +258,13 @@ def kernel_work(name, a, shapes):
         return "tensor", 2.0 * a[9] * a[10] * (a[5] - a[4])  # 2 * U * d * items
     # Linear family at d = 64..256: arithmetic intensity of a few FLOP/B -> HBM-bound; algorithmic bytes = every operand
     # and result once
-    if name == "rbm_linear_fwd":
+    if name in ("rbm_attn_live_fwd", "rbm_attn_live_bwd"):
+        # compact SASRec attention: a (sequence, head) item is ~ len^2 / 2 scores of d_k = 64 -- latency / instruction bound, reported
+        # against the bytes it has to move: q, k|v, out (+ dout, dq, dk|dv, the padding-key rows in the backward) of the live rows
+        o = 10 if name == "rbm_attn_live_fwd" else 16
+        h, dk = a[o + 2], a[o + 3]
+        return "hbm", (4.0 if name == "rbm_attn_live_fwd" else 10.0) * shapes.get("live_rows", 0.0) * h * dk * 4
+    if name in ("rbm_linear_fwd", "rbm_linear_fwd_ws"):
         M, N, K = a[7], a[8], a[9]
         return "hbm", 4.0 * (M * K + N * K + M * N * (1 + (1 if a[6] else 0) + (1 if a[11] else 0)))  # + pre-activation, + residual
     if name == "rbm_linear_bwd_data":
@@ -438,6 +444,8 @@ def train_workload(ctx, key, steps, warmup, batch=None, with_cpu=True, with_roof
                       n_params=sum(p.numel() for p in model.parameters()))
         if spec["kind"] == "bert":
             shapes["P"] = float(np.mean([(b[1] != 0).sum() for b in raw]))
+        else:
+            shapes["live_rows"] = float(np.mean([(b[0] != 0).sum() for b in raw]))
         roofline, shares, compact = roofline_from_profile(prof, 3, shapes, ctx.peaks)
 
     cpu = None
@@ -459,6 +467,12 @@ def train_workload(ctx, key, steps, warmup, batch=None, with_cpu=True, with_roof
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_time_shares": shares,
             "roofline_by_entry_point": compact, "cpu_baseline": cpu, "final_loss": losses[-1] if losses else None}
+    if spec["kind"] == "sas":
+        frac = float(np.mean([(b[0] != 0).mean() for b in raw]))
+        cap = getattr(trainer, "_graph_row_cap", 0) if step_mode == "graph" else None
+        line["config"]["live_rows"] = ("%.1f %% of the positions are non-padding; LayerNorm / Linear / feed-forward / attention / embedding "
+                                       "gradient run on those rows only (exact: the reference multiplies padding rows by zero after every "
+                                       "block; captured row capacity %s of %d)" % (100 * frac, cap, Bsz * spec["L"]))
     if equiv is not None:
         line["single_gpu_equivalence"] = equiv
     del trainer, model

@@ -53,6 +53,7 @@ class AbstractTrainer(metaclass=ABCMeta):
         self.dist_sync = None  # set to rbm_b200.dist.GradSync for data-parallel training
         self._graph = None     # set by capture_train_step()
         self._graph_b = None
+        self._graph_row_cap = 0  # SASRec live-row capacity the graph was captured with (0 = dense path)
 
     @classmethod
     @abstractmethod
