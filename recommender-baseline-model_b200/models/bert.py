@@ -7,6 +7,7 @@ built from the same torch layers in the same order after ``fix_random_seed_as(mo
 modules' own ``forward`` is ever used.
 """
 import math
+import os
 import random
 
 import numpy as np
@@ -115,9 +116,11 @@ class BERTModel(BaseModel):
         return 'bert'
 
     # ------------------------------------------------------------------ transformer body (a7-a11)
-    def hidden_states(self, x, last_only=False):
+    def hidden_states(self, x, last_only=False, label_rows=None):
         """BERT.forward NN/models/bert_modules/bert.py:36-43 -> [B, L, d]; ``last_only`` (evaluation, K20): [B, d], the last position
-        alone, with the final block computed for that position only (keys / values still from every position)."""
+        alone, with the final block computed for that position only (keys / values still from every position).  ``label_rows``
+        (training, an ``ops.LiveRows`` over the labels): [cap, d], the labelled positions alone -- the loss reads no other row of the
+        final block's output, so its output projection, LayerNorm and feed-forward run on those rows only."""
         bert = self.bert
         tok = self._device_long(x)
         Bsz, Ln = tok.shape
@@ -157,6 +160,14 @@ class BERTModel(BaseModel):
             b_qkv = torch.cat([l.bias for l in att.linear_layers], 0)
             qkv = ops.linear(n1, w_qkv, b_qkv)
             ctx = ops.attention(qkv, None, tok, Bsz, Ln, h, 0, d, 2 * d, L.MASK_KEYPAD, scale, p_a, seed, s)
+            if label_rows is not None and b == len(bert.transformer_blocks) - 1:
+                # the rest of the final block on the labelled rows only (their element-wise dropout sites index the Philox stream
+                # by (labelled-row ordinal, column)); keys / values above came from every position
+                xc = ops.linear(ops.rows_gather(ctx.view(-1, d), label_rows), att.output_linear.weight, att.output_linear.bias,
+                                residual=ops.rows_gather(x.view(-1, d), label_rows), pA=p_h, siteA=s + 1, seed=seed)
+                n2, xc = ops.layernorm_residual(xc, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+                u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH, pA=p_h, siteA=s + 2, seed=seed)
+                return ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=xc, pA=p_h, siteA=s + 3, pB=p_h, siteB=s + 4, seed=seed)
             x = ops.linear(ctx.view(Bsz, Ln, d), att.output_linear.weight, att.output_linear.bias, residual=x, pA=p_h,
                            siteA=s + 1, seed=seed)
             n2, x = ops.layernorm_residual(x, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
@@ -182,8 +193,13 @@ class BERTModel(BaseModel):
     # ------------------------------------------------------------------ fused paths used by the drop-in trainer
     def loss(self, x, labels):
         """CE(ignore_index=0) of NN/trainers/bert.py:30-41 without materialising [B*L, V+1] logits (K15-K16)."""
-        h = self.hidden_states(x)
         sh = getattr(self, "_shard", None)
+        if sh is None and self.training:
+            lab = self._device_long(labels)
+            live = self._label_rows(lab)
+            if live is not None:  # final block and scoring on the labelled rows only
+                return ops.score_cross_entropy(self.hidden_states(x, label_rows=live), live.ids, self.out.weight, self.out.bias)
+        h = self.hidden_states(x)
         if sh is not None:  # data-parallel rows x row-sharded output layer: the loss of the GLOBAL batch (SURVEY 8e)
             from ..dist import hybrid_vocab_parallel_loss
             loss, sh.overflow = hybrid_vocab_parallel_loss(h, self._device_long(labels), self.out.weight, self.out.bias, sh.out_begin,
@@ -192,6 +208,39 @@ class BERTModel(BaseModel):
             sh.overflow_any = sh.overflow if getattr(sh, "overflow_any", None) is None else (sh.overflow_any | sh.overflow)
             return loss
         return ops.score_cross_entropy(h, self._device_long(labels), self.out.weight, self.out.bias)
+
+    # ------------------------------------------------------------------ labelled-row path (training)
+    LABEL_ROWS_MAX_FRACTION = 0.5  # above this share of labelled positions the final block runs on every row
+
+    def _label_rows(self, labels):
+        """``ops.LiveRows`` over the labelled positions, or None (final block on every row).  Eager steps read the number of labels
+        back (one host sync); under a CUDA graph the trainer fixes the capacity before capture (``_row_cap``: rows, 0 = off) and
+        checks every replayed batch against it."""
+        if os.environ.get("RBM_BERT_LABEL_ROWS", "1") == "0":
+            return None
+        n = labels.numel()
+        cap = getattr(self, "_row_cap", None)
+        if cap is None:
+            cnt = int(torch.count_nonzero(labels).item())
+            if cnt > self.LABEL_ROWS_MAX_FRACTION * n:
+                return None
+            cap = max(128, -(-cnt // 128) * 128)
+        elif cap <= 0:
+            return None
+        return ops.LiveRows(labels, cap, keep_ids=True)
+
+    def row_capacity_for(self, tokens, labels) -> int:
+        """Capacity (rows) a captured step should be built with for batches like this one: 25 % headroom over its labelled rows
+        (0 = run the final block on every row).  ``live_row_count`` tells the trainer whether a later batch still fits."""
+        if os.environ.get("RBM_BERT_LABEL_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
+            return 0
+        n, cnt = int(torch.as_tensor(labels).numel()), self.live_row_count(tokens, labels)
+        cap = -(-(cnt + cnt // 4 + 64) // 128) * 128
+        return cap if cap <= self.LABEL_ROWS_MAX_FRACTION * n else 0
+
+    @staticmethod
+    def live_row_count(tokens, labels) -> int:
+        return int(torch.count_nonzero(torch.as_tensor(labels)).item())
 
     def last_hidden(self, x):
         if not self.training and not torch.is_grad_enabled():

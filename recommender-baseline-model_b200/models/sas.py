@@ -134,7 +134,7 @@ class SASModel(BaseModel):
         if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
             return 0
         n, cnt = int(seq.numel()), self.live_row_count(seq, *also)
-        cap = -(-(cnt + cnt // 4 + 256) // 128) * 128
+        cap = -(-(cnt + cnt // 4 + 64) // 128) * 128
         return cap if cap <= self.LIVE_ROWS_MAX_FRACTION * n else 0
 
     @staticmethod

@@ -120,14 +120,18 @@ class AbstractTrainer(metaclass=ABCMeta):
         step0 = self.model._step
         side = torch.cuda.Stream(device=dev)
         side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            for _ in range(max(1, warmup)):
-                self.optimizer.zero_grad()
-                loss = self.calculate_loss(static)
-                loss.backward()
-                if sync is not None:
-                    sync.allreduce_grads()
-                self.optimizer.step()
+        try:
+            with torch.cuda.stream(side):
+                for _ in range(max(1, warmup)):
+                    self.optimizer.zero_grad()
+                    loss = self.calculate_loss(static)
+                    loss.backward()
+                    if sync is not None:
+                        sync.allreduce_grads()
+                    self.optimizer.step()
+        except BaseException:
+            self.model._row_cap = None
+            raise
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         self.model.load_state_dict(model_sd)

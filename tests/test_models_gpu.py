@@ -40,13 +40,17 @@ def relclose(a, b, rel=1e-3, floor=1e-4, msg=""):
     assert np.abs(a - b).max() <= rel * scale, "%s: max err %g vs scale %g" % (msg, np.abs(a - b).max(), scale)
 
 
+@pytest.mark.parametrize("label_rows", [False, True])
 @pytest.mark.parametrize("name", ["bert_tiny", "bert_odd"])
-def test_bert_vs_reference_golden(name):
+def test_bert_vs_reference_golden(name, label_rows):
+    """``label_rows``: the final block's output projection / LayerNorm / feed-forward on the labelled rows only (forced here
+    whatever the label share; off = every row) -- same goldens, same tolerances."""
     z = load(name)
     V, Ln, d, nb, h, B, seed = z["cfg"].tolist()
     model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, seed=seed))
     model.load_state_dict(sd_of(z))
     model.to(DEV).train()
+    model.LABEL_ROWS_MAX_FRACTION = 1.0 if label_rows else -1.0
     t, l = torch.from_numpy(z["tokens"]), torch.from_numpy(z["labels"])
     logits = model(t.to(DEV))
     assert logits.shape == (B, Ln, V + 1) and logits.is_contiguous()
@@ -174,12 +178,16 @@ def test_cfg_shaped_losses():
     np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
 
 
-def test_training_mode_dropout_against_injected_masks():
-    """Training-mode BERT4Rec: the oracle consumes the Philox masks the kernels used (exported per site)."""
+@pytest.mark.parametrize("label_rows", [True, False])
+def test_training_mode_dropout_against_injected_masks(label_rows):
+    """Training-mode BERT4Rec: the oracle consumes the Philox masks the kernels used (exported per site).  ``label_rows``: the
+    final block's output projection / LayerNorm / feed-forward on the labelled rows only (the default when at most half of the
+    positions are labelled) or on every row."""
     from oracle.common import DropoutPlan
     V, Ln, d, nb, h, B, p = 37, 8, 16, 2, 2, 4, 0.25
     model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, p=p, seed=1)).to(DEV).train()
     model.dropout_seed = 4242
+    model.LABEL_ROWS_MAX_FRACTION = 1.0 if label_rows else -1.0
     rng = np.random.RandomState(0)
     tok = torch.from_numpy(rng.randint(1, V + 2, size=(B, Ln)).astype(np.int64))
     tok[0, :3] = 0
@@ -189,11 +197,22 @@ def test_training_mode_dropout_against_injected_masks():
     loss.backward()
     base = step0 * 64
     masks = {0: ops.dropout_mask(B * Ln * d, p, 4242, base, DEV).cpu()}
+    labelled = np.flatnonzero(lab.numpy().reshape(-1))
+    compact = len(labelled) <= model.LABEL_ROWS_MAX_FRACTION * B * Ln  # the final block then runs on the labelled rows only
+    cap = max(128, -(-len(labelled) // 128) * 128)
     for b in range(nb):
         s = ob.block_sites(b)
         masks[s["attn"]] = ops.dropout_mask_attn(B * h * Ln, Ln, p, 4242, base + s["attn"], DEV).cpu()
-        for key, n in (("sub_in", B * Ln * d), ("ffn", B * Ln * 4 * d), ("sub_out", B * Ln * d), ("block", B * Ln * d)):
-            masks[s[key]] = ops.dropout_mask(n, p, 4242, base + s[key], DEV).cpu()
+        for key, w in (("sub_in", d), ("ffn", 4 * d), ("sub_out", d), ("block", d)):
+            if compact and b == nb - 1:
+                # element-wise sites of the final block: Philox stream indexed by (labelled-row ordinal, column); the other rows of
+                # that block never reach the loss, whatever mask the oracle applies to them
+                mc = ops.dropout_mask(cap * w, p, 4242, base + s[key], DEV).cpu().reshape(cap, w)
+                full = torch.ones(B * Ln, w, dtype=mc.dtype)
+                full[torch.from_numpy(labelled)] = mc[: len(labelled)]
+                masks[s[key]] = full
+            else:
+                masks[s[key]] = ops.dropout_mask(B * Ln * w, p, 4242, base + s[key], DEV).cpu()
     sd = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
     ref = ob.loss(sd, tok, lab, nb, h, p_attn=p, p_hidden=p, drop=DropoutPlan(True, masks))
     ref.backward()
@@ -270,6 +289,8 @@ def test_cuda_graph_train_step_equals_eager(kind):
     t1 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m1, None, None, None, None)
     t2 = rbm_b200.trainer_factory(SimpleNamespace(**vars(a), **common), m2, None, None, None, None)
     m1.train(); m2.train()
+    for m in (m1, m2):  # the row-compacting paths size their tensors per batch (eager) / per capture (graph): bit-identity across
+        m.LIVE_ROWS_MAX_FRACTION = m.LABEL_ROWS_MAX_FRACTION = -1.0  # capacities is test_live_rows_cuda_graph's subject
     eager = [t1.train_step(b).item() for b in batches]
     t2.capture_train_step(batches[0])
     graphed = [t2.train_step(b).item() for b in batches]
@@ -569,23 +590,29 @@ def test_sas_live_rows_training(V, Ln, d, nb, h, B, p):
 
 
 @pytest.mark.gpu
-def test_sas_live_rows_cuda_graph():
-    """The captured SASRec step with a fixed live-row capacity: replays are bit-identical to eager steps run with the same
-    capacity; a batch with more non-padding rows than the capacity takes an eager step and training continues."""
+@pytest.mark.parametrize("kind", ["sas", "bert"])
+def test_live_rows_cuda_graph(kind):
+    """The captured step with a fixed row capacity (SASRec: non-padding rows; BERT4Rec: labelled rows of the final block): replays
+    are bit-identical to eager steps run with the same capacity; a batch with more such rows than the capacity takes an eager
+    step and training continues."""
     V, Ln, d, B = 80, 20, 32, 48
     rs = np.random.RandomState(5)
 
-    def batch(i, keep=4):
-        s = rs.randint(1, V + 1, size=(B, Ln))
-        for b in range(B):
-            s[b, : Ln - rs.randint(1, keep + 1)] = 0
-        p_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
-        n_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
-        return tuple(torch.from_numpy(x).to(DEV) for x in (s, p_, n_))
+    def batch(i, keep=4, p_label=0.15):
+        if kind == "sas":
+            s = rs.randint(1, V + 1, size=(B, Ln))
+            for b in range(B):
+                s[b, : Ln - rs.randint(1, keep + 1)] = 0
+            p_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+            n_ = np.where(s != 0, rs.randint(1, V + 1, size=(B, Ln)), 0)
+            return tuple(torch.from_numpy(x).to(DEV) for x in (s, p_, n_))
+        t = rs.randint(1, V + 1, size=(B, Ln)); t[:, : i % 3] = 0
+        l = np.where((rs.rand(B, Ln) < p_label) & (t != 0), t, 0)
+        return torch.from_numpy(np.where(l != 0, V + 1, t)).to(DEV), torch.from_numpy(l).to(DEV)
 
-    a = sas_args(V, Ln, d, 2, 1, p=0.2)
+    a = sas_args(V, Ln, d, 2, 1, p=0.2) if kind == "sas" else bert_args(V, Ln, d, 2, 2, p=0.2, seed=3)
     common = dict(optimizer="Adam", lr=2e-3, weight_decay=0, momentum=None, decay_step=50, gamma=1.0, num_epochs=1, metric_ks=[10],
-                  best_metric="NDCG@10", train_batch_size=B, resume_path=None, l2_emb=0.0)
+                  best_metric="NDCG@10", train_batch_size=B, resume_path=None, **({"l2_emb": 0.0} if kind == "sas" else {}))
     batches = [batch(i) for i in range(5)]
     torch.manual_seed(0)
     m1, m2 = rbm_b200.model_factory(a), rbm_b200.model_factory(a)
@@ -597,14 +624,17 @@ def test_sas_live_rows_cuda_graph():
     t2.capture_train_step(batches[0])
     cap = t2._graph_row_cap
     assert 0 < cap < B * Ln
-    m1._row_cap = cap  # the eager twin runs with the captured capacity
     # a batch that does not fit the capacity: eager step inside the graphed trainer, dense / self-sized in the twin
-    sf = rs.randint(1, V + 1, size=(B, Ln))
-    big = tuple(torch.from_numpy(x).to(DEV) for x in (sf, rs.randint(1, V + 1, size=(B, Ln)), rs.randint(1, V + 1, size=(B, Ln))))
-    assert m2.live_row_count(big[0]) > cap
+    if kind == "sas":
+        sf = rs.randint(1, V + 1, size=(B, Ln))
+        big = tuple(torch.from_numpy(x).to(DEV) for x in (sf, rs.randint(1, V + 1, size=(B, Ln)), rs.randint(1, V + 1, size=(B, Ln))))
+    else:
+        big = batch(1, p_label=0.45)
+    assert m2.live_row_count(*big) > cap
     # (the twin takes all its steps first: the device-side step counter the captured trainer installs is process-wide)
+    m1._row_cap = cap  # the eager twin runs with the captured capacity ...
     eager = [t1.train_step(b).item() for b in batches]
-    m1._row_cap = None
+    m1._row_cap = None  # ... and sizes the oversized batch by itself, like the eager step inside the graphed trainer
     eager.append(t1.train_step(big).item())
     m1._row_cap = cap
     eager.append(t1.train_step(batches[1]).item())
