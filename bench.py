@@ -250,6 +250,10 @@ def kernel_work(name, a, shapes):
         B, Ln, h, dk, mode = a[o:o + 5]
         pairs = Ln * (Ln + 1) / 2 if mode == 1 else Ln * Ln  # causal touches half the score matrix
         return "tensor", (4.0 if name == "rbm_attn_fwd" else 10.0) * pairs * dk * B * h
+    if name in ("rbm_attn_fwd_lq", "rbm_attn_bwd_lq"):  # Lq compacted queries per sequence against all L keys
+        o = 10 if name == "rbm_attn_fwd_lq" else 18
+        B, Ln, Lq, h, dk = a[o:o + 5]
+        return "tensor", (4.0 if name == "rbm_attn_fwd_lq" else 10.0) * Lq * Ln * dk * B * h
     if name == "rbm_ce_fwd":
         return "tensor", 2.0 * shapes["P"] * a[9] * a[10]
     if name == "rbm_ce_bwd":
@@ -467,6 +471,10 @@ def train_workload(ctx, key, steps, warmup, batch=None, with_cpu=True, with_roof
                     "ms_per_step": ms_e2e / steps},
             "gpu_launches": launches, "clocks": clocks, "roofline": roofline, "kernel_time_shares": shares,
             "roofline_by_entry_point": compact, "cpu_baseline": cpu, "final_loss": losses[-1] if losses else None}
+    if spec["kind"] == "bert":
+        line["config"]["label_rows"] = ("%.1f %% of the positions are labelled; the final block's attention queries, output projection, "
+                                        "LayerNorm, feed-forward and the scoring run on those rows only (exact: the loss reads no other "
+                                        "row of that block)" % (100 * float(np.mean([(b[1] != 0).mean() for b in raw]))))
     if spec["kind"] == "sas":
         frac = float(np.mean([(b[0] != 0).mean() for b in raw]))
         cap = getattr(trainer, "_graph_row_cap", 0) if step_mode == "graph" else None

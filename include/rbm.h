@@ -149,6 +149,21 @@ int rbm_linear_bwd_weight(const float* dpre, int64_t lddpre, const float* x, int
  * P = dropout(softmax(mask(scale * q.k^T)));  out = P.v;  stats[(b*h+hh)*L+i] = {rowmax, 1/rowsum}.
  * replaces Attention.forward NN/models/bert_modules/attention/single.py:13-35 and the core of
  * nn.MultiheadAttention at NN/models/sas_model/sas.py:75-76. */
+/* rbm_attn_fwd / rbm_attn_bwd with the queries a per-sequence compacted subset: q / out / dout / dq are [B*Lq, ld] (Lq rows per
+ * sequence, zero rows after the real ones), k / v / dk / dv [B*L, ld], stats [B*h*Lq, 2], ws rbm_attn_bwd_lq_ws_bytes(B, Lq, h).
+ * BERT4Rec training reads the final block's output at the labelled positions only (NN/trainers/bert.py:36-40), so that block's
+ * attention needs those queries only -- against every key.  Tensor path only: d_k = 32, Lq <= L <= 256, mask NONE / KEYPAD; dropout
+ * fields are indexed by (sequence-head, compact query ordinal, key position). */
+int rbm_attn_lq_supported(int L, int Lq, int dk, int mask_mode);
+int rbm_attn_fwd_lq(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                    const int64_t* tok, float* out, int64_t ldo, float* stats, int B, int L, int Lq, int h, int dk,
+                    int mask_mode, float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream);
+size_t rbm_attn_bwd_lq_ws_bytes(int B, int Lq, int h);
+int rbm_attn_bwd_lq(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                    const int64_t* tok, const float* out, int64_t ldo, const float* dout, int64_t lddo,
+                    const float* stats, float* dq, int64_t lddq, float* dk_, int64_t lddk, float* dv, int64_t lddv, int B,
+                    int L, int Lq, int h, int dk, int mask_mode, float scale, float p, uint64_t seed, uint64_t site, void* ws,
+                    size_t ws_bytes, rbm_stream_t stream);
 /* evaluation (K20): attention of the LAST query position of every sequence only -- q/out are [B, h*dk] (row b = sequence b),
  * k/v the [B*L, ld] rows of every position.  Same masks as rbm_attn_fwd (the causal mask leaves the last query every key), no
  * dropout.  Replaces the `[:, -1, :]` slice of NN/trainers/bert.py:47 and NN/models/sas_model/sas.py:111 being taken AFTER the
@@ -184,6 +199,12 @@ int rbm_rows_dead_colsum(const float* src, int64_t ld, const int64_t* tok, int64
 /* out[c] = sum of the first *count rows of the compact [cap, d] tensor (ws: rbm_rows_dead_colsum_ws_bytes(d)) */
 int rbm_rows_live_colsum(const float* src, int64_t ld, const int32_t* count, int64_t cap, int d, float* out, void* ws,
                          size_t ws_bytes, rbm_stream_t stream);
+
+/* compact rows <-> per-sequence padded layout [B, Lq, d]: slot o of sequence b = compact row seq_start[b] + o, zero rows past the
+ * sequence's last live row (no sequence may have more than Lq live rows: the caller checks).  Each is the other's gradient. */
+int rbm_rows_to_seq(const float* src, const int32_t* seq_start, int B, int Lq, int d, float* dst, rbm_stream_t stream);
+int rbm_seq_to_rows(const float* src, const int32_t* rows, const int32_t* seq_start, const int32_t* count, int64_t cap, int L,
+                    int Lq, int d, float* dst, rbm_stream_t stream);
 
 /* ---- SASRec attention on the compact (live-row) layout (csrc/attention_live.cu) ---------------------
  * q [cap, h*dk] and kv [cap, 2*h*dk] (k | v) hold the live rows in ascending (sequence, position) order (rows / count / tok as

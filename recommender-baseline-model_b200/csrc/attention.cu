@@ -484,7 +484,7 @@ extern "C" int rbm_attn_fwd(const float* q, int64_t ldq, const float* k, int64_t
                   ((uintptr_t)out & 7) == 0,
               "rbm_attn_fwd: q/k/v must be 16B aligned with strides %% 4 == 0 (out: 8B, stride %% 2)");
   if (rbm_attn_fwd_tc_supported(L, dk, ldq, ldk, ldv, ldo, q, k, v, out))  // Blackwell tensor path (d_k == 32)
-    return rbm_attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site,
+    return rbm_attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, L, h, mask_mode, scale, p, seed, site,
                                   (cudaStream_t)stream);
   if (rbm_attn_pair_supported(L, dk, mask_mode) && stats && ldo % 2 == 0)  // d_k = 64, L <= 64: split-fp16 tcgen05 path (attention_pair.cu)
     return rbm_attn_pair_fwd(q, ldq, k, ldk, v, ldv, out, ldo, stats, B, L, h, mask_mode, scale, p, seed, site, (cudaStream_t)stream);
@@ -531,14 +531,14 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
   cudaStream_t st = (cudaStream_t)stream;
   int warps = pick_warps(L), rc;
   if (rbm_attn_bwd_dq_tc_supported(L, dk, ldq, ldk, ldv, ldo, lddo, lddq, q, k, v, out, dout, dq)) {
-    rc = rbm_attn_bwd_dq_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, dout, lddo, stats, dq, lddq, (float*)ws, B, L, h, mask_mode,
+    rc = rbm_attn_bwd_dq_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, dout, lddo, stats, dq, lddq, (float*)ws, B, L, L, h, mask_mode,
                                    scale, p, seed, site, st);
   } else {
     ATTN_DISPATCH(attn_bwd_dq_kernel, smem_dq, "rbm_attn_bwd(dq)");
   }
   if (rc) return rc;
   if (rbm_attn_bwd_dkv_tc_supported(L, dk, ldq, ldk, ldv, lddo, lddk, lddv, q, k, v, dout, dk_, dv))
-    return rbm_attn_bwd_dkv_tc_launch(q, ldq, k, ldk, v, ldv, tok, dout, lddo, stats, (const float*)ws, dk_, lddk, dv, lddv, B, L, h,
+    return rbm_attn_bwd_dkv_tc_launch(q, ldq, k, ldk, v, ldv, tok, dout, lddo, stats, (const float*)ws, dk_, lddk, dv, lddv, B, L, L, h,
                                       mask_mode, scale, p, seed, site, st);
   if (warps <= 4 && dk <= 64) {  // (the d_k = 128 accumulators do not fit 168 registers: 2 KB of spills)
     if (dk <= 32) rc = launch(attn_bwd_dkv_kernel<4, 4>, a, B, warps, smem_dkv, st, "rbm_attn_bwd(dkv)");
@@ -547,6 +547,47 @@ extern "C" int rbm_attn_bwd(const float* q, int64_t ldq, const float* k, int64_t
     ATTN_DISPATCH(attn_bwd_dkv_kernel, smem_dkv, "rbm_attn_bwd(dkv)");
   }
   return rc;
+}
+
+// ---- queries are a per-sequence compacted subset (Lq rows per sequence, zero rows after the real ones), keys / values all L positions.
+// Tensor path only (d_k = 32, L <= 256), no causal mask (a compacted query has lost its position); dropout fields are indexed by
+// (sequence-head, compact query ordinal, key position).
+extern "C" int rbm_attn_lq_supported(int L, int Lq, int dk, int mask_mode) {
+  return dk == 32 && L >= 1 && L <= 256 && Lq >= 1 && Lq <= L && mask_mode != RBM_MASK_CAUSAL ? 1 : 0;
+}
+
+extern "C" int rbm_attn_fwd_lq(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                               const int64_t* tok, float* out, int64_t ldo, float* stats, int B, int L, int Lq, int h, int dk,
+                               int mask_mode, float scale, float p, uint64_t seed, uint64_t site, rbm_stream_t stream) {
+  RBM_REQUIRE(q && k && v && out && stats, "rbm_attn_fwd_lq: null pointer");
+  if (check_common("rbm_attn_fwd_lq", B, L, h, dk, mask_mode, p, tok)) return -1;
+  RBM_REQUIRE(rbm_attn_lq_supported(L, Lq, dk, mask_mode), "rbm_attn_fwd_lq: need d_k = 32, Lq <= L <= 256, no causal mask (L=%d Lq=%d d_k=%d)", L,
+              Lq, dk);
+  RBM_REQUIRE(rbm_attn_fwd_tc_supported(L, dk, ldq, ldk, ldv, ldo, q, k, v, out), "rbm_attn_fwd_lq: operands not laid out for the tensor path");
+  return rbm_attn_fwd_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, stats, B, L, Lq, h, mask_mode, scale, p, seed, site, (cudaStream_t)stream);
+}
+
+extern "C" size_t rbm_attn_bwd_lq_ws_bytes(int B, int Lq, int h) { return (size_t)B * Lq * h * sizeof(float); }
+
+extern "C" int rbm_attn_bwd_lq(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv,
+                               const int64_t* tok, const float* out, int64_t ldo, const float* dout, int64_t lddo,
+                               const float* stats, float* dq, int64_t lddq, float* dk_, int64_t lddk, float* dv, int64_t lddv, int B,
+                               int L, int Lq, int h, int dk, int mask_mode, float scale, float p, uint64_t seed, uint64_t site, void* ws,
+                               size_t ws_bytes, rbm_stream_t stream) {
+  RBM_REQUIRE(q && k && v && out && dout && stats && dq && dk_ && dv && ws, "rbm_attn_bwd_lq: null pointer");
+  if (check_common("rbm_attn_bwd_lq", B, L, h, dk, mask_mode, p, tok)) return -1;
+  RBM_REQUIRE(rbm_attn_lq_supported(L, Lq, dk, mask_mode), "rbm_attn_bwd_lq: need d_k = 32, Lq <= L <= 256, no causal mask (L=%d Lq=%d d_k=%d)", L,
+              Lq, dk);
+  RBM_REQUIRE(ws_bytes >= rbm_attn_bwd_lq_ws_bytes(B, Lq, h), "rbm_attn_bwd_lq: workspace too small");
+  RBM_REQUIRE(rbm_attn_bwd_dq_tc_supported(L, dk, ldq, ldk, ldv, ldo, lddo, lddq, q, k, v, out, dout, dq) &&
+                  rbm_attn_bwd_dkv_tc_supported(L, dk, ldq, ldk, ldv, lddo, lddk, lddv, q, k, v, dout, dk_, dv),
+              "rbm_attn_bwd_lq: operands not laid out for the tensor path");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = rbm_attn_bwd_dq_tc_launch(q, ldq, k, ldk, v, ldv, tok, out, ldo, dout, lddo, stats, dq, lddq, (float*)ws, B, L, Lq, h, mask_mode, scale,
+                                     p, seed, site, st);
+  if (rc) return rc;
+  return rbm_attn_bwd_dkv_tc_launch(q, ldq, k, ldk, v, ldv, tok, dout, lddo, stats, (const float*)ws, dk_, lddk, dv, lddv, B, L, Lq, h,
+                                    mask_mode, scale, p, seed, site, st);
 }
 
 RBM_DEFINE_STEP_PTR_SETTER(rbm_step_ptr_set_attention)

@@ -127,6 +127,7 @@ struct TcAttnArgs {
   float* stats;
   int64_t ldo;
   int L, LPK, h, NT, mask_mode, items;
+  int Lq;  // query rows per sequence (== L unless the queries are a compacted subset: rbm_attn_fwd_lq / rbm_attn_bwd_lq)
   float scale_log2;
   uint32_t thr16;
   float inv_keep;
@@ -299,7 +300,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
       const int item = (int)blockIdx.x + n * (int)gridDim.x;
       const int bh = item / a.NT, mt = item - bh * a.NT;
       const int i = mt * 128 + rl;
-      const bool warp_live = mt * 128 + q * 32 < L;  // a warp whose 32 rows all lie beyond the sequence only keeps the hand-shakes going
+      const bool warp_live = mt * 128 + q * 32 < a.Lq;  // a warp whose 32 rows all lie beyond the sequence only keeps the hand-shakes going
       const float* ku = kuse[n & 1];
       const float* kf = kfill[n & 1];
       // ---- pass 1: row maximum (log2 domain) over this group's chunks
@@ -384,8 +385,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
       if (grp == 0) {
         const float inv = 1.f / (xsum[0][rl] + xsum[1][rl]);
         xinv[n & 1][rl] = inv;
-        if (i < L && a.stats) {
-          const int64_t sr = ((int64_t)bh * L + i) * 2;
+        if (i < a.Lq && a.stats) {
+          const int64_t sr = ((int64_t)bh * a.Lq + i) * 2;
           a.stats[sr] = mx;
           a.stats[sr + 1] = inv;
         }
@@ -445,8 +446,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) attn_fwd_tc_kernel(const __grid_
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&o_free));
-      const int64_t row0 = (int64_t)b * L + mt * 128 + q * 32;
-      const int rows_ok = L - (mt * 128 + q * 32);
+      const int64_t row0 = (int64_t)b * a.Lq + mt * 128 + q * 32;
+      const int rows_ok = a.Lq - (mt * 128 + q * 32);
       float* base = a.out + row0 * a.ldo + hh * DK;
 #pragma unroll
       for (int it = 0; it < 8; ++it) {
@@ -542,6 +543,7 @@ struct TcBwdArgs {
   int64_t ldq, ldo, lddo, lddq;
   const int64_t* tok;
   int L, LPK, h, NT, mask_mode, items;
+  int Lq;  // query rows per sequence (== L unless the queries are a compacted subset: rbm_attn_fwd_lq / rbm_attn_bwd_lq)
   float scale, scale_log2;
   uint32_t thr16;
   float inv_keep;
@@ -730,11 +732,11 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
         bh = item / a.NT;
         const int mt = item - bh * a.NT;
         i = mt * 128 + rl;
-        warp_live = mt * 128 + q * 32 < L;  // a warp whose 32 rows all lie beyond the sequence has nothing to do
+        warp_live = mt * 128 + q * 32 < a.Lq;  // a warp whose 32 rows all lie beyond the sequence has nothing to do
         // rows beyond the sequence hold zero operands: mx = 0, inv = 0 makes every dS of theirs an exact zero
         mx = 0.f; inv = 0.f;
-        if (i < L) {
-          const int64_t sr = ((int64_t)bh * L + i) * 2;
+        if (i < a.Lq) {
+          const int64_t sr = ((int64_t)bh * a.Lq + i) * 2;
           mx = a.stats[sr];
           inv = a.stats[sr + 1];
         }
@@ -834,8 +836,8 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
       __syncwarp();
       if (lane == 0) mbar_arrive(smem_u32(&dq_free[n & 1]));
       if (q == 0) tc_trace(a.trace, tcnt, 9, n);
-      if (i < L) {
-        float* dst = a.dq + ((int64_t)b * L + i) * a.lddq + hh * DK;
+      if (i < a.Lq) {
+        float* dst = a.dq + ((int64_t)b * a.Lq + i) * a.lddq + hh * DK;
 #pragma unroll
         for (int jj = 0; jj < 32; jj += 4)
           st4(dst + jj, make_float4(o[jj] * a.scale, o[jj + 1] * a.scale, o[jj + 2] * a.scale, o[jj + 3] * a.scale));
@@ -850,7 +852,7 @@ __global__ void __launch_bounds__(A_THREADS, 1) attn_bwd_dq_tc_kernel(const __gr
       kvalid[n & 1][t128] = kval0 ? 1.f : 0.f;
       kvalid[n & 1][t128 + 128] = kval1 ? 1.f : 0.f;
       xdelta[n & 1][rl] = dl;
-      if (i < L) a.delta[(int64_t)bh * L + i] = dl;
+      if (i < a.Lq) a.delta[(int64_t)bh * a.Lq + i] = dl;
       if (q == 0) tc_trace(a.trace, tcnt, 14, n);
       if (n >= 1) {
         mbar_wait(smem_u32(&ops_free), (n - 1) & 1);  // every S / dP of the previous item has read its Q / dO
@@ -939,6 +941,7 @@ struct TcBwdKvArgs {
   int64_t lddk, lddv;
   const int64_t* tok;
   int L, LPK, h, NT, mask_mode, items;
+  int Lq;  // query rows per sequence (== L unless the queries are a compacted subset: rbm_attn_fwd_lq / rbm_attn_bwd_lq)
   float scale, scale_log2;
   uint32_t thr16;
   float inv_keep;
@@ -1210,12 +1213,12 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_dkv_tc_kernel(const __g
       const int item = (int)blockIdx.x + n * (int)gridDim.x;
       const int bh = item / a.NT;
       m0 = i0 = d0 = m1 = i1 = d1 = 0.f;
-      if (t128 < L) {
-        const int64_t r = (int64_t)bh * L + t128;
+      if (t128 < a.Lq) {
+        const int64_t r = (int64_t)bh * a.Lq + t128;
         m0 = a.stats[r * 2]; i0 = a.stats[r * 2 + 1]; d0 = a.delta[r];
       }
-      if (t128 + 128 < L) {
-        const int64_t r = (int64_t)bh * L + t128 + 128;
+      if (t128 + 128 < a.Lq) {
+        const int64_t r = (int64_t)bh * a.Lq + t128 + 128;
         m1 = a.stats[r * 2]; i1 = a.stats[r * 2 + 1]; d1 = a.delta[r];
       }
       mbar_wait(smem_u32(&rows_full), n & 1);
@@ -1391,17 +1394,17 @@ bool rbm_attn_fwd_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64_t 
 }
 
 int rbm_attn_fwd_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
-                           float* out, int64_t ldo, float* stats, int B, int L, int h, int mask_mode, float scale, float p,
+                           float* out, int64_t ldo, float* stats, int B, int L, int Lq, int h, int mask_mode, float scale, float p,
                            uint64_t seed, uint64_t site, cudaStream_t st) {
-  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+  const int LPK = (L + 15) & ~15, NT = (Lq + 127) / 128;  // query tiles over Lq rows, keys over L
   CUtensorMap mapQ, mapK, mapV;
-  if (!encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) || !encode_map3(&mapK, k, B, L, h * DK, ldk, 64, false) ||
+  if (!encode_map3(&mapQ, q, B, Lq, h * DK, ldq, 128, false) || !encode_map3(&mapK, k, B, L, h * DK, ldk, 64, false) ||
       !encode_map3(&mapV, v, B, L, h * DK, ldv, 64, true)) {
     rbm_set_error("rbm_attn_fwd(tcgen05): cuTensorMapEncodeTiled failed");
     return -1;
   }
   TcAttnArgs a{};
-  a.tok = tok; a.out = out; a.stats = stats; a.ldo = ldo; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode;
+  a.tok = tok; a.out = out; a.stats = stats; a.ldo = ldo; a.L = L; a.Lq = Lq; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode;
   a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   a.items = B * h * NT;
@@ -1438,19 +1441,19 @@ bool rbm_attn_bwd_dq_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int64
 
 int rbm_attn_bwd_dq_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
                               const float* o, int64_t ldo, const float* dout, int64_t lddo, const float* stats, float* dq, int64_t lddq,
-                              float* delta, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed, uint64_t site,
-                              cudaStream_t st) {
-  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+                              float* delta, int B, int L, int Lq, int h, int mask_mode, float scale, float p, uint64_t seed,
+                              uint64_t site, cudaStream_t st) {
+  const int LPK = (L + 15) & ~15, NT = (Lq + 127) / 128;
   CUtensorMap mapKk, mapKm, mapVk, mapQ, mapDO, mapO;
   if (!encode_map3(&mapKk, k, B, L, h * DK, ldk, CW, false) || !encode_map3(&mapKm, k, B, L, h * DK, ldk, CW, true) ||
-      !encode_map3(&mapVk, v, B, L, h * DK, ldv, CW, false) || !encode_map3(&mapQ, q, B, L, h * DK, ldq, 128, false) ||
-      !encode_map3(&mapDO, dout, B, L, h * DK, lddo, 128, false) || !encode_map3(&mapO, o, B, L, h * DK, ldo, 128, false)) {
+      !encode_map3(&mapVk, v, B, L, h * DK, ldv, CW, false) || !encode_map3(&mapQ, q, B, Lq, h * DK, ldq, 128, false) ||
+      !encode_map3(&mapDO, dout, B, Lq, h * DK, lddo, 128, false) || !encode_map3(&mapO, o, B, Lq, h * DK, ldo, 128, false)) {
     rbm_set_error("rbm_attn_bwd(tcgen05): cuTensorMapEncodeTiled failed");
     return -1;
   }
   TcBwdArgs a{};
   a.q = q; a.o = o; a.dout = dout; a.stats = stats; a.dq = dq; a.delta = delta; a.ldq = ldq; a.ldo = ldo; a.lddo = lddo; a.lddq = lddq;
-  a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
+  a.tok = tok; a.L = L; a.Lq = Lq; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   a.items = B * h * NT;
   a.trace = trace_begin();
@@ -1488,19 +1491,19 @@ bool rbm_attn_bwd_dkv_tc_supported(int L, int dk, int64_t ldq, int64_t ldk, int6
 
 int rbm_attn_bwd_dkv_tc_launch(const float* q, int64_t ldq, const float* k, int64_t ldk, const float* v, int64_t ldv, const int64_t* tok,
                                const float* dout, int64_t lddo, const float* stats, const float* delta, float* dk_, int64_t lddk,
-                               float* dv, int64_t lddv, int B, int L, int h, int mask_mode, float scale, float p, uint64_t seed,
+                               float* dv, int64_t lddv, int B, int L, int Lq, int h, int mask_mode, float scale, float p, uint64_t seed,
                                uint64_t site, cudaStream_t st) {
-  const int LPK = (L + 15) & ~15, NT = (L + 127) / 128;
+  const int LPK = (Lq + 15) & ~15, NT = (L + 127) / 128;  // this kernel tiles the KEYS (L) and streams the queries (Lq, padded to 16)
   CUtensorMap mQk, mQm, mOk, mOm, mK, mV;
-  if (!encode_map3(&mQk, q, B, L, h * DK, ldq, SQ, false) || !encode_map3(&mQm, q, B, L, h * DK, ldq, SQ, true) ||
-      !encode_map3(&mOk, dout, B, L, h * DK, lddo, SQ, false) || !encode_map3(&mOm, dout, B, L, h * DK, lddo, SQ, true) ||
+  if (!encode_map3(&mQk, q, B, Lq, h * DK, ldq, SQ, false) || !encode_map3(&mQm, q, B, Lq, h * DK, ldq, SQ, true) ||
+      !encode_map3(&mOk, dout, B, Lq, h * DK, lddo, SQ, false) || !encode_map3(&mOm, dout, B, Lq, h * DK, lddo, SQ, true) ||
       !encode_map3(&mK, k, B, L, h * DK, ldk, 128, false) || !encode_map3(&mV, v, B, L, h * DK, ldv, 128, false)) {
     rbm_set_error("rbm_attn_bwd(tcgen05 dkv): cuTensorMapEncodeTiled failed");
     return -1;
   }
   TcBwdKvArgs a{};
   a.stats = stats; a.delta = delta; a.dk = dk_; a.dv = dv; a.lddk = lddk; a.lddv = lddv;
-  a.tok = tok; a.L = L; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
+  a.tok = tok; a.L = L; a.Lq = Lq; a.LPK = LPK; a.h = h; a.NT = NT; a.mask_mode = mask_mode; a.scale = scale; a.scale_log2 = scale * RBM_LOG2E;
   a.thr16 = rbm_drop_threshold16(p); a.inv_keep = 1.f / (1.f - p); a.seed = seed; a.site = site;
   a.items = B * h * NT;
   a.trace = nullptr;

@@ -46,6 +46,33 @@ __global__ void __launch_bounds__(256) rows_scatter_kernel(const float* __restri
   }
 }
 
+// compact rows <-> a per-sequence padded layout [B, Lq, d]: slot o of sequence b = compact row seq_start[b] + o (zero rows past the
+// sequence's last live row).  The caller guarantees that no sequence has more than Lq live rows.
+__global__ void __launch_bounds__(256) rows_to_seq_kernel(const float* __restrict__ src, const int32_t* __restrict__ seq_start, int64_t nslots,
+                                                          int Lq, int d4, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= nslots * d4) return;
+  const int64_t slot = i / d4;
+  const int c = (int)(i - slot * d4) * 4;
+  const int b = (int)(slot / Lq), o = (int)(slot - (int64_t)b * Lq);
+  const int r = seq_start[b] + o;
+  st4(dst + slot * (int64_t)d4 * 4 + c, r < seq_start[b + 1] ? ld4(src + (int64_t)r * d4 * 4 + c) : make_float4(0.f, 0.f, 0.f, 0.f));
+}
+__global__ void __launch_bounds__(256) seq_to_rows_kernel(const float* __restrict__ src, const int32_t* __restrict__ rows,
+                                                          const int32_t* __restrict__ seq_start, const int32_t* __restrict__ count, int64_t cap,
+                                                          int L, int Lq, int d4, float* __restrict__ dst) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cap * d4) return;
+  const int64_t r = i / d4;
+  const int c = (int)(i - r * d4) * 4;
+  float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (r < *count) {
+    const int b = rows[r] / L, o = (int)r - seq_start[b];
+    if (o < Lq) v = ld4(src + ((int64_t)b * Lq + o) * d4 * 4 + c);
+  }
+  st4(dst + r * (int64_t)d4 * 4 + c, v);
+}
+
 constexpr int DC_BLOCKS = 8 * RBM_NUM_SMS;
 // stage 1: block b sums the padding rows of its contiguous row range.  Thread t owns the float4 column group t % d4 of the rows
 // r0 + t / d4, + 256 / d4, ... (ascending); the 256 / d4 row lanes are then added in lane order: a fixed summation tree.
@@ -143,5 +170,26 @@ extern "C" int rbm_rows_live_colsum(const float* src, int64_t ld, const int32_t*
   RBM_LAUNCH_CHECK("rbm_rows_live_colsum");
   dead_colsum_final_kernel<<<(unsigned)d, 256, 0, (cudaStream_t)stream>>>(part, DC_BLOCKS, d, out);
   RBM_LAUNCH_CHECK("rbm_rows_live_colsum(final)");
+  return 0;
+}
+
+extern "C" int rbm_rows_to_seq(const float* src, const int32_t* seq_start, int B, int Lq, int d, float* dst, rbm_stream_t stream) {
+  RBM_REQUIRE(src && seq_start && dst && B >= 0 && Lq >= 1 && d > 0 && d % 4 == 0, "rbm_rows_to_seq: bad arguments");
+  RBM_REQUIRE(rbm_aligned16(src) && rbm_aligned16(dst), "rbm_rows_to_seq: pointers must be 16B aligned");
+  const int64_t total = (int64_t)B * Lq * (d / 4);
+  if (total == 0) return 0;
+  rows_to_seq_kernel<<<(unsigned)rbm_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, seq_start, (int64_t)B * Lq, Lq, d / 4, dst);
+  RBM_LAUNCH_CHECK("rbm_rows_to_seq");
+  return 0;
+}
+
+extern "C" int rbm_seq_to_rows(const float* src, const int32_t* rows, const int32_t* seq_start, const int32_t* count, int64_t cap, int L,
+                               int Lq, int d, float* dst, rbm_stream_t stream) {
+  RBM_REQUIRE(src && rows && seq_start && count && dst && cap >= 0 && L >= 1 && Lq >= 1 && d > 0 && d % 4 == 0, "rbm_seq_to_rows: bad arguments");
+  RBM_REQUIRE(rbm_aligned16(src) && rbm_aligned16(dst), "rbm_seq_to_rows: pointers must be 16B aligned");
+  const int64_t total = cap * (d / 4);
+  if (total == 0) return 0;
+  seq_to_rows_kernel<<<(unsigned)rbm_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(src, rows, seq_start, count, cap, L, Lq, d / 4, dst);
+  RBM_LAUNCH_CHECK("rbm_seq_to_rows");
   return 0;
 }

@@ -56,6 +56,13 @@ SIGNATURES = {
     "rbm_rows_seq_start": (_I, [_P, _P, _I, _I, _P, _P]),
     "rbm_attn_live_fwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
     "rbm_attn_live_bwd": (_I, [_P, _L, _P, _L, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
+    "rbm_rows_to_seq": (_I, [_P, _P, _I, _I, _I, _P, _P]),
+    "rbm_seq_to_rows": (_I, [_P, _P, _P, _P, _L, _I, _I, _I, _P, _P]),
+    "rbm_attn_lq_supported": (_I, [_I, _I, _I, _I]),
+    "rbm_attn_fwd_lq": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
+    "rbm_attn_bwd_lq_ws_bytes": (_SZ, [_I, _I, _I]),
+    "rbm_attn_bwd_lq": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _P, _L, _P, _L, _P, _L, _I, _I, _I, _I, _I, _I, _F,
+                             _F, _U64, _U64, _P, _SZ, _P]),
     "rbm_attn_last_query": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _I, _I, _I, _I, _I, _F, _P]),
     "rbm_attn_fwd": (_I, [_P, _L, _P, _L, _P, _L, _P, _P, _L, _P, _I, _I, _I, _I, _I, _F, _F, _U64, _U64, _P]),
     "rbm_attn_bwd_ws_bytes": (_SZ, [_I, _I, _I]),

@@ -156,6 +156,21 @@ class BERTModel(BaseModel):
                 u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH)
                 return ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=xl)
             n1, x = ops.layernorm_residual(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            lq = getattr(label_rows, "lq", None) if (label_rows is not None and b == len(bert.transformer_blocks) - 1) else None
+            if lq is not None and ops.attention_lq_supported(Ln, lq, d // h, L.MASK_KEYPAD):
+                # final block, labelled rows: queries of those rows only (<= lq per sequence, compacted per sequence) against the
+                # keys / values of every position; the attention site indexes its Philox stream by (sequence-head, query ordinal, key)
+                wq, wk, wv = att.linear_layers
+                kv = ops.linear(n1, torch.cat([wk.weight, wv.weight], 0), torch.cat([wk.bias, wv.bias], 0))
+                qc = ops.linear(ops.rows_gather(n1.view(-1, d), label_rows), wq.weight, wq.bias)
+                ctx = ops.attention_lq(ops.rows_to_seq(qc, label_rows, Bsz, Ln, lq), kv, tok, Bsz, Ln, lq, h, L.MASK_KEYPAD, scale, p_a,
+                                       seed, s)
+                ctx = ops.seq_to_rows(ctx, label_rows, Bsz, Ln, lq)
+                xc = ops.linear(ctx, att.output_linear.weight, att.output_linear.bias, residual=ops.rows_gather(x.view(-1, d), label_rows),
+                                pA=p_h, siteA=s + 1, seed=seed)
+                n2, xc = ops.layernorm_residual(xc, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+                u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH, pA=p_h, siteA=s + 2, seed=seed)
+                return ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=xc, pA=p_h, siteA=s + 3, pB=p_h, siteB=s + 4, seed=seed)
             w_qkv = torch.cat([l.weight for l in att.linear_layers], 0)
             b_qkv = torch.cat([l.bias for l in att.linear_layers], 0)
             qkv = ops.linear(n1, w_qkv, b_qkv)
@@ -213,34 +228,57 @@ class BERTModel(BaseModel):
     LABEL_ROWS_MAX_FRACTION = 0.5  # above this share of labelled positions the final block runs on every row
 
     def _label_rows(self, labels):
-        """``ops.LiveRows`` over the labelled positions, or None (final block on every row).  Eager steps read the number of labels
-        back (one host sync); under a CUDA graph the trainer fixes the capacity before capture (``_row_cap``: rows, 0 = off) and
-        checks every replayed batch against it."""
+        """``ops.LiveRows`` over the labelled positions (``.lq``: an upper bound on the labelled positions of one sequence, None =
+        keep every query in the final block's attention), or None (final block on every row).  Eager steps read the counts back
+        (one host sync); under a CUDA graph the trainer fixes both capacities before capture (``_row_cap``: rows, 0 = off;
+        ``_graph_lq``) and checks every replayed batch against them."""
         if os.environ.get("RBM_BERT_LABEL_ROWS", "1") == "0":
             return None
-        n = labels.numel()
+        n, Ln = labels.numel(), labels.shape[-1]
         cap = getattr(self, "_row_cap", None)
         if cap is None:
-            cnt = int(torch.count_nonzero(labels).item())
+            cnt, mx = self._label_counts(labels)
             if cnt > self.LABEL_ROWS_MAX_FRACTION * n:
                 return None
-            cap = max(128, -(-cnt // 128) * 128)
+            cap, lq = max(128, -(-cnt // 128) * 128), max(16, -(-mx // 16) * 16)
         elif cap <= 0:
             return None
-        return ops.LiveRows(labels, cap, keep_ids=True)
+        else:
+            lq = getattr(self, "_graph_lq", None)
+        live = ops.LiveRows(labels, cap, keep_ids=True)
+        live.lq = lq if (lq is not None and lq < Ln and os.environ.get("RBM_BERT_LABEL_QUERIES", "1") != "0") else None
+        return live
+
+    @staticmethod
+    def _label_counts(labels):
+        """(labelled positions of the batch, most labelled positions of one sequence) -- one device -> host read."""
+        m = torch.as_tensor(labels) != 0
+        cnt, mx = torch.stack([m.sum(), m.reshape(-1, m.shape[-1]).sum(1).max()]).tolist()
+        return int(cnt), int(mx)
 
     def row_capacity_for(self, tokens, labels) -> int:
         """Capacity (rows) a captured step should be built with for batches like this one: 25 % headroom over its labelled rows
-        (0 = run the final block on every row).  ``live_row_count`` tells the trainer whether a later batch still fits."""
+        (0 = run the final block on every row), and the per-sequence query capacity ``_graph_lq`` of the final block's attention.
+        ``live_row_count`` tells the trainer whether a later batch still fits."""
+        self._graph_lq = None
         if os.environ.get("RBM_BERT_LABEL_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
             return 0
-        n, cnt = int(torch.as_tensor(labels).numel()), self.live_row_count(tokens, labels)
+        labels = torch.as_tensor(labels)
+        n, Ln = int(labels.numel()), int(labels.shape[-1])
+        cnt, mx = self._label_counts(labels)
         cap = -(-(cnt + cnt // 4 + 64) // 128) * 128
-        return cap if cap <= self.LABEL_ROWS_MAX_FRACTION * n else 0
+        if cap > self.LABEL_ROWS_MAX_FRACTION * n:
+            return 0
+        lq = -(-(mx + mx // 4 + 8) // 16) * 16
+        self._graph_lq = lq if lq < Ln else None
+        return cap
 
-    @staticmethod
-    def live_row_count(tokens, labels) -> int:
-        return int(torch.count_nonzero(torch.as_tensor(labels)).item())
+    def live_row_count(self, tokens, labels) -> int:
+        """Labelled rows of the batch -- or more than any capacity when one sequence has more labels than the captured step's
+        per-sequence query capacity."""
+        cnt, mx = self._label_counts(labels)
+        lq = getattr(self, "_graph_lq", None)
+        return (1 << 60) if (lq is not None and mx > lq) else cnt
 
     def last_hidden(self, x):
         if not self.training and not torch.is_grad_enabled():

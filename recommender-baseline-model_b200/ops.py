@@ -487,6 +487,105 @@ def attention(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p=0.0, seed=0
     return AttnFn.apply(a, b, tok, Bsz, Ln, h, qc, kc, vc, mask_mode, scale, p, seed, site)
 
 
+class AttnLqFn(torch.autograd.Function):
+    """Attention with per-sequence compacted queries: ``q`` [B*Lq, d] (Lq rows per sequence, zero rows after the real ones) against
+    the keys / values of all L positions, ``kv`` [B*L, 2d] (k | v).  Tensor path only (rbm_attn_fwd_lq / rbm_attn_bwd_lq)."""
+
+    @staticmethod
+    def forward(ctx, q, kv, tok, Bsz, Ln, Lq, h, mask_mode, scale, p, seed, site):
+        lib = L.load()
+        L.require_cuda(q, kv)
+        q, kv = q.contiguous(), kv.contiguous()
+        d = q.shape[1]
+        if tok is not None:
+            tok = tok.reshape(-1).contiguous()
+        out = torch.empty(Bsz * Lq, d, device=q.device, dtype=torch.float32)
+        stats = torch.empty(Bsz * h * Lq, 2, device=q.device, dtype=torch.float32)
+        check(lib.rbm_attn_fwd_lq(ptr(q), d, ptr(kv), 2 * d, kv.data_ptr() + 4 * d, 2 * d, ptr(tok), ptr(out), d, ptr(stats), Bsz, Ln, Lq,
+                                  h, d // h, int(mask_mode), float(scale), float(p), seed, site, stream()), "attn_fwd_lq")
+        count_launches()
+        ctx.save_for_backward(q, kv, tok, out, stats)
+        ctx.meta = (Bsz, Ln, Lq, h, d, int(mask_mode), float(scale), float(p), seed, site)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        lib = L.load()
+        q, kv, tok, out, stats = ctx.saved_tensors
+        Bsz, Ln, Lq, h, d, mask_mode, scale, p, seed, site = ctx.meta
+        dout = dout.contiguous()
+        dq = torch.empty_like(q)
+        dkv = torch.empty_like(kv)
+        nb = lib.rbm_attn_bwd_lq_ws_bytes(Bsz, Lq, h)
+        ws = _ws("attn", nb, q.device)
+        check(lib.rbm_attn_bwd_lq(ptr(q), d, ptr(kv), 2 * d, kv.data_ptr() + 4 * d, 2 * d, ptr(tok), ptr(out), d, ptr(dout), d, ptr(stats),
+                                  ptr(dq), d, ptr(dkv), 2 * d, dkv.data_ptr() + 4 * d, 2 * d, Bsz, Ln, Lq, h, d // h, mask_mode, scale, p,
+                                  seed, site, ptr(ws), nb, stream()), "attn_bwd_lq")
+        count_launches(2)
+        return (dq, dkv) + (None,) * 10
+
+
+def attention_lq(q, kv, tok, Bsz, Ln, Lq, h, mask_mode, scale, p=0.0, seed=0, site=0):
+    return AttnLqFn.apply(q, kv, tok, Bsz, Ln, Lq, h, mask_mode, scale, p, seed, site)
+
+
+def attention_lq_supported(Ln, Lq, dk, mask_mode) -> bool:
+    return bool(L.load().rbm_attn_lq_supported(int(Ln), int(Lq), int(dk), int(mask_mode)))
+
+
+def _rows_to_seq(xc, live, Bsz, Lq):
+    lib = L.load()
+    d = xc.shape[1]
+    out = torch.empty(Bsz * Lq, d, device=xc.device, dtype=torch.float32)
+    check(lib.rbm_rows_to_seq(ptr(xc), ptr(live.seq_start), Bsz, Lq, d, ptr(out), stream()), "rows_to_seq")
+    count_launches()
+    return out
+
+
+def _seq_to_rows(xs, live, Ln, Lq):
+    lib = L.load()
+    d = xs.shape[1]
+    out = torch.empty(live.cap, d, device=xs.device, dtype=torch.float32)
+    check(lib.rbm_seq_to_rows(ptr(xs), ptr(live.rows), ptr(live.seq_start), ptr(live.count), live.cap, Ln, Lq, d, ptr(out), stream()),
+          "seq_to_rows")
+    count_launches()
+    return out
+
+
+class RowsToSeqFn(torch.autograd.Function):
+    """[cap, d] compact rows -> [B*Lq, d]: slot o of sequence b = its o-th live row, zero rows after the last one."""
+
+    @staticmethod
+    def forward(ctx, xc, live, Bsz, Ln, Lq):
+        ctx.live, ctx.meta = live, (Bsz, Ln, Lq)
+        return _rows_to_seq(xc.contiguous(), live, Bsz, Lq)
+
+    @staticmethod
+    def backward(ctx, dy):
+        Bsz, Ln, Lq = ctx.meta
+        return _seq_to_rows(dy.contiguous(), ctx.live, Ln, Lq), None, None, None, None
+
+
+class SeqToRowsFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, xs, live, Bsz, Ln, Lq):
+        ctx.live, ctx.meta = live, (Bsz, Ln, Lq)
+        return _seq_to_rows(xs.contiguous(), live, Ln, Lq)
+
+    @staticmethod
+    def backward(ctx, dy):
+        Bsz, Ln, Lq = ctx.meta
+        return _rows_to_seq(dy.contiguous(), ctx.live, Bsz, Lq), None, None, None, None
+
+
+def rows_to_seq(xc, live, Bsz, Ln, Lq):
+    return RowsToSeqFn.apply(xc, live, Bsz, Ln, Lq)
+
+
+def seq_to_rows(xs, live, Bsz, Ln, Lq):
+    return SeqToRowsFn.apply(xs, live, Bsz, Ln, Lq)
+
+
 class AttnLiveFn(torch.autograd.Function):
     """SASRec causal attention on the compact live-row layout (csrc/attention_live.cu): q [cap, d], kv [cap, 2d] (k | v), every
     padding position's key / value = bkv [2d].  Rows past the live count stay zero."""

@@ -230,6 +230,51 @@ def test_attention_packed(B, Ln, h, dk, mode, p):
     close(qg.grad, qr.grad, 1e-3, 2e-5)
 
 
+@pytest.mark.parametrize("B,Ln,Lq,h", [(5, 200, 48, 2), (90, 200, 32, 2), (3, 200, 128, 1), (7, 130, 16, 2), (2, 256, 144, 2), (4, 40, 16, 2)])
+@pytest.mark.parametrize("mode", [L.MASK_NONE, L.MASK_KEYPAD])
+@pytest.mark.parametrize("p", [0.0, 0.15])
+def test_attention_compacted_queries(B, Ln, Lq, h, mode, p):
+    """rbm_attn_fwd_lq / rbm_attn_bwd_lq (Lq query rows per sequence against all L keys; the final block of BERT4Rec training needs
+    the labelled positions' queries only) against the same reference with the Philox mask the kernels used: the dropout stream is
+    indexed by (sequence-head, query ordinal, key), i.e. the first Lq rows of the exported [L x L] mask."""
+    torch.manual_seed(B * Ln + Lq)
+    dk = 32
+    d = h * dk
+    q = torch.randn(B * Lq, d)
+    nreal = torch.randint(0, Lq + 1, (B,))
+    nreal[0] = Lq
+    for b in range(B):
+        q[b * Lq + int(nreal[b]): (b + 1) * Lq] = 0  # the zero rows that pad a sequence's queries
+    kv = torch.randn(B * Ln, 2 * d)
+    tok = torch.randint(1, 50, (B, Ln))
+    tok[0, : Ln // 3] = 0
+    if B > 1:
+        tok[1, :] = 0
+    dout = torch.randn(B * Lq, d)
+    for b in range(B):
+        dout[b * Lq + int(nreal[b]): (b + 1) * Lq] = 0
+    scale = 1 / math.sqrt(dk)
+    seed, site = 7, 13
+    qg, kvg = g(q).requires_grad_(True), g(kv).requires_grad_(True)
+    out = ops.attention_lq(qg, kvg, g(tok), B, Ln, Lq, h, mode, scale, p, seed, site)
+    out.backward(g(dout))
+    mask = ops.dropout_mask_attn(B * h * Ln, Ln, p, seed, site, DEV).cpu().view(B, h, Ln, Ln)[:, :, :Lq, :] if p > 0 else None
+    qr, kvr = q.clone().requires_grad_(True), kv.clone().requires_grad_(True)
+    qq = qr.view(B, Lq, h, dk).transpose(1, 2).double()
+    kk, vv = (kvr[:, i * d:(i + 1) * d].view(B, Ln, h, dk).transpose(1, 2).double() for i in range(2))
+    sc = qq @ kk.transpose(-1, -2) * scale
+    if mode == L.MASK_KEYPAD:
+        sc = sc.masked_fill((tok == 0)[:, None, None, :], -1e9)
+    pr = torch.softmax(sc, -1)
+    if p > 0:
+        pr = pr * mask.double() / (1 - p)
+    ref = (pr @ vv).transpose(1, 2).reshape(B * Lq, d)
+    ref.backward(dout.double())
+    close(out, ref.float(), 1e-4, 1e-5)
+    close(qg.grad, qr.grad, 1e-3, 2e-5)
+    close(kvg.grad, kvr.grad, 1e-3, 2e-5)
+
+
 @pytest.mark.parametrize("mode", [L.MASK_CAUSAL, L.MASK_KEYPAD])
 def test_attention_persistent_many_items(mode):
     """More (sequence, head, tile) work items than SMs: every persistent tcgen05 CTA walks several items, so the

@@ -178,20 +178,21 @@ def test_cfg_shaped_losses():
     np.testing.assert_array_equal(ids.cpu().numpy(), ref_i)
 
 
-@pytest.mark.parametrize("label_rows", [True, False])
-def test_training_mode_dropout_against_injected_masks(label_rows):
+@pytest.mark.parametrize("label_rows,Ln,d", [(True, 8, 16), (False, 8, 16), (True, 40, 64)])
+def test_training_mode_dropout_against_injected_masks(label_rows, Ln, d):
     """Training-mode BERT4Rec: the oracle consumes the Philox masks the kernels used (exported per site).  ``label_rows``: the
     final block's output projection / LayerNorm / feed-forward on the labelled rows only (the default when at most half of the
-    positions are labelled) or on every row."""
+    positions are labelled) or on every row; at d_k = 32 (d = 64) the final block's attention also takes the labelled positions'
+    queries only, compacted per sequence."""
     from oracle.common import DropoutPlan
-    V, Ln, d, nb, h, B, p = 37, 8, 16, 2, 2, 4, 0.25
+    V, nb, h, B, p = 37, 2, 2, 4, 0.25
     model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, p=p, seed=1)).to(DEV).train()
     model.dropout_seed = 4242
     model.LABEL_ROWS_MAX_FRACTION = 1.0 if label_rows else -1.0
     rng = np.random.RandomState(0)
     tok = torch.from_numpy(rng.randint(1, V + 2, size=(B, Ln)).astype(np.int64))
     tok[0, :3] = 0
-    lab = torch.from_numpy(np.where(rng.rand(B, Ln) < 0.4, rng.randint(1, V + 1, size=(B, Ln)), 0).astype(np.int64))
+    lab = torch.from_numpy(np.where(rng.rand(B, Ln) < (0.4 if Ln == 8 else 0.25), rng.randint(1, V + 1, size=(B, Ln)), 0).astype(np.int64))
     step0 = model._step
     loss = model.loss(tok, lab)
     loss.backward()
@@ -200,9 +201,20 @@ def test_training_mode_dropout_against_injected_masks(label_rows):
     labelled = np.flatnonzero(lab.numpy().reshape(-1))
     compact = len(labelled) <= model.LABEL_ROWS_MAX_FRACTION * B * Ln  # the final block then runs on the labelled rows only
     cap = max(128, -(-len(labelled) // 128) * 128)
+    per_seq = (lab != 0).sum(1)
+    lq = max(16, -(-int(per_seq.max()) // 16) * 16)
+    compact_q = compact and d // h == 32 and lq < Ln  # the final block's attention on per-sequence compacted queries
+    assert compact_q == (label_rows and d == 64)
     for b in range(nb):
         s = ob.block_sites(b)
-        masks[s["attn"]] = ops.dropout_mask_attn(B * h * Ln, Ln, p, 4242, base + s["attn"], DEV).cpu()
+        am = ops.dropout_mask_attn(B * h * Ln, Ln, p, 4242, base + s["attn"], DEV).cpu()
+        if compact_q and b == nb - 1:
+            # Philox stream indexed by (sequence-head, ordinal of the labelled position within its sequence, key)
+            am, src = torch.ones_like(am).view(B, h, Ln, Ln), am.view(B, h, Ln, Ln)
+            for bb in range(B):
+                for o, pos in enumerate(np.flatnonzero(lab[bb].numpy())):
+                    am[bb, :, pos, :] = src[bb, :, o, :]
+        masks[s["attn"]] = am
         for key, w in (("sub_in", d), ("ffn", 4 * d), ("sub_out", d), ("block", d)):
             if compact and b == nb - 1:
                 # element-wise sites of the final block: Philox stream indexed by (labelled-row ordinal, column); the other rows of
