@@ -253,11 +253,8 @@ class BERTModel(BaseModel):
     def _label_counts(labels):
         """(labelled positions of the batch, most labelled positions of one sequence) -- one device -> host read."""
         labels = torch.as_tensor(labels)
-        if not labels.is_cuda:  # host batch (the trainer checks a batch before replaying a captured step): numpy, no tensor temporaries
-            per = np.count_nonzero(labels.numpy().reshape(-1, labels.shape[-1]), axis=1)
-            return int(per.sum()), int(per.max()) if per.size else 0
-        m = labels != 0
-        cnt, mx = torch.stack([m.sum(), m.reshape(-1, m.shape[-1]).sum(1).max()]).tolist()
+        per = torch.count_nonzero(labels.reshape(-1, labels.shape[-1]), dim=1)
+        cnt, mx = torch.stack([per.sum(), per.max()]).tolist()
         return int(cnt), int(mx)
 
     def row_capacity_for(self, tokens, labels) -> int:

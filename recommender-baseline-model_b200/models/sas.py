@@ -7,7 +7,6 @@ given torch seed yields the reference's initial weights); their own ``forward`` 
 import math
 import os
 
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -142,8 +141,6 @@ class SASModel(BaseModel):
     def live_row_count(*ids) -> int:
         """The largest number of non-zero ids among the given tensors (seq, pos, neg of a batch)."""
         ts = [torch.as_tensor(t) for t in ids]
-        if not any(t.is_cuda for t in ts):  # host batch: numpy, no tensor temporaries
-            return max(int(np.count_nonzero(t.numpy())) for t in ts)
         return int(torch.stack([torch.count_nonzero(t) for t in ts]).max().item())
 
     def _blocks_live_rows(self, seq, live, Bsz, Ln, p, seed, base, scale):

@@ -231,10 +231,12 @@ class AbstractTrainer(metaclass=ABCMeta):
         batch = tuple(torch.as_tensor(x) for x in batch)
         if len(batch) != len(self._graph_static) or any(tuple(s.shape) != tuple(d.shape) for s, d in zip(batch, self._graph_static)):
             return self._odd_shaped_step(batch)  # never copy_ a mismatching batch: a 1-row remainder would broadcast silently
-        if self._graph_row_cap and self.model.live_row_count(*batch) > self._graph_row_cap:
-            return self._odd_shaped_step(batch)  # more non-padding rows than the captured live-row capacity
         for dst, src in zip(self._graph_static, batch):
             dst.copy_(src, non_blocking=True)
+        # (the copies are in flight while the host counts: a batch with more live / labelled rows than the captured capacity takes
+        #  an eager step instead -- the static buffers then just hold an unused copy)
+        if self._graph_row_cap and self.model.live_row_count(*batch) > self._graph_row_cap:
+            return self._odd_shaped_step(batch)
         self._graph.replay()
         if self._graph_b is not None:
             self.dist_sync.allreduce_bucket()
