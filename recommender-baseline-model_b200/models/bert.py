@@ -240,7 +240,7 @@ class BERTModel(BaseModel):
             cnt, mx = self._label_counts(labels)
             if cnt > self.LABEL_ROWS_MAX_FRACTION * n:
                 return None
-            cap, lq = max(128, -(-cnt // 128) * 128), max(16, -(-mx // 16) * 16)
+            cap, lq = self._capacities(cnt, mx)  # the same rule a captured step is sized by
         elif cap <= 0:
             return None
         else:
@@ -248,6 +248,13 @@ class BERTModel(BaseModel):
         live = ops.LiveRows(labels, cap, keep_ids=True)
         live.lq = lq if (lq is not None and lq < Ln and os.environ.get("RBM_BERT_LABEL_QUERIES", "1") != "0") else None
         return live
+
+    @staticmethod
+    def _capacities(cnt: int, mx: int):
+        """(row capacity, per-sequence query capacity) for a batch with ``cnt`` labelled positions, at most ``mx`` in one sequence:
+        25 % headroom, rounded to the kernels' tiles.  Eager steps and captured steps use the same rule, so a step replayed from a
+        graph captured on a batch with the same counts is bit-identical to the eager step."""
+        return -(-(cnt + cnt // 4 + 64) // 128) * 128, -(-(mx + mx // 4 + 8) // 16) * 16
 
     @staticmethod
     def _label_counts(labels):
@@ -267,12 +274,11 @@ class BERTModel(BaseModel):
         labels = torch.as_tensor(labels)
         n, Ln = int(labels.numel()), int(labels.shape[-1])
         cnt, mx = self._label_counts(labels)
-        cap = -(-(cnt + cnt // 4 + 64) // 128) * 128
-        if cap > self.LABEL_ROWS_MAX_FRACTION * n:
+        if cnt > self.LABEL_ROWS_MAX_FRACTION * n:
             return 0
-        lq = -(-(mx + mx // 4 + 8) // 16) * 16
+        cap, lq = self._capacities(cnt, mx)
         self._graph_lq = lq if lq < Ln else None
-        return cap
+        return min(cap, -(-n // 128) * 128)
 
     def live_row_count(self, tokens, labels) -> int:
         """Labelled rows of the batch -- or more than any capacity when one sequence has more labels than the captured step's

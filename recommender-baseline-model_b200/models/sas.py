@@ -121,7 +121,7 @@ class SASModel(BaseModel):
             cnts = torch.stack([torch.count_nonzero(t) for t in (seq,) + also]).tolist()
             if cnts[0] > self.LIVE_ROWS_MAX_FRACTION * n:
                 return None
-            cap = max(128, -(-max(cnts) // 128) * 128)
+            cap = self._capacity(max(cnts))  # the same rule a captured step is sized by
         elif cap <= 0:
             return None
         live = ops.LiveRows(seq, cap)
@@ -133,9 +133,15 @@ class SASModel(BaseModel):
         ids, 0 when the dense path is the better choice.  ``live_row_count`` tells the trainer whether a later batch still fits."""
         if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
             return 0
-        n, cnt = int(seq.numel()), self.live_row_count(seq, *also)
-        cap = -(-(cnt + cnt // 4 + 64) // 128) * 128
-        return cap if cap <= self.LIVE_ROWS_MAX_FRACTION * n else 0
+        n, cnt = int(torch.as_tensor(seq).numel()), self.live_row_count(seq, *also)
+        if int(torch.count_nonzero(torch.as_tensor(seq))) > self.LIVE_ROWS_MAX_FRACTION * n:
+            return 0
+        return min(self._capacity(cnt), -(-n // 128) * 128)
+
+    @staticmethod
+    def _capacity(cnt: int) -> int:
+        """Row capacity for ``cnt`` non-zero ids: 25 % headroom, rounded to 128-row tiles (eager and captured steps alike)."""
+        return -(-(cnt + cnt // 4 + 64) // 128) * 128
 
     @staticmethod
     def live_row_count(*ids) -> int:

@@ -200,9 +200,8 @@ def test_training_mode_dropout_against_injected_masks(label_rows, Ln, d):
     masks = {0: ops.dropout_mask(B * Ln * d, p, 4242, base, DEV).cpu()}
     labelled = np.flatnonzero(lab.numpy().reshape(-1))
     compact = len(labelled) <= model.LABEL_ROWS_MAX_FRACTION * B * Ln  # the final block then runs on the labelled rows only
-    cap = max(128, -(-len(labelled) // 128) * 128)
     per_seq = (lab != 0).sum(1)
-    lq = max(16, -(-int(per_seq.max()) // 16) * 16)
+    cap, lq = model._capacities(len(labelled), int(per_seq.max()))
     compact_q = compact and d // h == 32 and lq < Ln  # the final block's attention on per-sequence compacted queries
     assert compact_q == (label_rows and d == 64)
     for b in range(nb):
@@ -576,7 +575,7 @@ def test_sas_live_rows_training(V, Ln, d, nb, h, B, p):
         ref = osr.loss(sd, tseq, tpos, tneg, nb, h)
     else:
         live = np.flatnonzero(seq.reshape(-1))
-        cap = max(128, -(-len(live) // 128) * 128)
+        cap = model._capacity(max(len(live), int((pos != 0).sum()), int((neg != 0).sum())))
         base = step0 * 64
         masks = {0: ops.dropout_mask(B * Ln * d, p, 777, base, DEV).cpu()}
         for b in range(nb):
