@@ -191,3 +191,43 @@ def test_registries_mirror_the_reference():
     from types import SimpleNamespace
     with pytest.raises(KeyError):
         rbm_b200.dataloader_factory(SimpleNamespace(model_code="gru", max_len=5), dataset=[[], [], [], 0, 0])
+
+
+def test_row_capacity_rules_host_side():
+    """Host logic of the row-compacting training paths (models/sas.py live rows, models/bert.py labelled rows): one capacity rule
+    for eager and captured steps, dense path above the live / labelled share, and the per-batch fit check a captured step relies
+    on -- incl. the per-sequence query capacity of BERT4Rec's final block.  CPU tensors only."""
+    from types import SimpleNamespace
+    import rbm_b200
+    from rbm_b200.models.bert import BERTModel
+    from rbm_b200.models.sas import SASModel
+    # the rules: 25 % headroom, whole tiles, monotone
+    assert SASModel._capacity(0) == 128 and SASModel._capacity(1000) == 1408 and SASModel._capacity(28672) % 128 == 0
+    caps = [SASModel._capacity(c) for c in range(0, 5000, 37)]
+    assert all(a <= b for a, b in zip(caps, caps[1:])) and all(c >= n + n // 4 for c, n in zip(caps, range(0, 5000, 37)))
+    cap, lq = BERTModel._capacities(30000, 47)
+    assert cap % 128 == 0 and cap >= 37500 and lq % 16 == 0 and lq >= 58
+    # SASRec: capacity from the largest non-zero count of (seq, pos, neg); dense path above 60 % live rows
+    sas = rbm_b200.model_factory(SimpleNamespace(model_code="sas", num_items=50, max_len=20, device="cpu", sas_hidden_units=16, sas_num_blocks=1,
+                                                 sas_heads=1, sas_dropout=0.1))
+    seq = torch.zeros(64, 20, dtype=torch.int64)
+    seq[:, -3:] = 7
+    pos = seq.clone()
+    pos[0, 0] = 9  # one label on a padding row
+    assert sas.live_row_count(seq, pos, seq) == 64 * 3 + 1
+    assert sas.row_capacity_for(seq, pos, seq) == SASModel._capacity(64 * 3 + 1)
+    assert sas.row_capacity_for(torch.ones(64, 20, dtype=torch.int64)) == 0
+    # BERT4Rec: rows from the labels, per-sequence query capacity remembered for the fit check
+    bert = rbm_b200.model_factory(SimpleNamespace(model_code="bert", num_items=50, max_len=40, device="cpu", model_init_seed=0, bert_num_blocks=1,
+                                                  bert_num_heads=2, bert_hidden_units=64, bert_dropout=0.1, bert_hidden_dropout=0.1))
+    tok = torch.ones(32, 40, dtype=torch.int64)
+    lab = torch.zeros(32, 40, dtype=torch.int64)
+    lab[:, :5] = 3
+    assert bert._label_counts(lab) == (160, 5)
+    cap = bert.row_capacity_for(tok, lab)
+    assert cap == min(BERTModel._capacities(160, 5)[0], 1280) and bert._graph_lq == 16
+    assert bert.live_row_count(tok, lab) == 160
+    lab2 = lab.clone()
+    lab2[3, :20] = 3  # one sequence with more labels than the captured per-sequence query capacity
+    assert bert.live_row_count(tok, lab2) > (1 << 40)
+    assert bert.row_capacity_for(tok, torch.ones(32, 40, dtype=torch.int64)) == 0 and bert._graph_lq is None
