@@ -666,6 +666,10 @@ bool set_smem(K kern, size_t bytes, const char* name) {
 
 bool rbm_ce_tc_supported(int V1, int d, const void* h, const void* w) {
   if (!tc_enabled() || (d != 32 && d != 64) || V1 < CW) return false;  // backward: 4d + 256 TMEM columns
+  if (d == 64) {  // experiment switch: hand d = 64 to the split-fp16 kernels of ce_wide.cu
+    const char* e = getenv("RBM_CE_WIDE_D64");
+    if (e && atoi(e) != 0) return false;
+  }
   if (((uintptr_t)h | (uintptr_t)w) & 15) return false;
   return get_encode() != nullptr;
 }

@@ -966,14 +966,24 @@ int prepare(const float* h, const int32_t* rows, const int32_t* count, const flo
 
 }  // namespace
 
+// d = 64 is an experiment switch (RBM_CE_WIDE_D64=1): the 3xTF32 kernels of ce_tc.cu serve it by default
+static bool wide_d64() {
+  static const bool v = [] {
+    const char* e = getenv("RBM_CE_WIDE_D64");
+    return e && atoi(e) != 0;
+  }();
+  return v;
+}
+static bool wide_dim(int d) { return d == 128 || d == 256 || (d == 64 && wide_d64()); }
+
 bool rbm_ce_wide_supported(int V1, int d, const void* h, const void* w) {
-  if (!wide_enabled() || (d != 128 && d != 256) || V1 < 64) return false;
+  if (!wide_enabled() || !wide_dim(d) || V1 < 64) return false;
   if (((uintptr_t)h | (uintptr_t)w) & 15) return false;
   return get_encode() != nullptr;
 }
 
 size_t rbm_ce_wide_ws_floats(int64_t cap, int V1, int d) {
-  if (d != 128 && d != 256) return 0;
+  if (!wide_dim(d)) return 0;
   return carve(nullptr, cap, V1, d).total + 64;
 }
 
