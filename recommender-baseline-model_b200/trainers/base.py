@@ -233,9 +233,10 @@ class AbstractTrainer(metaclass=ABCMeta):
             return self._odd_shaped_step(batch)  # never copy_ a mismatching batch: a 1-row remainder would broadcast silently
         for dst, src in zip(self._graph_static, batch):
             dst.copy_(src, non_blocking=True)
-        # (the copies are in flight while the host counts: a batch with more live / labelled rows than the captured capacity takes
-        #  an eager step instead -- the static buffers then just hold an unused copy)
-        if self._graph_row_cap and self.model.live_row_count(*batch) > self._graph_row_cap:
+        # a batch with more live / labelled rows than the captured capacity takes an eager step instead (the static buffers then just
+        # hold an unused copy).  The rows are counted on the device copy: the graph cannot start before the copies have landed
+        # anyway, and a few small reductions + one read-back cost less than counting a [B, L] int64 batch on the host.
+        if self._graph_row_cap and self.model.live_row_count(*self._graph_static) > self._graph_row_cap:
             return self._odd_shaped_step(batch)
         self._graph.replay()
         if self._graph_b is not None:
