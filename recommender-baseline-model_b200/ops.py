@@ -740,11 +740,19 @@ class SasScoreFn(torch.autograd.Function):
             scatter_add_sorted_(dtable, pos, f2, dpl, 1.0, padding_idx=0)
             scatter_add_sorted_(dtable, neg, f2, dnl, 1.0, padding_idx=0)
         else:
-            # at most `cap` ids are non-zero (the caller's promise, see SASModel._live_rows): sort and reduce those entries only --
-            # same contributions (coefficient folded in with the same rounding) in the same order, so the same bits
-            for idx, coef in ((pos, dpl), (neg, dnl)):
-                lr = LiveRows(idx, ctx.cap, keep_ids=True)
-                scatter_add_sorted_(dtable, lr.ids, _rows_gather(f2, lr, coef), None, 1.0, padding_idx=0)
+            # at most `cap` ids are non-zero (the caller's promise, see SASModel._live_rows): sort and reduce those entries only
+            # (same contributions, the coefficient folded in with the same rounding) ...
+            # ... and both id lists in ONE sort / segment reduction: [positive entries ; negative entries], cap each
+            cap = ctx.cap
+            ids = torch.empty(2 * cap, device=f2.device, dtype=torch.int64)
+            src = torch.empty(2 * cap, d, device=f2.device, dtype=torch.float32)
+            for k, (idx, coef) in enumerate(((pos, dpl), (neg, dnl))):
+                lr = LiveRows(idx, cap, keep_ids=True)
+                ids[k * cap:(k + 1) * cap].copy_(lr.ids)
+                check(lib.rbm_rows_gather(ptr(f2), f2.stride(0), ptr(lr.rows), ptr(lr.count), cap, d, ptr(coef),
+                                          src.data_ptr() + 4 * k * cap * d, stream()), "rows_gather")
+                count_launches(2)
+            scatter_add_sorted_(dtable, ids, src, None, 1.0, padding_idx=0)
         return df.view(ctx.shape), dtable, None, None, None
 
 
