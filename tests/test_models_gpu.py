@@ -185,6 +185,8 @@ def test_training_mode_dropout_against_injected_masks(label_rows, Ln, d):
     positions are labelled) or on every row; at d_k = 32 (d = 64) the final block's attention also takes the labelled positions'
     queries only, compacted per sequence."""
     from oracle.common import DropoutPlan
+    if label_rows and (os.environ.get("RBM_BERT_LABEL_ROWS", "1") == "0" or (d == 64 and os.environ.get("RBM_BERT_LABEL_QUERIES", "1") == "0")):
+        pytest.skip("the labelled-row path is switched off by the environment")
     V, nb, h, B, p = 37, 2, 2, 4, 0.25
     model = rbm_b200.model_factory(bert_args(V, Ln, d, nb, h, p=p, seed=1)).to(DEV).train()
     model.dropout_seed = 4242
@@ -551,6 +553,8 @@ def test_sas_live_rows_training(V, Ln, d, nb, h, B, p):
     loss and EVERY gradient against the oracle -- dropout on: the oracle consumes the Philox masks the kernels used, the
     element-wise sites of this path being indexed by (live-row ordinal, column) -- and against the dense path at p = 0."""
     from oracle.common import DropoutPlan
+    if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0":
+        pytest.skip("the live-row path is switched off by the environment")
     rng = np.random.RandomState(V + B)
     seq = rng.randint(1, V + 1, size=(B, Ln)).astype(np.int64)
     for b in range(B):
@@ -606,6 +610,8 @@ def test_live_rows_cuda_graph(kind):
     """The captured step with a fixed row capacity (SASRec: non-padding rows; BERT4Rec: labelled rows of the final block): replays
     are bit-identical to eager steps run with the same capacity; a batch with more such rows than the capacity takes an eager
     step and training continues."""
+    if os.environ.get("RBM_SAS_LIVE_ROWS" if kind == "sas" else "RBM_BERT_LABEL_ROWS", "1") == "0":
+        pytest.skip("the row-compacting path is switched off by the environment")
     V, Ln, d, B = 80, 20, 32, 48
     rs = np.random.RandomState(5)
 
