@@ -155,14 +155,19 @@ class BERTModel(BaseModel):
                 n2 = ops.layernorm(xl, blk.output_sublayer.norm.a_2, blk.output_sublayer.norm.b_2, 1e-6, L.LN_BERT)
                 u = ops.linear(n2, ff.w_1.weight, ff.w_1.bias, act=L.ACT_GELU_TANH)
                 return ops.linear(u, ff.w_2.weight, ff.w_2.bias, residual=xl)
-            n1, x = ops.layernorm_residual(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
             lq = getattr(label_rows, "lq", None) if (label_rows is not None and b == len(bert.transformer_blocks) - 1) else None
-            if lq is not None and ops.attention_lq_supported(Ln, lq, d // h, L.MASK_KEYPAD):
+            lq_path = lq is not None and ops.attention_lq_supported(Ln, lq, d // h, L.MASK_KEYPAD)
+            if lq_path:  # the normalised rows feed two consumers here (k / v of every row, q of the labelled rows): their gradients
+                #          and the residual one meet inside the LayerNorm-backward launch
+                n1, n1q, x = ops.layernorm_fanout(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            else:
+                n1, x = ops.layernorm_residual(x, blk.input_sublayer.norm.a_2, blk.input_sublayer.norm.b_2, 1e-6, L.LN_BERT)
+            if lq_path:
                 # final block, labelled rows: queries of those rows only (<= lq per sequence, compacted per sequence) against the
                 # keys / values of every position; the attention site indexes its Philox stream by (sequence-head, query ordinal, key)
                 wq, wk, wv = att.linear_layers
                 kv = ops.linear(n1, torch.cat([wk.weight, wv.weight], 0), torch.cat([wk.bias, wv.bias], 0))
-                qc = ops.linear(ops.rows_gather(n1.view(-1, d), label_rows), wq.weight, wq.bias)
+                qc = ops.linear(ops.rows_gather(n1q.view(-1, d), label_rows), wq.weight, wq.bias)
                 ctx = ops.attention_lq(ops.rows_to_seq(qc, label_rows, Bsz, Ln, lq), kv, tok, Bsz, Ln, lq, h, L.MASK_KEYPAD, scale, p_a,
                                        seed, s)
                 ctx = ops.seq_to_rows(ctx, label_rows, Bsz, Ln, lq)
