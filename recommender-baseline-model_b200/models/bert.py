@@ -257,9 +257,10 @@ class BERTModel(BaseModel):
     @staticmethod
     def _capacities(cnt: int, mx: int):
         """(row capacity, per-sequence query capacity) for a batch with ``cnt`` labelled positions, at most ``mx`` in one sequence:
-        25 % headroom, rounded to the kernels' tiles.  Eager steps and captured steps use the same rule, so a step replayed from a
+        headroom 12.5 % + 8 sqrt(cnt) rows (a batch's count is a sum over its sequences: small batches vary more) resp. 25 % + 8,
+        rounded to the kernels' tiles.  Eager steps and captured steps use the same rule, so a step replayed from a
         graph captured on a batch with the same counts is bit-identical to the eager step."""
-        return -(-(cnt + cnt // 4 + 64) // 128) * 128, -(-(mx + mx // 4 + 8) // 16) * 16
+        return -(-(cnt + cnt // 8 + 8 * math.isqrt(cnt) + 64) // 128) * 128, -(-(mx + mx // 4 + 8) // 16) * 16
 
     @staticmethod
     def _label_counts(labels):
@@ -270,7 +271,7 @@ class BERTModel(BaseModel):
         return int(cnt), int(mx)
 
     def row_capacity_for(self, tokens, labels) -> int:
-        """Capacity (rows) a captured step should be built with for batches like this one: 25 % headroom over its labelled rows
+        """Capacity (rows) a captured step should be built with for batches like this one: headroom over its labelled rows (``_capacities``)
         (0 = run the final block on every row), and the per-sequence query capacity ``_graph_lq`` of the final block's attention.
         ``live_row_count`` tells the trainer whether a later batch still fits."""
         self._graph_lq = None

@@ -129,7 +129,7 @@ class SASModel(BaseModel):
         return live
 
     def row_capacity_for(self, seq, *also) -> int:
-        """Capacity (rows) a captured step should be built with for batches like (seq, pos, neg): 25 % headroom over the non-zero
+        """Capacity (rows) a captured step should be built with for batches like (seq, pos, neg): headroom (``_capacity``) over the non-zero
         ids, 0 when the dense path is the better choice.  ``live_row_count`` tells the trainer whether a later batch still fits."""
         if os.environ.get("RBM_SAS_LIVE_ROWS", "1") == "0" or getattr(self, "_shard", None) is not None:
             return 0
@@ -140,8 +140,9 @@ class SASModel(BaseModel):
 
     @staticmethod
     def _capacity(cnt: int) -> int:
-        """Row capacity for ``cnt`` non-zero ids: 25 % headroom, rounded to 128-row tiles (eager and captured steps alike)."""
-        return -(-(cnt + cnt // 4 + 64) // 128) * 128
+        """Row capacity for ``cnt`` non-zero ids: 12.5 % + 8 sqrt(cnt) rows of headroom (a batch's count is a sum over its sequences:
+        small batches vary more), rounded to 128-row tiles (eager and captured steps alike)."""
+        return -(-(cnt + cnt // 8 + 8 * math.isqrt(cnt) + 64) // 128) * 128
 
     @staticmethod
     def live_row_count(*ids) -> int:
