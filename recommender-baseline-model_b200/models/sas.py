@@ -67,10 +67,10 @@ class SASModel(BaseModel):
         seed = self.dropout_seed
         base = self._next_site_base() if train else 0
         sh = getattr(self, "_shard", None)
-        if live is None and train and sh is None and not last_only:
-            live = self._live_rows(seq)
+        if live is None and sh is None and (train or (last_only and not torch.is_grad_enabled())):
+            live = self._live_rows(seq)  # training, and evaluation of the last position: token-wise layers on the non-padding rows only
         if live is not None and live is not False:  # (False: the caller already decided for the dense path)
-            return self._blocks_live_rows(seq, live, Bsz, Ln, p, seed, base, math.sqrt(1.0 / (d // h)))
+            return self._blocks_live_rows(seq, live, Bsz, Ln, p, seed, base, math.sqrt(1.0 / (d // h)), last_only)
         if sh is None:
             x = ops.EmbedFn.apply(seq, sas.item_emb.weight, sas.pos_emb.weight, float(d ** 0.5), 1, p, seed, base)
         else:  # row-sharded item table (rbm_b200.dist.shard_sas_model): common seed + global element indices for this site,
@@ -150,12 +150,13 @@ class SASModel(BaseModel):
         ts = [torch.as_tensor(t) for t in ids]
         return int(torch.stack([torch.count_nonzero(t) for t in ts]).max().item())
 
-    def _blocks_live_rows(self, seq, live, Bsz, Ln, p, seed, base, scale):
+    def _blocks_live_rows(self, seq, live, Bsz, Ln, p, seed, base, scale, last_only=False):
         """The block loop with LayerNorm / Linear / feed-forward on the live rows only (csrc/rows.cu explains why that is exact).
         Attention runs on the same compact layout (csrc/attention_live.cu: every padding key of a sequence is the projection bias,
         which is what W.0 + b gives the reference, so they enter as one key with a multiplicity); sequences longer than 64 keep the
         dense kernels on the [B, L] layout (queries / keys / values scattered back).  The element-wise dropout sites of this path
-        index their Philox stream by (live-row ordinal, column); the attention site by (sequence-head, i, j) as always."""
+        index their Philox stream by (live-row ordinal, column); the attention site by (sequence-head, i, j) as always.
+        ``last_only`` (evaluation): [B, d], the final block for the last position alone, its keys / values from the compact rows."""
         sas = self.sas
         d, h = sas.hidden, sas.heads
         if ops.embed_live_supported(Ln, d):
@@ -166,6 +167,16 @@ class SASModel(BaseModel):
             s = base + 1 + 3 * b
             ln1, mha, ln2, ffn = sas.attention_layernorms[b], sas.attention_layers[b], sas.forward_layernorms[b], sas.forward_layers[b]
             w_in, b_in = mha.in_proj_weight, mha.in_proj_bias
+            if last_only and b == len(sas.attention_layers) - 1:
+                kv = ops.rows_scatter(ops.linear(xc, w_in[d:], b_in[d:]), b_in[d:], live)  # [B*L, 2d]; padding rows: the bias
+                x_last = ops.rows_scatter(xc, None, live).view(Bsz, Ln, d)[:, -1, :]        # (a padding row is zero, as in the dense path)
+                Ql = ops.layernorm(x_last, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
+                ctx = ops.attention_last_query(ops.linear(Ql, w_in[:d], b_in[:d]), kv, None, Bsz, Ln, h, 0, d, L.MASK_CAUSAL, scale)
+                xl = ops.linear(ctx, mha.out_proj.weight, mha.out_proj.bias, residual=Ql)
+                xl = ops.layernorm(xl, ln2.weight, ln2.bias, 1e-8, L.LN_TORCH)
+                u = ops.linear(xl, ffn.conv1.weight.squeeze(-1), ffn.conv1.bias, act=L.ACT_RELU)
+                xl = ops.linear(u, ffn.conv2.weight.squeeze(-1), ffn.conv2.bias, residual=xl, row_tok=seq[:, -1])
+                return ops.layernorm(xl, sas.last_layernorm.weight, sas.last_layernorm.bias, 1e-8, L.LN_TORCH)
             Q, Qres, xkv = ops.layernorm_fanout(xc, ln1.weight, ln1.bias, 1e-8, L.LN_TORCH)
             q = ops.linear(Q, w_in[:d], b_in[:d])
             kv = ops.linear(xkv, w_in[d:], b_in[d:])

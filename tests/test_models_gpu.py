@@ -504,6 +504,11 @@ def test_eval_last_position_only(kind, V, Ln, d, nb, h, B):
         last = model.last_hidden(x)
         assert last.shape == full.shape
         relclose(last.cpu().numpy(), full.cpu().numpy(), 1e-5, msg="last hidden")
+        if kind == "sas":  # SASRec: the blocks before the last one on the non-padding rows only (forced) / on every row (forced)
+            for frac in (1.0, -1.0):
+                model.LIVE_ROWS_MAX_FRACTION = frac
+                relclose(model.last_hidden(x).cpu().numpy(), full.cpu().numpy(), 1e-5, msg="last hidden, live-row share limit %g" % frac)
+            model.LIVE_ROWS_MAX_FRACTION = 1.0
         cand = torch.from_numpy(rng.randint(1, V + 1, size=(B, 11)).astype(np.int64)).to(DEV)
         sc = model.candidate_scores(x, cand) if kind == "bert" else model.predict(x, cand)
         w = model.out.weight if kind == "bert" else model.sas.item_emb.weight
