@@ -15,7 +15,7 @@
  *    no allocation, no global state besides the thread-local last-error string).
  *  - return 0 on success, <0 for an invalid argument / unsupported shape (no CPU fallback),
  *    >0 = cudaError_t of the launch.  rbm_last_error() describes the last failure on this thread.
- *  - dropout: keep-mask = Philox4x32-10(key=seed, counter=(element/4, site)) >= p*2^32, scaled by
+ *  - dropout: keep-mask = Philox4x32-7(key=seed, counter=(element/4, site)) >= p*2^32, scaled by
  *    1/(1-p); `site` identifies the dropout call site within a step (DESIGN.md "dropout").  The
  *    backward entry points regenerate the mask from (seed, site); nothing is stored.
  */

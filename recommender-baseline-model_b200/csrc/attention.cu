@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_fwd_kernel(AttnArgs a) {
 #pragma unroll
         for (int qd = 0; qd < 4; ++qd) {
           if (jb + qd * 16 < LP8) {
-            uint4 rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
+            uint4 rnd = rbm_philox_drop(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
             for (int bb = 0; bb < 2; ++bb)
 #pragma unroll
@@ -259,7 +259,7 @@ __global__ void __launch_bounds__(32 * MAX_WARPS) attn_bwd_dq_kernel(AttnArgs a)
       for (int qd = 0; qd < 4; ++qd) {
         uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
         if (a.thr16 && jb + qd * 16 < LP8)
-          rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
+          rnd = rbm_philox_drop(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, i0 >> 4, g, t, (jb >> 4) + qd));
 #pragma unroll
         for (int bb = 0; bb < 2; ++bb) {
           const int nt = qd * 2 + bb;
@@ -370,7 +370,7 @@ __global__ void __launch_bounds__(32 * MAXW, MAXW <= 4 ? 3 : 1) attn_bwd_dkv_ker
         for (int e = 0; e < 2; ++e) {
           uint4 rnd = make_uint4(~0u, ~0u, ~0u, ~0u);
           if (a.thr16 && ib + qd * 16 < LP8)
-            rnd = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, (ib >> 4) + qd, 2 * t + e, g >> 1, j0 >> 4));
+            rnd = rbm_philox_drop(a.seed, site_e, rbm_attn_call((uint64_t)blockIdx.x, (ib >> 4) + qd, 2 * t + e, g >> 1, j0 >> 4));
 #pragma unroll
           for (int bb = 0; bb < 2; ++bb) {
             const int nt = qd * 2 + bb;

@@ -46,7 +46,7 @@ __device__ __forceinline__ unsigned long long keep_mask8(const LiveArgs& a, uint
 #pragma unroll
   for (int c = 0; c < 2; ++c) {
     const int call = sub + 8 * c, np = call >> 2, t = call & 3;
-    const uint4 r = rbm_philox(a.seed, site_e, rbm_attn_call(bh, i >> 4, i & 7, t, np));
+    const uint4 r = rbm_philox_drop(a.seed, site_e, rbm_attn_call(bh, i >> 4, i & 7, t, np));
 #pragma unroll
     for (int e = 0; e < 2; ++e)
 #pragma unroll

@@ -182,7 +182,7 @@ __device__ __forceinline__ uint32_t keep_bits_row(uint64_t seed, uint64_t site, 
                                   // and of my partner's call t = 2 (1 - rh) + tt (got)
 #pragma unroll
   for (int tt = 0; tt < 2; ++tt) {
-    const uint4 r = rbm_philox(seed, site, rbm_attn_call(bh, tile, g, 2 * rh + tt, np));
+    const uint4 r = rbm_philox_drop(seed, site, rbm_attn_call(bh, tile, g, 2 * rh + tt, np));
     own[tt][0] = rh ? r.z : r.x;
     own[tt][1] = rh ? r.w : r.y;
     got[tt][0] = __shfl_xor_sync(0xffffffffu, rh ? r.x : r.z, 8);  // my partner's words of my call <-> mine of theirs
@@ -206,7 +206,7 @@ __device__ __forceinline__ uint32_t keep_bits_col(uint64_t seed, uint64_t site, 
   uint32_t bits = 0;
 #pragma unroll
   for (int g = 0; g < 8; ++g) {
-    const uint4 r = rbm_philox(seed, site, rbm_attn_call(bh, T, g, t, np));
+    const uint4 r = rbm_philox_drop(seed, site, rbm_attn_call(bh, T, g, t, np));
     const uint32_t w0 = e ? r.y : r.x, w1 = e ? r.w : r.z;  // rh = 0 / rh = 1
     if (((w0 >> (16 * n1)) & 0xffffu) >= thr16) bits |= 1u << g;
     if (((w1 >> (16 * n1)) & 0xffffu) >= thr16) bits |= 1u << (g + 8);

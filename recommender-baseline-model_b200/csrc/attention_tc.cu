@@ -44,8 +44,8 @@ struct KeepWords {
 };
 __device__ __forceinline__ KeepWords attn_keep_words(uint64_t seed, uint64_t site, uint64_t bh, int i, int npair) {
   const int tile = i >> 4, g = i & 7, rh = (i >> 3) & 1;
-  const uint4 ca = rbm_philox(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 0, npair));
-  const uint4 cb = rbm_philox(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 1, npair));
+  const uint4 ca = rbm_philox_drop(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 0, npair));
+  const uint4 cb = rbm_philox_drop(seed, site, rbm_attn_call(bh, tile, g, rh * 2 + 1, npair));
   // mine: words rh*2 + e; the partner row (rh ^ 1) wants the other pair
   const uint32_t ma0 = rh ? ca.z : ca.x, ma1 = rh ? ca.w : ca.y, mb0 = rh ? cb.z : cb.x, mb1 = rh ? cb.w : cb.y;
   const uint32_t sa0 = rh ? ca.x : ca.z, sa1 = rh ? ca.y : ca.w, sb0 = rh ? cb.x : cb.z, sb1 = rh ? cb.y : cb.w;
@@ -1152,8 +1152,8 @@ __global__ void __launch_bounds__(B_THREADS, 1) attn_bwd_dkv_tc_kernel(const __g
             const int i0 = c * SQ + c0;  // 16 consecutive queries, one Philox "tile"
             uint32_t w0[8], w1[8];       // per query-in-octet g: the two words (rh = 0, 1) that hold this key's fields
             if (DROP) {
-              uint4 ca = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
-              uint4 cb = rbm_philox(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
+              uint4 ca = rbm_philox_drop(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 0, t_j, np_j));
+              uint4 cb = rbm_philox_drop(a.seed, site_e, rbm_attn_call((uint64_t)bh, i0 >> 4, 2 * wq + 1, t_j, np_j));
 #pragma unroll
               for (int gq = 0; gq < 8; ++gq) {
                 // call of query-octet position gq is owned by the lane whose (bit0, bit3) = ((gq>>1)&1, (gq>>2)&1); the

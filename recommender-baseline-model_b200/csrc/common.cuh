@@ -31,7 +31,7 @@ static inline bool rbm_aligned16(const void* p) { return (reinterpret_cast<uintp
 static inline int64_t rbm_cdiv(int64_t a, int64_t b) { return (a + b - 1) / b; }
 
 // ---------------------------------------------------------------------------------------------
-// Philox4x32-10 counter-based RNG.  One call yields 4 x u32 for 4 consecutive logical elements.
+// Philox4x32 counter-based RNG.  One call yields 4 x u32 for 4 consecutive logical elements.
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ __forceinline__ uint32_t rbm_mulhi(uint32_t a, uint32_t b) {
 #ifdef __CUDA_ARCH__
@@ -41,11 +41,12 @@ __host__ __device__ __forceinline__ uint32_t rbm_mulhi(uint32_t a, uint32_t b) {
 #endif
 }
 
-__host__ __device__ __forceinline__ uint4 rbm_philox(uint64_t seed, uint64_t site, uint64_t idx4) {
+template <int ROUNDS>
+__host__ __device__ __forceinline__ uint4 rbm_philox_rounds(uint64_t seed, uint64_t site, uint64_t idx4) {
   uint32_t c0 = (uint32_t)idx4, c1 = (uint32_t)(idx4 >> 32), c2 = (uint32_t)site, c3 = (uint32_t)(site >> 32);
   uint32_t k0 = (uint32_t)seed, k1 = (uint32_t)(seed >> 32);
 #pragma unroll
-  for (int r = 0; r < 10; ++r) {
+  for (int r = 0; r < ROUNDS; ++r) {
     uint32_t hi0 = rbm_mulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
     uint32_t hi1 = rbm_mulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
     c0 = hi1 ^ c1 ^ k0;
@@ -56,6 +57,16 @@ __host__ __device__ __forceinline__ uint4 rbm_philox(uint64_t seed, uint64_t sit
     k1 += 0xBB67AE85u;
   }
   return make_uint4(c0, c1, c2, c3);
+}
+// Philox4x32-10: batch construction and negative sampling (bit-exact against oracle/batches.py and its goldens)
+__host__ __device__ __forceinline__ uint4 rbm_philox(uint64_t seed, uint64_t site, uint64_t idx4) {
+  return rbm_philox_rounds<10>(seed, site, idx4);
+}
+// Philox4x32-7 for the dropout sites (element-wise and attention): seven rounds are the fewest that pass BigCrush (Salmon et al.,
+// SC'11, table 2; ten is the library default for margin).  Dropout needs independent-looking keep bits, not cryptographic
+// margin, and the rounds are a visible share of the softmax / epilogue instruction streams (~100 of them per call).
+__host__ __device__ __forceinline__ uint4 rbm_philox_drop(uint64_t seed, uint64_t site, uint64_t idx4) {
+  return rbm_philox_rounds<7>(seed, site, idx4);
 }
 
 // dropout threshold: an element is KEPT iff its u32 >= thr, i.e. dropped with probability thr / 2^32.
@@ -68,7 +79,7 @@ __host__ __device__ __forceinline__ uint32_t rbm_drop_threshold(float p) {
 
 // keep-scale of the 4 elements [4*idx4, 4*idx4+4) of an elementwise site: 0 or 1/(1-p)
 __device__ __forceinline__ float4 rbm_drop4(uint64_t seed, uint64_t site, uint64_t idx4, uint32_t thr, float inv_keep) {
-  uint4 r = rbm_philox(seed, site, idx4);
+  uint4 r = rbm_philox_drop(seed, site, idx4);
   return make_float4(r.x >= thr ? inv_keep : 0.f, r.y >= thr ? inv_keep : 0.f, r.z >= thr ? inv_keep : 0.f,
                      r.w >= thr ? inv_keep : 0.f);
 }
@@ -110,7 +121,7 @@ __host__ __device__ __forceinline__ uint32_t rbm_drop_threshold16(float p) {
 }
 // reference implementation of the per-element rule (debug mask kernel, tests)
 __host__ __device__ __forceinline__ bool rbm_attn_keep(uint64_t seed, uint64_t site, uint64_t bh, int i, int j, uint32_t thr16) {
-  uint4 r = rbm_philox(seed, site, rbm_attn_call(bh, i >> 4, i & 7, (j & 7) >> 1, j >> 4));
+  uint4 r = rbm_philox_drop(seed, site, rbm_attn_call(bh, i >> 4, i & 7, (j & 7) >> 1, j >> 4));
   return rbm_attn_field(r, ((i >> 3) & 1) * 4 + (j & 1) * 2 + ((j >> 3) & 1)) >= thr16;
 }
 

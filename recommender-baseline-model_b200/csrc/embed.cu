@@ -131,7 +131,7 @@ __global__ void __launch_bounds__(256) embed_dpos_final_kernel(const float* __re
 __global__ void dropout_mask_kernel(uint8_t* out, int64_t n, uint32_t thr, uint64_t seed, uint64_t site) {
   int64_t i4 = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i4 * 4 >= n) return;
-  uint4 r = rbm_philox(seed, site, (uint64_t)i4);
+  uint4 r = rbm_philox_drop(seed, site, (uint64_t)i4);
   uint32_t v[4] = {r.x, r.y, r.z, r.w};
   for (int c = 0; c < 4; ++c)
     if (i4 * 4 + c < n) out[i4 * 4 + c] = v[c] >= thr ? 1 : 0;
