@@ -365,12 +365,12 @@ __global__ void __launch_bounds__(128 + 32 * EPI_WARPS, 1) tc_linear_persistent_
             }
             const uint64_t e4 = (uint64_t)(row * p.N + col) >> 2;
             if constexpr (DROPA) {
-              const float4 m = rbm_drop4(p.seed, rbm_site(p.siteA), e4, p.thrA, p.invA);
+              const float4 m = rbm_drop4(p.seed, siteA_e, e4, p.thrA, p.invA);
               x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
             }
             x.x += res[i].x; x.y += res[i].y; x.z += res[i].z; x.w += res[i].w;
             if constexpr (DROPB) {
-              const float4 m = rbm_drop4(p.seed, rbm_site(p.siteB), e4, p.thrB, p.invB);
+              const float4 m = rbm_drop4(p.seed, siteB_e, e4, p.thrB, p.invB);
               x.x *= m.x; x.y *= m.y; x.z *= m.z; x.w *= m.w;
             }
             if ((zero_rows >> i) & 1u) x = make_float4(0.f, 0.f, 0.f, 0.f);
